@@ -1,0 +1,327 @@
+// evx_device.cuh -- integer arithmetic contract and warp-level block metrics shared by
+// the sm_100a kernels.  Every routine cites the reference line whose arithmetic it must
+// reproduce bit for bit.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define EVX_MB 16
+#define EVX_SAD_CAP 8192u          // EVX_MOTION_SAD_THRESHOLD, motion.cpp:19
+#define EVX_SEARCH_RADIUS 16       // motion.cpp:24
+#define EVX_BIG 0x7FFFFFFF
+
+enum { EVX_T_INTRA = 1, EVX_T_MOTION = 2, EVX_T_COPY = 4 };   // types.h:68-71
+
+struct EvxGeom
+{
+    int w, h;        // 16-aligned luma plane size (evx1enc.cpp:79-80)
+    int vw, vh;      // visible size
+    int mbw, mbh;
+};
+
+struct EvxPlanes { int16_t *y, *u, *v; };
+
+// ------------------------------------------------------------------ scalar helpers
+
+// math.h:228-236
+__device__ __forceinline__ int evx_rdiv(int n, int d)
+{
+    return ((n ^ d) < 0) ? (n - d / 2) / d : (n + d / 2) / d;
+}
+
+// rounded_div by a positive power of two 2^s (d/2 = 2^(s-1)); truncating division of the biased numerator
+__device__ __forceinline__ int evx_rdiv_pow2(int n, int s)
+{
+    int half = 1 << (s - 1);
+    int t = n < 0 ? n - half : n + half;
+    // C division truncates toward zero
+    return t < 0 ? -((-t) >> s) : (t >> s);
+}
+
+__device__ __forceinline__ int evx_tdiv_pow2(int n, int s) { return n < 0 ? -((-n) >> s) : (n >> s); }   // C '/' by 2^s
+
+__device__ __forceinline__ int evx_ilog2(uint32_t v) { return v ? 31 - __clz(v) : 0; }                  // math.h:69-138
+__device__ __forceinline__ int evx_clip(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+__device__ __forceinline__ int evx_abs16(int v) { return v == -32768 ? 32767 : (v < 0 ? -v : v); }          // math.h:197-203
+__device__ __forceinline__ int evx_sign(int v) { return (v > 0) - (v < 0); }
+
+// macroblock.h:203-241: (a+b+-1)/2 and (3a+b+-2)/4 with C truncation == add, bias away from zero, arithmetic shift
+__device__ __forceinline__ int evx_lerp_half(int a, int b) { int t = a + b; return (t + 1 + (t >> 31)) >> 1; }
+__device__ __forceinline__ int evx_lerp_quarter(int a, int b) { int t = 3 * a + b; return (t + 2 + (t >> 31)) >> 2; }
+
+__device__ __forceinline__ int evx_lo16(uint32_t v) { return (int) (short) (v & 0xFFFFu); }
+__device__ __forceinline__ int evx_hi16(uint32_t v) { return ((int) v) >> 16; }
+__device__ __forceinline__ uint32_t evx_pack16(int lo, int hi) { return ((uint32_t) lo & 0xFFFFu) | ((uint32_t) hi << 16); }
+
+// motion.cpp:61-84
+__device__ __forceinline__ int evx_frac_index(int i, int j)
+{
+    i++; j++;
+    if (j == 0) return i;
+    if (j == 1) return i == 0 ? 3 : 4;
+    return i + 5;
+}
+
+// motion.cpp:86-109
+__device__ __forceinline__ void evx_frac_direction(int idx, int &dx, int &dy)
+{
+    if (idx <= 2) { dy = -1; dx = idx - 1; }
+    else if (idx == 3) { dx = -1; dy = 0; }
+    else if (idx == 4) { dx = 1; dy = 0; }
+    else { dy = 1; dx = idx - 6; }
+}
+
+// ------------------------------------------------------------------ block descriptor (16 bytes, common.h:78-95)
+
+struct __align__(16) EvxDesc
+{
+    uint32_t w0, w1, w2, w3;
+    __device__ __forceinline__ int type() const { return (int) w0; }
+    __device__ __forceinline__ int target() const { return (int) (w1 & 0xFF); }
+    __device__ __forceinline__ int mx() const { return evx_hi16(w1); }
+    __device__ __forceinline__ int my() const { return evx_lo16(w2); }
+    __device__ __forceinline__ int sp_pred() const { return (int) ((w2 >> 16) & 0xFF); }
+    __device__ __forceinline__ int sp_amount() const { return (int) ((w2 >> 24) & 0xFF); }
+    __device__ __forceinline__ int sp_index() const { return (int) (w3 & 0xFF); }
+    __device__ __forceinline__ int q_index() const { return (int) ((w3 >> 8) & 0xFF); }
+    __device__ __forceinline__ void set_q(int q, int var) { w3 = (w3 & 0xFFu) | (((uint32_t) q & 0xFFu) << 8) | (((uint32_t) var & 0xFFFFu) << 16); }
+};
+
+__device__ __forceinline__ EvxDesc evx_make_desc(int type, int target, int mx, int my, int sp_pred, int sp_amount, int sp_index)
+{
+    EvxDesc d;
+    d.w0 = (uint32_t) type;
+    d.w1 = ((uint32_t) target & 0xFFu) | ((uint32_t) mx << 16);
+    d.w2 = ((uint32_t) my & 0xFFFFu) | (((uint32_t) sp_pred & 0xFFu) << 16) | (((uint32_t) sp_amount & 0xFFu) << 24);
+    d.w3 = (uint32_t) sp_index & 0xFFu;
+    return d;
+}
+
+// ------------------------------------------------------------------ search state (motion.cpp:47-59)
+
+struct EvxSel
+{
+    int bx, by;              // best full-pel position, frame coordinates
+    int sad, mad, ssd;
+    int sp_index, sp_amount, sp_enabled;
+};
+
+// motion.cpp:111-149.  Second rule as written: sad<best || (sad==best && ssd<best_ssd && sad<8192) || mad<thr
+__device__ __forceinline__ void evx_accept_fullpel(EvxSel &s, int x, int y, int sad, int mad, int px, int py, int thr)
+{
+    int ssd = (x - px) * (x - px) + (y - py) * (y - py);
+    bool take;
+    if (s.mad < thr) take = mad < s.mad || (mad == s.mad && ssd < s.ssd);
+    else take = sad < s.sad || (sad == s.sad && ssd < s.ssd && (uint32_t) sad < EVX_SAD_CAP) || mad < thr;
+    if (take) { s.bx = x; s.by = y; s.sad = sad; s.ssd = ssd; s.mad = mad; }
+}
+
+// motion.cpp:151-223 (one of the two tests of a direction)
+__device__ __forceinline__ void evx_accept_subpel(EvxSel &s, int i, int j, int quarter, int sad, int mad, int thr)
+{
+    bool take;
+    if (s.mad < thr) take = mad < s.mad;
+    else take = (sad < s.sad && (uint32_t) sad < EVX_SAD_CAP) || mad < thr;
+    if (take) { s.sp_enabled = 1; s.sp_amount = quarter; s.sp_index = evx_frac_index(i, j); s.sad = sad; s.mad = mad; }
+}
+
+__device__ __forceinline__ EvxDesc evx_desc_from_sel(const EvxSel &s, int intra, int target, int px, int py, int thr)
+{
+    int type = intra ? EVX_T_INTRA : 0;
+    if (s.bx != px || s.by != py || s.sp_enabled) type |= EVX_T_MOTION;
+    if (s.mad < thr) type |= EVX_T_COPY;
+    return evx_make_desc(type, target, s.bx - px, s.by - py, s.sp_enabled, s.sp_amount, s.sp_index);
+}
+
+// ------------------------------------------------------------------ warp-level block metrics
+//
+// A search window lives in shared memory as packed int16 pairs (one 32-bit word = two
+// horizontally adjacent samples).  A warp evaluates one 16x16+8x8+8x8 candidate:
+//   luma   lane -> (rr = lane>>3, cc = lane&7): words (row rr+4k, pixel pair cc), k=0..3
+//   chroma lane -> (row lane>>2, pixel pair lane&3), one word of U and one of V
+// With a row pitch of 8 (mod 32) words for luma and 4*odd (mod 32) for chroma every one
+// of these loads is bank-conflict free.
+
+struct EvxWin
+{
+    const uint32_t *y, *u, *v;   // shared memory
+    int pw_y, pw_c;              // row pitch in 32-bit words
+    int ox, oy;                  // frame coordinates of the window's first luma sample (ox even)
+    int cox, coy;                // same for chroma (cox even)
+};
+
+struct EvxLaneBlock { uint32_t w[6]; };   // 4 luma words, U word, V word of this lane
+
+__device__ __forceinline__ void evx_load_block(const EvxWin &win, int x, int y, int lane, EvxLaneBlock &b)
+{
+    int wx = x - win.ox, wy = y - win.oy;
+    const uint32_t *p = win.y + (wy + (lane >> 3)) * win.pw_y + (wx >> 1) + (lane & 7);
+    if (wx & 1)
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b.w[k] = __byte_perm(p[4 * k * win.pw_y], p[4 * k * win.pw_y + 1], 0x5432);
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b.w[k] = p[4 * k * win.pw_y];
+    }
+    int cx = (x >> 1) - win.cox, cy = (y >> 1) - win.coy;
+    int off = (cy + (lane >> 2)) * win.pw_c + (cx >> 1) + (lane & 3);
+    if (cx & 1)
+    {
+        b.w[4] = __byte_perm(win.u[off], win.u[off + 1], 0x5432);
+        b.w[5] = __byte_perm(win.v[off], win.v[off + 1], 0x5432);
+    }
+    else
+    {
+        b.w[4] = win.u[off];
+        b.w[5] = win.v[off];
+    }
+}
+
+// The source macroblock of a warp, in the lane layout above: packed negation (for
+// VIADDMNMX) and the lane's luma sum.
+struct EvxLaneSrc
+{
+    uint32_t neg[6];     // -src, packed
+    uint32_t pos[6];     // src, packed
+    int lsum;            // sum of this lane's 8 luma samples
+};
+
+__device__ __forceinline__ uint32_t evx_neg16x2(uint32_t v) { return __vadd2(~v, 0x00010001u); }
+
+__device__ __forceinline__ void evx_make_src(const EvxLaneBlock &b, EvxLaneSrc &s)
+{
+    s.lsum = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { s.pos[k] = b.w[k]; s.neg[k] = evx_neg16x2(b.w[k]); }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s.lsum += evx_lo16(b.w[k]) + evx_hi16(b.w[k]);
+}
+
+// SAD over luma (analysis.h:42-55) and MAD over luma+chroma (analysis.h:103-125) of one
+// candidate against the warp's source block.  Per packed word: three VIADDMNMX.S16x2
+// (running max and min of ref-src, and relu(ref-src)) and two IDP.2A:
+//   sum|d| = 2*sum relu(d) - sum d,   max|d| = max(max d, -min d).
+__device__ __forceinline__ void evx_block_cost(const EvxLaneBlock &ref, const EvxLaneSrc &src, int &sad, int &mad)
+{
+    uint32_t amx = 0x80008000u, amn = 0x7FFF7FFFu;
+    int acc = src.lsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        amx = __viaddmax_s16x2(ref.w[k], src.neg[k], amx);
+        amn = __viaddmin_s16x2(ref.w[k], src.neg[k], amn);
+        uint32_t r = __viaddmax_s16x2_relu(ref.w[k], src.neg[k], 0u);
+        acc = __dp2a_lo((int) r, 0x0202, acc);
+        acc = __dp2a_lo((int) ref.w[k], 0xFFFF, acc);
+    }
+#pragma unroll
+    for (int k = 4; k < 6; ++k)
+    {
+        amx = __viaddmax_s16x2(ref.w[k], src.neg[k], amx);
+        amn = __viaddmin_s16x2(ref.w[k], src.neg[k], amn);
+    }
+    int m = max(max(evx_lo16(amx), evx_hi16(amx)), -min(evx_lo16(amn), evx_hi16(amn)));
+    sad = __reduce_add_sync(0xFFFFFFFFu, acc);
+    mad = __reduce_max_sync(0xFFFFFFFFu, m);
+}
+
+// One sub-pel direction: both the half- and the quarter-pel blend of `best` with its
+// neighbour `nb` (macroblock.h:203-241), SAD/MAD of each against the source.
+__device__ __forceinline__ void evx_subpel_cost(const EvxLaneBlock &best, const EvxLaneBlock &nb, const EvxLaneSrc &src,
+                                                int &sad_h, int &mad_h, int &sad_q, int &mad_q)
+{
+    int sh = 0, mh = 0, sq = 0, mq = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+    {
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+        {
+            int a = half ? evx_hi16(best.w[k]) : evx_lo16(best.w[k]);
+            int b = half ? evx_hi16(nb.w[k]) : evx_lo16(nb.w[k]);
+            int s = half ? evx_hi16(src.pos[k]) : evx_lo16(src.pos[k]);
+            // the blended sample is stored as int16 before it is compared (macroblock.h:210, 230)
+            int dh = abs(s - (int) (short) evx_lerp_half(a, b));
+            int dq = abs(s - (int) (short) evx_lerp_quarter(a, b));
+            if (k < 4) { sh += dh; sq += dq; }
+            mh = max(mh, dh);
+            mq = max(mq, dq);
+        }
+    }
+    sad_h = __reduce_add_sync(0xFFFFFFFFu, sh);
+    mad_h = __reduce_max_sync(0xFFFFFFFFu, mh);
+    sad_q = __reduce_add_sync(0xFFFFFFFFu, sq);
+    mad_q = __reduce_max_sync(0xFFFFFFFFu, mq);
+}
+
+// ------------------------------------------------------------------ transform / quantiser tables
+
+// xftables.h:57-67: LUT[j*8+i] = round(128 cos((2i+1) j pi / 16)), from the 8 magnitudes
+__device__ __forceinline__ int evx_dct_lut(int j, int i)
+{
+    const int c16[9] = { 128, 126, 118, 106, 91, 71, 49, 25, 0 };
+    int k = ((2 * i + 1) * j) & 31;
+    if (k <= 8) return c16[k];
+    if (k <= 16) return -c16[16 - k];
+    if (k <= 24) return -c16[k - 16];
+    return c16[32 - k];
+}
+
+// quantize.cpp:13-35
+__constant__ int16_t EVX_QM_INTRA[64] = {
+     8, 17, 18, 19, 21, 23, 25, 27,   17, 18, 19, 21, 23, 25, 27, 28,
+    20, 21, 22, 23, 24, 26, 28, 30,   21, 22, 23, 24, 26, 28, 30, 32,
+    22, 23, 24, 26, 28, 30, 32, 35,   23, 24, 26, 28, 30, 32, 35, 38,
+    25, 26, 28, 30, 32, 35, 38, 41,   27, 28, 30, 32, 35, 38, 41, 45 };
+__constant__ int16_t EVX_QM_INTER[64] = {
+    16, 17, 18, 19, 20, 21, 22, 23,   17, 18, 19, 20, 21, 22, 23, 24,
+    18, 19, 20, 21, 22, 23, 24, 25,   19, 20, 21, 22, 23, 24, 26, 27,
+    20, 21, 22, 23, 25, 26, 27, 28,   21, 22, 23, 24, 26, 27, 28, 30,
+    22, 23, 24, 26, 27, 28, 30, 31,   23, 24, 25, 27, 28, 30, 31, 33 };
+// deblock.cpp:13-27
+__constant__ int16_t EVX_ALPHA[32] = { 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 2, 2, 3, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 16, 18, 20, 22, 24, 26, 29, 32, 35 };
+__constant__ int16_t EVX_BETA[32]  = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 10, 11 };
+
+// quantize.cpp:37-55
+__device__ __forceinline__ int evx_luma_dc_scale(int qp) { return qp < 5 ? 8 : qp < 9 ? qp << 1 : qp < 25 ? qp + 8 : (qp << 1) - 16; }
+__device__ __forceinline__ int evx_chroma_dc_scale(int qp) { return qp < 5 ? 8 : qp < 25 ? (qp + 13) >> 1 : qp - 6; }
+
+// quantize.cpp:79-180: one coefficient.  mode 0 intra luma, 1 intra chroma, 2 inter; pos = j*8+k
+__device__ __forceinline__ int evx_quant(int s, int pos, int mode, int qp, int linear, const int16_t *qm_intra, const int16_t *qm_inter)
+{
+    int out;
+    if (linear)
+    {
+        if (mode < 2) out = (short) evx_rdiv(s, qp << 1);
+        else { int m = (short) (evx_abs16(s) - (qp >> 1)); out = (short) evx_rdiv(m, qp << 1); out = (short) (out * evx_sign(s)); }
+    }
+    else if (mode < 2)
+    {
+        if (pos == 0) out = (short) evx_rdiv(s, mode == 0 ? evx_luma_dc_scale(qp) : evx_chroma_dc_scale(qp));
+        else out = (short) evx_rdiv(evx_rdiv(s * 16, qm_intra[pos]), qp << 1);
+    }
+    else
+    {
+        int f = (short) evx_rdiv(s * 16, qm_inter[pos]);
+        out = (short) evx_rdiv(f - evx_sign(f) * qp, qp << 1);
+    }
+    return out;
+}
+
+// quantize.cpp:182-243
+__device__ __forceinline__ int evx_dequant(int s, int pos, int mode, int qp, int linear, const int16_t *qm_intra, const int16_t *qm_inter)
+{
+    int out;
+    if (linear)
+    {
+        out = 0;
+        if (s) { int modq = (qp + 1) % 2; int m = (short) ((evx_abs16(s) << 1) + 1); out = (short) (m * qp - modq); out = (short) (out * evx_sign(s)); }
+    }
+    else if (mode < 2 && pos == 0) out = (short) (s * (mode == 0 ? evx_luma_dc_scale(qp) : evx_chroma_dc_scale(qp)));
+    else out = (short) evx_tdiv_pow2(2 * s * (mode < 2 ? qm_intra[pos] : qm_inter[pos]) * qp, 4);
+    return out;
+}

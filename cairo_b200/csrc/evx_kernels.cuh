@@ -1,0 +1,991 @@
+// evx_kernels.cuh -- the sm_100a kernels of the EVX-1 pixel pipeline.
+//
+//   K1 evx_rgb_to_yuv420      convert.cpp:95-160      HBM bound, element-wise
+//   K2 evx_inter_search       motion.cpp:421-494      integer-ALU bound; TMA-staged windows
+//   K3 evx_wavefront          motion.cpp:354-419 + encode.cpp:17-203 + decode.cpp:15-144
+//   K4 evx_deblock            deblock.cpp:201-275     HBM bound; independent 8x8 tiles
+//   K5 evx_decode_recon       decode.cpp:146-170
+//   K6 evx_yuv420_to_rgb      convert.cpp:162-223     HBM bound, element-wise
+#pragma once
+
+#include <cuda.h>
+
+#include "evx_device.cuh"
+
+// ------------------------------------------------------------------ K1: RGB -> YUV 4:2:0
+// One thread per 8x2 pixel strip: 2 x 24 B in, 2 x 16 B luma + 2 x 8 B chroma out.
+// y uses >>8, chroma uses C '/' (toward zero); the four chroma samples of a quad are
+// summed in an int16 and averaged with (sum+2)>>2 (convert.cpp:11-14, 30-73).
+// Samples outside the visible frame are never written (they stay 0).
+__global__ void __launch_bounds__(256) evx_rgb_to_yuv420(const uint8_t *__restrict__ rgb, EvxPlanes dst, EvxGeom g)
+{
+    int strips_x = (g.vw + 7) >> 3;
+    int sx = blockIdx.x * blockDim.x + threadIdx.x;
+    int sy = blockIdx.y;
+    if (sx >= strips_x) return;
+    int x0 = sx * 8, y0 = sy * 2;
+    int n = min(8, g.vw - x0);                       // visible pixels in this strip (even)
+    uint8_t px[2][24];
+    bool fast = (n == 8) && ((g.vw & 3) == 0) && ((((size_t) rgb) & 3) == 0);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+    {
+        const uint8_t *row = rgb + ((size_t) (y0 + r) * g.vw + x0) * 3;
+        if (fast)
+        {
+            const uint32_t *row4 = reinterpret_cast<const uint32_t *>(row);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { uint32_t v = __ldg(row4 + k); px[r][4 * k] = v; px[r][4 * k + 1] = v >> 8; px[r][4 * k + 2] = v >> 16; px[r][4 * k + 3] = v >> 24; }
+        }
+        else
+        {
+            for (int k = 0; k < 24; ++k) px[r][k] = k < n * 3 ? __ldg(row + k) : 0;
+        }
+    }
+    short yv[2][8], uv[4], vv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+    {
+        short su = 0, sv = 0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+        {
+            int i = 2 * q + d;
+            int R = px[r][3 * i], G = px[r][3 * i + 1], B = px[r][3 * i + 2];
+            yv[r][i] = (short) (((77 * R + 150 * G + 29 * B + 128) >> 8) + 16);
+            su = (short) (su + ((-43 * R - 85 * G + 128 * B + 128) / 256 + 128));
+            sv = (short) (sv + ((128 * R - 107 * G - 21 * B + 128) / 256 + 128));
+        }
+        uv[q] = (short) ((su + 2) >> 2);
+        vv[q] = (short) ((sv + 2) >> 2);
+    }
+    int cw = g.w >> 1;
+    if (n == 8)
+    {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+        {
+            uint4 o;
+            o.x = evx_pack16(yv[r][0], yv[r][1]); o.y = evx_pack16(yv[r][2], yv[r][3]);
+            o.z = evx_pack16(yv[r][4], yv[r][5]); o.w = evx_pack16(yv[r][6], yv[r][7]);
+            *reinterpret_cast<uint4 *>(dst.y + (size_t) (y0 + r) * g.w + x0) = o;
+        }
+        uint2 ou = { evx_pack16(uv[0], uv[1]), evx_pack16(uv[2], uv[3]) };
+        uint2 ov = { evx_pack16(vv[0], vv[1]), evx_pack16(vv[2], vv[3]) };
+        *reinterpret_cast<uint2 *>(dst.u + (size_t) sy * cw + (x0 >> 1)) = ou;
+        *reinterpret_cast<uint2 *>(dst.v + (size_t) sy * cw + (x0 >> 1)) = ov;
+    }
+    else
+    {
+        for (int i = 0; i < n; ++i) { dst.y[(size_t) y0 * g.w + x0 + i] = yv[0][i]; dst.y[(size_t) (y0 + 1) * g.w + x0 + i] = yv[1][i]; }
+        for (int q = 0; q < n / 2; ++q) { dst.u[(size_t) sy * cw + (x0 >> 1) + q] = uv[q]; dst.v[(size_t) sy * cw + (x0 >> 1) + q] = vv[q]; }
+    }
+}
+
+// ------------------------------------------------------------------ K6: YUV 4:2:0 -> RGB
+// convert.cpp:16-19, 162-223.  saturate() funnels through an int16 parameter (math.h:218-221).
+__device__ __forceinline__ uint8_t evx_sat8(int v) { return (uint8_t) evx_clip((int) (short) v, 0, 255); }
+
+__global__ void __launch_bounds__(256) evx_yuv420_to_rgb(EvxPlanes src, uint8_t *__restrict__ rgb, EvxGeom g)
+{
+    int strips_x = (g.vw + 7) >> 3;
+    int sx = blockIdx.x * blockDim.x + threadIdx.x;
+    int sy = blockIdx.y;
+    if (sx >= strips_x) return;
+    int x0 = sx * 8, y0 = sy * 2;
+    int n = min(8, g.vw - x0);
+    int cw = g.w >> 1;
+    short uv[4], vv[4];
+    {
+        uint2 a = *reinterpret_cast<const uint2 *>(src.u + (size_t) sy * cw + (x0 >> 1));
+        uint2 b = *reinterpret_cast<const uint2 *>(src.v + (size_t) sy * cw + (x0 >> 1));
+        uv[0] = a.x; uv[1] = a.x >> 16; uv[2] = a.y; uv[3] = a.y >> 16;
+        vv[0] = b.x; vv[1] = b.x >> 16; vv[2] = b.y; vv[3] = b.y >> 16;
+    }
+    bool fast = (n == 8) && ((g.vw & 3) == 0) && ((((size_t) rgb) & 3) == 0);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+    {
+        uint4 yy = *reinterpret_cast<const uint4 *>(src.y + (size_t) (y0 + r) * g.w + x0);
+        short yv[8] = { (short) yy.x, (short) (yy.x >> 16), (short) yy.y, (short) (yy.y >> 16), (short) yy.z, (short) (yy.z >> 16), (short) yy.w, (short) (yy.w >> 16) };
+        uint8_t o[24];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            int y = yv[i], u = uv[i >> 1], v = vv[i >> 1];
+            o[3 * i]     = evx_sat8((256 * (y - 16) + 358 * (v - 128) + 128) >> 8);
+            o[3 * i + 1] = evx_sat8((256 * (y - 16) - 88 * (u - 128) - 182 * (v - 128) + 128) >> 8);
+            o[3 * i + 2] = evx_sat8((256 * (y - 16) + 452 * (u - 128) + 128) >> 8);
+        }
+        uint8_t *row = rgb + ((size_t) (y0 + r) * g.vw + x0) * 3;
+        if (fast)
+        {
+            uint32_t *row4 = reinterpret_cast<uint32_t *>(row);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) row4[k] = o[4 * k] | (o[4 * k + 1] << 8) | (o[4 * k + 2] << 16) | ((uint32_t) o[4 * k + 3] << 24);
+        }
+        else
+        {
+            for (int k = 0; k < n * 3; ++k) row[k] = o[k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ TMA / mbarrier (sm_100a PTX)
+
+__device__ __forceinline__ uint32_t evx_smem_addr(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void evx_mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(evx_smem_addr(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void evx_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(evx_smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void evx_mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(evx_smem_addr(bar)), "r"(phase) : "memory");
+}
+
+__device__ __forceinline__ void evx_tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(evx_smem_addr(dst)), "l"(map), "r"(x), "r"(y), "r"(evx_smem_addr(bar)) : "memory");
+}
+
+// ------------------------------------------------------------------ K2: inter search
+//
+// grid = (ceil(mbw/8), mbh, refs), block = 8 warps.  A CTA serves eight horizontally adjacent
+// macroblocks against ONE reference frame; their +-32 px search windows overlap into one
+// 208x80 luma tile and two 104x40 chroma tiles (49.9 KB), fetched by three TMA tile loads
+// (out-of-frame samples are zero-filled and never evaluated).  Each WARP then runs the whole
+// sequential search of its macroblock (motion.cpp:421-494) with no block-level
+// synchronisation: the 16x16+8x8+8x8 candidate cost is a warp-collective (evx_block_cost),
+// the acceptance rule is replayed identically in every lane.
+
+#define EVX_K2_MBS 8
+#define EVX_K2_WIN_W 208          // 32 + 8*16 + 48; 104 words = 8 (mod 32)
+#define EVX_K2_WIN_H 80
+#define EVX_K2_CWIN_W 104         // 52 words = 20 (mod 32) = 4*5
+#define EVX_K2_CWIN_H 40
+#define EVX_K2_SMEM (EVX_K2_WIN_W * EVX_K2_WIN_H * 2 + 2 * EVX_K2_CWIN_W * EVX_K2_CWIN_H * 2 + 16)
+
+struct EvxInterResult { EvxDesc desc; int sad; int pad[3]; };    // 32 bytes per (macroblock, reference)
+
+struct EvxK2Maps { CUtensorMap m[3 * 7]; };   // [ref][Y,U,V] for up to 7 past references
+
+__device__ __forceinline__ void evx_load_src_lane(const EvxPlanes &srcp, const EvxGeom &g, int px, int py, int lane, EvxLaneBlock &b)
+{
+    const uint32_t *y = reinterpret_cast<const uint32_t *>(srcp.y + (size_t) (py + (lane >> 3)) * g.w + px) + (lane & 7);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b.w[k] = __ldg(y + (size_t) 4 * k * (g.w >> 1));
+    int cw = g.w >> 1;
+    size_t off = (size_t) ((py >> 1) + (lane >> 2)) * cw + (px >> 1);
+    b.w[4] = __ldg(reinterpret_cast<const uint32_t *>(srcp.u + off) + (lane & 3));
+    b.w[5] = __ldg(reinterpret_cast<const uint32_t *>(srcp.v + off) + (lane & 3));
+}
+
+// the sequential search of one macroblock against one window (motion.cpp:254-275, 319-352, 421-494)
+__device__ __forceinline__ void evx_inter_search_warp(const EvxWin &win, const EvxLaneSrc &src, const EvxGeom &g, int px, int py, int thr,
+                                                      int lane, EvxSel &s, uint32_t &n_full, uint32_t &n_sub)
+{
+    EvxLaneBlock ref;
+    s.bx = px; s.by = py; s.ssd = EVX_BIG; s.sp_index = 0; s.sp_amount = 0; s.sp_enabled = 0;
+    evx_load_block(win, px, py, lane, ref);
+    evx_block_cost(ref, src, s.sad, s.mad);
+    n_full = 1; n_sub = 0;
+    if (s.mad < thr) return;                       // already a copy block: no search (motion.cpp:452)
+    for (int step = EVX_SEARCH_RADIUS; step > 0; step >>= 1)
+    {
+        int basex = s.bx, basey = s.by;
+#pragma unroll 1
+        for (int j = -1; j <= 1; ++j)
+#pragma unroll
+        for (int i = -1; i <= 1; ++i)
+        {
+            int x = basex + i * step, y = basey + j * step;
+            if (x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB) continue;
+            int sad, mad;
+            evx_load_block(win, x, y, lane, ref);
+            evx_block_cost(ref, src, sad, mad);
+            n_full++;
+            evx_accept_fullpel(s, x, y, sad, mad, px, py, thr);
+        }
+    }
+    EvxLaneBlock best;
+    evx_load_block(win, s.bx, s.by, lane, best);
+#pragma unroll 1
+    for (int j = -1; j <= 1; ++j)
+#pragma unroll 1
+    for (int i = -1; i <= 1; ++i)
+    {
+        int x = s.bx + i, y = s.by + j;
+        if (i == 0 && j == 0) continue;
+        if (x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB) continue;
+        int sh, mh, sq, mq;
+        evx_load_block(win, x, y, lane, ref);
+        evx_subpel_cost(best, ref, src, sh, mh, sq, mq);
+        n_sub += 2;
+        evx_accept_subpel(s, i, j, 0, sh, mh, thr);
+        evx_accept_subpel(s, i, j, 1, sq, mq, thr);
+    }
+}
+
+__global__ void __launch_bounds__(256) evx_inter_search(const __grid_constant__ EvxK2Maps maps, EvxPlanes srcp, EvxGeom g,
+                                                        EvxInterResult *__restrict__ results, int thr,
+                                                        unsigned long long *__restrict__ counters)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    int16_t *wy = reinterpret_cast<int16_t *>(smem);
+    int16_t *wu = wy + EVX_K2_WIN_W * EVX_K2_WIN_H;
+    int16_t *wv = wu + EVX_K2_CWIN_W * EVX_K2_CWIN_H;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wv + EVX_K2_CWIN_W * EVX_K2_CWIN_H);
+
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int ref = blockIdx.z;                           // 0-based: ring offset ref+1
+    int bx0 = blockIdx.x * EVX_K2_MBS, by = blockIdx.y;
+    int ox = bx0 * EVX_MB - 32, oy = by * EVX_MB - 32;
+
+    if (threadIdx.x == 0) evx_mbar_init(bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        evx_mbar_expect_tx(bar, EVX_K2_WIN_W * EVX_K2_WIN_H * 2 + 2 * EVX_K2_CWIN_W * EVX_K2_CWIN_H * 2);
+        evx_tma_load_2d(wy, &maps.m[ref * 3 + 0], ox, oy, bar);
+        evx_tma_load_2d(wu, &maps.m[ref * 3 + 1], ox >> 1, oy >> 1, bar);
+        evx_tma_load_2d(wv, &maps.m[ref * 3 + 2], ox >> 1, oy >> 1, bar);
+    }
+
+    int bx = bx0 + warp;
+    bool active = bx < g.mbw;
+    int px = bx * EVX_MB, py = by * EVX_MB;
+    EvxLaneSrc src;
+    if (active)
+    {
+        EvxLaneBlock sb;
+        evx_load_src_lane(srcp, g, px, py, lane, sb);       // overlaps the TMA flight
+        evx_make_src(sb, src);
+    }
+    evx_mbar_wait(bar, 0);
+    if (!active) return;
+
+    EvxWin win;
+    win.y = reinterpret_cast<const uint32_t *>(wy); win.u = reinterpret_cast<const uint32_t *>(wu); win.v = reinterpret_cast<const uint32_t *>(wv);
+    win.pw_y = EVX_K2_WIN_W / 2; win.pw_c = EVX_K2_CWIN_W / 2;
+    win.ox = ox; win.oy = oy; win.cox = ox >> 1; win.coy = oy >> 1;
+
+    EvxSel s;
+    uint32_t n_full, n_sub;
+    evx_inter_search_warp(win, src, g, px, py, thr, lane, s, n_full, n_sub);
+
+    if (lane == 0)
+    {
+        EvxInterResult r;
+        r.desc = evx_desc_from_sel(s, 0, ref + 1, px, py, thr);
+        r.sad = s.sad; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        results[(size_t) ref * g.mbw * g.mbh + (size_t) by * g.mbw + bx] = r;
+        atomicAdd(&counters[0], (unsigned long long) n_full);
+        atomicAdd(&counters[1], (unsigned long long) n_sub);
+    }
+}
+
+// ------------------------------------------------------------------ K3 / K5 shared: transform + reconstruction of one macroblock
+//
+// Coefficient buffers are block-major: 6 blocks (Y00 Y01 Y10 Y11 U V) x 64.
+
+struct EvxMbShared
+{
+    int16_t src[384];        // source samples, block-major
+    int16_t pred[384];       // prediction, block-major
+    int16_t bufa[384];
+    int16_t bufb[384];
+    int16_t lut[64];         // DCT basis, xftables.h:57-67
+    int16_t qmi[64], qmt[64];
+    int red[3 * 32];
+    int qp, var;
+};
+
+// position of element e (0..383, block-major) inside the macroblock: plane comp, x, y
+__device__ __forceinline__ void evx_mb_pos(int e, int &comp, int &x, int &y)
+{
+    int b = e >> 6, r = (e >> 3) & 7, c = e & 7;
+    if (b < 4) { comp = 0; x = (b & 1) * 8 + c; y = (b >> 1) * 8 + r; }
+    else { comp = b - 3; x = c; y = r; }
+}
+
+// record layout handed to the host: 16x16 luma row-major, then U 8x8, V 8x8
+__device__ __forceinline__ int evx_record_index(int e)
+{
+    int comp, x, y;
+    evx_mb_pos(e, comp, x, y);
+    return comp == 0 ? y * 16 + x : 256 + (comp - 1) * 64 + y * 8 + x;
+}
+
+__device__ __forceinline__ void evx_init_tables(EvxMbShared &sh, int tid, int nt)
+{
+    for (int k = tid; k < 64; k += nt)
+    {
+        sh.lut[k] = (int16_t) evx_dct_lut(k >> 3, k & 7);
+        sh.qmi[k] = EVX_QM_INTRA[k];
+        sh.qmt[k] = EVX_QM_INTER[k];
+    }
+}
+
+// forward 8x8 passes (transform.cpp:264-301): in[b][line][k] -> out, scale after the sum
+__device__ __forceinline__ void evx_fdct_pass(const int16_t *in, int16_t *out, const int16_t *lut, int tid, int nt, bool columns)
+{
+    for (int e = tid; e < 384; e += nt)
+    {
+        int b = e >> 6, a = (e >> 3) & 7, i = e & 7;
+        int t = 0;
+        if (!columns)
+        {   // row pass: out[b][a][i] = sum_k in[b][a][k] * lut[i][k]
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += in[b * 64 + a * 8 + k] * lut[i * 8 + k];
+        }
+        else
+        {   // column pass: out[b][i][a] = sum_k in[b][k][a] * lut[i][k]   (e enumerates (a=column, i))
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += in[b * 64 + k * 8 + a] * lut[i * 8 + k];
+        }
+        t = i == 0 ? evx_tdiv_pow2(t * 45, 7) : evx_tdiv_pow2(t, 1);
+        int v = (short) evx_rdiv_pow2(t, 7);
+        if (!columns) out[b * 64 + a * 8 + i] = (int16_t) v;
+        else out[b * 64 + i * 8 + a] = (int16_t) v;
+    }
+}
+
+// inverse 8x8 passes (transform.cpp:330-366, 418-433): scale per term
+__device__ __forceinline__ int evx_idct_sum(const int16_t *in, int stride, const int16_t *lut, int i)
+{
+    int t = evx_tdiv_pow2((in[0] * lut[i]) * 45, 7);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += evx_tdiv_pow2(in[k * stride] * lut[k * 8 + i], 1);
+    return evx_rdiv_pow2(t, 7);
+}
+
+// Reconstruct a non-copy macroblock from quantised coefficients in sh.bufa (block-major):
+// dequantise, inverse transform, add the prediction (if any), store into the ring slot.
+// (decode.cpp:19-24, 50-72, 107-141)
+__device__ __forceinline__ void evx_reconstruct(EvxMbShared &sh, int type, int qp, int linear, bool has_pred,
+                                                const EvxPlanes &dst, const EvxGeom &g, int px, int py, int tid, int nt)
+{
+    bool intra_q = (type & EVX_T_INTRA) && !(type & EVX_T_MOTION);
+    for (int e = tid; e < 384; e += nt)
+    {
+        int b = e >> 6;
+        int mode = intra_q ? (b < 4 ? 0 : 1) : 2;
+        sh.bufb[e] = (int16_t) evx_dequant(sh.bufa[e], e & 63, mode, qp, linear, sh.qmi, sh.qmt);
+    }
+    __syncthreads();
+    for (int e = tid; e < 384; e += nt)
+    {   // vertical pass: scratch[b][i][j] from column j
+        int b = e >> 6, i = (e >> 3) & 7, j = e & 7;
+        sh.bufa[b * 64 + i * 8 + j] = (int16_t) evx_idct_sum(sh.bufb + b * 64 + j, 8, sh.lut, i);
+    }
+    __syncthreads();
+    int cw = g.w >> 1;
+    for (int e = tid; e < 384; e += nt)
+    {   // horizontal pass: out[b][j][i] from row j, plus prediction
+        int b = e >> 6, j = (e >> 3) & 7, i = e & 7;
+        int v = evx_idct_sum(sh.bufa + b * 64 + j * 8, 1, sh.lut, i);
+        if (has_pred) v += sh.pred[e];
+        int comp, x, y;
+        evx_mb_pos(e, comp, x, y);
+        if (comp == 0) dst.y[(size_t) (py + y) * g.w + px + x] = (int16_t) v;
+        else (comp == 1 ? dst.u : dst.v)[(size_t) ((py >> 1) + y) * cw + (px >> 1) + x] = (int16_t) v;
+    }
+}
+
+__device__ __forceinline__ void evx_store_pred_as_recon(const EvxMbShared &sh, const EvxPlanes &dst, const EvxGeom &g, int px, int py, int tid, int nt)
+{
+    int cw = g.w >> 1;
+    for (int e = tid; e < 384; e += nt)
+    {
+        int comp, x, y;
+        evx_mb_pos(e, comp, x, y);
+        if (comp == 0) dst.y[(size_t) (py + y) * g.w + px + x] = sh.pred[e];
+        else (comp == 1 ? dst.u : dst.v)[(size_t) ((py >> 1) + y) * cw + (px >> 1) + x] = sh.pred[e];
+    }
+}
+
+// Prediction of a block type straight from a ring slot in global memory (L2 loads: the slot
+// may be the frame under construction).  encode.cpp:83-141 / decode.cpp:27-135.
+__device__ __forceinline__ void evx_build_pred_global(EvxMbShared &sh, const EvxPlanes &ref, const EvxGeom &g,
+                                                      int bxp, int byp, bool sp, int sp_amount, int dx, int dy, int tid, int nt)
+{
+    int cw = g.w >> 1;
+    for (int e = tid; e < 384; e += nt)
+    {
+        int comp, x, y;
+        evx_mb_pos(e, comp, x, y);
+        int a, b = 0;
+        if (comp == 0)
+        {
+            a = __ldcg(ref.y + (size_t) (byp + y) * g.w + bxp + x);
+            if (sp) b = __ldcg(ref.y + (size_t) (byp + dy + y) * g.w + bxp + dx + x);
+        }
+        else
+        {
+            const int16_t *pl = comp == 1 ? ref.u : ref.v;
+            a = __ldcg(pl + (size_t) ((byp >> 1) + y) * cw + (bxp >> 1) + x);
+            if (sp) b = __ldcg(pl + (size_t) (((byp + dy) >> 1) + y) * cw + ((bxp + dx) >> 1) + x);
+        }
+        sh.pred[e] = (int16_t) (sp ? (sp_amount ? evx_lerp_quarter(a, b) : evx_lerp_half(a, b)) : a);
+    }
+}
+
+// ------------------------------------------------------------------ wavefront scheduling
+//
+// Macroblock (bx,by) may start when (bx-1,by) and (min(bx+2,W-1),by-1) are complete; this
+// satisfies both the read-after-write side of the intra search (reconstructed neighbours)
+// and its write-after-read side (stale samples of the ring slot, still needed by the row
+// above).  progress[by] = number of completed macroblocks of row `by`.  Work is handed out by
+// an atomic ticket in wavefront order, so a CTA holding ticket k only ever waits on tickets
+// < k, all of which are already held by running (or finished) CTAs: no deadlock for any grid.
+
+__device__ __forceinline__ int evx_ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void evx_st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void evx_wait_deps(const int *progress, int bx, int by, int mbw)
+{
+    if (bx > 0) while (evx_ld_acquire(progress + by) < bx) __nanosleep(20);
+    if (by > 0)
+    {
+        int need = min(bx + 2, mbw - 1) + 1;
+        while (evx_ld_acquire(progress + by - 1) < need) __nanosleep(20);
+    }
+}
+
+// ------------------------------------------------------------------ K3: encoder wavefront
+//
+// One CTA of 9 warps per macroblock in flight.  Intra search (motion.cpp:354-419) over a
+// window of the frame under construction staged in shared memory: nine warps = the nine
+// candidates of a 3x3 round, one __syncthreads per round, acceptance replayed by every
+// thread.  Then classify (encode.cpp:17-67) against K2's results, residual, 6x 8x8 DCT,
+// adaptive QP, quantise, and the reconstruction loop (decode.cpp:15-144).
+
+#define EVX_K3_THREADS 288
+#define EVX_K3_WIN 80
+#define EVX_K3_CWIN 40
+
+struct EvxK3Params
+{
+    EvxPlanes src;             // input_cache
+    EvxPlanes ring[8];         // prediction_cache[slot]
+    EvxGeom g;
+    int R, linear;
+    int frame_type, quality;
+    uint32_t frame_index;
+    const EvxInterResult *inter;   // [R-1][nmb], valid when frame_type == 1
+    EvxDesc *table;                // block_table
+    int16_t *records;              // [nmb][384] coefficient records, slot = record_slot[mb]
+    int *record_slot;              // [nmb] slot of each non-copy macroblock (-1 for copy blocks)
+    const uint32_t *order;         // [nmb] wavefront order: bx | by << 16
+    int *sync;                     // [0] ticket, [1] record counter, [2..] progress[mbh]
+    unsigned long long *counters;
+};
+
+__global__ void __launch_bounds__(EVX_K3_THREADS) evx_wavefront(const __grid_constant__ EvxK3Params p)
+{
+    __shared__ __align__(16) int16_t win_y[EVX_K3_WIN * EVX_K3_WIN];
+    __shared__ __align__(16) int16_t win_u[EVX_K3_CWIN * EVX_K3_CWIN];
+    __shared__ __align__(16) int16_t win_v[EVX_K3_CWIN * EVX_K3_CWIN];
+    __shared__ EvxMbShared sh;
+    __shared__ int2 cand[2][16];
+    __shared__ int s_ticket, s_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const EvxGeom g = p.g;
+    const int nmb = g.mbw * g.mbh;
+    const int thr = (p.quality >> 2) + 1;                                  // motion.cpp:369, 436
+    const int dest = (int) (p.frame_index % (uint32_t) p.R);               // common.cpp:192-195
+    const EvxPlanes cur = p.ring[dest];
+    int *progress = p.sync + 2;
+    const int cw = g.w >> 1;
+
+    evx_init_tables(sh, tid, EVX_K3_THREADS);
+
+    for (;;)
+    {
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(&p.sync[0], 1);
+        __syncthreads();
+        const int ticket = s_ticket;
+        if (ticket >= nmb) break;
+        const uint32_t ord = p.order[ticket];
+        const int bx = ord & 0xFFFF, by = ord >> 16;
+        const int px = bx * EVX_MB, py = by * EVX_MB;
+        const int mb = by * g.mbw + bx;
+
+        // source macroblock -> shared (block-major), independent of the neighbours
+        for (int e = tid; e < 384; e += EVX_K3_THREADS)
+        {
+            int comp, x, y;
+            evx_mb_pos(e, comp, x, y);
+            sh.src[e] = comp == 0 ? p.src.y[(size_t) (py + y) * g.w + px + x]
+                                  : (comp == 1 ? p.src.u : p.src.v)[(size_t) ((py >> 1) + y) * cw + (px >> 1) + x];
+        }
+        if (tid == 0) evx_wait_deps(progress, bx, by, g.mbw);
+        __syncthreads();
+
+        // stage the intra window: rows py-48..py-1 full width, rows py..py+31 only left of px
+        const int ox = px - 32, oy = py - 48, cox = (px >> 1) - 16, coy = (py >> 1) - 24;
+        for (int c = tid; c < EVX_K3_WIN * (EVX_K3_WIN / 8); c += EVX_K3_THREADS)
+        {
+            int r = c / (EVX_K3_WIN / 8), k = c % (EVX_K3_WIN / 8);
+            int y = oy + r, x = ox + 8 * k;
+            if (y < 0 || y >= g.h || x < 0 || x >= g.w) continue;
+            if (r >= 48 && k >= 4) continue;
+            *reinterpret_cast<int4 *>(win_y + r * EVX_K3_WIN + 8 * k) = __ldcg(reinterpret_cast<const int4 *>(cur.y + (size_t) y * g.w + x));
+        }
+        for (int c = tid; c < 2 * EVX_K3_CWIN * (EVX_K3_CWIN / 8); c += EVX_K3_THREADS)
+        {
+            int pl = c / (EVX_K3_CWIN * (EVX_K3_CWIN / 8)), cc = c % (EVX_K3_CWIN * (EVX_K3_CWIN / 8));
+            int r = cc / (EVX_K3_CWIN / 8), k = cc % (EVX_K3_CWIN / 8);
+            int y = coy + r, x = cox + 8 * k;
+            if (y < 0 || y >= (g.h >> 1) || x < 0 || x >= cw) continue;
+            if (r >= 24 && k >= 2) continue;
+            const int16_t *sp = (pl ? cur.v : cur.u) + (size_t) y * cw + x;
+            *reinterpret_cast<int4 *>((pl ? win_v : win_u) + r * EVX_K3_CWIN + 8 * k) = __ldcg(reinterpret_cast<const int4 *>(sp));
+        }
+        __syncthreads();
+
+        EvxWin win;
+        win.y = reinterpret_cast<const uint32_t *>(win_y); win.u = reinterpret_cast<const uint32_t *>(win_u); win.v = reinterpret_cast<const uint32_t *>(win_v);
+        win.pw_y = EVX_K3_WIN / 2; win.pw_c = EVX_K3_CWIN / 2;
+        win.ox = ox; win.oy = oy; win.cox = cox; win.coy = coy;
+
+        // this warp's copy of the source block in the lane layout
+        EvxLaneSrc src;
+        {
+            EvxLaneBlock sb;
+            int rr = lane >> 3, cc = lane & 7;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                int y = rr + 4 * k, x = 2 * cc;
+                int e = ((y >> 3) * 2 + (x >> 3)) * 64 + (y & 7) * 8 + (x & 7);
+                sb.w[k] = evx_pack16(sh.src[e], sh.src[e + 1]);
+            }
+            int e = 256 + (lane >> 2) * 8 + 2 * (lane & 3);
+            sb.w[4] = evx_pack16(sh.src[e], sh.src[e + 1]);
+            sb.w[5] = evx_pack16(sh.src[e + 64], sh.src[e + 65]);
+            evx_make_src(sb, src);
+        }
+
+        // ---- intra search, motion.cpp:354-419
+        EvxSel s;
+        s.bx = px; s.by = py; s.mad = EVX_BIG; s.ssd = EVX_BIG; s.sp_index = 0; s.sp_amount = 0; s.sp_enabled = 0;
+        {   // compute_block_sad(src): the int16 abs overload (analysis.h:57-68)
+            int a = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a += evx_abs16(evx_lo16(src.pos[k])) + evx_abs16(evx_hi16(src.pos[k]));
+            s.sad = __reduce_add_sync(0xFFFFFFFFu, a);
+        }
+        uint32_t n_full = 0, n_sub = 0;
+        int buf = 0;
+        for (int round = 0; round < 5; ++round)
+        {
+            const int step = round == 0 ? EVX_SEARCH_RADIUS : (EVX_SEARCH_RADIUS >> round);
+            const int top = round == 0 ? -2 : -1;          // first round scans rows -32,-16,0 (motion.cpp:384-386)
+            // candidate of this warp
+            const int j = warp / 3, i = warp % 3;
+            const int x = s.bx + (i - 1) * step, y = s.by + (top + j) * step;
+            bool legal = !(y > py - EVX_MB && x > px - EVX_MB) && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);
+            if (legal)
+            {
+                EvxLaneBlock ref;
+                int sad, mad;
+                evx_load_block(win, x, y, lane, ref);
+                evx_block_cost(ref, src, sad, mad);
+                if (lane == 0) cand[buf][warp] = make_int2(sad, mad);
+            }
+            __syncthreads();
+            const int basex = s.bx, basey = s.by;
+#pragma unroll
+            for (int c = 0; c < 9; ++c)
+            {
+                int cx = basex + (c % 3 - 1) * step, cy = basey + (top + c / 3) * step;
+                bool ok = !(cy > py - EVX_MB && cx > px - EVX_MB) && !(cx < 0 || cx > g.w - EVX_MB || cy < 0 || cy > g.h - EVX_MB);
+                if (!ok) continue;
+                int2 v = cand[buf][c];
+                n_full++;
+                evx_accept_fullpel(s, cx, cy, v.x, v.y, px, py, thr);
+            }
+            buf ^= 1;
+        }
+        // ---- intra sub-pel, motion.cpp:277-317: warp d < 8 handles direction d
+        {
+            const int d = warp < 4 ? warp : warp + 1;          // skip the centre
+            const int j = d / 3 - 1, i = d % 3 - 1;
+            const int x = s.bx + i, y = s.by + j;
+            bool legal = warp < 8 && !(y > py - EVX_MB && x > px - EVX_MB) && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);
+            if (legal)
+            {
+                EvxLaneBlock best, nb;
+                int shh, mh, sq, mq;
+                evx_load_block(win, s.bx, s.by, lane, best);
+                evx_load_block(win, x, y, lane, nb);
+                evx_subpel_cost(best, nb, src, shh, mh, sq, mq);
+                if (lane == 0) { cand[buf][2 * warp] = make_int2(shh, mh); cand[buf][2 * warp + 1] = make_int2(sq, mq); }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8)
+            {
+                int dd = w8 < 4 ? w8 : w8 + 1;
+                int jj = dd / 3 - 1, ii = dd % 3 - 1;
+                int cx = s.bx + ii, cy = s.by + jj;
+                bool ok = !(cy > py - EVX_MB && cx > px - EVX_MB) && !(cx < 0 || cx > g.w - EVX_MB || cy < 0 || cy > g.h - EVX_MB);
+                if (!ok) continue;
+                int2 h = cand[buf][2 * w8], q = cand[buf][2 * w8 + 1];
+                n_sub += 2;
+                evx_accept_subpel(s, ii, jj, 0, h.x, h.y, thr);
+                evx_accept_subpel(s, ii, jj, 1, q.x, q.y, thr);
+            }
+            buf ^= 1;
+        }
+
+        // ---- classify, encode.cpp:17-67
+        EvxDesc d = evx_desc_from_sel(s, 1, 0, px, py, thr);
+        int best_sad = s.sad;
+        if (p.frame_type == 1)
+        {
+            for (int off = 1; off < p.R; ++off)
+            {
+                const EvxInterResult *ir = p.inter + (size_t) (off - 1) * nmb + mb;
+                int4 raw = __ldg(reinterpret_cast<const int4 *>(&ir->desc));
+                int isad = __ldg(&ir->sad);
+                bool cc = (raw.x & EVX_T_COPY) != 0, bc = (d.type() & EVX_T_COPY) != 0;
+                bool take = (cc != bc) ? cc : (isad < best_sad);
+                if (take) { d.w0 = raw.x; d.w1 = raw.y; d.w2 = raw.z; d.w3 = raw.w; best_sad = isad; }
+            }
+        }
+        const int type = d.type();
+
+        // ---- prediction (encode.cpp:83-141)
+        bool has_pred = type != EVX_T_INTRA;
+        if (has_pred)
+        {
+            int mx = (type & EVX_T_MOTION) ? d.mx() : 0, my = (type & EVX_T_MOTION) ? d.my() : 0;
+            bool sp = (type & EVX_T_MOTION) && d.sp_pred();
+            int dx = 0, dy = 0;
+            if (sp) evx_frac_direction(d.sp_index(), dx, dy);
+            if (type & EVX_T_INTRA)
+            {   // from the staged window
+                int bxp = px + mx - ox, byp = py + my - oy;
+                int cbx = ((px + mx) >> 1) - cox, cby = ((py + my) >> 1) - coy;
+                int cnx = ((px + mx + dx) >> 1) - cox, cny = ((py + my + dy) >> 1) - coy;
+                for (int e = tid; e < 384; e += EVX_K3_THREADS)
+                {
+                    int comp, x, y;
+                    evx_mb_pos(e, comp, x, y);
+                    int a, b = 0;
+                    if (comp == 0)
+                    {
+                        a = win_y[(byp + y) * EVX_K3_WIN + bxp + x];
+                        if (sp) b = win_y[(byp + dy + y) * EVX_K3_WIN + bxp + dx + x];
+                    }
+                    else
+                    {
+                        const int16_t *wp = comp == 1 ? win_u : win_v;
+                        a = wp[(cby + y) * EVX_K3_CWIN + cbx + x];
+                        if (sp) b = wp[(cny + y) * EVX_K3_CWIN + cnx + x];
+                    }
+                    sh.pred[e] = (int16_t) (sp ? (d.sp_amount() ? evx_lerp_quarter(a, b) : evx_lerp_half(a, b)) : a);
+                }
+            }
+            else
+            {
+                int slot = (int) ((p.frame_index + (uint32_t) p.R - (uint32_t) d.target()) % (uint32_t) p.R);
+                evx_build_pred_global(sh, p.ring[slot], g, px + mx, py + my, sp, d.sp_amount(), dx, dy, tid, EVX_K3_THREADS);
+            }
+        }
+        __syncthreads();
+
+        if (type & EVX_T_COPY)
+        {   // copy blocks: prediction is the reconstruction; no coefficients (encode.cpp:155-157)
+            evx_store_pred_as_recon(sh, cur, g, px, py, tid, EVX_K3_THREADS);
+            if (tid == 0) { p.table[mb] = d; p.record_slot[mb] = -1; }
+        }
+        else
+        {
+            // residual (transform.cpp:29-32: int16 subtraction)
+            for (int e = tid; e < 384; e += EVX_K3_THREADS) sh.bufa[e] = (int16_t) (has_pred ? sh.src[e] - sh.pred[e] : sh.src[e]);
+            __syncthreads();
+            evx_fdct_pass(sh.bufa, sh.bufb, sh.lut, tid, EVX_K3_THREADS, false);
+            __syncthreads();
+            evx_fdct_pass(sh.bufb, sh.bufa, sh.lut, tid, EVX_K3_THREADS, true);
+            __syncthreads();
+            // compute_block_variance2 over the 16x16 luma coefficients except (0,0) (analysis.h:176-198)
+            {
+                uint32_t sum = 0, sq = 0; int cnt = 0;
+                if (tid >= 1 && tid < 256) { int t = sh.bufa[tid]; if (t) { sum = (uint32_t) t; sq = (uint32_t) (t * t); cnt = 1; } }
+                sum = __reduce_add_sync(0xFFFFFFFFu, sum); sq = __reduce_add_sync(0xFFFFFFFFu, sq); cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+                if (lane == 0) { sh.red[warp] = (int) sum; sh.red[32 + warp] = (int) sq; sh.red[64 + warp] = cnt; }
+                __syncthreads();
+                if (tid == 0)
+                {
+                    uint32_t S = 0, Q = 0; int C = 0;
+                    for (int w8 = 0; w8 < 8; ++w8) { S += (uint32_t) sh.red[w8]; Q += (uint32_t) sh.red[32 + w8]; C += sh.red[64 + w8]; }
+                    int var = 0;
+                    if (C > 0) var = (int) (Q - (uint32_t) evx_rdiv((int) (S * S), C));
+                    // query_block_quantization_parameter, quantize.cpp:60-77
+                    int q = p.quality & 0xFF;
+                    int idx = evx_clip(evx_ilog2((uint32_t) var) >> 1, 1, 31);
+                    int qp = q;
+                    if (idx > q) qp = evx_clip(q + ((idx - q) >> 1), 1, 31);
+                    else if (idx < q) qp = evx_clip(q - ((q - idx) >> 1), 1, 31);
+                    sh.qp = qp; sh.var = var;
+                    s_slot = atomicAdd(&p.sync[1], 1);
+                }
+                __syncthreads();
+            }
+            const int qp = sh.qp;
+            const bool intra_q = (type & EVX_T_INTRA) && !(type & EVX_T_MOTION);
+            int16_t *rec = p.records + (size_t) s_slot * 384;
+            for (int e = tid; e < 384; e += EVX_K3_THREADS)
+            {
+                int b = e >> 6;
+                int mode = intra_q ? (b < 4 ? 0 : 1) : 2;
+                int qv = evx_quant(sh.bufa[e], e & 63, mode, qp, p.linear, sh.qmi, sh.qmt);
+                sh.bufb[e] = (int16_t) qv;
+            }
+            __syncthreads();
+            for (int e = tid; e < 384; e += EVX_K3_THREADS) { sh.bufa[e] = sh.bufb[e]; rec[evx_record_index(e)] = sh.bufb[e]; }
+            if (tid == 0) { d.set_q(qp, sh.var); p.table[mb] = d; p.record_slot[mb] = s_slot; }
+            __syncthreads();
+            evx_reconstruct(sh, type, qp, p.linear, has_pred, cur, g, px, py, tid, EVX_K3_THREADS);
+        }
+
+        if (tid == 32) { atomicAdd(&p.counters[0], (unsigned long long) n_full); atomicAdd(&p.counters[1], (unsigned long long) n_sub); }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); evx_st_release(progress + by, bx + 1); }
+    }
+}
+
+// ------------------------------------------------------------------ K5: decoder reconstruction (decode.cpp:146-170)
+// Same wavefront rule (INTRA_MOTION_* blocks read the frame under construction, stale samples
+// included); no search.  One CTA of 128 threads per macroblock in flight.
+
+#define EVX_K5_THREADS 128
+
+struct EvxK5Params
+{
+    EvxPlanes ring[8];
+    EvxGeom g;
+    int R, linear;
+    uint32_t frame_index;
+    const EvxDesc *table;
+    const int16_t *records;        // dense, raster order of the non-copy macroblocks
+    const int *record_slot;        // [nmb]
+    const uint32_t *order;
+    int *sync;
+};
+
+__global__ void __launch_bounds__(EVX_K5_THREADS) evx_decode_recon(const __grid_constant__ EvxK5Params p)
+{
+    __shared__ EvxMbShared sh;
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x;
+    const EvxGeom g = p.g;
+    const int nmb = g.mbw * g.mbh;
+    const int dest = (int) (p.frame_index % (uint32_t) p.R);
+    const EvxPlanes cur = p.ring[dest];
+    int *progress = p.sync + 2;
+
+    evx_init_tables(sh, tid, EVX_K5_THREADS);
+    for (;;)
+    {
+        __syncthreads();
+        if (tid == 0) s_ticket = atomicAdd(&p.sync[0], 1);
+        __syncthreads();
+        const int ticket = s_ticket;
+        if (ticket >= nmb) break;
+        const uint32_t ord = p.order[ticket];
+        const int bx = ord & 0xFFFF, by = ord >> 16;
+        const int px = bx * EVX_MB, py = by * EVX_MB;
+        const int mb = by * g.mbw + bx;
+        const EvxDesc d = p.table[mb];
+        const int type = d.type() & 7;
+        const bool has_pred = type != EVX_T_INTRA;
+        if (!(type & EVX_T_COPY))
+        {
+            const int16_t *rec = p.records + (size_t) p.record_slot[mb] * 384;
+            for (int e = tid; e < 384; e += EVX_K5_THREADS) sh.bufa[e] = rec[evx_record_index(e)];
+        }
+        if (tid == 0) evx_wait_deps(progress, bx, by, g.mbw);
+        __syncthreads();
+        if (has_pred)
+        {
+            int mx = (type & EVX_T_MOTION) ? d.mx() : 0, my = (type & EVX_T_MOTION) ? d.my() : 0;
+            bool sp = (type & EVX_T_MOTION) && d.sp_pred();
+            int dx = 0, dy = 0;
+            if (sp) evx_frac_direction(d.sp_index() & 7, dx, dy);
+            int off = (type & EVX_T_INTRA) ? 0 : d.target();
+            int slot = (int) ((p.frame_index + (uint32_t) p.R - (uint32_t) (off % p.R)) % (uint32_t) p.R);
+            // a valid stream never points outside the frame; clamp so a corrupt one cannot fault
+            int bxp = evx_clip(px + mx, 0, g.w - EVX_MB), byp = evx_clip(py + my, 0, g.h - EVX_MB);
+            if (sp) { dx = evx_clip(bxp + dx, 0, g.w - EVX_MB) - bxp; dy = evx_clip(byp + dy, 0, g.h - EVX_MB) - byp; }
+            evx_build_pred_global(sh, p.ring[slot], g, bxp, byp, sp, d.sp_amount(), dx, dy, tid, EVX_K5_THREADS);
+        }
+        __syncthreads();
+        if (type & EVX_T_COPY) evx_store_pred_as_recon(sh, cur, g, px, py, tid, EVX_K5_THREADS);
+        else evx_reconstruct(sh, type, d.q_index(), p.linear, has_pred, cur, g, px, py, tid, EVX_K5_THREADS);
+        __syncthreads();
+        if (tid == 0) { __threadfence(); evx_st_release(progress + by, bx + 1); }
+    }
+}
+
+// ------------------------------------------------------------------ K4: deblocking
+//
+// The reference filters in place in raster order (deblock.cpp:201-254).  Because every
+// filter reads 4+4 and writes at most 3+3 samples on an 8-sample grid, the sweep decomposes
+// into INDEPENDENT 8x8 tiles centred on the grid crossings (rows j-4..j+3, cols i-4..i+3):
+// inside a tile, the upper band's vertical edge on rows j-4..j-1, then the horizontal edge on
+// all eight columns, then the lower band's vertical edge on rows j..j+3; no tile reads or
+// writes outside itself (proved against the reference order in tests/test_schedules.py).
+// One thread per tile; 16-byte rows -> coalesced 8-byte accesses.
+
+__device__ __forceinline__ void evx_edge_params(const EvxDesc *table, int ia, int ib, int &qp, int &strength)
+{
+    uint32_t a0 = __ldg(&table[ia].w0), a3 = __ldg(&table[ia].w3), b0 = __ldg(&table[ib].w0), b3 = __ldg(&table[ib].w3);
+    bool ac = (a0 & EVX_T_COPY) != 0, bc = (b0 & EVX_T_COPY) != 0;
+    int qa = (a3 >> 8) & 0xFF, qb = (b3 >> 8) & 0xFF;
+    qp = (!ac && !bc) ? (qa + qb) >> 1 : (!ac ? qa : (!bc ? qb : 0));        // deblock.cpp:49-65
+    strength = (ac && bc) ? 0 : ((ac != bc) ? 1 : 2);                          // deblock.cpp:67-79
+}
+
+// deblock.cpp:81-129 on p3..q3 = s[0..7]
+__device__ __forceinline__ void evx_filter8(int s[8], int qp, int strength, bool luma)
+{
+    int p3 = s[0], p2 = s[1], p1 = s[2], p0 = s[3], q0 = s[4], q1 = s[5], q2 = s[6], q3 = s[7];
+    int d0 = (short) abs(p0 - q0), d1 = (short) abs(p1 - p0), d2 = (short) abs(q1 - q0);
+    int al = EVX_ALPHA[qp & 31], be = EVX_BETA[qp & 31];
+    if (d0 >= al || d1 >= be || d2 >= be) return;
+    if (strength == 2)
+    {
+        s[3] = (short) evx_rdiv_pow2(p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1, 3);
+        s[2] = (short) evx_rdiv_pow2(p2 + p1 + p0 + q0, 2);
+        s[4] = (short) evx_rdiv_pow2(p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2, 3);
+        s[5] = (short) evx_rdiv_pow2(p0 + q0 + q1 + q2, 2);
+        if (luma)
+        {
+            s[1] = (short) evx_rdiv_pow2(2 * p3 + 3 * p2 + p1 + p0 + q0, 3);
+            s[6] = (short) evx_rdiv_pow2(2 * q3 + 3 * q2 + q1 + q0 + p0, 3);
+        }
+    }
+    else if (strength == 1)
+    {
+        s[3] = (short) evx_rdiv_pow2(((q0 + p0) * 4) + p1 - q1, 3);
+        s[4] = (short) evx_rdiv_pow2(((q0 + p0) * 4) + q1 - p1, 3);
+        if (luma)
+        {
+            s[2] = (short) evx_rdiv_pow2((p2 * 4) + (p0 * 2) + (q0 * 2), 3);
+            s[5] = (short) evx_rdiv_pow2((q2 * 4) + (q0 * 2) + (p0 * 2), 3);
+        }
+    }
+}
+
+struct EvxK4Params { EvxPlanes pl; EvxGeom g; const EvxDesc *table; };
+
+__global__ void __launch_bounds__(128) evx_deblock(const __grid_constant__ EvxK4Params p)
+{
+    // blockIdx.z: plane; tiles enumerated with i = 8*tx (0..w), j = 8*ty (0..h)
+    const int comp = blockIdx.z;
+    const bool luma = comp == 0;
+    const int w = luma ? p.g.w : p.g.w >> 1, h = luma ? p.g.h : p.g.h >> 1;
+    const int mbs = luma ? 16 : 8;
+    const int wb = w / mbs;
+    int16_t *img = comp == 0 ? p.pl.y : (comp == 1 ? p.pl.u : p.pl.v);
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y;
+    if (tx > w / 8 || ty > h / 8) return;
+    const int i = tx * 8, j = ty * 8;
+    const bool has_l = i > 0, has_r = i < w, has_t = j > 0, has_b = j < h;
+
+    int t[8][8];          // t[row][col], rows j-4..j+3, cols i-4..i+3
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+    {
+        bool rv = r < 4 ? has_t : has_b;
+        uint2 a = make_uint2(0, 0), b = make_uint2(0, 0);
+        if (rv && has_l) a = *reinterpret_cast<const uint2 *>(img + (size_t) (j - 4 + r) * w + i - 4);
+        if (rv && has_r) b = *reinterpret_cast<const uint2 *>(img + (size_t) (j - 4 + r) * w + i);
+        t[r][0] = evx_lo16(a.x); t[r][1] = evx_hi16(a.x); t[r][2] = evx_lo16(a.y); t[r][3] = evx_hi16(a.y);
+        t[r][4] = evx_lo16(b.x); t[r][5] = evx_hi16(b.x); t[r][6] = evx_lo16(b.y); t[r][7] = evx_hi16(b.y);
+    }
+    int qp, st;
+    // 1. vertical edge at column i, upper band (rows j-4..j-1 belong to band j-8)
+    if (has_l && has_r && has_t)
+    {
+        int brow = ((j - 8) / mbs) * wb;
+        evx_edge_params(p.table, (i - 1) / mbs + brow, i / mbs + brow, qp, st);
+        if (st)
+        {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) evx_filter8(t[r], qp, st, luma);
+        }
+    }
+    // 2. horizontal edge at row j: columns i-4..i-1 belong to edge segment i-8, columns i..i+3 to segment i
+    if (has_t && has_b)
+    {
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+        {
+            if (half == 0 ? !has_l : !has_r) continue;
+            int col = half == 0 ? i - 8 : i;
+            evx_edge_params(p.table, col / mbs + ((j - 1) / mbs) * wb, col / mbs + (j / mbs) * wb, qp, st);
+            if (!st) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+            {
+                int s[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) s[r] = t[r][half * 4 + c];
+                evx_filter8(s, qp, st, luma);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) t[r][half * 4 + c] = s[r];
+            }
+        }
+    }
+    // 3. vertical edge at column i, lower band (rows j..j+3 belong to band j)
+    if (has_l && has_r && has_b)
+    {
+        int brow = (j / mbs) * wb;
+        evx_edge_params(p.table, (i - 1) / mbs + brow, i / mbs + brow, qp, st);
+        if (st)
+        {
+#pragma unroll
+            for (int r = 4; r < 8; ++r) evx_filter8(t[r], qp, st, luma);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+    {
+        bool rv = r < 4 ? has_t : has_b;
+        if (rv && has_l) *reinterpret_cast<uint2 *>(img + (size_t) (j - 4 + r) * w + i - 4) = make_uint2(evx_pack16(t[r][0], t[r][1]), evx_pack16(t[r][2], t[r][3]));
+        if (rv && has_r) *reinterpret_cast<uint2 *>(img + (size_t) (j - 4 + r) * w + i) = make_uint2(evx_pack16(t[r][4], t[r][5]), evx_pack16(t[r][6], t[r][7]));
+    }
+}

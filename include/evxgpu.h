@@ -1,0 +1,126 @@
+/* include/evxgpu.h -- C-ABI of the B200 pixel pipeline for the EVX-1 ("Cairo") codec.
+ *
+ * This is the device boundary introduced under the reference's frame engine.  The
+ * reference has no FFI or plugin seam of its own; its pixel pipeline is reached through
+ * two internal C++ functions, and this library replaces what those two call:
+ *
+ *   engine_encode_frame (encode.cpp:205-232)  = convert_image -> encode_slice ->
+ *       [serialize_slice, host] -> deblock_image_filter
+ *   engine_decode_frame (decode.cpp:172-198)  = [unserialize_slice, host] -> decode_slice ->
+ *       deblock_image_filter -> convert_image
+ *
+ * Everything crossing the boundary is plain data: RGB8 frames in, and per-macroblock
+ * records out (the reference's evx_block_desc table, common.h:78-95, plus the quantised
+ * coefficients of the non-copy macroblocks) -- exactly what serialize_slice reads
+ * (serialize.cpp:125-154, 288-340).  Reference frames never leave the device.
+ *
+ * One handle = one video stream = one CUDA stream.  Calls return 0 on success or an
+ * evx_status-compatible code (base.h:152-169): 1 invalid argument, 3 out of memory,
+ * 5 hardware (CUDA) failure, 8 invalid resource, 15 not ready.
+ * There is NO CPU fallback: with no usable CUDA device evxgpu_create fails with 5.
+ */
+#ifndef EVXGPU_H
+#define EVXGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Layout-identical to the reference's evx_block_desc (common.h:78-95, #pragma pack(2)):
+ * offsets type@0 target@4 mx@6 my@8 sp_pred@10 sp_amount@11 sp_index@12 q@13 var@14. */
+#pragma pack(push, 2)
+typedef struct evxgpu_block_desc
+{
+    int32_t block_type;          /* types.h:68-87: intra | motion<<1 | copy<<2 */
+    uint8_t prediction_target;   /* ring offset, 0 = the frame under construction */
+    int16_t motion_x;
+    int16_t motion_y;
+    uint8_t sp_pred;
+    uint8_t sp_amount;           /* 0 half-pel, 1 quarter-pel */
+    uint8_t sp_index;            /* direction code, motion.cpp:61-109 */
+    uint8_t q_index;
+    int16_t variance;
+} evxgpu_block_desc;
+#pragma pack(pop)
+
+/* The reference's compile-time switches (config.h:38-53) as run-time values. */
+typedef struct evxgpu_config
+{
+    int32_t ref_count;        /* EVX_REFERENCE_FRAME_COUNT: ring slots incl. the current frame, 2..8 */
+    int32_t linear_quant;     /* EVX_ENABLE_LINEAR_QUANTIZATION */
+    int32_t deblocking;       /* EVX_ENABLE_DEBLOCKING */
+    int32_t reserved;
+} evxgpu_config;
+
+#define EVXGPU_MB_COEFFS 384   /* 16x16 luma (row-major, stride 16) + 8x8 U + 8x8 V, int16 */
+
+/* kernels timed by evxgpu_get_timing() */
+enum { EVXGPU_T_CONVERT_IN = 0, EVXGPU_T_INTER_SEARCH, EVXGPU_T_WAVEFRONT, EVXGPU_T_DEBLOCK,
+       EVXGPU_T_DECODE_RECON, EVXGPU_T_CONVERT_OUT, EVXGPU_T_COUNT };
+
+typedef struct evxgpu_handle evxgpu_handle;
+
+int evxgpu_device_count(void);
+
+/* cuda_stream: a cudaStream_t to run on (e.g. torch's current stream), or NULL to own one. */
+int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, void *cuda_stream, evxgpu_handle **out);
+int evxgpu_destroy(evxgpu_handle *h);
+int evxgpu_reset(evxgpu_handle *h);                 /* zero the ring, as a fresh context (image.cpp:89) */
+int evxgpu_block_count(const evxgpu_handle *h);
+int evxgpu_synchronize(evxgpu_handle *h);
+
+/* pinned host memory for callers that want true asynchronous copies */
+void *evxgpu_host_alloc(uint64_t bytes);
+void evxgpu_host_free(void *p);
+void *evxgpu_device_alloc(uint64_t bytes);
+void evxgpu_device_free(void *p);
+int evxgpu_upload(evxgpu_handle *h, void *dst_device, const void *src_host, uint64_t bytes);
+
+/* ---- encoder: replaces convert_image + encode_slice + deblock_image_filter ----
+ * submit: queues H2D of the frame (rgb_is_device=0) or uses the device pointer, then the
+ * kernels; returns immediately.  collect: waits, then hands back the block table
+ * (block_count entries) and the coefficient records of the non-copy macroblocks in
+ * raster order (n_noncopy * 384 int16). */
+int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device,
+                         int frame_type, uint32_t frame_index, int quality);
+int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_t *records_out, uint32_t *n_noncopy);
+
+/* ---- decoder: replaces decode_slice + deblock_image_filter + convert_image ----
+ * table: block_count descriptors as unserialize_slice leaves them; records: the
+ * non-copy macroblocks' coefficients in raster order. */
+int evxgpu_decode_submit(evxgpu_handle *h, const evxgpu_block_desc *table, const int16_t *records, uint32_t n_noncopy,
+                         int frame_type, uint32_t frame_index);
+int evxgpu_decode_collect(evxgpu_handle *h, uint8_t *rgb_out, int rgb_is_device);
+
+/* ---- single stages, for parity tests and profiling ---- */
+int evxgpu_stage_convert_in(evxgpu_handle *h, const uint8_t *rgb_host);
+int evxgpu_stage_inter_search(evxgpu_handle *h, uint32_t frame_index, int quality);
+int evxgpu_stage_get_inter_result(evxgpu_handle *h, int offset, evxgpu_block_desc *desc_out, int32_t *sad_out);
+int evxgpu_stage_deblock(evxgpu_handle *h, uint32_t frame_index);
+int evxgpu_stage_set_block_table(evxgpu_handle *h, const evxgpu_block_desc *table);
+
+/* which: 0 source YUV, 2 ring slot `slot`; comp 0 Y / 1 U / 2 V; tightly pitched int16,
+ * aligned size (width,height rounded up to 16; chroma half of that). */
+int evxgpu_peek_plane(evxgpu_handle *h, int which, int slot, int comp, int16_t *out_host);
+int evxgpu_poke_plane(evxgpu_handle *h, int which, int slot, int comp, const int16_t *in_host);
+
+/* per-kernel device time of the last submitted frame, CUDA events on the handle's stream (ms) */
+int evxgpu_get_timing(evxgpu_handle *h, float *ms_out /* [EVXGPU_T_COUNT] */);
+int evxgpu_enable_timing(evxgpu_handle *h, int on);
+/* evaluated full-pel candidates / sub-pel tests since the last reset (SURVEY 8d roofline unit) */
+int evxgpu_get_counters(evxgpu_handle *h, uint64_t *fullpel, uint64_t *subpel, int reset);
+uint64_t evxgpu_launch_count(const evxgpu_handle *h);
+
+/* integer-pipe micro-benchmark (the roofline denominator MEASURED_PEAKS.json lacks):
+ * kind 0 IADD3, 1 VIADDMNMX.S16x2, 2 IDP.2A, 3 the 3:2 mix the search kernels issue.
+ * Returns tera-instructions-lanes/s (lane-ops, i.e. one packed op counts once). */
+double evxgpu_measure_int_peak(int device, int kind);
+
+const char *evxgpu_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,141 @@
+"""Parity of the CUDA pixel pipeline (through the C-ABI, include/evxgpu.h) against the
+C oracle and the committed golden vectors.  Needs a B200: run with -m gpu."""
+import numpy as np
+import pytest
+
+import goldenutil as G
+import oracleharness as O
+from cairo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a, b):
+    return all((np.asarray(x) == np.asarray(y)).all() for x, y in zip(a, b))
+
+
+def _pipeline(*a, **k):
+    from cairo_b200 import gpu
+    return gpu.Pipeline(*a, **k)
+
+
+def _run_encode(w, h, nf, R, lin, db, q, kind, seed=0, intra_every=0):
+    from cairo_b200 import gpu
+    p = _pipeline(w, h, R, lin, db)
+    o = O.Oracle(w, h, R, lin, db)
+    coef = [np.zeros((o.ah, o.aw), np.int16), np.zeros((o.ah // 2, o.aw // 2), np.int16), np.zeros((o.ah // 2, o.aw // 2), np.int16)]
+    for t in range(nf):
+        f = synth.frame(w, h, t, seed, kind)
+        ft = 0 if (t == 0 or (intra_every and t % intra_every == 0)) else 1
+        o.convert_in(f)
+        o.encode_slice(ft, t, q)
+        tbl, rec = p.encode(f, ft, t, q)
+        assert _same(p.planes(0), o.planes(0)), f"yuv frame {t}"
+        ot = o.block_table().copy()
+        assert O.tables_equal(ot, tbl), f"block table frame {t}: {np.flatnonzero(ot['block_type'] != tbl['block_type'])[:8]}"
+        gpu.records_to_planes(tbl, rec, coef, o.aw, o.ah)
+        assert _same(coef, o.planes(1)), f"coefficients frame {t}"
+        o.deblock(t)
+        assert _same(p.planes(2, t % R), o.planes(2, t % R)), f"deblocked reconstruction frame {t}"
+    p.close()
+
+
+def test_convert_in_matches_oracle():
+    for (w, h) in [(352, 288), (200, 120), (1920, 1080)]:
+        p = _pipeline(w, h)
+        o = O.Oracle(w, h)
+        f = synth.frame(w, h, 2, 3, "noise")
+        p.convert_in(f)
+        o.convert_in(f)
+        assert _same(p.planes(0), o.planes(0)), (w, h)
+        p.close()
+
+
+def test_inter_search_matches_oracle():
+    w, h, q, R = 352, 288, 16, 4
+    p = _pipeline(w, h, R)
+    o = O.Oracle(w, h, R)
+    for t in range(4):
+        f = synth.frame(w, h, t, 1, "moving")
+        o.convert_in(f); o.encode_slice(0 if t == 0 else 1, t, q); o.deblock(t)
+    for s in range(R):
+        for c in range(3):
+            p.set_plane(2, s, c, o.plane(2, s, c))
+    f = synth.frame(w, h, 4, 1, "moving")
+    o.convert_in(f)
+    p.convert_in(f)
+    p.inter_search(4, q)
+    for off in (1, 2, 3):
+        d, sad = p.inter_result(off)
+        for mb in range(p.nblocks):
+            px, py = (mb % (o.aw // 16)) * 16, (mb // (o.aw // 16)) * 16
+            od, osad = o.inter_prediction(4, q, px, py, off)
+            assert osad == sad[mb] and O.tables_equal(np.array([od]), d[mb:mb + 1]), (off, mb, od, d[mb], osad, sad[mb])
+
+
+@pytest.mark.parametrize("cfg", [(4, 0, 1), (2, 0, 1), (4, 1, 1), (4, 0, 0)])
+def test_encode_cif_all_configs(cfg):
+    _run_encode(352, 288, 5, *cfg, 16, "moving")
+
+
+@pytest.mark.parametrize("kind", ["static", "flat", "noise", "dark"])
+def test_encode_adversarial(kind):
+    _run_encode(176, 144, 5, 4, 0, 1, 16, kind, seed=1)
+
+
+@pytest.mark.parametrize("q", [1, 7, 8, 24, 31])
+def test_encode_quality_sweep(q):
+    _run_encode(176, 144, 4, 4, 0, 1, q, "moving", seed=2)
+
+
+def test_encode_unaligned_and_periodic_intra():
+    _run_encode(200, 120, 6, 4, 0, 1, 16, "moving", seed=3, intra_every=3)
+    _run_encode(200, 120, 4, 2, 0, 1, 12, "noise", seed=4)
+
+
+def test_deblock_kernel_random():
+    rng = np.random.default_rng(5)
+    w, h = 96, 80
+    p = _pipeline(w, h)
+    o = O.Oracle(w, h)
+    for trial in range(12):
+        span = [4, 16, 64, 300][trial % 4]
+        for comp in range(3):
+            pa = o.plane(2, 0, comp)
+            pa[...] = rng.integers(-span, span, size=pa.shape, dtype=np.int16) + 128
+            p.set_plane(2, 0, comp, pa)
+        t = o.block_table()
+        t["block_type"] = rng.integers(0, 8, size=t.shape[0])
+        t["q_index"] = rng.integers(1, 32, size=t.shape[0])
+        p.set_block_table(t.copy())
+        o.deblock(0)
+        p.deblock(0)
+        assert _same(p.planes(2, 0), o.planes(2, 0)), trial
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_golden_encode_and_decode(name):
+    from cairo_b200 import gpu
+    g = G.Golden(name)
+    enc = _pipeline(g.w, g.h, g.R, g.linear, g.deblocking)
+    dec = _pipeline(g.w, g.h, g.R, g.linear, g.deblocking)
+    aw, ah = enc.aw, enc.ah
+    coef = [np.zeros((ah, aw), np.int16), np.zeros((ah // 2, aw // 2), np.int16), np.zeros((ah // 2, aw // 2), np.int16)]
+    for t in range(g.frames):
+        ft = 0 if g.is_intra(t) else 1
+        tbl, rec = enc.encode(g.rgb(t), ft, t, g.q)
+        assert O.tables_equal(g.table(t), tbl), t
+        gpu.records_to_planes(tbl, rec, coef, aw, ah)
+        assert _same(coef, g.planes(t, "coef")), t
+        assert _same(enc.planes(2, t % g.R), g.planes(t, "deblocked")), t
+        # decoder: feed the golden table + golden coefficients
+        gt = g.table(t)
+        grec = gpu.planes_to_records(gt, g.planes(t, "coef"), aw)
+        rgb = dec.decode(gt, grec, ft, t)
+        assert _same(dec.planes(2, t % g.R), g.planes(t, "deblocked")), t
+        assert (rgb == g.decoded_rgb(t)).all(), t
+
+
+def test_1080p_encode_matches_oracle_two_frames():
+    """BASELINE config size; the oracle needs ~2 s per 1080p P-frame, so two frames only."""
+    _run_encode(1920, 1080, 2, 2, 0, 1, 16, "moving", seed=5)
