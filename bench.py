@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- 1080p P-frame encode throughput of the B200 pixel pipeline (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one P-frame of the configs[1] workload: 1080p synthetic sequence, quality 16, ring
+of 2 slots (= 1 past reference frame), quarter-pel search, MPEG quantiser, deblocking on.  The
+sequence's frame 0 (intra) is always part of the warm-up.  One process per GPU (torchrun for
+N>1); each rank encodes its own independent stream (no collective on the data path -- nothing
+reduces), so scaling is weak and `value` is the frames all ranks encoded / the slowest rank's
+device time.
+
+  value  : frames already resident in HBM -> pixel pipeline (K1..K4) -> records back on the host
+           (table + coefficient D2H inside the timed region, host entropy stage excluded).
+  e2e    : evx1_encoder::encode (the reference's public API, include/evx1_c.h) with HOST frames
+           in pinned memory -> EVX1 bitstream bytes: H2D, kernels, D2H and the host entropy stage.
+  --impl reference : the unmodified reference (oracle/_ref, built from /root/reference by
+           oracle/Makefile) through the same public API on the host CPU.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, QUALITY, REF_COUNT, SEQ_FRAMES = 1920, 1080, 16, 2, 60
+METRIC = "1080p P-frame encode frames/s per B200 (+1/2/4/8-GPU streams), bit-exact"
+WORKLOAD = "configs[1]: 1080p synthetic 60-frame sequence, quality 16, 1 reference frame (ring of 2), quarter-pel ME"
+# algorithmic integer ops of one full-pel candidate / one sub-pel test
+OPS_FULLPEL, OPS_SUBPEL = 1024, 2560
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------- reference arm
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    import refharness as R
+    variant = "r2"
+    if not R.available(variant):
+        # oracle/_ref travels with the snapshot; rebuild only where the reference sources exist
+        subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    if not R.available(variant):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libevxref_r2.so missing and /root/reference absent"}))
+        return 0
+    from cairo_b200 import synth
+    n_streams = max(1, args.gpus)
+    steps, warmup = args.steps, max(1, args.warmup)
+    # bounded sample: the reference needs ~1 s per 1080p P-frame per core
+    steps = min(steps, 8)
+    warmup = min(warmup, 2)
+    frames = [[synth.frame(W, H, t, s, "moving") for t in range(warmup + steps)] for s in range(n_streams)]
+    encs = []
+    for s in range(n_streams):
+        e = R.RefEncoder(variant)
+        e.set_quality(QUALITY)
+        encs.append(e)
+    times = [0.0] * n_streams
+
+    def work(s):
+        for t in range(warmup):
+            encs[s].encode(frames[s][t])
+        t0 = time.perf_counter()
+        for t in range(warmup, warmup + steps):
+            encs[s].encode(frames[s][t])
+        times[s] = time.perf_counter() - t0
+
+    th = [threading.Thread(target=work, args=(s,)) for s in range(n_streams)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    elapsed = max(times)
+    value = n_streams * steps / elapsed
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * elapsed / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "streams": n_streams, "hardware": "host CPU"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": n_streams, "kind": "reference",
+                         "sample": f"{n_streams} stream(s) x {steps} P-frames after {warmup} warm-up frames (frame 0 intra), one thread per stream, "
+                                   "unmodified reference via evx1_encoder::encode, g++ -O2"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------- our arm
+
+def cpu_baseline_sample():
+    """The reference's CPU encoder on this box's host cores, bounded sample (rank 0, N=1 only)."""
+    import refharness as R
+    from cairo_b200 import synth
+    if R.available("r2"):
+        enc = R.RefEncoder("r2")
+        enc.set_quality(QUALITY)
+        enc.encode(synth.frame(W, H, 0, 0, "moving"))
+        n = 6
+        t0 = time.perf_counter()
+        for t in range(1, 1 + n):
+            enc.encode(synth.frame(W, H, t, 0, "moving"))
+        dt = time.perf_counter() - t0
+        return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "reference",
+                "sample": f"{n} P-frames of the same 1080p sequence after the intra frame, single thread (the reference is single-threaded), oracle/_ref g++ -O2"}
+    import oracleharness as O
+    o = O.Oracle(W, H, REF_COUNT, 0, 1)
+    o.convert_in(synth.frame(W, H, 0, 0, "moving")); o.encode_slice(0, 0, QUALITY); o.serialize(); o.deblock(0)
+    n = 4
+    t0 = time.perf_counter()
+    for t in range(1, 1 + n):
+        o.convert_in(synth.frame(W, H, t, 0, "moving")); o.encode_slice(1, t, QUALITY); o.serialize(); o.deblock(t)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+            "sample": f"{n} P-frames of the same 1080p sequence, single thread, oracle/evx_oracle.c gcc -O2"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from cairo_b200 import api, gpu, synth, build
+    build.build_all()
+
+    steps, warmup = args.steps, max(3, args.warmup)
+    nframes = warmup + steps
+    seed = rank
+    # distinct frames, larger than L2 in total (60 x 6.2 MB = 373 MB > 126 MB L2)
+    uniq = min(nframes, SEQ_FRAMES)
+    host = torch.empty((uniq, H, W, 3), dtype=torch.uint8).pin_memory()
+    hnp = host.numpy()
+    for t in range(uniq):
+        hnp[t] = synth.frame(W, H, t, seed, "moving")
+    dev = host.to("cuda", non_blocking=False)
+    fidx = lambda t: t if t < uniq else 1 + (t - 1) % (uniq - 1)       # wrap inside the P-frames if K > 59
+
+    stream = torch.cuda.current_stream()
+    pipe = gpu.Pipeline(W, H, REF_COUNT, 0, 1, device=local_rank, stream=stream.cuda_stream)
+    pipe.enable_timing(True)
+    frame_bytes = W * H * 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident frames through the pixel pipeline
+    for t in range(warmup):
+        pipe.encode(int(dev[fidx(t)].data_ptr()), 0 if t == 0 else 1, t, QUALITY)
+    pipe.counters(reset=True)
+    launches0 = pipe.launch_count()
+    ksum = {k: 0.0 for k in gpu.T_NAMES}
+    d2h_bytes = 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(warmup, nframes):
+        tbl, rec = pipe.encode(int(dev[fidx(t)].data_ptr()), 1, t, QUALITY)
+        d2h_bytes += tbl.nbytes + rec.nbytes + 4 * tbl.shape[0] + 8
+        for k, v in pipe.timing().items():
+            ksum[k] += v
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    launches = pipe.launch_count() - launches0
+    fullpel, subpel = pipe.counters()
+    pipe.close()
+
+    # ---- e2e: the public API with host frames
+    enc = api.evx1_encoder(device=local_rank, ref_count=REF_COUNT)
+    enc.set_quality(QUALITY)
+    out_bits = 0
+    for t in range(warmup):
+        enc.encode((int(host[fidx(t)].data_ptr()), W, H))
+    ent_ms = gpu_ms = 0.0
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(warmup, nframes):
+        _, bits = enc.encode((int(host[fidx(t)].data_ptr()), W, H))
+        out_bits += bits
+        st = enc.stats()
+        ent_ms += st["entropy_ms"]; gpu_ms += st["gpu_ms"]
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    del enc
+
+    t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t_dev[0]), float(t_dev[1])
+
+    if rank == 0:
+        peaks, peaks_kind = measured_peaks()
+        k2_ms = ksum["inter_search"] / steps
+        k3_ms = ksum["wavefront"] / steps
+        ops_per_frame = (fullpel * OPS_FULLPEL + subpel * OPS_SUBPEL) / steps
+        # split the counted work between K2 (inter) and K3 (intra): counters are shared, so
+        # attribute by the reference's structure: K3 evaluates <= 43 full-pel + 16 sub-pel per block
+        int_peak = gpu.lib().evxgpu_measure_int_peak(local_rank, 1)
+        dominant = max(ksum, key=ksum.get)
+        search_ms = k2_ms + k3_ms
+        achieved = ops_per_frame / (search_ms * 1e-3) / 1e12 if search_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": world * steps / (dev_ms_max * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "value_scope": "frames resident in HBM -> K1..K4 -> table+coefficient records on the host; host entropy excluded",
+                       "e2e_scope": "evx1_encoder::encode, pinned host RGB -> EVX1 bitstream bytes (H2D, kernels, D2H, host Exp-Golomb+ABAC)",
+                       "l2": f"{uniq} distinct 6.2 MB frames (373 MB) cycle through, larger than the 126 MB L2"},
+            "e2e": {"value": world * steps / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes,
+                    "d2h_bytes_per_step": d2h_bytes // steps, "entropy_ms_per_step": ent_ms / steps, "gpu_ms_per_step": gpu_ms / steps,
+                    "bits_per_frame": out_bits // steps},
+            "gpu_launches": int(launches),
+            "kernel_ms_per_step": {k: v / steps for k, v in ksum.items()},
+            "roofline": {"bound": "int_alu", "kernel": "evx_inter_search + evx_wavefront (motion search)", "achieved": achieved, "peak": int_peak,
+                         "unit": "Tiop/s", "frac": achieved / int_peak if int_peak > 0 else None, "traffic": None,
+                         "peak_source": "evxgpu_measure_int_peak: dependency-free VIADDMNMX.S16x2 stream on all SMs, measured in this run",
+                         "algorithmic_ops_per_step": ops_per_frame, "fullpel_candidates_per_step": fullpel / steps, "subpel_tests_per_step": subpel / steps,
+                         "dominant_kernel_by_time": dominant,
+                         "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_kind": peaks_kind},
+            "clocks": clocks,
+        }
+        if world == 1:
+            try:
+                line["cpu_baseline"] = cpu_baseline_sample()
+            except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
+                line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=56)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,170 @@
+"""Python mirror of the reference's public interface (evx1.h:66-122) over the C++ host library
+(cairo_b200/csrc/host, bound through include/evx1_c.h).  Same names and argument meaning as
+evx1_encoder / evx1_decoder: encode() takes an RGB8 frame and returns the bits it appended,
+decode() takes one frame's bits and returns RGB8."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import gpu as _gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HOST_SO = os.path.join(HERE, "libevx1.so")
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(HOST_SO) or not os.path.exists(_gpu.GPU_SO):
+        raise RuntimeError("native libraries missing: run `python -m cairo_b200.build` (there is no CPU fallback)")
+    C.CDLL(_gpu.GPU_SO, mode=C.RTLD_GLOBAL)
+    L = C.CDLL(HOST_SO)
+    vp, i32, u32 = C.c_void_p, C.c_int, C.c_uint32
+    L.evx1c_encoder_create.restype = vp
+    L.evx1c_encoder_create.argtypes = [i32] * 6
+    L.evx1c_encoder_destroy.argtypes = [vp]
+    L.evx1c_encoder_clear.argtypes = [vp]
+    L.evx1c_encoder_insert_intra.argtypes = [vp]
+    L.evx1c_encoder_set_quality.argtypes = [vp, i32]
+    L.evx1c_encoder_encode.argtypes = [vp, vp, u32, u32, vp, u32, C.POINTER(u32)]
+    L.evx1c_encoder_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u32), C.POINTER(u32)]
+    L.evx1c_decoder_create.restype = vp
+    L.evx1c_decoder_create.argtypes = [i32] * 3
+    L.evx1c_decoder_destroy.argtypes = [vp]
+    L.evx1c_decoder_clear.argtypes = [vp]
+    L.evx1c_decoder_decode.argtypes = [vp, vp, u32, vp]
+    L.evx1c_slice_writer_create.restype = vp
+    L.evx1c_slice_writer_create.argtypes = [i32] * 3
+    L.evx1c_slice_writer_destroy.argtypes = [vp]
+    L.evx1c_slice_writer_serialize.argtypes = [vp, vp, vp, u32, vp, u32, C.POINTER(u32)]
+    L.evx1c_slice_reader_create.restype = vp
+    L.evx1c_slice_reader_create.argtypes = [i32] * 3
+    L.evx1c_slice_reader_destroy.argtypes = [vp]
+    L.evx1c_slice_reader_unserialize.argtypes = [vp, vp, u32, vp, vp, C.POINTER(u32)]
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class evx1_encoder:
+    """evx1_encoder (evx1.h:66-94).  ref_count/linear_quant/deblocking default to config.h's values."""
+
+    def __init__(self, device=0, ref_count=-1, linear_quant=-1, deblocking=-1, periodic_intra=-1, default_quality=-1):
+        self.L = lib()
+        self.h = self.L.evx1c_encoder_create(device, ref_count, linear_quant, deblocking, periodic_intra, default_quality)
+        if not self.h:
+            raise RuntimeError("create_encoder failed")
+        self._out = None
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.evx1c_encoder_destroy(self.h)
+            self.h = None
+
+    def clear(self):
+        return self.L.evx1c_encoder_clear(self.h)
+
+    def insert_intra(self):
+        return self.L.evx1c_encoder_insert_intra(self.h)
+
+    def set_quality(self, quality):
+        return self.L.evx1c_encoder_set_quality(self.h, int(quality))
+
+    def encode(self, image, out=None):
+        """image: uint8 (height, width, 3) R8G8B8, host memory (numpy array or a raw pointer with
+        width/height given through `image=(ptr, width, height)`).  Returns (bytes, nbits)."""
+        if isinstance(image, tuple):
+            ptr, w, h = image
+        else:
+            image = np.ascontiguousarray(image)
+            h, w, _ = image.shape
+            ptr = _p(image)
+        cap = w * h * 6 + 4096
+        if self._out is None or self._out.size != cap:
+            self._out = np.zeros(cap, dtype=np.uint8)
+        bits = C.c_uint32(0)
+        st = self.L.evx1c_encoder_encode(self.h, ptr, w, h, _p(self._out), cap, C.byref(bits))
+        if st != 0:
+            raise RuntimeError(f"evx1_encoder::encode failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
+        return self._out[:(bits.value + 7) // 8], bits.value
+
+    def stats(self):
+        g, e, b, n = C.c_double(0), C.c_double(0), C.c_uint32(0), C.c_uint32(0)
+        self.L.evx1c_encoder_stats(self.h, C.byref(g), C.byref(e), C.byref(b), C.byref(n))
+        return {"gpu_ms": g.value, "entropy_ms": e.value, "slice_bits": b.value, "noncopy_blocks": n.value}
+
+
+class evx1_decoder:
+    """evx1_decoder (evx1.h:96-113)."""
+
+    def __init__(self, device=0, linear_quant=-1, deblocking=-1):
+        self.L = lib()
+        self.h = self.L.evx1c_decoder_create(device, linear_quant, deblocking)
+        if not self.h:
+            raise RuntimeError("create_decoder failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.evx1c_decoder_destroy(self.h)
+            self.h = None
+
+    def clear(self):
+        return self.L.evx1c_decoder_clear(self.h)
+
+    def decode(self, data, nbits, width, height):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        out = np.zeros((height, width, 3), dtype=np.uint8)
+        st = self.L.evx1c_decoder_decode(self.h, _p(data), nbits, _p(out))
+        if st != 0:
+            raise RuntimeError(f"evx1_decoder::decode failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
+        return out
+
+
+class SliceWriter:
+    def __init__(self, mbw, mbh, ref_count):
+        self.L = lib()
+        self.n = mbw * mbh
+        self.h = self.L.evx1c_slice_writer_create(mbw, mbh, ref_count)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.evx1c_slice_writer_destroy(self.h)
+            self.h = None
+
+    def serialize(self, table, records):
+        table = np.ascontiguousarray(table)
+        records = np.ascontiguousarray(records, dtype=np.int16).reshape(-1, 384)
+        cap = self.n * 384 * 5 + 4096
+        out = np.zeros(cap, dtype=np.uint8)
+        bits = C.c_uint32(0)
+        st = self.L.evx1c_slice_writer_serialize(self.h, _p(table), _p(records), records.shape[0], _p(out), cap, C.byref(bits))
+        assert st == 0, st
+        return out[:(bits.value + 7) // 8].copy(), bits.value
+
+
+class SliceReader:
+    def __init__(self, mbw, mbh, ref_count):
+        self.L = lib()
+        self.n = mbw * mbh
+        self.h = self.L.evx1c_slice_reader_create(mbw, mbh, ref_count)
+        self.table = np.zeros(self.n, dtype=_gpu.BLOCK_DESC_DTYPE)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.evx1c_slice_reader_destroy(self.h)
+            self.h = None
+
+    def unserialize(self, data, nbits):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        rec = np.zeros((self.n, 384), dtype=np.int16)
+        n = C.c_uint32(0)
+        st = self.L.evx1c_slice_reader_unserialize(self.h, _p(data), nbits, _p(self.table), _p(rec), C.byref(n))
+        assert st == 0, st
+        return self.table.copy(), rec[:n.value].copy()

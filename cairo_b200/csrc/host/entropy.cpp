@@ -1,0 +1,347 @@
+// entropy.cpp -- see entropy.h.
+#include "entropy.h"
+
+#include <string.h>
+
+namespace evx {
+
+namespace {
+
+enum { T_INTRA = 1, T_MOTION = 2, T_COPY = 4 };      // types.h:68-71
+
+const uint32_t AB_MAX = 0xFFFFu, AB_HALF = 0x7FFFu, AB_QTR = 0x3FFFu, AB_3QTR = 3u * 0x3FFFu;   // abac.cpp:4-10
+
+inline int bit_length(uint32_t v) { return 32 - __builtin_clz(v); }
+
+// 8x8 zig-zag (scan.h:60-70), built by walking the anti-diagonals; entries are offsets into a
+// stride-16 (luma record) or stride-8 (chroma record) block
+struct zigzag_tables
+{
+    uint8_t pos[64];          // row*8+col
+    uint8_t luma[64];         // row*16+col
+    zigzag_tables()
+    {
+        int n = 0;
+        for (int s = 0; s < 15; ++s)
+        {
+            int lo = s < 8 ? 0 : s - 7, hi = s < 8 ? s : 7;
+            for (int k = lo; k <= hi; ++k)
+            {
+                int row = (s & 1) ? k : s - k, col = s - row;
+                pos[n] = (uint8_t) (row * 8 + col);
+                luma[n] = (uint8_t) (row * 16 + col);
+                ++n;
+            }
+        }
+    }
+};
+const zigzag_tables ZZ;
+
+// ---------------------------------------------------------------- encoder side
+
+class abac_writer
+{
+    uint32_t low_, high_, e3_, h0_, h1_;
+    uint64_t acc_;
+    uint32_t nacc_;
+    uint8_t *out_;
+    size_t pos_;
+
+    inline void put(uint32_t bit)
+    {
+        acc_ |= (uint64_t) bit << nacc_;
+        if (++nacc_ == 64) { memcpy(out_ + pos_, &acc_, 8); pos_ += 8; acc_ = 0; nacc_ = 0; }
+    }
+    inline void emit(uint32_t bit)        // write_bit + flush_inverse_bits, abac.cpp:156-178
+    {
+        put(bit);
+        for (; e3_; --e3_) put(bit ^ 1u);
+    }
+
+public:
+    explicit abac_writer(uint8_t *out) : low_(0), high_(AB_MAX), e3_(0), h0_(1), h1_(1), acc_(0), nacc_(0), out_(out), pos_(0) {}
+
+    size_t bytes_pending() const { return pos_ + 8; }
+    void rebase(uint8_t *out) { out_ = out; }
+
+    // encode_symbol + resolve_encode_scaling, abac.cpp:97-121, 180-224
+    inline void encode(uint32_t bit)
+    {
+        const uint32_t range = high_ - low_;
+        const uint32_t mid = low_ + (h0_ <= 0xFFFFu ? (range * h0_) / (h0_ + h1_) : (uint32_t) (((uint64_t) range * h0_) / (h0_ + h1_)));
+        if (bit) { low_ = mid + 1; h1_++; } else { high_ = mid; h0_++; }
+        for (;;)
+        {
+            if (((high_ ^ low_) & 0x8000u) == 0)
+            {
+                const uint32_t msb = high_ >> 15;
+                low_ -= msb << 15; high_ -= msb << 15;
+                emit(msb);
+            }
+            else if (high_ <= AB_3QTR && low_ > AB_QTR) { high_ -= AB_QTR + 1; low_ -= AB_QTR + 1; e3_++; }
+            else break;
+            high_ = ((high_ << 1) & AB_MAX) | 1u;
+            low_ = (low_ << 1) & AB_MAX;
+        }
+    }
+
+    inline void encode_bits_lsb(uint32_t v, int n) { for (int k = 0; k < n; ++k) encode((v >> k) & 1u); }
+
+    // Exp-Golomb (golomb.cpp:8-91): n-1 zeros, then x MSB-first
+    inline void encode_code(uint32_t x)
+    {
+        const int n = bit_length(x);
+        for (int i = 0; i < n - 1; ++i) encode(0);
+        for (int i = n - 1; i >= 0; --i) encode((x >> i) & 1u);
+    }
+    inline void encode_unsigned(uint32_t v) { encode_code(v + 1); }
+    inline void encode_signed(int v) { encode_code(v == 0 ? 1u : (((uint32_t) (v < 0 ? -v : v) << 1) | (v < 0 ? 1u : 0u))); }
+
+    // flush_encoder, abac.cpp:281-313.  Returns the total number of bits written.
+    uint64_t finish()
+    {
+        e3_++;
+        emit(low_ < AB_QTR ? 0u : 1u);
+        uint64_t bits = (uint64_t) pos_ * 8 + nacc_;
+        memcpy(out_ + pos_, &acc_, 8);
+        return bits;
+    }
+};
+
+// stream.cpp:550-581 + serialize.cpp:10-23: one 8x8 block of a record
+inline void put_block(abac_writer &w, const int16_t *blk, const uint8_t *zz, int16_t last_dc)
+{
+    const int16_t dc = (int16_t) (blk[0] - last_dc);
+    int run = 63;
+    for (; run >= 1; --run) if (blk[zz[run]]) break;
+    if (run == 0 && dc == 0) run = -1;
+    run++;
+    w.encode_unsigned((uint32_t) run);
+    if (run > 0)
+    {
+        w.encode_signed(dc);
+        for (int k = 1; k < run; ++k) w.encode_signed(blk[zz[k]]);
+    }
+}
+
+}  // namespace
+
+void slice_writer::configure(int mbw, int mbh, int ref_count)
+{
+    mbw_ = mbw; mbh_ = mbh;
+    target_bits_ = bit_length((uint32_t) (ref_count & 0xFF)) - 1;     // log2((uint8) R), serialize.cpp:179
+    dc_.resize((size_t) mbw * mbh);
+    // worst case: every coefficient an escape-length code; grown on demand below
+    buf_.assign((size_t) mbw * mbh * 384 * 5 + 4096, 0);
+}
+
+void slice_writer::reset() { dc_.resize((size_t) mbw_ * mbh_); }
+
+uint32_t slice_writer::serialize(const evxgpu_block_desc *t, const int16_t *records, uint32_t n_noncopy)
+{
+    const int n = mbw_ * mbh_;
+    abac_writer w(buf_.data());
+
+    // refresh the DC mirror with this frame's non-copy macroblocks (serialisation reads the
+    // coefficient planes AFTER the whole slice was encoded, encode.cpp:214-220)
+    {
+        uint32_t k = 0;
+        for (int i = 0; i < n; ++i)
+        {
+            if (t[i].block_type & T_COPY) continue;
+            const int16_t *r = records + (size_t) k * 384;
+            dc_.y_tr[i] = r[8]; dc_.y_bl[i] = r[8 * 16]; dc_.u[i] = r[256]; dc_.v[i] = r[320];
+            ++k;
+        }
+        if (k != n_noncopy) return 0;
+    }
+
+    // block table by field, serialize.cpp:156-317
+    for (int i = 0; i < n; ++i) w.encode_bits_lsb((uint32_t) t[i].block_type, 3);
+    for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_INTRA)) w.encode_bits_lsb(t[i].prediction_target, target_bits_);
+    int last = 0;
+    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) { w.encode_signed((int16_t) (t[i].motion_x - last)); last = t[i].motion_x; }
+    last = 0;
+    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) { w.encode_signed((int16_t) (t[i].motion_y - last)); last = t[i].motion_y; }
+    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) w.encode(t[i].sp_pred & 1u);
+    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) w.encode(t[i].sp_amount & 1u);
+    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) w.encode_bits_lsb(t[i].sp_index, 3);
+    last = 0;
+    for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_COPY)) { w.encode_signed((int16_t) (t[i].q_index - last)); last = t[i].q_index; }
+
+    // residuals: all luma, then all U, then all V (serialize.cpp:125-154)
+    for (int comp = 0; comp < 3; ++comp)
+    {
+        uint32_t k = 0;
+        int idx = 0;
+        for (int by = 0; by < mbh_; ++by)
+        for (int bx = 0; bx < mbw_; ++bx, ++idx)
+        {
+            if (t[idx].block_type & T_COPY) continue;
+            const int16_t *r = records + (size_t) (k++) * 384;
+            if (comp == 0)
+            {
+                int16_t last_dc = bx >= 1 ? dc_.y_tr[idx - 1] : (by >= 1 ? dc_.y_bl[idx - mbw_] : 0);
+                put_block(w, r, ZZ.luma, last_dc);                     // serialize.cpp:25-34
+                put_block(w, r + 8, ZZ.luma, r[0]);
+                put_block(w, r + 8 * 16, ZZ.luma, r[0]);
+                put_block(w, r + 8 * 16 + 8, ZZ.luma, r[8 * 16]);
+            }
+            else
+            {
+                const std::vector<int16_t> &m = comp == 1 ? dc_.u : dc_.v;
+                int16_t last_dc = bx >= 1 ? m[idx - 1] : (by >= 1 ? m[idx - mbw_] : 0);
+                put_block(w, r + 256 + (comp - 1) * 64, ZZ.pos, last_dc);
+            }
+            if (w.bytes_pending() + 8192 > buf_.size()) { buf_.resize(buf_.size() * 2); w.rebase(buf_.data()); }
+        }
+    }
+    return (uint32_t) w.finish();
+}
+
+// ---------------------------------------------------------------- decoder side
+
+namespace {
+
+class abac_reader
+{
+    const uint8_t *data_;
+    uint32_t pos_, end_;
+    uint32_t low_, high_, value_, h0_, h1_;
+
+    inline bool empty() const { return pos_ >= end_; }
+    inline uint32_t get() { uint32_t b = (data_[pos_ >> 3] >> (pos_ & 7)) & 1u; pos_++; return b; }
+
+public:
+    abac_reader(const uint8_t *data, uint32_t pos, uint32_t end) : data_(data), pos_(pos), end_(end), low_(0), high_(AB_MAX), value_(0), h0_(1), h1_(1)
+    {   // start_decode, abac.cpp:398-420: past the end the LAST bit read is repeated
+        uint32_t bit = 0;
+        for (int i = 0; i < 16; ++i) { if (!empty()) bit = get(); value_ = (value_ << 1) | bit; }
+    }
+
+    // decode_symbol + resolve_decode_scaling, abac.cpp:123-154, 226-279
+    inline uint32_t decode()
+    {
+        const uint32_t range = high_ - low_;
+        const uint32_t mid = low_ + (uint32_t) (((uint64_t) range * h0_) / (h0_ + h1_));
+        uint32_t out = 0;
+        if (value_ >= low_ && value_ <= mid) { high_ = mid; h0_++; }
+        else if (value_ > mid && value_ <= high_) { low_ = mid + 1; h1_++; out = 1; }
+        uint32_t bit = 0;
+        for (;;)
+        {
+            if (high_ <= AB_HALF) { }
+            else if (low_ > AB_HALF) { high_ -= AB_HALF + 1; low_ -= AB_HALF + 1; value_ -= AB_HALF + 1; }
+            else if (high_ <= AB_3QTR && low_ > AB_QTR) { high_ -= AB_QTR + 1; low_ -= AB_QTR + 1; value_ -= AB_QTR + 1; }
+            else break;
+            if (!empty()) bit = get();
+            high_ = ((high_ << 1) & AB_MAX) | 1u;
+            low_ = (low_ << 1) & AB_MAX;
+            value_ = ((value_ << 1) & AB_MAX) | bit;
+        }
+        return out;
+    }
+
+    inline uint32_t decode_bits_lsb(int n) { uint32_t v = 0; for (int k = 0; k < n; ++k) v |= decode() << k; return v; }
+
+    // stream.cpp:292-436
+    inline uint16_t decode_code(int *nbits)
+    {
+        int zeros = 0;
+        uint32_t bit = decode();
+        while (!bit && zeros < 48) { zeros++; bit = decode(); }
+        uint16_t r = 0;
+        for (int i = 0; i < zeros + 1; ++i) { r = (uint16_t) ((r << 1) | (bit & 1u)); if (i < zeros) bit = decode(); }
+        *nbits = zeros + 1;
+        return r;
+    }
+    inline uint16_t decode_unsigned() { int n; return (uint16_t) (decode_code(&n) - 1); }
+    inline int16_t decode_signed()
+    {
+        int n;
+        int16_t r = (int16_t) decode_code(&n);
+        int16_t sign = (int16_t) (1 - 2 * (r & 1));
+        r = (int16_t) (sign * ((r >> 1) & 0x7FFF));
+        if (n + (n - 1) > 0x20) r = (int16_t) (r | 0x8000);
+        return r;
+    }
+};
+
+// stream.cpp:583-605 + unserialize.cpp:10-22
+inline void get_block(abac_reader &rd, int16_t *blk, int stride, int16_t last_dc)
+{
+    for (int j = 0; j < 8; ++j) memset(blk + j * stride, 0, 16);
+    uint16_t run = rd.decode_unsigned();
+    for (uint32_t k = 0; k < run && k < 64; ++k)
+    {
+        int p = ZZ.pos[k];
+        blk[(p >> 3) * stride + (p & 7)] = rd.decode_signed();
+    }
+    blk[0] = (int16_t) (blk[0] + last_dc);
+}
+
+}  // namespace
+
+void slice_reader::configure(int mbw, int mbh, int ref_count)
+{
+    mbw_ = mbw; mbh_ = mbh;
+    target_bits_ = bit_length((uint32_t) (ref_count & 0xFF)) - 1;
+    dc_.resize((size_t) mbw * mbh);
+}
+
+void slice_reader::reset() { dc_.resize((size_t) mbw_ * mbh_); }
+
+int slice_reader::unserialize(const uint8_t *data, uint32_t pos, uint32_t end, evxgpu_block_desc *t, int16_t *records, uint32_t *n_noncopy)
+{
+    const int n = mbw_ * mbh_;
+    abac_reader rd(data, pos, end);
+    for (int i = 0; i < n; ++i) t[i].block_type = (t[i].block_type & ~7) | (int32_t) rd.decode_bits_lsb(3);
+    for (int i = 0; i < n; ++i)
+        if (!(t[i].block_type & T_INTRA))
+            t[i].prediction_target = (uint8_t) ((t[i].prediction_target & ~((1u << target_bits_) - 1u)) | rd.decode_bits_lsb(target_bits_));
+    int16_t last = 0;
+    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) { t[i].motion_x = (int16_t) (last + rd.decode_signed()); last = t[i].motion_x; }
+    last = 0;
+    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) { t[i].motion_y = (int16_t) (last + rd.decode_signed()); last = t[i].motion_y; }
+    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) t[i].sp_pred = (uint8_t) ((t[i].sp_pred & 0xFE) | rd.decode());
+    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) t[i].sp_amount = (uint8_t) ((t[i].sp_amount & 0xFE) | rd.decode());
+    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) t[i].sp_index = (uint8_t) ((t[i].sp_index & ~7u) | rd.decode_bits_lsb(3));
+    last = 0;
+    for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_COPY)) { t[i].q_index = (uint8_t) (rd.decode_signed() + last); last = t[i].q_index; }
+
+    uint32_t count = 0;
+    for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_COPY)) count++;
+    *n_noncopy = count;
+
+    for (int comp = 0; comp < 3; ++comp)
+    {
+        uint32_t k = 0;
+        int idx = 0;
+        for (int by = 0; by < mbh_; ++by)
+        for (int bx = 0; bx < mbw_; ++bx, ++idx)
+        {
+            if (t[idx].block_type & T_COPY) continue;
+            int16_t *r = records + (size_t) (k++) * 384;
+            if (comp == 0)
+            {
+                int16_t last_dc = bx >= 1 ? dc_.y_tr[idx - 1] : (by >= 1 ? dc_.y_bl[idx - mbw_] : 0);
+                get_block(rd, r, 16, last_dc);                         // unserialize.cpp:24-33
+                get_block(rd, r + 8, 16, r[0]);
+                get_block(rd, r + 8 * 16, 16, r[0]);
+                get_block(rd, r + 8 * 16 + 8, 16, r[8 * 16]);
+                dc_.y_tr[idx] = r[8]; dc_.y_bl[idx] = r[8 * 16];
+            }
+            else
+            {
+                std::vector<int16_t> &m = comp == 1 ? dc_.u : dc_.v;
+                int16_t last_dc = bx >= 1 ? m[idx - 1] : (by >= 1 ? m[idx - mbw_] : 0);
+                int16_t *b = r + 256 + (comp - 1) * 64;
+                get_block(rd, b, 8, last_dc);
+                m[idx] = b[0];
+            }
+        }
+    }
+    return 0;
+}
+
+}  // namespace evx

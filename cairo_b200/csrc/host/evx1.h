@@ -1,0 +1,167 @@
+// evx1.h -- public API of the B200 build, source-compatible with the reference's evx1.h
+// (evx1.h:66-122) and bitstream.h (bitstream.h:43-92): same namespace, class names, method
+// names, argument meaning and status codes, so a caller of the reference recompiles against
+// this header unchanged.  The pixel pipeline behind encode()/decode() runs on the GPU
+// (include/evxgpu.h); only the serial entropy stage runs on the host.
+//
+// Additions (not in the reference): evx1_config + create_encoder_ex/create_decoder_ex make the
+// reference's compile-time switches (config.h:38-53) run-time values, bit_stream gains
+// query_read_index()/query_write_index(), and the encoder exposes last_frame_stats().
+#ifndef CAIRO_B200_EVX1_H
+#define CAIRO_B200_EVX1_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+namespace evx {
+
+typedef int64_t int64;
+typedef int32_t int32;
+typedef int16_t int16;
+typedef int8_t int8;
+typedef uint64_t uint64;
+typedef uint32_t uint32;
+typedef uint16_t uint16;
+typedef uint8_t uint8;
+
+typedef uint8 evx_status;          // base.h:150
+
+}  // namespace evx
+
+// status codes, base.h:152-169
+#define EVX_SUCCESS                    (0)
+#define EVX_ERROR_INVALIDARG           (1)
+#define EVX_ERROR_NOTIMPL              (2)
+#define EVX_ERROR_OUTOFMEMORY          (3)
+#define EVX_ERROR_UNDEFINED            (4)
+#define EVX_ERROR_HARDWAREFAIL         (5)
+#define EVX_ERROR_INVALID_INDEX        (6)
+#define EVX_ERROR_CAPACITY_LIMIT       (7)
+#define EVX_ERROR_INVALID_RESOURCE     (8)
+#define EVX_ERROR_OPERATION_TIMEDOUT   (9)
+#define EVX_ERROR_EXECUTION_FAILURE    (10)
+#define EVX_ERROR_NOT_READY            (15)
+
+#define evx_succeeded(status) ((status) == EVX_SUCCESS)
+#define evx_failed(status) (!evx_succeeded(status))
+
+namespace evx {
+
+// LSB-first bit FIFO (bitstream.h:43-92).  Capacity and indices are in BITS.
+class bit_stream
+{
+    uint32 read_index;
+    uint32 write_index;
+    uint32 data_capacity;      // bytes
+    uint8 *data_store;
+
+public:
+    bit_stream();
+    bit_stream(uint32 size);
+    bit_stream(void *bytes, uint32 size);
+    virtual ~bit_stream();
+
+    uint8 *query_data() const;
+    uint32 query_capacity() const;
+    uint32 query_occupancy() const;
+    uint32 query_byte_occupancy() const;
+    uint32 resize_capacity(uint32 size_in_bits);
+    evx_status assign(void *bytes, uint32 size);
+
+    void seek(uint32 offset);      // read index only (and it overshoots exactly like bitstream.cpp:87-95)
+    void clear();
+    void empty();
+    bool is_empty() const;
+    bool is_full() const;
+
+    evx_status write_byte(uint8 value);
+    evx_status write_bit(uint8 value);
+    evx_status write_bytes(void *data, uint32 count);
+    evx_status write_bits(void *data, uint32 count);
+
+    evx_status read_byte(void *data);
+    evx_status read_bit(void *data);
+    evx_status read_bytes(void *data, uint32 count);
+    evx_status read_bits(void *data, uint32 count);
+
+    evx_status peek_byte(void *data);
+    evx_status peek_bit(void *data);
+    evx_status peek_bytes(void *data, uint32 count);
+    evx_status peek_bits(void *data, uint32 count);
+
+    // additions
+    uint32 query_read_index() const { return read_index; }
+    uint32 query_write_index() const { return write_index; }
+
+private:
+    bit_stream(const bit_stream &);
+    bit_stream &operator=(const bit_stream &);
+};
+
+enum EVX_PEEK_STATE      // evx1.h:53-62
+{
+    EVX_PEEK_SOURCE = 0,
+    EVX_PEEK_PREDICTION,
+    EVX_PEEK_BLOCK_TABLE,
+    EVX_PEEK_QUANT_TABLE,
+    EVX_PEEK_SPMP_TABLE,
+    EVX_PEEK_BLOCK_VARIANCE,
+    EVX_PEEK_DESTINATION,
+};
+
+// addition: per-frame timing/size facts of the last encode() call
+struct evx1_frame_stats
+{
+    double gpu_ms;           // submit -> records on the host (H2D, kernels, D2H)
+    double entropy_ms;       // host serialisation (Exp-Golomb + ABAC)
+    uint32 slice_bits;
+    uint32 noncopy_blocks;
+};
+
+class evx1_encoder
+{
+protected:
+    virtual ~evx1_encoder() {}
+
+public:
+    virtual evx_status clear() = 0;
+    virtual evx_status insert_intra() = 0;
+    virtual evx_status set_quality(uint8 quality) = 0;                                  // clipped to 1..31
+    virtual evx_status encode(void *image, uint32 width, uint32 height, bit_stream *output) = 0;   // R8G8B8 in, appends to output
+    virtual evx_status peek(EVX_PEEK_STATE peek_state, void *output) = 0;              // debug views: not implemented here
+    virtual evx_status last_frame_stats(evx1_frame_stats *out) = 0;                    // addition
+};
+
+class evx1_decoder
+{
+protected:
+    virtual ~evx1_decoder() {}
+
+public:
+    virtual evx_status clear() = 0;
+    virtual evx_status decode(bit_stream *input, void *output) = 0;
+};
+
+// addition: the reference's config.h switches at run time
+struct evx1_config
+{
+    int32 device;            // CUDA device ordinal
+    int32 ref_count;         // EVX_REFERENCE_FRAME_COUNT (default 4)
+    int32 linear_quant;      // EVX_ENABLE_LINEAR_QUANTIZATION (default 0)
+    int32 deblocking;        // EVX_ENABLE_DEBLOCKING (default 1)
+    int32 periodic_intra;    // EVX_PERIODIC_INTRA_RATE (default 3600; 0 = never)
+    int32 default_quality;   // EVX_DEFAULT_QUALITY_LEVEL (default 8)
+};
+
+void default_config(evx1_config *cfg);
+
+evx_status create_encoder(evx1_encoder **output);       // evx1.h:118-122
+evx_status create_decoder(evx1_decoder **output);
+evx_status destroy_encoder(evx1_encoder *input);
+evx_status destroy_decoder(evx1_decoder *input);
+evx_status create_encoder_ex(const evx1_config &cfg, evx1_encoder **output);
+evx_status create_decoder_ex(const evx1_config &cfg, evx1_decoder **output);
+
+}  // namespace evx
+
+#endif

@@ -1,0 +1,285 @@
+// evx1_session.cpp -- encoder / decoder sessions behind the public API.  They mirror
+// evx1_encoder_impl (evx1enc.cpp:11-168) and evx1_decoder_impl (evx1dec.cpp:10-135): stream
+// header once, a 10-byte frame descriptor per frame, lazy initialisation on the first frame,
+// frame counter, periodic intra.  Where the reference calls engine_encode_frame /
+// engine_decode_frame (encode.cpp:205, decode.cpp:172) these sessions call the device
+// library (include/evxgpu.h) for the pixel pipeline and entropy.cpp for the slice.
+#include <string.h>
+
+#include <chrono>
+#include <new>
+#include <vector>
+
+#include "entropy.h"
+#include "evx1.h"
+#include "evxgpu.h"
+
+namespace evx {
+
+namespace {
+
+const uint16 kVersionWord = (2u << 8) | 47u;        // EVX_VERSION_WORD(2, 47), version.h:36-41
+
+#pragma pack(push, 2)
+struct stream_header          // evx_header, common.h:53-62 (14 bytes; byte 7 is padding)
+{
+    uint8 magic[4];
+    uint16 size;
+    uint8 ref_count;
+    uint16 version;
+    uint16 frame_width;
+    uint16 frame_height;
+};
+struct frame_desc             // evx_frame, common.h:68-74 (10 bytes)
+{
+    uint32 type;              // EVX_FRAME_TYPE: 0 intra, 1 inter
+    uint32 index;
+    uint16 quality;
+};
+#pragma pack(pop)
+static_assert(sizeof(stream_header) == 14, "evx_header is 14 bytes on the wire");
+static_assert(sizeof(frame_desc) == 10, "evx_frame is 10 bytes on the wire");
+
+inline int clip(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+evx_status map_gpu_status(int rc)
+{
+    if (rc == 0) return EVX_SUCCESS;
+    if (rc == 3) return EVX_ERROR_OUTOFMEMORY;
+    if (rc == 1) return EVX_ERROR_INVALIDARG;
+    return EVX_ERROR_HARDWAREFAIL;
+}
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------- encoder
+
+class encoder_session : public evx1_encoder
+{
+    evx1_config cfg_;
+    bool initialized_;
+    frame_desc frame_;
+    stream_header header_;
+    evxgpu_handle *gpu_;
+    slice_writer writer_;
+    std::vector<evxgpu_block_desc> table_;
+    std::vector<int16> records_;
+    evx1_frame_stats stats_;
+
+    void clear_frame()          // clear_frame, common.cpp:50-64
+    {
+        frame_.type = 0;
+        frame_.index = 0;
+        frame_.quality = (uint16) clip(cfg_.default_quality, 1, 100);
+    }
+
+    evx_status initialize(uint32 width, uint32 height)      // evx1enc.cpp:66-90
+    {
+        if (initialized_) return EVX_ERROR_INVALID_RESOURCE;
+        memset(&header_, 0, sizeof(header_));
+        header_.magic[0] = 'E'; header_.magic[1] = 'V'; header_.magic[2] = 'X'; header_.magic[3] = '1';
+        header_.ref_count = (uint8) cfg_.ref_count;
+        header_.version = kVersionWord;
+        header_.frame_width = (uint16) width;
+        header_.frame_height = (uint16) height;
+        header_.size = sizeof(stream_header);
+        evxgpu_config gc = { cfg_.ref_count, cfg_.linear_quant, cfg_.deblocking, 0 };
+        int rc = evxgpu_create(cfg_.device, (int) width, (int) height, &gc, NULL, &gpu_);
+        if (rc) return map_gpu_status(rc);
+        int mbw = (int) ((width + 15) / 16), mbh = (int) ((height + 15) / 16);
+        writer_.configure(mbw, mbh, cfg_.ref_count);
+        table_.assign((size_t) mbw * mbh, evxgpu_block_desc());
+        records_.assign((size_t) mbw * mbh * EVXGPU_MB_COEFFS, 0);
+        initialized_ = true;
+        return EVX_SUCCESS;
+    }
+
+public:
+    explicit encoder_session(const evx1_config &cfg) : cfg_(cfg), initialized_(false), gpu_(NULL)
+    {
+        memset(&stats_, 0, sizeof(stats_));
+        memset(&header_, 0, sizeof(header_));
+        clear_frame();
+    }
+    ~encoder_session() { clear(); }
+
+    evx_status clear()                                       // evx1enc.cpp:27-40
+    {
+        if (!initialized_) return EVX_SUCCESS;
+        clear_frame();
+        if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }
+        initialized_ = false;
+        return EVX_SUCCESS;
+    }
+
+    evx_status insert_intra() { frame_.type = 0; return EVX_SUCCESS; }                      // evx1enc.cpp:42-51
+
+    evx_status set_quality(uint8 quality) { frame_.quality = (uint16) clip(quality, 1, 31); return EVX_SUCCESS; }   // evx1enc.cpp:53-64
+
+    evx_status encode(void *image, uint32 width, uint32 height, bit_stream *output)        // evx1enc.cpp:92-156
+    {
+        if (!output || !width || !height || !image) return EVX_ERROR_INVALIDARG;
+        if (!initialized_)
+        {
+            if ((width & 1) || (height & 1) || width > 0xFFFF || height > 0xFFFF) return EVX_ERROR_EXECUTION_FAILURE;   // convert.cpp:126-130
+            evx_status st = initialize(width, height);
+            if (evx_failed(st)) return EVX_ERROR_EXECUTION_FAILURE;
+            if (evx_failed(output->write_bytes(&header_, sizeof(header_)))) return EVX_ERROR_EXECUTION_FAILURE;
+        }
+        if (width != header_.frame_width || height != header_.frame_height) return EVX_ERROR_INVALID_RESOURCE;
+        if (evx_failed(output->write_bytes(&frame_, sizeof(frame_)))) return EVX_ERROR_EXECUTION_FAILURE;
+
+        // engine_encode_frame, encode.cpp:205-232
+        double t0 = now_ms();
+        int rc = evxgpu_encode_submit(gpu_, static_cast<const uint8 *>(image), 0, (int) frame_.type, frame_.index, (int) frame_.quality);
+        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+        uint32 n_noncopy = 0;
+        rc = evxgpu_encode_collect(gpu_, table_.data(), records_.data(), &n_noncopy);
+        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+        double t1 = now_ms();
+        uint32 bits = writer_.serialize(table_.data(), records_.data(), n_noncopy);
+        if (!bits) return EVX_ERROR_EXECUTION_FAILURE;
+        evx_status wst = output->write_bits(const_cast<uint8 *>(writer_.data()), bits);
+        double t2 = now_ms();
+        stats_.gpu_ms = t1 - t0; stats_.entropy_ms = t2 - t1; stats_.slice_bits = bits; stats_.noncopy_blocks = n_noncopy;
+        // serialize_slice's write failures are ignored by the reference; report ours
+        if (evx_failed(wst)) return EVX_ERROR_EXECUTION_FAILURE;
+
+        frame_.type = 1;                                                                   // EVX_ALLOW_INTER_FRAMES
+        if (cfg_.periodic_intra > 0 && 0 == ((frame_.index + 1) % (uint32) cfg_.periodic_intra)) insert_intra();
+        frame_.index++;
+        return EVX_SUCCESS;
+    }
+
+    evx_status peek(EVX_PEEK_STATE, void *) { return EVX_ERROR_NOTIMPL; }                  // debug visualisers: out of scope
+
+    evx_status last_frame_stats(evx1_frame_stats *out) { if (!out) return EVX_ERROR_INVALIDARG; *out = stats_; return EVX_SUCCESS; }
+};
+
+// ---------------------------------------------------------------- decoder
+
+class decoder_session : public evx1_decoder
+{
+    evx1_config cfg_;
+    bool initialized_;
+    frame_desc frame_;
+    stream_header header_;
+    evxgpu_handle *gpu_;
+    slice_reader reader_;
+    std::vector<evxgpu_block_desc> table_;
+    std::vector<int16> records_;
+
+    void clear_frame() { frame_.type = 0; frame_.index = 0; frame_.quality = (uint16) clip(cfg_.default_quality, 1, 100); }
+
+    evx_status initialize(bit_stream *input)                 // evx1dec.cpp:41-69, verify_header common.cpp:25-43
+    {
+        if (initialized_) return EVX_ERROR_INVALID_RESOURCE;
+        if (evx_failed(input->read_bytes(&header_, sizeof(header_)))) return EVX_ERROR_INVALID_RESOURCE;
+        if (header_.magic[0] != 'E' || header_.magic[1] != 'V' || header_.magic[2] != 'X' || header_.magic[3] != '1') return EVX_ERROR_INVALID_RESOURCE;
+        if (header_.version != kVersionWord || header_.size != sizeof(stream_header)) return EVX_ERROR_INVALID_RESOURCE;
+        // the reference rejects any ring size but its compiled one; here the header decides
+        if (header_.ref_count < 2 || header_.ref_count > 8) return EVX_ERROR_INVALID_RESOURCE;
+        if (!header_.frame_width || !header_.frame_height || (header_.frame_width & 1) || (header_.frame_height & 1)) return EVX_ERROR_INVALID_RESOURCE;
+        evxgpu_config gc = { header_.ref_count, cfg_.linear_quant, cfg_.deblocking, 0 };
+        int rc = evxgpu_create(cfg_.device, header_.frame_width, header_.frame_height, &gc, NULL, &gpu_);
+        if (rc) return map_gpu_status(rc);
+        int mbw = (header_.frame_width + 15) / 16, mbh = (header_.frame_height + 15) / 16;
+        reader_.configure(mbw, mbh, header_.ref_count);
+        evxgpu_block_desc zero;
+        memset(&zero, 0, sizeof(zero));
+        table_.assign((size_t) mbw * mbh, zero);             // aligned_zero_memory, common.cpp:146
+        records_.assign((size_t) mbw * mbh * EVXGPU_MB_COEFFS, 0);
+        initialized_ = true;
+        return EVX_SUCCESS;
+    }
+
+public:
+    explicit decoder_session(const evx1_config &cfg) : cfg_(cfg), initialized_(false), gpu_(NULL)
+    {
+        memset(&header_, 0, sizeof(header_));
+        clear_frame();
+    }
+    ~decoder_session() { clear(); }
+
+    evx_status clear()                                       // evx1dec.cpp:27-39
+    {
+        if (!initialized_) return EVX_SUCCESS;
+        clear_frame();
+        if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }
+        initialized_ = false;
+        return EVX_SUCCESS;
+    }
+
+    evx_status decode(bit_stream *input, void *output)       // evx1dec.cpp:87-123
+    {
+        if (!input || !output) return EVX_ERROR_INVALIDARG;
+        if (!initialized_ && evx_failed(initialize(input))) return EVX_ERROR_EXECUTION_FAILURE;
+        frame_desc incoming;
+        if (evx_failed(input->read_bytes(&incoming, sizeof(incoming)))) return EVX_ERROR_EXECUTION_FAILURE;
+        if (incoming.index != frame_.index) return EVX_ERROR_EXECUTION_FAILURE;          // evx1dec.cpp:77-80
+        frame_ = incoming;
+
+        // engine_decode_frame, decode.cpp:172-198
+        uint32 n_noncopy = 0;
+        if (reader_.unserialize(input->query_data(), input->query_read_index(), input->query_write_index(), table_.data(), records_.data(), &n_noncopy))
+            return EVX_ERROR_EXECUTION_FAILURE;
+        int rc = evxgpu_decode_submit(gpu_, table_.data(), records_.data(), n_noncopy, (int) frame_.type, frame_.index);
+        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+        rc = evxgpu_decode_collect(gpu_, static_cast<uint8 *>(output), 0);
+        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+        frame_.index++;
+        input->empty();
+        return EVX_SUCCESS;
+    }
+};
+
+}  // namespace
+
+void default_config(evx1_config *cfg)                        // config.h:38-53
+{
+    cfg->device = 0;
+    cfg->ref_count = 4;
+    cfg->linear_quant = 0;
+    cfg->deblocking = 1;
+    cfg->periodic_intra = 3600;
+    cfg->default_quality = 8;
+}
+
+static bool config_ok(const evx1_config &c) { return c.ref_count >= 2 && c.ref_count <= 8 && c.device >= 0; }
+
+evx_status create_encoder_ex(const evx1_config &cfg, evx1_encoder **output)
+{
+    if (!output || !config_ok(cfg)) return EVX_ERROR_INVALIDARG;
+    *output = new (std::nothrow) encoder_session(cfg);
+    return *output ? EVX_SUCCESS : EVX_ERROR_OUTOFMEMORY;
+}
+
+evx_status create_decoder_ex(const evx1_config &cfg, evx1_decoder **output)
+{
+    if (!output || !config_ok(cfg)) return EVX_ERROR_INVALIDARG;
+    *output = new (std::nothrow) decoder_session(cfg);
+    return *output ? EVX_SUCCESS : EVX_ERROR_OUTOFMEMORY;
+}
+
+evx_status create_encoder(evx1_encoder **output) { evx1_config c; default_config(&c); return create_encoder_ex(c, output); }   // evx1.cpp:8-24
+evx_status create_decoder(evx1_decoder **output) { evx1_config c; default_config(&c); return create_decoder_ex(c, output); }   // evx1.cpp:26-42
+
+evx_status destroy_encoder(evx1_encoder *input)              // evx1.cpp:44-60
+{
+    if (!input) return EVX_ERROR_INVALIDARG;
+    delete static_cast<encoder_session *>(input);
+    return EVX_SUCCESS;
+}
+
+evx_status destroy_decoder(evx1_decoder *input)              // evx1.cpp:62-78
+{
+    if (!input) return EVX_ERROR_INVALIDARG;
+    delete static_cast<decoder_session *>(input);
+    return EVX_SUCCESS;
+}
+
+}  // namespace evx

@@ -1,0 +1,55 @@
+/* include/evx1_c.h -- flat C view of the C++ public API (cairo_b200/csrc/host/evx1.h, itself
+ * source-compatible with the reference's evx1.h:66-122) for callers that bind through an FFI
+ * (ctypes in tests/ and bench.py).  One call = one method of evx1_encoder / evx1_decoder; the
+ * transport unit is one frame per bit_stream, as in the reference (evx1dec.cpp:120).
+ * Status codes are the reference's evx_status values (base.h:152-169). */
+#ifndef EVX1_C_H
+#define EVX1_C_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct evx1c_encoder evx1c_encoder;
+typedef struct evx1c_decoder evx1c_decoder;
+
+/* ref_count / linear_quant / deblocking / periodic_intra / default_quality < 0 select the
+ * reference's config.h defaults (4, 0, 1, 3600, 8). */
+evx1c_encoder *evx1c_encoder_create(int device, int ref_count, int linear_quant, int deblocking, int periodic_intra, int default_quality);
+void evx1c_encoder_destroy(evx1c_encoder *e);
+int evx1c_encoder_clear(evx1c_encoder *e);                       /* evx1_encoder::clear */
+int evx1c_encoder_insert_intra(evx1c_encoder *e);                /* evx1_encoder::insert_intra */
+int evx1c_encoder_set_quality(evx1c_encoder *e, int quality);    /* evx1_encoder::set_quality */
+/* evx1_encoder::encode into a fresh bit_stream; copies ceil(out_bits/8) bytes to out. */
+int evx1c_encoder_encode(evx1c_encoder *e, const uint8_t *rgb, uint32_t width, uint32_t height,
+                         uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits);
+int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks);
+
+evx1c_decoder *evx1c_decoder_create(int device, int linear_quant, int deblocking);
+void evx1c_decoder_destroy(evx1c_decoder *d);
+int evx1c_decoder_clear(evx1c_decoder *d);                       /* evx1_decoder::clear */
+/* evx1_decoder::decode of one frame (nbits bits at data); rgb_out is width*height*3 bytes. */
+int evx1c_decoder_decode(evx1c_decoder *d, const uint8_t *data, uint32_t nbits, uint8_t *rgb_out);
+
+/* The host entropy stage on its own (serialize_slice / unserialize_slice of the reference,
+ * serialize.cpp:319-340, unserialize.cpp:321-341).  A writer/reader is persistent per stream:
+ * it carries the DC-prediction state that the reference keeps in its coefficient planes.
+ * table: evxgpu_block_desc[mbw*mbh]; records: int16[n_noncopy][384] in raster order. */
+typedef struct evx1c_slice_writer evx1c_slice_writer;
+typedef struct evx1c_slice_reader evx1c_slice_reader;
+evx1c_slice_writer *evx1c_slice_writer_create(int mbw, int mbh, int ref_count);
+void evx1c_slice_writer_destroy(evx1c_slice_writer *w);
+int evx1c_slice_writer_serialize(evx1c_slice_writer *w, const void *table, const int16_t *records, uint32_t n_noncopy,
+                                 uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits);
+evx1c_slice_reader *evx1c_slice_reader_create(int mbw, int mbh, int ref_count);
+void evx1c_slice_reader_destroy(evx1c_slice_reader *r);
+/* table is in/out (persistent across frames); records_out must hold mbw*mbh*384 int16. */
+int evx1c_slice_reader_unserialize(evx1c_slice_reader *r, const uint8_t *data, uint32_t nbits, void *table,
+                                   int16_t *records_out, uint32_t *n_noncopy);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

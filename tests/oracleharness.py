@@ -153,7 +153,7 @@ def bits_equal(a, abits, b, bbits):
     return bool((ua == ub).all())
 
 
-def tables_equal(a, b):
+def tables_equal(a, b, check_variance=True):
     """Field-wise block-table comparison; q_index/variance only where defined (non-copy blocks),
     motion/sub-pel fields only where the type uses them."""
     if not (a["block_type"] == b["block_type"]).all():
@@ -166,6 +166,6 @@ def tables_equal(a, b):
     sp = motion & (a["sp_pred"] != 0)
     for f in ("sp_amount", "sp_index"):
         ok &= (a[f][sp] == b[f][sp]).all()
-    for f in ("q_index", "variance"):
+    for f in ("q_index", "variance") if check_variance else ("q_index",):
         ok &= (a[f][~copy] == b[f][~copy]).all()
     return bool(ok)

@@ -1,0 +1,75 @@
+"""Host entropy stage (cairo_b200/csrc/host/entropy.cpp) against the golden slices made by the
+reference: the writer must reproduce the reference's bits from the reference's block table and
+coefficients, the reader must invert them -- including the stale-DC semantics across frames
+(SURVEY H4).  No GPU needed."""
+import numpy as np
+import pytest
+
+import goldenutil as G
+import oracleharness as O
+from cairo_b200 import api, gpu
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_slice_writer_reproduces_reference_bits(name):
+    g = G.Golden(name)
+    aw = (g.w + 15) // 16 * 16
+    ah = (g.h + 15) // 16 * 16
+    wr = api.SliceWriter(aw // 16, ah // 16, g.R)
+    for t in range(g.frames):
+        tbl = g.table(t)
+        rec = gpu.planes_to_records(tbl, g.planes(t, "coef"), aw)
+        d, b = wr.serialize(tbl, rec)
+        gd, gb = g.slice_bits(t)
+        assert O.bits_equal(d, b, gd, gb), (name, t, b, gb)
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_slice_reader_inverts_reference_bits(name):
+    g = G.Golden(name)
+    aw = (g.w + 15) // 16 * 16
+    ah = (g.h + 15) // 16 * 16
+    rd = api.SliceReader(aw // 16, ah // 16, g.R)
+    coef = [np.zeros((ah, aw), np.int16), np.zeros((ah // 2, aw // 2), np.int16), np.zeros((ah // 2, aw // 2), np.int16)]
+    for t in range(g.frames):
+        gd, gb = g.slice_bits(t)
+        tbl, rec = rd.unserialize(gd, gb)
+        assert O.tables_equal(g.table(t), tbl, check_variance=False), (name, t)   # variance is not on the wire
+        gpu.records_to_planes(tbl, rec, coef, aw, ah)
+        assert all((a == b).all() for a, b in zip(coef, g.planes(t, "coef"))), (name, t)
+
+
+def test_writer_reader_round_trip_random_tables():
+    rng = np.random.default_rng(3)
+    mbw, mbh, R = 7, 5, 4
+    wr, rd = api.SliceWriter(mbw, mbh, R), api.SliceReader(mbw, mbh, R)
+    for trial in range(8):
+        tbl = np.zeros(mbw * mbh, dtype=gpu.BLOCK_DESC_DTYPE)
+        tbl["block_type"] = rng.integers(0, 8, size=tbl.shape[0])
+        tbl["prediction_target"] = rng.integers(0, R, size=tbl.shape[0])
+        tbl["motion_x"] = rng.integers(-40, 40, size=tbl.shape[0])
+        tbl["motion_y"] = rng.integers(-40, 40, size=tbl.shape[0])
+        tbl["sp_pred"] = rng.integers(0, 2, size=tbl.shape[0])
+        tbl["sp_amount"] = rng.integers(0, 2, size=tbl.shape[0])
+        tbl["sp_index"] = rng.integers(0, 8, size=tbl.shape[0])
+        tbl["q_index"] = rng.integers(1, 32, size=tbl.shape[0])
+        n = int(((tbl["block_type"] & 4) == 0).sum())
+        rec = rng.integers(-300, 300, size=(n, 384)).astype(np.int16)
+        rec[rng.random(rec.shape) < 0.8] = 0
+        if n:
+            rec[0, 5] = 32767 if trial % 2 else -32767      # long escape codes
+        d, b = wr.serialize(tbl, rec)
+        t2, r2 = rd.unserialize(d, b)
+        assert O.tables_equal(tbl, t2, check_variance=False)
+        assert (r2 == rec).all()
+
+
+def test_empty_frame_all_copy_blocks():
+    mbw, mbh, R = 4, 3, 2
+    wr, rd = api.SliceWriter(mbw, mbh, R), api.SliceReader(mbw, mbh, R)
+    tbl = np.zeros(mbw * mbh, dtype=gpu.BLOCK_DESC_DTYPE)
+    tbl["block_type"] = 4          # INTER_COPY everywhere: no vectors, no q, no residuals
+    tbl["prediction_target"] = 1
+    d, b = wr.serialize(tbl, np.zeros((0, 384), np.int16))
+    t2, r2 = rd.unserialize(d, b)
+    assert (t2["block_type"] == 4).all() and r2.shape[0] == 0
