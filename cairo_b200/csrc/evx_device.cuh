@@ -181,6 +181,47 @@ __device__ __forceinline__ void evx_load_block(const EvxWin &win, int x, int y, 
     }
 }
 
+// Same lane layout against a window that is CIRCULAR in x (K3): rows of 64 luma words
+// (128 samples) / 32 chroma words (64 samples) addressed by absolute frame x modulo the
+// ring, row pitch padded to 72 / 36 words so that the loads stay bank-conflict free.
+struct EvxRingWin
+{
+    const uint32_t *y, *u, *v;
+    int oy, coy;                 // frame row of window row 0 (luma / chroma)
+};
+#define EVX_RING_PWY 72
+#define EVX_RING_PWC 36
+
+__device__ __forceinline__ void evx_load_block_ring(const EvxRingWin &win, int x, int y, int lane, EvxLaneBlock &b)
+{
+    const uint32_t *row = win.y + (y - win.oy + (lane >> 3)) * EVX_RING_PWY;
+    int w0 = (x >> 1) + (lane & 7);
+    if (x & 1)
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            b.w[k] = __byte_perm(row[4 * k * EVX_RING_PWY + (w0 & 63)], row[4 * k * EVX_RING_PWY + ((w0 + 1) & 63)], 0x5432);
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b.w[k] = row[4 * k * EVX_RING_PWY + (w0 & 63)];
+    }
+    int cx = x >> 1;
+    int crow = ((y >> 1) - win.coy + (lane >> 2)) * EVX_RING_PWC;
+    int c0 = (cx >> 1) + (lane & 3);
+    if (cx & 1)
+    {
+        b.w[4] = __byte_perm(win.u[crow + (c0 & 31)], win.u[crow + ((c0 + 1) & 31)], 0x5432);
+        b.w[5] = __byte_perm(win.v[crow + (c0 & 31)], win.v[crow + ((c0 + 1) & 31)], 0x5432);
+    }
+    else
+    {
+        b.w[4] = win.u[crow + (c0 & 31)];
+        b.w[5] = win.v[crow + (c0 & 31)];
+    }
+}
+
 // The source macroblock of a warp, in the lane layout above: packed negation (for
 // VIADDMNMX) and the lane's luma sum.
 struct EvxLaneSrc

@@ -478,17 +478,7 @@ __device__ __forceinline__ void evx_wait_deps(const int *progress, int bx, int b
     }
 }
 
-// ------------------------------------------------------------------ K3: encoder wavefront
-//
-// One CTA of 9 warps per macroblock in flight.  Intra search (motion.cpp:354-419) over a
-// window of the frame under construction staged in shared memory: nine warps = the nine
-// candidates of a 3x3 round, one __syncthreads per round, acceptance replayed by every
-// thread.  Then classify (encode.cpp:17-67) against K2's results, residual, 6x 8x8 DCT,
-// adaptive QP, quantise, and the reconstruction loop (decode.cpp:15-144).
-
-#define EVX_K3_THREADS 288
-#define EVX_K3_WIN 80
-#define EVX_K3_CWIN 40
+// ------------------------------------------------------------------ K3 parameters (kernel in evx_wavefront.cuh)
 
 struct EvxK3Params
 {
@@ -500,289 +490,54 @@ struct EvxK3Params
     uint32_t frame_index;
     const EvxInterResult *inter;   // [R-1][nmb], valid when frame_type == 1
     EvxDesc *table;                // block_table
-    int16_t *records;              // [nmb][384] coefficient records, slot = record_slot[mb]
-    int *record_slot;              // [nmb] slot of each non-copy macroblock (-1 for copy blocks)
-    const uint32_t *order;         // [nmb] wavefront order: bx | by << 16
-    int *sync;                     // [0] ticket, [1] record counter, [2..] progress[mbh]
+    int16_t *records;              // [nmb][384] coefficient records, slot = macroblock index
+    int *row_records;              // [mbh] non-copy macroblocks per row (for evx_pack_records)
+    int *sync;                     // [0] row ticket, [1] total records, [2..] progress[mbh]
     unsigned long long *counters;
 };
 
-__global__ void __launch_bounds__(EVX_K3_THREADS) evx_wavefront(const __grid_constant__ EvxK3Params p)
+// ------------------------------------------------------------------ K7: pack the non-copy macroblocks' records densely, raster order
+// (what serialize_slice consumes, serialize.cpp:125-154).  One CTA per macroblock row.
+__global__ void __launch_bounds__(256) evx_pack_records(const EvxDesc *__restrict__ table, const int16_t *__restrict__ records_mb,
+                                                        const int *__restrict__ row_records, int16_t *__restrict__ dense, int *total_out, EvxGeom g)
 {
-    __shared__ __align__(16) int16_t win_y[EVX_K3_WIN * EVX_K3_WIN];
-    __shared__ __align__(16) int16_t win_u[EVX_K3_CWIN * EVX_K3_CWIN];
-    __shared__ __align__(16) int16_t win_v[EVX_K3_CWIN * EVX_K3_CWIN];
-    __shared__ EvxMbShared sh;
-    __shared__ int2 cand[2][16];
-    __shared__ int s_ticket, s_slot;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const EvxGeom g = p.g;
-    const int nmb = g.mbw * g.mbh;
-    const int thr = (p.quality >> 2) + 1;                                  // motion.cpp:369, 436
-    const int dest = (int) (p.frame_index % (uint32_t) p.R);               // common.cpp:192-195
-    const EvxPlanes cur = p.ring[dest];
-    int *progress = p.sync + 2;
-    const int cw = g.w >> 1;
-
-    evx_init_tables(sh, tid, EVX_K3_THREADS);
-
-    for (;;)
+    __shared__ int s_idx[256];
+    __shared__ int s_wtot[8];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, by = blockIdx.x;
+    if (tid == 0)
     {
+        int base = 0, total = 0;
+        for (int r = 0; r < g.mbh; ++r) { int c = row_records[r]; if (r < by) base += c; total += c; }
+        s_base = base;
+        if (by == 0) *total_out = total;
+    }
+    __syncthreads();
+    int running = s_base;
+    for (int c0 = 0; c0 < g.mbw; c0 += 256)
+    {
+        const int m = c0 + tid;
+        const bool flag = m < g.mbw && !(table[by * g.mbw + m].w0 & EVX_T_COPY);
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, flag);
+        if (lane == 0) s_wtot[warp] = __popc(bal);
         __syncthreads();
-        if (tid == 0) s_ticket = atomicAdd(&p.sync[0], 1);
-        __syncthreads();
-        const int ticket = s_ticket;
-        if (ticket >= nmb) break;
-        const uint32_t ord = p.order[ticket];
-        const int bx = ord & 0xFFFF, by = ord >> 16;
-        const int px = bx * EVX_MB, py = by * EVX_MB;
-        const int mb = by * g.mbw + bx;
-
-        // source macroblock -> shared (block-major), independent of the neighbours
-        for (int e = tid; e < 384; e += EVX_K3_THREADS)
-        {
-            int comp, x, y;
-            evx_mb_pos(e, comp, x, y);
-            sh.src[e] = comp == 0 ? p.src.y[(size_t) (py + y) * g.w + px + x]
-                                  : (comp == 1 ? p.src.u : p.src.v)[(size_t) ((py >> 1) + y) * cw + (px >> 1) + x];
-        }
-        if (tid == 0) evx_wait_deps(progress, bx, by, g.mbw);
-        __syncthreads();
-
-        // stage the intra window: rows py-48..py-1 full width, rows py..py+31 only left of px
-        const int ox = px - 32, oy = py - 48, cox = (px >> 1) - 16, coy = (py >> 1) - 24;
-        for (int c = tid; c < EVX_K3_WIN * (EVX_K3_WIN / 8); c += EVX_K3_THREADS)
-        {
-            int r = c / (EVX_K3_WIN / 8), k = c % (EVX_K3_WIN / 8);
-            int y = oy + r, x = ox + 8 * k;
-            if (y < 0 || y >= g.h || x < 0 || x >= g.w) continue;
-            if (r >= 48 && k >= 4) continue;
-            *reinterpret_cast<int4 *>(win_y + r * EVX_K3_WIN + 8 * k) = __ldcg(reinterpret_cast<const int4 *>(cur.y + (size_t) y * g.w + x));
-        }
-        for (int c = tid; c < 2 * EVX_K3_CWIN * (EVX_K3_CWIN / 8); c += EVX_K3_THREADS)
-        {
-            int pl = c / (EVX_K3_CWIN * (EVX_K3_CWIN / 8)), cc = c % (EVX_K3_CWIN * (EVX_K3_CWIN / 8));
-            int r = cc / (EVX_K3_CWIN / 8), k = cc % (EVX_K3_CWIN / 8);
-            int y = coy + r, x = cox + 8 * k;
-            if (y < 0 || y >= (g.h >> 1) || x < 0 || x >= cw) continue;
-            if (r >= 24 && k >= 2) continue;
-            const int16_t *sp = (pl ? cur.v : cur.u) + (size_t) y * cw + x;
-            *reinterpret_cast<int4 *>((pl ? win_v : win_u) + r * EVX_K3_CWIN + 8 * k) = __ldcg(reinterpret_cast<const int4 *>(sp));
-        }
-        __syncthreads();
-
-        EvxWin win;
-        win.y = reinterpret_cast<const uint32_t *>(win_y); win.u = reinterpret_cast<const uint32_t *>(win_u); win.v = reinterpret_cast<const uint32_t *>(win_v);
-        win.pw_y = EVX_K3_WIN / 2; win.pw_c = EVX_K3_CWIN / 2;
-        win.ox = ox; win.oy = oy; win.cox = cox; win.coy = coy;
-
-        // this warp's copy of the source block in the lane layout
-        EvxLaneSrc src;
-        {
-            EvxLaneBlock sb;
-            int rr = lane >> 3, cc = lane & 7;
+        int woff = 0, ctot = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-            {
-                int y = rr + 4 * k, x = 2 * cc;
-                int e = ((y >> 3) * 2 + (x >> 3)) * 64 + (y & 7) * 8 + (x & 7);
-                sb.w[k] = evx_pack16(sh.src[e], sh.src[e + 1]);
-            }
-            int e = 256 + (lane >> 2) * 8 + 2 * (lane & 3);
-            sb.w[4] = evx_pack16(sh.src[e], sh.src[e + 1]);
-            sb.w[5] = evx_pack16(sh.src[e + 64], sh.src[e + 65]);
-            evx_make_src(sb, src);
-        }
-
-        // ---- intra search, motion.cpp:354-419
-        EvxSel s;
-        s.bx = px; s.by = py; s.mad = EVX_BIG; s.ssd = EVX_BIG; s.sp_index = 0; s.sp_amount = 0; s.sp_enabled = 0;
-        {   // compute_block_sad(src): the int16 abs overload (analysis.h:57-68)
-            int a = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) a += evx_abs16(evx_lo16(src.pos[k])) + evx_abs16(evx_hi16(src.pos[k]));
-            s.sad = __reduce_add_sync(0xFFFFFFFFu, a);
-        }
-        uint32_t n_full = 0, n_sub = 0;
-        int buf = 0;
-        for (int round = 0; round < 5; ++round)
-        {
-            const int step = round == 0 ? EVX_SEARCH_RADIUS : (EVX_SEARCH_RADIUS >> round);
-            const int top = round == 0 ? -2 : -1;          // first round scans rows -32,-16,0 (motion.cpp:384-386)
-            // candidate of this warp
-            const int j = warp / 3, i = warp % 3;
-            const int x = s.bx + (i - 1) * step, y = s.by + (top + j) * step;
-            bool legal = !(y > py - EVX_MB && x > px - EVX_MB) && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);
-            if (legal)
-            {
-                EvxLaneBlock ref;
-                int sad, mad;
-                evx_load_block(win, x, y, lane, ref);
-                evx_block_cost(ref, src, sad, mad);
-                if (lane == 0) cand[buf][warp] = make_int2(sad, mad);
-            }
-            __syncthreads();
-            const int basex = s.bx, basey = s.by;
-#pragma unroll
-            for (int c = 0; c < 9; ++c)
-            {
-                int cx = basex + (c % 3 - 1) * step, cy = basey + (top + c / 3) * step;
-                bool ok = !(cy > py - EVX_MB && cx > px - EVX_MB) && !(cx < 0 || cx > g.w - EVX_MB || cy < 0 || cy > g.h - EVX_MB);
-                if (!ok) continue;
-                int2 v = cand[buf][c];
-                n_full++;
-                evx_accept_fullpel(s, cx, cy, v.x, v.y, px, py, thr);
-            }
-            buf ^= 1;
-        }
-        // ---- intra sub-pel, motion.cpp:277-317: warp d < 8 handles direction d
-        {
-            const int d = warp < 4 ? warp : warp + 1;          // skip the centre
-            const int j = d / 3 - 1, i = d % 3 - 1;
-            const int x = s.bx + i, y = s.by + j;
-            bool legal = warp < 8 && !(y > py - EVX_MB && x > px - EVX_MB) && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);
-            if (legal)
-            {
-                EvxLaneBlock best, nb;
-                int shh, mh, sq, mq;
-                evx_load_block(win, s.bx, s.by, lane, best);
-                evx_load_block(win, x, y, lane, nb);
-                evx_subpel_cost(best, nb, src, shh, mh, sq, mq);
-                if (lane == 0) { cand[buf][2 * warp] = make_int2(shh, mh); cand[buf][2 * warp + 1] = make_int2(sq, mq); }
-            }
-            __syncthreads();
-#pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8)
-            {
-                int dd = w8 < 4 ? w8 : w8 + 1;
-                int jj = dd / 3 - 1, ii = dd % 3 - 1;
-                int cx = s.bx + ii, cy = s.by + jj;
-                bool ok = !(cy > py - EVX_MB && cx > px - EVX_MB) && !(cx < 0 || cx > g.w - EVX_MB || cy < 0 || cy > g.h - EVX_MB);
-                if (!ok) continue;
-                int2 h = cand[buf][2 * w8], q = cand[buf][2 * w8 + 1];
-                n_sub += 2;
-                evx_accept_subpel(s, ii, jj, 0, h.x, h.y, thr);
-                evx_accept_subpel(s, ii, jj, 1, q.x, q.y, thr);
-            }
-            buf ^= 1;
-        }
-
-        // ---- classify, encode.cpp:17-67
-        EvxDesc d = evx_desc_from_sel(s, 1, 0, px, py, thr);
-        int best_sad = s.sad;
-        if (p.frame_type == 1)
-        {
-            for (int off = 1; off < p.R; ++off)
-            {
-                const EvxInterResult *ir = p.inter + (size_t) (off - 1) * nmb + mb;
-                int4 raw = __ldg(reinterpret_cast<const int4 *>(&ir->desc));
-                int isad = __ldg(&ir->sad);
-                bool cc = (raw.x & EVX_T_COPY) != 0, bc = (d.type() & EVX_T_COPY) != 0;
-                bool take = (cc != bc) ? cc : (isad < best_sad);
-                if (take) { d.w0 = raw.x; d.w1 = raw.y; d.w2 = raw.z; d.w3 = raw.w; best_sad = isad; }
-            }
-        }
-        const int type = d.type();
-
-        // ---- prediction (encode.cpp:83-141)
-        bool has_pred = type != EVX_T_INTRA;
-        if (has_pred)
-        {
-            int mx = (type & EVX_T_MOTION) ? d.mx() : 0, my = (type & EVX_T_MOTION) ? d.my() : 0;
-            bool sp = (type & EVX_T_MOTION) && d.sp_pred();
-            int dx = 0, dy = 0;
-            if (sp) evx_frac_direction(d.sp_index(), dx, dy);
-            if (type & EVX_T_INTRA)
-            {   // from the staged window
-                int bxp = px + mx - ox, byp = py + my - oy;
-                int cbx = ((px + mx) >> 1) - cox, cby = ((py + my) >> 1) - coy;
-                int cnx = ((px + mx + dx) >> 1) - cox, cny = ((py + my + dy) >> 1) - coy;
-                for (int e = tid; e < 384; e += EVX_K3_THREADS)
-                {
-                    int comp, x, y;
-                    evx_mb_pos(e, comp, x, y);
-                    int a, b = 0;
-                    if (comp == 0)
-                    {
-                        a = win_y[(byp + y) * EVX_K3_WIN + bxp + x];
-                        if (sp) b = win_y[(byp + dy + y) * EVX_K3_WIN + bxp + dx + x];
-                    }
-                    else
-                    {
-                        const int16_t *wp = comp == 1 ? win_u : win_v;
-                        a = wp[(cby + y) * EVX_K3_CWIN + cbx + x];
-                        if (sp) b = wp[(cny + y) * EVX_K3_CWIN + cnx + x];
-                    }
-                    sh.pred[e] = (int16_t) (sp ? (d.sp_amount() ? evx_lerp_quarter(a, b) : evx_lerp_half(a, b)) : a);
-                }
-            }
-            else
-            {
-                int slot = (int) ((p.frame_index + (uint32_t) p.R - (uint32_t) d.target()) % (uint32_t) p.R);
-                evx_build_pred_global(sh, p.ring[slot], g, px + mx, py + my, sp, d.sp_amount(), dx, dy, tid, EVX_K3_THREADS);
-            }
-        }
+        for (int w = 0; w < 8; ++w) { if (w < warp) woff += s_wtot[w]; ctot += s_wtot[w]; }
+        s_idx[tid] = flag ? running + woff + __popc(bal & ((1u << lane) - 1u)) : -1;
         __syncthreads();
-
-        if (type & EVX_T_COPY)
-        {   // copy blocks: prediction is the reconstruction; no coefficients (encode.cpp:155-157)
-            evx_store_pred_as_recon(sh, cur, g, px, py, tid, EVX_K3_THREADS);
-            if (tid == 0) { p.table[mb] = d; p.record_slot[mb] = -1; }
-        }
-        else
+        const int cnt = min(256, g.mbw - c0);
+        for (int k = warp; k < cnt; k += 8)
         {
-            // residual (transform.cpp:29-32: int16 subtraction)
-            for (int e = tid; e < 384; e += EVX_K3_THREADS) sh.bufa[e] = (int16_t) (has_pred ? sh.src[e] - sh.pred[e] : sh.src[e]);
-            __syncthreads();
-            evx_fdct_pass(sh.bufa, sh.bufb, sh.lut, tid, EVX_K3_THREADS, false);
-            __syncthreads();
-            evx_fdct_pass(sh.bufb, sh.bufa, sh.lut, tid, EVX_K3_THREADS, true);
-            __syncthreads();
-            // compute_block_variance2 over the 16x16 luma coefficients except (0,0) (analysis.h:176-198)
-            {
-                uint32_t sum = 0, sq = 0; int cnt = 0;
-                if (tid >= 1 && tid < 256) { int t = sh.bufa[tid]; if (t) { sum = (uint32_t) t; sq = (uint32_t) (t * t); cnt = 1; } }
-                sum = __reduce_add_sync(0xFFFFFFFFu, sum); sq = __reduce_add_sync(0xFFFFFFFFu, sq); cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-                if (lane == 0) { sh.red[warp] = (int) sum; sh.red[32 + warp] = (int) sq; sh.red[64 + warp] = cnt; }
-                __syncthreads();
-                if (tid == 0)
-                {
-                    uint32_t S = 0, Q = 0; int C = 0;
-                    for (int w8 = 0; w8 < 8; ++w8) { S += (uint32_t) sh.red[w8]; Q += (uint32_t) sh.red[32 + w8]; C += sh.red[64 + w8]; }
-                    int var = 0;
-                    if (C > 0) var = (int) (Q - (uint32_t) evx_rdiv((int) (S * S), C));
-                    // query_block_quantization_parameter, quantize.cpp:60-77
-                    int q = p.quality & 0xFF;
-                    int idx = evx_clip(evx_ilog2((uint32_t) var) >> 1, 1, 31);
-                    int qp = q;
-                    if (idx > q) qp = evx_clip(q + ((idx - q) >> 1), 1, 31);
-                    else if (idx < q) qp = evx_clip(q - ((q - idx) >> 1), 1, 31);
-                    sh.qp = qp; sh.var = var;
-                    s_slot = atomicAdd(&p.sync[1], 1);
-                }
-                __syncthreads();
-            }
-            const int qp = sh.qp;
-            const bool intra_q = (type & EVX_T_INTRA) && !(type & EVX_T_MOTION);
-            int16_t *rec = p.records + (size_t) s_slot * 384;
-            for (int e = tid; e < 384; e += EVX_K3_THREADS)
-            {
-                int b = e >> 6;
-                int mode = intra_q ? (b < 4 ? 0 : 1) : 2;
-                int qv = evx_quant(sh.bufa[e], e & 63, mode, qp, p.linear, sh.qmi, sh.qmt);
-                sh.bufb[e] = (int16_t) qv;
-            }
-            __syncthreads();
-            for (int e = tid; e < 384; e += EVX_K3_THREADS) { sh.bufa[e] = sh.bufb[e]; rec[evx_record_index(e)] = sh.bufb[e]; }
-            if (tid == 0) { d.set_q(qp, sh.var); p.table[mb] = d; p.record_slot[mb] = s_slot; }
-            __syncthreads();
-            evx_reconstruct(sh, type, qp, p.linear, has_pred, cur, g, px, py, tid, EVX_K3_THREADS);
+            const int idx = s_idx[k];
+            if (idx < 0) continue;
+            const uint4 *srcp = reinterpret_cast<const uint4 *>(records_mb + (size_t) (by * g.mbw + c0 + k) * 384);
+            uint4 *dstp = reinterpret_cast<uint4 *>(dense + (size_t) idx * 384);
+            dstp[lane] = srcp[lane];
+            if (lane < 16) dstp[32 + lane] = srcp[32 + lane];
         }
-
-        if (tid == 32) { atomicAdd(&p.counters[0], (unsigned long long) n_full); atomicAdd(&p.counters[1], (unsigned long long) n_sub); }
+        running += ctot;
         __syncthreads();
-        if (tid == 0) { __threadfence(); evx_st_release(progress + by, bx + 1); }
     }
 }
 

@@ -1,0 +1,531 @@
+// evx_wavefront.cuh -- K3, the encoder's serial spine: intra search in the frame under
+// construction (motion.cpp:354-419), classify (encode.cpp:17-67), encode_block
+// (encode.cpp:69-163) and the reconstruction loop (decode.cpp:15-144).
+//
+// Macroblocks depend on each other in raster order through the intra search (it reads the
+// neighbours' reconstructions, and stale samples of the ring slot -- SURVEY H3).  The legal
+// schedule is a wavefront: (bx,by) after (bx-1,by) and (min(bx+2,W-1),by-1).
+//
+// Mapping: ONE CTA PER MACROBLOCK ROW, warp specialised --
+//   warps 0..8  compute: nine candidates of a 3x3 search round in parallel, then the
+//               transform path of the macroblock;
+//   warp  9     loader: one macroblock ahead, stages the source block, K2's inter results and
+//               their predictions, and slides the search window (a ring of 8 macroblock
+//               columns in shared memory) -- the 16 new columns of the three rows above once
+//               the row above has published them, the stale columns of the row below any time;
+//   warp 10     publisher: fences and releases progress[by] so the row below can follow.
+// The left-neighbour dependency is thus inside the CTA (its reconstruction is written straight
+// into the window), and the inter-row latency (flag + L2 round trip) is paid once per row
+// instead of once per macroblock: frame time ~ (W + 3(H-1)) * T_mb + (H-1) * latency.
+#pragma once
+
+#include "evx_kernels.cuh"
+
+#define EVX_K3_CW 9
+#define EVX_K3_CT (EVX_K3_CW * 32)
+#define EVX_K3_NT (EVX_K3_CT + 64)
+#define EVX_K3_ROWS 80            // window rows py-48 .. py+31
+#define EVX_K3_CROWS 40
+#define EVX_MAXREF 7
+
+struct EvxK3Smem
+{
+    uint32_t wy[EVX_K3_ROWS * EVX_RING_PWY];
+    uint32_t wu[EVX_K3_CROWS * EVX_RING_PWC];
+    uint32_t wv[EVX_K3_CROWS * EVX_RING_PWC];
+    int16_t src[2][384];                      // block-major source macroblocks, double buffered
+    int16_t ipred[2][EVX_MAXREF][384];        // predictions of K2's candidates, block-major
+    int4 idesc[2][EVX_MAXREF];
+    int isad[2][EVX_MAXREF + 1];
+    EvxMbShared sh;
+    int4 cand[2][16];
+    uint64_t full[2], empty[2];
+    int done;                                 // macroblocks of this row whose reconstruction is stored
+    int row;
+};
+
+__device__ __forceinline__ void evx_mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(evx_smem_addr(bar)) : "memory");
+}
+
+__device__ __forceinline__ void evx_compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EVX_K3_CT) : "memory"); }
+
+// int16 sample of the ring window
+__device__ __forceinline__ int evx_ring_y(const EvxK3Smem &S, int x, int wrow) { return reinterpret_cast<const int16_t *>(S.wy)[wrow * (EVX_RING_PWY * 2) + (x & 127)]; }
+__device__ __forceinline__ int evx_ring_c(const uint32_t *pl, int cx, int wrow) { return reinterpret_cast<const int16_t *>(pl)[wrow * (EVX_RING_PWC * 2) + (cx & 63)]; }
+
+// ---------------------------------------------------------------- loader warp
+
+__device__ __forceinline__ void evx_k3_loader(EvxK3Smem &S, const EvxK3Params &p, int by, int lane)
+{
+    const EvxGeom g = p.g;
+    const int nmb = g.mbw * g.mbh, cw = g.w >> 1, py = by * EVX_MB;
+    const int dest = (int) (p.frame_index % (uint32_t) p.R);
+    const EvxPlanes cur = p.ring[dest];
+    const int *progress = p.sync + 2;
+    const int nref = p.frame_type == 1 ? p.R - 1 : 0;
+
+    for (int n = 0; n < g.mbw; ++n)
+    {
+        const int slot = n & 1, px = n * EVX_MB, mb = by * g.mbw + n;
+        if (n >= 2) evx_mbar_wait(&S.empty[slot], (uint32_t) (((n >> 1) - 1) & 1));
+
+        // source macroblock -> block-major
+        {
+            int row = lane >> 1, half = lane & 1;
+            uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.src.y + (size_t) (py + row) * g.w + px + 8 * half));
+            *reinterpret_cast<uint4 *>(&S.src[slot][((row >> 3) * 2 + half) * 64 + (row & 7) * 8]) = v;
+            if (lane < 16)
+            {
+                const int16_t *pl = lane < 8 ? p.src.u : p.src.v;
+                uint4 c = __ldg(reinterpret_cast<const uint4 *>(pl + (size_t) ((py >> 1) + (lane & 7)) * cw + (px >> 1)));
+                *reinterpret_cast<uint4 *>(&S.src[slot][256 + (lane >> 3) * 64 + (lane & 7) * 8]) = c;
+            }
+        }
+        // K2's candidates and their predictions (encode.cpp:110-141), so that classification
+        // never waits on global memory
+        for (int r = 0; r < nref; ++r)
+        {
+            const EvxInterResult *ir = p.inter + (size_t) r * nmb + mb;
+            int4 raw = __ldg(reinterpret_cast<const int4 *>(&ir->desc));
+            int isad = __ldg(&ir->sad);
+            if (lane == 0) { S.idesc[slot][r] = raw; S.isad[slot][r] = isad; }
+            EvxDesc d; d.w0 = raw.x; d.w1 = raw.y; d.w2 = raw.z; d.w3 = raw.w;
+            const int type = d.type();
+            const int rslot = (int) ((p.frame_index + (uint32_t) p.R - (uint32_t) (r + 1)) % (uint32_t) p.R);
+            const EvxPlanes ref = p.ring[rslot];
+            const int mx = (type & EVX_T_MOTION) ? d.mx() : 0, my = (type & EVX_T_MOTION) ? d.my() : 0;
+            const bool sp = (type & EVX_T_MOTION) && d.sp_pred();
+            int dx = 0, dy = 0;
+            if (sp) evx_frac_direction(d.sp_index(), dx, dy);
+            const int bxp = px + mx, byp = py + my;
+            int a[12], b[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+            {
+                int comp, x, y;
+                evx_mb_pos(lane + 32 * k, comp, x, y);
+                b[k] = 0;
+                if (comp == 0)
+                {
+                    a[k] = __ldg(ref.y + (size_t) (byp + y) * g.w + bxp + x);
+                    if (sp) b[k] = __ldg(ref.y + (size_t) (byp + dy + y) * g.w + bxp + dx + x);
+                }
+                else
+                {
+                    const int16_t *pl = comp == 1 ? ref.u : ref.v;
+                    a[k] = __ldg(pl + (size_t) ((byp >> 1) + y) * cw + (bxp >> 1) + x);
+                    if (sp) b[k] = __ldg(pl + (size_t) (((byp + dy) >> 1) + y) * cw + ((bxp + dx) >> 1) + x);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                S.ipred[slot][r][lane + 32 * k] = (int16_t) (sp ? (d.sp_amount() ? evx_lerp_quarter(a[k], b[k]) : evx_lerp_half(a[k], b[k])) : a[k]);
+        }
+        // stale samples of the row below, macroblock column n-1 (read by the intra search of
+        // columns n and n+1; the row below overwrites them only after we finished column n+1)
+        if (n >= 1 && by + 1 < g.mbh)
+        {
+            int row = lane >> 1, half = lane & 1, x0 = (n - 1) * EVX_MB + 8 * half;
+            uint4 v = __ldcg(reinterpret_cast<const uint4 *>(cur.y + (size_t) (py + 16 + row) * g.w + x0));
+            *reinterpret_cast<uint4 *>(&S.wy[(64 + row) * EVX_RING_PWY + ((x0 >> 1) & 63)]) = v;
+            if (lane < 16)
+            {
+                const int16_t *pl = lane < 8 ? cur.u : cur.v;
+                int cx0 = (n - 1) * 8;
+                uint4 c = __ldcg(reinterpret_cast<const uint4 *>(pl + (size_t) ((py >> 1) + 8 + (lane & 7)) * cw + cx0));
+                *reinterpret_cast<uint4 *>(&(lane < 8 ? S.wu : S.wv)[(32 + (lane & 7)) * EVX_RING_PWC + ((cx0 >> 1) & 31)]) = c;
+            }
+        }
+        // the three rows above: wait for (min(n+2,W-1), by-1), then pull the new column(s)
+        if (by > 0)
+        {
+            const int need = min(n + 2, g.mbw - 1) + 1;
+            if (lane == 0) while (evx_ld_acquire(progress + by - 1) < need) __nanosleep(32);
+            __syncwarp();
+            const int first = n == 0 ? 0 : n + 2, last = min(n + 2, g.mbw - 1);
+            for (int col = first; col <= last; ++col)
+            {
+                uint4 v[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                {
+                    int c = lane + 32 * k;                 // 96 chunks: 48 rows x 2 halves
+                    int row = c >> 1, half = c & 1, y = py - 48 + row;
+                    v[k] = make_uint4(0, 0, 0, 0);
+                    if (y >= 0) v[k] = __ldcg(reinterpret_cast<const uint4 *>(cur.y + (size_t) y * g.w + col * EVX_MB + 8 * half));
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                {
+                    int c = lane + 32 * k;
+                    int row = c >> 1, half = c & 1;
+                    *reinterpret_cast<uint4 *>(&S.wy[row * EVX_RING_PWY + (((col * EVX_MB + 8 * half) >> 1) & 63)]) = v[k];
+                }
+                uint4 cv[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                {
+                    int c = lane + 32 * k;                 // 48 chunks: 2 planes x 24 rows
+                    cv[k] = make_uint4(0, 0, 0, 0);
+                    if (c < 48)
+                    {
+                        int plane = c / 24, row = c % 24, y = (py >> 1) - 24 + row;
+                        if (y >= 0) cv[k] = __ldcg(reinterpret_cast<const uint4 *>((plane ? cur.v : cur.u) + (size_t) y * cw + col * 8));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                {
+                    int c = lane + 32 * k;
+                    if (c < 48)
+                    {
+                        int plane = c / 24, row = c % 24;
+                        *reinterpret_cast<uint4 *>(&(plane ? S.wv : S.wu)[row * EVX_RING_PWC + (((col * 8) >> 1) & 31)]) = cv[k];
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) evx_mbar_arrive(&S.full[slot]);
+    }
+}
+
+// ---------------------------------------------------------------- compute warps
+
+__device__ __forceinline__ bool evx_intra_legal(int x, int y, int px, int py, const EvxGeom &g)
+{
+    return !(y > py - EVX_MB && x > px - EVX_MB) && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);   // motion.cpp:238-248
+}
+
+__device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &p, int by, int tid)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    const EvxGeom g = p.g;
+    const int cw = g.w >> 1, py = by * EVX_MB;
+    const int thr = (p.quality >> 2) + 1;                                  // motion.cpp:369, 436
+    const int dest = (int) (p.frame_index % (uint32_t) p.R);               // common.cpp:192-195
+    const EvxPlanes cur = p.ring[dest];
+    const int nref = p.frame_type == 1 ? p.R - 1 : 0;
+    EvxMbShared &sh = S.sh;
+    int16_t *wy16 = reinterpret_cast<int16_t *>(S.wy), *wu16 = reinterpret_cast<int16_t *>(S.wu), *wv16 = reinterpret_cast<int16_t *>(S.wv);
+
+    EvxRingWin win;
+    win.y = S.wy; win.u = S.wu; win.v = S.wv; win.oy = py - 48; win.coy = (py >> 1) - 24;
+
+    // this thread's row of the DCT basis (fixed output index i = tid & 7 in every pass)
+    int lut_f[8], lut_i[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { lut_f[k] = evx_dct_lut(tid & 7, k); lut_i[k] = evx_dct_lut(k, tid & 7); }
+
+    uint32_t n_full = 0, n_sub = 0;
+    int row_records = 0;
+
+    for (int n = 0; n < g.mbw; ++n)
+    {
+        const int slot = n & 1, px = n * EVX_MB, mb = by * g.mbw + n;
+        evx_mbar_wait(&S.full[slot], (uint32_t) ((n >> 1) & 1));
+        const int16_t *srcb = S.src[slot];
+
+        EvxLaneSrc src;
+        {
+            EvxLaneBlock sb;
+            int rr = lane >> 3, cc = lane & 7;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                int y = rr + 4 * k, x = 2 * cc;
+                sb.w[k] = *reinterpret_cast<const uint32_t *>(&srcb[((y >> 3) * 2 + (x >> 3)) * 64 + (y & 7) * 8 + (x & 7)]);
+            }
+            int e = 256 + (lane >> 2) * 8 + 2 * (lane & 3);
+            sb.w[4] = *reinterpret_cast<const uint32_t *>(&srcb[e]);
+            sb.w[5] = *reinterpret_cast<const uint32_t *>(&srcb[e + 64]);
+            evx_make_src(sb, src);
+        }
+
+        // ---- intra search, motion.cpp:354-419
+        EvxSel s;
+        s.bx = px; s.by = py; s.mad = EVX_BIG; s.ssd = EVX_BIG; s.sp_index = 0; s.sp_amount = 0; s.sp_enabled = 0;
+        {   // compute_block_sad(src) with the int16 abs overload (analysis.h:57-68)
+            int a = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a += evx_abs16(evx_lo16(src.pos[k])) + evx_abs16(evx_hi16(src.pos[k]));
+            s.sad = __reduce_add_sync(0xFFFFFFFFu, a);
+        }
+        int buf = 0;
+#pragma unroll 1
+        for (int round = 0; round < 5; ++round)
+        {
+            const int step = EVX_SEARCH_RADIUS >> (round == 0 ? 0 : round);
+            const int top = round == 0 ? -2 : -1;          // first round scans rows -32,-16,0 (motion.cpp:384-386)
+            {
+                const int x = s.bx + (warp % 3 - 1) * step, y = s.by + (top + warp / 3) * step;
+                int4 res = make_int4(0, 0, 0, 0);
+                if (evx_intra_legal(x, y, px, py, g))
+                {
+                    EvxLaneBlock ref;
+                    int sad, mad;
+                    evx_load_block_ring(win, x, y, lane, ref);
+                    evx_block_cost(ref, src, sad, mad);
+                    res = make_int4(sad, mad, (x - px) * (x - px) + (y - py) * (y - py), 1);
+                }
+                if (lane == 0) S.cand[buf][warp] = res;
+            }
+            evx_compute_sync();
+            const int basex = s.bx, basey = s.by;
+#pragma unroll
+            for (int c = 0; c < 9; ++c)
+            {
+                const int4 v = S.cand[buf][c];
+                if (!v.w) continue;
+                n_full++;
+                bool take;
+                if (s.mad < thr) take = v.y < s.mad || (v.y == s.mad && v.z < s.ssd);
+                else take = v.x < s.sad || (v.x == s.sad && v.z < s.ssd && (uint32_t) v.x < EVX_SAD_CAP) || v.y < thr;
+                if (take) { s.bx = basex + (c % 3 - 1) * step; s.by = basey + (top + c / 3) * step; s.sad = v.x; s.mad = v.y; s.ssd = v.z; }
+            }
+            buf ^= 1;
+        }
+        // ---- intra sub-pel, motion.cpp:277-317: warp d < 8 takes direction d (both blends)
+        {
+            const int d = warp < 4 ? warp : warp + 1;          // skip the centre
+            const int j = d / 3 - 1, i = d % 3 - 1;
+            const int x = s.bx + i, y = s.by + j;
+            int4 res = make_int4(0, 0, 0, 0), res2 = make_int4(0, 0, 0, 0);
+            if (warp < 8 && evx_intra_legal(x, y, px, py, g))
+            {
+                EvxLaneBlock best, nb;
+                int shh, mh, sq, mq;
+                evx_load_block_ring(win, s.bx, s.by, lane, best);
+                evx_load_block_ring(win, x, y, lane, nb);
+                evx_subpel_cost(best, nb, src, shh, mh, sq, mq);
+                res = make_int4(shh, mh, 0, 1); res2 = make_int4(sq, mq, 0, 1);
+            }
+            if (lane == 0 && warp < 8) { S.cand[buf][2 * warp] = res; S.cand[buf][2 * warp + 1] = res2; }
+            evx_compute_sync();
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8)
+            {
+                const int4 h = S.cand[buf][2 * w8], q = S.cand[buf][2 * w8 + 1];
+                if (!h.w) continue;
+                const int dd = w8 < 4 ? w8 : w8 + 1;
+                n_sub += 2;
+                evx_accept_subpel(s, dd % 3 - 1, dd / 3 - 1, 0, h.x, h.y, thr);
+                evx_accept_subpel(s, dd % 3 - 1, dd / 3 - 1, 1, q.x, q.y, thr);
+            }
+        }
+
+        // ---- classify, encode.cpp:17-67
+        EvxDesc d = evx_desc_from_sel(s, 1, 0, px, py, thr);
+        int best_sad = s.sad, best_ref = -1;
+        for (int r = 0; r < nref; ++r)
+        {
+            const int4 raw = S.idesc[slot][r];
+            const int isad = S.isad[slot][r];
+            const bool cc = (raw.x & EVX_T_COPY) != 0, bc = (d.type() & EVX_T_COPY) != 0;
+            const bool take = (cc != bc) ? cc : (isad < best_sad);
+            if (take) { d.w0 = raw.x; d.w1 = raw.y; d.w2 = raw.z; d.w3 = raw.w; best_sad = isad; best_ref = r; }
+        }
+        const int type = d.type();
+        const bool has_pred = type != EVX_T_INTRA;
+
+        // ---- prediction (encode.cpp:83-141): intra from the window, inter from the loader's copy
+        if (has_pred)
+        {
+            if (type & EVX_T_INTRA)
+            {
+                const int bxp = px + d.mx(), byp = py + d.my();
+                const bool sp = d.sp_pred() != 0;
+                int dx = 0, dy = 0;
+                if (sp) evx_frac_direction(d.sp_index(), dx, dy);
+                for (int e = tid; e < 384; e += EVX_K3_CT)
+                {
+                    int comp, x, y, a, b = 0;
+                    evx_mb_pos(e, comp, x, y);
+                    if (comp == 0)
+                    {
+                        a = evx_ring_y(S, bxp + x, byp + y - win.oy);
+                        if (sp) b = evx_ring_y(S, bxp + dx + x, byp + dy + y - win.oy);
+                    }
+                    else
+                    {
+                        const uint32_t *pl = comp == 1 ? S.wu : S.wv;
+                        a = evx_ring_c(pl, (bxp >> 1) + x, (byp >> 1) + y - win.coy);
+                        if (sp) b = evx_ring_c(pl, ((bxp + dx) >> 1) + x, ((byp + dy) >> 1) + y - win.coy);
+                    }
+                    sh.pred[e] = (int16_t) (sp ? (d.sp_amount() ? evx_lerp_quarter(a, b) : evx_lerp_half(a, b)) : a);
+                }
+            }
+            else
+            {
+                for (int e = tid; e < 384; e += EVX_K3_CT) sh.pred[e] = S.ipred[slot][best_ref][e];
+            }
+        }
+        evx_compute_sync();
+
+        // reconstruction target: global ring slot + our own window rows (py..py+15 -> 48..63)
+        auto store_recon = [&](int e, int v)
+        {
+            int comp, x, y;
+            evx_mb_pos(e, comp, x, y);
+            if (comp == 0)
+            {
+                cur.y[(size_t) (py + y) * g.w + px + x] = (int16_t) v;
+                wy16[(48 + y) * (EVX_RING_PWY * 2) + ((px + x) & 127)] = (int16_t) v;
+            }
+            else
+            {
+                (comp == 1 ? cur.u : cur.v)[(size_t) ((py >> 1) + y) * cw + (px >> 1) + x] = (int16_t) v;
+                (comp == 1 ? wu16 : wv16)[(24 + y) * (EVX_RING_PWC * 2) + (((px >> 1) + x) & 63)] = (int16_t) v;
+            }
+        };
+
+        if (type & EVX_T_COPY)
+        {   // copy blocks: the prediction is the reconstruction; no coefficients (encode.cpp:155-157)
+            for (int e = tid; e < 384; e += EVX_K3_CT) store_recon(e, sh.pred[e]);
+            if (tid == 0) p.table[mb] = d;
+        }
+        else
+        {
+            // residual (int16, transform.cpp:29-32) and row pass (transform.cpp:264-301)
+            for (int e = tid; e < 384; e += EVX_K3_CT)
+            {
+                const int base = e & ~7;
+                int t = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                {
+                    int r = has_pred ? (short) (srcb[base + k] - sh.pred[base + k]) : srcb[base + k];
+                    t += r * lut_f[k];
+                }
+                t = (e & 7) == 0 ? evx_tdiv_pow2(t * 45, 7) : evx_tdiv_pow2(t, 1);
+                sh.bufb[e] = (int16_t) evx_rdiv_pow2(t, 7);
+            }
+            evx_compute_sync();
+            // column pass: thread e -> (block b, column a, output row i = e & 7)
+            for (int e = tid; e < 384; e += EVX_K3_CT)
+            {
+                const int b = e >> 6, a = (e >> 3) & 7, i = e & 7;
+                int t = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) t += sh.bufb[b * 64 + k * 8 + a] * lut_f[k];
+                t = i == 0 ? evx_tdiv_pow2(t * 45, 7) : evx_tdiv_pow2(t, 1);
+                sh.bufa[b * 64 + i * 8 + a] = (int16_t) evx_rdiv_pow2(t, 7);
+            }
+            evx_compute_sync();
+            // compute_block_variance2 over the 16x16 luma coefficients except (0,0) (analysis.h:176-198)
+            {
+                uint32_t sum = 0, sq = 0; int cnt = 0;
+                if (tid >= 1 && tid < 256) { int t = sh.bufa[tid]; if (t) { sum = (uint32_t) t; sq = (uint32_t) (t * t); cnt = 1; } }
+                sum = __reduce_add_sync(0xFFFFFFFFu, sum); sq = __reduce_add_sync(0xFFFFFFFFu, sq); cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+                if (lane == 0) { sh.red[warp] = (int) sum; sh.red[32 + warp] = (int) sq; sh.red[64 + warp] = cnt; }
+                evx_compute_sync();
+            }
+            int qp, var = 0;
+            {
+                uint32_t Ssum = 0, Q = 0; int C = 0;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) { Ssum += (uint32_t) sh.red[w8]; Q += (uint32_t) sh.red[32 + w8]; C += sh.red[64 + w8]; }
+                if (C > 0) var = (int) (Q - (uint32_t) evx_rdiv((int) (Ssum * Ssum), C));
+                // query_block_quantization_parameter, quantize.cpp:60-77
+                const int q = p.quality & 0xFF;
+                const int idx = evx_clip(evx_ilog2((uint32_t) var) >> 1, 1, 31);
+                qp = q;
+                if (idx > q) qp = evx_clip(q + ((idx - q) >> 1), 1, 31);
+                else if (idx < q) qp = evx_clip(q - ((q - idx) >> 1), 1, 31);
+            }
+            const bool intra_q = (type & EVX_T_INTRA) && !(type & EVX_T_MOTION);
+            int16_t *rec = p.records + (size_t) mb * 384;
+            // quantise (quantize.cpp:79-180), hand the record out, dequantise (quantize.cpp:182-243)
+            for (int e = tid; e < 384; e += EVX_K3_CT)
+            {
+                const int mode = intra_q ? ((e >> 6) < 4 ? 0 : 1) : 2;
+                const int qv = evx_quant(sh.bufa[e], e & 63, mode, qp, p.linear, sh.qmi, sh.qmt);
+                rec[evx_record_index(e)] = (int16_t) qv;
+                sh.bufb[e] = (int16_t) evx_dequant(qv, e & 63, mode, qp, p.linear, sh.qmi, sh.qmt);
+            }
+            if (tid == 0) { d.set_q(qp, var); p.table[mb] = d; }
+            evx_compute_sync();
+            // inverse transform (transform.cpp:330-366, 418-433): columns, then rows + prediction
+            for (int e = tid; e < 384; e += EVX_K3_CT)
+            {
+                const int b = e >> 6, j = (e >> 3) & 7;      // column j, output row i = e & 7
+                const int16_t *in = sh.bufb + b * 64 + j;
+                int t = evx_tdiv_pow2((in[0] * lut_i[0]) * 45, 7);
+#pragma unroll
+                for (int k = 1; k < 8; ++k) t += evx_tdiv_pow2(in[k * 8] * lut_i[k], 1);
+                sh.bufa[b * 64 + (e & 7) * 8 + j] = (int16_t) evx_rdiv_pow2(t, 7);
+            }
+            evx_compute_sync();
+            for (int e = tid; e < 384; e += EVX_K3_CT)
+            {
+                const int16_t *in = sh.bufa + (e & ~7);      // row (e>>3), output column i = e & 7
+                int t = evx_tdiv_pow2((in[0] * lut_i[0]) * 45, 7);
+#pragma unroll
+                for (int k = 1; k < 8; ++k) t += evx_tdiv_pow2(in[k] * lut_i[k], 1);
+                int v = evx_rdiv_pow2(t, 7);
+                if (has_pred) v += sh.pred[e];
+                store_recon(e, v);
+            }
+            row_records++;
+        }
+        evx_compute_sync();
+        if (tid == 0)
+        {
+            evx_mbar_arrive(&S.empty[slot]);
+            asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(evx_smem_addr(&S.done)), "r"(n + 1) : "memory");
+        }
+    }
+    if (tid == 0)
+    {
+        p.row_records[by] = row_records;
+        atomicAdd(&p.counters[0], (unsigned long long) n_full);
+        atomicAdd(&p.counters[1], (unsigned long long) n_sub);
+    }
+}
+
+__global__ void __launch_bounds__(EVX_K3_NT, 1) evx_wavefront(const __grid_constant__ EvxK3Params p)
+{
+    extern __shared__ __align__(16) uint8_t evx_k3_smem[];
+    EvxK3Smem &S = *reinterpret_cast<EvxK3Smem *>(evx_k3_smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0)
+    {
+        // rows are claimed in order: a CTA only ever waits on rows claimed before its own
+        S.row = atomicAdd(&p.sync[0], 1);
+        evx_mbar_init(&S.full[0], 1); evx_mbar_init(&S.full[1], 1);
+        evx_mbar_init(&S.empty[0], 1); evx_mbar_init(&S.empty[1], 1);
+        S.done = 0;
+    }
+    evx_init_tables(S.sh, tid, EVX_K3_NT);
+    __syncthreads();
+    const int by = S.row;
+    if (by >= p.g.mbh) return;
+
+    if (warp < EVX_K3_CW) evx_k3_compute(S, p, by, tid);
+    else if (warp == EVX_K3_CW) evx_k3_loader(S, p, by, lane);
+    else
+    {   // publisher: make the row's writes visible device-wide, then advance progress[by].
+        // It follows a counter, not a phase, so a fast compute side can never lap it.
+        int *progress = p.sync + 2;
+        if (lane == 0)
+        {
+            int last = 0;
+            while (last < p.g.mbw)
+            {
+                int d;
+                for (;;)
+                {
+                    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(d) : "r"(evx_smem_addr(&S.done)) : "memory");
+                    if (d > last) break;
+                    __nanosleep(64);
+                }
+                __threadfence();
+                evx_st_release(progress + by, d);
+                last = d;
+            }
+        }
+    }
+}

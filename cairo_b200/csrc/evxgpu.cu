@@ -17,6 +17,7 @@
 
 #include "../../include/evxgpu.h"
 #include "evx_kernels.cuh"
+#include "evx_wavefront.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -55,7 +56,9 @@ struct evxgpu_handle
     uint8_t *d_rgb;                 // frame staging (input on the encoder, output on the decoder)
     EvxDesc *d_table;
     EvxInterResult *d_inter;
-    int16_t *d_records;
+    int16_t *d_records;             // per-macroblock slots written by K3
+    int16_t *d_dense;               // packed raster-order records (K7) / decoder input
+    int *d_row_records;
     int *d_record_slot;
     uint32_t *d_order;
     int *d_sync;
@@ -120,7 +123,7 @@ int evxgpu_destroy(evxgpu_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->src_mem);
     for (int i = 0; i < 8; ++i) cudaFree(h->ring_mem[i]);
-    cudaFree(h->d_rgb); cudaFree(h->d_table); cudaFree(h->d_inter); cudaFree(h->d_records);
+    cudaFree(h->d_rgb); cudaFree(h->d_table); cudaFree(h->d_inter); cudaFree(h->d_records); cudaFree(h->d_dense); cudaFree(h->d_row_records);
     cudaFree(h->d_record_slot); cudaFree(h->d_order); cudaFree(h->d_sync); cudaFree(h->d_counters);
     cudaFreeHost(h->h_table); cudaFreeHost(h->h_records); cudaFreeHost(h->h_record_slot); cudaFreeHost(h->h_sync); cudaFreeHost(h->h_rgb);
     for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[k][e]) cudaEventDestroy(h->ev[k][e]);
@@ -163,6 +166,8 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     ok = ok && cudaMalloc(&h->d_table, (size_t) h->nmb * 16) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_inter, (size_t) h->nmb * (cfg->ref_count - 1) * sizeof(EvxInterResult)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_records, (size_t) h->nmb * 384 * 2) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_dense, (size_t) h->nmb * 384 * 2) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_row_records, (size_t) h->g.mbh * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_record_slot, (size_t) h->nmb * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_order, (size_t) h->nmb * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
@@ -208,6 +213,8 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     {
         cudaError_t e = cudaFuncSetAttribute(evx_inter_search, cudaFuncAttributeMaxDynamicSharedMemorySize, EVX_K2_SMEM);
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_inter_search)", e); }
+        e = cudaFuncSetAttribute(evx_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EvxK3Smem));
+        if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_wavefront)", e); }
     }
     for (int k = 0; k < EVXGPU_T_COUNT; ++k)
         for (int e = 0; e < 2; ++e)
@@ -316,13 +323,15 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
     for (int i = 0; i < 8; ++i) p.ring[i] = h->ring[i];
     p.g = h->g; p.R = h->cfg.ref_count; p.linear = h->cfg.linear_quant;
     p.frame_type = frame_type; p.quality = quality; p.frame_index = index;
-    p.inter = h->d_inter; p.table = h->d_table; p.records = h->d_records; p.record_slot = h->d_record_slot;
-    p.order = h->d_order; p.sync = h->d_sync; p.counters = h->d_counters;
+    p.inter = h->d_inter; p.table = h->d_table; p.records = h->d_records; p.row_records = h->d_row_records;
+    p.sync = h->d_sync; p.counters = h->d_counters;
     CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
     t_begin(h, EVXGPU_T_WAVEFRONT);
-    evx_wavefront<<<h->wave_grid, EVX_K3_THREADS, 0, h->stream>>>(p);
+    // one CTA per macroblock row; rows are claimed by ticket, so any residency is deadlock-free
+    evx_wavefront<<<h->g.mbh, EVX_K3_NT, sizeof(EvxK3Smem), h->stream>>>(p);
+    evx_pack_records<<<h->g.mbh, 256, 0, h->stream>>>(h->d_table, h->d_records, h->d_row_records, h->d_dense, h->d_sync + 1, h->g);
     t_end(h, EVXGPU_T_WAVEFRONT);
-    h->launches++;
+    h->launches += 2;
     CK(cudaGetLastError());
     return 0;
 }
@@ -361,7 +370,6 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     // the records leave before deblocking so the copy overlaps it
     CK(cudaMemcpyAsync(h->h_sync, h->d_sync, 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(h->h_table, h->d_table, (size_t) h->nmb * 16, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_record_slot, h->d_record_slot, (size_t) h->nmb * 4, cudaMemcpyDeviceToHost, h->stream));
     if ((rc = launch_deblock(h, frame_index))) return rc;
     h->pending_encode = true;
     return 0;
@@ -380,18 +388,10 @@ int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_
     *n_noncopy = (uint32_t) n;
     if (n && records_out)
     {
-        CK(cudaMemcpyAsync(h->h_records, h->d_records, (size_t) n * 384 * 2, cudaMemcpyDeviceToHost, h->stream));
+        // K7 already packed the records in raster order; straight into the caller's buffer
+        // (asynchronous DMA when that buffer is pinned, see evxgpu_host_alloc)
+        CK(cudaMemcpyAsync(records_out, h->d_dense, (size_t) n * 384 * 2, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        // device slots are handed out in completion order; the ABI promises raster order
-        uint32_t k = 0;
-        for (int mb = 0; mb < h->nmb; ++mb)
-        {
-            int slot = h->h_record_slot[mb];
-            if (slot < 0) continue;
-            memcpy(records_out + (size_t) k * 384, h->h_records + (size_t) slot * 384, 768);
-            ++k;
-        }
-        if (k != (uint32_t) n) return fail(5, "evxgpu_encode_collect: slot table inconsistent");
     }
     return 0;
 }
@@ -416,11 +416,11 @@ int evxgpu_decode_submit(evxgpu_handle *h, const evxgpu_block_desc *table, const
     if (k) memcpy(h->h_records, records, (size_t) k * 768);
     CK(cudaMemcpyAsync(h->d_table, h->h_table, (size_t) h->nmb * 16, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_record_slot, h->h_record_slot, (size_t) h->nmb * 4, cudaMemcpyHostToDevice, h->stream));
-    if (k) CK(cudaMemcpyAsync(h->d_records, h->h_records, (size_t) k * 768, cudaMemcpyHostToDevice, h->stream));
+    if (k) CK(cudaMemcpyAsync(h->d_dense, h->h_records, (size_t) k * 768, cudaMemcpyHostToDevice, h->stream));
     EvxK5Params p;
     for (int i = 0; i < 8; ++i) p.ring[i] = h->ring[i];
     p.g = h->g; p.R = h->cfg.ref_count; p.linear = h->cfg.linear_quant; p.frame_index = frame_index;
-    p.table = h->d_table; p.records = h->d_records; p.record_slot = h->d_record_slot; p.order = h->d_order; p.sync = h->d_sync;
+    p.table = h->d_table; p.records = h->d_dense; p.record_slot = h->d_record_slot; p.order = h->d_order; p.sync = h->d_sync;
     CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
     t_begin(h, EVXGPU_T_DECODE_RECON);
     evx_decode_recon<<<h->wave_grid, EVX_K5_THREADS, 0, h->stream>>>(p);
@@ -498,6 +498,14 @@ int evxgpu_stage_set_block_table(evxgpu_handle *h, const evxgpu_block_desc *tabl
     if (!h || !table) return 1;
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpy(h->d_table, table, (size_t) h->nmb * 16, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas)
+{
+    if (!h) return 1;
+    if (ctas <= 0) ctas = std::min(h->g.mbh, (h->g.mbw + 2) / 3) + 8;
+    h->wave_grid = std::max(1, std::min(h->nmb, ctas));
     return 0;
 }
 

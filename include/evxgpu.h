@@ -112,6 +112,8 @@ int evxgpu_enable_timing(evxgpu_handle *h, int on);
 /* evaluated full-pel candidates / sub-pel tests since the last reset (SURVEY 8d roofline unit) */
 int evxgpu_get_counters(evxgpu_handle *h, uint64_t *fullpel, uint64_t *subpel, int reset);
 uint64_t evxgpu_launch_count(const evxgpu_handle *h);
+/* tuning knob: number of persistent CTAs of the decoder's wavefront kernel (0 = default) */
+int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas);
 
 /* integer-pipe micro-benchmark (the roofline denominator MEASURED_PEAKS.json lacks):
  * kind 0 IADD3, 1 VIADDMNMX.S16x2, 2 IDP.2A, 3 the 3:2 mix the search kernels issue.
