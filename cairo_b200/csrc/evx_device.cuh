@@ -126,6 +126,27 @@ __device__ __forceinline__ void evx_accept_subpel(EvxSel &s, int i, int j, int q
     if (take) { s.sp_enabled = 1; s.sp_amount = quarter; s.sp_index = evx_frac_index(i, j); s.sad = sad; s.mad = mad; }
 }
 
+// Branch-free forms of the two acceptance rules for the replay loops of K3 (same truth tables
+// as evx_accept_fullpel / evx_accept_subpel; `legal` gates the whole update).
+__device__ __forceinline__ void evx_replay_fullpel(EvxSel &s, bool legal, int sad, int mad, int ssd, int x, int y, int thr)
+{
+    const bool closer = ssd < s.ssd;
+    const bool t1 = (mad < s.mad) | ((mad == s.mad) & closer);
+    const bool t2 = (sad < s.sad) | ((sad == s.sad) & closer & ((uint32_t) sad < EVX_SAD_CAP)) | (mad < thr);
+    const bool take = legal & ((s.mad < thr) ? t1 : t2);
+    s.bx = take ? x : s.bx; s.by = take ? y : s.by;
+    s.sad = take ? sad : s.sad; s.ssd = take ? ssd : s.ssd; s.mad = take ? mad : s.mad;
+}
+
+__device__ __forceinline__ void evx_replay_subpel(EvxSel &s, bool legal, int index, int quarter, int sad, int mad, int thr)
+{
+    const bool t1 = mad < s.mad;
+    const bool t2 = ((sad < s.sad) & ((uint32_t) sad < EVX_SAD_CAP)) | (mad < thr);
+    const bool take = legal & ((s.mad < thr) ? t1 : t2);
+    s.sp_enabled = take ? 1 : s.sp_enabled; s.sp_amount = take ? quarter : s.sp_amount; s.sp_index = take ? index : s.sp_index;
+    s.sad = take ? sad : s.sad; s.mad = take ? mad : s.mad;
+}
+
 __device__ __forceinline__ EvxDesc evx_desc_from_sel(const EvxSel &s, int intra, int target, int px, int py, int thr)
 {
     int type = intra ? EVX_T_INTRA : 0;
@@ -220,6 +241,24 @@ __device__ __forceinline__ void evx_load_block_ring(const EvxRingWin &win, int x
         b.w[4] = win.u[crow + (c0 & 31)];
         b.w[5] = win.v[crow + (c0 & 31)];
     }
+}
+
+// Branch-free variant (both neighbouring words are always fetched and the parity picks the
+// byte selector), so two candidates of one warp can be scheduled in the same basic block.
+__device__ __forceinline__ void evx_load_block_ring_bf(const EvxRingWin &win, int x, int y, int lane, EvxLaneBlock &b)
+{
+    const uint32_t *row = win.y + (y - win.oy + (lane >> 3)) * EVX_RING_PWY;
+    const int w0 = (x >> 1) + (lane & 7);
+    const uint32_t sel = (x & 1) ? 0x5432u : 0x3210u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        b.w[k] = __byte_perm(row[4 * k * EVX_RING_PWY + (w0 & 63)], row[4 * k * EVX_RING_PWY + ((w0 + 1) & 63)], sel);
+    const int cx = x >> 1;
+    const int crow = ((y >> 1) - win.coy + (lane >> 2)) * EVX_RING_PWC;
+    const int c0 = (cx >> 1) + (lane & 3);
+    const uint32_t csel = (cx & 1) ? 0x5432u : 0x3210u;
+    b.w[4] = __byte_perm(win.u[crow + (c0 & 31)], win.u[crow + ((c0 + 1) & 31)], csel);
+    b.w[5] = __byte_perm(win.v[crow + (c0 & 31)], win.v[crow + ((c0 + 1) & 31)], csel);
 }
 
 // The source macroblock of a warp, in the lane layout above: packed negation (for

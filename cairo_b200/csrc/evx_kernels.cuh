@@ -313,6 +313,7 @@ struct EvxMbShared
     int16_t bufb[384];
     int16_t lut[64];         // DCT basis, xftables.h:57-67
     int16_t qmi[64], qmt[64];
+    uint32_t recip[128];     // ceil(2^32 / d): exact n/d = umulhi(n, recip[d]) for n < 2^26, 2 <= d < 128
     int red[3 * 32];
     int qp, var;
 };
@@ -341,6 +342,39 @@ __device__ __forceinline__ void evx_init_tables(EvxMbShared &sh, int tid, int nt
         sh.qmi[k] = EVX_QM_INTRA[k];
         sh.qmt[k] = EVX_QM_INTER[k];
     }
+    for (int d = tid; d < 128; d += nt) sh.recip[d] = d >= 2 ? (uint32_t) ((0x100000000ull + (unsigned) d - 1) / (unsigned) d) : 0u;
+}
+
+// rounded_div (math.h:228-236) for 2 <= d < 128 by multiply-high with M = ceil(2^32/d).  With
+// M*d = 2^32 + e, 0 <= e < d, floor(a*M / 2^32) == floor(a/d) whenever a*e < 2^32, i.e. for every
+// a < 2^25; here a = |n| + d/2 <= 32767*16 + 63 < 2^20.
+__device__ __forceinline__ int evx_rdiv_recip(int n, int d, const uint32_t *recip)
+{
+    uint32_t a = (uint32_t) (n < 0 ? -n : n) + (uint32_t) (d >> 1);
+    int q = (int) __umulhi(a, recip[d]);
+    return n < 0 ? -q : q;
+}
+
+// evx_quant without hardware division (the divisors are matrix entries 8..45, 2*qp <= 62, dc scales <= 46)
+__device__ __forceinline__ int evx_quant_fast(int s, int pos, int mode, int qp, int linear, const int16_t *qm_intra, const int16_t *qm_inter, const uint32_t *recip)
+{
+    int out;
+    if (linear)
+    {
+        if (mode < 2) out = (short) evx_rdiv_recip(s, qp << 1, recip);
+        else { int m = (short) (evx_abs16(s) - (qp >> 1)); out = (short) evx_rdiv_recip(m, qp << 1, recip); out = (short) (out * evx_sign(s)); }
+    }
+    else if (mode < 2)
+    {
+        if (pos == 0) out = (short) evx_rdiv_recip(s, mode == 0 ? evx_luma_dc_scale(qp) : evx_chroma_dc_scale(qp), recip);
+        else out = (short) evx_rdiv_recip(evx_rdiv_recip(s * 16, qm_intra[pos], recip), qp << 1, recip);
+    }
+    else
+    {
+        int f = (short) evx_rdiv_recip(s * 16, qm_inter[pos], recip);
+        out = (short) evx_rdiv_recip(f - evx_sign(f) * qp, qp << 1, recip);
+    }
+    return out;
 }
 
 // forward 8x8 passes (transform.cpp:264-301): in[b][line][k] -> out, scale after the sum
@@ -463,6 +497,21 @@ __device__ __forceinline__ int evx_ld_acquire(const int *p)
     return v;
 }
 
+// Polling with an acquire load costs an L1 invalidate (CCTL.IVALL) per poll, which stalls the
+// LSU the compute warps of the same SM are using; poll relaxed, fence once on success.
+__device__ __forceinline__ int evx_ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void evx_wait_ge(const int *p, int need)
+{
+    while (evx_ld_relaxed(p) < need) __nanosleep(100);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
 __device__ __forceinline__ void evx_st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -470,12 +519,8 @@ __device__ __forceinline__ void evx_st_release(int *p, int v)
 
 __device__ __forceinline__ void evx_wait_deps(const int *progress, int bx, int by, int mbw)
 {
-    if (bx > 0) while (evx_ld_acquire(progress + by) < bx) __nanosleep(20);
-    if (by > 0)
-    {
-        int need = min(bx + 2, mbw - 1) + 1;
-        while (evx_ld_acquire(progress + by - 1) < need) __nanosleep(20);
-    }
+    if (bx > 0) evx_wait_ge(progress + by, bx);
+    if (by > 0) evx_wait_ge(progress + by - 1, min(bx + 2, mbw - 1) + 1);
 }
 
 // ------------------------------------------------------------------ K3 parameters (kernel in evx_wavefront.cuh)
@@ -494,6 +539,7 @@ struct EvxK3Params
     int *row_records;              // [mbh] non-copy macroblocks per row (for evx_pack_records)
     int *sync;                     // [0] row ticket, [1] total records, [2..] progress[mbh]
     unsigned long long *counters;
+    long long *prof;               // optional [mbh][6] per-row phase cycle sums (NULL in production)
 };
 
 // ------------------------------------------------------------------ K7: pack the non-copy macroblocks' records densely, raster order

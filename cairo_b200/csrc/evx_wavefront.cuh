@@ -7,13 +7,16 @@
 // schedule is a wavefront: (bx,by) after (bx-1,by) and (min(bx+2,W-1),by-1).
 //
 // Mapping: ONE CTA PER MACROBLOCK ROW, warp specialised --
-//   warps 0..8  compute: nine candidates of a 3x3 search round in parallel, then the
-//               transform path of the macroblock;
-//   warp  9     loader: one macroblock ahead, stages the source block, K2's inter results and
+//   warps 0..3  compute (one per SM sub-partition): the eight outer candidates of a 3x3 search
+//               round, two per warp (the centre is the running best, whose cost is already
+//               known), then the transform path of the macroblock.  More warps were slower:
+//               every warp replays the acceptance rule, and eight warps on four schedulers spent
+//               most of a round contending for issue slots and waiting at the barrier;
+//   warp  4     loader: one macroblock ahead, stages the source block, K2's inter results and
 //               their predictions, and slides the search window (a ring of 8 macroblock
 //               columns in shared memory) -- the 16 new columns of the three rows above once
 //               the row above has published them, the stale columns of the row below any time;
-//   warp 10     publisher: fences and releases progress[by] so the row below can follow.
+//   warp  5     publisher: fences and releases progress[by] so the row below can follow.
 // The left-neighbour dependency is thus inside the CTA (its reconstruction is written straight
 // into the window), and the inter-row latency (flag + L2 round trip) is paid once per row
 // instead of once per macroblock: frame time ~ (W + 3(H-1)) * T_mb + (H-1) * latency.
@@ -21,7 +24,10 @@
 
 #include "evx_kernels.cuh"
 
-#define EVX_K3_CW 9
+#ifndef EVX_K3_CW
+#define EVX_K3_CW 4               // compute warps: one per SM sub-partition
+#endif
+#define EVX_K3_CPW (8 / EVX_K3_CW)  // search cells (and sub-pel directions) per compute warp
 #define EVX_K3_CT (EVX_K3_CW * 32)
 #define EVX_K3_NT (EVX_K3_CT + 64)
 #define EVX_K3_ROWS 80            // window rows py-48 .. py+31
@@ -38,7 +44,8 @@ struct EvxK3Smem
     int4 idesc[2][EVX_MAXREF];
     int isad[2][EVX_MAXREF + 1];
     EvxMbShared sh;
-    int4 cand[2][16];
+    int4 cand[2][16];                         // per candidate: {key1, key1-if-taken, key2, flags}  (sub-pel: {sad, mad, 0, legal})
+    int4 cval[2][16];                         // per candidate: {sad, mad, ssd, 0}
     uint64_t full[2], empty[2];
     int done;                                 // macroblocks of this row whose reconstruction is stored
     int row;
@@ -142,7 +149,7 @@ __device__ __forceinline__ void evx_k3_loader(EvxK3Smem &S, const EvxK3Params &p
         if (by > 0)
         {
             const int need = min(n + 2, g.mbw - 1) + 1;
-            if (lane == 0) while (evx_ld_acquire(progress + by - 1) < need) __nanosleep(32);
+            if (lane == 0) evx_wait_ge(progress + by - 1, need);
             __syncwarp();
             const int first = n == 0 ? 0 : n + 2, last = min(n + 2, g.mbw - 1);
             for (int col = first; col <= last; ++col)
@@ -194,6 +201,24 @@ __device__ __forceinline__ void evx_k3_loader(EvxK3Smem &S, const EvxK3Params &p
 
 // ---------------------------------------------------------------- compute warps
 
+// Sortable form of a full-pel candidate for the acceptance replay (motion.cpp:111-149):
+//   x = key1   = sad:ssd'  with ssd' = 4095 ("infinite") when sad >= 8192 -- that disables the
+//                tie rule exactly where the reference's `&& sad < 8192` does;
+//   y = key1 the state takes on if this candidate is accepted (true ssd);
+//   z = key2   = mad:ssd   (the copy-mode order);   w = flags: bit0 legal, bit1 mad < thr.
+// ssd <= 32^2 + 48^2 = 3328 < 4095 for every reachable position; sad, mad are clamped to 20 bits.
+__device__ __forceinline__ int4 evx_candidate_keys(int sad, int mad, int ssd, int thr)
+{
+    const uint32_t hi1 = (uint32_t) min(sad, 0xFFFFE) << 12;
+    const uint32_t z = (uint32_t) min(ssd, 4095);
+    int4 r;
+    r.x = (int) (hi1 | ((uint32_t) sad < EVX_SAD_CAP ? z : 4095u));
+    r.y = (int) (hi1 | z);
+    r.z = (int) (((uint32_t) min(mad, 0xFFFFE) << 12) | z);
+    r.w = 1 | (mad < thr ? 2 : 0);
+    return r;
+}
+
 __device__ __forceinline__ bool evx_intra_legal(int x, int y, int px, int py, const EvxGeom &g)
 {
     return !(y > py - EVX_MB && x > px - EVX_MB) && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);   // motion.cpp:238-248
@@ -221,11 +246,14 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
 
     uint32_t n_full = 0, n_sub = 0;
     int row_records = 0;
+    long long prof[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }, tprev = clock64();
+#define EVX_K3_PROF(k) do { if (p.prof) { long long tn = clock64(); prof[k] += tn - tprev; tprev = tn; } } while (0)
 
     for (int n = 0; n < g.mbw; ++n)
     {
         const int slot = n & 1, px = n * EVX_MB, mb = by * g.mbw + n;
         evx_mbar_wait(&S.full[slot], (uint32_t) ((n >> 1) & 1));
+        EVX_K3_PROF(0);
         const int16_t *srcb = S.src[slot];
 
         EvxLaneSrc src;
@@ -259,63 +287,119 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         {
             const int step = EVX_SEARCH_RADIUS >> (round == 0 ? 0 : round);
             const int top = round == 0 ? -2 : -1;          // first round scans rows -32,-16,0 (motion.cpp:384-386)
+            // Round 0: grid cells 0..7 are evaluated (cells 7,8 = (0,0),(16,0) are never legal).
+            // Later rounds: the centre cell 4 is the running best itself; its sad/mad/ssd are the
+            // state's own (it was evaluated when it was accepted), so only the 8 outer cells run.
+            // Every cell is evaluated unconditionally (any position a round can name lies inside the
+            // staged window rows, and the ring masks the columns); illegal ones are flagged, not skipped,
+            // which keeps the cells of a warp in one basic block.
+#pragma unroll
+            for (int q = 0; q < EVX_K3_CPW; ++q)
             {
-                const int x = s.bx + (warp % 3 - 1) * step, y = s.by + (top + warp / 3) * step;
-                int4 res = make_int4(0, 0, 0, 0);
-                if (evx_intra_legal(x, y, px, py, g))
+                const int k = warp + q * EVX_K3_CW;                       // 0..7
+                const int cell = round == 0 ? k : (k < 4 ? k : k + 1);
+                const int x = s.bx + (cell % 3 - 1) * step, y = s.by + (top + cell / 3) * step;
+                EvxLaneBlock ref;
+                int sad, mad;
+                evx_load_block_ring_bf(win, x, y, lane, ref);
+                evx_block_cost(ref, src, sad, mad);
+                const int ssd = (x - px) * (x - px) + (y - py) * (y - py);
+                int4 res = evx_candidate_keys(sad, mad, ssd, thr);
+                if (!evx_intra_legal(x, y, px, py, g)) res.w = 0;
+                if (lane == 0) { S.cand[buf][cell] = res; S.cval[buf][cell] = make_int4(sad, mad, ssd, 0); }
+            }
+            if (warp == 0 && lane == 0)
+            {
+                if (round == 0) S.cand[buf][8] = make_int4(0, 0, 0, 0);
+                else
                 {
-                    EvxLaneBlock ref;
-                    int sad, mad;
-                    evx_load_block_ring(win, x, y, lane, ref);
-                    evx_block_cost(ref, src, sad, mad);
-                    res = make_int4(sad, mad, (x - px) * (x - px) + (y - py) * (y - py), 1);
+                    int4 c4 = evx_candidate_keys(s.sad, s.mad, s.ssd, thr);
+                    if (s.bx == px && s.by == py) c4.w = 0;
+                    S.cand[buf][4] = c4;
+                    S.cval[buf][4] = make_int4(s.sad, s.mad, s.ssd, 0);
                 }
-                if (lane == 0) S.cand[buf][warp] = res;
             }
             evx_compute_sync();
-            const int basex = s.bx, basey = s.by;
-#pragma unroll
-            for (int c = 0; c < 9; ++c)
+            // The reference accepts candidates sequentially (motion.cpp:111-149).  With the candidates
+            // as sortable keys that fold has a closed form, evaluated here lane-parallel (lane c = cell c):
+            //   * already in copy mode (best_mad < thr): every take needs (mad,ssd) < (best_mad,best_ssd),
+            //     so the survivor is the FIRST minimum of key2, if it beats the state;
+            //   * otherwise, if some legal cell has mad < thr, the first such cell c* is taken
+            //     unconditionally and flips the state to copy mode: survivor = first minimum of key2 over c >= c*;
+            //   * otherwise every take needs (sad,ssd') < (best_sad,best_ssd): survivor = first minimum of key1.
+            // (key1 carries ssd' = "infinite" for sad >= 8192, which is exactly the reference's tie rule.)
             {
-                const int4 v = S.cand[buf][c];
-                if (!v.w) continue;
-                n_full++;
-                bool take;
-                if (s.mad < thr) take = v.y < s.mad || (v.y == s.mad && v.z < s.ssd);
-                else take = v.x < s.sad || (v.x == s.sad && v.z < s.ssd && (uint32_t) v.x < EVX_SAD_CAP) || v.y < thr;
-                if (take) { s.bx = basex + (c % 3 - 1) * step; s.by = basey + (top + c / 3) * step; s.sad = v.x; s.mad = v.y; s.ssd = v.z; }
+                const int4 v = lane < 9 ? S.cand[buf][lane] : make_int4(0, 0, 0, 0);
+                const bool legal = (v.w & 1) != 0;
+                const unsigned legal_mask = __ballot_sync(0xFFFFFFFFu, legal);
+                const unsigned lt_mask = __ballot_sync(0xFFFFFFFFu, legal && (v.w & 2));
+                n_full += __popc(legal_mask);
+                const bool copy0 = s.mad < thr;
+                uint32_t key, init;
+                unsigned elig = legal_mask;
+                if (copy0) { key = (uint32_t) v.z; init = ((uint32_t) min(s.mad, 0xFFFFE) << 12) | (uint32_t) min(s.ssd, 4095); }
+                else if (lt_mask) { key = (uint32_t) v.z; elig &= 0xFFFFFFFFu << (__ffs(lt_mask) - 1); init = 0xFFFFFFFFu; }
+                else { key = (uint32_t) v.x; init = ((uint32_t) min(s.sad, 0xFFFFE) << 12) | (uint32_t) min(s.ssd, 4095); }
+                const uint32_t mykey = ((elig >> lane) & 1u) ? key : 0xFFFFFFFFu;
+                const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, mykey);
+                if (m < init)
+                {
+                    const int wcell = __ffs(__ballot_sync(0xFFFFFFFFu, mykey == m)) - 1;
+                    const int4 val = S.cval[buf][wcell];
+                    s.bx += (wcell % 3 - 1) * step; s.by += (top + wcell / 3) * step;
+                    s.sad = val.x; s.mad = val.y; s.ssd = val.z;
+                }
             }
             buf ^= 1;
         }
-        // ---- intra sub-pel, motion.cpp:277-317: warp d < 8 takes direction d (both blends)
+        EVX_K3_PROF(1);
+        // ---- intra sub-pel, motion.cpp:277-317: eight directions, both blends each
         {
-            const int d = warp < 4 ? warp : warp + 1;          // skip the centre
-            const int j = d / 3 - 1, i = d % 3 - 1;
-            const int x = s.bx + i, y = s.by + j;
-            int4 res = make_int4(0, 0, 0, 0), res2 = make_int4(0, 0, 0, 0);
-            if (warp < 8 && evx_intra_legal(x, y, px, py, g))
+#pragma unroll
+            for (int q = 0; q < EVX_K3_CPW; ++q)
             {
+                const int k = warp + q * EVX_K3_CW;                       // direction slot 0..7
+                const int d = k < 4 ? k : k + 1;                          // skip the centre
+                const int x = s.bx + d % 3 - 1, y = s.by + d / 3 - 1;
                 EvxLaneBlock best, nb;
                 int shh, mh, sq, mq;
-                evx_load_block_ring(win, s.bx, s.by, lane, best);
-                evx_load_block_ring(win, x, y, lane, nb);
+                evx_load_block_ring_bf(win, s.bx, s.by, lane, best);
+                evx_load_block_ring_bf(win, x, y, lane, nb);
                 evx_subpel_cost(best, nb, src, shh, mh, sq, mq);
-                res = make_int4(shh, mh, 0, 1); res2 = make_int4(sq, mq, 0, 1);
+                const int ok = evx_intra_legal(x, y, px, py, g) ? 1 : 0;
+                if (lane == 0) { S.cand[buf][2 * k] = make_int4(shh, mh, 0, ok); S.cand[buf][2 * k + 1] = make_int4(sq, mq, 0, ok); }
             }
-            if (lane == 0 && warp < 8) { S.cand[buf][2 * warp] = res; S.cand[buf][2 * warp + 1] = res2; }
             evx_compute_sync();
-#pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8)
+            // sub-pel acceptance (motion.cpp:151-223), same closed form over the 16 tests in reference
+            // order (direction-major, half before quarter): copy mode -> first minimum of mad;
+            // else a test with mad < thr exists -> first minimum of mad from the first such test on;
+            // else -> first minimum of sad among tests with sad < 8192.
             {
-                const int4 h = S.cand[buf][2 * w8], q = S.cand[buf][2 * w8 + 1];
-                if (!h.w) continue;
-                const int dd = w8 < 4 ? w8 : w8 + 1;
-                n_sub += 2;
-                evx_accept_subpel(s, dd % 3 - 1, dd / 3 - 1, 0, h.x, h.y, thr);
-                evx_accept_subpel(s, dd % 3 - 1, dd / 3 - 1, 1, q.x, q.y, thr);
+                const int4 v = lane < 16 ? S.cand[buf][lane] : make_int4(0, 0, 0, 0);
+                const bool legal = v.w != 0;
+                const unsigned legal_mask = __ballot_sync(0xFFFFFFFFu, legal);
+                const unsigned lt_mask = __ballot_sync(0xFFFFFFFFu, legal && v.y < thr);
+                const unsigned cap_mask = __ballot_sync(0xFFFFFFFFu, legal && (uint32_t) v.x < EVX_SAD_CAP);
+                n_sub += __popc(legal_mask);
+                const bool copy0 = s.mad < thr;
+                int key, init;
+                unsigned elig = legal_mask;
+                if (copy0) { key = v.y; init = s.mad; }
+                else if (lt_mask) { key = v.y; elig &= 0xFFFFFFFFu << (__ffs(lt_mask) - 1); init = EVX_BIG; }
+                else { key = v.x; elig = cap_mask; init = s.sad; }
+                const int mykey = ((elig >> lane) & 1u) ? key : EVX_BIG;
+                const int m = __reduce_min_sync(0xFFFFFFFFu, mykey);
+                if (m < init)
+                {
+                    const int wt = __ffs(__ballot_sync(0xFFFFFFFFu, mykey == m)) - 1;
+                    const int dd = (wt >> 1) < 4 ? (wt >> 1) : (wt >> 1) + 1;
+                    s.sp_enabled = 1; s.sp_amount = wt & 1; s.sp_index = evx_frac_index(dd % 3 - 1, dd / 3 - 1);
+                    s.sad = __shfl_sync(0xFFFFFFFFu, v.x, wt); s.mad = __shfl_sync(0xFFFFFFFFu, v.y, wt);
+                }
             }
         }
 
+        EVX_K3_PROF(2);
         // ---- classify, encode.cpp:17-67
         EvxDesc d = evx_desc_from_sel(s, 1, 0, px, py, thr);
         int best_sad = s.sad, best_ref = -1;
@@ -363,6 +447,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             }
         }
         evx_compute_sync();
+        EVX_K3_PROF(3);
 
         // reconstruction target: global ring slot + our own window rows (py..py+15 -> 48..63)
         auto store_recon = [&](int e, int v)
@@ -417,7 +502,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             // compute_block_variance2 over the 16x16 luma coefficients except (0,0) (analysis.h:176-198)
             {
                 uint32_t sum = 0, sq = 0; int cnt = 0;
-                if (tid >= 1 && tid < 256) { int t = sh.bufa[tid]; if (t) { sum = (uint32_t) t; sq = (uint32_t) (t * t); cnt = 1; } }
+                for (int e = tid; e < 256; e += EVX_K3_CT) { int t = e ? sh.bufa[e] : 0; if (t) { sum += (uint32_t) t; sq += (uint32_t) (t * t); cnt++; } }
                 sum = __reduce_add_sync(0xFFFFFFFFu, sum); sq = __reduce_add_sync(0xFFFFFFFFu, sq); cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
                 if (lane == 0) { sh.red[warp] = (int) sum; sh.red[32 + warp] = (int) sq; sh.red[64 + warp] = cnt; }
                 evx_compute_sync();
@@ -426,7 +511,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             {
                 uint32_t Ssum = 0, Q = 0; int C = 0;
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) { Ssum += (uint32_t) sh.red[w8]; Q += (uint32_t) sh.red[32 + w8]; C += sh.red[64 + w8]; }
+                for (int w8 = 0; w8 < EVX_K3_CW; ++w8) { Ssum += (uint32_t) sh.red[w8]; Q += (uint32_t) sh.red[32 + w8]; C += sh.red[64 + w8]; }
                 if (C > 0) var = (int) (Q - (uint32_t) evx_rdiv((int) (Ssum * Ssum), C));
                 // query_block_quantization_parameter, quantize.cpp:60-77
                 const int q = p.quality & 0xFF;
@@ -441,7 +526,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             for (int e = tid; e < 384; e += EVX_K3_CT)
             {
                 const int mode = intra_q ? ((e >> 6) < 4 ? 0 : 1) : 2;
-                const int qv = evx_quant(sh.bufa[e], e & 63, mode, qp, p.linear, sh.qmi, sh.qmt);
+                const int qv = evx_quant_fast(sh.bufa[e], e & 63, mode, qp, p.linear, sh.qmi, sh.qmt, sh.recip);
                 rec[evx_record_index(e)] = (int16_t) qv;
                 sh.bufb[e] = (int16_t) evx_dequant(qv, e & 63, mode, qp, p.linear, sh.qmi, sh.qmt);
             }
@@ -471,6 +556,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             row_records++;
         }
         evx_compute_sync();
+        EVX_K3_PROF(4);
         if (tid == 0)
         {
             evx_mbar_arrive(&S.empty[slot]);
@@ -480,6 +566,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     if (tid == 0)
     {
         p.row_records[by] = row_records;
+        if (p.prof) for (int k = 0; k < 10; ++k) p.prof[by * 10 + k] = prof[k];
         atomicAdd(&p.counters[0], (unsigned long long) n_full);
         atomicAdd(&p.counters[1], (unsigned long long) n_sub);
     }

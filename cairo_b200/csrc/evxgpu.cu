@@ -78,6 +78,7 @@ struct evxgpu_handle
     uint64_t launches;
     bool pending_encode, pending_decode;
     int wave_grid;
+    long long *d_prof;
 };
 
 static size_t plane_elems(const EvxGeom &g) { return (size_t) g.w * g.h * 3 / 2; }
@@ -124,7 +125,7 @@ int evxgpu_destroy(evxgpu_handle *h)
     cudaFree(h->src_mem);
     for (int i = 0; i < 8; ++i) cudaFree(h->ring_mem[i]);
     cudaFree(h->d_rgb); cudaFree(h->d_table); cudaFree(h->d_inter); cudaFree(h->d_records); cudaFree(h->d_dense); cudaFree(h->d_row_records);
-    cudaFree(h->d_record_slot); cudaFree(h->d_order); cudaFree(h->d_sync); cudaFree(h->d_counters);
+    cudaFree(h->d_record_slot); cudaFree(h->d_order); cudaFree(h->d_sync); cudaFree(h->d_counters); cudaFree(h->d_prof);
     cudaFreeHost(h->h_table); cudaFreeHost(h->h_records); cudaFreeHost(h->h_record_slot); cudaFreeHost(h->h_sync); cudaFreeHost(h->h_rgb);
     for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[k][e]) cudaEventDestroy(h->ev[k][e]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -324,7 +325,7 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
     p.g = h->g; p.R = h->cfg.ref_count; p.linear = h->cfg.linear_quant;
     p.frame_type = frame_type; p.quality = quality; p.frame_index = index;
     p.inter = h->d_inter; p.table = h->d_table; p.records = h->d_records; p.row_records = h->d_row_records;
-    p.sync = h->d_sync; p.counters = h->d_counters;
+    p.sync = h->d_sync; p.counters = h->d_counters; p.prof = h->d_prof;
     CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
     t_begin(h, EVXGPU_T_WAVEFRONT);
     // one CTA per macroblock row; rows are claimed by ticket, so any residency is deadlock-free
@@ -506,6 +507,18 @@ int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas)
     if (!h) return 1;
     if (ctas <= 0) ctas = std::min(h->g.mbh, (h->g.mbw + 2) / 3) + 8;
     h->wave_grid = std::max(1, std::min(h->nmb, ctas));
+    return 0;
+}
+
+// debug: per-row phase cycle sums of the wavefront kernel's compute warps, 6 x int64 per row
+int evxgpu_debug_profile(evxgpu_handle *h, int enable, long long *out_host)
+{
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    if (enable && !h->d_prof) { CK(cudaMalloc(&h->d_prof, (size_t) h->g.mbh * 10 * 8)); CK(cudaMemset(h->d_prof, 0, (size_t) h->g.mbh * 10 * 8)); }
+    if (out_host && h->d_prof) CK(cudaMemcpy(out_host, h->d_prof, (size_t) h->g.mbh * 10 * 8, cudaMemcpyDeviceToHost));
+    if (!enable && h->d_prof) { cudaFree(h->d_prof); h->d_prof = NULL; }
     return 0;
 }
 

@@ -112,6 +112,8 @@ int evxgpu_enable_timing(evxgpu_handle *h, int on);
 /* evaluated full-pel candidates / sub-pel tests since the last reset (SURVEY 8d roofline unit) */
 int evxgpu_get_counters(evxgpu_handle *h, uint64_t *fullpel, uint64_t *subpel, int reset);
 uint64_t evxgpu_launch_count(const evxgpu_handle *h);
+/* debug: per-row phase cycle sums of the encoder wavefront kernel, 6 x int64 per macroblock row */
+int evxgpu_debug_profile(evxgpu_handle *h, int enable, long long *out_host);
 /* tuning knob: number of persistent CTAs of the decoder's wavefront kernel (0 = default) */
 int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas);
 
