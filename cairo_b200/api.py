@@ -142,11 +142,12 @@ class SliceWriter:
         table = np.ascontiguousarray(table)
         records = np.ascontiguousarray(records, dtype=np.int16).reshape(-1, 384)
         cap = self.n * 384 * 5 + 4096
-        out = np.zeros(cap, dtype=np.uint8)
+        if getattr(self, "_out", None) is None:
+            self._out = np.zeros(cap, dtype=np.uint8)
         bits = C.c_uint32(0)
-        st = self.L.evx1c_slice_writer_serialize(self.h, _p(table), _p(records), records.shape[0], _p(out), cap, C.byref(bits))
+        st = self.L.evx1c_slice_writer_serialize(self.h, _p(table), _p(records), records.shape[0], _p(self._out), cap, C.byref(bits))
         assert st == 0, st
-        return out[:(bits.value + 7) // 8].copy(), bits.value
+        return self._out[:(bits.value + 7) // 8].copy(), bits.value
 
 
 class SliceReader:

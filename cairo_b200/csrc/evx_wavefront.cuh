@@ -244,6 +244,16 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
 #pragma unroll
     for (int k = 0; k < 8; ++k) { lut_f[k] = evx_dct_lut(tid & 7, k); lut_i[k] = evx_dct_lut(k, tid & 7); }
 
+    // the search cells this warp owns: (dx,dy) in units of the round's step
+    int cdx0[EVX_K3_CPW], cdy0[EVX_K3_CPW], cdx[EVX_K3_CPW], cdy[EVX_K3_CPW], ccell0[EVX_K3_CPW], ccell[EVX_K3_CPW];
+#pragma unroll
+    for (int q = 0; q < EVX_K3_CPW; ++q)
+    {
+        const int k = warp + q * EVX_K3_CW;
+        ccell0[q] = k; cdx0[q] = k % 3 - 1; cdy0[q] = k / 3 - 2;          // round 0: rows -32,-16,0
+        ccell[q] = k < 4 ? k : k + 1; cdx[q] = ccell[q] % 3 - 1; cdy[q] = ccell[q] / 3 - 1;
+    }
+
     uint32_t n_full = 0, n_sub = 0;
     int row_records = 0;
     long long prof[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }, tprev = clock64();
@@ -296,9 +306,8 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
 #pragma unroll
             for (int q = 0; q < EVX_K3_CPW; ++q)
             {
-                const int k = warp + q * EVX_K3_CW;                       // 0..7
-                const int cell = round == 0 ? k : (k < 4 ? k : k + 1);
-                const int x = s.bx + (cell % 3 - 1) * step, y = s.by + (top + cell / 3) * step;
+                const int cell = round == 0 ? ccell0[q] : ccell[q];
+                const int x = s.bx + (round == 0 ? cdx0[q] : cdx[q]) * step, y = s.by + (round == 0 ? cdy0[q] : cdy[q]) * step;
                 EvxLaneBlock ref;
                 int sad, mad;
                 evx_load_block_ring_bf(win, x, y, lane, ref);
@@ -358,9 +367,8 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
 #pragma unroll
             for (int q = 0; q < EVX_K3_CPW; ++q)
             {
-                const int k = warp + q * EVX_K3_CW;                       // direction slot 0..7
-                const int d = k < 4 ? k : k + 1;                          // skip the centre
-                const int x = s.bx + d % 3 - 1, y = s.by + d / 3 - 1;
+                const int k = warp + q * EVX_K3_CW;                       // direction slot 0..7 (centre skipped)
+                const int x = s.bx + cdx[q], y = s.by + cdy[q];
                 EvxLaneBlock best, nb;
                 int shh, mh, sq, mq;
                 evx_load_block_ring_bf(win, s.bx, s.by, lane, best);

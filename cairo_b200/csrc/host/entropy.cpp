@@ -3,6 +3,9 @@
 
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 namespace evx {
 
 namespace {
@@ -39,18 +42,53 @@ const zigzag_tables ZZ;
 
 // ---------------------------------------------------------------- encoder side
 
+// The model divides by the number of symbols seen so far + 2 (abac.cpp:80-95), a divisor that
+// simply counts up.  floor(a / t) for a < 2^40 is the high half of a * ceil(2^64 / t) exactly
+// (error term a * (M*t - 2^64) < 2^40 * 2^24 < 2^64), so one table of reciprocals, shared by
+// every coder of the process and grown on demand, replaces the hardware divide on the bin path.
+class reciprocal_table
+{
+    static const size_t kMax = size_t(1) << 24;
+    uint64_t *m_;
+    std::atomic<size_t> size_;
+    std::mutex lock_;
+
+public:
+    reciprocal_table() : m_(new uint64_t[kMax]), size_(0) { grow(size_t(1) << 18); }
+    const uint64_t *data() const { return m_; }
+    size_t size() const { return size_.load(std::memory_order_acquire); }
+    void grow(size_t want)
+    {
+        std::lock_guard<std::mutex> g(lock_);
+        size_t have = size_.load(std::memory_order_relaxed);
+        if (want > kMax) want = kMax;
+        for (size_t t = have; t < want; ++t)
+            m_[t] = t < 2 ? 0 : (uint64_t) ((((unsigned __int128) 1 << 64) + t - 1) / t);
+        if (want > have) size_.store(want, std::memory_order_release);
+    }
+};
+reciprocal_table &recips() { static reciprocal_table t; return t; }
+
 class abac_writer
 {
-    uint32_t low_, high_, e3_, h0_, h1_;
+    uint32_t low_, high_, e3_, h0_, tot_;
     uint64_t acc_;
     uint32_t nacc_;
     uint8_t *out_;
     size_t pos_;
+    const uint64_t *recip_;
+    size_t recip_size_;
 
+    inline void flush_acc() { memcpy(out_ + pos_, &acc_, 8); pos_ += 8; acc_ = 0; nacc_ = 0; }
     inline void put(uint32_t bit)
     {
         acc_ |= (uint64_t) bit << nacc_;
-        if (++nacc_ == 64) { memcpy(out_ + pos_, &acc_, 8); pos_ += 8; acc_ = 0; nacc_ = 0; }
+        if (++nacc_ == 64) flush_acc();
+    }
+    // n <= 16 bits, value's bit (n-1) goes out first (the stream is LSB-first, so reverse them)
+    inline void put_msb_first(uint32_t value, uint32_t n)
+    {
+        for (uint32_t i = n; i-- > 0;) put((value >> i) & 1u);
     }
     inline void emit(uint32_t bit)        // write_bit + flush_inverse_bits, abac.cpp:156-178
     {
@@ -59,7 +97,11 @@ class abac_writer
     }
 
 public:
-    explicit abac_writer(uint8_t *out) : low_(0), high_(AB_MAX), e3_(0), h0_(1), h1_(1), acc_(0), nacc_(0), out_(out), pos_(0) {}
+    explicit abac_writer(uint8_t *out) : low_(0), high_(AB_MAX), e3_(0), h0_(1), tot_(2), acc_(0), nacc_(0), out_(out), pos_(0)
+    {
+        recip_ = recips().data();
+        recip_size_ = recips().size();
+    }
 
     size_t bytes_pending() const { return pos_ + 8; }
     void rebase(uint8_t *out) { out_ = out; }
@@ -67,21 +109,34 @@ public:
     // encode_symbol + resolve_encode_scaling, abac.cpp:97-121, 180-224
     inline void encode(uint32_t bit)
     {
-        const uint32_t range = high_ - low_;
-        const uint32_t mid = low_ + (h0_ <= 0xFFFFu ? (range * h0_) / (h0_ + h1_) : (uint32_t) (((uint64_t) range * h0_) / (h0_ + h1_)));
-        if (bit) { low_ = mid + 1; h1_++; } else { high_ = mid; h0_++; }
+        const uint64_t a = (uint64_t) (high_ - low_) * h0_;
+        uint32_t q;
+        if (__builtin_expect(tot_ < recip_size_, 1)) q = (uint32_t) (((unsigned __int128) a * recip_[tot_]) >> 64);
+        else
+        {
+            if (tot_ < (size_t(1) << 24)) { recips().grow((size_t) tot_ * 2); recip_size_ = recips().size(); }
+            q = (uint32_t) (a / tot_);
+        }
+        const uint32_t mid = low_ + q;
+        if (bit) low_ = mid + 1; else { high_ = mid; h0_++; }
+        tot_++;
+        // E1/E2: all leading bits on which low and high agree leave at once; the first of them
+        // is followed by the pending E3 bits (inverted), the rest go out verbatim
         for (;;)
         {
-            if (((high_ ^ low_) & 0x8000u) == 0)
-            {
-                const uint32_t msb = high_ >> 15;
-                low_ -= msb << 15; high_ -= msb << 15;
-                emit(msb);
-            }
-            else if (high_ <= AB_3QTR && low_ > AB_QTR) { high_ -= AB_QTR + 1; low_ -= AB_QTR + 1; e3_++; }
-            else break;
-            high_ = ((high_ << 1) & AB_MAX) | 1u;
-            low_ = (low_ << 1) & AB_MAX;
+            const uint32_t k = (uint32_t) __builtin_clz((high_ ^ low_) | 1u) - 16;      // 0..15 common leading bits
+            if (!k) break;
+            emit(high_ >> 15);
+            if (k > 1) put_msb_first((high_ >> (16 - k)) & ((1u << (k - 1)) - 1u), k - 1);
+            low_ = (low_ << k) & AB_MAX;
+            high_ = ((high_ << k) & AB_MAX) | ((1u << k) - 1u);
+        }
+        // E3: low = 01..., high = 10... (with the reference's 3*QTR = 0xBFFD quirk)
+        while (low_ > AB_QTR && high_ <= AB_3QTR && ((high_ ^ low_) & 0x8000u))
+        {
+            low_ = ((low_ - (AB_QTR + 1)) << 1) & AB_MAX;
+            high_ = (((high_ - (AB_QTR + 1)) << 1) & AB_MAX) | 1u;
+            e3_++;
         }
     }
 
