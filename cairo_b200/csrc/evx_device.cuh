@@ -285,10 +285,10 @@ __device__ __forceinline__ void evx_make_src(const EvxLaneBlock &b, EvxLaneSrc &
 // candidate against the warp's source block.  Per packed word: three VIADDMNMX.S16x2
 // (running max and min of ref-src, and relu(ref-src)) and two IDP.2A:
 //   sum|d| = 2*sum relu(d) - sum d,   max|d| = max(max d, -min d).
-__device__ __forceinline__ void evx_block_cost(const EvxLaneBlock &ref, const EvxLaneSrc &src, int &sad, int &mad)
+__device__ __forceinline__ void evx_block_cost_lane(const EvxLaneBlock &ref, const EvxLaneSrc &src, int &acc, int &m)
 {
     uint32_t amx = 0x80008000u, amn = 0x7FFF7FFFu;
-    int acc = src.lsum;
+    acc = src.lsum;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
     {
@@ -304,32 +304,65 @@ __device__ __forceinline__ void evx_block_cost(const EvxLaneBlock &ref, const Ev
         amx = __viaddmax_s16x2(ref.w[k], src.neg[k], amx);
         amn = __viaddmin_s16x2(ref.w[k], src.neg[k], amn);
     }
-    int m = max(max(evx_lo16(amx), evx_hi16(amx)), -min(evx_lo16(amn), evx_hi16(amn)));
+    m = max(max(evx_lo16(amx), evx_hi16(amx)), -min(evx_lo16(amn), evx_hi16(amn)));
+}
+
+__device__ __forceinline__ void evx_block_cost(const EvxLaneBlock &ref, const EvxLaneSrc &src, int &sad, int &mad)
+{
+    int acc, m;
+    evx_block_cost_lane(ref, src, acc, m);
     sad = __reduce_add_sync(0xFFFFFFFFu, acc);
     mad = __reduce_max_sync(0xFFFFFFFFu, m);
 }
 
 // One sub-pel direction: both the half- and the quarter-pel blend of `best` with its
 // neighbour `nb` (macroblock.h:203-241), SAD/MAD of each against the source.
+//
+// Fast path (every sample of both blocks in [0, 16383], i.e. always for real video): the
+// blends are computed on packed pairs.  For t >= 0 the reference's (t+1)/2 and (t+2)/4 are
+// plain floors, so   half = (a+b+1) >> 1   and   quarter = a + floor((b-a+2)/4), the latter
+// with a +0x4000 bias so the per-halfword shift can be a logical one.  Otherwise the exact
+// scalar form (negative sums round away from zero) is used.
 __device__ __forceinline__ void evx_subpel_cost(const EvxLaneBlock &best, const EvxLaneBlock &nb, const EvxLaneSrc &src,
                                                 int &sad_h, int &mad_h, int &sad_q, int &mad_q)
 {
-    int sh = 0, mh = 0, sq = 0, mq = 0;
+    uint32_t any = 0;
 #pragma unroll
-    for (int k = 0; k < 6; ++k)
+    for (int k = 0; k < 6; ++k) any |= best.w[k] | nb.w[k];
+    int sh, mh, sq, mq;
+    if (!__any_sync(0xFFFFFFFFu, (any & 0xC000C000u) != 0))
     {
+        EvxLaneBlock hb, qb;
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
+        for (int k = 0; k < 6; ++k)
         {
-            int a = half ? evx_hi16(best.w[k]) : evx_lo16(best.w[k]);
-            int b = half ? evx_hi16(nb.w[k]) : evx_lo16(nb.w[k]);
-            int s = half ? evx_hi16(src.pos[k]) : evx_lo16(src.pos[k]);
-            // the blended sample is stored as int16 before it is compared (macroblock.h:210, 230)
-            int dh = abs(s - (int) (short) evx_lerp_half(a, b));
-            int dq = abs(s - (int) (short) evx_lerp_quarter(a, b));
-            if (k < 4) { sh += dh; sq += dq; }
-            mh = max(mh, dh);
-            mq = max(mq, dq);
+            const uint32_t a = best.w[k], b = nb.w[k];
+            hb.w[k] = (__vadd2(__vadd2(a, b), 0x00010001u) >> 1) & 0x7FFF7FFFu;
+            const uint32_t d = __vadd2(b, __vadd2(~a, 0x40034003u));            // b - a + 2 + 0x4000 per halfword
+            qb.w[k] = __vadd2((d >> 2) & 0x3FFF3FFFu, __vadd2(a, 0xF000F000u));  // floor(d/4) - 0x1000 + a
+        }
+        evx_block_cost_lane(hb, src, sh, mh);
+        evx_block_cost_lane(qb, src, sq, mq);
+    }
+    else
+    {
+        sh = 0; mh = 0; sq = 0; mq = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+        {
+#pragma unroll
+            for (int half = 0; half < 2; ++half)
+            {
+                int a = half ? evx_hi16(best.w[k]) : evx_lo16(best.w[k]);
+                int b = half ? evx_hi16(nb.w[k]) : evx_lo16(nb.w[k]);
+                int s = half ? evx_hi16(src.pos[k]) : evx_lo16(src.pos[k]);
+                // the blended sample is stored as int16 before it is compared (macroblock.h:210, 230)
+                int dh = abs(s - (int) (short) evx_lerp_half(a, b));
+                int dq = abs(s - (int) (short) evx_lerp_quarter(a, b));
+                if (k < 4) { sh += dh; sq += dq; }
+                mh = max(mh, dh);
+                mq = max(mq, dq);
+            }
         }
     }
     sad_h = __reduce_add_sync(0xFFFFFFFFu, sh);

@@ -209,19 +209,27 @@ __device__ __forceinline__ void evx_inter_search_warp(const EvxWin &win, const E
     if (s.mad < thr) return;                       // already a copy block: no search (motion.cpp:452)
     for (int step = EVX_SEARCH_RADIUS; step > 0; step >>= 1)
     {
-        int basex = s.bx, basey = s.by;
-#pragma unroll 1
-        for (int j = -1; j <= 1; ++j)
+        // One 3x3 round (motion.cpp:254-275).  The eight outer cells are costed back to back (no
+        // dependence between them, so their loads and arithmetic overlap); the centre is the
+        // running best itself, whose sad/mad are already in the state.  Out-of-frame cells still
+        // lie inside the zero-filled TMA window, so they are costed too and simply not accepted.
+        const int basex = s.bx, basey = s.by;
+        int csad[9], cmad[9];
+        csad[4] = s.sad; cmad[4] = s.mad;
 #pragma unroll
-        for (int i = -1; i <= 1; ++i)
+        for (int c = 0; c < 9; ++c)
         {
-            int x = basex + i * step, y = basey + j * step;
-            if (x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB) continue;
-            int sad, mad;
-            evx_load_block(win, x, y, lane, ref);
-            evx_block_cost(ref, src, sad, mad);
-            n_full++;
-            evx_accept_fullpel(s, x, y, sad, mad, px, py, thr);
+            if (c == 4) continue;
+            evx_load_block(win, basex + (c % 3 - 1) * step, basey + (c / 3 - 1) * step, lane, ref);
+            evx_block_cost(ref, src, csad[c], cmad[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 9; ++c)
+        {
+            const int x = basex + (c % 3 - 1) * step, y = basey + (c / 3 - 1) * step;
+            const bool legal = !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);
+            n_full += legal;
+            evx_replay_fullpel(s, legal, csad[c], cmad[c], (x - px) * (x - px) + (y - py) * (y - py), x, y, thr);
         }
     }
     EvxLaneBlock best;

@@ -25,7 +25,7 @@
 #include "evx_kernels.cuh"
 
 #ifndef EVX_K3_CW
-#define EVX_K3_CW 4               // compute warps: one per SM sub-partition
+#define EVX_K3_CW 8               // compute warps
 #endif
 #define EVX_K3_CPW (8 / EVX_K3_CW)  // search cells (and sub-pel directions) per compute warp
 #define EVX_K3_CT (EVX_K3_CW * 32)
@@ -575,8 +575,8 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     {
         p.row_records[by] = row_records;
         if (p.prof) for (int k = 0; k < 10; ++k) p.prof[by * 10 + k] = prof[k];
-        atomicAdd(&p.counters[0], (unsigned long long) n_full);
-        atomicAdd(&p.counters[1], (unsigned long long) n_sub);
+        atomicAdd(&p.counters[2], (unsigned long long) n_full);
+        atomicAdd(&p.counters[3], (unsigned long long) n_sub);
     }
 }
 

@@ -172,7 +172,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     ok = ok && cudaMalloc(&h->d_record_slot, (size_t) h->nmb * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_order, (size_t) h->nmb * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&h->d_counters, 16) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_counters, 32) == cudaSuccess;
     ok = ok && cudaHostAlloc(&h->h_table, (size_t) h->nmb * 16, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&h->h_records, (size_t) h->nmb * 384 * 2, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&h->h_record_slot, (size_t) h->nmb * 4, cudaHostAllocDefault) == cudaSuccess;
@@ -236,7 +236,7 @@ int evxgpu_reset(evxgpu_handle *h)
     CK(cudaMemsetAsync(h->src_mem, 0, pe * 2, h->stream));
     for (int i = 0; i < h->cfg.ref_count; ++i) CK(cudaMemsetAsync(h->ring_mem[i], 0, pe * 2, h->stream));
     CK(cudaMemsetAsync(h->d_table, 0, (size_t) h->nmb * 16, h->stream));
-    CK(cudaMemsetAsync(h->d_counters, 0, 16, h->stream));
+    CK(cudaMemsetAsync(h->d_counters, 0, 32, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->pending_encode = h->pending_decode = false;
     return 0;
@@ -273,16 +273,25 @@ int evxgpu_get_timing(evxgpu_handle *h, float *ms_out)
     return 0;
 }
 
+int evxgpu_get_counters_split(evxgpu_handle *h, uint64_t *out4, int reset)
+{
+    if (!h || !out4) return 1;
+    CK(cudaSetDevice(h->device));
+    unsigned long long c[4];
+    CK(cudaMemcpyAsync(c, h->d_counters, 32, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 4; ++k) out4[k] = c[k];
+    if (reset) { CK(cudaMemsetAsync(h->d_counters, 0, 32, h->stream)); }
+    return 0;
+}
+
 int evxgpu_get_counters(evxgpu_handle *h, uint64_t *fullpel, uint64_t *subpel, int reset)
 {
-    if (!h) return 1;
-    CK(cudaSetDevice(h->device));
-    unsigned long long c[2];
-    CK(cudaMemcpyAsync(c, h->d_counters, 16, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    if (fullpel) *fullpel = c[0];
-    if (subpel) *subpel = c[1];
-    if (reset) { CK(cudaMemsetAsync(h->d_counters, 0, 16, h->stream)); }
+    uint64_t c[4];
+    int rc = evxgpu_get_counters_split(h, c, reset);
+    if (rc) return rc;
+    if (fullpel) *fullpel = c[0] + c[2];
+    if (subpel) *subpel = c[1] + c[3];
     return 0;
 }
 

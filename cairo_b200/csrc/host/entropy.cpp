@@ -4,7 +4,10 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <mutex>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace evx {
 
@@ -69,6 +72,11 @@ public:
 };
 reciprocal_table &recips() { static reciprocal_table t; return t; }
 
+// bit reversal of a byte (the stream is LSB-first, the coder's bits leave MSB-first)
+struct rev8_table { uint8_t v[256]; rev8_table() { for (int i = 0; i < 256; ++i) { int r = 0; for (int b = 0; b < 8; ++b) if (i & (1 << b)) r |= 0x80 >> b; v[i] = (uint8_t) r; } } };
+const rev8_table REV8_T;
+#define REV8 REV8_T.v
+
 class abac_writer
 {
     uint32_t low_, high_, e3_, h0_, tot_;
@@ -106,7 +114,12 @@ public:
     size_t bytes_pending() const { return pos_ + 8; }
     void rebase(uint8_t *out) { out_ = out; }
 
-    // encode_symbol + resolve_encode_scaling, abac.cpp:97-121, 180-224
+    // encode_symbol + resolve_encode_scaling, abac.cpp:97-121, 180-224.
+    // The bin values are close to coin flips for the branch predictor, so the common path is
+    // written without data-dependent branches: the interval update is a pair of selects, the
+    // E1/E2 bits that leave (all leading bits on which low and high agree) are assembled into one
+    // word -- first bit, then the pending E3 bits inverted, then the remaining k-1 bits -- and
+    // OR-ed into the accumulator, and the first E3 step is a select as well.
     inline void encode(uint32_t bit)
     {
         const uint64_t a = (uint64_t) (high_ - low_) * h0_;
@@ -118,21 +131,50 @@ public:
             q = (uint32_t) (a / tot_);
         }
         const uint32_t mid = low_ + q;
-        if (bit) low_ = mid + 1; else { high_ = mid; h0_++; }
+        low_ = bit ? mid + 1 : low_;
+        high_ = bit ? high_ : mid;
+        h0_ += bit ^ 1u;
         tot_++;
-        // E1/E2: all leading bits on which low and high agree leave at once; the first of them
-        // is followed by the pending E3 bits (inverted), the rest go out verbatim
-        for (;;)
+
+        uint32_t k = (uint32_t) __builtin_clz((high_ ^ low_) | 1u) - 16;      // 0..15 common leading bits
+        if (__builtin_expect(e3_ > 40 || nacc_ > 64 - 57 + 0 && nacc_ + k + e3_ > 64 || (high_ == low_), 0))
+        {   // rare: long E3 run, accumulator about to wrap, or a collapsed interval -- bit at a time
+            for (;;)
+            {
+                k = (uint32_t) __builtin_clz((high_ ^ low_) | 1u) - 16;
+                if (!k) break;
+                emit(high_ >> 15);
+                if (k > 1) put_msb_first((high_ >> (16 - k)) & ((1u << (k - 1)) - 1u), k - 1);
+                low_ = (low_ << k) & AB_MAX;
+                high_ = ((high_ << k) & AB_MAX) | ((1u << k) - 1u);
+            }
+        }
+        else
         {
-            const uint32_t k = (uint32_t) __builtin_clz((high_ ^ low_) | 1u) - 16;      // 0..15 common leading bits
-            if (!k) break;
-            emit(high_ >> 15);
-            if (k > 1) put_msb_first((high_ >> (16 - k)) & ((1u << (k - 1)) - 1u), k - 1);
+            const uint32_t msb = high_ >> 15;
+            const uint32_t km1 = k - (k != 0);
+            const uint32_t rest = (high_ >> (16 - k)) & ((1u << km1) - 1u);                     // k-1 bits, first-out at the top
+            const uint32_t rest_rev = (uint32_t) ((REV8[rest & 0xFF] << 8) | REV8[rest >> 8]) >> (16 - km1);
+            const uint64_t pend = msb ? 0 : ((uint64_t(1) << e3_) - 1);                          // e3 copies of !msb
+            uint64_t v = (uint64_t) msb | (pend << 1) | ((uint64_t) rest_rev << (1 + e3_));
+            const uint32_t len = k ? k + e3_ : 0;
+            v = k ? v : 0;
+            acc_ |= v << nacc_;
+            nacc_ += len;
+            e3_ = k ? 0 : e3_;
+            if (nacc_ >= 64)
+            {   // exactly full (the guard above keeps nacc_ + len <= 64)
+                memcpy(out_ + pos_, &acc_, 8); pos_ += 8; acc_ = 0; nacc_ = 0;
+            }
             low_ = (low_ << k) & AB_MAX;
             high_ = ((high_ << k) & AB_MAX) | ((1u << k) - 1u);
         }
-        // E3: low = 01..., high = 10... (with the reference's 3*QTR = 0xBFFD quirk)
-        while (low_ > AB_QTR && high_ <= AB_3QTR && ((high_ ^ low_) & 0x8000u))
+        // E3: low = 01..., high = 10... (with the reference's 3*QTR = 0xBFFD quirk); MSBs differ here
+        uint32_t c = (low_ > AB_QTR) & (high_ <= AB_3QTR);
+        low_ = c ? ((low_ - (AB_QTR + 1)) << 1) & AB_MAX : low_;
+        high_ = c ? ((((high_ - (AB_QTR + 1)) << 1) & AB_MAX) | 1u) : high_;
+        e3_ += c;
+        while (__builtin_expect(c && low_ > AB_QTR && high_ <= AB_3QTR, 0))
         {
             low_ = ((low_ - (AB_QTR + 1)) << 1) & AB_MAX;
             high_ = (((high_ - (AB_QTR + 1)) << 1) & AB_MAX) | 1u;
@@ -196,6 +238,9 @@ uint32_t slice_writer::serialize(const evxgpu_block_desc *t, const int16_t *reco
 {
     const int n = mbw_ * mbh_;
     abac_writer w(buf_.data());
+    static const bool prof = getenv("EVX_ENTROPY_PROFILE") != NULL;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tp0 = prof ? now() : 0, tp1 = 0, tp2 = 0;
 
     // refresh the DC mirror with this frame's non-copy macroblocks (serialisation reads the
     // coefficient planes AFTER the whole slice was encoded, encode.cpp:214-220)
@@ -211,6 +256,7 @@ uint32_t slice_writer::serialize(const evxgpu_block_desc *t, const int16_t *reco
         if (k != n_noncopy) return 0;
     }
 
+    if (prof) tp1 = now();
     // block table by field, serialize.cpp:156-317
     for (int i = 0; i < n; ++i) w.encode_bits_lsb((uint32_t) t[i].block_type, 3);
     for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_INTRA)) w.encode_bits_lsb(t[i].prediction_target, target_bits_);
@@ -224,6 +270,7 @@ uint32_t slice_writer::serialize(const evxgpu_block_desc *t, const int16_t *reco
     last = 0;
     for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_COPY)) { w.encode_signed((int16_t) (t[i].q_index - last)); last = t[i].q_index; }
 
+    if (prof) tp2 = now();
     // residuals: all luma, then all U, then all V (serialize.cpp:125-154)
     for (int comp = 0; comp < 3; ++comp)
     {
@@ -251,7 +298,9 @@ uint32_t slice_writer::serialize(const evxgpu_block_desc *t, const int16_t *reco
             if (w.bytes_pending() + 8192 > buf_.size()) { buf_.resize(buf_.size() * 2); w.rebase(buf_.data()); }
         }
     }
-    return (uint32_t) w.finish();
+    uint32_t total_bits = (uint32_t) w.finish();
+    if (prof) fprintf(stderr, "[entropy] mirror %.3f ms, table %.3f ms, residuals %.3f ms, %u bits\n", tp1 - tp0, tp2 - tp1, now() - tp2, total_bits);
+    return total_bits;
 }
 
 // ---------------------------------------------------------------- decoder side

@@ -61,6 +61,7 @@ def lib():
     L.evxgpu_get_timing.argtypes = [vp, C.POINTER(C.c_float)]
     L.evxgpu_enable_timing.argtypes = [vp, i32]
     L.evxgpu_get_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), i32]
+    L.evxgpu_get_counters_split.argtypes = [vp, C.POINTER(C.c_uint64), i32]
     L.evxgpu_launch_count.restype = C.c_uint64
     L.evxgpu_launch_count.argtypes = [vp]
     L.evxgpu_measure_int_peak.restype = C.c_double
@@ -176,6 +177,12 @@ class Pipeline:
         a, b = C.c_uint64(0), C.c_uint64(0)
         _check(self.L.evxgpu_get_counters(self.h, C.byref(a), C.byref(b), int(reset)), "evxgpu_get_counters")
         return a.value, b.value
+
+    def counters_split(self, reset=False):
+        """(inter full-pel, inter sub-pel, intra full-pel, intra sub-pel) evaluated since the last reset."""
+        out = (C.c_uint64 * 4)()
+        _check(self.L.evxgpu_get_counters_split(self.h, out, int(reset)), "evxgpu_get_counters_split")
+        return tuple(int(v) for v in out)
 
     def launch_count(self):
         return int(self.L.evxgpu_launch_count(self.h))

@@ -111,6 +111,8 @@ int evxgpu_get_timing(evxgpu_handle *h, float *ms_out /* [EVXGPU_T_COUNT] */);
 int evxgpu_enable_timing(evxgpu_handle *h, int on);
 /* evaluated full-pel candidates / sub-pel tests since the last reset (SURVEY 8d roofline unit) */
 int evxgpu_get_counters(evxgpu_handle *h, uint64_t *fullpel, uint64_t *subpel, int reset);
+/* the same split by kernel: out4 = { inter full-pel, inter sub-pel, intra full-pel, intra sub-pel } */
+int evxgpu_get_counters_split(evxgpu_handle *h, uint64_t *out4, int reset);
 uint64_t evxgpu_launch_count(const evxgpu_handle *h);
 /* debug: per-row phase cycle sums of the encoder wavefront kernel, 6 x int64 per macroblock row */
 int evxgpu_debug_profile(evxgpu_handle *h, int enable, long long *out_host);
