@@ -307,12 +307,44 @@ __device__ __forceinline__ void evx_block_cost_lane(const EvxLaneBlock &ref, con
     m = max(max(evx_lo16(amx), evx_hi16(amx)), -min(evx_lo16(amn), evx_hi16(amn)));
 }
 
-__device__ __forceinline__ void evx_block_cost(const EvxLaneBlock &ref, const EvxLaneSrc &src, int &sad, int &mad)
+// SAD only: one VIADDMNMX.S16x2.RELU and two IDP.2A per packed word.
+__device__ __forceinline__ int evx_block_sad_lane(const EvxLaneBlock &ref, const EvxLaneSrc &src)
 {
-    int acc, m;
-    evx_block_cost_lane(ref, src, acc, m);
-    sad = __reduce_add_sync(0xFFFFFFFFu, acc);
-    mad = __reduce_max_sync(0xFFFFFFFFu, m);
+    int acc = src.lsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        uint32_t r = __viaddmax_s16x2_relu(ref.w[k], src.neg[k], 0u);
+        acc = __dp2a_lo((int) r, 0x0202, acc);
+        acc = __dp2a_lo((int) ref.w[k], 0xFFFF, acc);
+    }
+    return acc;
+}
+
+// MAD only (luma + chroma): two VIADDMNMX.S16x2 per packed word.
+__device__ __forceinline__ int evx_block_mad_lane(const EvxLaneBlock &ref, const EvxLaneSrc &src)
+{
+    uint32_t amx = 0x80008000u, amn = 0x7FFF7FFFu;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+    {
+        amx = __viaddmax_s16x2(ref.w[k], src.neg[k], amx);
+        amn = __viaddmin_s16x2(ref.w[k], src.neg[k], amn);
+    }
+    return max(max(evx_lo16(amx), evx_hi16(amx)), -min(evx_lo16(amn), evx_hi16(amn)));
+}
+
+// The MAD feeds the reference's decisions only through `mad < thr` and, once a copy candidate
+// is held, through comparisons among values below thr (motion.cpp:123-140, 165-213): its exact
+// value never matters when it is >= thr.  And mad < thr implies every one of the 256 luma
+// differences is below thr, i.e. sad < 256*thr.  So the MAD pass is run only for candidates
+// whose SAD is under that bound; all others report EVX_BIG.  (Bit-exact by construction; the
+// parity tests compare every descriptor and SAD with the oracle.)
+__device__ __forceinline__ void evx_block_cost(const EvxLaneBlock &ref, const EvxLaneSrc &src, int thr, int &sad, int &mad)
+{
+    sad = __reduce_add_sync(0xFFFFFFFFu, evx_block_sad_lane(ref, src));
+    mad = EVX_BIG;
+    if (sad < 256 * thr) mad = __reduce_max_sync(0xFFFFFFFFu, evx_block_mad_lane(ref, src));
 }
 
 // One sub-pel direction: both the half- and the quarter-pel blend of `best` with its
@@ -323,7 +355,7 @@ __device__ __forceinline__ void evx_block_cost(const EvxLaneBlock &ref, const Ev
 // plain floors, so   half = (a+b+1) >> 1   and   quarter = a + floor((b-a+2)/4), the latter
 // with a +0x4000 bias so the per-halfword shift can be a logical one.  Otherwise the exact
 // scalar form (negative sums round away from zero) is used.
-__device__ __forceinline__ void evx_subpel_cost(const EvxLaneBlock &best, const EvxLaneBlock &nb, const EvxLaneSrc &src,
+__device__ __forceinline__ void evx_subpel_cost(const EvxLaneBlock &best, const EvxLaneBlock &nb, const EvxLaneSrc &src, int thr,
                                                 int &sad_h, int &mad_h, int &sad_q, int &mad_q)
 {
     uint32_t any = 0;
@@ -341,8 +373,12 @@ __device__ __forceinline__ void evx_subpel_cost(const EvxLaneBlock &best, const 
             const uint32_t d = __vadd2(b, __vadd2(~a, 0x40034003u));            // b - a + 2 + 0x4000 per halfword
             qb.w[k] = __vadd2((d >> 2) & 0x3FFF3FFFu, __vadd2(a, 0xF000F000u));  // floor(d/4) - 0x1000 + a
         }
-        evx_block_cost_lane(hb, src, sh, mh);
-        evx_block_cost_lane(qb, src, sq, mq);
+        sad_h = __reduce_add_sync(0xFFFFFFFFu, evx_block_sad_lane(hb, src));
+        sad_q = __reduce_add_sync(0xFFFFFFFFu, evx_block_sad_lane(qb, src));
+        mad_h = EVX_BIG; mad_q = EVX_BIG;
+        if (sad_h < 256 * thr) mad_h = __reduce_max_sync(0xFFFFFFFFu, evx_block_mad_lane(hb, src));
+        if (sad_q < 256 * thr) mad_q = __reduce_max_sync(0xFFFFFFFFu, evx_block_mad_lane(qb, src));
+        return;
     }
     else
     {

@@ -204,7 +204,7 @@ __device__ __forceinline__ void evx_inter_search_warp(const EvxWin &win, const E
     EvxLaneBlock ref;
     s.bx = px; s.by = py; s.ssd = EVX_BIG; s.sp_index = 0; s.sp_amount = 0; s.sp_enabled = 0;
     evx_load_block(win, px, py, lane, ref);
-    evx_block_cost(ref, src, s.sad, s.mad);
+    evx_block_cost(ref, src, thr, s.sad, s.mad);
     n_full = 1; n_sub = 0;
     if (s.mad < thr) return;                       // already a copy block: no search (motion.cpp:452)
     for (int step = EVX_SEARCH_RADIUS; step > 0; step >>= 1)
@@ -221,7 +221,7 @@ __device__ __forceinline__ void evx_inter_search_warp(const EvxWin &win, const E
         {
             if (c == 4) continue;
             evx_load_block(win, basex + (c % 3 - 1) * step, basey + (c / 3 - 1) * step, lane, ref);
-            evx_block_cost(ref, src, csad[c], cmad[c]);
+            evx_block_cost(ref, src, thr, csad[c], cmad[c]);
         }
 #pragma unroll
         for (int c = 0; c < 9; ++c)
@@ -244,14 +244,14 @@ __device__ __forceinline__ void evx_inter_search_warp(const EvxWin &win, const E
         if (x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB) continue;
         int sh, mh, sq, mq;
         evx_load_block(win, x, y, lane, ref);
-        evx_subpel_cost(best, ref, src, sh, mh, sq, mq);
+        evx_subpel_cost(best, ref, src, thr, sh, mh, sq, mq);
         n_sub += 2;
         evx_accept_subpel(s, i, j, 0, sh, mh, thr);
         evx_accept_subpel(s, i, j, 1, sq, mq, thr);
     }
 }
 
-__global__ void __launch_bounds__(256) evx_inter_search(const __grid_constant__ EvxK2Maps maps, EvxPlanes srcp, EvxGeom g,
+__global__ void __launch_bounds__(256, 4) evx_inter_search(const __grid_constant__ EvxK2Maps maps, EvxPlanes srcp, EvxGeom g,
                                                         EvxInterResult *__restrict__ results, int thr,
                                                         unsigned long long *__restrict__ counters)
 {

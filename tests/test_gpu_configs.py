@@ -1,0 +1,109 @@
+"""The remaining BASELINE.json configurations as parity / property tests on the GPU:
+ configs[2] 1080p, ring of 4 (3 past references), MPEG + adaptive quant, deblocking;
+ configs[3] 4K intra+P with periodic intra frames and a decode round trip;
+ configs[4] many independent streams on one GPU, each equal to its own single-stream oracle."""
+import threading
+
+import numpy as np
+import pytest
+
+import oracleharness as O
+from cairo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(a, b):
+    return all((np.asarray(x) == np.asarray(y)).all() for x, y in zip(a, b))
+
+
+def test_1080p_four_slot_ring_matches_oracle():
+    """configs[2]: one intra + one P frame against the oracle (the oracle needs ~4 s per such frame)."""
+    from cairo_b200 import gpu
+    w, h, q, R = 1920, 1080, 16, 4
+    p = gpu.Pipeline(w, h, R, 0, 1)
+    o = O.Oracle(w, h, R, 0, 1)
+    coef = [np.zeros((o.ah, o.aw), np.int16), np.zeros((o.ah // 2, o.aw // 2), np.int16), np.zeros((o.ah // 2, o.aw // 2), np.int16)]
+    for t in range(2):
+        f = synth.frame(w, h, t, 2, "moving")
+        o.convert_in(f)
+        o.encode_slice(0 if t == 0 else 1, t, q)
+        tbl, rec = p.encode(f, 0 if t == 0 else 1, t, q)
+        assert O.tables_equal(o.block_table().copy(), tbl), t
+        gpu.records_to_planes(tbl, rec, coef, o.aw, o.ah)
+        assert _same(coef, o.planes(1)), t
+        o.deblock(t)
+        assert _same(p.planes(2, t % R), o.planes(2, t % R)), t
+
+
+def test_4k_periodic_intra_decode_round_trip():
+    """configs[3]: 3840x2160, intra every 3rd frame; the decoder must rebuild, bit for bit, the
+    encoder's in-loop reconstruction from nothing but the stream (closed loop), and the first
+    frame must equal the oracle's stream."""
+    from cairo_b200 import api, gpu
+    w, h, q = 3840, 2160, 16
+    enc = api.evx1_encoder(ref_count=2)
+    enc.set_quality(q)
+    dec = api.evx1_decoder()
+    # a second, raw pipeline fed the same frames exposes the encoder-side reconstruction
+    side = gpu.Pipeline(w, h, 2, 0, 1)
+    o = O.Oracle(w, h, 2, 0, 1)
+    for t in range(4):
+        f = synth.frame(w, h, t, 1, "moving")
+        intra = t % 3 == 0
+        if intra and t:
+            enc.insert_intra()
+        data, bits = enc.encode(f)
+        rgb = dec.decode(data, bits, w, h)
+        side.encode(f, 0 if intra else 1, t, q)
+        yuv = side.planes(2, t % 2)
+        # decoded RGB == colour conversion of the encoder's own reconstruction
+        y, u, v = [a.astype(np.int32) for a in yuv]
+        yy = y[:h, :w]
+        uu = np.repeat(np.repeat(u, 2, 0), 2, 1)[:h, :w]
+        vv = np.repeat(np.repeat(v, 2, 0), 2, 1)[:h, :w]
+        sat = lambda x: np.clip(x.astype(np.int16), 0, 255).astype(np.uint8)
+        r = sat((256 * (yy - 16) + 358 * (vv - 128) + 128) >> 8)
+        g = sat((256 * (yy - 16) - 88 * (uu - 128) - 182 * (vv - 128) + 128) >> 8)
+        b = sat((256 * (yy - 16) + 452 * (uu - 128) + 128) >> 8)
+        assert (rgb[..., 0] == r).all() and (rgb[..., 1] == g).all() and (rgb[..., 2] == b).all(), t
+        if t == 0:
+            o.convert_in(f)
+            o.encode_slice(0, 0, q)
+            od, ob = o.serialize()
+            got = np.packbits(np.unpackbits(data, bitorder="little")[24 * 8:bits], bitorder="little")
+            assert O.bits_equal(got, bits - 24 * 8, od, ob)
+
+
+def test_many_streams_on_one_gpu_are_independent():
+    """configs[4] in miniature: 8 concurrent streams (one host thread, one handle, one CUDA stream
+    each) produce exactly what each produces alone -- checked against per-stream oracle runs."""
+    from cairo_b200 import api
+    w, h, q, n_streams, n_frames = 176, 144, 16, 8, 4
+    results = [None] * n_streams
+
+    def work(sidx):
+        enc = api.evx1_encoder()
+        enc.set_quality(q)
+        out = []
+        for t in range(n_frames):
+            d, b = enc.encode(synth.frame(w, h, t, sidx, "moving"))
+            out.append((d.copy(), b))
+        results[sidx] = out
+
+    threads = [threading.Thread(target=work, args=(s,)) for s in range(n_streams)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for sidx in range(n_streams):
+        o = O.Oracle(w, h, 4, 0, 1)
+        for t in range(n_frames):
+            o.convert_in(synth.frame(w, h, t, sidx, "moving"))
+            o.encode_slice(0 if t == 0 else 1, t, q)
+            od, ob = o.serialize()
+            o.deblock(t)
+            d, b = results[sidx][t]
+            skip = (24 if t == 0 else 10) * 8
+            got = np.packbits(np.unpackbits(d, bitorder="little")[skip:b], bitorder="little")
+            assert O.bits_equal(got, b - skip, od, ob), (sidx, t)
