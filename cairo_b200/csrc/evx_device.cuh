@@ -347,6 +347,15 @@ __device__ __forceinline__ void evx_block_cost(const EvxLaneBlock &ref, const Ev
     if (sad < 256 * thr) mad = __reduce_max_sync(0xFFFFFFFFu, evx_block_mad_lane(ref, src));
 }
 
+// Latency-optimised form for the serial kernel (K3): both reductions are issued back to back
+// instead of making the MAD pass wait for the SAD's warp reduction.
+__device__ __forceinline__ void evx_block_cost_both(const EvxLaneBlock &ref, const EvxLaneSrc &src, int &sad, int &mad)
+{
+    const int a = evx_block_sad_lane(ref, src), m = evx_block_mad_lane(ref, src);
+    sad = __reduce_add_sync(0xFFFFFFFFu, a);
+    mad = __reduce_max_sync(0xFFFFFFFFu, m);
+}
+
 // One sub-pel direction: both the half- and the quarter-pel blend of `best` with its
 // neighbour `nb` (macroblock.h:203-241), SAD/MAD of each against the source.
 //
@@ -355,6 +364,7 @@ __device__ __forceinline__ void evx_block_cost(const EvxLaneBlock &ref, const Ev
 // plain floors, so   half = (a+b+1) >> 1   and   quarter = a + floor((b-a+2)/4), the latter
 // with a +0x4000 bias so the per-halfword shift can be a logical one.  Otherwise the exact
 // scalar form (negative sums round away from zero) is used.
+// thr < 0 selects the latency-optimised variant (every MAD computed, reductions overlapped).
 __device__ __forceinline__ void evx_subpel_cost(const EvxLaneBlock &best, const EvxLaneBlock &nb, const EvxLaneSrc &src, int thr,
                                                 int &sad_h, int &mad_h, int &sad_q, int &mad_q)
 {
@@ -372,6 +382,14 @@ __device__ __forceinline__ void evx_subpel_cost(const EvxLaneBlock &best, const 
             hb.w[k] = (__vadd2(__vadd2(a, b), 0x00010001u) >> 1) & 0x7FFF7FFFu;
             const uint32_t d = __vadd2(b, __vadd2(~a, 0x40034003u));            // b - a + 2 + 0x4000 per halfword
             qb.w[k] = __vadd2((d >> 2) & 0x3FFF3FFFu, __vadd2(a, 0xF000F000u));  // floor(d/4) - 0x1000 + a
+        }
+        if (thr < 0)
+        {   // latency-optimised (K3): four independent reductions in flight
+            const int a1 = evx_block_sad_lane(hb, src), a2 = evx_block_sad_lane(qb, src);
+            const int m1 = evx_block_mad_lane(hb, src), m2 = evx_block_mad_lane(qb, src);
+            sad_h = __reduce_add_sync(0xFFFFFFFFu, a1); sad_q = __reduce_add_sync(0xFFFFFFFFu, a2);
+            mad_h = __reduce_max_sync(0xFFFFFFFFu, m1); mad_q = __reduce_max_sync(0xFFFFFFFFu, m2);
+            return;
         }
         sad_h = __reduce_add_sync(0xFFFFFFFFu, evx_block_sad_lane(hb, src));
         sad_q = __reduce_add_sync(0xFFFFFFFFu, evx_block_sad_lane(qb, src));

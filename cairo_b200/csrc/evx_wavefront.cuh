@@ -311,7 +311,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 EvxLaneBlock ref;
                 int sad, mad;
                 evx_load_block_ring_bf(win, x, y, lane, ref);
-                evx_block_cost(ref, src, thr, sad, mad);
+                evx_block_cost_both(ref, src, sad, mad);
                 const int ssd = (x - px) * (x - px) + (y - py) * (y - py);
                 int4 res = evx_candidate_keys(sad, mad, ssd, thr);
                 if (!evx_intra_legal(x, y, px, py, g)) res.w = 0;
@@ -373,7 +373,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 int shh, mh, sq, mq;
                 evx_load_block_ring_bf(win, s.bx, s.by, lane, best);
                 evx_load_block_ring_bf(win, x, y, lane, nb);
-                evx_subpel_cost(best, nb, src, thr, shh, mh, sq, mq);
+                evx_subpel_cost(best, nb, src, -1, shh, mh, sq, mq);
                 const int ok = evx_intra_legal(x, y, px, py, g) ? 1 : 0;
                 if (lane == 0) { S.cand[buf][2 * k] = make_int4(shh, mh, 0, ok); S.cand[buf][2 * k + 1] = make_int4(sq, mq, 0, ok); }
             }
