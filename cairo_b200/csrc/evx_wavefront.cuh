@@ -580,7 +580,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     }
 }
 
-__global__ void __launch_bounds__(EVX_K3_NT, 1) evx_wavefront(const __grid_constant__ EvxK3Params p)
+__global__ void __launch_bounds__(EVX_K3_NT, 2) evx_wavefront(const __grid_constant__ EvxK3Params p)
 {
     extern __shared__ __align__(16) uint8_t evx_k3_smem[];
     EvxK3Smem &S = *reinterpret_cast<EvxK3Smem *>(evx_k3_smem);
