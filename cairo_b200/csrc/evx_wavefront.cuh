@@ -46,7 +46,7 @@ struct EvxK3Smem
     EvxMbShared sh;
     int4 cand[2][16];                         // per candidate: {key1, key1-if-taken, key2, flags}  (sub-pel: {sad, mad, 0, legal})
     int4 cval[2][16];                         // per candidate: {sad, mad, ssd, 0}
-    uint64_t full[2], empty[2];
+    uint64_t full[2], full2[2], empty[2];      // full: everything but the far-right column; full2: that column too
     int done;                                 // macroblocks of this row whose reconstruction is stored
     int row;
 };
@@ -145,57 +145,70 @@ __device__ __forceinline__ void evx_k3_loader(EvxK3Smem &S, const EvxK3Params &p
                 *reinterpret_cast<uint4 *>(&(lane < 8 ? S.wu : S.wv)[(32 + (lane & 7)) * EVX_RING_PWC + ((cx0 >> 1) & 31)]) = c;
             }
         }
-        // the three rows above: wait for (min(n+2,W-1), by-1), then pull the new column(s)
-        if (by > 0)
+        // The three rows above.  Columns up to macroblock n+1 are what the search needs at once
+        // (they arrived while staging macroblock n-1, except at the row start); the far-right
+        // column n+2 is needed only by candidates with x >= px+17 and, as (n+2,by-1)'s completion,
+        // before this macroblock may overwrite the samples the row above still reads (write-after-
+        // read).  Staging it AFTER `full` is signalled gives every macroblock one macroblock-time of
+        // slack against jitter in the row above instead of a hard stall.
+        auto pull_column = [&](int col)
         {
-            const int need = min(n + 2, g.mbw - 1) + 1;
-            if (lane == 0) evx_wait_ge(progress + by - 1, need);
-            __syncwarp();
-            const int first = n == 0 ? 0 : n + 2, last = min(n + 2, g.mbw - 1);
-            for (int col = first; col <= last; ++col)
+            uint4 v[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
             {
-                uint4 v[3];
+                int c = lane + 32 * k;                 // 96 chunks: 48 rows x 2 halves
+                int row = c >> 1, half = c & 1, y = py - 48 + row;
+                v[k] = make_uint4(0, 0, 0, 0);
+                if (y >= 0) v[k] = __ldcg(reinterpret_cast<const uint4 *>(cur.y + (size_t) y * g.w + col * EVX_MB + 8 * half));
+            }
+            uint4 cv[2];
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
+            for (int k = 0; k < 2; ++k)
+            {
+                int c = lane + 32 * k;                 // 48 chunks: 2 planes x 24 rows
+                cv[k] = make_uint4(0, 0, 0, 0);
+                if (c < 48)
                 {
-                    int c = lane + 32 * k;                 // 96 chunks: 48 rows x 2 halves
-                    int row = c >> 1, half = c & 1, y = py - 48 + row;
-                    v[k] = make_uint4(0, 0, 0, 0);
-                    if (y >= 0) v[k] = __ldcg(reinterpret_cast<const uint4 *>(cur.y + (size_t) y * g.w + col * EVX_MB + 8 * half));
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                {
-                    int c = lane + 32 * k;
-                    int row = c >> 1, half = c & 1;
-                    *reinterpret_cast<uint4 *>(&S.wy[row * EVX_RING_PWY + (((col * EVX_MB + 8 * half) >> 1) & 63)]) = v[k];
-                }
-                uint4 cv[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                {
-                    int c = lane + 32 * k;                 // 48 chunks: 2 planes x 24 rows
-                    cv[k] = make_uint4(0, 0, 0, 0);
-                    if (c < 48)
-                    {
-                        int plane = c / 24, row = c % 24, y = (py >> 1) - 24 + row;
-                        if (y >= 0) cv[k] = __ldcg(reinterpret_cast<const uint4 *>((plane ? cur.v : cur.u) + (size_t) y * cw + col * 8));
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                {
-                    int c = lane + 32 * k;
-                    if (c < 48)
-                    {
-                        int plane = c / 24, row = c % 24;
-                        *reinterpret_cast<uint4 *>(&(plane ? S.wv : S.wu)[row * EVX_RING_PWC + (((col * 8) >> 1) & 31)]) = cv[k];
-                    }
+                    int plane = c / 24, row = c % 24, y = (py >> 1) - 24 + row;
+                    if (y >= 0) cv[k] = __ldcg(reinterpret_cast<const uint4 *>((plane ? cur.v : cur.u) + (size_t) y * cw + col * 8));
                 }
             }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                int c = lane + 32 * k;
+                int row = c >> 1, half = c & 1;
+                *reinterpret_cast<uint4 *>(&S.wy[row * EVX_RING_PWY + (((col * EVX_MB + 8 * half) >> 1) & 63)]) = v[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+            {
+                int c = lane + 32 * k;
+                if (c < 48)
+                {
+                    int plane = c / 24, row = c % 24;
+                    *reinterpret_cast<uint4 *>(&(plane ? S.wv : S.wu)[row * EVX_RING_PWC + (((col * 8) >> 1) & 31)]) = cv[k];
+                }
+            }
+        };
+        if (by > 0 && n == 0)
+        {
+            if (lane == 0) evx_wait_ge(progress + by - 1, min(1, g.mbw - 1) + 1);
+            __syncwarp();
+            pull_column(0);
+            if (g.mbw > 1) pull_column(1);
         }
         __syncwarp();
         if (lane == 0) evx_mbar_arrive(&S.full[slot]);
+        if (by > 0)
+        {
+            if (lane == 0) evx_wait_ge(progress + by - 1, min(n + 2, g.mbw - 1) + 1);
+            __syncwarp();
+            if (n + 2 < g.mbw) pull_column(n + 2);
+        }
+        __syncwarp();
+        if (lane == 0) evx_mbar_arrive(&S.full2[slot]);
     }
 }
 
@@ -264,6 +277,8 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         const int slot = n & 1, px = n * EVX_MB, mb = by * g.mbw + n;
         evx_mbar_wait(&S.full[slot], (uint32_t) ((n >> 1) & 1));
         EVX_K3_PROF(0);
+        bool have2 = false;      // far-right column (and write permission) not yet confirmed
+#define EVX_K3_NEED2() do { if (!have2) { evx_mbar_wait(&S.full2[slot], (uint32_t) ((n >> 1) & 1)); have2 = true; } } while (0)
         const int16_t *srcb = S.src[slot];
 
         EvxLaneSrc src;
@@ -297,6 +312,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         {
             const int step = EVX_SEARCH_RADIUS >> (round == 0 ? 0 : round);
             const int top = round == 0 ? -2 : -1;          // first round scans rows -32,-16,0 (motion.cpp:384-386)
+            if (s.bx + step >= px + 17) EVX_K3_NEED2();      // a cell of this round reaches into column n+2
             // Round 0: grid cells 0..7 are evaluated (cells 7,8 = (0,0),(16,0) are never legal).
             // Later rounds: the centre cell 4 is the running best itself; its sad/mad/ssd are the
             // state's own (it was evaluated when it was accepted), so only the 8 outer cells run.
@@ -364,6 +380,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         EVX_K3_PROF(1);
         // ---- intra sub-pel, motion.cpp:277-317: eight directions, both blends each
         {
+            if (s.bx + 1 >= px + 17) EVX_K3_NEED2();
 #pragma unroll
             for (int q = 0; q < EVX_K3_CPW; ++q)
             {
@@ -457,6 +474,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         evx_compute_sync();
         EVX_K3_PROF(3);
 
+        EVX_K3_NEED2();          // (n+2,by-1) is complete: the row above no longer reads this macroblock's stale samples
         // reconstruction target: global ring slot + our own window rows (py..py+15 -> 48..63)
         auto store_recon = [&](int e, int v)
         {
@@ -591,6 +609,7 @@ __global__ void __launch_bounds__(EVX_K3_NT, 2) evx_wavefront(const __grid_const
         // rows are claimed in order: a CTA only ever waits on rows claimed before its own
         S.row = atomicAdd(&p.sync[0], 1);
         evx_mbar_init(&S.full[0], 1); evx_mbar_init(&S.full[1], 1);
+        evx_mbar_init(&S.full2[0], 1); evx_mbar_init(&S.full2[1], 1);
         evx_mbar_init(&S.empty[0], 1); evx_mbar_init(&S.empty[1], 1);
         S.done = 0;
     }
