@@ -304,6 +304,12 @@ def run_ours(args):
         ops_k2 = (c_inter_full * OPS_FULLPEL + c_inter_sub * OPS_SUBPEL) / steps
         ops_k3 = (c_intra_full * OPS_FULLPEL + c_intra_sub * OPS_SUBPEL) / steps
         int_peak = gpu.lib().evxgpu_measure_int_peak(local_rank, 1)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f).get("evx_inter_search", {})
+            traffic = tj.get("dram_bytes_read", 0) + tj.get("dram_bytes_write", 0)
         dominant = max(ksum, key=ksum.get)
         achieved = ops_k2 / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else 0.0
         achieved_all = (ops_k2 + ops_k3) / ((k2_ms + k3_ms) * 1e-3) / 1e12 if k2_ms + k3_ms > 0 else 0.0
@@ -324,7 +330,9 @@ def run_ours(args):
                              "host_cores": os.cpu_count()},
             "kernel_ms_per_step": {k: v / steps for k, v in ksum.items()},
             "roofline": {"bound": "int_alu", "kernel": "evx_inter_search (the motion-search kernel: all macroblocks x past references in parallel)",
-                         "achieved": achieved, "peak": int_peak, "unit": "Tiop/s", "frac": achieved / int_peak if int_peak > 0 else None, "traffic": None,
+                         "achieved": achieved, "peak": int_peak, "unit": "Tiop/s", "frac": achieved / int_peak if int_peak > 0 else None, "traffic": traffic,
+                         "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/r01_traffic.json); "
+                                         "algorithmic bytes per launch = reference planes 6.27 MB + source planes 6.27 MB",
                          "peak_source": "evxgpu_measure_int_peak: dependency-free VIADDMNMX.S16x2 stream on all SMs, measured in this run "
                                         "(MEASURED_PEAKS.json has no integer figure)",
                          "algorithmic_ops_per_launch": ops_k2, "kernel_ms_per_launch": k2_ms,

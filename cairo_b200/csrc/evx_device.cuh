@@ -147,6 +147,72 @@ __device__ __forceinline__ void evx_replay_subpel(EvxSel &s, bool legal, int ind
     s.sad = take ? sad : s.sad; s.mad = take ? mad : s.mad;
 }
 
+// ------------------------------------------------------------------ closed-form acceptance
+//
+// The reference accepts the candidates of a round one after the other (motion.cpp:111-149).
+// With each candidate as sortable keys that fold has a closed form:
+//   key1 = sad:ssd'  (ssd' = 4095 = "infinite" when sad >= 8192: that disables the tie rule exactly
+//                     where the reference's `&& sad < 8192` does),   key2 = mad:ssd,
+//   * state already in copy mode (best_mad < thr): every take needs (mad,ssd) < (best_mad,best_ssd)
+//     -> survivor = FIRST minimum of key2, if it beats the state;
+//   * else, if some legal candidate has mad < thr: the first such is taken unconditionally and flips
+//     the state to copy mode; later ones need a smaller key2 -> survivor = first minimum of key2 among
+//     the candidates with mad < thr (the others can never be smaller);
+//   * else every take needs (sad,ssd') < (best_sad,best_ssd) -> survivor = first minimum of key1.
+// ssd <= 32^2 + 48^2 = 3328 < 4095 for every reachable position; sad, mad are clamped to 20 bits.
+struct EvxKeys { uint32_t k1, k2; bool legal, lt; };
+
+__device__ __forceinline__ EvxKeys evx_make_keys(int sad, int mad, int ssd, int thr, bool legal)
+{
+    EvxKeys k;
+    const uint32_t z = (uint32_t) min(ssd, 4095);
+    k.k1 = ((uint32_t) min(sad, 0xFFFFE) << 12) | ((uint32_t) sad < EVX_SAD_CAP ? z : 4095u);
+    k.k2 = ((uint32_t) min(mad, 0xFFFFE) << 12) | z;
+    k.legal = legal;
+    k.lt = legal && mad < thr;
+    return k;
+}
+
+// Lane c holds candidate c (in the reference's visiting order); lanes without a candidate pass
+// legal = false.  Returns the surviving candidate's lane, or -1 when the state stands.
+__device__ __forceinline__ int evx_select_fullpel(const EvxSel &s, const EvxKeys &k, int lane, int thr, uint32_t &n_legal)
+{
+    const unsigned legal_mask = __ballot_sync(0xFFFFFFFFu, k.legal);
+    const unsigned lt_mask = __ballot_sync(0xFFFFFFFFu, k.lt);
+    n_legal += __popc(legal_mask);
+    const bool copy0 = s.mad < thr;
+    uint32_t key, init;
+    unsigned elig;
+    if (copy0) { key = k.k2; elig = legal_mask; init = ((uint32_t) min(s.mad, 0xFFFFE) << 12) | (uint32_t) min(s.ssd, 4095); }
+    else if (lt_mask) { key = k.k2; elig = lt_mask; init = 0xFFFFFFFFu; }
+    else { key = k.k1; elig = legal_mask; init = ((uint32_t) min(s.sad, 0xFFFFE) << 12) | (uint32_t) min(s.ssd, 4095); }
+    const uint32_t mykey = ((elig >> lane) & 1u) ? key : 0xFFFFFFFFu;
+    const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, mykey);
+    if (m >= init) return -1;
+    return __ffs(__ballot_sync(0xFFFFFFFFu, mykey == m)) - 1;
+}
+
+// Sub-pel tests (motion.cpp:151-223), lane t = test t in reference order (direction-major, half
+// before quarter): copy mode -> first minimum of mad; else a test with mad < thr exists -> first
+// minimum of mad among those; else -> first minimum of sad among tests with sad < 8192.
+__device__ __forceinline__ int evx_select_subpel(const EvxSel &s, int sad, int mad, bool legal, int lane, int thr, uint32_t &n_legal)
+{
+    const unsigned legal_mask = __ballot_sync(0xFFFFFFFFu, legal);
+    const unsigned lt_mask = __ballot_sync(0xFFFFFFFFu, legal && mad < thr);
+    const unsigned cap_mask = __ballot_sync(0xFFFFFFFFu, legal && (uint32_t) sad < EVX_SAD_CAP);
+    n_legal += __popc(legal_mask);
+    const bool copy0 = s.mad < thr;
+    int key, init;
+    unsigned elig;
+    if (copy0) { key = mad; elig = legal_mask; init = s.mad; }
+    else if (lt_mask) { key = mad; elig = lt_mask; init = EVX_BIG; }
+    else { key = sad; elig = cap_mask; init = s.sad; }
+    const int mykey = ((elig >> lane) & 1u) ? key : EVX_BIG;
+    const int m = __reduce_min_sync(0xFFFFFFFFu, mykey);
+    if (m >= init) return -1;
+    return __ffs(__ballot_sync(0xFFFFFFFFu, mykey == m)) - 1;
+}
+
 __device__ __forceinline__ EvxDesc evx_desc_from_sel(const EvxSel &s, int intra, int target, int px, int py, int thr)
 {
     int type = intra ? EVX_T_INTRA : 0;

@@ -223,31 +223,46 @@ __device__ __forceinline__ void evx_inter_search_warp(const EvxWin &win, const E
             evx_load_block(win, basex + (c % 3 - 1) * step, basey + (c / 3 - 1) * step, lane, ref);
             evx_block_cost(ref, src, thr, csad[c], cmad[c]);
         }
+        // acceptance in closed form (evx_select_fullpel): lane c takes cell c
+        int mysad = csad[0], mymad = cmad[0];
 #pragma unroll
-        for (int c = 0; c < 9; ++c)
+        for (int c = 1; c < 9; ++c) { mysad = lane == c ? csad[c] : mysad; mymad = lane == c ? cmad[c] : mymad; }
+        const int lc = lane < 9 ? lane : 0;
+        const int x = basex + (lc % 3 - 1) * step, y = basey + (lc / 3 - 1) * step;
+        const bool legal = lane < 9 && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);
+        const int ssd = (x - px) * (x - px) + (y - py) * (y - py);
+        const int wl = evx_select_fullpel(s, evx_make_keys(mysad, mymad, ssd, thr, legal), lane, thr, n_full);
+        if (wl >= 0)
         {
-            const int x = basex + (c % 3 - 1) * step, y = basey + (c / 3 - 1) * step;
-            const bool legal = !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);
-            n_full += legal;
-            evx_replay_fullpel(s, legal, csad[c], cmad[c], (x - px) * (x - px) + (y - py) * (y - py), x, y, thr);
+            s.bx = __shfl_sync(0xFFFFFFFFu, x, wl); s.by = __shfl_sync(0xFFFFFFFFu, y, wl);
+            s.sad = __shfl_sync(0xFFFFFFFFu, mysad, wl); s.mad = __shfl_sync(0xFFFFFFFFu, mymad, wl); s.ssd = __shfl_sync(0xFFFFFFFFu, ssd, wl);
         }
     }
+    // sub-pel (motion.cpp:319-352): eight directions, half and quarter each; lane t takes test t
     EvxLaneBlock best;
     evx_load_block(win, s.bx, s.by, lane, best);
-#pragma unroll 1
-    for (int j = -1; j <= 1; ++j)
-#pragma unroll 1
-    for (int i = -1; i <= 1; ++i)
+    int tsad = 0, tmad = 0;
+#pragma unroll
+    for (int d8 = 0; d8 < 8; ++d8)
     {
-        int x = s.bx + i, y = s.by + j;
-        if (i == 0 && j == 0) continue;
-        if (x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB) continue;
+        const int d = d8 < 4 ? d8 : d8 + 1;
         int sh, mh, sq, mq;
-        evx_load_block(win, x, y, lane, ref);
+        evx_load_block(win, s.bx + d % 3 - 1, s.by + d / 3 - 1, lane, ref);
         evx_subpel_cost(best, ref, src, thr, sh, mh, sq, mq);
-        n_sub += 2;
-        evx_accept_subpel(s, i, j, 0, sh, mh, thr);
-        evx_accept_subpel(s, i, j, 1, sq, mq, thr);
+        tsad = lane == 2 * d8 ? sh : (lane == 2 * d8 + 1 ? sq : tsad);
+        tmad = lane == 2 * d8 ? mh : (lane == 2 * d8 + 1 ? mq : tmad);
+    }
+    {
+        const int d8 = (lane >> 1) & 7, d = d8 < 4 ? d8 : d8 + 1;
+        const int x = s.bx + d % 3 - 1, y = s.by + d / 3 - 1;
+        const bool legal = lane < 16 && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);
+        const int wt = evx_select_subpel(s, tsad, tmad, legal, lane, thr, n_sub);
+        if (wt >= 0)
+        {
+            const int wd8 = wt >> 1, wd = wd8 < 4 ? wd8 : wd8 + 1;
+            s.sp_enabled = 1; s.sp_amount = wt & 1; s.sp_index = evx_frac_index(wd % 3 - 1, wd / 3 - 1);
+            s.sad = __shfl_sync(0xFFFFFFFFu, tsad, wt); s.mad = __shfl_sync(0xFFFFFFFFu, tmad, wt);
+        }
     }
 }
 
