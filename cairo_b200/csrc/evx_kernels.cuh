@@ -611,8 +611,18 @@ __global__ void __launch_bounds__(256) evx_pack_records(const EvxDesc *__restric
 }
 
 // ------------------------------------------------------------------ K5: decoder reconstruction (decode.cpp:146-170)
-// Same wavefront rule (INTRA_MOTION_* blocks read the frame under construction, stale samples
-// included); no search.  One CTA of 128 threads per macroblock in flight.
+//
+// The reference decodes macroblocks in raster order.  Only blocks that predict from the frame under
+// construction (INTRA_MOTION_*: decode.cpp:27-72) make that order observable:
+//   read-after-write   such a block R reads macroblocks X < R (raster) as already decoded this frame;
+//   write-after-read   it reads macroblocks X > R as they were BEFORE this frame (stale ring contents),
+//                      so X must not be written until R has read them.
+// Everything else is independent.  A tiny pre-pass (evx_decode_deps) counts, per macroblock, the
+// earlier blocks that still have to read its stale samples; the main kernel hands macroblocks out
+// by an atomic ticket in raster order (a block only ever waits on raster-earlier blocks, which are
+// already claimed: deadlock-free for any grid), waits on done[] for its decoded sources, signals its
+// stale reads, waits for its own readers, then reconstructs.  P-frames -- few intra blocks -- decode
+// with the whole GPU in parallel; I-frames serialise only along their real chains.
 
 #define EVX_K5_THREADS 128
 
@@ -625,9 +635,49 @@ struct EvxK5Params
     const EvxDesc *table;
     const int16_t *records;        // dense, raster order of the non-copy macroblocks
     const int *record_slot;        // [nmb]
-    const uint32_t *order;
-    int *sync;
+    int *sync;                     // [0] ticket
+    int *done;                     // [nmb] 1 once the macroblock is reconstructed
+    int *readers;                  // [nmb] raster-earlier blocks that have yet to read this block's stale samples
 };
+
+// source rectangle of a block's prediction, as the macroblocks it touches
+struct EvxSrcRect { int bx0, bx1, by0, by1; int bxp, byp, dx, dy; bool sp, current; int slot; };
+
+__device__ __forceinline__ EvxSrcRect evx_decode_source(const EvxDesc &d, const EvxGeom &g, int px, int py, uint32_t frame_index, int R)
+{
+    EvxSrcRect r;
+    const int type = d.type() & 7;
+    const int mx = (type & EVX_T_MOTION) ? d.mx() : 0, my = (type & EVX_T_MOTION) ? d.my() : 0;
+    r.sp = (type & EVX_T_MOTION) && d.sp_pred();
+    r.dx = 0; r.dy = 0;
+    if (r.sp) evx_frac_direction(d.sp_index() & 7, r.dx, r.dy);
+    const int off = (type & EVX_T_INTRA) ? 0 : d.target();
+    r.slot = (int) ((frame_index + (uint32_t) R - (uint32_t) (off % R)) % (uint32_t) R);
+    r.current = type != EVX_T_INTRA && r.slot == (int) (frame_index % (uint32_t) R);
+    // a valid stream never points outside the frame; clamp so a corrupt one cannot fault
+    r.bxp = evx_clip(px + mx, 0, g.w - EVX_MB); r.byp = evx_clip(py + my, 0, g.h - EVX_MB);
+    if (r.sp) { r.dx = evx_clip(r.bxp + r.dx, 0, g.w - EVX_MB) - r.bxp; r.dy = evx_clip(r.byp + r.dy, 0, g.h - EVX_MB) - r.byp; }
+    const int x0 = min(r.bxp, r.bxp + r.dx), x1 = max(r.bxp, r.bxp + r.dx) + EVX_MB - 1;
+    const int y0 = min(r.byp, r.byp + r.dy), y1 = max(r.byp, r.byp + r.dy) + EVX_MB - 1;
+    r.bx0 = x0 >> 4; r.bx1 = x1 >> 4; r.by0 = y0 >> 4; r.by1 = y1 >> 4;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) evx_decode_deps(const EvxDesc *__restrict__ table, EvxGeom g, uint32_t frame_index, int R, int *__restrict__ readers)
+{
+    const int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mb >= g.mbw * g.mbh) return;
+    const EvxDesc d = table[mb];
+    const int bx = mb % g.mbw, by = mb / g.mbw;
+    const EvxSrcRect r = evx_decode_source(d, g, bx * EVX_MB, by * EVX_MB, frame_index, R);
+    if (!r.current) return;
+    for (int y = r.by0; y <= r.by1; ++y)
+    for (int x = r.bx0; x <= r.bx1; ++x)
+    {
+        const int m = y * g.mbw + x;
+        if (m > mb) atomicAdd(&readers[m], 1);
+    }
+}
 
 __global__ void __launch_bounds__(EVX_K5_THREADS) evx_decode_recon(const __grid_constant__ EvxK5Params p)
 {
@@ -638,7 +688,6 @@ __global__ void __launch_bounds__(EVX_K5_THREADS) evx_decode_recon(const __grid_
     const int nmb = g.mbw * g.mbh;
     const int dest = (int) (p.frame_index % (uint32_t) p.R);
     const EvxPlanes cur = p.ring[dest];
-    int *progress = p.sync + 2;
 
     evx_init_tables(sh, tid, EVX_K5_THREADS);
     for (;;)
@@ -646,40 +695,53 @@ __global__ void __launch_bounds__(EVX_K5_THREADS) evx_decode_recon(const __grid_
         __syncthreads();
         if (tid == 0) s_ticket = atomicAdd(&p.sync[0], 1);
         __syncthreads();
-        const int ticket = s_ticket;
-        if (ticket >= nmb) break;
-        const uint32_t ord = p.order[ticket];
-        const int bx = ord & 0xFFFF, by = ord >> 16;
+        const int mb = s_ticket;                      // raster order
+        if (mb >= nmb) break;
+        const int bx = mb % g.mbw, by = mb / g.mbw;
         const int px = bx * EVX_MB, py = by * EVX_MB;
-        const int mb = by * g.mbw + bx;
         const EvxDesc d = p.table[mb];
         const int type = d.type() & 7;
         const bool has_pred = type != EVX_T_INTRA;
+        const EvxSrcRect r = evx_decode_source(d, g, px, py, p.frame_index, p.R);
         if (!(type & EVX_T_COPY))
         {
             const int16_t *rec = p.records + (size_t) p.record_slot[mb] * 384;
             for (int e = tid; e < 384; e += EVX_K5_THREADS) sh.bufa[e] = rec[evx_record_index(e)];
         }
-        if (tid == 0) evx_wait_deps(progress, bx, by, g.mbw);
+        if (r.current)
+        {   // sources decoded earlier in this frame must be complete
+            if (tid == 0)
+                for (int y = r.by0; y <= r.by1; ++y)
+                for (int x = r.bx0; x <= r.bx1; ++x)
+                {
+                    const int m = y * g.mbw + x;
+                    if (m < mb) evx_wait_ge(p.done + m, 1);
+                }
+            __syncthreads();
+        }
+        if (has_pred) evx_build_pred_global(sh, p.ring[r.slot], g, r.bxp, r.byp, r.sp, d.sp_amount(), r.dx, r.dy, tid, EVX_K5_THREADS);
         __syncthreads();
-        if (has_pred)
+        if (tid == 0)
         {
-            int mx = (type & EVX_T_MOTION) ? d.mx() : 0, my = (type & EVX_T_MOTION) ? d.my() : 0;
-            bool sp = (type & EVX_T_MOTION) && d.sp_pred();
-            int dx = 0, dy = 0;
-            if (sp) evx_frac_direction(d.sp_index() & 7, dx, dy);
-            int off = (type & EVX_T_INTRA) ? 0 : d.target();
-            int slot = (int) ((p.frame_index + (uint32_t) p.R - (uint32_t) (off % p.R)) % (uint32_t) p.R);
-            // a valid stream never points outside the frame; clamp so a corrupt one cannot fault
-            int bxp = evx_clip(px + mx, 0, g.w - EVX_MB), byp = evx_clip(py + my, 0, g.h - EVX_MB);
-            if (sp) { dx = evx_clip(bxp + dx, 0, g.w - EVX_MB) - bxp; dy = evx_clip(byp + dy, 0, g.h - EVX_MB) - byp; }
-            evx_build_pred_global(sh, p.ring[slot], g, bxp, byp, sp, d.sp_amount(), dx, dy, tid, EVX_K5_THREADS);
+            if (r.current)
+            {   // our stale reads are in shared memory now: release the blocks we read from
+                __threadfence();
+                for (int y = r.by0; y <= r.by1; ++y)
+                for (int x = r.bx0; x <= r.bx1; ++x)
+                {
+                    const int m = y * g.mbw + x;
+                    if (m > mb) atomicSub(&p.readers[m], 1);
+                }
+            }
+            // and nobody may still need the samples we are about to overwrite
+            while (evx_ld_relaxed(p.readers + mb) > 0) __nanosleep(100);
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
         __syncthreads();
         if (type & EVX_T_COPY) evx_store_pred_as_recon(sh, cur, g, px, py, tid, EVX_K5_THREADS);
         else evx_reconstruct(sh, type, d.q_index(), p.linear, has_pred, cur, g, px, py, tid, EVX_K5_THREADS);
         __syncthreads();
-        if (tid == 0) { __threadfence(); evx_st_release(progress + by, bx + 1); }
+        if (tid == 0) { __threadfence(); evx_st_release(p.done + mb, 1); }
     }
 }
 

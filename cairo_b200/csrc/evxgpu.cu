@@ -62,6 +62,7 @@ struct evxgpu_handle
     int *d_record_slot;
     uint32_t *d_order;
     int *d_sync;
+    int *d_done;                      // decoder dependency tracking: done[nmb] followed by readers[nmb]
     unsigned long long *d_counters;
     CUtensorMap maps[8][3];
 
@@ -125,7 +126,7 @@ int evxgpu_destroy(evxgpu_handle *h)
     cudaFree(h->src_mem);
     for (int i = 0; i < 8; ++i) cudaFree(h->ring_mem[i]);
     cudaFree(h->d_rgb); cudaFree(h->d_table); cudaFree(h->d_inter); cudaFree(h->d_records); cudaFree(h->d_dense); cudaFree(h->d_row_records);
-    cudaFree(h->d_record_slot); cudaFree(h->d_order); cudaFree(h->d_sync); cudaFree(h->d_counters); cudaFree(h->d_prof);
+    cudaFree(h->d_record_slot); cudaFree(h->d_order); cudaFree(h->d_sync); cudaFree(h->d_done); cudaFree(h->d_counters); cudaFree(h->d_prof);
     cudaFreeHost(h->h_table); cudaFreeHost(h->h_records); cudaFreeHost(h->h_record_slot); cudaFreeHost(h->h_sync); cudaFreeHost(h->h_rgb);
     for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[k][e]) cudaEventDestroy(h->ev[k][e]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -172,6 +173,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     ok = ok && cudaMalloc(&h->d_record_slot, (size_t) h->nmb * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_order, (size_t) h->nmb * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_done, (size_t) h->nmb * 8) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_counters, 32) == cudaSuccess;
     ok = ok && cudaHostAlloc(&h->h_table, (size_t) h->nmb * 16, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&h->h_records, (size_t) h->nmb * 384 * 2, cudaHostAllocDefault) == cudaSuccess;
@@ -221,7 +223,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
         for (int e = 0; e < 2; ++e)
             if (cudaEventCreate(&h->ev[k][e]) != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaEventCreate"); }
     // enough CTAs to cover the widest wavefront plus a few to prefetch the next step
-    h->wave_grid = std::min(h->nmb, std::min(148, std::min(h->g.mbh, (h->g.mbw + 2) / 3) + 8));
+    h->wave_grid = std::min(h->nmb, 148 * 8);      // persistent CTAs of the decoder kernel
     int rc = evxgpu_reset(h);
     if (rc) { evxgpu_destroy(h); return rc; }
     *out = h;
@@ -430,12 +432,15 @@ int evxgpu_decode_submit(evxgpu_handle *h, const evxgpu_block_desc *table, const
     EvxK5Params p;
     for (int i = 0; i < 8; ++i) p.ring[i] = h->ring[i];
     p.g = h->g; p.R = h->cfg.ref_count; p.linear = h->cfg.linear_quant; p.frame_index = frame_index;
-    p.table = h->d_table; p.records = h->d_dense; p.record_slot = h->d_record_slot; p.order = h->d_order; p.sync = h->d_sync;
+    p.table = h->d_table; p.records = h->d_dense; p.record_slot = h->d_record_slot; p.sync = h->d_sync;
+    p.done = h->d_done; p.readers = h->d_done + h->nmb;
     CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_done, 0, (size_t) h->nmb * 8, h->stream));
     t_begin(h, EVXGPU_T_DECODE_RECON);
-    evx_decode_recon<<<h->wave_grid, EVX_K5_THREADS, 0, h->stream>>>(p);
+    evx_decode_deps<<<(h->nmb + 255) / 256, 256, 0, h->stream>>>(h->d_table, h->g, frame_index, h->cfg.ref_count, p.readers);
+    evx_decode_recon<<<std::min(h->nmb, h->wave_grid), EVX_K5_THREADS, 0, h->stream>>>(p);
     t_end(h, EVXGPU_T_DECODE_RECON);
-    h->launches++;
+    h->launches += 2;
     CK(cudaGetLastError());
     int rc;
     if ((rc = launch_deblock(h, frame_index))) return rc;
@@ -514,7 +519,7 @@ int evxgpu_stage_set_block_table(evxgpu_handle *h, const evxgpu_block_desc *tabl
 int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas)
 {
     if (!h) return 1;
-    if (ctas <= 0) ctas = std::min(h->g.mbh, (h->g.mbw + 2) / 3) + 8;
+    if (ctas <= 0) ctas = 148 * 8;
     h->wave_grid = std::max(1, std::min(h->nmb, ctas));
     return 0;
 }

@@ -139,3 +139,45 @@ def test_golden_encode_and_decode(name):
 def test_1080p_encode_matches_oracle_two_frames():
     """BASELINE config size; the oracle needs ~2 s per 1080p P-frame, so two frames only."""
     _run_encode(1920, 1080, 2, 2, 0, 1, 16, "moving", seed=5)
+
+
+def test_decoder_dependency_tracking_on_adversarial_tables():
+    """Random block tables: intra-motion blocks pointing anywhere in the frame under construction
+    (already-decoded blocks AND not-yet-decoded ones, whose stale ring contents must be read),
+    random sub-pel, random coefficients.  The GPU decoder must equal the oracle's raster-order
+    decode_slice.  Sources never overlap the block's own position (no valid stream does that)."""
+    from cairo_b200 import gpu
+    rng = np.random.default_rng(11)
+    w, h, R = 128, 96, 4
+    mbw, mbh = w // 16, h // 16
+    p = gpu.Pipeline(w, h, R, 0, 1)
+    o = O.Oracle(w, h, R, 0, 1)
+    for t in range(6):
+        tbl = np.zeros(mbw * mbh, dtype=gpu.BLOCK_DESC_DTYPE)
+        for mb in range(mbw * mbh):
+            bx, by = mb % mbw, mb // mbw
+            ty = int(rng.choice([1, 3, 7, 3, 7, 0, 2, 4, 6]))       # intra-motion types over-represented
+            tbl["block_type"][mb] = ty
+            tbl["prediction_target"][mb] = rng.integers(1, R) if not (ty & 1) else 0
+            if ty & 2:
+                while True:
+                    sx, sy = int(rng.integers(1, w - 17)), int(rng.integers(1, h - 17))
+                    if abs(sx - bx * 16) >= 18 or abs(sy - by * 16) >= 18:
+                        break
+                tbl["motion_x"][mb], tbl["motion_y"][mb] = sx - bx * 16, sy - by * 16
+                tbl["sp_pred"][mb] = rng.integers(0, 2)
+                tbl["sp_amount"][mb] = rng.integers(0, 2)
+                tbl["sp_index"][mb] = rng.integers(0, 8)
+            tbl["q_index"][mb] = rng.integers(1, 32)
+        n = int(((tbl["block_type"] & 4) == 0).sum())
+        rec = rng.integers(-40, 40, size=(n, 384)).astype(np.int16)
+        rec[rng.random(rec.shape) < 0.85] = 0
+        # oracle: table + coefficient planes, then the reference's raster-order decode
+        o.block_table()[...] = tbl
+        coef = [o.plane(1, 0, c) for c in range(3)]
+        gpu.records_to_planes(tbl, rec, coef, o.aw, o.ah)
+        o.decode_slice(0 if t == 0 else 1, t)
+        o.deblock(t)
+        rgb = p.decode(tbl, rec, 0 if t == 0 else 1, t)
+        assert _same(p.planes(2, t % R), o.planes(2, t % R)), t
+        assert (rgb == o.convert_out(t)).all(), t
