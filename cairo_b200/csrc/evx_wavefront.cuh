@@ -319,19 +319,33 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             // Every cell is evaluated unconditionally (any position a round can name lies inside the
             // staged window rows, and the ring masks the columns); illegal ones are flagged, not skipped,
             // which keeps the cells of a warp in one basic block.
-#pragma unroll
-            for (int q = 0; q < EVX_K3_CPW; ++q)
             {
-                const int cell = round == 0 ? ccell0[q] : ccell[q];
-                const int x = s.bx + (round == 0 ? cdx0[q] : cdx[q]) * step, y = s.by + (round == 0 ? cdy0[q] : cdy[q]) * step;
-                EvxLaneBlock ref;
-                int sad, mad;
-                evx_load_block_ring_bf(win, x, y, lane, ref);
-                evx_block_cost_both(ref, src, sad, mad);
-                const int ssd = (x - px) * (x - px) + (y - py) * (y - py);
-                int4 res = evx_candidate_keys(sad, mad, ssd, thr);
-                if (!evx_intra_legal(x, y, px, py, g)) res.w = 0;
-                if (lane == 0) { S.cand[buf][cell] = res; S.cval[buf][cell] = make_int4(sad, mad, ssd, 0); }
+                // all of this warp's cells: loads and packed arithmetic first, then every reduction
+                // back to back, so the cells overlap instead of queueing behind each other's REDUX
+                int cx_[EVX_K3_CPW], cy_[EVX_K3_CPW], la[EVX_K3_CPW], lm[EVX_K3_CPW];
+#pragma unroll
+                for (int q = 0; q < EVX_K3_CPW; ++q)
+                {
+                    cx_[q] = s.bx + (round == 0 ? cdx0[q] : cdx[q]) * step;
+                    cy_[q] = s.by + (round == 0 ? cdy0[q] : cdy[q]) * step;
+                    EvxLaneBlock ref;
+                    evx_load_block_ring_bf(win, cx_[q], cy_[q], lane, ref);
+                    la[q] = evx_block_sad_lane(ref, src);
+                    lm[q] = evx_block_mad_lane(ref, src);
+                }
+                int sad[EVX_K3_CPW], mad[EVX_K3_CPW];
+#pragma unroll
+                for (int q = 0; q < EVX_K3_CPW; ++q) { sad[q] = __reduce_add_sync(0xFFFFFFFFu, la[q]); mad[q] = __reduce_max_sync(0xFFFFFFFFu, lm[q]); }
+#pragma unroll
+                for (int q = 0; q < EVX_K3_CPW; ++q)
+                {
+                    const int cell = round == 0 ? ccell0[q] : ccell[q];
+                    const int x = cx_[q], y = cy_[q];
+                    const int ssd = (x - px) * (x - px) + (y - py) * (y - py);
+                    int4 res = evx_candidate_keys(sad[q], mad[q], ssd, thr);
+                    if (!evx_intra_legal(x, y, px, py, g)) res.w = 0;
+                    if (lane == 0) { S.cand[buf][cell] = res; S.cval[buf][cell] = make_int4(sad[q], mad[q], ssd, 0); }
+                }
             }
             if (warp == 0 && lane == 0)
             {

@@ -181,3 +181,51 @@ def test_decoder_dependency_tracking_on_adversarial_tables():
         rgb = p.decode(tbl, rec, 0 if t == 0 else 1, t)
         assert _same(p.planes(2, t % R), o.planes(2, t % R)), t
         assert (rgb == o.convert_out(t)).all(), t
+
+
+@pytest.mark.parametrize("size", [(2, 2), (16, 16), (18, 34), (48, 16), (16, 48), (30, 30), (130, 18), (34, 130)])
+def test_tiny_and_ragged_frames(size):
+    """Smallest and ragged frames: one macroblock, one row, one column, widths that are not
+    multiples of 8 (byte-path colour conversion) -- encode parity and decode round trip."""
+    from cairo_b200 import gpu
+    w, h = size
+    R, q = 4, 12
+    p = gpu.Pipeline(w, h, R, 0, 1)
+    dec = gpu.Pipeline(w, h, R, 0, 1)
+    o = O.Oracle(w, h, R, 0, 1)
+    rng = np.random.default_rng(w * 1000 + h)
+    for t in range(4):
+        f = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8) if t % 2 else np.full((h, w, 3), 40 + 50 * t, np.uint8)
+        ft = 0 if t == 0 else 1
+        o.convert_in(f)
+        o.encode_slice(ft, t, q)
+        tbl, rec = p.encode(f, ft, t, q)
+        assert _same(p.planes(0), o.planes(0)), (size, t)
+        assert O.tables_equal(o.block_table().copy(), tbl), (size, t)
+        o.deblock(t)
+        assert _same(p.planes(2, t % R), o.planes(2, t % R)), (size, t)
+        rgb = dec.decode(tbl, rec, ft, t)
+        assert (rgb == o.convert_out(t)).all(), (size, t)
+
+
+def test_create_rejects_bad_geometry():
+    from cairo_b200 import gpu
+    for w, h in [(0, 16), (16, 0), (15, 16), (16, 15), (4096, 4096)]:      # odd sizes; > 65535 macroblocks
+        with pytest.raises(RuntimeError):
+            gpu.Pipeline(w, h)
+    with pytest.raises(RuntimeError):
+        gpu.Pipeline(64, 64, ref_count=1)        # a ring of one slot has no past frame
+    with pytest.raises(RuntimeError):
+        gpu.Pipeline(64, 64, ref_count=9)
+
+
+def test_largest_frame_geometry_runs():
+    """4096x4080 = 65280 macroblocks, just under the uint16 block_count limit (serialize.cpp:321)."""
+    from cairo_b200 import gpu
+    w, h = 4096, 4080
+    p = gpu.Pipeline(w, h, 2, 0, 1)
+    assert p.nblocks == 65280
+    f = synth.frame(w, h, 0, 0, "moving")
+    tbl, rec = p.encode(f, 0, 0, 16)
+    tbl2, rec2 = p.encode(f, 1, 1, 16)
+    assert ((tbl2["block_type"] & 4) != 0).mean() > 0.5      # a repeated frame is mostly copy blocks
