@@ -107,49 +107,13 @@ struct EvxSel
     int sp_index, sp_amount, sp_enabled;
 };
 
-// motion.cpp:111-149.  Second rule as written: sad<best || (sad==best && ssd<best_ssd && sad<8192) || mad<thr
-__device__ __forceinline__ void evx_accept_fullpel(EvxSel &s, int x, int y, int sad, int mad, int px, int py, int thr)
-{
-    int ssd = (x - px) * (x - px) + (y - py) * (y - py);
-    bool take;
-    if (s.mad < thr) take = mad < s.mad || (mad == s.mad && ssd < s.ssd);
-    else take = sad < s.sad || (sad == s.sad && ssd < s.ssd && (uint32_t) sad < EVX_SAD_CAP) || mad < thr;
-    if (take) { s.bx = x; s.by = y; s.sad = sad; s.ssd = ssd; s.mad = mad; }
-}
-
-// motion.cpp:151-223 (one of the two tests of a direction)
-__device__ __forceinline__ void evx_accept_subpel(EvxSel &s, int i, int j, int quarter, int sad, int mad, int thr)
-{
-    bool take;
-    if (s.mad < thr) take = mad < s.mad;
-    else take = (sad < s.sad && (uint32_t) sad < EVX_SAD_CAP) || mad < thr;
-    if (take) { s.sp_enabled = 1; s.sp_amount = quarter; s.sp_index = evx_frac_index(i, j); s.sad = sad; s.mad = mad; }
-}
-
-// Branch-free forms of the two acceptance rules for the replay loops of K3 (same truth tables
-// as evx_accept_fullpel / evx_accept_subpel; `legal` gates the whole update).
-__device__ __forceinline__ void evx_replay_fullpel(EvxSel &s, bool legal, int sad, int mad, int ssd, int x, int y, int thr)
-{
-    const bool closer = ssd < s.ssd;
-    const bool t1 = (mad < s.mad) | ((mad == s.mad) & closer);
-    const bool t2 = (sad < s.sad) | ((sad == s.sad) & closer & ((uint32_t) sad < EVX_SAD_CAP)) | (mad < thr);
-    const bool take = legal & ((s.mad < thr) ? t1 : t2);
-    s.bx = take ? x : s.bx; s.by = take ? y : s.by;
-    s.sad = take ? sad : s.sad; s.ssd = take ? ssd : s.ssd; s.mad = take ? mad : s.mad;
-}
-
-__device__ __forceinline__ void evx_replay_subpel(EvxSel &s, bool legal, int index, int quarter, int sad, int mad, int thr)
-{
-    const bool t1 = mad < s.mad;
-    const bool t2 = ((sad < s.sad) & ((uint32_t) sad < EVX_SAD_CAP)) | (mad < thr);
-    const bool take = legal & ((s.mad < thr) ? t1 : t2);
-    s.sp_enabled = take ? 1 : s.sp_enabled; s.sp_amount = take ? quarter : s.sp_amount; s.sp_index = take ? index : s.sp_index;
-    s.sad = take ? sad : s.sad; s.mad = take ? mad : s.mad;
-}
-
 // ------------------------------------------------------------------ closed-form acceptance
 //
-// The reference accepts the candidates of a round one after the other (motion.cpp:111-149).
+// The reference accepts the candidates of a round one after the other (motion.cpp:111-149):
+//   holding a copy candidate (best_mad < thr):  take iff mad < best_mad || (mad == best_mad && ssd < best_ssd)
+//   otherwise: take iff sad < best_sad || (sad == best_sad && ssd < best_ssd && sad < 8192) || mad < thr
+// (operator precedence as written in the source); sub-pel tests (motion.cpp:151-223):
+//   copy mode: take iff mad < best_mad;  otherwise: take iff (sad < best_sad && sad < 8192) || mad < thr.
 // With each candidate as sortable keys that fold has a closed form:
 //   key1 = sad:ssd'  (ssd' = 4095 = "infinite" when sad >= 8192: that disables the tie rule exactly
 //                     where the reference's `&& sad < 8192` does),   key2 = mad:ssd,
@@ -279,38 +243,8 @@ struct EvxRingWin
 #define EVX_RING_PWY 72
 #define EVX_RING_PWC 36
 
-__device__ __forceinline__ void evx_load_block_ring(const EvxRingWin &win, int x, int y, int lane, EvxLaneBlock &b)
-{
-    const uint32_t *row = win.y + (y - win.oy + (lane >> 3)) * EVX_RING_PWY;
-    int w0 = (x >> 1) + (lane & 7);
-    if (x & 1)
-    {
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            b.w[k] = __byte_perm(row[4 * k * EVX_RING_PWY + (w0 & 63)], row[4 * k * EVX_RING_PWY + ((w0 + 1) & 63)], 0x5432);
-    }
-    else
-    {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) b.w[k] = row[4 * k * EVX_RING_PWY + (w0 & 63)];
-    }
-    int cx = x >> 1;
-    int crow = ((y >> 1) - win.coy + (lane >> 2)) * EVX_RING_PWC;
-    int c0 = (cx >> 1) + (lane & 3);
-    if (cx & 1)
-    {
-        b.w[4] = __byte_perm(win.u[crow + (c0 & 31)], win.u[crow + ((c0 + 1) & 31)], 0x5432);
-        b.w[5] = __byte_perm(win.v[crow + (c0 & 31)], win.v[crow + ((c0 + 1) & 31)], 0x5432);
-    }
-    else
-    {
-        b.w[4] = win.u[crow + (c0 & 31)];
-        b.w[5] = win.v[crow + (c0 & 31)];
-    }
-}
-
-// Branch-free variant (both neighbouring words are always fetched and the parity picks the
-// byte selector), so two candidates of one warp can be scheduled in the same basic block.
+// Both neighbouring words are always fetched and the parity picks the byte selector: no branch,
+// so several candidates can be scheduled in one basic block.
 __device__ __forceinline__ void evx_load_block_ring_bf(const EvxRingWin &win, int x, int y, int lane, EvxLaneBlock &b)
 {
     const uint32_t *row = win.y + (y - win.oy + (lane >> 3)) * EVX_RING_PWY;
@@ -351,28 +285,6 @@ __device__ __forceinline__ void evx_make_src(const EvxLaneBlock &b, EvxLaneSrc &
 // candidate against the warp's source block.  Per packed word: three VIADDMNMX.S16x2
 // (running max and min of ref-src, and relu(ref-src)) and two IDP.2A:
 //   sum|d| = 2*sum relu(d) - sum d,   max|d| = max(max d, -min d).
-__device__ __forceinline__ void evx_block_cost_lane(const EvxLaneBlock &ref, const EvxLaneSrc &src, int &acc, int &m)
-{
-    uint32_t amx = 0x80008000u, amn = 0x7FFF7FFFu;
-    acc = src.lsum;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-    {
-        amx = __viaddmax_s16x2(ref.w[k], src.neg[k], amx);
-        amn = __viaddmin_s16x2(ref.w[k], src.neg[k], amn);
-        uint32_t r = __viaddmax_s16x2_relu(ref.w[k], src.neg[k], 0u);
-        acc = __dp2a_lo((int) r, 0x0202, acc);
-        acc = __dp2a_lo((int) ref.w[k], 0xFFFF, acc);
-    }
-#pragma unroll
-    for (int k = 4; k < 6; ++k)
-    {
-        amx = __viaddmax_s16x2(ref.w[k], src.neg[k], amx);
-        amn = __viaddmin_s16x2(ref.w[k], src.neg[k], amn);
-    }
-    m = max(max(evx_lo16(amx), evx_hi16(amx)), -min(evx_lo16(amn), evx_hi16(amn)));
-}
-
 // SAD only: one VIADDMNMX.S16x2.RELU and two IDP.2A per packed word.
 __device__ __forceinline__ int evx_block_sad_lane(const EvxLaneBlock &ref, const EvxLaneSrc &src)
 {
@@ -522,28 +434,6 @@ __constant__ int16_t EVX_BETA[32]  = { 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2,
 // quantize.cpp:37-55
 __device__ __forceinline__ int evx_luma_dc_scale(int qp) { return qp < 5 ? 8 : qp < 9 ? qp << 1 : qp < 25 ? qp + 8 : (qp << 1) - 16; }
 __device__ __forceinline__ int evx_chroma_dc_scale(int qp) { return qp < 5 ? 8 : qp < 25 ? (qp + 13) >> 1 : qp - 6; }
-
-// quantize.cpp:79-180: one coefficient.  mode 0 intra luma, 1 intra chroma, 2 inter; pos = j*8+k
-__device__ __forceinline__ int evx_quant(int s, int pos, int mode, int qp, int linear, const int16_t *qm_intra, const int16_t *qm_inter)
-{
-    int out;
-    if (linear)
-    {
-        if (mode < 2) out = (short) evx_rdiv(s, qp << 1);
-        else { int m = (short) (evx_abs16(s) - (qp >> 1)); out = (short) evx_rdiv(m, qp << 1); out = (short) (out * evx_sign(s)); }
-    }
-    else if (mode < 2)
-    {
-        if (pos == 0) out = (short) evx_rdiv(s, mode == 0 ? evx_luma_dc_scale(qp) : evx_chroma_dc_scale(qp));
-        else out = (short) evx_rdiv(evx_rdiv(s * 16, qm_intra[pos]), qp << 1);
-    }
-    else
-    {
-        int f = (short) evx_rdiv(s * 16, qm_inter[pos]);
-        out = (short) evx_rdiv(f - evx_sign(f) * qp, qp << 1);
-    }
-    return out;
-}
 
 // quantize.cpp:182-243
 __device__ __forceinline__ int evx_dequant(int s, int pos, int mode, int qp, int linear, const int16_t *qm_intra, const int16_t *qm_inter)

@@ -378,7 +378,8 @@ __device__ __forceinline__ int evx_rdiv_recip(int n, int d, const uint32_t *reci
     return n < 0 ? -q : q;
 }
 
-// evx_quant without hardware division (the divisors are matrix entries 8..45, 2*qp <= 62, dc scales <= 46)
+// quantize.cpp:79-180: one coefficient (mode 0 intra luma, 1 intra chroma, 2 inter; pos = j*8+k),
+// without hardware division (the divisors are matrix entries 8..45, 2*qp <= 62, dc scales <= 46)
 __device__ __forceinline__ int evx_quant_fast(int s, int pos, int mode, int qp, int linear, const int16_t *qm_intra, const int16_t *qm_inter, const uint32_t *recip)
 {
     int out;
@@ -398,30 +399,6 @@ __device__ __forceinline__ int evx_quant_fast(int s, int pos, int mode, int qp, 
         out = (short) evx_rdiv_recip(f - evx_sign(f) * qp, qp << 1, recip);
     }
     return out;
-}
-
-// forward 8x8 passes (transform.cpp:264-301): in[b][line][k] -> out, scale after the sum
-__device__ __forceinline__ void evx_fdct_pass(const int16_t *in, int16_t *out, const int16_t *lut, int tid, int nt, bool columns)
-{
-    for (int e = tid; e < 384; e += nt)
-    {
-        int b = e >> 6, a = (e >> 3) & 7, i = e & 7;
-        int t = 0;
-        if (!columns)
-        {   // row pass: out[b][a][i] = sum_k in[b][a][k] * lut[i][k]
-#pragma unroll
-            for (int k = 0; k < 8; ++k) t += in[b * 64 + a * 8 + k] * lut[i * 8 + k];
-        }
-        else
-        {   // column pass: out[b][i][a] = sum_k in[b][k][a] * lut[i][k]   (e enumerates (a=column, i))
-#pragma unroll
-            for (int k = 0; k < 8; ++k) t += in[b * 64 + k * 8 + a] * lut[i * 8 + k];
-        }
-        t = i == 0 ? evx_tdiv_pow2(t * 45, 7) : evx_tdiv_pow2(t, 1);
-        int v = (short) evx_rdiv_pow2(t, 7);
-        if (!columns) out[b * 64 + a * 8 + i] = (int16_t) v;
-        else out[b * 64 + i * 8 + a] = (int16_t) v;
-    }
 }
 
 // inverse 8x8 passes (transform.cpp:330-366, 418-433): scale per term
@@ -513,13 +490,6 @@ __device__ __forceinline__ void evx_build_pred_global(EvxMbShared &sh, const Evx
 // an atomic ticket in wavefront order, so a CTA holding ticket k only ever waits on tickets
 // < k, all of which are already held by running (or finished) CTAs: no deadlock for any grid.
 
-__device__ __forceinline__ int evx_ld_acquire(const int *p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // Polling with an acquire load costs an L1 invalidate (CCTL.IVALL) per poll, which stalls the
 // LSU the compute warps of the same SM are using; poll relaxed, fence once on success.
 __device__ __forceinline__ int evx_ld_relaxed(const int *p)
@@ -538,12 +508,6 @@ __device__ __forceinline__ void evx_wait_ge(const int *p, int need)
 __device__ __forceinline__ void evx_st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-__device__ __forceinline__ void evx_wait_deps(const int *progress, int bx, int by, int mbw)
-{
-    if (bx > 0) evx_wait_ge(progress + by, bx);
-    if (by > 0) evx_wait_ge(progress + by - 1, min(bx + 2, mbw - 1) + 1);
 }
 
 // ------------------------------------------------------------------ K3 parameters (kernel in evx_wavefront.cuh)

@@ -214,23 +214,8 @@ __device__ __forceinline__ void evx_k3_loader(EvxK3Smem &S, const EvxK3Params &p
 
 // ---------------------------------------------------------------- compute warps
 
-// Sortable form of a full-pel candidate for the acceptance replay (motion.cpp:111-149):
-//   x = key1   = sad:ssd'  with ssd' = 4095 ("infinite") when sad >= 8192 -- that disables the
-//                tie rule exactly where the reference's `&& sad < 8192` does;
-//   y = key1 the state takes on if this candidate is accepted (true ssd);
-//   z = key2   = mad:ssd   (the copy-mode order);   w = flags: bit0 legal, bit1 mad < thr.
-// ssd <= 32^2 + 48^2 = 3328 < 4095 for every reachable position; sad, mad are clamped to 20 bits.
-__device__ __forceinline__ int4 evx_candidate_keys(int sad, int mad, int ssd, int thr)
-{
-    const uint32_t hi1 = (uint32_t) min(sad, 0xFFFFE) << 12;
-    const uint32_t z = (uint32_t) min(ssd, 4095);
-    int4 r;
-    r.x = (int) (hi1 | ((uint32_t) sad < EVX_SAD_CAP ? z : 4095u));
-    r.y = (int) (hi1 | z);
-    r.z = (int) (((uint32_t) min(mad, 0xFFFFE) << 12) | z);
-    r.w = 1 | (mad < thr ? 2 : 0);
-    return r;
-}
+// a published candidate: {key1, key2, flags (bit0 legal, bit1 mad < thr), unused}; see evx_make_keys
+__device__ __forceinline__ int4 evx_pack_keys(const EvxKeys &k) { return make_int4((int) k.k1, (int) k.k2, (k.legal ? 1 : 0) | (k.lt ? 2 : 0), 0); }
 
 __device__ __forceinline__ bool evx_intra_legal(int x, int y, int px, int py, const EvxGeom &g)
 {
@@ -342,8 +327,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                     const int cell = round == 0 ? ccell0[q] : ccell[q];
                     const int x = cx_[q], y = cy_[q];
                     const int ssd = (x - px) * (x - px) + (y - py) * (y - py);
-                    int4 res = evx_candidate_keys(sad[q], mad[q], ssd, thr);
-                    if (!evx_intra_legal(x, y, px, py, g)) res.w = 0;
+                    const int4 res = evx_pack_keys(evx_make_keys(sad[q], mad[q], ssd, thr, evx_intra_legal(x, y, px, py, g)));
                     if (lane == 0) { S.cand[buf][cell] = res; S.cval[buf][cell] = make_int4(sad[q], mad[q], ssd, 0); }
                 }
             }
@@ -352,38 +336,19 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 if (round == 0) S.cand[buf][8] = make_int4(0, 0, 0, 0);
                 else
                 {
-                    int4 c4 = evx_candidate_keys(s.sad, s.mad, s.ssd, thr);
-                    if (s.bx == px && s.by == py) c4.w = 0;
-                    S.cand[buf][4] = c4;
+                    S.cand[buf][4] = evx_pack_keys(evx_make_keys(s.sad, s.mad, s.ssd, thr, s.bx != px || s.by != py));
                     S.cval[buf][4] = make_int4(s.sad, s.mad, s.ssd, 0);
                 }
             }
             evx_compute_sync();
-            // The reference accepts candidates sequentially (motion.cpp:111-149).  With the candidates
-            // as sortable keys that fold has a closed form, evaluated here lane-parallel (lane c = cell c):
-            //   * already in copy mode (best_mad < thr): every take needs (mad,ssd) < (best_mad,best_ssd),
-            //     so the survivor is the FIRST minimum of key2, if it beats the state;
-            //   * otherwise, if some legal cell has mad < thr, the first such cell c* is taken
-            //     unconditionally and flips the state to copy mode: survivor = first minimum of key2 over c >= c*;
-            //   * otherwise every take needs (sad,ssd') < (best_sad,best_ssd): survivor = first minimum of key1.
-            // (key1 carries ssd' = "infinite" for sad >= 8192, which is exactly the reference's tie rule.)
+            // acceptance in closed form (evx_select_fullpel), lane c = cell c in visiting order
             {
                 const int4 v = lane < 9 ? S.cand[buf][lane] : make_int4(0, 0, 0, 0);
-                const bool legal = (v.w & 1) != 0;
-                const unsigned legal_mask = __ballot_sync(0xFFFFFFFFu, legal);
-                const unsigned lt_mask = __ballot_sync(0xFFFFFFFFu, legal && (v.w & 2));
-                n_full += __popc(legal_mask);
-                const bool copy0 = s.mad < thr;
-                uint32_t key, init;
-                unsigned elig = legal_mask;
-                if (copy0) { key = (uint32_t) v.z; init = ((uint32_t) min(s.mad, 0xFFFFE) << 12) | (uint32_t) min(s.ssd, 4095); }
-                else if (lt_mask) { key = (uint32_t) v.z; elig &= 0xFFFFFFFFu << (__ffs(lt_mask) - 1); init = 0xFFFFFFFFu; }
-                else { key = (uint32_t) v.x; init = ((uint32_t) min(s.sad, 0xFFFFE) << 12) | (uint32_t) min(s.ssd, 4095); }
-                const uint32_t mykey = ((elig >> lane) & 1u) ? key : 0xFFFFFFFFu;
-                const uint32_t m = __reduce_min_sync(0xFFFFFFFFu, mykey);
-                if (m < init)
+                EvxKeys k;
+                k.k1 = (uint32_t) v.x; k.k2 = (uint32_t) v.y; k.legal = (v.z & 1) != 0; k.lt = (v.z & 2) != 0;
+                const int wcell = evx_select_fullpel(s, k, lane, thr, n_full);
+                if (wcell >= 0)
                 {
-                    const int wcell = __ffs(__ballot_sync(0xFFFFFFFFu, mykey == m)) - 1;
                     const int4 val = S.cval[buf][wcell];
                     s.bx += (wcell % 3 - 1) * step; s.by += (top + wcell / 3) * step;
                     s.sad = val.x; s.mad = val.y; s.ssd = val.z;
@@ -409,28 +374,12 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 if (lane == 0) { S.cand[buf][2 * k] = make_int4(shh, mh, 0, ok); S.cand[buf][2 * k + 1] = make_int4(sq, mq, 0, ok); }
             }
             evx_compute_sync();
-            // sub-pel acceptance (motion.cpp:151-223), same closed form over the 16 tests in reference
-            // order (direction-major, half before quarter): copy mode -> first minimum of mad;
-            // else a test with mad < thr exists -> first minimum of mad from the first such test on;
-            // else -> first minimum of sad among tests with sad < 8192.
+            // sub-pel acceptance in closed form (evx_select_subpel), lane t = test t
             {
                 const int4 v = lane < 16 ? S.cand[buf][lane] : make_int4(0, 0, 0, 0);
-                const bool legal = v.w != 0;
-                const unsigned legal_mask = __ballot_sync(0xFFFFFFFFu, legal);
-                const unsigned lt_mask = __ballot_sync(0xFFFFFFFFu, legal && v.y < thr);
-                const unsigned cap_mask = __ballot_sync(0xFFFFFFFFu, legal && (uint32_t) v.x < EVX_SAD_CAP);
-                n_sub += __popc(legal_mask);
-                const bool copy0 = s.mad < thr;
-                int key, init;
-                unsigned elig = legal_mask;
-                if (copy0) { key = v.y; init = s.mad; }
-                else if (lt_mask) { key = v.y; elig &= 0xFFFFFFFFu << (__ffs(lt_mask) - 1); init = EVX_BIG; }
-                else { key = v.x; elig = cap_mask; init = s.sad; }
-                const int mykey = ((elig >> lane) & 1u) ? key : EVX_BIG;
-                const int m = __reduce_min_sync(0xFFFFFFFFu, mykey);
-                if (m < init)
+                const int wt = evx_select_subpel(s, v.x, v.y, v.w != 0, lane, thr, n_sub);
+                if (wt >= 0)
                 {
-                    const int wt = __ffs(__ballot_sync(0xFFFFFFFFu, mykey == m)) - 1;
                     const int dd = (wt >> 1) < 4 ? (wt >> 1) : (wt >> 1) + 1;
                     s.sp_enabled = 1; s.sp_amount = wt & 1; s.sp_index = evx_frac_index(dd % 3 - 1, dd / 3 - 1);
                     s.sad = __shfl_sync(0xFFFFFFFFu, v.x, wt); s.mad = __shfl_sync(0xFFFFFFFFu, v.y, wt);

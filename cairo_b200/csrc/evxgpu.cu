@@ -60,7 +60,6 @@ struct evxgpu_handle
     int16_t *d_dense;               // packed raster-order records (K7) / decoder input
     int *d_row_records;
     int *d_record_slot;
-    uint32_t *d_order;
     int *d_sync;
     int *d_done;                      // decoder dependency tracking: done[nmb] followed by readers[nmb]
     unsigned long long *d_counters;
@@ -126,7 +125,7 @@ int evxgpu_destroy(evxgpu_handle *h)
     cudaFree(h->src_mem);
     for (int i = 0; i < 8; ++i) cudaFree(h->ring_mem[i]);
     cudaFree(h->d_rgb); cudaFree(h->d_table); cudaFree(h->d_inter); cudaFree(h->d_records); cudaFree(h->d_dense); cudaFree(h->d_row_records);
-    cudaFree(h->d_record_slot); cudaFree(h->d_order); cudaFree(h->d_sync); cudaFree(h->d_done); cudaFree(h->d_counters); cudaFree(h->d_prof);
+    cudaFree(h->d_record_slot); cudaFree(h->d_sync); cudaFree(h->d_done); cudaFree(h->d_counters); cudaFree(h->d_prof);
     cudaFreeHost(h->h_table); cudaFreeHost(h->h_records); cudaFreeHost(h->h_record_slot); cudaFreeHost(h->h_sync); cudaFreeHost(h->h_rgb);
     for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[k][e]) cudaEventDestroy(h->ev[k][e]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -171,7 +170,6 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     ok = ok && cudaMalloc(&h->d_dense, (size_t) h->nmb * 384 * 2) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_row_records, (size_t) h->g.mbh * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_record_slot, (size_t) h->nmb * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&h->d_order, (size_t) h->nmb * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_done, (size_t) h->nmb * 8) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_counters, 32) == cudaSuccess;
@@ -184,20 +182,6 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     set_planes(h->src, h->src_mem, h->g);
     for (int i = 0; i < cfg->ref_count; ++i) set_planes(h->ring[i], h->ring_mem[i], h->g);
 
-    // wavefront order: step = bx + 3*by, rows ascending inside a step
-    {
-        std::vector<uint32_t> order;
-        order.reserve(h->nmb);
-        int steps = h->g.mbw + 3 * (h->g.mbh - 1);
-        for (int s = 0; s < steps; ++s)
-            for (int by = 0; by < h->g.mbh; ++by)
-            {
-                int bx = s - 3 * by;
-                if (bx >= 0 && bx < h->g.mbw) order.push_back((uint32_t) bx | ((uint32_t) by << 16));
-            }
-        cudaError_t e = cudaMemcpy(h->d_order, order.data(), (size_t) h->nmb * 4, cudaMemcpyHostToDevice);
-        if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "upload wavefront order", e); }
-    }
     // TMA descriptors of every ring slot (search windows of K2)
     {
         void *fn = NULL;
