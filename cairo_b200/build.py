@@ -3,6 +3,7 @@
     python -m cairo_b200.build          # libevxgpu.so (CUDA pixel pipeline + C-ABI) and libevx1.so (C++ host API)
 """
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -39,7 +40,24 @@ def build_gpu(force=False, verbose=False):
         return GPU_SO
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", GPU_SO, os.path.join(CSRC, "evxgpu.cu")]
     subprocess.check_call(cmd)
+    lint_sass(GPU_SO)
     return GPU_SO
+
+
+def lint_sass(so):
+    """Guard against a ptxas 12.9 miscompile met in round 1: when it rematerialises the packed
+    negation `add.u16x2 r, ~v, 0x00010001` (evx_neg16x2) in split halves it can drop the immediate and
+    emit `VIADD.16x2 Rd, Ra, 0x0` -- every difference against that source word is then off by one
+    (the PTX is correct; profiles/r01_summary.md has the trace).  No kernel here adds a zero
+    constant on purpose, so that instruction anywhere in the library fails the build."""
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        return
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True, check=True).stdout
+    bad = re.findall(r"VIADD\.16x2 R\d+, R\d+, 0x0 ;", sass)
+    if bad:
+        os.remove(so)
+        raise RuntimeError("ptxas dropped a packed-add immediate (%d x '%s'); perturb the source and rebuild" % (len(bad), bad[0]))
 
 
 def build_host(force=False):

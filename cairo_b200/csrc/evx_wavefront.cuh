@@ -44,8 +44,8 @@ struct EvxK3Smem
     int4 idesc[2][EVX_MAXREF];
     int isad[2][EVX_MAXREF + 1];
     EvxMbShared sh;
-    int4 cand[2][16];                         // per candidate: {key1, key1-if-taken, key2, flags}  (sub-pel: {sad, mad, 0, legal})
-    int4 cval[2][16];                         // per candidate: {sad, mad, ssd, 0}
+    int4 cand[2][16];                         // sub-pel tests: {sad, mad, 0, legal}
+    int2 cand2[2][16];                        // full-pel rounds: raw {sad, mad} per cell
     uint64_t full[2], full2[2], empty[2];      // full: everything but the far-right column; full2: that column too
     int done;                                 // macroblocks of this row whose reconstruction is stored
     int row;
@@ -214,9 +214,6 @@ __device__ __forceinline__ void evx_k3_loader(EvxK3Smem &S, const EvxK3Params &p
 
 // ---------------------------------------------------------------- compute warps
 
-// a published candidate: {key1, key2, flags (bit0 legal, bit1 mad < thr), unused}; see evx_make_keys
-__device__ __forceinline__ int4 evx_pack_keys(const EvxKeys &k) { return make_int4((int) k.k1, (int) k.k2, (k.legal ? 1 : 0) | (k.lt ? 2 : 0), 0); }
-
 __device__ __forceinline__ bool evx_intra_legal(int x, int y, int px, int py, const EvxGeom &g)
 {
     return !(y > py - EVX_MB && x > px - EVX_MB) && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);   // motion.cpp:238-248
@@ -251,6 +248,9 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         ccell0[q] = k; cdx0[q] = k % 3 - 1; cdy0[q] = k / 3 - 2;          // round 0: rows -32,-16,0
         ccell[q] = k < 4 ? k : k + 1; cdx[q] = ccell[q] % 3 - 1; cdy[q] = ccell[q] / 3 - 1;
     }
+
+    // selecting side: lane c owns cell c of a round (visiting order j-major, motion.cpp:232-233)
+    const int lc = lane < 9 ? lane : 0, ldx = lc % 3 - 1, ldy = lc / 3;
 
     uint32_t n_full = 0, n_sub = 0;
     int row_records = 0;
@@ -305,53 +305,42 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             // staged window rows, and the ring masks the columns); illegal ones are flagged, not skipped,
             // which keeps the cells of a warp in one basic block.
             {
-                // all of this warp's cells: loads and packed arithmetic first, then every reduction
-                // back to back, so the cells overlap instead of queueing behind each other's REDUX
-                int cx_[EVX_K3_CPW], cy_[EVX_K3_CPW], la[EVX_K3_CPW], lm[EVX_K3_CPW];
+                // this warp's cells: loads and packed arithmetic first, then every reduction back to back;
+                // only the raw (sad, mad) pair is published -- keys are built by the selecting lanes
+                int la[EVX_K3_CPW], lm[EVX_K3_CPW];
 #pragma unroll
                 for (int q = 0; q < EVX_K3_CPW; ++q)
                 {
-                    cx_[q] = s.bx + (round == 0 ? cdx0[q] : cdx[q]) * step;
-                    cy_[q] = s.by + (round == 0 ? cdy0[q] : cdy[q]) * step;
+                    const int x = s.bx + (round == 0 ? cdx0[q] : cdx[q]) * step;
+                    const int y = s.by + (round == 0 ? cdy0[q] : cdy[q]) * step;
                     EvxLaneBlock ref;
-                    evx_load_block_ring_bf(win, cx_[q], cy_[q], lane, ref);
+                    evx_load_block_ring_bf(win, x, y, lane, ref);
                     la[q] = evx_block_sad_lane(ref, src);
                     lm[q] = evx_block_mad_lane(ref, src);
                 }
-                int sad[EVX_K3_CPW], mad[EVX_K3_CPW];
-#pragma unroll
-                for (int q = 0; q < EVX_K3_CPW; ++q) { sad[q] = __reduce_add_sync(0xFFFFFFFFu, la[q]); mad[q] = __reduce_max_sync(0xFFFFFFFFu, lm[q]); }
 #pragma unroll
                 for (int q = 0; q < EVX_K3_CPW; ++q)
                 {
-                    const int cell = round == 0 ? ccell0[q] : ccell[q];
-                    const int x = cx_[q], y = cy_[q];
-                    const int ssd = (x - px) * (x - px) + (y - py) * (y - py);
-                    const int4 res = evx_pack_keys(evx_make_keys(sad[q], mad[q], ssd, thr, evx_intra_legal(x, y, px, py, g)));
-                    if (lane == 0) { S.cand[buf][cell] = res; S.cval[buf][cell] = make_int4(sad[q], mad[q], ssd, 0); }
+                    const int sad = __reduce_add_sync(0xFFFFFFFFu, la[q]), mad = __reduce_max_sync(0xFFFFFFFFu, lm[q]);
+                    if (lane == 0) S.cand2[buf][round == 0 ? ccell0[q] : ccell[q]] = make_int2(sad, mad);
                 }
             }
-            if (warp == 0 && lane == 0)
-            {
-                if (round == 0) S.cand[buf][8] = make_int4(0, 0, 0, 0);
-                else
-                {
-                    S.cand[buf][4] = evx_pack_keys(evx_make_keys(s.sad, s.mad, s.ssd, thr, s.bx != px || s.by != py));
-                    S.cval[buf][4] = make_int4(s.sad, s.mad, s.ssd, 0);
-                }
-            }
+            // selecting side, lane c = cell c in visiting order: everything that does not depend on the
+            // published costs (position, legality, distance) is computed before the barrier
+            const int cxl = s.bx + ldx * step, cyl = s.by + (top + ldy) * step;
+            const int ssdl = (cxl - px) * (cxl - px) + (cyl - py) * (cyl - py);
+            const bool from_state = round != 0 && lane == 4;            // the centre is the running best itself
+            const bool legall = lane < 9 && evx_intra_legal(cxl, cyl, px, py, g) && !(round == 0 && lane == 8);
             evx_compute_sync();
-            // acceptance in closed form (evx_select_fullpel), lane c = cell c in visiting order
             {
-                const int4 v = lane < 9 ? S.cand[buf][lane] : make_int4(0, 0, 0, 0);
-                EvxKeys k;
-                k.k1 = (uint32_t) v.x; k.k2 = (uint32_t) v.y; k.legal = (v.z & 1) != 0; k.lt = (v.z & 2) != 0;
-                const int wcell = evx_select_fullpel(s, k, lane, thr, n_full);
+                int2 v = S.cand2[buf][lc];
+                if (from_state) v = make_int2(s.sad, s.mad);
+                const int wcell = evx_select_fullpel(s, evx_make_keys(v.x, v.y, ssdl, thr, legall), lane, thr, n_full);
                 if (wcell >= 0)
                 {
-                    const int4 val = S.cval[buf][wcell];
-                    s.bx += (wcell % 3 - 1) * step; s.by += (top + wcell / 3) * step;
-                    s.sad = val.x; s.mad = val.y; s.ssd = val.z;
+                    s.bx = __shfl_sync(0xFFFFFFFFu, cxl, wcell); s.by = __shfl_sync(0xFFFFFFFFu, cyl, wcell);
+                    s.sad = __shfl_sync(0xFFFFFFFFu, v.x, wcell); s.mad = __shfl_sync(0xFFFFFFFFu, v.y, wcell);
+                    s.ssd = __shfl_sync(0xFFFFFFFFu, ssdl, wcell);
                 }
             }
             buf ^= 1;

@@ -37,6 +37,14 @@ def test_host_library_exports_every_declared_symbol():
         assert hasattr(lib, name), name
 
 
+def test_shipped_sass_has_no_dropped_packed_add_immediate():
+    """build.lint_sass: the ptxas miscompile of the packed negation (VIADD.16x2 with a zero immediate)
+    must not be present in the library that ships."""
+    from cairo_b200 import build
+    build.build_all()
+    build.lint_sass(build.GPU_SO)
+
+
 def test_no_device_means_loud_failure_not_fallback():
     """Without a GPU the product must refuse to run (status 5), never fall back to the CPU."""
     import torch
