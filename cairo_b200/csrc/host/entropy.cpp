@@ -3,6 +3,7 @@
 
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -77,148 +78,213 @@ struct rev8_table { uint8_t v[256]; rev8_table() { for (int i = 0; i < 256; ++i)
 const rev8_table REV8_T;
 #define REV8 REV8_T.v
 
-class abac_writer
+// Phase 1 of a slice: everything the coder will be fed, as one string of bins (bit i of the
+// string = the i-th call of the reference's encode_symbol).  Binarisation is independent per
+// syntax element, so it is a handful of shifts per CODE instead of a coder step per bin.
+class bin_string
 {
-    uint32_t low_, high_, e3_, h0_, tot_;
-    uint64_t acc_;
-    uint32_t nacc_;
-    uint8_t *out_;
+    std::vector<uint64_t> &w_;
     size_t pos_;
-    const uint64_t *recip_;
-    size_t recip_size_;
-
-    inline void flush_acc() { memcpy(out_ + pos_, &acc_, 8); pos_ += 8; acc_ = 0; nacc_ = 0; }
-    inline void put(uint32_t bit)
-    {
-        acc_ |= (uint64_t) bit << nacc_;
-        if (++nacc_ == 64) flush_acc();
-    }
-    // n <= 16 bits, value's bit (n-1) goes out first (the stream is LSB-first, so reverse them)
-    inline void put_msb_first(uint32_t value, uint32_t n)
-    {
-        for (uint32_t i = n; i-- > 0;) put((value >> i) & 1u);
-    }
-    inline void emit(uint32_t bit)        // write_bit + flush_inverse_bits, abac.cpp:156-178
-    {
-        put(bit);
-        for (; e3_; --e3_) put(bit ^ 1u);
-    }
+    uint64_t acc_;
+    uint32_t n_;
 
 public:
-    explicit abac_writer(uint8_t *out) : low_(0), high_(AB_MAX), e3_(0), h0_(1), tot_(2), acc_(0), nacc_(0), out_(out), pos_(0)
+    explicit bin_string(std::vector<uint64_t> &words) : w_(words), pos_(0), acc_(0), n_(0) {}
+
+    // room for at least `bins` more bins
+    inline void reserve(size_t bins)
     {
-        recip_ = recips().data();
-        recip_size_ = recips().size();
+        const size_t need = pos_ + (bins >> 6) + 3;
+        if (need > w_.size()) w_.resize(need * 2);
     }
-
-    size_t bytes_pending() const { return pos_ + 8; }
-    void rebase(uint8_t *out) { out_ = out; }
-
-    // encode_symbol + resolve_encode_scaling, abac.cpp:97-121, 180-224.
-    // The bin values are close to coin flips for the branch predictor, so the common path is
-    // written without data-dependent branches: the interval update is a pair of selects, the
-    // E1/E2 bits that leave (all leading bits on which low and high agree) are assembled into one
-    // word -- first bit, then the pending E3 bits inverted, then the remaining k-1 bits -- and
-    // OR-ed into the accumulator, and the first E3 step is a select as well.
-    inline void encode(uint32_t bit)
+    // n <= 40 bins, bit 0 of v first
+    inline void put(uint64_t v, uint32_t n)
     {
-        const uint64_t a = (uint64_t) (high_ - low_) * h0_;
-        uint32_t q;
-        if (__builtin_expect(tot_ < recip_size_, 1)) q = (uint32_t) (((unsigned __int128) a * recip_[tot_]) >> 64);
-        else
+        acc_ |= v << n_;
+        if (n_ + n >= 64)
         {
-            if (tot_ < (size_t(1) << 24)) { recips().grow((size_t) tot_ * 2); recip_size_ = recips().size(); }
-            q = (uint32_t) (a / tot_);
+            w_[pos_++] = acc_;
+            acc_ = n_ ? v >> (64 - n_) : 0;
+            n_ = n_ + n - 64;
         }
-        const uint32_t mid = low_ + q;
-        low_ = bit ? mid + 1 : low_;
-        high_ = bit ? high_ : mid;
-        h0_ += bit ^ 1u;
-        tot_++;
-
-        uint32_t k = (uint32_t) __builtin_clz((high_ ^ low_) | 1u) - 16;      // 0..15 common leading bits
-        if (__builtin_expect(e3_ > 40 || nacc_ > 64 - 57 + 0 && nacc_ + k + e3_ > 64 || (high_ == low_), 0))
-        {   // rare: long E3 run, accumulator about to wrap, or a collapsed interval -- bit at a time
-            for (;;)
-            {
-                k = (uint32_t) __builtin_clz((high_ ^ low_) | 1u) - 16;
-                if (!k) break;
-                emit(high_ >> 15);
-                if (k > 1) put_msb_first((high_ >> (16 - k)) & ((1u << (k - 1)) - 1u), k - 1);
-                low_ = (low_ << k) & AB_MAX;
-                high_ = ((high_ << k) & AB_MAX) | ((1u << k) - 1u);
-            }
-        }
-        else
-        {
-            const uint32_t msb = high_ >> 15;
-            const uint32_t km1 = k - (k != 0);
-            const uint32_t rest = (high_ >> (16 - k)) & ((1u << km1) - 1u);                     // k-1 bits, first-out at the top
-            const uint32_t rest_rev = (uint32_t) ((REV8[rest & 0xFF] << 8) | REV8[rest >> 8]) >> (16 - km1);
-            const uint64_t pend = msb ? 0 : ((uint64_t(1) << e3_) - 1);                          // e3 copies of !msb
-            uint64_t v = (uint64_t) msb | (pend << 1) | ((uint64_t) rest_rev << (1 + e3_));
-            const uint32_t len = k ? k + e3_ : 0;
-            v = k ? v : 0;
-            acc_ |= v << nacc_;
-            nacc_ += len;
-            e3_ = k ? 0 : e3_;
-            if (nacc_ >= 64)
-            {   // exactly full (the guard above keeps nacc_ + len <= 64)
-                memcpy(out_ + pos_, &acc_, 8); pos_ += 8; acc_ = 0; nacc_ = 0;
-            }
-            low_ = (low_ << k) & AB_MAX;
-            high_ = ((high_ << k) & AB_MAX) | ((1u << k) - 1u);
-        }
-        // E3: low = 01..., high = 10... (with the reference's 3*QTR = 0xBFFD quirk); MSBs differ here
-        uint32_t c = (low_ > AB_QTR) & (high_ <= AB_3QTR);
-        low_ = c ? ((low_ - (AB_QTR + 1)) << 1) & AB_MAX : low_;
-        high_ = c ? ((((high_ - (AB_QTR + 1)) << 1) & AB_MAX) | 1u) : high_;
-        e3_ += c;
-        while (__builtin_expect(c && low_ > AB_QTR && high_ <= AB_3QTR, 0))
-        {
-            low_ = ((low_ - (AB_QTR + 1)) << 1) & AB_MAX;
-            high_ = (((high_ - (AB_QTR + 1)) << 1) & AB_MAX) | 1u;
-            e3_++;
-        }
+        else n_ += n;
     }
-
-    inline void encode_bits_lsb(uint32_t v, int n) { for (int k = 0; k < n; ++k) encode((v >> k) & 1u); }
-
-    // Exp-Golomb (golomb.cpp:8-91): n-1 zeros, then x MSB-first
-    inline void encode_code(uint32_t x)
+    inline void put_bits_lsb(uint32_t v, int n) { put(v & ((1u << n) - 1u), (uint32_t) n); }
+    // Exp-Golomb (golomb.cpp:8-91): n-1 zeros, then the n bits of x, most significant first
+    inline void put_code(uint32_t x)
     {
-        const int n = bit_length(x);
-        for (int i = 0; i < n - 1; ++i) encode(0);
-        for (int i = n - 1; i >= 0; --i) encode((x >> i) & 1u);
+        const uint32_t n = (uint32_t) bit_length(x);
+        uint32_t r = x;                                   // reverse the low n bits
+        r = ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+        r = ((r >> 2) & 0x33333333u) | ((r & 0x33333333u) << 2);
+        r = ((r >> 4) & 0x0F0F0F0Fu) | ((r & 0x0F0F0F0Fu) << 4);
+        r = __builtin_bswap32(r) >> (32 - n);
+        put((uint64_t) r << (n - 1), 2 * n - 1);
     }
-    inline void encode_unsigned(uint32_t v) { encode_code(v + 1); }
-    inline void encode_signed(int v) { encode_code(v == 0 ? 1u : (((uint32_t) (v < 0 ? -v : v) << 1) | (v < 0 ? 1u : 0u))); }
+    inline void put_unsigned(uint32_t v) { put_code(v + 1); }
+    inline void put_signed(int v) { put_code(v == 0 ? 1u : (((uint32_t) (v < 0 ? -v : v) << 1) | (v < 0 ? 1u : 0u))); }
 
-    // flush_encoder, abac.cpp:281-313.  Returns the total number of bits written.
-    uint64_t finish()
+    size_t finish()
     {
-        e3_++;
-        emit(low_ < AB_QTR ? 0u : 1u);
-        uint64_t bits = (uint64_t) pos_ * 8 + nacc_;
-        memcpy(out_ + pos_, &acc_, 8);
-        return bits;
+        const size_t bins = pos_ * 64 + n_;
+        w_[pos_] = acc_;
+        return bins;
     }
 };
 
 // stream.cpp:550-581 + serialize.cpp:10-23: one 8x8 block of a record
-inline void put_block(abac_writer &w, const int16_t *blk, const uint8_t *zz, int16_t last_dc)
+inline void put_block(bin_string &w, const int16_t *blk, const uint8_t *zz, int16_t last_dc)
 {
     const int16_t dc = (int16_t) (blk[0] - last_dc);
     int run = 63;
     for (; run >= 1; --run) if (blk[zz[run]]) break;
     if (run == 0 && dc == 0) run = -1;
     run++;
-    w.encode_unsigned((uint32_t) run);
+    w.put_unsigned((uint32_t) run);
     if (run > 0)
     {
-        w.encode_signed(dc);
-        for (int k = 1; k < run; ++k) w.encode_signed(blk[zz[k]]);
+        w.put_signed(dc);
+        for (int k = 1; k < run; ++k) w.put_signed(blk[zz[k]]);
     }
+}
+
+// Phase 2: the adaptive binary arithmetic coder over the bin string -- encode_symbol +
+// resolve_encode_scaling (abac.cpp:97-121, 180-224) per bin, flush_encoder (abac.cpp:281-313)
+// at the end.  The coder is one serial dependency chain through (low, high); everything here is
+// about keeping that chain short and free of unpredictable branches (bin values are coin flips
+// for a branch predictor, and one mispredict costs as much as the arithmetic of a whole bin):
+//  * the model's split point floor((high-low) * h0 / tot) is ONE 64-bit multiply on the chain:
+//    F = floor(h0 * 2^48 / tot) + (1..257) is prepared off the chain from the reciprocal table
+//    (h0 and tot depend on the bins only), and ((high-low) * F) >> 48 equals the exact quotient
+//    for tot < 2^23 (the excess of F adds less than 1/tot to a value whose fractional part is
+//    at most 1 - 1/tot) -- profiles/abac_bench.cpp checks this identity exhaustively per tot;
+//  * interval update and the first E3 step are selects written as masks;
+//  * all leading bits on which low and high agree leave at once (E1/E2): with k such bits,
+//    T = the top k bits of high and e3 pending bits, the bits that leave are, most significant
+//    first, T + ((2^e3 - 1) << (k-1)) in k + e3 bits (first bit, e3 inverted copies, the
+//    other k-1 bits).  They are shifted into a most-significant-first accumulator that is
+//    stored every bin and advanced by whole bytes -- no "accumulator full" branch; one pass at
+//    the end turns each byte around, because the stream is least-significant-bit first.
+// Rare cases (collapsed interval, a long run of pending E3 bits, tot >= 2^23) take the
+// bit-at-a-time path.  Returns the number of bits written to out.
+// (built twice: a portable clone and one for BMI2/LZCNT machines, whose three-operand shifts
+// and leading-zero count shave a fifth off the instruction count; picked at load time)
+__attribute__((noinline, target_clones("default", "arch=haswell")))
+uint64_t abac_encode_bins(const uint64_t *bins, size_t nbins, std::vector<uint8_t> &outv)
+{
+    uint64_t low = 0, high = AB_MAX, h0 = 1, tot = 2;
+    uint64_t e3 = 0;
+    uint64_t acc = 0;                                   // the low nacc bits are pending output, oldest on top
+    uint64_t nacc = 0;                                  // < 8 between bins
+    if (outv.size() < 4096) outv.resize(4096);
+    uint8_t *wp = outv.data();                          // next output byte
+
+    reciprocal_table &rt = recips();
+    const size_t kFastTot = size_t(1) << 23;
+    if (rt.size() < std::min(nbins + 4, kFastTot)) rt.grow(std::min(nbins + 4, kFastTot));
+    const uint64_t *recip = rt.data();
+    const uint64_t fast_limit = std::min<uint64_t>(rt.size(), kFastTot);
+
+#define EVX_DRAIN() do { const uint64_t top_ = __builtin_bswap64(acc << ((64 - nacc) & 63)); memcpy(wp, &top_, 8); wp += nacc >> 3; nacc &= 7; } while (0)
+#define EVX_PUT(b) do { acc = (acc << 1) | (uint64_t) (b); ++nacc; EVX_DRAIN(); } while (0)
+#define EVX_GROW(need) do { const size_t pos_ = (size_t) (wp - outv.data()); if (pos_ + (need) > outv.size()) { outv.resize((pos_ + (need)) * 2); wp = outv.data() + pos_; } } while (0)
+    // E1/E2 one bit at a time, as the reference does it (write_bit + flush_inverse_bits, abac.cpp:156-178)
+#define EVX_RENORM_SLOW() \
+    for (;;) \
+    { \
+        uint64_t b_; \
+        if (high <= AB_HALF) b_ = 0; \
+        else if (low > AB_HALF) { b_ = 1; low -= AB_HALF + 1; high -= AB_HALF + 1; } \
+        else break; \
+        EVX_GROW(64 + (e3 >> 3)); \
+        EVX_PUT(b_); \
+        for (; e3; --e3) EVX_PUT(b_ ^ 1u); \
+        low = (low << 1) & AB_MAX; \
+        high = ((high << 1) & AB_MAX) | 1u; \
+    }
+    // E3: low = 01..., high = 10... (with the reference's 3*QTR = 0xBFFD quirk); the MSBs differ here.
+    // One step maps low -> 2*low - 0x8000, high -> 2*high - 0x7FFF.
+#define EVX_E3() \
+    do { \
+        const uint64_t c_ = (uint64_t) (low > AB_QTR) & (uint64_t) (high <= AB_3QTR), cm_ = 0 - c_; \
+        low += (low - 0x8000u) & cm_; \
+        high += (high - 0x7FFFu) & cm_; \
+        e3 += c_; \
+        while (__builtin_expect(c_ && low > AB_QTR && high <= AB_3QTR, 0)) { low = 2 * low - 0x8000u; high = 2 * high - 0x7FFFu; e3++; } \
+    } while (0)
+
+    size_t base = 0;
+    for (; base < nbins && tot + 64 <= fast_limit; base += 64)
+    {
+        uint64_t word = bins[base >> 6];
+        const int cnt = nbins - base < 64 ? (int) (nbins - base) : 64;
+        // a bin leaves at most 16 E1/E2 bits plus the E3 bits pending before it (one per earlier step)
+        EVX_GROW((size_t) 64 * 4 + (e3 >> 3) + 64);
+        for (int j = 0; j < cnt; ++j, word >>= 1)
+        {
+            const uint64_t bm = 0 - (word & 1u);
+            const uint64_t F = (uint64_t) (((unsigned __int128) h0 * recip[tot]) >> 16) + 1;
+            const uint64_t q = ((high - low) * F) >> 48;
+            const uint64_t mid = low + q;
+            low += (q + 1) & bm;                      // bit ? mid + 1 : low
+            high = (high & bm) | (mid & ~bm);         // bit ? high : mid
+            h0 += 1 + bm;                             // counts the zeros
+            tot++;
+
+            // k = number of leading bits low and high share (16 = collapsed interval)
+            const uint64_t k = (uint64_t) __builtin_clz((uint32_t) (((low ^ high) << 16) + 0x8000u));
+            if (__builtin_expect((k == 16) | (e3 > 40), 0)) EVX_RENORM_SLOW()
+            else
+            {
+                const uint64_t nzm = 0 - ((k + 15) >> 4);                           // any bit leaving? (k <= 15 here)
+                const uint64_t e3f = e3 & nzm;                                      // pending bits leave with the first one
+                const uint64_t v = (high >> (16 - k)) + ((((uint64_t(1) << e3f) - 1) << k) >> 1);
+                const uint64_t len = k + e3f;
+                acc = (acc << len) | v;              // nacc <= 7, len <= 15 + 40
+                nacc += len;
+                e3 -= e3f;
+                EVX_DRAIN();
+                low = (low << k) & AB_MAX;
+                high = ((high << k) & AB_MAX) | ((uint64_t(1) << k) - 1u);
+            }
+            EVX_E3();
+        }
+    }
+    // beyond the reciprocal table (slices of more than 8M bins): the plain form
+    for (; base < nbins; base += 64)
+    {
+        uint64_t word = bins[base >> 6];
+        const int cnt = nbins - base < 64 ? (int) (nbins - base) : 64;
+        for (int j = 0; j < cnt; ++j, word >>= 1)
+        {
+            const uint64_t bit = word & 1u;
+            const uint64_t mid = low + ((high - low) * h0) / tot;
+            if (bit) low = mid + 1; else { high = mid; h0++; }
+            tot++;
+            EVX_RENORM_SLOW()
+            EVX_E3();
+        }
+    }
+    // flush_encoder: one more pending bit, then the quarter the interval sits in
+    EVX_GROW((e3 >> 3) + 64);
+    e3++;
+    {
+        const uint64_t b = low < AB_QTR ? 0u : 1u;
+        EVX_PUT(b);
+        for (; e3; --e3) EVX_PUT(b ^ 1u);
+    }
+    uint8_t *out = outv.data();
+    const uint64_t bits = (uint64_t) (wp - out) * 8 + nacc;
+    { const uint64_t top_ = __builtin_bswap64(acc << ((64 - nacc) & 63)); memcpy(wp, &top_, 8); if (!nacc) *wp = 0; }
+#undef EVX_DRAIN
+#undef EVX_PUT
+#undef EVX_GROW
+#undef EVX_RENORM_SLOW
+#undef EVX_E3
+    // the stream is least-significant-bit first within a byte
+    const size_t nbytes = (size_t) ((bits + 7) >> 3);
+    for (size_t i = 0; i < nbytes; ++i) out[i] = REV8[out[i]];
+    return bits;
 }
 
 }  // namespace
@@ -228,8 +294,8 @@ void slice_writer::configure(int mbw, int mbh, int ref_count)
     mbw_ = mbw; mbh_ = mbh;
     target_bits_ = bit_length((uint32_t) (ref_count & 0xFF)) - 1;     // log2((uint8) R), serialize.cpp:179
     dc_.resize((size_t) mbw * mbh);
-    // worst case: every coefficient an escape-length code; grown on demand below
-    buf_.assign((size_t) mbw * mbh * 384 * 5 + 4096, 0);
+    bins_.assign((size_t) mbw * mbh * 8 + 1024, 0);                   // grown on demand
+    buf_.assign((size_t) mbw * mbh * 64 + 4096, 0);
 }
 
 void slice_writer::reset() { dc_.resize((size_t) mbw_ * mbh_); }
@@ -237,10 +303,9 @@ void slice_writer::reset() { dc_.resize((size_t) mbw_ * mbh_); }
 uint32_t slice_writer::serialize(const evxgpu_block_desc *t, const int16_t *records, uint32_t n_noncopy)
 {
     const int n = mbw_ * mbh_;
-    abac_writer w(buf_.data());
     static const bool prof = getenv("EVX_ENTROPY_PROFILE") != NULL;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double tp0 = prof ? now() : 0, tp1 = 0, tp2 = 0;
+    const double tp0 = prof ? now() : 0;
 
     // refresh the DC mirror with this frame's non-copy macroblocks (serialisation reads the
     // coefficient planes AFTER the whole slice was encoded, encode.cpp:214-220)
@@ -256,21 +321,21 @@ uint32_t slice_writer::serialize(const evxgpu_block_desc *t, const int16_t *reco
         if (k != n_noncopy) return 0;
     }
 
-    if (prof) tp1 = now();
+    bin_string w(bins_);
+    w.reserve((size_t) n * 160);
     // block table by field, serialize.cpp:156-317
-    for (int i = 0; i < n; ++i) w.encode_bits_lsb((uint32_t) t[i].block_type, 3);
-    for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_INTRA)) w.encode_bits_lsb(t[i].prediction_target, target_bits_);
+    for (int i = 0; i < n; ++i) w.put_bits_lsb((uint32_t) t[i].block_type, 3);
+    for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_INTRA)) w.put_bits_lsb(t[i].prediction_target, target_bits_);
     int last = 0;
-    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) { w.encode_signed((int16_t) (t[i].motion_x - last)); last = t[i].motion_x; }
+    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) { w.put_signed((int16_t) (t[i].motion_x - last)); last = t[i].motion_x; }
     last = 0;
-    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) { w.encode_signed((int16_t) (t[i].motion_y - last)); last = t[i].motion_y; }
-    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) w.encode(t[i].sp_pred & 1u);
-    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) w.encode(t[i].sp_amount & 1u);
-    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) w.encode_bits_lsb(t[i].sp_index, 3);
+    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) { w.put_signed((int16_t) (t[i].motion_y - last)); last = t[i].motion_y; }
+    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) w.put(t[i].sp_pred & 1u, 1);
+    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) w.put(t[i].sp_amount & 1u, 1);
+    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) w.put_bits_lsb(t[i].sp_index, 3);
     last = 0;
-    for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_COPY)) { w.encode_signed((int16_t) (t[i].q_index - last)); last = t[i].q_index; }
+    for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_COPY)) { w.put_signed((int16_t) (t[i].q_index - last)); last = t[i].q_index; }
 
-    if (prof) tp2 = now();
     // residuals: all luma, then all U, then all V (serialize.cpp:125-154)
     for (int comp = 0; comp < 3; ++comp)
     {
@@ -281,6 +346,7 @@ uint32_t slice_writer::serialize(const evxgpu_block_desc *t, const int16_t *reco
         {
             if (t[idx].block_type & T_COPY) continue;
             const int16_t *r = records + (size_t) (k++) * 384;
+            w.reserve(384 * 40);
             if (comp == 0)
             {
                 int16_t last_dc = bx >= 1 ? dc_.y_tr[idx - 1] : (by >= 1 ? dc_.y_bl[idx - mbw_] : 0);
@@ -295,11 +361,12 @@ uint32_t slice_writer::serialize(const evxgpu_block_desc *t, const int16_t *reco
                 int16_t last_dc = bx >= 1 ? m[idx - 1] : (by >= 1 ? m[idx - mbw_] : 0);
                 put_block(w, r + 256 + (comp - 1) * 64, ZZ.pos, last_dc);
             }
-            if (w.bytes_pending() + 8192 > buf_.size()) { buf_.resize(buf_.size() * 2); w.rebase(buf_.data()); }
         }
     }
-    uint32_t total_bits = (uint32_t) w.finish();
-    if (prof) fprintf(stderr, "[entropy] mirror %.3f ms, table %.3f ms, residuals %.3f ms, %u bits\n", tp1 - tp0, tp2 - tp1, now() - tp2, total_bits);
+    const size_t nbins = w.finish();
+    const double tp1 = prof ? now() : 0;
+    const uint32_t total_bits = (uint32_t) abac_encode_bins(bins_.data(), nbins, buf_);
+    if (prof) fprintf(stderr, "[entropy] binarise %.3f ms (%zu bins), coder %.3f ms, %u bits\n", tp1 - tp0, nbins, now() - tp1, total_bits);
     return total_bits;
 }
 

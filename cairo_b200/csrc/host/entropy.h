@@ -27,7 +27,8 @@ class slice_writer
 {
     int mbw_, mbh_, target_bits_;
     dc_mirror dc_;
-    std::vector<uint8_t> buf_;
+    std::vector<uint64_t> bins_;    // the slice as a string of bins (phase 1)
+    std::vector<uint8_t> buf_;      // the coded bits (phase 2)
 
 public:
     void configure(int mbw, int mbh, int ref_count);

@@ -2,6 +2,8 @@
 reference: the writer must reproduce the reference's bits from the reference's block table and
 coefficients, the reader must invert them -- including the stale-DC semantics across frames
 (SURVEY H4).  No GPU needed."""
+import os
+
 import numpy as np
 import pytest
 
@@ -73,3 +75,16 @@ def test_empty_frame_all_copy_blocks():
     d, b = wr.serialize(tbl, np.zeros((0, 384), np.int16))
     t2, r2 = rd.unserialize(d, b)
     assert (t2["block_type"] == 4).all() and r2.shape[0] == 0
+
+
+def test_fast_coder_against_plain_coder(tmp_path):
+    """profiles/abac_bench.cpp `check`: the production arithmetic-coder loop (reciprocal split point,
+    batched E1/E2, byte-drained accumulator, >8M-bin tail) against a bit-at-a-time coder written from the
+    algorithm, over skewed/bursty bin strings; and the split-point identity for every tot < 2^23."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "abac_bench")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", os.path.join(root, "include"), "-I", os.path.join(root, "cairo_b200", "csrc", "host"),
+                           "-o", exe, os.path.join(root, "profiles", "abac_bench.cpp"), "-lpthread"])
+    out = subprocess.run([exe, "check"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "all ok" in out.stdout, out.stdout[-2000:]
