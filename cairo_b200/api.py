@@ -31,7 +31,7 @@ def lib():
     L.evx1c_encoder_insert_intra.argtypes = [vp]
     L.evx1c_encoder_set_quality.argtypes = [vp, i32]
     L.evx1c_encoder_encode.argtypes = [vp, vp, u32, u32, vp, u32, C.POINTER(u32)]
-    L.evx1c_encoder_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u32), C.POINTER(u32)]
+    L.evx1c_encoder_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     L.evx1c_decoder_create.restype = vp
     L.evx1c_decoder_create.argtypes = [i32] * 3
     L.evx1c_decoder_destroy.argtypes = [vp]
@@ -41,6 +41,7 @@ def lib():
     L.evx1c_slice_writer_create.argtypes = [i32] * 3
     L.evx1c_slice_writer_destroy.argtypes = [vp]
     L.evx1c_slice_writer_serialize.argtypes = [vp, vp, vp, u32, vp, u32, C.POINTER(u32)]
+    L.evx1c_slice_writer_serialize_bins.argtypes = [vp, vp, C.c_uint64, vp, u32, C.POINTER(u32)]
     L.evx1c_slice_reader_create.restype = vp
     L.evx1c_slice_reader_create.argtypes = [i32] * 3
     L.evx1c_slice_reader_destroy.argtypes = [vp]
@@ -96,9 +97,9 @@ class evx1_encoder:
         return self._out[:(bits.value + 7) // 8], bits.value
 
     def stats(self):
-        g, e, b, n = C.c_double(0), C.c_double(0), C.c_uint32(0), C.c_uint32(0)
-        self.L.evx1c_encoder_stats(self.h, C.byref(g), C.byref(e), C.byref(b), C.byref(n))
-        return {"gpu_ms": g.value, "entropy_ms": e.value, "slice_bits": b.value, "noncopy_blocks": n.value}
+        g, e, b, n, d = C.c_double(0), C.c_double(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        self.L.evx1c_encoder_stats(self.h, C.byref(g), C.byref(e), C.byref(b), C.byref(n), C.byref(d))
+        return {"gpu_ms": g.value, "entropy_ms": e.value, "slice_bits": b.value, "noncopy_blocks": n.value, "d2h_bytes": d.value}
 
 
 class evx1_decoder:
@@ -146,6 +147,17 @@ class SliceWriter:
             self._out = np.zeros(cap, dtype=np.uint8)
         bits = C.c_uint32(0)
         st = self.L.evx1c_slice_writer_serialize(self.h, _p(table), _p(records), records.shape[0], _p(self._out), cap, C.byref(bits))
+        assert st == 0, st
+        return self._out[:(bits.value + 7) // 8].copy(), bits.value
+
+
+    def serialize_bins(self, words, nbins):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        cap = self.n * 384 * 5 + 4096
+        if getattr(self, "_out", None) is None:
+            self._out = np.zeros(cap, dtype=np.uint8)
+        bits = C.c_uint32(0)
+        st = self.L.evx1c_slice_writer_serialize_bins(self.h, _p(words), nbins, _p(self._out), cap, C.byref(bits))
         assert st == 0, st
         return self._out[:(bits.value + 7) // 8].copy(), bits.value
 

@@ -18,6 +18,7 @@
 #include "../../include/evxgpu.h"
 #include "evx_kernels.cuh"
 #include "evx_wavefront.cuh"
+#include "evx_bins.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -79,6 +80,18 @@ struct evxgpu_handle
     bool pending_encode, pending_decode;
     int wave_grid;
     long long *d_prof;
+
+    // K8: the slice as a bin string (evx_bins.cuh)
+    int out_mode;                   // 0 table+records, 1 bins, 2 both
+    int16_t *d_dc;                  // persistent DC mirror [4][nmb]
+    int *d_prev;                    // prev_motion[nmb], prev_coded[nmb]
+    uint32_t *d_len, *d_tile_sum, *d_bins, *d_bins_total;
+    uint32_t bins_cap_bits;         // capacity of d_bins
+    uint32_t *h_bins;               // pinned: [0..3] total, overflow, non-copy count; [4..] the string
+    uint32_t h_bins_cap_bits;
+    uint32_t bins_prefix_bits;      // how much of the string the submit already copied
+    cudaEvent_t ev_out;
+    bool pending_bins;
 };
 
 static size_t plane_elems(const EvxGeom &g) { return (size_t) g.w * g.h * 3 / 2; }
@@ -126,6 +139,9 @@ int evxgpu_destroy(evxgpu_handle *h)
     for (int i = 0; i < 8; ++i) cudaFree(h->ring_mem[i]);
     cudaFree(h->d_rgb); cudaFree(h->d_table); cudaFree(h->d_inter); cudaFree(h->d_records); cudaFree(h->d_dense); cudaFree(h->d_row_records);
     cudaFree(h->d_record_slot); cudaFree(h->d_sync); cudaFree(h->d_done); cudaFree(h->d_counters); cudaFree(h->d_prof);
+    cudaFree(h->d_dc); cudaFree(h->d_prev); cudaFree(h->d_len); cudaFree(h->d_tile_sum); cudaFree(h->d_bins); cudaFree(h->d_bins_total);
+    cudaFreeHost(h->h_bins);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     cudaFreeHost(h->h_table); cudaFreeHost(h->h_records); cudaFreeHost(h->h_record_slot); cudaFreeHost(h->h_sync); cudaFreeHost(h->h_rgb);
     for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[k][e]) cudaEventDestroy(h->ev[k][e]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -173,6 +189,19 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     ok = ok && cudaMalloc(&h->d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_done, (size_t) h->nmb * 8) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_counters, 32) == cudaSuccess;
+    {   // K8 (bin string): 256 bins per macroblock to start with (a 1080p intra frame needs ~45); grown on demand
+        const size_t ntiles = ((size_t) EVX_BINS_ITEMS * h->nmb + EVX_BINS_TILE - 1) / EVX_BINS_TILE;
+        h->bins_cap_bits = (uint32_t) std::max<size_t>((size_t) h->nmb * 256, 1u << 16);
+        h->h_bins_cap_bits = h->bins_cap_bits;
+        ok = ok && cudaMalloc(&h->d_dc, (size_t) h->nmb * 4 * 2) == cudaSuccess;
+        ok = ok && cudaMalloc(&h->d_prev, (size_t) h->nmb * 2 * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&h->d_len, (size_t) EVX_BINS_ITEMS * h->nmb * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&h->d_tile_sum, ntiles * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&h->d_bins, (size_t) h->bins_cap_bits / 8 + 8) == cudaSuccess;
+        ok = ok && cudaMalloc(&h->d_bins_total, 16) == cudaSuccess;
+        ok = ok && cudaHostAlloc(&h->h_bins, (size_t) h->h_bins_cap_bits / 8 + 32, cudaHostAllocDefault) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) == cudaSuccess;
+    }
     ok = ok && cudaHostAlloc(&h->h_table, (size_t) h->nmb * 16, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&h->h_records, (size_t) h->nmb * 384 * 2, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&h->h_record_slot, (size_t) h->nmb * 4, cudaHostAllocDefault) == cudaSuccess;
@@ -223,8 +252,9 @@ int evxgpu_reset(evxgpu_handle *h)
     for (int i = 0; i < h->cfg.ref_count; ++i) CK(cudaMemsetAsync(h->ring_mem[i], 0, pe * 2, h->stream));
     CK(cudaMemsetAsync(h->d_table, 0, (size_t) h->nmb * 16, h->stream));
     CK(cudaMemsetAsync(h->d_counters, 0, 32, h->stream));
+    CK(cudaMemsetAsync(h->d_dc, 0, (size_t) h->nmb * 4 * 2, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->pending_encode = h->pending_decode = false;
+    h->pending_encode = h->pending_decode = h->pending_bins = false;
     return 0;
 }
 
@@ -325,9 +355,13 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
     t_begin(h, EVXGPU_T_WAVEFRONT);
     // one CTA per macroblock row; rows are claimed by ticket, so any residency is deadlock-free
     evx_wavefront<<<h->g.mbh, EVX_K3_NT, sizeof(EvxK3Smem), h->stream>>>(p);
-    evx_pack_records<<<h->g.mbh, 256, 0, h->stream>>>(h->d_table, h->d_records, h->d_row_records, h->d_dense, h->d_sync + 1, h->g);
+    h->launches++;
+    if (h->out_mode != 1)
+    {
+        evx_pack_records<<<h->g.mbh, 256, 0, h->stream>>>(h->d_table, h->d_records, h->d_row_records, h->d_dense, h->d_sync + 1, h->g);
+        h->launches++;
+    }
     t_end(h, EVXGPU_T_WAVEFRONT);
-    h->launches += 2;
     CK(cudaGetLastError());
     return 0;
 }
@@ -346,7 +380,48 @@ static int launch_deblock(evxgpu_handle *h, uint32_t index)
     return 0;
 }
 
+static EvxBinsParams bins_params(evxgpu_handle *h)
+{
+    EvxBinsParams p;
+    p.table = h->d_table; p.records = h->d_records; p.dc = h->d_dc;
+    p.prev_motion = h->d_prev; p.prev_coded = h->d_prev + h->nmb;
+    p.len = h->d_len; p.tile_sum = h->d_tile_sum; p.bins = h->d_bins; p.total = h->d_bins_total;
+    p.cap_bits = h->bins_cap_bits;
+    p.mbw = h->g.mbw; p.mbh = h->g.mbh; p.nmb = h->nmb;
+    int tb = 0;
+    for (int r = h->cfg.ref_count & 0xFF; r > 1; r >>= 1) ++tb;       // log2((uint8) R), serialize.cpp:179
+    p.target_bits = tb;
+    return p;
+}
+
+static int launch_bins(evxgpu_handle *h, bool emit_only)
+{
+    const EvxBinsParams p = bins_params(h);
+    const int ntiles = (EVX_BINS_ITEMS * h->nmb + EVX_BINS_TILE - 1) / EVX_BINS_TILE;
+    CK(cudaMemsetAsync(h->d_bins, 0, (size_t) h->bins_cap_bits / 8 + 8, h->stream));
+    t_begin(h, EVXGPU_T_BINS);
+    if (!emit_only)
+    {
+        evx_bins_prepare<<<1, 1024, 0, h->stream>>>(p);
+        evx_bins_lengths<<<ntiles, EVX_BINS_TILE, 0, h->stream>>>(p);
+        h->launches += 2;
+    }
+    evx_bins_emit<<<ntiles, EVX_BINS_TILE, 0, h->stream>>>(p);
+    t_end(h, EVXGPU_T_BINS);
+    h->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 // ------------------------------------------------------------------ encoder
+
+int evxgpu_set_output(evxgpu_handle *h, int mode)
+{
+    if (!h || mode < 0 || mode > 2) return fail(1, "evxgpu_set_output: bad argument");
+    if (h->pending_encode) return fail(8, "evxgpu_set_output: a frame is in flight");
+    h->out_mode = mode;
+    return 0;
+}
 
 int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device, int frame_type, uint32_t frame_index, int quality)
 {
@@ -363,11 +438,65 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     if ((rc = launch_convert_in(h, d_rgb))) return rc;
     if (frame_type == 1 && (rc = launch_inter_search(h, frame_index, quality))) return rc;
     if ((rc = launch_wavefront(h, frame_type, frame_index, quality))) return rc;
-    // the records leave before deblocking so the copy overlaps it
-    CK(cudaMemcpyAsync(h->h_sync, h->d_sync, 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_table, h->d_table, (size_t) h->nmb * 16, cudaMemcpyDeviceToHost, h->stream));
+    // the results leave before deblocking so the copies (and the host's entropy stage) overlap it
+    if (h->out_mode != 1)
+    {
+        CK(cudaMemcpyAsync(h->h_sync, h->d_sync, 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_table, h->d_table, (size_t) h->nmb * 16, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (h->out_mode != 0)
+    {
+        if ((rc = launch_bins(h, false))) return rc;
+        // the bin count and, optimistically, the head of the string in the same breath
+        h->bins_prefix_bits = std::min<uint32_t>(std::min(h->bins_cap_bits, h->h_bins_cap_bits), 1u << 19);
+        CK(cudaMemcpyAsync(h->h_bins, h->d_bins_total, 16, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_bins + 4, h->d_bins, h->bins_prefix_bits / 8, cudaMemcpyDeviceToHost, h->stream));
+        h->pending_bins = true;
+    }
+    CK(cudaEventRecord(h->ev_out, h->stream));
     if ((rc = launch_deblock(h, frame_index))) return rc;
     h->pending_encode = true;
+    return 0;
+}
+
+int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins_out, uint64_t *nbins, uint32_t *n_noncopy)
+{
+    if (!h || !bins_out || !nbins) return fail(1, "evxgpu_encode_collect_bins: bad argument");
+    if (!h->pending_encode || !h->pending_bins) return fail(15, "evxgpu_encode_collect_bins: no frame submitted with bin output enabled (evxgpu_set_output)");
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventSynchronize(h->ev_out));
+    const uint32_t total = h->h_bins[0], coded = h->h_bins[2];
+    if (h->h_bins[1])
+    {   // the string outgrew the device buffer: enlarge it and emit again (lengths and tile sums stand)
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFree(h->d_bins); h->d_bins = NULL;
+        const uint64_t want = ((uint64_t) total + total / 2 + 4096) & ~63ull;
+        if (want > 0xFFFFFFFFull) return fail(3, "evxgpu_encode_collect_bins: slice of more than 2^32 bins");
+        h->bins_cap_bits = (uint32_t) want;
+        if (cudaMalloc(&h->d_bins, (size_t) h->bins_cap_bits / 8 + 8) != cudaSuccess) return fail(3, "evxgpu_encode_collect_bins: out of device memory");
+        int rc = launch_bins(h, true);
+        if (rc) return rc;
+        h->bins_prefix_bits = 0;
+    }
+    if (total > h->h_bins_cap_bits)
+    {
+        CK(cudaStreamSynchronize(h->stream));
+        cudaFreeHost(h->h_bins); h->h_bins = NULL;
+        h->h_bins_cap_bits = (uint32_t) std::min<uint64_t>(((uint64_t) total + total / 2 + 4096) & ~63ull, 0xFFFFFFC0ull);
+        if (cudaHostAlloc(&h->h_bins, (size_t) h->h_bins_cap_bits / 8 + 32, cudaHostAllocDefault) != cudaSuccess) return fail(3, "evxgpu_encode_collect_bins: out of pinned memory");
+        h->bins_prefix_bits = 0;
+    }
+    if (total > h->bins_prefix_bits)
+    {   // the tail (or everything, after a re-emit)
+        const size_t from = h->bins_prefix_bits / 8, to = ((size_t) total + 7) / 8;
+        CK(cudaMemcpyAsync((uint8_t *) (h->h_bins + 4) + from, (const uint8_t *) h->d_bins + from, to - from, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    h->pending_bins = false;
+    if (h->out_mode == 1) h->pending_encode = false;
+    *bins_out = reinterpret_cast<const uint64_t *>(h->h_bins + 4);
+    *nbins = total;
+    if (n_noncopy) *n_noncopy = coded;
     return 0;
 }
 
@@ -375,6 +504,7 @@ int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_
 {
     if (!h || !table_out || !n_noncopy) return fail(1, "evxgpu_encode_collect: bad argument");
     if (!h->pending_encode) return fail(15, "evxgpu_encode_collect: nothing submitted");
+    if (h->out_mode == 1) return fail(15, "evxgpu_encode_collect: the handle outputs bins only (evxgpu_set_output)");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     h->pending_encode = false;
@@ -497,6 +627,19 @@ int evxgpu_stage_set_block_table(evxgpu_handle *h, const evxgpu_block_desc *tabl
     if (!h || !table) return 1;
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpy(h->d_table, table, (size_t) h->nmb * 16, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int evxgpu_debug_set_bins_capacity(evxgpu_handle *h, uint32_t bits)
+{
+    if (!h || bits < 64 || h->pending_encode) return fail(1, "evxgpu_debug_set_bins_capacity: bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_bins); h->d_bins = NULL;
+    cudaFreeHost(h->h_bins); h->h_bins = NULL;
+    h->bins_cap_bits = h->h_bins_cap_bits = bits & ~63u;
+    if (cudaMalloc(&h->d_bins, (size_t) h->bins_cap_bits / 8 + 8) != cudaSuccess) return fail(3, "evxgpu_debug_set_bins_capacity: out of device memory");
+    if (cudaHostAlloc(&h->h_bins, (size_t) h->h_bins_cap_bits / 8 + 32, cudaHostAllocDefault) != cudaSuccess) return fail(3, "evxgpu_debug_set_bins_capacity: out of pinned memory");
     return 0;
 }
 

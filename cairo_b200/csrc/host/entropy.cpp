@@ -370,6 +370,11 @@ uint32_t slice_writer::serialize(const evxgpu_block_desc *t, const int16_t *reco
     return total_bits;
 }
 
+uint32_t slice_writer::serialize_bins(const uint64_t *bins, uint64_t nbins)
+{
+    return (uint32_t) abac_encode_bins(bins, (size_t) nbins, buf_);
+}
+
 // ---------------------------------------------------------------- decoder side
 
 namespace {

@@ -36,6 +36,8 @@ public:
     // table: mbw*mbh descriptors; records: the non-copy macroblocks' 384 coefficients in raster
     // order.  Returns the slice's bit count; the bits are in data() (LSB-first).
     uint32_t serialize(const evxgpu_block_desc *table, const int16_t *records, uint32_t n_noncopy);
+    // The bin string built on the device (evxgpu_encode_collect_bins): the coder only.
+    uint32_t serialize_bins(const uint64_t *bins, uint64_t nbins);
     const uint8_t *data() const { return buf_.data(); }
 };
 

@@ -116,6 +116,7 @@ struct evx1_frame_stats
     double entropy_ms;       // host serialisation (Exp-Golomb + ABAC)
     uint32 slice_bits;
     uint32 noncopy_blocks;
+    uint32 d2h_bytes;        // what came back from the device for this frame (bin string, or table + records)
 };
 
 class evx1_encoder

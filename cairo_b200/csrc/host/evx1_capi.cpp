@@ -52,7 +52,7 @@ int evx1c_encoder_encode(evx1c_encoder *e, const uint8_t *rgb, uint32_t width, u
     return st;
 }
 
-int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks)
+int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks, uint32_t *d2h_bytes)
 {
     if (!e) return EVX_ERROR_INVALIDARG;
     evx1_frame_stats s;
@@ -61,6 +61,7 @@ int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, ui
     if (entropy_ms) *entropy_ms = s.entropy_ms;
     if (slice_bits) *slice_bits = s.slice_bits;
     if (noncopy_blocks) *noncopy_blocks = s.noncopy_blocks;
+    if (d2h_bytes) *d2h_bytes = s.d2h_bytes;
     return st;
 }
 
@@ -101,6 +102,17 @@ int evx1c_slice_writer_serialize(evx1c_slice_writer *w, const void *table, const
 {
     if (!w || !table || !out || !out_bits) return EVX_ERROR_INVALIDARG;
     uint32_t bits = w->w.serialize(static_cast<const evxgpu_block_desc *>(table), records, n_noncopy);
+    if (!bits) return EVX_ERROR_EXECUTION_FAILURE;
+    if (((bits + 7) >> 3) > out_cap_bytes) return EVX_ERROR_CAPACITY_LIMIT;
+    memcpy(out, w->w.data(), (bits + 7) >> 3);
+    *out_bits = bits;
+    return EVX_SUCCESS;
+}
+
+int evx1c_slice_writer_serialize_bins(evx1c_slice_writer *w, const uint64_t *bins, uint64_t nbins, uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits)
+{
+    if (!w || !bins || !out || !out_bits) return EVX_ERROR_INVALIDARG;
+    uint32_t bits = w->w.serialize_bins(bins, nbins);
     if (!bits) return EVX_ERROR_EXECUTION_FAILURE;
     if (((bits + 7) >> 3) > out_cap_bytes) return EVX_ERROR_CAPACITY_LIMIT;
     memcpy(out, w->w.data(), (bits + 7) >> 3);

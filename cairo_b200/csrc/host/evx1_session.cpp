@@ -4,6 +4,7 @@
 // frame counter, periodic intra.  Where the reference calls engine_encode_frame /
 // engine_decode_frame (encode.cpp:205, decode.cpp:172) these sessions call the device
 // library (include/evxgpu.h) for the pixel pipeline and entropy.cpp for the slice.
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
@@ -69,6 +70,7 @@ class encoder_session : public evx1_encoder
     std::vector<evxgpu_block_desc> table_;
     std::vector<int16> records_;
     evx1_frame_stats stats_;
+    bool device_bins_;
 
     void clear_frame()          // clear_frame, common.cpp:50-64
     {
@@ -90,6 +92,10 @@ class encoder_session : public evx1_encoder
         evxgpu_config gc = { cfg_.ref_count, cfg_.linear_quant, cfg_.deblocking, 0 };
         int rc = evxgpu_create(cfg_.device, (int) width, (int) height, &gc, NULL, &gpu_);
         if (rc) return map_gpu_status(rc);
+        // The device binarises the slice (include/evxgpu.h, evxgpu_set_output); EVX1_HOST_BINARISE=1 keeps
+        // the table + records path and binarises here instead (same bits; for A/B measurements).
+        device_bins_ = getenv("EVX1_HOST_BINARISE") == NULL;
+        if (device_bins_ && (rc = evxgpu_set_output(gpu_, 1))) return map_gpu_status(rc);
         int mbw = (int) ((width + 15) / 16), mbh = (int) ((height + 15) / 16);
         writer_.configure(mbw, mbh, cfg_.ref_count);
         table_.assign((size_t) mbw * mbh, evxgpu_block_desc());
@@ -137,11 +143,26 @@ public:
         double t0 = now_ms();
         int rc = evxgpu_encode_submit(gpu_, static_cast<const uint8 *>(image), 0, (int) frame_.type, frame_.index, (int) frame_.quality);
         if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        uint32 n_noncopy = 0;
-        rc = evxgpu_encode_collect(gpu_, table_.data(), records_.data(), &n_noncopy);
-        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        double t1 = now_ms();
-        uint32 bits = writer_.serialize(table_.data(), records_.data(), n_noncopy);
+        uint32 n_noncopy = 0, bits = 0;
+        double t1;
+        if (device_bins_)
+        {
+            const uint64_t *bins = NULL;
+            uint64_t nbins = 0;
+            rc = evxgpu_encode_collect_bins(gpu_, &bins, &nbins, &n_noncopy);
+            if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+            t1 = now_ms();
+            bits = writer_.serialize_bins(bins, nbins);
+            stats_.d2h_bytes = (uint32) ((nbins + 7) / 8 + 16);
+        }
+        else
+        {
+            rc = evxgpu_encode_collect(gpu_, table_.data(), records_.data(), &n_noncopy);
+            if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+            t1 = now_ms();
+            bits = writer_.serialize(table_.data(), records_.data(), n_noncopy);
+            stats_.d2h_bytes = (uint32) (table_.size() * 16 + (size_t) n_noncopy * 768 + 8);
+        }
         if (!bits) return EVX_ERROR_EXECUTION_FAILURE;
         evx_status wst = output->write_bits(const_cast<uint8 *>(writer_.data()), bits);
         double t2 = now_ms();

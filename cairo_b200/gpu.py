@@ -16,7 +16,7 @@ BLOCK_DESC_DTYPE = np.dtype({
     "itemsize": 16,
 })
 
-T_NAMES = ["convert_in", "inter_search", "wavefront", "deblock", "decode_recon", "convert_out"]
+T_NAMES = ["convert_in", "inter_search", "wavefront", "deblock", "decode_recon", "convert_out", "bins"]
 
 
 class Config(C.Structure):
@@ -49,6 +49,9 @@ def lib():
     L.evxgpu_upload.argtypes = [vp, vp, vp, C.c_uint64]
     L.evxgpu_encode_submit.argtypes = [vp, vp, i32, i32, u32, i32]
     L.evxgpu_encode_collect.argtypes = [vp, vp, vp, C.POINTER(u32)]
+    L.evxgpu_set_output.argtypes = [vp, i32]
+    L.evxgpu_encode_collect_bins.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64), C.POINTER(u32)]
+    L.evxgpu_debug_set_bins_capacity.argtypes = [vp, u32]
     L.evxgpu_decode_submit.argtypes = [vp, vp, vp, u32, i32, u32]
     L.evxgpu_decode_collect.argtypes = [vp, vp, i32]
     L.evxgpu_stage_convert_in.argtypes = [vp, vp]
@@ -119,6 +122,22 @@ class Pipeline:
         _check(self.L.evxgpu_encode_collect(self.h, _p(tbl), _p(self._records), C.byref(n)), "evxgpu_encode_collect")
         return tbl, self._records[:n.value].copy()
 
+    def set_output(self, mode):
+        """0 = table + records, 1 = the slice's bin string only, 2 = both (collect bins first)."""
+        _check(self.L.evxgpu_set_output(self.h, mode), "evxgpu_set_output")
+
+    def encode_collect_bins(self):
+        """-> (uint64 words of the bin string, number of bins, non-copy macroblocks)"""
+        ptr = C.POINTER(C.c_uint64)()
+        n, nc = C.c_uint64(0), C.c_uint32(0)
+        _check(self.L.evxgpu_encode_collect_bins(self.h, C.byref(ptr), C.byref(n), C.byref(nc)), "evxgpu_encode_collect_bins")
+        words = (n.value + 63) // 64
+        arr = np.ctypeslib.as_array(ptr, shape=(max(words, 1),)).copy() if words else np.zeros(1, np.uint64)
+        return arr, n.value, nc.value
+
+    def set_bins_capacity(self, bits):
+        _check(self.L.evxgpu_debug_set_bins_capacity(self.h, bits), "evxgpu_debug_set_bins_capacity")
+
     def encode(self, rgb, frame_type, index, quality):
         self.encode_submit(rgb, frame_type, index, quality)
         return self.encode_collect()
@@ -169,7 +188,7 @@ class Pipeline:
         self.L.evxgpu_enable_timing(self.h, int(on))
 
     def timing(self):
-        ms = (C.c_float * 6)()
+        ms = (C.c_float * len(T_NAMES))()
         _check(self.L.evxgpu_get_timing(self.h, ms), "evxgpu_get_timing")
         return dict(zip(T_NAMES, [float(v) for v in ms]))
 

@@ -25,7 +25,7 @@ int evx1c_encoder_set_quality(evx1c_encoder *e, int quality);    /* evx1_encoder
 /* evx1_encoder::encode into a fresh bit_stream; copies ceil(out_bits/8) bytes to out. */
 int evx1c_encoder_encode(evx1c_encoder *e, const uint8_t *rgb, uint32_t width, uint32_t height,
                          uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits);
-int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks);
+int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks, uint32_t *d2h_bytes);
 
 evx1c_decoder *evx1c_decoder_create(int device, int linear_quant, int deblocking);
 void evx1c_decoder_destroy(evx1c_decoder *d);
@@ -43,6 +43,8 @@ evx1c_slice_writer *evx1c_slice_writer_create(int mbw, int mbh, int ref_count);
 void evx1c_slice_writer_destroy(evx1c_slice_writer *w);
 int evx1c_slice_writer_serialize(evx1c_slice_writer *w, const void *table, const int16_t *records, uint32_t n_noncopy,
                                  uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits);
+/* the coder alone, over a bin string from evxgpu_encode_collect_bins */
+int evx1c_slice_writer_serialize_bins(evx1c_slice_writer *w, const uint64_t *bins, uint64_t nbins, uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits);
 evx1c_slice_reader *evx1c_slice_reader_create(int mbw, int mbh, int ref_count);
 void evx1c_slice_reader_destroy(evx1c_slice_reader *r);
 /* table is in/out (persistent across frames); records_out must hold mbw*mbh*384 int16. */

@@ -58,7 +58,7 @@ typedef struct evxgpu_config
 
 /* kernels timed by evxgpu_get_timing() */
 enum { EVXGPU_T_CONVERT_IN = 0, EVXGPU_T_INTER_SEARCH, EVXGPU_T_WAVEFRONT, EVXGPU_T_DEBLOCK,
-       EVXGPU_T_DECODE_RECON, EVXGPU_T_CONVERT_OUT, EVXGPU_T_COUNT };
+       EVXGPU_T_DECODE_RECON, EVXGPU_T_CONVERT_OUT, EVXGPU_T_BINS, EVXGPU_T_COUNT };
 
 typedef struct evxgpu_handle evxgpu_handle;
 
@@ -86,6 +86,16 @@ int evxgpu_upload(evxgpu_handle *h, void *dst_device, const void *src_host, uint
 int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device,
                          int frame_type, uint32_t frame_index, int quality);
 int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_t *records_out, uint32_t *n_noncopy);
+
+/* The same slice as the string of bins serialize_slice feeds its arithmetic coder (serialize.cpp:156-340:
+ * block table by field, then the Y, U, V residual blocks; raw bits and Exp-Golomb codes of golomb.cpp:8-91,
+ * DC prediction of serialize.cpp:25-72 including the stale DC of copy blocks), binarised on the device.
+ * Only encode_symbol (abac.cpp:97-121) is left for the host: it walks bin i = bit (i & 63) of word (i >> 6).
+ * set_output: 0 = table + records (default), 1 = bins only, 2 = both (collect_bins first, then collect).
+ * The device keeps the DC state of serialize.cpp:59-72 across frames, so the mode is chosen once per stream.
+ * collect_bins: *bins points into the handle's pinned buffer, valid until the next submit. */
+int evxgpu_set_output(evxgpu_handle *h, int mode);
+int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins, uint64_t *nbins, uint32_t *n_noncopy /* may be NULL */);
 
 /* ---- decoder: replaces decode_slice + deblock_image_filter + convert_image ----
  * table: block_count descriptors as unserialize_slice leaves them; records: the
@@ -118,6 +128,8 @@ uint64_t evxgpu_launch_count(const evxgpu_handle *h);
 int evxgpu_debug_profile(evxgpu_handle *h, int enable, long long *out_host);
 /* tuning knob: number of persistent CTAs of the decoder's wavefront kernel (0 = default) */
 int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas);
+/* tests: shrink the bin-string buffers so that the grow-and-emit-again path of collect_bins runs */
+int evxgpu_debug_set_bins_capacity(evxgpu_handle *h, uint32_t bits);
 
 /* integer-pipe micro-benchmark (the roofline denominator MEASURED_PEAKS.json lacks):
  * kind 0 IADD3, 1 VIADDMNMX.S16x2, 2 IDP.2A, 3 the 3:2 mix the search kernels issue.
