@@ -38,7 +38,8 @@ def build_gpu(force=False, verbose=False):
     deps = _sources("", (".cu", ".cuh")) + [os.path.join(ROOT, "include", "evxgpu.h")]
     if not force and not _newer(GPU_SO, deps):
         return GPU_SO
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", GPU_SO, os.path.join(CSRC, "evxgpu.cu")]
+    extra = os.environ.get("EVX_EXTRA_NVCC", "").split()      # e.g. -DEVX_K3_TRACE for profiles/trace_k3.py
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", GPU_SO, os.path.join(CSRC, "evxgpu.cu")]
     subprocess.check_call(cmd)
     lint_sass(GPU_SO)
     return GPU_SO

@@ -7,16 +7,19 @@
 // schedule is a wavefront: (bx,by) after (bx-1,by) and (min(bx+2,W-1),by-1).
 //
 // Mapping: ONE CTA PER MACROBLOCK ROW, warp specialised --
-//   warps 0..3  compute (one per SM sub-partition): the eight outer candidates of a 3x3 search
-//               round, two per warp (the centre is the running best, whose cost is already
-//               known), then the transform path of the macroblock.  More warps were slower:
-//               every warp replays the acceptance rule, and eight warps on four schedulers spent
-//               most of a round contending for issue slots and waiting at the barrier;
-//   warp  4     loader: one macroblock ahead, stages the source block, K2's inter results and
-//               their predictions, and slides the search window (a ring of 8 macroblock
-//               columns in shared memory) -- the 16 new columns of the three rows above once
-//               the row above has published them, the stale columns of the row below any time;
-//   warp  5     publisher: fences and releases progress[by] so the row below can follow.
+//   warps 0..7  compute: the eight outer candidates of a 3x3 search round, one per warp (the
+//               centre is the running best, whose cost is already known), then the transform
+//               path of the macroblock;
+//   warp  8     publisher + block loader.  Each time a macroblock of the row completes it first
+//               fences and releases progress[by] so the row below can follow, then stages the
+//               macroblock after next: source block, K2's inter results and their predictions,
+//               the stale columns of the row below -- nothing that depends on the row above;
+//   warp  9     column loader: slides the search window (a ring of 8 macroblock columns in
+//               shared memory) -- the 16 new columns of the three rows above as soon as the row
+//               above has published them.  A loader of its own, because this is the row-to-row
+//               critical path: with one loader doing both, staging macroblock n+1 queued behind
+//               the wait for column n+2 and every row trailed its predecessor by 4 macroblock
+//               times instead of 2 + the hand-off;
 // The left-neighbour dependency is thus inside the CTA (its reconstruction is written straight
 // into the window), and the inter-row latency (flag + L2 round trip) is paid once per row
 // instead of once per macroblock: frame time ~ (W + 3(H-1)) * T_mb + (H-1) * latency.
@@ -46,8 +49,7 @@ struct EvxK3Smem
     EvxMbShared sh;
     int4 cand[2][16];                         // sub-pel tests: {sad, mad, 0, legal}
     int2 cand2[2][16];                        // full-pel rounds: raw {sad, mad} per cell
-    uint64_t full[2], full2[2], empty[2];      // full: everything but the far-right column; full2: that column too
-    int done;                                 // macroblocks of this row whose reconstruction is stored
+    uint64_t full[2], fullb[2], full2[2], empty[2];   // full: block data; fullb: window columns <= n+1; full2: column n+2
     int row;
 };
 
@@ -62,21 +64,29 @@ __device__ __forceinline__ void evx_compute_sync() { asm volatile("bar.sync 1, %
 __device__ __forceinline__ int evx_ring_y(const EvxK3Smem &S, int x, int wrow) { return reinterpret_cast<const int16_t *>(S.wy)[wrow * (EVX_RING_PWY * 2) + (x & 127)]; }
 __device__ __forceinline__ int evx_ring_c(const uint32_t *pl, int cx, int wrow) { return reinterpret_cast<const int16_t *>(pl)[wrow * (EVX_RING_PWC * 2) + (cx & 63)]; }
 
-// ---------------------------------------------------------------- loader warp
+// ---------------------------------------------------------------- block loader warp
 
-__device__ __forceinline__ void evx_k3_loader(EvxK3Smem &S, const EvxK3Params &p, int by, int lane)
+__device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Params &p, int by, int lane)
 {
     const EvxGeom g = p.g;
     const int nmb = g.mbw * g.mbh, cw = g.w >> 1, py = by * EVX_MB;
     const int dest = (int) (p.frame_index % (uint32_t) p.R);
     const EvxPlanes cur = p.ring[dest];
-    const int *progress = p.sync + 2;
+    int *progress = p.sync + 2;
     const int nref = p.frame_type == 1 ? p.R - 1 : 0;
+    // macroblock m of this row is complete (its `empty` phase has passed; the compute warps cannot
+    // be more than one macroblock past the one being staged, so a phase is never lapped): make the
+    // row's writes visible device-wide, then advance progress[by]
+    auto publish = [&](int m)
+    {
+        evx_mbar_wait(&S.empty[m & 1], (uint32_t) ((m >> 1) & 1));
+        if (lane == 0) evx_st_release(progress + by, m + 1);     // release is cumulative over what this thread observed through the barrier
+    };
 
     for (int n = 0; n < g.mbw; ++n)
     {
         const int slot = n & 1, px = n * EVX_MB, mb = by * g.mbw + n;
-        if (n >= 2) evx_mbar_wait(&S.empty[slot], (uint32_t) (((n >> 1) - 1) & 1));
+        if (n >= 2) publish(n - 2);          // also frees this slot's staging buffers
 
         // source macroblock -> block-major
         {
@@ -145,70 +155,84 @@ __device__ __forceinline__ void evx_k3_loader(EvxK3Smem &S, const EvxK3Params &p
                 *reinterpret_cast<uint4 *>(&(lane < 8 ? S.wu : S.wv)[(32 + (lane & 7)) * EVX_RING_PWC + ((cx0 >> 1) & 31)]) = c;
             }
         }
-        // The three rows above.  Columns up to macroblock n+1 are what the search needs at once
-        // (they arrived while staging macroblock n-1, except at the row start); the far-right
-        // column n+2 is needed only by candidates with x >= px+17 and, as (n+2,by-1)'s completion,
-        // before this macroblock may overwrite the samples the row above still reads (write-after-
-        // read).  Staging it AFTER `full` is signalled gives every macroblock one macroblock-time of
-        // slack against jitter in the row above instead of a hard stall.
-        auto pull_column = [&](int col)
-        {
-            uint4 v[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-            {
-                int c = lane + 32 * k;                 // 96 chunks: 48 rows x 2 halves
-                int row = c >> 1, half = c & 1, y = py - 48 + row;
-                v[k] = make_uint4(0, 0, 0, 0);
-                if (y >= 0) v[k] = __ldcg(reinterpret_cast<const uint4 *>(cur.y + (size_t) y * g.w + col * EVX_MB + 8 * half));
-            }
-            uint4 cv[2];
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-            {
-                int c = lane + 32 * k;                 // 48 chunks: 2 planes x 24 rows
-                cv[k] = make_uint4(0, 0, 0, 0);
-                if (c < 48)
-                {
-                    int plane = c / 24, row = c % 24, y = (py >> 1) - 24 + row;
-                    if (y >= 0) cv[k] = __ldcg(reinterpret_cast<const uint4 *>((plane ? cur.v : cur.u) + (size_t) y * cw + col * 8));
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-            {
-                int c = lane + 32 * k;
-                int row = c >> 1, half = c & 1;
-                *reinterpret_cast<uint4 *>(&S.wy[row * EVX_RING_PWY + (((col * EVX_MB + 8 * half) >> 1) & 63)]) = v[k];
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-            {
-                int c = lane + 32 * k;
-                if (c < 48)
-                {
-                    int plane = c / 24, row = c % 24;
-                    *reinterpret_cast<uint4 *>(&(plane ? S.wv : S.wu)[row * EVX_RING_PWC + (((col * 8) >> 1) & 31)]) = cv[k];
-                }
-            }
-        };
-        if (by > 0 && n == 0)
-        {
-            if (lane == 0) evx_wait_ge(progress + by - 1, min(1, g.mbw - 1) + 1);
-            __syncwarp();
-            pull_column(0);
-            if (g.mbw > 1) pull_column(1);
-        }
         __syncwarp();
         if (lane == 0) evx_mbar_arrive(&S.full[slot]);
+    }
+    for (int m = max(0, g.mbw - 2); m < g.mbw; ++m) publish(m);
+}
+
+// ---------------------------------------------------------------- column loader warp
+//
+// Column c of the three macroblock rows above enters the window once (c,by-1) is complete.
+// Macroblock n may start when columns <= n+1 are in (fullb); it needs column n+2 only for
+// candidates with x >= px+17, for the sub-pel taps there, and -- as the proof that (n+2,by-1)
+// is complete -- before it overwrites samples the row above still reads (full2).  Two virtual
+// columns past the right edge carry the last macroblocks' signals.
+
+__device__ __forceinline__ void evx_k3_column_loader(EvxK3Smem &S, const EvxK3Params &p, int by, int lane)
+{
+    const EvxGeom g = p.g;
+    const int cw = g.w >> 1, py = by * EVX_MB;
+    const EvxPlanes cur = p.ring[(int) (p.frame_index % (uint32_t) p.R)];
+    const int *progress = p.sync + 2;
+    auto pull_column = [&](int col)
+    {
+        uint4 v[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            int c = lane + 32 * k;                 // 96 chunks: 48 rows x 2 halves
+            int row = c >> 1, half = c & 1, y = py - 48 + row;
+            v[k] = make_uint4(0, 0, 0, 0);
+            if (y >= 0) v[k] = __ldcg(reinterpret_cast<const uint4 *>(cur.y + (size_t) y * g.w + col * EVX_MB + 8 * half));
+        }
+        uint4 cv[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+        {
+            int c = lane + 32 * k;                 // 48 chunks: 2 planes x 24 rows
+            cv[k] = make_uint4(0, 0, 0, 0);
+            if (c < 48)
+            {
+                int plane = c / 24, row = c % 24, y = (py >> 1) - 24 + row;
+                if (y >= 0) cv[k] = __ldcg(reinterpret_cast<const uint4 *>((plane ? cur.v : cur.u) + (size_t) y * cw + col * 8));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            int c = lane + 32 * k;
+            int row = c >> 1, half = c & 1;
+            *reinterpret_cast<uint4 *>(&S.wy[row * EVX_RING_PWY + (((col * EVX_MB + 8 * half) >> 1) & 63)]) = v[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+        {
+            int c = lane + 32 * k;
+            if (c < 48)
+            {
+                int plane = c / 24, row = c % 24;
+                *reinterpret_cast<uint4 *>(&(plane ? S.wv : S.wu)[row * EVX_RING_PWC + (((col * 8) >> 1) & 31)]) = cv[k];
+            }
+        }
+    };
+    for (int c = 0; c < g.mbw + 2; ++c)
+    {
+        // macroblock c-3 finished: the barrier phases of macroblocks c-1 / c-2 are free again and
+        // nobody reads ring column c-8 any more
+        if (c >= 3) evx_mbar_wait(&S.empty[(c - 3) & 1], (uint32_t) (((c - 3) >> 1) & 1));
         if (by > 0)
         {
-            if (lane == 0) evx_wait_ge(progress + by - 1, min(n + 2, g.mbw - 1) + 1);
+            if (lane == 0) evx_wait_ge(progress + by - 1, min(c, g.mbw - 1) + 1);
             __syncwarp();
-            if (n + 2 < g.mbw) pull_column(n + 2);
+            if (c < g.mbw) pull_column(c);
         }
         __syncwarp();
-        if (lane == 0) evx_mbar_arrive(&S.full2[slot]);
+        if (lane == 0)
+        {
+            if (c >= 1 && c - 1 < g.mbw) evx_mbar_arrive(&S.fullb[(c - 1) & 1]);
+            if (c >= 2) evx_mbar_arrive(&S.full2[(c - 2) & 1]);
+        }
     }
 }
 
@@ -255,15 +279,22 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     uint32_t n_full = 0, n_sub = 0;
     int row_records = 0;
     long long prof[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }, tprev = clock64();
+#ifdef EVX_K3_TRACE
+#define EVX_K3_STAMP(k) do { if (p.prof && tid == 0) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); p.prof[(size_t) g.mbh * 10 + (size_t) mb * 4 + (k)] = (long long) gt_; } } while (0)
+#else
+#define EVX_K3_STAMP(k) do { } while (0)
+#endif
 #define EVX_K3_PROF(k) do { if (p.prof) { long long tn = clock64(); prof[k] += tn - tprev; tprev = tn; } } while (0)
 
     for (int n = 0; n < g.mbw; ++n)
     {
         const int slot = n & 1, px = n * EVX_MB, mb = by * g.mbw + n;
         evx_mbar_wait(&S.full[slot], (uint32_t) ((n >> 1) & 1));
+        evx_mbar_wait(&S.fullb[slot], (uint32_t) ((n >> 1) & 1));
         EVX_K3_PROF(0);
+        EVX_K3_STAMP(0);
         bool have2 = false;      // far-right column (and write permission) not yet confirmed
-#define EVX_K3_NEED2() do { if (!have2) { evx_mbar_wait(&S.full2[slot], (uint32_t) ((n >> 1) & 1)); have2 = true; } } while (0)
+#define EVX_K3_NEED2() do { if (!have2) { evx_mbar_wait(&S.full2[slot], (uint32_t) ((n >> 1) & 1)); have2 = true; EVX_K3_STAMP(1); } } while (0)
         const int16_t *srcb = S.src[slot];
 
         EvxLaneSrc src;
@@ -535,10 +566,10 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         }
         evx_compute_sync();
         EVX_K3_PROF(4);
+        EVX_K3_STAMP(2);
         if (tid == 0)
         {
             evx_mbar_arrive(&S.empty[slot]);
-            asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(evx_smem_addr(&S.done)), "r"(n + 1) : "memory");
         }
     }
     if (tid == 0)
@@ -561,9 +592,9 @@ __global__ void __launch_bounds__(EVX_K3_NT, 2) evx_wavefront(const __grid_const
         // rows are claimed in order: a CTA only ever waits on rows claimed before its own
         S.row = atomicAdd(&p.sync[0], 1);
         evx_mbar_init(&S.full[0], 1); evx_mbar_init(&S.full[1], 1);
+        evx_mbar_init(&S.fullb[0], 1); evx_mbar_init(&S.fullb[1], 1);
         evx_mbar_init(&S.full2[0], 1); evx_mbar_init(&S.full2[1], 1);
         evx_mbar_init(&S.empty[0], 1); evx_mbar_init(&S.empty[1], 1);
-        S.done = 0;
     }
     evx_init_tables(S.sh, tid, EVX_K3_NT);
     __syncthreads();
@@ -571,27 +602,6 @@ __global__ void __launch_bounds__(EVX_K3_NT, 2) evx_wavefront(const __grid_const
     if (by >= p.g.mbh) return;
 
     if (warp < EVX_K3_CW) evx_k3_compute(S, p, by, tid);
-    else if (warp == EVX_K3_CW) evx_k3_loader(S, p, by, lane);
-    else
-    {   // publisher: make the row's writes visible device-wide, then advance progress[by].
-        // It follows a counter, not a phase, so a fast compute side can never lap it.
-        int *progress = p.sync + 2;
-        if (lane == 0)
-        {
-            int last = 0;
-            while (last < p.g.mbw)
-            {
-                int d;
-                for (;;)
-                {
-                    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(d) : "r"(evx_smem_addr(&S.done)) : "memory");
-                    if (d > last) break;
-                    __nanosleep(64);
-                }
-                __threadfence();
-                evx_st_release(progress + by, d);
-                last = d;
-            }
-        }
-    }
+    else if (warp == EVX_K3_CW) evx_k3_block_loader(S, p, by, lane);
+    else if (warp == EVX_K3_CW + 1) evx_k3_column_loader(S, p, by, lane);
 }

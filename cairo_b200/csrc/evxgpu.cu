@@ -657,8 +657,10 @@ int evxgpu_debug_profile(evxgpu_handle *h, int enable, long long *out_host)
     if (!h) return 1;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    if (enable && !h->d_prof) { CK(cudaMalloc(&h->d_prof, (size_t) h->g.mbh * 10 * 8)); CK(cudaMemset(h->d_prof, 0, (size_t) h->g.mbh * 10 * 8)); }
-    if (out_host && h->d_prof) CK(cudaMemcpy(out_host, h->d_prof, (size_t) h->g.mbh * 10 * 8, cudaMemcpyDeviceToHost));
+    // [mbh][10] phase sums, then (builds with -DEVX_K3_TRACE only) [nmb][4] globaltimer stamps per macroblock
+    const size_t elems = (size_t) h->g.mbh * 10 + (size_t) h->nmb * 4;
+    if (enable && !h->d_prof) { CK(cudaMalloc(&h->d_prof, elems * 8)); CK(cudaMemset(h->d_prof, 0, elems * 8)); }
+    if (out_host && h->d_prof) CK(cudaMemcpy(out_host, h->d_prof, elems * 8, cudaMemcpyDeviceToHost));
     if (!enable && h->d_prof) { cudaFree(h->d_prof); h->d_prof = NULL; }
     return 0;
 }

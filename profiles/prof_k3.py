@@ -14,8 +14,9 @@ for t in range(3):
 L.evxgpu_debug_profile(p.h, 1, None)
 tbl, rec = p.encode(frames[3], 1, 3, 16)
 tm = p.timing()
-prof = np.zeros((p.ah // 16, 10), dtype=np.int64)
-L.evxgpu_debug_profile(p.h, 1, prof.ctypes.data_as(C.c_void_p))
+raw = np.zeros((p.ah // 16) * 10 + p.nblocks * 4, dtype=np.int64)
+L.evxgpu_debug_profile(p.h, 1, raw.ctypes.data_as(C.c_void_p))
+prof = raw[:(p.ah // 16) * 10].reshape(-1, 10)
 names = ['wait_loader', 'search5', 'subpel', 'classify+pred', 'transform+recon', 'unused', 'r_eval', 'r_barrier', 'r_replay', 'x']
 mbw = p.aw // 16
 print(f"wavefront {tm['wavefront']:.3f} ms, inter {tm['inter_search']:.3f} ms, non-copy share {rec.shape[0] / p.nblocks:.2f}")
