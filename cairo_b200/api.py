@@ -37,6 +37,7 @@ def lib():
     L.evx1c_decoder_destroy.argtypes = [vp]
     L.evx1c_decoder_clear.argtypes = [vp]
     L.evx1c_decoder_decode.argtypes = [vp, vp, u32, vp]
+    L.evx1c_decoder_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.evx1c_slice_writer_create.restype = vp
     L.evx1c_slice_writer_create.argtypes = [i32] * 3
     L.evx1c_slice_writer_destroy.argtypes = [vp]
@@ -119,9 +120,16 @@ class evx1_decoder:
     def clear(self):
         return self.L.evx1c_decoder_clear(self.h)
 
-    def decode(self, data, nbits, width, height):
+    def stats(self):
+        g, e = C.c_double(0), C.c_double(0)
+        self.L.evx1c_decoder_stats(self.h, C.byref(g), C.byref(e))
+        return {"gpu_ms": g.value, "entropy_ms": e.value}
+
+    def decode(self, data, nbits, width, height, out=None):
+        """out: optional uint8 (height, width, 3) array to decode into (e.g. a view of pinned memory)."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
-        out = np.zeros((height, width, 3), dtype=np.uint8)
+        if out is None:
+            out = np.empty((height, width, 3), dtype=np.uint8)
         st = self.L.evx1c_decoder_decode(self.h, _p(data), nbits, _p(out))
         if st != 0:
             raise RuntimeError(f"evx1_decoder::decode failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")

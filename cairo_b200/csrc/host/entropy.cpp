@@ -379,30 +379,31 @@ uint32_t slice_writer::serialize_bins(const uint64_t *bins, uint64_t nbins)
 
 namespace {
 
+// decode_symbol + resolve_decode_scaling (abac.cpp:123-154, 226-279).  Like the encoder, the
+// decoder is one dependency chain through (low, high, value); the common path uses the same
+// reciprocal split point (see abac_encode_bins), mask selects, and takes all E1/E2 shifts of a
+// symbol at once: with k leading bits shared by low and high, the next k stream bits enter
+// `value` together.  The stream is least-significant-bit first, so the slice is copied once with
+// every byte turned around and the coder peeks 17 bits from a big-endian load.  Everything that
+// is not the common case -- the last 17 bits of the slice (past its end the reference repeats
+// the last bit read within the call), a collapsed interval, a value outside [low, high] (corrupt
+// streams: the reference then updates nothing) -- goes bit at a time exactly as the reference does.
 class abac_reader
 {
-    const uint8_t *data_;
+    const uint8_t *data_;           // the caller's bits (LSB-first), absolute bit positions
+    const uint8_t *rev_;            // the same bytes, each bit-reversed (MSB-first), padded
     uint32_t pos_, end_;
-    uint32_t low_, high_, value_, h0_, h1_;
+    uint32_t low_, high_, value_;
+    uint64_t h0_, tot_;
+    const uint64_t *recip_;
+    uint64_t fast_limit_;
 
     inline bool empty() const { return pos_ >= end_; }
     inline uint32_t get() { uint32_t b = (data_[pos_ >> 3] >> (pos_ & 7)) & 1u; pos_++; return b; }
 
-public:
-    abac_reader(const uint8_t *data, uint32_t pos, uint32_t end) : data_(data), pos_(pos), end_(end), low_(0), high_(AB_MAX), value_(0), h0_(1), h1_(1)
-    {   // start_decode, abac.cpp:398-420: past the end the LAST bit read is repeated
-        uint32_t bit = 0;
-        for (int i = 0; i < 16; ++i) { if (!empty()) bit = get(); value_ = (value_ << 1) | bit; }
-    }
-
-    // decode_symbol + resolve_decode_scaling, abac.cpp:123-154, 226-279
-    inline uint32_t decode()
+    // the reference's loop, one scaling step per turn
+    inline void renorm_slow()
     {
-        const uint32_t range = high_ - low_;
-        const uint32_t mid = low_ + (uint32_t) (((uint64_t) range * h0_) / (h0_ + h1_));
-        uint32_t out = 0;
-        if (value_ >= low_ && value_ <= mid) { high_ = mid; h0_++; }
-        else if (value_ > mid && value_ <= high_) { low_ = mid + 1; h1_++; out = 1; }
         uint32_t bit = 0;
         for (;;)
         {
@@ -415,7 +416,58 @@ public:
             low_ = (low_ << 1) & AB_MAX;
             value_ = ((value_ << 1) & AB_MAX) | bit;
         }
-        return out;
+    }
+
+public:
+    abac_reader(const uint8_t *data, const uint8_t *rev, uint32_t pos, uint32_t end)
+        : data_(data), rev_(rev), pos_(pos), end_(end), low_(0), high_(AB_MAX), value_(0), h0_(1), tot_(2)
+    {   // start_decode, abac.cpp:398-420: past the end the LAST bit read is repeated
+        uint32_t bit = 0;
+        for (int i = 0; i < 16; ++i) { if (!empty()) bit = get(); value_ = (value_ << 1) | bit; }
+        reciprocal_table &rt = recips();
+        const size_t want = std::min<size_t>((size_t) (end - pos) * 2 + 64, size_t(1) << 23);     // a bin costs >= ~1/2 bit on real slices; grown below if not
+        if (rt.size() < want) rt.grow(want);
+        recip_ = rt.data();
+        fast_limit_ = std::min<uint64_t>(rt.size(), uint64_t(1) << 23);
+    }
+
+    inline uint32_t decode()
+    {
+        const uint64_t range = high_ - low_;
+        uint64_t q;
+        if (__builtin_expect(tot_ < fast_limit_, 1)) q = (range * ((uint64_t) (((unsigned __int128) h0_ * recip_[tot_]) >> 16) + 1)) >> 48;
+        else
+        {
+            q = (range * h0_) / tot_;
+            if (tot_ < (uint64_t(1) << 23)) { recips().grow((size_t) tot_ * 2); recip_ = recips().data(); fast_limit_ = std::min<uint64_t>(recips().size(), uint64_t(1) << 23); }
+        }
+        const uint32_t mid = low_ + (uint32_t) q;
+        const uint32_t in0 = (uint32_t) (value_ >= low_) & (uint32_t) (value_ <= mid);
+        const uint32_t in1 = (uint32_t) (value_ > mid) & (uint32_t) (value_ <= high_);
+        const uint32_t m0 = 0u - in0, m1 = 0u - in1;
+        low_ += ((uint32_t) q + 1) & m1;              // bit 1: low = mid + 1
+        high_ = (high_ & ~m0) | (mid & m0);           // bit 0: high = mid
+        h0_ += in0;
+        tot_ += in0 | in1;                            // neither (corrupt stream): nothing moves
+
+        const uint32_t k = (uint32_t) __builtin_clz(((low_ ^ high_) << 16) + 0x8000u);           // shared leading bits; 16 = collapsed
+        if (__builtin_expect((k == 16) | (pos_ + 17 > end_), 0)) { renorm_slow(); return in1; }
+        // 17 stream bits from pos_, first one on top
+        uint64_t w;
+        memcpy(&w, rev_ + (pos_ >> 3), 8);
+        w = (__builtin_bswap64(w) << (pos_ & 7)) >> 47;
+        low_ = (low_ << k) & AB_MAX;
+        high_ = ((high_ << k) & AB_MAX) | ((1u << k) - 1u);
+        value_ = ((value_ << k) & AB_MAX) | (uint32_t) (w >> (17 - k));
+        // E3 (3*QTR = 0xBFFD as in the reference): low -> 2*low - 0x8000, high -> 2*high - 0x7FFF, value -> 2*value - 0x8000 (mod 2^16) | next bit
+        const uint32_t c = (uint32_t) (low_ > AB_QTR) & (uint32_t) (high_ <= AB_3QTR), cm = 0u - c;
+        const uint32_t b1 = (uint32_t) (w >> (16 - k)) & 1u;
+        low_ += (low_ - 0x8000u) & cm;
+        high_ += (high_ - 0x7FFFu) & cm;
+        value_ = (value_ & ~cm) | (((((value_ ^ 0x4000u) << 1) & AB_MAX) | b1) & cm);
+        pos_ += k + c;
+        if (__builtin_expect(c && low_ > AB_QTR && high_ <= AB_3QTR, 0)) renorm_slow();          // further E3 steps
+        return in1;
     }
 
     inline uint32_t decode_bits_lsb(int n) { uint32_t v = 0; for (int k = 0; k < n; ++k) v |= decode() << k; return v; }
@@ -470,7 +522,13 @@ void slice_reader::reset() { dc_.resize((size_t) mbw_ * mbh_); }
 int slice_reader::unserialize(const uint8_t *data, uint32_t pos, uint32_t end, evxgpu_block_desc *t, int16_t *records, uint32_t *n_noncopy)
 {
     const int n = mbw_ * mbh_;
-    abac_reader rd(data, pos, end);
+    {   // the slice's bytes, each turned around (see abac_reader); absolute byte positions, 16 bytes of padding
+        const size_t first = pos >> 3, last = ((size_t) end + 7) >> 3;
+        if (rev_.size() < last + 16) rev_.resize(last + 16);
+        for (size_t i = first; i < last; ++i) rev_[i] = REV8[data[i]];
+        memset(rev_.data() + last, 0, 16);
+    }
+    abac_reader rd(data, rev_.data(), pos, end);
     for (int i = 0; i < n; ++i) t[i].block_type = (t[i].block_type & ~7) | (int32_t) rd.decode_bits_lsb(3);
     for (int i = 0; i < n; ++i)
         if (!(t[i].block_type & T_INTRA))

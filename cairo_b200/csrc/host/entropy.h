@@ -45,6 +45,7 @@ class slice_reader
 {
     int mbw_, mbh_, target_bits_;
     dc_mirror dc_;
+    std::vector<uint8_t> rev_;      // the slice being read, bytes bit-reversed (see abac_reader)
 
 public:
     void configure(int mbw, int mbh, int ref_count);

@@ -141,6 +141,7 @@ protected:
 public:
     virtual evx_status clear() = 0;
     virtual evx_status decode(bit_stream *input, void *output) = 0;
+    virtual evx_status last_frame_stats(evx1_frame_stats *out) = 0;                    // addition (entropy_ms = unserialize)
 };
 
 // addition: the reference's config.h switches at run time

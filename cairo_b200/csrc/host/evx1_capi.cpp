@@ -75,6 +75,15 @@ evx1c_decoder *evx1c_decoder_create(int device, int linear_quant, int deblocking
 
 void evx1c_decoder_destroy(evx1c_decoder *d) { if (d) { destroy_decoder(d->dec); delete d; } }
 int evx1c_decoder_clear(evx1c_decoder *d) { return d ? d->dec->clear() : EVX_ERROR_INVALIDARG; }
+int evx1c_decoder_stats(evx1c_decoder *d, double *gpu_ms, double *entropy_ms)
+{
+    if (!d) return EVX_ERROR_INVALIDARG;
+    evx1_frame_stats s;
+    int st = d->dec->last_frame_stats(&s);
+    if (gpu_ms) *gpu_ms = s.gpu_ms;
+    if (entropy_ms) *entropy_ms = s.entropy_ms;
+    return st;
+}
 
 int evx1c_decoder_decode(evx1c_decoder *d, const uint8_t *data, uint32_t nbits, uint8_t *rgb_out)
 {

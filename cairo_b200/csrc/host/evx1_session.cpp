@@ -193,6 +193,7 @@ class decoder_session : public evx1_decoder
     slice_reader reader_;
     std::vector<evxgpu_block_desc> table_;
     std::vector<int16> records_;
+    evx1_frame_stats stats_;
 
     void clear_frame() { frame_.type = 0; frame_.index = 0; frame_.quality = (uint16) clip(cfg_.default_quality, 1, 100); }
 
@@ -246,16 +247,23 @@ public:
 
         // engine_decode_frame, decode.cpp:172-198
         uint32 n_noncopy = 0;
+        const double t0 = now_ms();
+        const uint32 bits_before = input->query_read_index();
         if (reader_.unserialize(input->query_data(), input->query_read_index(), input->query_write_index(), table_.data(), records_.data(), &n_noncopy))
             return EVX_ERROR_EXECUTION_FAILURE;
+        const double t1 = now_ms();
         int rc = evxgpu_decode_submit(gpu_, table_.data(), records_.data(), n_noncopy, (int) frame_.type, frame_.index);
         if (rc) return EVX_ERROR_EXECUTION_FAILURE;
         rc = evxgpu_decode_collect(gpu_, static_cast<uint8 *>(output), 0);
         if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+        stats_.entropy_ms = t1 - t0; stats_.gpu_ms = now_ms() - t1; stats_.noncopy_blocks = n_noncopy;
+        stats_.slice_bits = input->query_write_index() - bits_before; stats_.d2h_bytes = 0;
         frame_.index++;
         input->empty();
         return EVX_SUCCESS;
     }
+
+    evx_status last_frame_stats(evx1_frame_stats *out) { if (!out) return EVX_ERROR_INVALIDARG; *out = stats_; return EVX_SUCCESS; }
 };
 
 }  // namespace

@@ -30,6 +30,7 @@ int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, ui
 evx1c_decoder *evx1c_decoder_create(int device, int linear_quant, int deblocking);
 void evx1c_decoder_destroy(evx1c_decoder *d);
 int evx1c_decoder_clear(evx1c_decoder *d);                       /* evx1_decoder::clear */
+int evx1c_decoder_stats(evx1c_decoder *d, double *gpu_ms, double *entropy_ms);   /* last frame: submit->collect, unserialize */
 /* evx1_decoder::decode of one frame (nbits bits at data); rgb_out is width*height*3 bytes. */
 int evx1c_decoder_decode(evx1c_decoder *d, const uint8_t *data, uint32_t nbits, uint8_t *rgb_out);
 

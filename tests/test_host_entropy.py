@@ -88,3 +88,36 @@ def test_fast_coder_against_plain_coder(tmp_path):
                            "-o", exe, os.path.join(root, "profiles", "abac_bench.cpp"), "-lpthread"])
     out = subprocess.run([exe, "check"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "all ok" in out.stdout, out.stdout[-2000:]
+
+
+def test_reader_matches_oracle_on_truncated_and_corrupt_slices():
+    """The fast arithmetic decoder against the oracle's bit-at-a-time restatement of the reference
+    (abac.cpp:123-154, 226-279, 398-420) where their semantics are most particular: slices cut short
+    (past the end the last bit read in the call repeats), bit flips, and pure noise (values outside
+    [low, high], collapsed intervals, absurd run lengths).  Both sides start from the same state."""
+    g = G.Golden(G.names()[0])
+    aw, ah = (g.w + 15) // 16 * 16, (g.h + 15) // 16 * 16
+    rng = np.random.default_rng(11)
+    cases = []
+    for t in range(min(g.frames, 3)):
+        gd, gb = g.slice_bits(t)
+        gd = np.array(gd, dtype=np.uint8)
+        cases.append((gd, gb))
+        for cut in (gb - 1, gb - 9, gb - 17, gb // 2, 40, 17, 16, 3, 0):
+            if 0 <= cut < gb:
+                cases.append((gd, cut))
+        for _ in range(4):
+            bad = gd.copy()
+            for pos in rng.integers(0, gb, size=3):
+                bad[pos >> 3] ^= np.uint8(1 << (pos & 7))
+            cases.append((bad, gb))
+    for nbits in (64, 1000, 20000):
+        cases.append((rng.integers(0, 256, size=nbits // 8 + 8, dtype=np.uint8), nbits))
+    for data, nbits in cases:
+        o = O.Oracle(g.w, g.h, g.R, 0, 1)
+        rd = api.SliceReader(aw // 16, ah // 16, g.R)
+        o.unserialize(data, nbits)
+        tbl, rec = rd.unserialize(data, nbits)
+        assert O.tables_equal(o.block_table().copy(), tbl, check_variance=False), nbits
+        want = gpu.planes_to_records(tbl, o.planes(1), aw)
+        assert want.shape == rec.shape and (want == rec).all(), nbits
