@@ -288,7 +288,7 @@ def run_ours(args):
 
     # ---- configs[4] in miniature: several independent streams sharing this GPU (one host thread,
     # one handle, one CUDA stream each); aggregate end-to-end throughput through the public API
-    ms_streams = max(1, min(args.streams, (os.cpu_count() or 1)))
+    ms_streams = max(1, min(args.streams, (os.cpu_count() or 1) // max(1, world)))     # one host thread per stream
     ms_frames = min(12, steps)
     ms_fps = multi_stream_e2e(api, host, fidx, warmup, ms_frames, ms_streams, local_rank)
 
@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--steps", type=int, default=56)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--streams", type=int, default=8, help="streams per GPU of the extra multi_stream measurement")
+    ap.add_argument("--streams", type=int, default=16, help="streams per GPU of the extra multi_stream measurement (capped at the host core count)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -175,11 +175,14 @@ __device__ __forceinline__ void evx_tma_load_2d(void *dst, const CUtensorMap *ma
 // synchronisation: the 16x16+8x8+8x8 candidate cost is a warp-collective (evx_block_cost),
 // the acceptance rule is replayed identically in every lane.
 
-#define EVX_K2_MBS 8
-#define EVX_K2_WIN_W 208          // 32 + 8*16 + 48; 104 words = 8 (mod 32)
+#ifndef EVX_K2_MBS
+#define EVX_K2_MBS 8              // macroblocks (= warps) per CTA; 8 or 4 keep the pitches conflict-free
+#endif
+#define EVX_K2_WIN_W (32 + EVX_K2_MBS * 16 + 48)   // 208 px = 104 words = 8 (mod 32);  144 px = 72 words = 8 (mod 32)
 #define EVX_K2_WIN_H 80
-#define EVX_K2_CWIN_W 104         // 52 words = 20 (mod 32) = 4*5
+#define EVX_K2_CWIN_W (EVX_K2_WIN_W / 2)           // 52 words = 4*13 -> 20 (mod 32);  36 words = 4 (mod 32)
 #define EVX_K2_CWIN_H 40
+#define EVX_K2_CTAS_PER_SM (EVX_K2_MBS == 8 ? 4 : 6)
 #define EVX_K2_SMEM (EVX_K2_WIN_W * EVX_K2_WIN_H * 2 + 2 * EVX_K2_CWIN_W * EVX_K2_CWIN_H * 2 + 16)
 
 struct EvxInterResult { EvxDesc desc; int sad; int pad[3]; };    // 32 bytes per (macroblock, reference)
@@ -266,7 +269,7 @@ __device__ __forceinline__ void evx_inter_search_warp(const EvxWin &win, const E
     }
 }
 
-__global__ void __launch_bounds__(256, 4) evx_inter_search(const __grid_constant__ EvxK2Maps maps, EvxPlanes srcp, EvxGeom g,
+__global__ void __launch_bounds__(EVX_K2_MBS * 32, EVX_K2_CTAS_PER_SM) evx_inter_search(const __grid_constant__ EvxK2Maps maps, EvxPlanes srcp, EvxGeom g,
                                                         EvxInterResult *__restrict__ results, int thr,
                                                         unsigned long long *__restrict__ counters)
 {

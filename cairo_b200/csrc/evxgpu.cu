@@ -333,7 +333,7 @@ static int launch_inter_search(evxgpu_handle *h, uint32_t index, int quality)
         int slot = (int) ((index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);     // common.cpp:192-195
         for (int c = 0; c < 3; ++c) maps.m[(off - 1) * 3 + c] = h->maps[slot][c];
     }
-    dim3 block(256), grid((h->g.mbw + EVX_K2_MBS - 1) / EVX_K2_MBS, h->g.mbh, R - 1);
+    dim3 block(EVX_K2_MBS * 32), grid((h->g.mbw + EVX_K2_MBS - 1) / EVX_K2_MBS, h->g.mbh, R - 1);
     t_begin(h, EVXGPU_T_INTER_SEARCH);
     evx_inter_search<<<grid, block, EVX_K2_SMEM, h->stream>>>(maps, h->src, h->g, h->d_inter, (quality >> 2) + 1, h->d_counters);
     t_end(h, EVXGPU_T_INTER_SEARCH);
