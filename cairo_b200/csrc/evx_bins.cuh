@@ -9,14 +9,16 @@
 // and (b) where its bins start, so it runs here, and the host receives ~20 KB of bins per
 // 1080p P-frame instead of 1.2 MB of coefficient records:
 //
-//   evx_bins_prepare   one CTA: for every macroblock the previous macroblock with a motion
-//                      vector / with coefficients (two running-maximum scans), and the refresh
-//                      of the persistent DC mirror (serialize.cpp:59-72: a copy block keeps the
-//                      DC values of the last frame that coded it)
+//   (evx_wavefront)    while it walks a row, K3 notes for every macroblock the previous one OF THAT
+//                      ROW with a motion vector / with coefficients, and each row's last such block
 //   evx_bins_lengths   one thread per ITEM (14 per macroblock: 8 table fields, 4 luma blocks,
 //                      U, V; laid out field-major = stream order): its bin count; per-tile sums
 //   evx_bins_emit      tile base = sum of the tiles before it, exclusive scan inside the tile,
 //                      then every item ORs its bins into the zeroed string
+// DC prediction (serialize.cpp:25-72) reads a neighbour's DC as of the end of this frame: from the
+// neighbour's record if it was coded in this frame, else from the persistent DC mirror -- a copy
+// block keeps the DC values of the last frame that coded it.  evx_bins_emit refreshes
+// the mirror entries of the blocks coded in this frame (entries nobody reads during this frame).
 //
 // Bin i of the slice is bit (i & 31) of 32-bit word (i >> 5): the layout the host coder
 // (entropy.cpp, abac_encode_bins) walks.
@@ -36,7 +38,9 @@ struct EvxBinsParams
     const EvxDesc *table;
     const int16_t *records;       // [nmb][384], slot = macroblock index (K3's layout)
     int16_t *dc;                  // persistent mirror: [4][nmb] = luma top-right DC, luma bottom-left DC, U DC, V DC
-    int *prev_motion, *prev_coded;   // [nmb]
+    const int *prev_motion, *prev_coded;   // [nmb] previous flagged macroblock of the same row, or -1 (written by K3)
+    const int *row_last;          // [2][mbh] last flagged macroblock per row, or -1
+    const int *row_records;       // [mbh] non-copy macroblocks per row
     uint32_t *len;                // [14*nmb]
     uint32_t *tile_sum;           // [ntiles]
     uint32_t *bins;               // the string, zeroed before evx_bins_emit
@@ -96,6 +100,23 @@ __device__ __forceinline__ void evx_bins_item_decode(uint32_t item, int nmb, int
     else { field = item < 13u * nmb ? 9 : 10; mb = (int) (item - (field == 9 ? 12u : 13u) * nmb); blk = 0; }
 }
 
+// previous flagged macroblock in raster order: in the row, else the last one of the nearest row above that has any
+__device__ __forceinline__ int evx_bins_prev(const int *prev_in_row, const int *row_last, int mb, int mbw)
+{
+    const int p = prev_in_row[mb];
+    if (p >= 0) return p;
+    for (int r = mb / mbw - 1; r >= 0; --r) { const int l = row_last[r]; if (l >= 0) return l; }
+    return -1;
+}
+
+// DC number k (0 luma top-right, 1 luma bottom-left, 2 U, 3 V) of macroblock nb as of the end of this frame
+__device__ __forceinline__ int evx_bins_dc(const EvxBinsParams &p, int nb, int k)
+{
+    if (p.table[nb].type() & EVX_T_COPY) return p.dc[(size_t) k * p.nmb + nb];
+    const int16_t *r = p.records + (size_t) nb * 384;
+    return r[k == 0 ? 8 : k == 1 ? 8 * 16 : k == 2 ? 256 : 320];
+}
+
 // stream.cpp:550-581 + serialize.cpp:10-23: one 8x8 block
 template <class Sink>
 __device__ __forceinline__ void evx_bins_block(Sink &s, const int16_t *blk, int stride, int last_dc)
@@ -137,7 +158,7 @@ __device__ __forceinline__ void evx_bins_item(Sink &s, const EvxBinsParams &p, u
     case 2: case 3:
         if (motion)
         {
-            const int pm = p.prev_motion[mb];
+            const int pm = evx_bins_prev(p.prev_motion, p.row_last, mb, p.mbw);
             int last = 0;
             if (pm >= 0) { const EvxDesc q = p.table[pm]; last = field == 2 ? q.mx() : q.my(); }
             const uint32_t x = evx_code_signed((int) (int16_t) ((field == 2 ? d.mx() : d.my()) - last));
@@ -150,7 +171,7 @@ __device__ __forceinline__ void evx_bins_item(Sink &s, const EvxBinsParams &p, u
     case 7:
         if (coded)
         {
-            const int pc = p.prev_coded[mb];
+            const int pc = evx_bins_prev(p.prev_coded, p.row_last + p.mbh, mb, p.mbw);
             const int last = pc >= 0 ? p.table[pc].q_index() : 0;
             const uint32_t x = evx_code_signed((int) (int16_t) (d.q_index() - last));
             s.put(evx_code_bins(x), evx_code_len(x));
@@ -164,15 +185,15 @@ __device__ __forceinline__ void evx_bins_item(Sink &s, const EvxBinsParams &p, u
             if (field == 8)
             {   // serialize.cpp:25-34: the four luma blocks and what each one's DC is predicted from
                 int last_dc;
-                if (b == 0) last_dc = bx >= 1 ? p.dc[0 * p.nmb + mb - 1] : (by >= 1 ? p.dc[1 * p.nmb + mb - p.mbw] : 0);
+                if (b == 0) last_dc = bx >= 1 ? evx_bins_dc(p, mb - 1, 0) : (by >= 1 ? evx_bins_dc(p, mb - p.mbw, 1) : 0);
                 else if (b == 3) last_dc = r[8 * 16];
                 else last_dc = r[0];
                 evx_bins_block(s, r + (b >> 1) * 8 * 16 + (b & 1) * 8, 16, last_dc);
             }
             else
             {
-                const int16_t *m = p.dc + (size_t) (field == 9 ? 2 : 3) * p.nmb;
-                const int last_dc = bx >= 1 ? m[mb - 1] : (by >= 1 ? m[mb - p.mbw] : 0);
+                const int k = field == 9 ? 2 : 3;
+                const int last_dc = bx >= 1 ? evx_bins_dc(p, mb - 1, k) : (by >= 1 ? evx_bins_dc(p, mb - p.mbw, k) : 0);
                 evx_bins_block(s, r + 256 + (field - 9) * 64, 8, last_dc);
             }
         }
@@ -181,52 +202,6 @@ __device__ __forceinline__ void evx_bins_item(Sink &s, const EvxBinsParams &p, u
 }
 
 // ---------------------------------------------------------------- kernels
-
-// Running maximum of (flag ? index : -1) in raster order, exclusive; and the DC mirror refresh.
-__global__ void __launch_bounds__(1024) evx_bins_prepare(EvxBinsParams p)
-{
-    __shared__ int s_w[2][32];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    int carry_m = -1, carry_c = -1, coded = 0;
-    for (int base = 0; base < p.nmb; base += 1024)
-    {
-        const int mb = base + tid;
-        int vm = -1, vc = -1;
-        if (mb < p.nmb)
-        {
-            const int type = p.table[mb].type();
-            if (type & EVX_T_MOTION) vm = mb;
-            if (!(type & EVX_T_COPY))
-            {
-                vc = mb;
-                const int16_t *r = p.records + (size_t) mb * 384;
-                p.dc[0 * p.nmb + mb] = r[8]; p.dc[1 * p.nmb + mb] = r[8 * 16]; p.dc[2 * p.nmb + mb] = r[256]; p.dc[3 * p.nmb + mb] = r[320];
-            }
-        }
-        int im = vm, ic = vc;                         // inclusive scans inside the warp
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const int a = __shfl_up_sync(0xFFFFFFFFu, im, o), c = __shfl_up_sync(0xFFFFFFFFu, ic, o);
-            if (lane >= o) { im = max(im, a); ic = max(ic, c); }
-        }
-        if (lane == 31) { s_w[0][warp] = im; s_w[1][warp] = ic; }
-        coded += __syncthreads_count(vc >= 0);
-        int pm = carry_m, pc = carry_c, tm = carry_m, tc = carry_c;
-        for (int w = 0; w < 32; ++w)
-        {
-            const int a = s_w[0][w], c = s_w[1][w];
-            if (w < warp) { pm = max(pm, a); pc = max(pc, c); }
-            tm = max(tm, a); tc = max(tc, c);
-        }
-        const int em = __shfl_up_sync(0xFFFFFFFFu, im, 1), ec = __shfl_up_sync(0xFFFFFFFFu, ic, 1);
-        if (lane > 0) { pm = max(pm, em); pc = max(pc, ec); }
-        if (mb < p.nmb) { p.prev_motion[mb] = pm; p.prev_coded[mb] = pc; }
-        carry_m = tm; carry_c = tc;
-        __syncthreads();
-    }
-    if (tid == 0) p.total[2] = (uint32_t) coded;
-}
 
 __global__ void __launch_bounds__(EVX_BINS_TILE) evx_bins_lengths(EvxBinsParams p)
 {
@@ -280,6 +255,18 @@ __global__ void __launch_bounds__(EVX_BINS_TILE) evx_bins_emit(EvxBinsParams p)
         const uint32_t total = off + n;
         p.total[0] = total;
         p.total[1] = total > p.cap_bits ? 1u : 0u;
+        uint32_t coded = 0;
+        for (int r = 0; r < p.mbh; ++r) coded += (uint32_t) p.row_records[r];
+        p.total[2] = coded;
+    }
+    if (item >= 7u * p.nmb && item < 8u * p.nmb)
+    {   // the quantiser-delta item exists once per macroblock: refresh the DC mirror of the coded ones
+        const int mb = (int) (item - 7u * p.nmb);
+        if (!(p.table[mb].type() & EVX_T_COPY))
+        {
+            const int16_t *r = p.records + (size_t) mb * 384;
+            p.dc[0 * p.nmb + mb] = r[8]; p.dc[1 * p.nmb + mb] = r[8 * 16]; p.dc[2 * p.nmb + mb] = r[256]; p.dc[3 * p.nmb + mb] = r[320];
+        }
     }
     if (n == 0 || off + n > p.cap_bits) return;      // an overflowing string is re-emitted into a larger buffer by the host side
     EvxBinSink s;

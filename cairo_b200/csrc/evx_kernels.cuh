@@ -530,6 +530,9 @@ struct EvxK3Params
     int *sync;                     // [0] row ticket, [1] total records, [2..] progress[mbh]
     unsigned long long *counters;
     long long *prof;               // optional [mbh][6] per-row phase cycle sums (NULL in production)
+    // for K8 (evx_bins.cuh): what serialize_slice's deltas and DC predictions refer to
+    int *prev_motion, *prev_coded; // [nmb] previous macroblock OF THE SAME ROW with a motion vector / with coefficients, or -1
+    int *row_last;                 // [2][mbh] last such macroblock of each row, or -1
 };
 
 // ------------------------------------------------------------------ K7: pack the non-copy macroblocks' records densely, raster order

@@ -51,6 +51,7 @@ struct EvxK3Smem
     int2 cand2[2][16];                        // full-pel rounds: raw {sad, mad} per cell
     uint64_t full[2], fullb[2], full2[2], empty[2];   // full: block data; fullb: window columns <= n+1; full2: column n+2
     int row;
+    int last_motion, last_coded;              // K8 bookkeeping (thread 0)
 };
 
 __device__ __forceinline__ void evx_mbar_arrive(uint64_t *bar)
@@ -277,6 +278,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     const int lc = lane < 9 ? lane : 0, ldx = lc % 3 - 1, ldy = lc / 3;
 
     uint32_t n_full = 0, n_sub = 0;
+    if (tid == 0) { S.last_motion = -1; S.last_coded = -1; }      // running, for K8; thread 0 only
     int row_records = 0;
     long long prof[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }, tprev = clock64();
 #ifdef EVX_K3_TRACE
@@ -478,7 +480,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         if (type & EVX_T_COPY)
         {   // copy blocks: the prediction is the reconstruction; no coefficients (encode.cpp:155-157)
             for (int e = tid; e < 384; e += EVX_K3_CT) store_recon(e, sh.pred[e]);
-            if (tid == 0) p.table[mb] = d;
+            if (tid == 0) { p.table[mb] = d; p.prev_motion[mb] = S.last_motion; p.prev_coded[mb] = S.last_coded; }
         }
         else
         {
@@ -539,7 +541,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 rec[evx_record_index(e)] = (int16_t) qv;
                 sh.bufb[e] = (int16_t) evx_dequant(qv, e & 63, mode, qp, p.linear, sh.qmi, sh.qmt);
             }
-            if (tid == 0) { d.set_q(qp, var); p.table[mb] = d; }
+            if (tid == 0) { d.set_q(qp, var); p.table[mb] = d; p.prev_motion[mb] = S.last_motion; p.prev_coded[mb] = S.last_coded; S.last_coded = mb; }
             evx_compute_sync();
             // inverse transform (transform.cpp:330-366, 418-433): columns, then rows + prediction
             for (int e = tid; e < 384; e += EVX_K3_CT)
@@ -564,6 +566,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             }
             row_records++;
         }
+        if (tid == 0 && (type & EVX_T_MOTION)) S.last_motion = mb;
         evx_compute_sync();
         EVX_K3_PROF(4);
         EVX_K3_STAMP(2);
@@ -575,6 +578,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     if (tid == 0)
     {
         p.row_records[by] = row_records;
+        p.row_last[by] = S.last_motion; p.row_last[g.mbh + by] = S.last_coded;
         if (p.prof) for (int k = 0; k < 10; ++k) p.prof[by * 10 + k] = prof[k];
         atomicAdd(&p.counters[2], (unsigned long long) n_full);
         atomicAdd(&p.counters[3], (unsigned long long) n_sub);

@@ -84,7 +84,7 @@ struct evxgpu_handle
     // K8: the slice as a bin string (evx_bins.cuh)
     int out_mode;                   // 0 table+records, 1 bins, 2 both
     int16_t *d_dc;                  // persistent DC mirror [4][nmb]
-    int *d_prev;                    // prev_motion[nmb], prev_coded[nmb]
+    int *d_prev;                    // prev_motion[nmb], prev_coded[nmb], row_last[2][mbh] (written by K3)
     uint32_t *d_len, *d_tile_sum, *d_bins, *d_bins_total;
     uint32_t bins_cap_bits;         // capacity of d_bins
     uint32_t *h_bins;               // pinned: [0..3] total, overflow, non-copy count; [4..] the string
@@ -194,7 +194,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
         h->bins_cap_bits = (uint32_t) std::max<size_t>((size_t) h->nmb * 256, 1u << 16);
         h->h_bins_cap_bits = h->bins_cap_bits;
         ok = ok && cudaMalloc(&h->d_dc, (size_t) h->nmb * 4 * 2) == cudaSuccess;
-        ok = ok && cudaMalloc(&h->d_prev, (size_t) h->nmb * 2 * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&h->d_prev, ((size_t) h->nmb * 2 + (size_t) h->g.mbh * 2) * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&h->d_len, (size_t) EVX_BINS_ITEMS * h->nmb * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&h->d_tile_sum, ntiles * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&h->d_bins, (size_t) h->bins_cap_bits / 8 + 8) == cudaSuccess;
@@ -351,6 +351,7 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
     p.frame_type = frame_type; p.quality = quality; p.frame_index = index;
     p.inter = h->d_inter; p.table = h->d_table; p.records = h->d_records; p.row_records = h->d_row_records;
     p.sync = h->d_sync; p.counters = h->d_counters; p.prof = h->d_prof;
+    p.prev_motion = h->d_prev; p.prev_coded = h->d_prev + h->nmb; p.row_last = h->d_prev + 2 * h->nmb;
     CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
     t_begin(h, EVXGPU_T_WAVEFRONT);
     // one CTA per macroblock row; rows are claimed by ticket, so any residency is deadlock-free
@@ -384,7 +385,7 @@ static EvxBinsParams bins_params(evxgpu_handle *h)
 {
     EvxBinsParams p;
     p.table = h->d_table; p.records = h->d_records; p.dc = h->d_dc;
-    p.prev_motion = h->d_prev; p.prev_coded = h->d_prev + h->nmb;
+    p.prev_motion = h->d_prev; p.prev_coded = h->d_prev + h->nmb; p.row_last = h->d_prev + 2 * h->nmb; p.row_records = h->d_row_records;
     p.len = h->d_len; p.tile_sum = h->d_tile_sum; p.bins = h->d_bins; p.total = h->d_bins_total;
     p.cap_bits = h->bins_cap_bits;
     p.mbw = h->g.mbw; p.mbh = h->g.mbh; p.nmb = h->nmb;
@@ -402,9 +403,8 @@ static int launch_bins(evxgpu_handle *h, bool emit_only)
     t_begin(h, EVXGPU_T_BINS);
     if (!emit_only)
     {
-        evx_bins_prepare<<<1, 1024, 0, h->stream>>>(p);
         evx_bins_lengths<<<ntiles, EVX_BINS_TILE, 0, h->stream>>>(p);
-        h->launches += 2;
+        h->launches++;
     }
     evx_bins_emit<<<ntiles, EVX_BINS_TILE, 0, h->stream>>>(p);
     t_end(h, EVXGPU_T_BINS);
