@@ -31,6 +31,8 @@ def lib():
     L.evx1c_encoder_insert_intra.argtypes = [vp]
     L.evx1c_encoder_set_quality.argtypes = [vp, i32]
     L.evx1c_encoder_encode.argtypes = [vp, vp, u32, u32, vp, u32, C.POINTER(u32)]
+    L.evx1c_encoder_submit.argtypes = [vp, vp, u32, u32]
+    L.evx1c_encoder_collect.argtypes = [vp, vp, u32, C.POINTER(u32)]
     L.evx1c_encoder_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     L.evx1c_decoder_create.restype = vp
     L.evx1c_decoder_create.argtypes = [i32] * 3
@@ -79,22 +81,44 @@ class evx1_encoder:
     def set_quality(self, quality):
         return self.L.evx1c_encoder_set_quality(self.h, int(quality))
 
-    def encode(self, image, out=None):
-        """image: uint8 (height, width, 3) R8G8B8, host memory (numpy array or a raw pointer with
-        width/height given through `image=(ptr, width, height)`).  Returns (bytes, nbits)."""
+    def _frame(self, image):
         if isinstance(image, tuple):
             ptr, w, h = image
         else:
             image = np.ascontiguousarray(image)
             h, w, _ = image.shape
             ptr = _p(image)
+            self._keep = image               # submit(): the frame must outlive the call
         cap = w * h * 6 + 4096
         if self._out is None or self._out.size != cap:
             self._out = np.zeros(cap, dtype=np.uint8)
+        return ptr, w, h, cap
+
+    def encode(self, image, out=None):
+        """image: uint8 (height, width, 3) R8G8B8, host memory (numpy array or a raw pointer with
+        width/height given through `image=(ptr, width, height)`).  Returns (bytes, nbits)."""
+        ptr, w, h, cap = self._frame(image)
         bits = C.c_uint32(0)
         st = self.L.evx1c_encoder_encode(self.h, ptr, w, h, _p(self._out), cap, C.byref(bits))
         if st != 0:
             raise RuntimeError(f"evx1_encoder::encode failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
+        return self._out[:(bits.value + 7) // 8], bits.value
+
+    def submit(self, image):
+        """First half of encode(): queue the frame on the device.  See evx1.h for the pairing rules."""
+        ptr, w, h, _ = self._frame(image)
+        st = self.L.evx1c_encoder_submit(self.h, ptr, w, h)
+        if st != 0:
+            raise RuntimeError(f"evx1_encoder::submit failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
+
+    def collect(self):
+        """Second half of encode(): (bytes, nbits) of the oldest uncollected frame."""
+        if self._out is None:
+            raise RuntimeError("evx1_encoder::collect failed with status 15: nothing submitted")
+        bits = C.c_uint32(0)
+        st = self.L.evx1c_encoder_collect(self.h, _p(self._out), self._out.size, C.byref(bits))
+        if st != 0:
+            raise RuntimeError(f"evx1_encoder::collect failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
         return self._out[:(bits.value + 7) // 8], bits.value
 
     def stats(self):

@@ -92,6 +92,8 @@ struct evxgpu_handle
     uint32_t bins_prefix_bits;      // how much of the string the submit already copied
     cudaEvent_t ev_out;
     bool pending_bins;
+    uint32_t bins_last_total;       // bin count of the previous frame (sizes the optimistic head copy)
+    uint64_t d2h_bytes;             // device-to-host bytes of the frame in flight / last collected
 };
 
 static size_t plane_elems(const EvxGeom &g) { return (size_t) g.w * g.h * 3 / 2; }
@@ -260,6 +262,8 @@ int evxgpu_reset(evxgpu_handle *h)
 
 int evxgpu_block_count(const evxgpu_handle *h) { return h ? h->nmb : 0; }
 int evxgpu_synchronize(evxgpu_handle *h) { if (!h) return 1; CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream)); return 0; }
+uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h) { return h ? h->d2h_bytes : 0; }
+
 uint64_t evxgpu_launch_count(const evxgpu_handle *h) { return h ? h->launches : 0; }
 
 int evxgpu_upload(evxgpu_handle *h, void *dst_device, const void *src_host, uint64_t bytes)
@@ -435,6 +439,7 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
         d_rgb = h->d_rgb;
     }
     int rc;
+    h->d2h_bytes = 0;
     if ((rc = launch_convert_in(h, d_rgb))) return rc;
     if (frame_type == 1 && (rc = launch_inter_search(h, frame_index, quality))) return rc;
     if ((rc = launch_wavefront(h, frame_type, frame_index, quality))) return rc;
@@ -443,14 +448,18 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     {
         CK(cudaMemcpyAsync(h->h_sync, h->d_sync, 8, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(h->h_table, h->d_table, (size_t) h->nmb * 16, cudaMemcpyDeviceToHost, h->stream));
+        h->d2h_bytes += 8 + (size_t) h->nmb * 16;
     }
     if (h->out_mode != 0)
     {
         if ((rc = launch_bins(h, false))) return rc;
         // the bin count and, optimistically, the head of the string in the same breath
-        h->bins_prefix_bits = std::min<uint32_t>(std::min(h->bins_cap_bits, h->h_bins_cap_bits), 1u << 19);
+        // (sized from the previous frame: consecutive slices are of similar length; a longer one costs a second copy)
+        const uint32_t guess = h->bins_last_total ? ((h->bins_last_total + h->bins_last_total / 4 + 8192) & ~63u) : 1u << 19;
+        h->bins_prefix_bits = std::min<uint32_t>(std::min(h->bins_cap_bits, h->h_bins_cap_bits), std::min<uint32_t>(guess, 1u << 22));
         CK(cudaMemcpyAsync(h->h_bins, h->d_bins_total, 16, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(h->h_bins + 4, h->d_bins, h->bins_prefix_bits / 8, cudaMemcpyDeviceToHost, h->stream));
+        h->d2h_bytes += 16 + h->bins_prefix_bits / 8;
         h->pending_bins = true;
     }
     CK(cudaEventRecord(h->ev_out, h->stream));
@@ -491,8 +500,10 @@ int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins_out, uint
         const size_t from = h->bins_prefix_bits / 8, to = ((size_t) total + 7) / 8;
         CK(cudaMemcpyAsync((uint8_t *) (h->h_bins + 4) + from, (const uint8_t *) h->d_bins + from, to - from, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        h->d2h_bytes += to - from;
     }
     h->pending_bins = false;
+    h->bins_last_total = total;
     if (h->out_mode == 1) h->pending_encode = false;
     *bins_out = reinterpret_cast<const uint64_t *>(h->h_bins + 4);
     *nbins = total;
@@ -518,6 +529,7 @@ int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_
         // (asynchronous DMA when that buffer is pinned, see evxgpu_host_alloc)
         CK(cudaMemcpyAsync(records_out, h->d_dense, (size_t) n * 384 * 2, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        h->d2h_bytes += (size_t) n * 384 * 2;
     }
     return 0;
 }

@@ -6,7 +6,9 @@
 //
 // Additions (not in the reference): evx1_config + create_encoder_ex/create_decoder_ex make the
 // reference's compile-time switches (config.h:38-53) run-time values, bit_stream gains
-// query_read_index()/query_write_index(), and the encoder exposes last_frame_stats().
+// query_read_index()/query_write_index(), the encoder exposes last_frame_stats(), and encode() is
+// also available as its two halves, submit() + collect(), so that the host entropy stage of frame n
+// overlaps the device's work on frame n+1 (one frame of latency, the same bytes).
 #ifndef CAIRO_B200_EVX1_H
 #define CAIRO_B200_EVX1_H
 
@@ -131,6 +133,17 @@ public:
     virtual evx_status encode(void *image, uint32 width, uint32 height, bit_stream *output) = 0;   // R8G8B8 in, appends to output
     virtual evx_status peek(EVX_PEEK_STATE peek_state, void *output) = 0;              // debug views: not implemented here
     virtual evx_status last_frame_stats(evx1_frame_stats *out) = 0;                    // addition
+
+    // additions: encode() == submit() + collect().  submit queues the frame on the device (colour
+    // conversion, motion search, transform/quantisation, reconstruction, deblocking, binarisation) and
+    // returns; collect appends what encode() would have appended for the oldest uncollected frame (stream
+    // header on the first frame, frame descriptor, slice).  One frame may be uncollected when submit is
+    // called: submit(n+1) first waits for frame n's device results, then starts frame n+1, so collect(n)
+    // runs the entropy coder while the device encodes frame n+1.  `image` must stay unchanged until the next
+    // submit() or collect() returns.  A second uncollected frame makes submit (and any uncollected frame
+    // makes encode) return EVX_ERROR_NOT_READY; collect with nothing submitted returns the same.
+    virtual evx_status submit(void *image, uint32 width, uint32 height) = 0;
+    virtual evx_status collect(bit_stream *output) = 0;
 };
 
 class evx1_decoder

@@ -52,6 +52,24 @@ int evx1c_encoder_encode(evx1c_encoder *e, const uint8_t *rgb, uint32_t width, u
     return st;
 }
 
+int evx1c_encoder_submit(evx1c_encoder *e, const uint8_t *rgb, uint32_t width, uint32_t height)
+{
+    if (!e) return EVX_ERROR_INVALIDARG;
+    return e->enc->submit(const_cast<uint8_t *>(rgb), width, height);
+}
+
+int evx1c_encoder_collect(evx1c_encoder *e, uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits)
+{
+    if (!e || !out || !out_bits) return EVX_ERROR_INVALIDARG;
+    if (e->bs.query_capacity() != out_cap_bytes * 8u) e->bs.resize_capacity(out_cap_bytes * 8u);
+    e->bs.empty();
+    int st = e->enc->collect(&e->bs);
+    uint32 bits = e->bs.query_occupancy();
+    memcpy(out, e->bs.query_data(), (bits + 7) >> 3);
+    *out_bits = bits;
+    return st;
+}
+
 int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks, uint32_t *d2h_bytes)
 {
     if (!e) return EVX_ERROR_INVALIDARG;

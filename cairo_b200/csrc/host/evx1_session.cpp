@@ -67,10 +67,23 @@ class encoder_session : public evx1_encoder
     stream_header header_;
     evxgpu_handle *gpu_;
     slice_writer writer_;
-    std::vector<evxgpu_block_desc> table_;
-    std::vector<int16> records_;
     evx1_frame_stats stats_;
     bool device_bins_;
+
+    // A frame between submit() and collect() is either on the device (its kernels and copies are queued
+    // or running) or retired: its per-macroblock results are on the host, waiting for the entropy stage.
+    struct pending_frame
+    {
+        bool valid, first;
+        frame_desc desc;
+        double t_submit, gpu_ms;
+        uint32 n_noncopy, d2h_bytes;
+        uint64_t nbins;
+    };
+    pending_frame on_device_, retired_;
+    std::vector<uint64_t> bins_;                   // retired frame, bin output
+    std::vector<evxgpu_block_desc> table_;         // retired frame, table + records output
+    std::vector<int16> records_;
 
     void clear_frame()          // clear_frame, common.cpp:50-64
     {
@@ -104,11 +117,40 @@ class encoder_session : public evx1_encoder
         return EVX_SUCCESS;
     }
 
+    // Waits for the frame on the device and moves its results into session memory, which frees the device
+    // library's staging buffers for the next submit.
+    evx_status retire()
+    {
+        pending_frame f = on_device_;
+        on_device_.valid = false;
+        int rc;
+        if (device_bins_)
+        {
+            const uint64_t *bins = NULL;
+            rc = evxgpu_encode_collect_bins(gpu_, &bins, &f.nbins, &f.n_noncopy);
+            if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+            const size_t words = (size_t) ((f.nbins + 63) / 64);
+            if (bins_.size() < words) bins_.resize(words + words / 2 + 64);
+            memcpy(bins_.data(), bins, words * 8);
+        }
+        else
+        {
+            rc = evxgpu_encode_collect(gpu_, table_.data(), records_.data(), &f.n_noncopy);
+            if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+        }
+        f.d2h_bytes = (uint32) evxgpu_d2h_bytes(gpu_);
+        f.gpu_ms = now_ms() - f.t_submit;
+        retired_ = f;
+        return EVX_SUCCESS;
+    }
+
 public:
     explicit encoder_session(const evx1_config &cfg) : cfg_(cfg), initialized_(false), gpu_(NULL)
     {
         memset(&stats_, 0, sizeof(stats_));
         memset(&header_, 0, sizeof(header_));
+        memset(&on_device_, 0, sizeof(on_device_));
+        memset(&retired_, 0, sizeof(retired_));
         clear_frame();
     }
     ~encoder_session() { clear(); }
@@ -117,7 +159,8 @@ public:
     {
         if (!initialized_) return EVX_SUCCESS;
         clear_frame();
-        if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }
+        if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }      // drains the stream; uncollected frames are dropped
+        on_device_.valid = retired_.valid = false;
         initialized_ = false;
         return EVX_SUCCESS;
     }
@@ -126,54 +169,77 @@ public:
 
     evx_status set_quality(uint8 quality) { frame_.quality = (uint16) clip(quality, 1, 31); return EVX_SUCCESS; }   // evx1enc.cpp:53-64
 
-    evx_status encode(void *image, uint32 width, uint32 height, bit_stream *output)        // evx1enc.cpp:92-156
+    // First half of encode (evx1enc.cpp:92-156 up to and including the pixel part of engine_encode_frame,
+    // encode.cpp:205-232): the frame goes to the device and the call returns.  The frame descriptor
+    // (type, index, quality) is the session's state at this moment, exactly as encode() would have used it.
+    evx_status submit(void *image, uint32 width, uint32 height)
     {
-        if (!output || !width || !height || !image) return EVX_ERROR_INVALIDARG;
+        if (!width || !height || !image) return EVX_ERROR_INVALIDARG;
+        if (on_device_.valid && retired_.valid) return EVX_ERROR_NOT_READY;      // two frames uncollected
+        bool first = false;
         if (!initialized_)
         {
             if ((width & 1) || (height & 1) || width > 0xFFFF || height > 0xFFFF) return EVX_ERROR_EXECUTION_FAILURE;   // convert.cpp:126-130
             evx_status st = initialize(width, height);
             if (evx_failed(st)) return EVX_ERROR_EXECUTION_FAILURE;
-            if (evx_failed(output->write_bytes(&header_, sizeof(header_)))) return EVX_ERROR_EXECUTION_FAILURE;
+            first = true;
         }
         if (width != header_.frame_width || height != header_.frame_height) return EVX_ERROR_INVALID_RESOURCE;
-        if (evx_failed(output->write_bytes(&frame_, sizeof(frame_)))) return EVX_ERROR_EXECUTION_FAILURE;
-
-        // engine_encode_frame, encode.cpp:205-232
-        double t0 = now_ms();
+        if (on_device_.valid)
+        {
+            evx_status st = retire();
+            if (evx_failed(st)) return st;
+        }
+        const double t0 = now_ms();
         int rc = evxgpu_encode_submit(gpu_, static_cast<const uint8 *>(image), 0, (int) frame_.type, frame_.index, (int) frame_.quality);
         if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        uint32 n_noncopy = 0, bits = 0;
-        double t1;
-        if (device_bins_)
-        {
-            const uint64_t *bins = NULL;
-            uint64_t nbins = 0;
-            rc = evxgpu_encode_collect_bins(gpu_, &bins, &nbins, &n_noncopy);
-            if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-            t1 = now_ms();
-            bits = writer_.serialize_bins(bins, nbins);
-            stats_.d2h_bytes = (uint32) ((nbins + 7) / 8 + 16);
-        }
-        else
-        {
-            rc = evxgpu_encode_collect(gpu_, table_.data(), records_.data(), &n_noncopy);
-            if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-            t1 = now_ms();
-            bits = writer_.serialize(table_.data(), records_.data(), n_noncopy);
-            stats_.d2h_bytes = (uint32) (table_.size() * 16 + (size_t) n_noncopy * 768 + 8);
-        }
-        if (!bits) return EVX_ERROR_EXECUTION_FAILURE;
-        evx_status wst = output->write_bits(const_cast<uint8 *>(writer_.data()), bits);
-        double t2 = now_ms();
-        stats_.gpu_ms = t1 - t0; stats_.entropy_ms = t2 - t1; stats_.slice_bits = bits; stats_.noncopy_blocks = n_noncopy;
-        // serialize_slice's write failures are ignored by the reference (SURVEY 8b); report ours
-        if (evx_failed(wst)) return EVX_ERROR_EXECUTION_FAILURE;
+        memset(&on_device_, 0, sizeof(on_device_));
+        on_device_.valid = true; on_device_.first = first; on_device_.desc = frame_; on_device_.t_submit = t0;
 
         frame_.type = 1;                                                                   // EVX_ALLOW_INTER_FRAMES
         if (cfg_.periodic_intra > 0 && 0 == ((frame_.index + 1) % (uint32) cfg_.periodic_intra)) insert_intra();
         frame_.index++;
         return EVX_SUCCESS;
+    }
+
+    // Second half: stream header (first frame only), frame descriptor and the entropy-coded slice of the
+    // oldest uncollected frame are appended to output -- the bytes encode() appends.
+    evx_status collect(bit_stream *output)
+    {
+        if (!output) return EVX_ERROR_INVALIDARG;
+        if (!retired_.valid)
+        {
+            if (!on_device_.valid) return EVX_ERROR_NOT_READY;
+            evx_status st = retire();
+            if (evx_failed(st)) return st;
+        }
+        const pending_frame f = retired_;
+        retired_.valid = false;
+        if (f.first && evx_failed(output->write_bytes(&header_, sizeof(header_)))) return EVX_ERROR_EXECUTION_FAILURE;
+        frame_desc desc = f.desc;
+        if (evx_failed(output->write_bytes(&desc, sizeof(desc)))) return EVX_ERROR_EXECUTION_FAILURE;
+        const double t1 = now_ms();
+        uint32 bits = device_bins_ ? writer_.serialize_bins(bins_.data(), f.nbins)
+                                   : writer_.serialize(table_.data(), records_.data(), f.n_noncopy);
+        if (!bits) return EVX_ERROR_EXECUTION_FAILURE;
+        evx_status wst = output->write_bits(const_cast<uint8 *>(writer_.data()), bits);
+        stats_.gpu_ms = f.gpu_ms; stats_.entropy_ms = now_ms() - t1; stats_.slice_bits = bits;
+        stats_.noncopy_blocks = f.n_noncopy; stats_.d2h_bytes = f.d2h_bytes;
+        // serialize_slice's write failures are ignored by the reference (SURVEY 8b); report ours
+        if (evx_failed(wst)) return EVX_ERROR_EXECUTION_FAILURE;
+        return EVX_SUCCESS;
+    }
+
+    evx_status encode(void *image, uint32 width, uint32 height, bit_stream *output)        // evx1enc.cpp:92-156
+    {
+        if (!output || !width || !height || !image) return EVX_ERROR_INVALIDARG;
+        if (on_device_.valid || retired_.valid) return EVX_ERROR_NOT_READY;       // finish the pipelined frames with collect() first
+        const frame_desc before = frame_;
+        evx_status st = submit(image, width, height);
+        if (evx_failed(st)) return st;
+        st = collect(output);
+        if (evx_failed(st)) frame_ = before;                 // the reference leaves its frame counter alone on failure
+        return st;
     }
 
     evx_status peek(EVX_PEEK_STATE, void *) { return EVX_ERROR_NOTIMPL; }                  // debug visualisers: out of scope

@@ -25,6 +25,11 @@ int evx1c_encoder_set_quality(evx1c_encoder *e, int quality);    /* evx1_encoder
 /* evx1_encoder::encode into a fresh bit_stream; copies ceil(out_bits/8) bytes to out. */
 int evx1c_encoder_encode(evx1c_encoder *e, const uint8_t *rgb, uint32_t width, uint32_t height,
                          uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits);
+/* evx1_encoder::submit / collect (additions of this build: encode == submit + collect; submit(n+1) before
+ * collect(n) overlaps the host entropy stage of frame n with the device's work on frame n+1).  rgb must stay
+ * unchanged until the next submit or collect returns. */
+int evx1c_encoder_submit(evx1c_encoder *e, const uint8_t *rgb, uint32_t width, uint32_t height);
+int evx1c_encoder_collect(evx1c_encoder *e, uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits);
 int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks, uint32_t *d2h_bytes);
 
 evx1c_decoder *evx1c_decoder_create(int device, int linear_quant, int deblocking);

@@ -124,6 +124,8 @@ int evxgpu_get_counters(evxgpu_handle *h, uint64_t *fullpel, uint64_t *subpel, i
 /* the same split by kernel: out4 = { inter full-pel, inter sub-pel, intra full-pel, intra sub-pel } */
 int evxgpu_get_counters_split(evxgpu_handle *h, uint64_t *out4, int reset);
 uint64_t evxgpu_launch_count(const evxgpu_handle *h);
+/* bytes copied device -> host for the last submitted frame, as queued by submit and the collect calls so far */
+uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h);
 /* debug: per-row phase cycle sums of the encoder wavefront kernel, 6 x int64 per macroblock row */
 int evxgpu_debug_profile(evxgpu_handle *h, int enable, long long *out_host);
 /* tuning knob: number of persistent CTAs of the decoder's wavefront kernel (0 = default) */

@@ -123,3 +123,57 @@ def test_1080p_round_trip_property():
         err = np.abs(rgb.astype(np.int32) - f.astype(np.int32)).mean()
         assert err < 6.0, (t, err)                # lossy but close at quality 16
         prev = rgb
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_pipelined_submit_collect_matches_golden_streams(name):
+    """submit(n+1) before collect(n): the frames leave one call later and are the same bytes, including
+    set_quality / insert_intra issued between the two halves (they belong to the next submit)."""
+    from cairo_b200 import api
+    g = G.Golden(name)
+    enc = api.evx1_encoder(ref_count=g.R, linear_quant=g.linear, deblocking=g.deblocking)
+    enc.set_quality(g.q)
+    frames = [np.ascontiguousarray(g.rgb(t)) for t in range(g.frames)]
+    enc.submit(frames[0])
+    for t in range(1, g.frames + 1):
+        if t < g.frames:
+            if g.is_intra(t):
+                enc.insert_intra()
+            enc.submit(frames[t])
+        data, bits = enc.collect()
+        gd, gb = g.stream(t - 1)
+        assert _streams_equal(data, bits, gd, gb, t == 1), (name, t - 1, bits, gb)
+
+
+def test_pipelined_1080p_equals_synchronous_and_state_rules():
+    from cairo_b200 import api
+    w, h, n = 1920, 1080, 6
+    frames = [synth.frame(w, h, t, 3, "moving") for t in range(n)]
+    a = api.evx1_encoder(ref_count=2)
+    a.set_quality(16)
+    sync = []
+    for t in range(n):
+        d, b = a.encode(frames[t])
+        sync.append((d.copy(), b))
+    p = api.evx1_encoder(ref_count=2)
+    p.set_quality(16)
+    with pytest.raises(RuntimeError):
+        p.collect()                               # nothing submitted: EVX_ERROR_NOT_READY
+    p.submit(frames[0])
+    with pytest.raises(RuntimeError):
+        p.encode(frames[1])                       # encode() with a frame uncollected
+    p.submit(frames[1])
+    with pytest.raises(RuntimeError):
+        p.submit(frames[2])                       # a second uncollected frame
+    out = [p.collect()]
+    out[0] = (out[0][0].copy(), out[0][1])
+    for t in range(2, n):
+        p.submit(frames[t])
+        d, b = p.collect()
+        out.append((d.copy(), b))
+    d, b = p.collect()
+    out.append((d.copy(), b))
+    d, b = p.encode(frames[0])                    # back to the synchronous call once drained
+    assert b > 0
+    for t in range(n):
+        assert out[t][1] == sync[t][1] and (out[t][0] == sync[t][0]).all(), t
