@@ -591,21 +591,31 @@ __global__ void __launch_bounds__(EVX_K3_NT, 2) evx_wavefront(const __grid_const
     EvxK3Smem &S = *reinterpret_cast<EvxK3Smem *>(evx_k3_smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (tid == 0)
-    {
-        // rows are claimed in order: a CTA only ever waits on rows claimed before its own
-        S.row = atomicAdd(&p.sync[0], 1);
-        evx_mbar_init(&S.full[0], 1); evx_mbar_init(&S.full[1], 1);
-        evx_mbar_init(&S.fullb[0], 1); evx_mbar_init(&S.fullb[1], 1);
-        evx_mbar_init(&S.full2[0], 1); evx_mbar_init(&S.full2[1], 1);
-        evx_mbar_init(&S.empty[0], 1); evx_mbar_init(&S.empty[1], 1);
-    }
     evx_init_tables(S.sh, tid, EVX_K3_NT);
-    __syncthreads();
-    const int by = S.row;
-    if (by >= p.g.mbh) return;
+    // Persistent over rows: row r can only be active during macroblock steps [3r, 3r + W), so at most
+    // ceil(W/3) rows are in flight at any time and that many CTAs carry the whole frame (the host sizes the
+    // grid so); a CTA that finished its row claims the next unclaimed one.  Rows are claimed in order: a
+    // CTA only ever waits on rows claimed before its own, by CTAs that are running.
+    for (bool first = true;; first = false)
+    {
+        if (tid == 0)
+        {
+            S.row = atomicAdd(&p.sync[0], 1);
+            auto rearm = [&](uint64_t *bar)
+            {
+                if (!first) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(evx_smem_addr(bar)) : "memory");
+                evx_mbar_init(bar, 1);
+            };
+            rearm(&S.full[0]); rearm(&S.full[1]); rearm(&S.fullb[0]); rearm(&S.fullb[1]);
+            rearm(&S.full2[0]); rearm(&S.full2[1]); rearm(&S.empty[0]); rearm(&S.empty[1]);
+        }
+        __syncthreads();
+        const int by = S.row;
+        if (by >= p.g.mbh) return;
 
-    if (warp < EVX_K3_CW) evx_k3_compute(S, p, by, tid);
-    else if (warp == EVX_K3_CW) evx_k3_block_loader(S, p, by, lane);
-    else if (warp == EVX_K3_CW + 1) evx_k3_column_loader(S, p, by, lane);
+        if (warp < EVX_K3_CW) evx_k3_compute(S, p, by, tid);
+        else if (warp == EVX_K3_CW) evx_k3_block_loader(S, p, by, lane);
+        else if (warp == EVX_K3_CW + 1) evx_k3_column_loader(S, p, by, lane);
+        __syncthreads();      // every role has left the row: its barriers and S.row may be reused
+    }
 }

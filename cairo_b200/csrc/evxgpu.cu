@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -79,6 +80,7 @@ struct evxgpu_handle
     uint64_t launches;
     bool pending_encode, pending_decode;
     int wave_grid;
+    int enc_grid;                   // persistent CTAs of the encoder's wavefront kernel
     long long *d_prof;
 
     // K8: the slice as a bin string (evx_bins.cuh)
@@ -239,6 +241,10 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
             if (cudaEventCreate(&h->ev[k][e]) != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaEventCreate"); }
     // enough CTAs to cover the widest wavefront plus a few to prefetch the next step
     h->wave_grid = std::min(h->nmb, 148 * 8);      // persistent CTAs of the decoder kernel
+    // encoder wavefront: at most ceil(W/3) rows are ever active at once (row r runs during steps [3r, 3r+W));
+    // a few spare CTAs absorb the row-to-row hand-over
+    h->enc_grid = std::min(h->g.mbh, (h->g.mbw + 2) / 3 + 4);
+    if (const char *e = getenv("EVXGPU_ENC_GRID")) { int v = atoi(e); if (v > 0) h->enc_grid = std::min(h->g.mbh, v); }      // measurements
     int rc = evxgpu_reset(h);
     if (rc) { evxgpu_destroy(h); return rc; }
     *out = h;
@@ -358,8 +364,8 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
     p.prev_motion = h->d_prev; p.prev_coded = h->d_prev + h->nmb; p.row_last = h->d_prev + 2 * h->nmb;
     CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
     t_begin(h, EVXGPU_T_WAVEFRONT);
-    // one CTA per macroblock row; rows are claimed by ticket, so any residency is deadlock-free
-    evx_wavefront<<<h->g.mbh, EVX_K3_NT, sizeof(EvxK3Smem), h->stream>>>(p);
+    // one CTA per macroblock row in flight; rows are claimed by ticket, so any residency is deadlock-free
+    evx_wavefront<<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), h->stream>>>(p);
     h->launches++;
     if (h->out_mode != 1)
     {
@@ -660,6 +666,14 @@ int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas)
     if (!h) return 1;
     if (ctas <= 0) ctas = 148 * 8;
     h->wave_grid = std::max(1, std::min(h->nmb, ctas));
+    return 0;
+}
+
+int evxgpu_set_encode_grid(evxgpu_handle *h, int ctas)
+{
+    if (!h) return 1;
+    if (ctas <= 0) ctas = (h->g.mbw + 2) / 3 + 4;
+    h->enc_grid = std::max(1, std::min(h->g.mbh, ctas));
     return 0;
 }
 

@@ -65,6 +65,9 @@ def lib():
     L.evxgpu_enable_timing.argtypes = [vp, i32]
     L.evxgpu_get_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), i32]
     L.evxgpu_get_counters_split.argtypes = [vp, C.POINTER(C.c_uint64), i32]
+    L.evxgpu_set_encode_grid.argtypes = [vp, i32]
+    L.evxgpu_d2h_bytes.restype = C.c_uint64
+    L.evxgpu_d2h_bytes.argtypes = [vp]
     L.evxgpu_launch_count.restype = C.c_uint64
     L.evxgpu_launch_count.argtypes = [vp]
     L.evxgpu_measure_int_peak.restype = C.c_double
@@ -202,6 +205,9 @@ class Pipeline:
         out = (C.c_uint64 * 4)()
         _check(self.L.evxgpu_get_counters_split(self.h, out, int(reset)), "evxgpu_get_counters_split")
         return tuple(int(v) for v in out)
+
+    def set_encode_grid(self, ctas):
+        _check(self.L.evxgpu_set_encode_grid(self.h, int(ctas)), "evxgpu_set_encode_grid")
 
     def launch_count(self):
         return int(self.L.evxgpu_launch_count(self.h))

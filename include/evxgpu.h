@@ -130,6 +130,9 @@ uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h);
 int evxgpu_debug_profile(evxgpu_handle *h, int enable, long long *out_host);
 /* tuning knob: number of persistent CTAs of the decoder's wavefront kernel (0 = default) */
 int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas);
+/* tuning knob: persistent CTAs of the encoder's wavefront kernel (0 = default, ceil(mbw/3) + 4: the number of
+ * macroblock rows that can be active at once, plus spares); any value >= 1 is correct */
+int evxgpu_set_encode_grid(evxgpu_handle *h, int ctas);
 /* tests: shrink the bin-string buffers so that the grow-and-emit-again path of collect_bins runs */
 int evxgpu_debug_set_bins_capacity(evxgpu_handle *h, uint32_t bits);
 

@@ -50,4 +50,25 @@ for S in counts:
     bar.wait(); t0 = time.perf_counter(); bar.wait(); dt2 = time.perf_counter() - t0
     for x in th: x.join()
     del encs
-    print(f"S={S}: pixel pipeline {fps_gpu:8.1f} frames/s aggregate ({fps_gpu / S:6.1f}/stream) | end-to-end {S * (NF - 4) / dt2:8.1f} frames/s ({(NF - 4) / dt2:6.1f}/stream)")
+    # (c) public API, the two halves of encode with one frame in flight per stream
+    encs = [api.evx1_encoder(ref_count=R) for _ in range(S)]
+    for e in encs: e.set_quality(Q)
+    bar = threading.Barrier(S + 1)
+    def work3(i):
+        e = encs[i]
+        for t in range(4):
+            e.encode((int(base[t].data_ptr()), W, H))
+        bar.wait()
+        e.submit((int(base[4].data_ptr()), W, H))
+        for t in range(5, NF):
+            e.submit((int(base[t].data_ptr()), W, H))
+            e.collect()
+        e.collect()
+        bar.wait()
+    th = [threading.Thread(target=work3, args=(i,)) for i in range(S)]
+    for x in th: x.start()
+    bar.wait(); t0 = time.perf_counter(); bar.wait(); dt3 = time.perf_counter() - t0
+    for x in th: x.join()
+    del encs
+    print(f"S={S}: pixel pipeline {fps_gpu:8.1f} frames/s aggregate ({fps_gpu / S:6.1f}/stream) | end-to-end encode() {S * (NF - 4) / dt2:8.1f} frames/s "
+          f"({(NF - 4) / dt2:6.1f}/stream) | submit/collect {S * (NF - 4) / dt3:8.1f} frames/s ({(NF - 4) / dt3:6.1f}/stream)")
