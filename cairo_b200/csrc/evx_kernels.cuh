@@ -148,15 +148,17 @@ __device__ __forceinline__ void evx_mbar_expect_tx(uint64_t *bar, uint32_t bytes
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(evx_smem_addr(bar)), "r"(bytes) : "memory");
 }
 
+// try_wait with a suspend-time hint: the warp is parked by the hardware until the phase completes (or
+// the hint runs out) instead of spinning through issue slots that other warps of the SM could use.
 __device__ __forceinline__ void evx_mbar_wait(uint64_t *bar, uint32_t phase)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(evx_smem_addr(bar)), "r"(phase) : "memory");
+        "DONE_%=:\n\t}" ::"r"(evx_smem_addr(bar)), "r"(phase), "r"(0x989680u) : "memory");
 }
 
 __device__ __forceinline__ void evx_tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
@@ -200,16 +202,22 @@ __device__ __forceinline__ void evx_load_src_lane(const EvxPlanes &srcp, const E
     b.w[5] = __ldg(reinterpret_cast<const uint32_t *>(srcp.v + off) + (lane & 3));
 }
 
-// the sequential search of one macroblock against one window (motion.cpp:254-275, 319-352, 421-494)
-__device__ __forceinline__ void evx_inter_search_warp(const EvxWin &win, const EvxLaneSrc &src, const EvxGeom &g, int px, int py, int thr,
-                                                      int lane, EvxSel &s, uint32_t &n_full, uint32_t &n_sub)
+// the sequential search of one macroblock against one window (motion.cpp:254-275, 319-352, 421-494).
+// `centre` is the co-located block; `stage(k, cx, cy, win)` is called before the first round (k = 0, centre
+// of the step-16 round) and after it (k = 1, its winner): a kernel whose window does not hold the whole
+// +-32 range re-centres it there (every later position stays within [-16, +32) of that winner).
+struct EvxNoStage { __device__ __forceinline__ void operator()(int, int, int, EvxWin &) const {} };
+
+template <class Stage>
+__device__ __forceinline__ void evx_inter_search_warp(EvxWin &win, const EvxLaneSrc &src, const EvxLaneBlock &centre, const EvxGeom &g, int px, int py, int thr,
+                                                      int lane, EvxSel &s, uint32_t &n_full, uint32_t &n_sub, Stage stage)
 {
     EvxLaneBlock ref;
     s.bx = px; s.by = py; s.ssd = EVX_BIG; s.sp_index = 0; s.sp_amount = 0; s.sp_enabled = 0;
-    evx_load_block(win, px, py, lane, ref);
-    evx_block_cost(ref, src, thr, s.sad, s.mad);
+    evx_block_cost(centre, src, thr, s.sad, s.mad);
     n_full = 1; n_sub = 0;
     if (s.mad < thr) return;                       // already a copy block: no search (motion.cpp:452)
+    stage(0, px, py, win);
     for (int step = EVX_SEARCH_RADIUS; step > 0; step >>= 1)
     {
         // One 3x3 round (motion.cpp:254-275).  The eight outer cells are costed back to back (no
@@ -240,6 +248,7 @@ __device__ __forceinline__ void evx_inter_search_warp(const EvxWin &win, const E
             s.bx = __shfl_sync(0xFFFFFFFFu, x, wl); s.by = __shfl_sync(0xFFFFFFFFu, y, wl);
             s.sad = __shfl_sync(0xFFFFFFFFu, mysad, wl); s.mad = __shfl_sync(0xFFFFFFFFu, mymad, wl); s.ssd = __shfl_sync(0xFFFFFFFFu, ssd, wl);
         }
+        if (step == EVX_SEARCH_RADIUS) stage(1, s.bx, s.by, win);
     }
     // sub-pel (motion.cpp:319-352): eight directions, half and quarter each; lane t takes test t
     EvxLaneBlock best;
@@ -269,7 +278,7 @@ __device__ __forceinline__ void evx_inter_search_warp(const EvxWin &win, const E
     }
 }
 
-__global__ void __launch_bounds__(EVX_K2_MBS * 32, EVX_K2_CTAS_PER_SM) evx_inter_search(const __grid_constant__ EvxK2Maps maps, EvxPlanes srcp, EvxGeom g,
+__global__ void __launch_bounds__(EVX_K2_MBS * 32, EVX_K2_CTAS_PER_SM) evx_inter_search_tile(const __grid_constant__ EvxK2Maps maps, EvxPlanes srcp, EvxGeom g,
                                                         EvxInterResult *__restrict__ results, int thr,
                                                         unsigned long long *__restrict__ counters)
 {
@@ -314,7 +323,9 @@ __global__ void __launch_bounds__(EVX_K2_MBS * 32, EVX_K2_CTAS_PER_SM) evx_inter
 
     EvxSel s;
     uint32_t n_full, n_sub;
-    evx_inter_search_warp(win, src, g, px, py, thr, lane, s, n_full, n_sub);
+    EvxLaneBlock centre;
+    evx_load_block(win, px, py, lane, centre);
+    evx_inter_search_warp(win, src, centre, g, px, py, thr, lane, s, n_full, n_sub, EvxNoStage());
 
     if (lane == 0)
     {
@@ -324,6 +335,110 @@ __global__ void __launch_bounds__(EVX_K2_MBS * 32, EVX_K2_CTAS_PER_SM) evx_inter
         results[(size_t) ref * g.mbw * g.mbh + (size_t) by * g.mbw + bx] = r;
         atomicAdd(&counters[0], (unsigned long long) n_full);
         atomicAdd(&counters[1], (unsigned long long) n_sub);
+    }
+}
+
+// ------------------------------------------------------------------ K2, one warp per macroblock
+//
+// grid = (mbw, mbh, refs), block = ONE warp = one (macroblock, reference) search.  About four in ten
+// macroblocks of ordinary video are copy blocks whose search ends at the centre test; in the tile kernel
+// above their warps sit dead in a CTA until its slowest member finishes (25 % achieved occupancy of a
+// 50 % limit, and a 24 % tail).  Here a finished search frees its SM slot at once:
+//   * the centre test reads the co-located block straight from global memory (no window at all);
+//   * a macroblock that does search never needs the whole +-32 range at once.  The step-16 round touches
+//     [px-16, px+32) x [py-16, py+32); everything after it (steps 8,4,2,1 and the sub-pel taps) stays within
+//     [-16, +32) of that round's winner.  So the window is 48x48 luma + two 24x24 chroma tiles (6.9 KB),
+//     fetched by TMA twice -- 28 searches resident per SM instead of 16 live ones.
+// Row pitches of 24 / 12 words keep the lane layout of evx_load_block bank-conflict free
+// (rows {0,24,48,72} + 0..7 and {0,12,..,84} + 0..3 tile the 32 banks).
+
+#define EVX_K2W_WIN 48
+#define EVX_K2W_CWIN 24
+#define EVX_K2W_BYTES (EVX_K2W_WIN * EVX_K2W_WIN * 2 + 2 * EVX_K2W_CWIN * EVX_K2W_CWIN * 2)
+#define EVX_K2W_SMEM (EVX_K2W_BYTES + 16)
+#define EVX_K2W_PER_SM 28         // (6.9 KB + 1 KB reserved) x 28 = 223 KB of the SM's 228 KB
+
+struct EvxK2Params
+{
+    EvxK2Maps maps;               // 48x48 / 24x24 boxes
+    EvxPlanes src, ref[7];
+    EvxGeom g;
+    EvxInterResult *results;
+    unsigned long long *counters;
+    int thr;
+};
+
+struct EvxK2Stage
+{
+    const CUtensorMap *my, *mu, *mv;
+    int16_t *wy, *wu, *wv;
+    uint64_t *bar;
+    int lane;
+    __device__ __forceinline__ void fetch(int cx, int cy) const
+    {
+        if (lane == 0)
+        {
+            evx_mbar_expect_tx(bar, EVX_K2W_BYTES);
+            evx_tma_load_2d(wy, my, cx - 16, cy - 16, bar);
+            evx_tma_load_2d(wu, mu, (cx - 16) >> 1, (cy - 16) >> 1, bar);
+            evx_tma_load_2d(wv, mv, (cx - 16) >> 1, (cy - 16) >> 1, bar);
+        }
+    }
+    // k = 0: the window around the macroblock itself was requested when the kernel started (it flies while
+    // the centre test runs); k = 1: re-centre on the first round's winner -- unless that is the macroblock's own
+    // position, whose window is the one already here.
+    __device__ __forceinline__ void operator()(int k, int cx, int cy, EvxWin &win) const
+    {
+        if (k == 0) { evx_mbar_wait(bar, 0); return; }
+        if (cx - 16 == win.ox && cy - 16 == win.oy) return;
+        __syncwarp();                                           // every lane is done reading the previous window
+        if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fetch(cx, cy);
+        win.ox = cx - 16; win.oy = cy - 16; win.cox = win.ox >> 1; win.coy = win.oy >> 1;
+        evx_mbar_wait(bar, 1);
+    }
+};
+
+__global__ void __launch_bounds__(32, EVX_K2W_PER_SM) evx_inter_search(const __grid_constant__ EvxK2Params p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    int16_t *wy = reinterpret_cast<int16_t *>(smem);
+    int16_t *wu = wy + EVX_K2W_WIN * EVX_K2W_WIN;
+    int16_t *wv = wu + EVX_K2W_CWIN * EVX_K2W_CWIN;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wv + EVX_K2W_CWIN * EVX_K2W_CWIN);
+
+    const int lane = threadIdx.x, ref = blockIdx.z, bx = blockIdx.x, by = blockIdx.y;
+    const int px = bx * EVX_MB, py = by * EVX_MB;
+    const EvxGeom g = p.g;
+    EvxK2Stage stage = { &p.maps.m[ref * 3 + 0], &p.maps.m[ref * 3 + 1], &p.maps.m[ref * 3 + 2], wy, wu, wv, bar, lane };
+    if (lane == 0) evx_mbar_init(bar, 1);
+    __syncwarp();
+    stage.fetch(px, py);
+
+    EvxLaneSrc src;
+    EvxLaneBlock sb, centre;
+    evx_load_src_lane(p.src, g, px, py, lane, sb);
+    evx_load_src_lane(p.ref[ref], g, px, py, lane, centre);
+    evx_make_src(sb, src);
+
+    EvxWin win;
+    win.y = reinterpret_cast<const uint32_t *>(wy); win.u = reinterpret_cast<const uint32_t *>(wu); win.v = reinterpret_cast<const uint32_t *>(wv);
+    win.pw_y = EVX_K2W_WIN / 2; win.pw_c = EVX_K2W_CWIN / 2;
+    win.ox = px - 16; win.oy = py - 16; win.cox = win.ox >> 1; win.coy = win.oy >> 1;
+
+    EvxSel s;
+    uint32_t n_full, n_sub;
+    evx_inter_search_warp(win, src, centre, g, px, py, p.thr, lane, s, n_full, n_sub, stage);
+    if (n_full == 1) evx_mbar_wait(bar, 0);      // copy block: the window was never used, but it must have landed before this CTA's shared memory is released
+
+    if (lane == 0)
+    {
+        EvxInterResult r;
+        r.desc = evx_desc_from_sel(s, 0, ref + 1, px, py, p.thr);
+        r.sad = s.sad; r.pad[0] = r.pad[1] = r.pad[2] = 0;
+        p.results[(size_t) ref * g.mbw * g.mbh + (size_t) by * g.mbw + bx] = r;
+        atomicAdd(&p.counters[0], (unsigned long long) n_full);
+        atomicAdd(&p.counters[1], (unsigned long long) n_sub);
     }
 }
 
@@ -505,6 +620,20 @@ __device__ __forceinline__ int evx_ld_relaxed(const int *p)
 __device__ __forceinline__ void evx_wait_ge(const int *p, int need)
 {
     while (evx_ld_relaxed(p) < need) __nanosleep(100);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+// The same for a counter that advances in known steps (a row's progress): far from the target the poll
+// backs off (the value cannot arrive sooner than one macroblock time per missing step), next to it the
+// poll is tight.
+__device__ __forceinline__ void evx_wait_ge_far(const int *p, int need)
+{
+    for (;;)
+    {
+        const int have = evx_ld_relaxed(p);
+        if (have >= need) break;
+        __nanosleep(need - have > 2 ? 2000 : (need - have > 1 ? 400 : 40));
+    }
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 

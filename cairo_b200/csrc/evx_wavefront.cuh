@@ -30,6 +30,9 @@
 #ifndef EVX_K3_CW
 #define EVX_K3_CW 8               // compute warps
 #endif
+#ifndef EVX_K3_MINCTAS
+#define EVX_K3_MINCTAS 2            // CTAs per SM the register budget is set for (3 = 64 registers, spills: measured slower)
+#endif
 #define EVX_K3_CPW (8 / EVX_K3_CW)  // search cells (and sub-pel directions) per compute warp
 #define EVX_K3_CT (EVX_K3_CW * 32)
 #define EVX_K3_NT (EVX_K3_CT + 64)
@@ -224,7 +227,7 @@ __device__ __forceinline__ void evx_k3_column_loader(EvxK3Smem &S, const EvxK3Pa
         if (c >= 3) evx_mbar_wait(&S.empty[(c - 3) & 1], (uint32_t) (((c - 3) >> 1) & 1));
         if (by > 0)
         {
-            if (lane == 0) evx_wait_ge(progress + by - 1, min(c, g.mbw - 1) + 1);
+            if (lane == 0) evx_wait_ge_far(progress + by - 1, min(c, g.mbw - 1) + 1);
             __syncwarp();
             if (c < g.mbw) pull_column(c);
         }
@@ -325,6 +328,9 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             s.sad = __reduce_add_sync(0xFFFFFFFFu, a);
         }
         int buf = 0;
+#ifdef EVX_K3_STATS
+        uint32_t n_hold = 0;
+#endif
 #pragma unroll 1
         for (int round = 0; round < 5; ++round)
         {
@@ -369,6 +375,9 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 int2 v = S.cand2[buf][lc];
                 if (from_state) v = make_int2(s.sad, s.mad);
                 const int wcell = evx_select_fullpel(s, evx_make_keys(v.x, v.y, ssdl, thr, legall), lane, thr, n_full);
+#ifdef EVX_K3_STATS
+                n_hold += wcell < 0 ? 1u << (6 * round) : 0u;      // five 6-bit counters... per macroblock, folded below
+#endif
                 if (wcell >= 0)
                 {
                     s.bx = __shfl_sync(0xFFFFFFFFu, cxl, wcell); s.by = __shfl_sync(0xFFFFFFFFu, cyl, wcell);
@@ -378,6 +387,9 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             }
             buf ^= 1;
         }
+#ifdef EVX_K3_STATS
+        for (int r = 0; r < 5; ++r) prof[5 + r] += (n_hold >> (6 * r)) & 63u;
+#endif
         EVX_K3_PROF(1);
         // ---- intra sub-pel, motion.cpp:277-317: eight directions, both blends each
         {
@@ -585,7 +597,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     }
 }
 
-__global__ void __launch_bounds__(EVX_K3_NT, 2) evx_wavefront(const __grid_constant__ EvxK3Params p)
+__global__ void __launch_bounds__(EVX_K3_NT, EVX_K3_MINCTAS) evx_wavefront(const __grid_constant__ EvxK3Params p)
 {
     extern __shared__ __align__(16) uint8_t evx_k3_smem[];
     EvxK3Smem &S = *reinterpret_cast<EvxK3Smem *>(evx_k3_smem);

@@ -65,7 +65,9 @@ struct evxgpu_handle
     int *d_sync;
     int *d_done;                      // decoder dependency tracking: done[nmb] followed by readers[nmb]
     unsigned long long *d_counters;
-    CUtensorMap maps[8][3];
+    CUtensorMap maps[8][3];         // tile kernel boxes
+    CUtensorMap maps_w[8][3];       // one-warp-per-macroblock kernel boxes
+    bool k2_tile;                   // EVXGPU_K2=tile selects the tile kernel (measurements)
 
     // pinned host staging
     EvxDesc *h_table;
@@ -227,11 +229,16 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
             int r = make_map(enc, &h->maps[i][0], h->ring[i].y, h->g.w, h->g.h, EVX_K2_WIN_W, EVX_K2_WIN_H);
             r |= make_map(enc, &h->maps[i][1], h->ring[i].u, h->g.w / 2, h->g.h / 2, EVX_K2_CWIN_W, EVX_K2_CWIN_H);
             r |= make_map(enc, &h->maps[i][2], h->ring[i].v, h->g.w / 2, h->g.h / 2, EVX_K2_CWIN_W, EVX_K2_CWIN_H);
+            r |= make_map(enc, &h->maps_w[i][0], h->ring[i].y, h->g.w, h->g.h, EVX_K2W_WIN, EVX_K2W_WIN);
+            r |= make_map(enc, &h->maps_w[i][1], h->ring[i].u, h->g.w / 2, h->g.h / 2, EVX_K2W_CWIN, EVX_K2W_CWIN);
+            r |= make_map(enc, &h->maps_w[i][2], h->ring[i].v, h->g.w / 2, h->g.h / 2, EVX_K2W_CWIN, EVX_K2W_CWIN);
             if (r) { evxgpu_destroy(h); return fail(5, "cuTensorMapEncodeTiled failed"); }
         }
     }
     {
-        cudaError_t e = cudaFuncSetAttribute(evx_inter_search, cudaFuncAttributeMaxDynamicSharedMemorySize, EVX_K2_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(evx_inter_search_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, EVX_K2_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(evx_inter_search, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        { const char *k2 = getenv("EVXGPU_K2"); h->k2_tile = k2 && !strcmp(k2, "tile"); }
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_inter_search)", e); }
         e = cudaFuncSetAttribute(evx_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EvxK3Smem));
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_wavefront)", e); }
@@ -337,15 +344,32 @@ static int launch_convert_in(evxgpu_handle *h, const uint8_t *d_rgb)
 static int launch_inter_search(evxgpu_handle *h, uint32_t index, int quality)
 {
     const int R = h->cfg.ref_count;
-    EvxK2Maps maps;
-    for (int off = 1; off < R; ++off)
+    if (h->k2_tile)
     {
-        int slot = (int) ((index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);     // common.cpp:192-195
-        for (int c = 0; c < 3; ++c) maps.m[(off - 1) * 3 + c] = h->maps[slot][c];
+        EvxK2Maps maps;
+        for (int off = 1; off < R; ++off)
+        {
+            int slot = (int) ((index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);     // common.cpp:192-195
+            for (int c = 0; c < 3; ++c) maps.m[(off - 1) * 3 + c] = h->maps[slot][c];
+        }
+        dim3 block(EVX_K2_MBS * 32), grid((h->g.mbw + EVX_K2_MBS - 1) / EVX_K2_MBS, h->g.mbh, R - 1);
+        t_begin(h, EVXGPU_T_INTER_SEARCH);
+        evx_inter_search_tile<<<grid, block, EVX_K2_SMEM, h->stream>>>(maps, h->src, h->g, h->d_inter, (quality >> 2) + 1, h->d_counters);
     }
-    dim3 block(EVX_K2_MBS * 32), grid((h->g.mbw + EVX_K2_MBS - 1) / EVX_K2_MBS, h->g.mbh, R - 1);
-    t_begin(h, EVXGPU_T_INTER_SEARCH);
-    evx_inter_search<<<grid, block, EVX_K2_SMEM, h->stream>>>(maps, h->src, h->g, h->d_inter, (quality >> 2) + 1, h->d_counters);
+    else
+    {
+        EvxK2Params p;
+        for (int off = 1; off < R; ++off)
+        {
+            int slot = (int) ((index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);     // common.cpp:192-195
+            for (int c = 0; c < 3; ++c) p.maps.m[(off - 1) * 3 + c] = h->maps_w[slot][c];
+            p.ref[off - 1] = h->ring[slot];
+        }
+        p.src = h->src; p.g = h->g; p.results = h->d_inter; p.counters = h->d_counters; p.thr = (quality >> 2) + 1;
+        dim3 block(32), grid(h->g.mbw, h->g.mbh, R - 1);
+        t_begin(h, EVXGPU_T_INTER_SEARCH);
+        evx_inter_search<<<grid, block, EVX_K2W_SMEM, h->stream>>>(p);
+    }
     t_end(h, EVXGPU_T_INTER_SEARCH);
     h->launches++;
     CK(cudaGetLastError());
