@@ -39,6 +39,8 @@ def lib():
     L.evx1c_decoder_destroy.argtypes = [vp]
     L.evx1c_decoder_clear.argtypes = [vp]
     L.evx1c_decoder_decode.argtypes = [vp, vp, u32, vp]
+    L.evx1c_decoder_submit.argtypes = [vp, vp, u32]
+    L.evx1c_decoder_collect.argtypes = [vp, vp]
     L.evx1c_decoder_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.evx1c_slice_writer_create.restype = vp
     L.evx1c_slice_writer_create.argtypes = [i32] * 3
@@ -157,6 +159,23 @@ class evx1_decoder:
         st = self.L.evx1c_decoder_decode(self.h, _p(data), nbits, _p(out))
         if st != 0:
             raise RuntimeError(f"evx1_decoder::decode failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
+        return out
+
+
+    def submit(self, data, nbits):
+        """First half of decode(): entropy-decode one frame on the host and queue it for the device."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        st = self.L.evx1c_decoder_submit(self.h, _p(data), nbits)
+        if st != 0:
+            raise RuntimeError(f"evx1_decoder::submit failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
+
+    def collect(self, width, height, out=None):
+        """Second half of decode(): the oldest submitted frame's picture."""
+        if out is None:
+            out = np.empty((height, width, 3), dtype=np.uint8)
+        st = self.L.evx1c_decoder_collect(self.h, _p(out))
+        if st != 0:
+            raise RuntimeError(f"evx1_decoder::collect failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
         return out
 
 

@@ -155,6 +155,14 @@ public:
     virtual evx_status clear() = 0;
     virtual evx_status decode(bit_stream *input, void *output) = 0;
     virtual evx_status last_frame_stats(evx1_frame_stats *out) = 0;                    // addition (entropy_ms = unserialize)
+
+    // additions: decode() == submit() + collect().  submit parses and entropy-decodes one frame on the host
+    // (and empties input, like decode); the frame starts on the device as soon as the device is free.  collect
+    // writes the oldest submitted frame's picture.  submit(n+1) before collect(n) overlaps the host entropy
+    // decoding of frame n+1 with the device's work on frame n; at most two frames may be uncollected
+    // (EVX_ERROR_NOT_READY otherwise, and for decode() with any frame uncollected, and for collect with none).
+    virtual evx_status submit(bit_stream *input) = 0;
+    virtual evx_status collect(void *output) = 0;
 };
 
 // addition: the reference's config.h switches at run time

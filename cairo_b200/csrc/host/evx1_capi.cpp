@@ -113,6 +113,22 @@ int evx1c_decoder_decode(evx1c_decoder *d, const uint8_t *data, uint32_t nbits, 
     return d->dec->decode(&d->bs, rgb_out);
 }
 
+int evx1c_decoder_submit(evx1c_decoder *d, const uint8_t *data, uint32_t nbits)
+{
+    if (!d || !data || !nbits) return EVX_ERROR_INVALIDARG;
+    uint32 need = ((nbits + 7) >> 3) * 8 + 64;
+    if (d->bs.query_capacity() < need) d->bs.resize_capacity(need);
+    d->bs.empty();
+    d->bs.write_bits(const_cast<uint8_t *>(data), nbits);
+    return d->dec->submit(&d->bs);
+}
+
+int evx1c_decoder_collect(evx1c_decoder *d, uint8_t *rgb_out)
+{
+    if (!d || !rgb_out) return EVX_ERROR_INVALIDARG;
+    return d->dec->collect(rgb_out);
+}
+
 struct evx1c_slice_writer { slice_writer w; };
 struct evx1c_slice_reader { slice_reader r; };
 

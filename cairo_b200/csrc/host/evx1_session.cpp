@@ -261,7 +261,28 @@ class decoder_session : public evx1_decoder
     std::vector<int16> records_;
     evx1_frame_stats stats_;
 
+    // A submitted frame is parsed (entropy-decoded into table_/records_, waiting for the device) or on the device.
+    struct pending_frame
+    {
+        bool valid;
+        frame_desc desc;
+        uint32 n_noncopy, slice_bits;
+        double entropy_ms, t_submit;
+    };
+    pending_frame parsed_, on_device_;
+
     void clear_frame() { frame_.type = 0; frame_.index = 0; frame_.quality = (uint16) clip(cfg_.default_quality, 1, 100); }
+
+    evx_status launch()          // the device copies table_/records_ into its own staging before returning
+    {
+        pending_frame f = parsed_;
+        parsed_.valid = false;
+        f.t_submit = now_ms();
+        int rc = evxgpu_decode_submit(gpu_, table_.data(), records_.data(), f.n_noncopy, (int) f.desc.type, f.desc.index);
+        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+        on_device_ = f;
+        return EVX_SUCCESS;
+    }
 
     evx_status initialize(bit_stream *input)                 // evx1dec.cpp:41-69, verify_header common.cpp:25-43
     {
@@ -289,6 +310,9 @@ public:
     explicit decoder_session(const evx1_config &cfg) : cfg_(cfg), initialized_(false), gpu_(NULL)
     {
         memset(&header_, 0, sizeof(header_));
+        memset(&stats_, 0, sizeof(stats_));
+        memset(&parsed_, 0, sizeof(parsed_));
+        memset(&on_device_, 0, sizeof(on_device_));
         clear_frame();
     }
     ~decoder_session() { clear(); }
@@ -298,35 +322,61 @@ public:
         if (!initialized_) return EVX_SUCCESS;
         clear_frame();
         if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }
+        parsed_.valid = on_device_.valid = false;
         initialized_ = false;
         return EVX_SUCCESS;
     }
 
-    evx_status decode(bit_stream *input, void *output)       // evx1dec.cpp:87-123
+    // First half of decode (evx1dec.cpp:87-123 up to unserialize_slice, decode.cpp:172-180): the frame is
+    // parsed and entropy-decoded on the host; it goes to the device at once if the device is free, otherwise
+    // when collect() has taken the previous frame off it.
+    evx_status submit(bit_stream *input)
     {
-        if (!input || !output) return EVX_ERROR_INVALIDARG;
+        if (!input) return EVX_ERROR_INVALIDARG;
+        if (parsed_.valid) return EVX_ERROR_NOT_READY;                                   // one frame may wait for the device
         if (!initialized_ && evx_failed(initialize(input))) return EVX_ERROR_EXECUTION_FAILURE;
         frame_desc incoming;
         if (evx_failed(input->read_bytes(&incoming, sizeof(incoming)))) return EVX_ERROR_EXECUTION_FAILURE;
         if (incoming.index != frame_.index) return EVX_ERROR_EXECUTION_FAILURE;          // evx1dec.cpp:77-80
         frame_ = incoming;
 
-        // engine_decode_frame, decode.cpp:172-198
-        uint32 n_noncopy = 0;
         const double t0 = now_ms();
         const uint32 bits_before = input->query_read_index();
+        uint32 n_noncopy = 0;
         if (reader_.unserialize(input->query_data(), input->query_read_index(), input->query_write_index(), table_.data(), records_.data(), &n_noncopy))
             return EVX_ERROR_EXECUTION_FAILURE;
-        const double t1 = now_ms();
-        int rc = evxgpu_decode_submit(gpu_, table_.data(), records_.data(), n_noncopy, (int) frame_.type, frame_.index);
-        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        rc = evxgpu_decode_collect(gpu_, static_cast<uint8 *>(output), 0);
-        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        stats_.entropy_ms = t1 - t0; stats_.gpu_ms = now_ms() - t1; stats_.noncopy_blocks = n_noncopy;
-        stats_.slice_bits = input->query_write_index() - bits_before; stats_.d2h_bytes = 0;
+        memset(&parsed_, 0, sizeof(parsed_));
+        parsed_.valid = true; parsed_.desc = frame_; parsed_.n_noncopy = n_noncopy;
+        parsed_.entropy_ms = now_ms() - t0; parsed_.slice_bits = input->query_write_index() - bits_before;
         frame_.index++;
-        input->empty();
+        input->empty();                                                                    // evx1dec.cpp:120
+        if (!on_device_.valid) return launch();
         return EVX_SUCCESS;
+    }
+
+    // Second half (decode_slice, deblocking, colour conversion: decode.cpp:182-198): the oldest submitted
+    // frame's RGB8 picture into output; a frame that was waiting for the device starts right after.
+    evx_status collect(void *output)
+    {
+        if (!output) return EVX_ERROR_INVALIDARG;
+        if (!on_device_.valid) return EVX_ERROR_NOT_READY;
+        const pending_frame f = on_device_;
+        on_device_.valid = false;
+        int rc = evxgpu_decode_collect(gpu_, static_cast<uint8 *>(output), 0);
+        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+        stats_.entropy_ms = f.entropy_ms; stats_.gpu_ms = now_ms() - f.t_submit; stats_.noncopy_blocks = f.n_noncopy;
+        stats_.slice_bits = f.slice_bits; stats_.d2h_bytes = (uint32) ((size_t) header_.frame_width * header_.frame_height * 3);
+        if (parsed_.valid) return launch();
+        return EVX_SUCCESS;
+    }
+
+    evx_status decode(bit_stream *input, void *output)       // evx1dec.cpp:87-123
+    {
+        if (!input || !output) return EVX_ERROR_INVALIDARG;
+        if (on_device_.valid || parsed_.valid) return EVX_ERROR_NOT_READY;      // finish the pipelined frames with collect() first
+        evx_status st = submit(input);
+        if (evx_failed(st)) return st;
+        return collect(output);
     }
 
     evx_status last_frame_stats(evx1_frame_stats *out) { if (!out) return EVX_ERROR_INVALIDARG; *out = stats_; return EVX_SUCCESS; }

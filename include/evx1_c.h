@@ -39,6 +39,11 @@ int evx1c_decoder_stats(evx1c_decoder *d, double *gpu_ms, double *entropy_ms);  
 /* evx1_decoder::decode of one frame (nbits bits at data); rgb_out is width*height*3 bytes. */
 int evx1c_decoder_decode(evx1c_decoder *d, const uint8_t *data, uint32_t nbits, uint8_t *rgb_out);
 
+/* evx1_decoder::submit / collect (additions: decode == submit + collect; submit(n+1) before collect(n) overlaps
+ * the host entropy decoding of frame n+1 with the device's work on frame n). */
+int evx1c_decoder_submit(evx1c_decoder *d, const uint8_t *data, uint32_t nbits);
+int evx1c_decoder_collect(evx1c_decoder *d, uint8_t *rgb_out);
+
 /* The host entropy stage on its own (serialize_slice / unserialize_slice of the reference,
  * serialize.cpp:319-340, unserialize.cpp:321-341).  A writer/reader is persistent per stream:
  * it carries the DC-prediction state that the reference keeps in its coefficient planes.

@@ -177,3 +177,35 @@ def test_pipelined_1080p_equals_synchronous_and_state_rules():
     assert b > 0
     for t in range(n):
         assert out[t][1] == sync[t][1] and (out[t][0] == sync[t][0]).all(), t
+
+
+def test_pipelined_decode_equals_synchronous():
+    """evx1_decoder::submit(n+1) before collect(n): same pictures as decode(), one call later; state rules."""
+    from cairo_b200 import api
+    w, h, n = 352, 288, 8
+    enc = api.evx1_encoder()
+    enc.set_quality(16)
+    streams = []
+    for t in range(n):
+        if t == 5:
+            enc.insert_intra()
+        d, b = enc.encode(synth.frame(w, h, t, 1, "moving"))
+        streams.append((d.copy(), b))
+    ref = api.evx1_decoder()
+    want = [ref.decode(d, b, w, h).copy() for d, b in streams]
+    dec = api.evx1_decoder()
+    with pytest.raises(RuntimeError):
+        dec.collect(w, h)                          # nothing submitted
+    dec.submit(*streams[0])
+    with pytest.raises(RuntimeError):
+        dec.decode(streams[1][0], streams[1][1], w, h)     # decode() with a frame uncollected
+    dec.submit(*streams[1])
+    with pytest.raises(RuntimeError):
+        dec.submit(*streams[2])                    # a third uncollected frame
+    got = [dec.collect(w, h).copy()]
+    for t in range(2, n):
+        dec.submit(*streams[t])
+        got.append(dec.collect(w, h).copy())
+    got.append(dec.collect(w, h).copy())
+    for t in range(n):
+        assert (got[t] == want[t]).all(), t
