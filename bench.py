@@ -111,7 +111,7 @@ def run_reference(args):
         # oracle/_ref travels with the snapshot; rebuild only where the reference sources exist
         subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
     if not R.available(variant):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libevxref_r2.so missing and /root/reference absent"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libevxref_r2.so missing and /root/reference absent"})
         return 0
     from cairo_b200 import synth
     n_streams = max(1, args.gpus)
@@ -152,7 +152,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -425,13 +425,30 @@ def run_ours(args):
                 line["cpu_baseline"] = cpu_baseline_sample()
             except Exception as ex:  # the baseline is a reported number, never a reason to lose the GPU line
                 line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else the process (NCCL's version banner,
+    library chatter) writes to fd 1 has been pointed at stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=56)
