@@ -270,7 +270,13 @@ struct EvxLaneSrc
     int lsum;            // sum of this lane's 8 luma samples
 };
 
-__device__ __forceinline__ uint32_t evx_neg16x2(uint32_t v) { return __vadd2(~v, 0x00010001u); }
+// Packed negation, halfword by halfword in scalar arithmetic (six words per macroblock: the cost is nil).
+// The packed form (~v + 0x00010001 through add.u16x2) is what ptxas 12.9 rematerialises in split halves,
+// dropping the immediate of one half (cairo_b200/build.py:lint_sass scans for the symptom).
+__device__ __forceinline__ uint32_t evx_neg16x2(uint32_t v)
+{
+    return ((0u - (v & 0xFFFFu)) & 0xFFFFu) | ((0u - (v >> 16)) << 16);
+}
 
 __device__ __forceinline__ void evx_make_src(const EvxLaneBlock &b, EvxLaneSrc &s)
 {

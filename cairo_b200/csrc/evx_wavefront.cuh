@@ -388,7 +388,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             buf ^= 1;
         }
 #ifdef EVX_K3_STATS
-        for (int r = 0; r < 5; ++r) prof[5 + r] += (n_hold >> (6 * r)) & 63u;
+        for (int r = 1; r < 5; ++r) prof[5 + r] += (n_hold >> (6 * r)) & 63u;      // round 0 always moves; slot 5 counts far-column waits
 #endif
         EVX_K3_PROF(1);
         // ---- intra sub-pel, motion.cpp:277-317: eight directions, both blends each
@@ -471,7 +471,11 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         evx_compute_sync();
         EVX_K3_PROF(3);
 
-        EVX_K3_NEED2();          // (n+2,by-1) is complete: the row above no longer reads this macroblock's stale samples
+        // Writing this macroblock needs no further wait.  The row above reads the stale samples under it only
+        // through its own shared-memory copy, which its block loader makes while staging macroblock n+1; that
+        // macroblock has completed (fullb, waited for above, needs progress[by-1] >= n+2), so the copy exists.
+        // Column n+2 of the row above is awaited only by a search that actually reaches into it (EVX_K3_NEED2):
+        // most macroblocks follow the row above at a lag of 2, not 3.
         // reconstruction target: global ring slot + our own window rows (py..py+15 -> 48..63)
         auto store_recon = [&](int e, int v)
         {
@@ -578,6 +582,9 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             }
             row_records++;
         }
+#ifdef EVX_K3_STATS
+        prof[5] += have2 ? 1 : 0;       // macroblocks that waited for column n+2 of the row above
+#endif
         if (tid == 0 && (type & EVX_T_MOTION)) S.last_motion = mb;
         evx_compute_sync();
         EVX_K3_PROF(4);

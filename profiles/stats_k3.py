@@ -21,5 +21,5 @@ for kind in ['moving', 'noise', 'static']:
     prof = raw[:(p.ah // 16) * 10].reshape(-1, 10)
     holds = prof[:, 5:10].sum(axis=0) / p.nblocks
     types, counts = np.unique(tbl['block_type'], return_counts=True)
-    print(kind, 'fraction of macroblocks whose round r kept its centre:', np.round(holds, 3), 'block types', dict(zip(types.tolist(), counts.tolist())))
+    print(kind, 'fraction of macroblocks that waited for column n+2 of the row above:', round(float(holds[0]), 3), '| whose round 1..4 kept its centre:', np.round(holds[1:], 3), 'block types', dict(zip(types.tolist(), counts.tolist())))
     p.close()
