@@ -31,7 +31,27 @@ def raw(rep):
     return {h: (v, u) for h, u, v in zip(hdr, units, vals)}
 
 
-for rep in sys.argv[1:]:
+def launch_table(path):
+    """Per-kernel totals of a `--metrics gpu__time_duration.sum --csv` launch list (the integer-peak
+    micro-benchmark launches are listed but excluded from the shares)."""
+    import collections
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
+    d = collections.defaultdict(list)
+    for r in rows:
+        d[r[4].split("(")[0].replace("void ", "")].append(float(r[-1]) / 1000)
+    tot = sum(sum(v) for k, v in d.items() if k.startswith("evx_") and "peak" not in k)
+    print("| kernel | launches | total µs | avg µs | share of encode kernels |\n|---|---|---|---|---|")
+    for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
+        share = f"{100 * sum(v) / tot:.1f}%" if k.startswith("evx_") and "peak" not in k else "(excluded)"
+        print(f"| {k} | {len(v)} | {sum(v):.1f} | {sum(v) / len(v):.1f} | {share} |")
+    print()
+
+
+args = sys.argv[1:]
+if args and args[0] == "--launches":
+    launch_table(args[1])
+    args = args[2:]
+for rep in args:
     m = raw(rep)
     print(f"## {m.get('Kernel Name', ('?', ''))[0]}  ({rep})\n")
     print("| metric | value | unit |\n|---|---|---|")
