@@ -33,6 +33,7 @@ def lib():
     L.evx1c_encoder_encode.argtypes = [vp, vp, u32, u32, vp, u32, C.POINTER(u32)]
     L.evx1c_encoder_submit.argtypes = [vp, vp, u32, u32]
     L.evx1c_encoder_collect.argtypes = [vp, vp, u32, C.POINTER(u32)]
+    L.evx1c_encoder_peek.argtypes = [vp, i32, vp]
     L.evx1c_encoder_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     L.evx1c_decoder_create.restype = vp
     L.evx1c_decoder_create.argtypes = [i32] * 3
@@ -122,6 +123,16 @@ class evx1_encoder:
         if st != 0:
             raise RuntimeError(f"evx1_encoder::collect failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
         return self._out[:(bits.value + 7) // 8], bits.value
+
+    PEEK_SOURCE, PEEK_PREDICTION, PEEK_BLOCK_TABLE, PEEK_QUANT_TABLE, PEEK_SPMP_TABLE, PEEK_BLOCK_VARIANCE, PEEK_DESTINATION = range(7)
+
+    def peek(self, state, width, height):
+        """evx1_encoder::peek: an R8G8B8 debug picture (EVX_PEEK_STATE, evx1.h:53-62)."""
+        out = np.zeros((height, width, 3), dtype=np.uint8)
+        st = self.L.evx1c_encoder_peek(self.h, int(state), _p(out))
+        if st != 0:
+            raise RuntimeError(f"evx1_encoder::peek failed with status {st}")
+        return out
 
     def stats(self):
         g, e, b, n, d = C.c_double(0), C.c_double(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)

@@ -748,6 +748,31 @@ int evxgpu_poke_plane(evxgpu_handle *h, int which, int slot, int comp, const int
     return 0;
 }
 
+// debug views behind evx1_encoder::peek (evx1enc.cpp:170-305): a plane set through the YUV -> RGB kernel
+int evxgpu_peek_rgb(evxgpu_handle *h, int which, int slot, uint8_t *rgb_out_host)
+{
+    if (!h || !rgb_out_host || (which != 0 && which != 2) || slot < 0 || slot >= h->cfg.ref_count) return fail(1, "evxgpu_peek_rgb: bad argument");
+    if (h->pending_encode || h->pending_decode) return fail(15, "evxgpu_peek_rgb: a frame is in flight (the RGB staging buffer is in use)");
+    CK(cudaSetDevice(h->device));
+    dim3 block(256), grid(((h->g.vw + 7) / 8 + 255) / 256, h->g.vh / 2);
+    evx_yuv420_to_rgb<<<grid, block, 0, h->stream>>>(which == 0 ? h->src : h->ring[slot], h->d_rgb, h->g);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rgb_out_host, h->d_rgb, (size_t) h->g.vw * h->g.vh * 3, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// the block table as the last encoded / decoded frame left it
+int evxgpu_peek_table(evxgpu_handle *h, evxgpu_block_desc *table_out)
+{
+    if (!h || !table_out) return fail(1, "evxgpu_peek_table: bad argument");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(table_out, h->d_table, (size_t) h->nmb * 16, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 } // extern "C"
 
 // ------------------------------------------------------------------ integer-pipe micro-benchmark

@@ -131,7 +131,7 @@ public:
     virtual evx_status insert_intra() = 0;
     virtual evx_status set_quality(uint8 quality) = 0;                                  // clipped to 1..31
     virtual evx_status encode(void *image, uint32 width, uint32 height, bit_stream *output) = 0;   // R8G8B8 in, appends to output
-    virtual evx_status peek(EVX_PEEK_STATE peek_state, void *output) = 0;              // debug views: not implemented here
+    virtual evx_status peek(EVX_PEEK_STATE peek_state, void *output) = 0;              // debug views, evx1enc.cpp:170-305
     virtual evx_status last_frame_stats(evx1_frame_stats *out) = 0;                    // addition
 
     // additions: encode() == submit() + collect().  submit queues the frame on the device (colour

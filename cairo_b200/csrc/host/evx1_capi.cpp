@@ -70,6 +70,12 @@ int evx1c_encoder_collect(evx1c_encoder *e, uint8_t *out, uint32_t out_cap_bytes
     return st;
 }
 
+int evx1c_encoder_peek(evx1c_encoder *e, int state, uint8_t *rgb_out)
+{
+    if (!e) return EVX_ERROR_INVALIDARG;
+    return e->enc->peek((EVX_PEEK_STATE) state, rgb_out);
+}
+
 int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks, uint32_t *d2h_bytes)
 {
     if (!e) return EVX_ERROR_INVALIDARG;

@@ -242,7 +242,49 @@ public:
         return st;
     }
 
-    evx_status peek(EVX_PEEK_STATE, void *) { return EVX_ERROR_NOTIMPL; }                  // debug visualisers: out of scope
+    // Debug views (evx1enc.cpp:170-305): an R8G8B8 picture of the source, the last reconstruction, or one of the
+    // block-table visualisations.  Not available while a pipelined frame is uncollected (EVX_ERROR_NOT_READY).
+    evx_status peek(EVX_PEEK_STATE peek_state, void *output)
+    {
+        if (!output) return EVX_ERROR_INVALIDARG;
+        if (!initialized_) return EVX_SUCCESS;
+        if (on_device_.valid || retired_.valid) return EVX_ERROR_NOT_READY;
+        const uint32 w = header_.frame_width, h = header_.frame_height, mbw = (w + 15) / 16;
+        uint8 *out = static_cast<uint8 *>(output);
+        switch (peek_state)
+        {
+            case EVX_PEEK_SOURCE:
+                return evxgpu_peek_rgb(gpu_, 0, 0, out) ? EVX_ERROR_EXECUTION_FAILURE : EVX_SUCCESS;
+            case EVX_PEEK_DESTINATION:
+            {   // query_prediction_index_by_offset(frame, 1): the slot the last encoded frame was reconstructed into
+                const uint32 R = (uint32) cfg_.ref_count;
+                return evxgpu_peek_rgb(gpu_, 2, (int) ((frame_.index + R - 1) % R), out) ? EVX_ERROR_EXECUTION_FAILURE : EVX_SUCCESS;
+            }
+            case EVX_PEEK_BLOCK_TABLE: case EVX_PEEK_QUANT_TABLE: case EVX_PEEK_BLOCK_VARIANCE: case EVX_PEEK_SPMP_TABLE:
+                break;
+            default:
+                return EVX_ERROR_NOTIMPL;                     // EVX_PEEK_PREDICTION has no case in the reference either
+        }
+        if (evxgpu_peek_table(gpu_, table_.data())) return EVX_ERROR_EXECUTION_FAILURE;
+        for (uint32 j = 0; j < h; ++j)
+        for (uint32 i = 0; i < w; ++i)
+        {
+            uint8 *px = out + ((size_t) j * w + i) * 3;
+            const evxgpu_block_desc &e = table_[(size_t) (i / 16) + (size_t) (j / 16) * mbw];
+            const bool intra = (e.block_type & 1) != 0, motion = (e.block_type & 2) != 0, copy = (e.block_type & 4) != 0;   // types.h:68-87
+            if (peek_state == EVX_PEEK_BLOCK_TABLE) { px[0] = intra ? 255 : 0; px[1] = motion ? 255 : 0; px[2] = copy ? 255 : 0; }
+            else if (peek_state == EVX_PEEK_SPMP_TABLE)
+            {
+                px[0] = 0;
+                px[1] = e.sp_pred ? (uint8) (255 * e.sp_amount) : 0;
+                px[2] = e.sp_pred ? (uint8) (255 * !e.sp_amount) : 0;
+            }
+            else if (copy) { px[0] = 255; px[1] = 0; px[2] = 0; }
+            else if (peek_state == EVX_PEEK_QUANT_TABLE) px[0] = px[1] = px[2] = (uint8) (255 - 15 * e.q_index);
+            else px[0] = px[1] = px[2] = (uint8) clip((int16) (e.variance / 30), 0, 255);
+        }
+        return EVX_SUCCESS;
+    }
 
     evx_status last_frame_stats(evx1_frame_stats *out) { if (!out) return EVX_ERROR_INVALIDARG; *out = stats_; return EVX_SUCCESS; }
 };

@@ -116,6 +116,11 @@ int evxgpu_stage_set_block_table(evxgpu_handle *h, const evxgpu_block_desc *tabl
 int evxgpu_peek_plane(evxgpu_handle *h, int which, int slot, int comp, int16_t *out_host);
 int evxgpu_poke_plane(evxgpu_handle *h, int which, int slot, int comp, const int16_t *in_host);
 
+/* debug views for evx1_encoder::peek (evx1enc.cpp:170-305): plane set `which` (0 source, 2 ring slot `slot`) through
+ * the YUV->RGB kernel into rgb_out (host, width*height*3); the block table of the last frame (block_count entries) */
+int evxgpu_peek_rgb(evxgpu_handle *h, int which, int slot, uint8_t *rgb_out_host);
+int evxgpu_peek_table(evxgpu_handle *h, evxgpu_block_desc *table_out);
+
 /* per-kernel device time of the last submitted frame, CUDA events on the handle's stream (ms) */
 int evxgpu_get_timing(evxgpu_handle *h, float *ms_out /* [EVXGPU_T_COUNT] */);
 int evxgpu_enable_timing(evxgpu_handle *h, int on);

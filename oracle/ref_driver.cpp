@@ -96,6 +96,11 @@ int evxref_encoder_encode(void *h, const uint8_t *rgb, uint32_t w, uint32_t hgt,
     return st;
 }
 
+int evxref_encoder_peek(void *h, int state, uint8_t *rgb_out)
+{
+    return ((evx1_encoder *) h)->peek((EVX_PEEK_STATE) state, rgb_out);
+}
+
 void *evxref_decoder_create(void)
 {
     evx1_decoder *dec = NULL;

@@ -34,6 +34,8 @@ def lib(variant="r4"):
     L.evxref_encoder_insert_intra.argtypes = [vp]
     L.evxref_encoder_set_quality.argtypes = [vp, i32]
     L.evxref_encoder_encode.argtypes = [vp, u8p, u32, u32, u8p, u32, C.POINTER(u32)]
+    if hasattr(L, "evxref_encoder_peek"):
+        L.evxref_encoder_peek.argtypes = [vp, i32, u8p]
     L.evxref_decoder_create.restype = vp
     L.evxref_decoder_destroy.argtypes = [vp]
     L.evxref_decoder_clear.argtypes = [vp]
@@ -93,6 +95,13 @@ class RefEncoder:
         st = self.L.evxref_encoder_encode(self.h, _p(rgb), w, h, _p(out), cap, C.byref(bits))
         assert st == 0, st
         return out[:(bits.value + 7) // 8].copy(), bits.value
+
+
+    def peek(self, state, width, height):
+        out = np.zeros((height, width, 3), dtype=np.uint8)
+        st = self.L.evxref_encoder_peek(self.h, int(state), _p(out))
+        assert st == 0, st
+        return out
 
 
 class RefDecoder:

@@ -209,3 +209,36 @@ def test_pipelined_decode_equals_synchronous():
     got.append(dec.collect(w, h).copy())
     for t in range(n):
         assert (got[t] == want[t]).all(), t
+
+
+def test_peek_views_match_reference():
+    """evx1_encoder::peek (evx1enc.cpp:170-305): the six implemented debug views against the golden pictures
+    of the reference (tests/golden/make_golden_peek.py) and, when oracle/_ref is present, the reference itself."""
+    import os
+    from cairo_b200 import api
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "peek", "peek_176x144.npz"))
+    w, h, q, n = int(g["w"]), int(g["h"]), int(g["q"]), int(g["frames"])
+    enc = api.evx1_encoder()
+    assert (enc.peek(enc.PEEK_SOURCE, w, h) == 0).all()          # not initialised yet: success, nothing written
+    enc.set_quality(q)
+    renc = R.RefEncoder("r4") if R.available("r4") and hasattr(R.lib("r4"), "evxref_encoder_peek") else None
+    if renc:
+        renc.set_quality(q)
+    for t in range(n):
+        f = synth.frame(w, h, t, 0, "moving")
+        enc.encode(f)
+        if renc:
+            renc.encode(f)
+    views = {"source": 0, "block_table": 2, "quant_table": 3, "spmp_table": 4, "block_variance": 5, "destination": 6}
+    for name, state in views.items():
+        got = enc.peek(state, w, h)
+        assert (got == g[name]).all(), name
+        if renc:
+            assert (got == renc.peek(state, w, h)).all(), name
+    with pytest.raises(RuntimeError):
+        enc.peek(enc.PEEK_PREDICTION, w, h)                       # no case in the reference's switch: EVX_ERROR_NOTIMPL
+    enc.submit(synth.frame(w, h, n, 0, "moving"))
+    with pytest.raises(RuntimeError):
+        enc.peek(enc.PEEK_SOURCE, w, h)                           # a pipelined frame is uncollected
+    enc.collect()
+    assert enc.peek(enc.PEEK_DESTINATION, w, h).any()
