@@ -91,7 +91,7 @@ class evx1_encoder:
             image = np.ascontiguousarray(image)
             h, w, _ = image.shape
             ptr = _p(image)
-            self._keep = image               # submit(): the frame must outlive the call
+            self._keep = (getattr(self, "_keep", (None, None))[1], image)      # submit(): the last two frames outlive their calls
         cap = w * h * 6 + 4096
         if self._out is None or self._out.size != cap:
             self._out = np.zeros(cap, dtype=np.uint8)

@@ -56,6 +56,10 @@ struct evxgpu_handle
     int16_t *src_mem, *ring_mem[8];
     EvxPlanes src, ring[8];
     uint8_t *d_rgb;                 // frame staging (input on the encoder, output on the decoder)
+    uint8_t *d_rgb_up;              // evxgpu_encode_upload: the next frame, copied on copy_stream while the current one encodes
+    cudaStream_t copy_stream;
+    cudaEvent_t ev_up, ev_k1;       // upload landed / colour conversion has consumed d_rgb_up
+    bool uploaded, up_ready;
     EvxDesc *d_table;
     EvxInterResult *d_inter;
     int16_t *d_records;             // per-macroblock slots written by K3
@@ -79,6 +83,8 @@ struct evxgpu_handle
     bool timing;
     cudaEvent_t ev[EVXGPU_T_COUNT][2];
     bool ev_valid[EVXGPU_T_COUNT];
+    double t_sum[EVXGPU_T_COUNT];   // accumulated kernel times of the frames since evxgpu_get_timing_sum(reset)
+    bool t_pending;                 // the last submitted frame's events are not in t_sum yet
     uint64_t launches;
     bool pending_encode, pending_decode;
     int wave_grid;
@@ -143,6 +149,10 @@ int evxgpu_destroy(evxgpu_handle *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->src_mem);
     for (int i = 0; i < 8; ++i) cudaFree(h->ring_mem[i]);
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    cudaFree(h->d_rgb_up);
+    if (h->ev_up) cudaEventDestroy(h->ev_up);
+    if (h->ev_k1) cudaEventDestroy(h->ev_k1);
     cudaFree(h->d_rgb); cudaFree(h->d_table); cudaFree(h->d_inter); cudaFree(h->d_records); cudaFree(h->d_dense); cudaFree(h->d_row_records);
     cudaFree(h->d_record_slot); cudaFree(h->d_sync); cudaFree(h->d_done); cudaFree(h->d_counters); cudaFree(h->d_prof);
     cudaFree(h->d_dc); cudaFree(h->d_prev); cudaFree(h->d_len); cudaFree(h->d_tile_sum); cudaFree(h->d_bins); cudaFree(h->d_bins_total);
@@ -186,6 +196,13 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     ok = ok && cudaMalloc(&h->src_mem, pe * 2) == cudaSuccess;
     for (int i = 0; i < cfg->ref_count; ++i) ok = ok && cudaMalloc(&h->ring_mem[i], pe * 2) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_rgb, rgb_bytes) == cudaSuccess;
+    // evxgpu_encode_upload: second input buffer, its copy stream and events (allocated here: a cudaMalloc in the
+    // middle of a run would stall every stream of the device)
+    ok = ok && cudaMalloc(&h->d_rgb_up, rgb_bytes) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_k1, cudaEventDisableTiming) == cudaSuccess;
+    h->up_ready = ok;
     ok = ok && cudaMalloc(&h->d_table, (size_t) h->nmb * 16) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_inter, (size_t) h->nmb * (cfg->ref_count - 1) * sizeof(EvxInterResult)) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_records, (size_t) h->nmb * 384 * 2) == cudaSuccess;
@@ -292,6 +309,30 @@ int evxgpu_enable_timing(evxgpu_handle *h, int on) { if (!h) return 1; h->timing
 
 static void t_begin(evxgpu_handle *h, int k) { if (h->timing) { cudaEventRecord(h->ev[k][0], h->stream); } }
 static void t_end(evxgpu_handle *h, int k) { if (h->timing) { cudaEventRecord(h->ev[k][1], h->stream); h->ev_valid[k] = true; } }
+
+// folds the events of the last submitted frame into the running sums (its kernels have been queued; the
+// last event is waited for, which costs nothing once the frame has been collected)
+static void t_fold(evxgpu_handle *h)
+{
+    if (!h->t_pending) return;
+    h->t_pending = false;
+    for (int k = 0; k < EVXGPU_T_COUNT; ++k)
+    {
+        if (!h->ev_valid[k]) continue;
+        float ms = 0.f;
+        if (cudaEventSynchronize(h->ev[k][1]) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev[k][0], h->ev[k][1]) == cudaSuccess) h->t_sum[k] += ms;
+        h->ev_valid[k] = false;
+    }
+}
+
+int evxgpu_get_timing_sum(evxgpu_handle *h, double *ms_out, int reset)
+{
+    if (!h || !ms_out) return 1;
+    CK(cudaSetDevice(h->device));
+    t_fold(h);
+    for (int k = 0; k < EVXGPU_T_COUNT; ++k) { ms_out[k] = h->t_sum[k]; if (reset) h->t_sum[k] = 0.0; }
+    return 0;
+}
 
 int evxgpu_get_timing(evxgpu_handle *h, float *ms_out)
 {
@@ -457,12 +498,28 @@ int evxgpu_set_output(evxgpu_handle *h, int mode)
     return 0;
 }
 
+int evxgpu_encode_upload(evxgpu_handle *h, const uint8_t *rgb_host)
+{
+    if (!h || !rgb_host) return fail(1, "evxgpu_encode_upload: bad argument");
+    if (h->uploaded) return fail(8, "evxgpu_encode_upload: the previous upload has not been submitted");
+    CK(cudaSetDevice(h->device));
+    if (!h->up_ready) return fail(8, "evxgpu_encode_upload: the handle has no upload stream");
+    CK(cudaStreamWaitEvent(h->copy_stream, h->ev_k1, 0));       // the frame uploaded before has been converted
+    CK(cudaMemcpyAsync(h->d_rgb_up, rgb_host, (size_t) h->g.vw * h->g.vh * 3, cudaMemcpyHostToDevice, h->copy_stream));
+    CK(cudaEventRecord(h->ev_up, h->copy_stream));
+    h->uploaded = true;
+    return 0;
+}
+
 int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device, int frame_type, uint32_t frame_index, int quality)
 {
+    if (h && !rgb && h->uploaded) { rgb = h->d_rgb_up; rgb_is_device = 2; }
     if (!h || !rgb || quality < 1 || quality > 31 || (frame_type != 0 && frame_type != 1)) return fail(1, "evxgpu_encode_submit: bad argument");
     if (h->pending_encode) return fail(8, "evxgpu_encode_submit: previous frame not collected");
     CK(cudaSetDevice(h->device));
+    if (h->timing) t_fold(h);
     const uint8_t *d_rgb = rgb;
+    if (rgb_is_device == 2) { CK(cudaStreamWaitEvent(h->stream, h->ev_up, 0)); h->uploaded = false; }
     if (!rgb_is_device)
     {
         CK(cudaMemcpyAsync(h->d_rgb, rgb, (size_t) h->g.vw * h->g.vh * 3, cudaMemcpyHostToDevice, h->stream));
@@ -471,6 +528,7 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     int rc;
     h->d2h_bytes = 0;
     if ((rc = launch_convert_in(h, d_rgb))) return rc;
+    if (rgb_is_device == 2) CK(cudaEventRecord(h->ev_k1, h->stream));
     if (frame_type == 1 && (rc = launch_inter_search(h, frame_index, quality))) return rc;
     if ((rc = launch_wavefront(h, frame_type, frame_index, quality))) return rc;
     // the results leave before deblocking so the copies (and the host's entropy stage) overlap it
@@ -495,6 +553,7 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     CK(cudaEventRecord(h->ev_out, h->stream));
     if ((rc = launch_deblock(h, frame_index))) return rc;
     h->pending_encode = true;
+    h->t_pending = h->timing;
     return 0;
 }
 

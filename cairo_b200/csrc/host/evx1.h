@@ -139,8 +139,8 @@ public:
     // returns; collect appends what encode() would have appended for the oldest uncollected frame (stream
     // header on the first frame, frame descriptor, slice).  One frame may be uncollected when submit is
     // called: submit(n+1) first waits for frame n's device results, then starts frame n+1, so collect(n)
-    // runs the entropy coder while the device encodes frame n+1.  `image` must stay unchanged until the next
-    // submit() or collect() returns.  A second uncollected frame makes submit (and any uncollected frame
+    // runs the entropy coder while the device encodes frame n+1 (whose host->device copy already ran under frame n's
+    // kernels).  `image` must stay unchanged until the next submit() or the frame's own collect() returns.  A second uncollected frame makes submit (and any uncollected frame
     // makes encode) return EVX_ERROR_NOT_READY; collect with nothing submitted returns the same.
     virtual evx_status submit(void *image, uint32 width, uint32 height) = 0;
     virtual evx_status collect(bit_stream *output) = 0;

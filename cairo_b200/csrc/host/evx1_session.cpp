@@ -185,13 +185,17 @@ public:
             first = true;
         }
         if (width != header_.frame_width || height != header_.frame_height) return EVX_ERROR_INVALID_RESOURCE;
+        const uint8 *rgb = static_cast<const uint8 *>(image);
         if (on_device_.valid)
         {
+            // the new frame's host->device copy runs under the kernels of the frame still on the device
+            if (evxgpu_encode_upload(gpu_, rgb)) return EVX_ERROR_EXECUTION_FAILURE;
+            rgb = NULL;
             evx_status st = retire();
             if (evx_failed(st)) return st;
         }
         const double t0 = now_ms();
-        int rc = evxgpu_encode_submit(gpu_, static_cast<const uint8 *>(image), 0, (int) frame_.type, frame_.index, (int) frame_.quality);
+        int rc = evxgpu_encode_submit(gpu_, rgb, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
         if (rc) return EVX_ERROR_EXECUTION_FAILURE;
         memset(&on_device_, 0, sizeof(on_device_));
         on_device_.valid = true; on_device_.first = first; on_device_.desc = frame_; on_device_.t_submit = t0;

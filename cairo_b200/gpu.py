@@ -63,6 +63,7 @@ def lib():
     L.evxgpu_poke_plane.argtypes = [vp, i32, i32, i32, vp]
     L.evxgpu_get_timing.argtypes = [vp, C.POINTER(C.c_float)]
     L.evxgpu_enable_timing.argtypes = [vp, i32]
+    L.evxgpu_get_timing_sum.argtypes = [vp, C.POINTER(C.c_double), i32]
     L.evxgpu_get_counters.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), i32]
     L.evxgpu_get_counters_split.argtypes = [vp, C.POINTER(C.c_uint64), i32]
     L.evxgpu_set_encode_grid.argtypes = [vp, i32]
@@ -195,6 +196,12 @@ class Pipeline:
         _check(self.L.evxgpu_get_timing(self.h, ms), "evxgpu_get_timing")
         return dict(zip(T_NAMES, [float(v) for v in ms]))
 
+    def timing_sum(self, reset=False):
+        """Kernel times (ms) summed over the frames encoded since the last reset."""
+        buf = (C.c_double * len(T_NAMES))()
+        _check(self.L.evxgpu_get_timing_sum(self.h, buf, 1 if reset else 0), "evxgpu_get_timing_sum")
+        return {n: buf[i] for i, n in enumerate(T_NAMES)}
+
     def counters(self, reset=False):
         a, b = C.c_uint64(0), C.c_uint64(0)
         _check(self.L.evxgpu_get_counters(self.h, C.byref(a), C.byref(b), int(reset)), "evxgpu_get_counters")
@@ -208,6 +215,9 @@ class Pipeline:
 
     def set_encode_grid(self, ctas):
         _check(self.L.evxgpu_set_encode_grid(self.h, int(ctas)), "evxgpu_set_encode_grid")
+
+    def d2h_bytes(self):
+        return int(self.L.evxgpu_d2h_bytes(self.h))
 
     def launch_count(self):
         return int(self.L.evxgpu_launch_count(self.h))

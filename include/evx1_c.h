@@ -27,7 +27,7 @@ int evx1c_encoder_encode(evx1c_encoder *e, const uint8_t *rgb, uint32_t width, u
                          uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits);
 /* evx1_encoder::submit / collect (additions of this build: encode == submit + collect; submit(n+1) before
  * collect(n) overlaps the host entropy stage of frame n with the device's work on frame n+1).  rgb must stay
- * unchanged until the next submit or collect returns. */
+ * unchanged until the next submit or the frame's own collect returns. */
 int evx1c_encoder_submit(evx1c_encoder *e, const uint8_t *rgb, uint32_t width, uint32_t height);
 int evx1c_encoder_collect(evx1c_encoder *e, uint8_t *out, uint32_t out_cap_bytes, uint32_t *out_bits);
 /* evx1_encoder::peek (evx1enc.cpp:170-305); state = EVX_PEEK_STATE (0 source, 2 block table, 3 quant table, 4 sub-pel

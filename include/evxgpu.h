@@ -86,6 +86,11 @@ int evxgpu_upload(evxgpu_handle *h, void *dst_device, const void *src_host, uint
 int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device,
                          int frame_type, uint32_t frame_index, int quality);
 int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_t *records_out, uint32_t *n_noncopy);
+/* Optional early copy of the NEXT frame: may be called while a frame is still in flight; the host->device copy
+ * runs on a second stream under the current frame's kernels.  The following evxgpu_encode_submit takes rgb = NULL
+ * and uses the uploaded frame.  rgb_host must stay unchanged until that submit's frame has been collected (or the
+ * handle synchronised). */
+int evxgpu_encode_upload(evxgpu_handle *h, const uint8_t *rgb_host);
 
 /* The same slice as the string of bins serialize_slice feeds its arithmetic coder (serialize.cpp:156-340:
  * block table by field, then the Y, U, V residual blocks; raw bits and Exp-Golomb codes of golomb.cpp:8-91,
@@ -124,6 +129,8 @@ int evxgpu_peek_table(evxgpu_handle *h, evxgpu_block_desc *table_out);
 /* per-kernel device time of the last submitted frame, CUDA events on the handle's stream (ms) */
 int evxgpu_get_timing(evxgpu_handle *h, float *ms_out /* [EVXGPU_T_COUNT] */);
 int evxgpu_enable_timing(evxgpu_handle *h, int on);
+/* the same, summed over the encoded frames since the last reset (no per-frame synchronisation by the caller) */
+int evxgpu_get_timing_sum(evxgpu_handle *h, double *ms_out /* [EVXGPU_T_COUNT] */, int reset);
 /* evaluated full-pel candidates / sub-pel tests since the last reset (SURVEY 8d roofline unit) */
 int evxgpu_get_counters(evxgpu_handle *h, uint64_t *fullpel, uint64_t *subpel, int reset);
 /* the same split by kernel: out4 = { inter full-pel, inter sub-pel, intra full-pel, intra sub-pel } */
