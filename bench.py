@@ -227,7 +227,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from cairo_b200 import api, gpu, synth, build
-    build.build_all()
+    # the libraries travel prebuilt; a rebuild (stale timestamps) is done by one rank only
+    if rank == 0:
+        build.build_all()
+    if world > 1:
+        dist.barrier()
 
     steps, warmup = args.steps, max(3, args.warmup)
     nframes = warmup + steps
