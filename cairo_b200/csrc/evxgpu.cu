@@ -81,10 +81,11 @@ struct evxgpu_handle
     uint8_t *h_rgb;
 
     bool timing;
-    cudaEvent_t ev[EVXGPU_T_COUNT][2];
-    bool ev_valid[EVXGPU_T_COUNT];
+    cudaEvent_t ev[2][EVXGPU_T_COUNT][2];   // [frame slot][kernel][begin, end]
+    bool ev_valid[2][EVXGPU_T_COUNT];
     double t_sum[EVXGPU_T_COUNT];   // accumulated kernel times of the frames since evxgpu_get_timing_sum(reset)
-    bool t_pending;                 // the last submitted frame's events are not in t_sum yet
+    bool t_pending[2];              // the slot's events are not in t_sum yet
+    int slot;                       // frame slot of the launches being queued / last queued
     uint64_t launches;
     bool pending_encode, pending_decode;
     int wave_grid;
@@ -95,15 +96,21 @@ struct evxgpu_handle
     int out_mode;                   // 0 table+records, 1 bins, 2 both
     int16_t *d_dc;                  // persistent DC mirror [4][nmb]
     int *d_prev;                    // prev_motion[nmb], prev_coded[nmb], row_last[2][mbh] (written by K3)
-    uint32_t *d_len, *d_tile_sum, *d_bins, *d_bins_total;
-    uint32_t bins_cap_bits;         // capacity of d_bins
-    uint32_t *h_bins;               // pinned: [0..3] total, overflow, non-copy count; [4..] the string
-    uint32_t h_bins_cap_bits;
-    uint32_t bins_prefix_bits;      // how much of the string the submit already copied
-    cudaEvent_t ev_out;
-    bool pending_bins;
+    uint32_t *d_len, *d_tile_sum;
+    // Two frame slots: in bin-only output mode a second frame may be queued behind the one in flight (its
+    // kernels start the moment the first one's end, the host is still busy with the first one's bins).
+    uint32_t *d_bins[2], *d_bins_total[2];
+    uint32_t bins_cap_bits;         // capacity of each d_bins
+    uint32_t bins_worst_bits;       // no slice of this geometry can be longer (evx_bins.cuh)
+    uint32_t *h_bins[2];            // pinned: [0..3] total, overflow, non-copy count; [4..] the string
+    uint32_t h_bins_cap_bits[2];
+    uint32_t bins_prefix_bits[2];   // how much of the string the submit already copied
+    cudaEvent_t ev_out[2];
+    bool pending_bins[2];
+    uint64_t d2h_bytes[2];          // device-to-host bytes of the slot's frame
+    int q_head, q_count;            // queue of submitted, uncollected frames: slots q_head, q_head ^ 1
+    int last_slot;                  // slot of the last collected frame (evxgpu_d2h_bytes)
     uint32_t bins_last_total;       // bin count of the previous frame (sizes the optimistic head copy)
-    uint64_t d2h_bytes;             // device-to-host bytes of the frame in flight / last collected
 };
 
 static size_t plane_elems(const EvxGeom &g) { return (size_t) g.w * g.h * 3 / 2; }
@@ -155,11 +162,10 @@ int evxgpu_destroy(evxgpu_handle *h)
     if (h->ev_k1) cudaEventDestroy(h->ev_k1);
     cudaFree(h->d_rgb); cudaFree(h->d_table); cudaFree(h->d_inter); cudaFree(h->d_records); cudaFree(h->d_dense); cudaFree(h->d_row_records);
     cudaFree(h->d_record_slot); cudaFree(h->d_sync); cudaFree(h->d_done); cudaFree(h->d_counters); cudaFree(h->d_prof);
-    cudaFree(h->d_dc); cudaFree(h->d_prev); cudaFree(h->d_len); cudaFree(h->d_tile_sum); cudaFree(h->d_bins); cudaFree(h->d_bins_total);
-    cudaFreeHost(h->h_bins);
-    if (h->ev_out) cudaEventDestroy(h->ev_out);
+    cudaFree(h->d_dc); cudaFree(h->d_prev); cudaFree(h->d_len); cudaFree(h->d_tile_sum);
+    for (int q = 0; q < 2; ++q) { cudaFree(h->d_bins[q]); cudaFree(h->d_bins_total[q]); cudaFreeHost(h->h_bins[q]); if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]); }
     cudaFreeHost(h->h_table); cudaFreeHost(h->h_records); cudaFreeHost(h->h_record_slot); cudaFreeHost(h->h_sync); cudaFreeHost(h->h_rgb);
-    for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[k][e]) cudaEventDestroy(h->ev[k][e]);
+    for (int q = 0; q < 2; ++q) for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[q][k][e]) cudaEventDestroy(h->ev[q][k][e]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -212,18 +218,17 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     ok = ok && cudaMalloc(&h->d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_done, (size_t) h->nmb * 8) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_counters, 32) == cudaSuccess;
-    {   // K8 (bin string): 256 bins per macroblock to start with (a 1080p intra frame needs ~45); grown on demand
+    {   // K8 (bin string): the scratch every encoder needs; the string buffers come with evxgpu_set_output
         const size_t ntiles = ((size_t) EVX_BINS_ITEMS * h->nmb + EVX_BINS_TILE - 1) / EVX_BINS_TILE;
-        h->bins_cap_bits = (uint32_t) std::max<size_t>((size_t) h->nmb * 256, 1u << 16);
-        h->h_bins_cap_bits = h->bins_cap_bits;
+        // No slice can be longer than this (evx_bins.cuh): per macroblock 8 table fields (3 + 3 raw bits, three
+        // Exp-Golomb codes of at most 33 bins, 1 + 1 + 3 raw bits) and 6 blocks of a run code (13 bins) + 64 codes of
+        // at most 33 bins each.
+        h->bins_worst_bits = (uint32_t) std::min<uint64_t>(((uint64_t) h->nmb * (110 + 6 * (13 + 64 * 33)) + 63) & ~63ull, 0xFFFFFFC0ull);
         ok = ok && cudaMalloc(&h->d_dc, (size_t) h->nmb * 4 * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&h->d_prev, ((size_t) h->nmb * 2 + (size_t) h->g.mbh * 2) * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&h->d_len, (size_t) EVX_BINS_ITEMS * h->nmb * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&h->d_tile_sum, ntiles * 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&h->d_bins, (size_t) h->bins_cap_bits / 8 + 8) == cudaSuccess;
-        ok = ok && cudaMalloc(&h->d_bins_total, 16) == cudaSuccess;
-        ok = ok && cudaHostAlloc(&h->h_bins, (size_t) h->h_bins_cap_bits / 8 + 32, cudaHostAllocDefault) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) == cudaSuccess;
+        for (int q = 0; q < 2; ++q) ok = ok && cudaEventCreateWithFlags(&h->ev_out[q], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaHostAlloc(&h->h_table, (size_t) h->nmb * 16, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&h->h_records, (size_t) h->nmb * 384 * 2, cudaHostAllocDefault) == cudaSuccess;
@@ -262,7 +267,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     }
     for (int k = 0; k < EVXGPU_T_COUNT; ++k)
         for (int e = 0; e < 2; ++e)
-            if (cudaEventCreate(&h->ev[k][e]) != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaEventCreate"); }
+            if (cudaEventCreate(&h->ev[0][k][e]) != cudaSuccess || cudaEventCreate(&h->ev[1][k][e]) != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaEventCreate"); }
     // enough CTAs to cover the widest wavefront plus a few to prefetch the next step
     h->wave_grid = std::min(h->nmb, 148 * 8);      // persistent CTAs of the decoder kernel
     // encoder wavefront: at most ceil(W/3) rows are ever active at once (row r runs during steps [3r, 3r+W));
@@ -286,13 +291,14 @@ int evxgpu_reset(evxgpu_handle *h)
     CK(cudaMemsetAsync(h->d_counters, 0, 32, h->stream));
     CK(cudaMemsetAsync(h->d_dc, 0, (size_t) h->nmb * 4 * 2, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->pending_encode = h->pending_decode = h->pending_bins = false;
+    h->pending_encode = h->pending_decode = h->pending_bins[0] = h->pending_bins[1] = false;
+    h->q_head = h->q_count = 0; h->uploaded = false;
     return 0;
 }
 
 int evxgpu_block_count(const evxgpu_handle *h) { return h ? h->nmb : 0; }
 int evxgpu_synchronize(evxgpu_handle *h) { if (!h) return 1; CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream)); return 0; }
-uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h) { return h ? h->d2h_bytes : 0; }
+uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h) { return h ? h->d2h_bytes[h->last_slot] : 0; }
 
 uint64_t evxgpu_launch_count(const evxgpu_handle *h) { return h ? h->launches : 0; }
 
@@ -307,21 +313,21 @@ int evxgpu_upload(evxgpu_handle *h, void *dst_device, const void *src_host, uint
 
 int evxgpu_enable_timing(evxgpu_handle *h, int on) { if (!h) return 1; h->timing = on != 0; return 0; }
 
-static void t_begin(evxgpu_handle *h, int k) { if (h->timing) { cudaEventRecord(h->ev[k][0], h->stream); } }
-static void t_end(evxgpu_handle *h, int k) { if (h->timing) { cudaEventRecord(h->ev[k][1], h->stream); h->ev_valid[k] = true; } }
+static void t_begin(evxgpu_handle *h, int k) { if (h->timing) { cudaEventRecord(h->ev[h->slot][k][0], h->stream); } }
+static void t_end(evxgpu_handle *h, int k) { if (h->timing) { cudaEventRecord(h->ev[h->slot][k][1], h->stream); h->ev_valid[h->slot][k] = true; } }
 
 // folds the events of the last submitted frame into the running sums (its kernels have been queued; the
 // last event is waited for, which costs nothing once the frame has been collected)
-static void t_fold(evxgpu_handle *h)
+static void t_fold(evxgpu_handle *h, int q)
 {
-    if (!h->t_pending) return;
-    h->t_pending = false;
+    if (!h->t_pending[q]) return;
+    h->t_pending[q] = false;
     for (int k = 0; k < EVXGPU_T_COUNT; ++k)
     {
-        if (!h->ev_valid[k]) continue;
+        if (!h->ev_valid[q][k]) continue;
         float ms = 0.f;
-        if (cudaEventSynchronize(h->ev[k][1]) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev[k][0], h->ev[k][1]) == cudaSuccess) h->t_sum[k] += ms;
-        h->ev_valid[k] = false;
+        if (cudaEventSynchronize(h->ev[q][k][1]) == cudaSuccess && cudaEventElapsedTime(&ms, h->ev[q][k][0], h->ev[q][k][1]) == cudaSuccess) h->t_sum[k] += ms;
+        h->ev_valid[q][k] = false;
     }
 }
 
@@ -329,7 +335,7 @@ int evxgpu_get_timing_sum(evxgpu_handle *h, double *ms_out, int reset)
 {
     if (!h || !ms_out) return 1;
     CK(cudaSetDevice(h->device));
-    t_fold(h);
+    t_fold(h, 0); t_fold(h, 1);
     for (int k = 0; k < EVXGPU_T_COUNT; ++k) { ms_out[k] = h->t_sum[k]; if (reset) h->t_sum[k] = 0.0; }
     return 0;
 }
@@ -342,7 +348,7 @@ int evxgpu_get_timing(evxgpu_handle *h, float *ms_out)
     for (int k = 0; k < EVXGPU_T_COUNT; ++k)
     {
         ms_out[k] = 0.f;
-        if (h->ev_valid[k]) cudaEventElapsedTime(&ms_out[k], h->ev[k][0], h->ev[k][1]);
+        if (h->ev_valid[h->slot][k]) cudaEventElapsedTime(&ms_out[k], h->ev[h->slot][k][0], h->ev[h->slot][k][1]);
     }
     return 0;
 }
@@ -461,7 +467,7 @@ static EvxBinsParams bins_params(evxgpu_handle *h)
     EvxBinsParams p;
     p.table = h->d_table; p.records = h->d_records; p.dc = h->d_dc;
     p.prev_motion = h->d_prev; p.prev_coded = h->d_prev + h->nmb; p.row_last = h->d_prev + 2 * h->nmb; p.row_records = h->d_row_records;
-    p.len = h->d_len; p.tile_sum = h->d_tile_sum; p.bins = h->d_bins; p.total = h->d_bins_total;
+    p.len = h->d_len; p.tile_sum = h->d_tile_sum; p.bins = h->d_bins[h->slot]; p.total = h->d_bins_total[h->slot];
     p.cap_bits = h->bins_cap_bits;
     p.mbw = h->g.mbw; p.mbh = h->g.mbh; p.nmb = h->nmb;
     int tb = 0;
@@ -474,7 +480,7 @@ static int launch_bins(evxgpu_handle *h, bool emit_only)
 {
     const EvxBinsParams p = bins_params(h);
     const int ntiles = (EVX_BINS_ITEMS * h->nmb + EVX_BINS_TILE - 1) / EVX_BINS_TILE;
-    CK(cudaMemsetAsync(h->d_bins, 0, (size_t) h->bins_cap_bits / 8 + 8, h->stream));
+    CK(cudaMemsetAsync(h->d_bins[h->slot], 0, (size_t) h->bins_cap_bits / 8 + 8, h->stream));
     t_begin(h, EVXGPU_T_BINS);
     if (!emit_only)
     {
@@ -490,10 +496,36 @@ static int launch_bins(evxgpu_handle *h, bool emit_only)
 
 // ------------------------------------------------------------------ encoder
 
+// (re)allocates the two slots' string buffers: device capacity cap_bits each, pinned host capacity hcap_bits each
+static int alloc_bins(evxgpu_handle *h, uint32_t cap_bits, uint32_t hcap_bits)
+{
+    for (int q = 0; q < 2; ++q)
+    {
+        cudaFree(h->d_bins[q]); h->d_bins[q] = NULL;
+        cudaFreeHost(h->h_bins[q]); h->h_bins[q] = NULL;
+        if (!h->d_bins_total[q] && cudaMalloc(&h->d_bins_total[q], 16) != cudaSuccess) return fail(3, "bin buffers: out of device memory");
+        if (cudaMalloc(&h->d_bins[q], (size_t) cap_bits / 8 + 8) != cudaSuccess) return fail(3, "bin buffers: out of device memory");
+        if (cudaHostAlloc(&h->h_bins[q], (size_t) hcap_bits / 8 + 32, cudaHostAllocDefault) != cudaSuccess) return fail(3, "bin buffers: out of pinned memory");
+        h->h_bins_cap_bits[q] = hcap_bits;
+    }
+    h->bins_cap_bits = cap_bits;
+    return 0;
+}
+
 int evxgpu_set_output(evxgpu_handle *h, int mode)
 {
     if (!h || mode < 0 || mode > 2) return fail(1, "evxgpu_set_output: bad argument");
     if (h->pending_encode) return fail(8, "evxgpu_set_output: a frame is in flight");
+    CK(cudaSetDevice(h->device));
+    if (mode != 0 && !h->d_bins[0])
+    {
+        // device: the longest slice this geometry can produce, so the string always fits (and a second frame may be
+        // queued behind the first); pinned host side: 256 bins per macroblock to start with (a 1080p intra frame needs
+        // about 45), grown on demand
+        CK(cudaStreamSynchronize(h->stream));
+        int rc = alloc_bins(h, h->bins_worst_bits, (uint32_t) std::max<size_t>((size_t) h->nmb * 256, 1u << 16));
+        if (rc) return rc;
+    }
     h->out_mode = mode;
     return 0;
 }
@@ -515,9 +547,13 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
 {
     if (h && !rgb && h->uploaded) { rgb = h->d_rgb_up; rgb_is_device = 2; }
     if (!h || !rgb || quality < 1 || quality > 31 || (frame_type != 0 && frame_type != 1)) return fail(1, "evxgpu_encode_submit: bad argument");
-    if (h->pending_encode) return fail(8, "evxgpu_encode_submit: previous frame not collected");
+    // one frame in flight -- or, with bin-only output and string buffers that cannot overflow, a second one queued behind it
+    if (h->q_count >= 2 || (h->q_count == 1 && !(h->out_mode == 1 && h->bins_cap_bits >= h->bins_worst_bits)))
+        return fail(8, "evxgpu_encode_submit: previous frame not collected");
     CK(cudaSetDevice(h->device));
-    if (h->timing) t_fold(h);
+    const int q = (h->q_head + h->q_count) & 1;
+    h->slot = q;
+    if (h->timing) t_fold(h, q);                 // the frame that used this slot before was collected long ago
     const uint8_t *d_rgb = rgb;
     if (rgb_is_device == 2) { CK(cudaStreamWaitEvent(h->stream, h->ev_up, 0)); h->uploaded = false; }
     if (!rgb_is_device)
@@ -526,7 +562,7 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
         d_rgb = h->d_rgb;
     }
     int rc;
-    h->d2h_bytes = 0;
+    h->d2h_bytes[q] = 0;
     if ((rc = launch_convert_in(h, d_rgb))) return rc;
     if (rgb_is_device == 2) CK(cudaEventRecord(h->ev_k1, h->stream));
     if (frame_type == 1 && (rc = launch_inter_search(h, frame_index, quality))) return rc;
@@ -536,7 +572,7 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     {
         CK(cudaMemcpyAsync(h->h_sync, h->d_sync, 8, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(h->h_table, h->d_table, (size_t) h->nmb * 16, cudaMemcpyDeviceToHost, h->stream));
-        h->d2h_bytes += 8 + (size_t) h->nmb * 16;
+        h->d2h_bytes[q] += 8 + (size_t) h->nmb * 16;
     }
     if (h->out_mode != 0)
     {
@@ -544,57 +580,69 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
         // the bin count and, optimistically, the head of the string in the same breath
         // (sized from the previous frame: consecutive slices are of similar length; a longer one costs a second copy)
         const uint32_t guess = h->bins_last_total ? ((h->bins_last_total + h->bins_last_total / 4 + 8192) & ~63u) : 1u << 19;
-        h->bins_prefix_bits = std::min<uint32_t>(std::min(h->bins_cap_bits, h->h_bins_cap_bits), std::min<uint32_t>(guess, 1u << 22));
-        CK(cudaMemcpyAsync(h->h_bins, h->d_bins_total, 16, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_bins + 4, h->d_bins, h->bins_prefix_bits / 8, cudaMemcpyDeviceToHost, h->stream));
-        h->d2h_bytes += 16 + h->bins_prefix_bits / 8;
-        h->pending_bins = true;
+        h->bins_prefix_bits[q] = std::min<uint32_t>(std::min(h->bins_cap_bits, h->h_bins_cap_bits[q]), std::min<uint32_t>(guess, 1u << 22));
+        CK(cudaMemcpyAsync(h->h_bins[q], h->d_bins_total[q], 16, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_bins[q] + 4, h->d_bins[q], h->bins_prefix_bits[q] / 8, cudaMemcpyDeviceToHost, h->stream));
+        h->d2h_bytes[q] += 16 + h->bins_prefix_bits[q] / 8;
+        h->pending_bins[q] = true;
     }
-    CK(cudaEventRecord(h->ev_out, h->stream));
+    CK(cudaEventRecord(h->ev_out[q], h->stream));
     if ((rc = launch_deblock(h, frame_index))) return rc;
+    h->q_count++;
     h->pending_encode = true;
-    h->t_pending = h->timing;
+    h->t_pending[q] = h->timing;
     return 0;
 }
 
 int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins_out, uint64_t *nbins, uint32_t *n_noncopy)
 {
     if (!h || !bins_out || !nbins) return fail(1, "evxgpu_encode_collect_bins: bad argument");
-    if (!h->pending_encode || !h->pending_bins) return fail(15, "evxgpu_encode_collect_bins: no frame submitted with bin output enabled (evxgpu_set_output)");
+    const int q = h ? h->q_head : 0;
+    if (!h->q_count || !h->pending_bins[q]) return fail(15, "evxgpu_encode_collect_bins: no frame submitted with bin output enabled (evxgpu_set_output)");
     CK(cudaSetDevice(h->device));
-    CK(cudaEventSynchronize(h->ev_out));
-    const uint32_t total = h->h_bins[0], coded = h->h_bins[2];
-    if (h->h_bins[1])
-    {   // the string outgrew the device buffer: enlarge it and emit again (lengths and tile sums stand)
+    CK(cudaEventSynchronize(h->ev_out[q]));
+    const uint32_t total = h->h_bins[q][0], coded = h->h_bins[q][2];
+    // what is left to copy goes over the copy stream: the main stream may already hold the next frame's kernels
+    cudaStream_t cs = h->q_count > 1 ? h->copy_stream : h->stream;
+    if (h->h_bins[q][1])
+    {   // the string outgrew the device buffer (only possible with a capacity below the worst case, see
+        // evxgpu_debug_set_bins_capacity, and then only one frame is in flight): enlarge both slots and emit again
+        // (lengths and tile sums stand)
+        if (h->q_count > 1) return fail(7, "evxgpu_encode_collect_bins: bin string overflow with a second frame queued");
         CK(cudaStreamSynchronize(h->stream));
-        cudaFree(h->d_bins); h->d_bins = NULL;
         const uint64_t want = ((uint64_t) total + total / 2 + 4096) & ~63ull;
         if (want > 0xFFFFFFFFull) return fail(3, "evxgpu_encode_collect_bins: slice of more than 2^32 bins");
+        for (int k = 0; k < 2; ++k)
+        {
+            cudaFree(h->d_bins[k]); h->d_bins[k] = NULL;
+            if (cudaMalloc(&h->d_bins[k], (size_t) want / 8 + 8) != cudaSuccess) return fail(3, "evxgpu_encode_collect_bins: out of device memory");
+        }
         h->bins_cap_bits = (uint32_t) want;
-        if (cudaMalloc(&h->d_bins, (size_t) h->bins_cap_bits / 8 + 8) != cudaSuccess) return fail(3, "evxgpu_encode_collect_bins: out of device memory");
+        h->slot = q;
         int rc = launch_bins(h, true);
         if (rc) return rc;
-        h->bins_prefix_bits = 0;
+        h->bins_prefix_bits[q] = 0;
     }
-    if (total > h->h_bins_cap_bits)
+    if (total > h->h_bins_cap_bits[q])
     {
-        CK(cudaStreamSynchronize(h->stream));
-        cudaFreeHost(h->h_bins); h->h_bins = NULL;
-        h->h_bins_cap_bits = (uint32_t) std::min<uint64_t>(((uint64_t) total + total / 2 + 4096) & ~63ull, 0xFFFFFFC0ull);
-        if (cudaHostAlloc(&h->h_bins, (size_t) h->h_bins_cap_bits / 8 + 32, cudaHostAllocDefault) != cudaSuccess) return fail(3, "evxgpu_encode_collect_bins: out of pinned memory");
-        h->bins_prefix_bits = 0;
+        CK(cudaStreamSynchronize(cs));
+        cudaFreeHost(h->h_bins[q]); h->h_bins[q] = NULL;
+        h->h_bins_cap_bits[q] = (uint32_t) std::min<uint64_t>(((uint64_t) total + total / 2 + 4096) & ~63ull, 0xFFFFFFC0ull);
+        if (cudaHostAlloc(&h->h_bins[q], (size_t) h->h_bins_cap_bits[q] / 8 + 32, cudaHostAllocDefault) != cudaSuccess) return fail(3, "evxgpu_encode_collect_bins: out of pinned memory");
+        h->bins_prefix_bits[q] = 0;
     }
-    if (total > h->bins_prefix_bits)
+    if (total > h->bins_prefix_bits[q])
     {   // the tail (or everything, after a re-emit)
-        const size_t from = h->bins_prefix_bits / 8, to = ((size_t) total + 7) / 8;
-        CK(cudaMemcpyAsync((uint8_t *) (h->h_bins + 4) + from, (const uint8_t *) h->d_bins + from, to - from, cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        h->d2h_bytes += to - from;
+        const size_t from = h->bins_prefix_bits[q] / 8, to = ((size_t) total + 7) / 8;
+        CK(cudaMemcpyAsync((uint8_t *) (h->h_bins[q] + 4) + from, (const uint8_t *) h->d_bins[q] + from, to - from, cudaMemcpyDeviceToHost, cs));
+        CK(cudaStreamSynchronize(cs));
+        h->d2h_bytes[q] += to - from;
     }
-    h->pending_bins = false;
+    h->pending_bins[q] = false;
     h->bins_last_total = total;
-    if (h->out_mode == 1) h->pending_encode = false;
-    *bins_out = reinterpret_cast<const uint64_t *>(h->h_bins + 4);
+    h->last_slot = q;
+    if (h->out_mode == 1) { h->q_head ^= 1; h->q_count--; h->pending_encode = h->q_count > 0; }
+    *bins_out = reinterpret_cast<const uint64_t *>(h->h_bins[q] + 4);
     *nbins = total;
     if (n_noncopy) *n_noncopy = coded;
     return 0;
@@ -607,7 +655,9 @@ int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_
     if (h->out_mode == 1) return fail(15, "evxgpu_encode_collect: the handle outputs bins only (evxgpu_set_output)");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    h->pending_encode = false;
+    const int q = h->q_head;
+    h->last_slot = q;
+    h->q_head ^= 1; h->q_count = 0; h->pending_encode = false;
     const int n = h->h_sync[1];
     if (n < 0 || n > h->nmb) return fail(5, "evxgpu_encode_collect: corrupt record counter");
     memcpy(table_out, h->h_table, (size_t) h->nmb * 16);
@@ -618,7 +668,7 @@ int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_
         // (asynchronous DMA when that buffer is pinned, see evxgpu_host_alloc)
         CK(cudaMemcpyAsync(records_out, h->d_dense, (size_t) n * 384 * 2, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
-        h->d2h_bytes += (size_t) n * 384 * 2;
+        h->d2h_bytes[q] += (size_t) n * 384 * 2;
     }
     return 0;
 }
@@ -736,12 +786,7 @@ int evxgpu_debug_set_bins_capacity(evxgpu_handle *h, uint32_t bits)
     if (!h || bits < 64 || h->pending_encode) return fail(1, "evxgpu_debug_set_bins_capacity: bad argument");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_bins); h->d_bins = NULL;
-    cudaFreeHost(h->h_bins); h->h_bins = NULL;
-    h->bins_cap_bits = h->h_bins_cap_bits = bits & ~63u;
-    if (cudaMalloc(&h->d_bins, (size_t) h->bins_cap_bits / 8 + 8) != cudaSuccess) return fail(3, "evxgpu_debug_set_bins_capacity: out of device memory");
-    if (cudaHostAlloc(&h->h_bins, (size_t) h->h_bins_cap_bits / 8 + 32, cudaHostAllocDefault) != cudaSuccess) return fail(3, "evxgpu_debug_set_bins_capacity: out of pinned memory");
-    return 0;
+    return alloc_bins(h, bits & ~63u, bits & ~63u);
 }
 
 int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas)

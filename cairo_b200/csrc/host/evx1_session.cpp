@@ -80,7 +80,8 @@ class encoder_session : public evx1_encoder
         uint32 n_noncopy, d2h_bytes;
         uint64_t nbins;
     };
-    pending_frame on_device_, retired_;
+    pending_frame dev_[2], retired_;               // dev_[0] is the older of the frames on the device
+    int dev_count_;
     std::vector<uint64_t> bins_;                   // retired frame, bin output
     std::vector<evxgpu_block_desc> table_;         // retired frame, table + records output
     std::vector<int16> records_;
@@ -121,8 +122,9 @@ class encoder_session : public evx1_encoder
     // library's staging buffers for the next submit.
     evx_status retire()
     {
-        pending_frame f = on_device_;
-        on_device_.valid = false;
+        pending_frame f = dev_[0];
+        dev_[0] = dev_[1];
+        dev_count_--;
         int rc;
         if (device_bins_)
         {
@@ -149,8 +151,9 @@ public:
     {
         memset(&stats_, 0, sizeof(stats_));
         memset(&header_, 0, sizeof(header_));
-        memset(&on_device_, 0, sizeof(on_device_));
+        memset(dev_, 0, sizeof(dev_));
         memset(&retired_, 0, sizeof(retired_));
+        dev_count_ = 0;
         clear_frame();
     }
     ~encoder_session() { clear(); }
@@ -160,7 +163,7 @@ public:
         if (!initialized_) return EVX_SUCCESS;
         clear_frame();
         if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }      // drains the stream; uncollected frames are dropped
-        on_device_.valid = retired_.valid = false;
+        dev_count_ = 0; retired_.valid = false;
         initialized_ = false;
         return EVX_SUCCESS;
     }
@@ -175,7 +178,7 @@ public:
     evx_status submit(void *image, uint32 width, uint32 height)
     {
         if (!width || !height || !image) return EVX_ERROR_INVALIDARG;
-        if (on_device_.valid && retired_.valid) return EVX_ERROR_NOT_READY;      // two frames uncollected
+        if (dev_count_ + (retired_.valid ? 1 : 0) > 1) return EVX_ERROR_NOT_READY;      // two frames uncollected
         bool first = false;
         if (!initialized_)
         {
@@ -186,19 +189,27 @@ public:
         }
         if (width != header_.frame_width || height != header_.frame_height) return EVX_ERROR_INVALID_RESOURCE;
         const uint8 *rgb = static_cast<const uint8 *>(image);
-        if (on_device_.valid)
-        {
-            // the new frame's host->device copy runs under the kernels of the frame still on the device
-            if (evxgpu_encode_upload(gpu_, rgb)) return EVX_ERROR_EXECUTION_FAILURE;
-            rgb = NULL;
-            evx_status st = retire();
-            if (evx_failed(st)) return st;
-        }
         const double t0 = now_ms();
-        int rc = evxgpu_encode_submit(gpu_, rgb, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
+        int rc;
+        if (dev_count_ == 1)
+        {
+            // the new frame's host->device copy runs under the kernels of the frame still on the device, and its own
+            // kernels are queued right behind them; a device library that takes one frame at a time (table + records
+            // output, or string buffers below the worst case) gets the older frame collected first
+            if (evxgpu_encode_upload(gpu_, rgb)) return EVX_ERROR_EXECUTION_FAILURE;
+            rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
+            if (rc == 8)
+            {
+                evx_status st = retire();
+                if (evx_failed(st)) return st;
+                rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
+            }
+        }
+        else rc = evxgpu_encode_submit(gpu_, rgb, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
         if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        memset(&on_device_, 0, sizeof(on_device_));
-        on_device_.valid = true; on_device_.first = first; on_device_.desc = frame_; on_device_.t_submit = t0;
+        pending_frame &f = dev_[dev_count_++];
+        memset(&f, 0, sizeof(f));
+        f.valid = true; f.first = first; f.desc = frame_; f.t_submit = t0;
 
         frame_.type = 1;                                                                   // EVX_ALLOW_INTER_FRAMES
         if (cfg_.periodic_intra > 0 && 0 == ((frame_.index + 1) % (uint32) cfg_.periodic_intra)) insert_intra();
@@ -213,7 +224,7 @@ public:
         if (!output) return EVX_ERROR_INVALIDARG;
         if (!retired_.valid)
         {
-            if (!on_device_.valid) return EVX_ERROR_NOT_READY;
+            if (!dev_count_) return EVX_ERROR_NOT_READY;
             evx_status st = retire();
             if (evx_failed(st)) return st;
         }
@@ -237,7 +248,7 @@ public:
     evx_status encode(void *image, uint32 width, uint32 height, bit_stream *output)        // evx1enc.cpp:92-156
     {
         if (!output || !width || !height || !image) return EVX_ERROR_INVALIDARG;
-        if (on_device_.valid || retired_.valid) return EVX_ERROR_NOT_READY;       // finish the pipelined frames with collect() first
+        if (dev_count_ || retired_.valid) return EVX_ERROR_NOT_READY;       // finish the pipelined frames with collect() first
         const frame_desc before = frame_;
         evx_status st = submit(image, width, height);
         if (evx_failed(st)) return st;
@@ -252,7 +263,7 @@ public:
     {
         if (!output) return EVX_ERROR_INVALIDARG;
         if (!initialized_) return EVX_SUCCESS;
-        if (on_device_.valid || retired_.valid) return EVX_ERROR_NOT_READY;
+        if (dev_count_ || retired_.valid) return EVX_ERROR_NOT_READY;
         const uint32 w = header_.frame_width, h = header_.frame_height, mbw = (w + 15) / 16;
         uint8 *out = static_cast<uint8 *>(output);
         switch (peek_state)

@@ -98,7 +98,11 @@ int evxgpu_encode_upload(evxgpu_handle *h, const uint8_t *rgb_host);
  * Only encode_symbol (abac.cpp:97-121) is left for the host: it walks bin i = bit (i & 63) of word (i >> 6).
  * set_output: 0 = table + records (default), 1 = bins only, 2 = both (collect_bins first, then collect).
  * The device keeps the DC state of serialize.cpp:59-72 across frames, so the mode is chosen once per stream.
- * collect_bins: *bins points into the handle's pinned buffer, valid until the next submit. */
+ * collect_bins: *bins points into the handle's pinned buffer, valid until the next-but-one submit.
+ * With mode 1 TWO frames may be in flight: a second evxgpu_encode_submit is accepted while the first frame is
+ * uncollected (its kernels are queued right behind the first frame's, so the device does not wait for the host);
+ * collect_bins returns the frames in order.  The device-side string buffers are sized for the longest slice the
+ * geometry can produce, so they cannot overflow.  Modes 0 and 2 take one frame at a time (status 8 otherwise). */
 int evxgpu_set_output(evxgpu_handle *h, int mode);
 int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins, uint64_t *nbins, uint32_t *n_noncopy /* may be NULL */);
 

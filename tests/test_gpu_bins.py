@@ -85,3 +85,39 @@ def test_public_encoder_both_binarisations(monkeypatch):
     assert len(a) == len(b)
     for x, y in zip(a, b):
         assert x == y
+
+
+def test_two_frames_queued_on_the_device():
+    """Bin-only output: a second frame may be queued behind the one in flight (evxgpu.h); the strings come back
+    in order and equal the one-at-a-time run.  With string buffers below the worst case the second submit is refused."""
+    from cairo_b200 import gpu
+    w, h, q, n = 352, 288, 16, 6
+    frames = [synth.frame(w, h, t, 5, "moving") for t in range(n)]
+    a = gpu.Pipeline(w, h, 2, 0, 1)
+    a.set_output(1)
+    want = []
+    for t in range(n):
+        a.encode_submit(frames[t], 0 if t == 0 else 1, t, q)
+        want.append(a.encode_collect_bins())
+    b = gpu.Pipeline(w, h, 2, 0, 1)
+    b.set_output(1)
+    got = []
+    b.encode_submit(frames[0], 0, 0, q)
+    for t in range(1, n):
+        b.encode_submit(frames[t], 1, t, q)
+        with pytest.raises(RuntimeError):
+            b.encode_submit(frames[t], 1, t + 1, q)          # a third frame
+        got.append(b.encode_collect_bins())
+    got.append(b.encode_collect_bins())
+    with pytest.raises(RuntimeError):
+        b.encode_collect_bins()
+    for t in range(n):
+        assert got[t][1] == want[t][1] and got[t][2] == want[t][2] and (got[t][0] == want[t][0]).all(), t
+    c = gpu.Pipeline(w, h, 2, 0, 1)
+    c.set_output(1)
+    c.set_bins_capacity(1 << 12)                              # far below the worst case: one frame at a time
+    c.encode_submit(frames[0], 0, 0, q)
+    with pytest.raises(RuntimeError):
+        c.encode_submit(frames[1], 1, 1, q)
+    words, nbins, coded = c.encode_collect_bins()             # grows and emits again
+    assert nbins == want[0][1] and (words == want[0][0]).all()
