@@ -199,10 +199,13 @@ def multi_stream_e2e(api, host, fidx, warmup, frames, n_streams, device):
             encs[i].encode((int(host[fidx(t)].data_ptr()), W, H))
         gate.wait()
         encs[i].submit((int(host[fidx(warmup)].data_ptr()), W, H))
-        for t in range(warmup + 1, warmup + frames):
+        if frames > 1:
+            encs[i].submit((int(host[fidx(warmup + 1)].data_ptr()), W, H))
+        for t in range(warmup + 2, warmup + frames):
             encs[i].submit((int(host[fidx(t)].data_ptr()), W, H))
             encs[i].collect()
-        encs[i].collect()
+        for _ in range(min(2, frames)):
+            encs[i].collect()
         gate.wait()
 
     th = [threading.Thread(target=work, args=(i,)) for i in range(n_streams)]
@@ -319,15 +322,20 @@ def run_ours(args):
     coded = []                                   # the K frames' bitstreams (a few KB each), for the decode extra
     barrier()
     t0 = time.perf_counter()
+    # two frames of lookahead: frame t is handed over while frame t-1 encodes and frame t-2 is being entropy-coded,
+    # so frame t's host->device copy runs under frame t-1's kernels
     enc.submit((int(host[fidx(warmup)].data_ptr()), W, H))
-    for t in range(warmup + 1, nframes):
+    if steps > 1:
+        enc.submit((int(host[fidx(warmup + 1)].data_ptr()), W, H))
+    for t in range(warmup + 2, nframes):
         enc.submit((int(host[fidx(t)].data_ptr()), W, H))
         d, b = enc.collect()
         out_bits += b
         coded.append((d.copy(), b))
-    d, b = enc.collect()
-    out_bits += b
-    coded.append((d.copy(), b))
+    for _ in range(min(2, steps)):
+        d, b = enc.collect()
+        out_bits += b
+        coded.append((d.copy(), b))
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if out_bits != sync_bits:
@@ -402,7 +410,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "value_scope": "frames resident in HBM -> K1 convert, K2 inter search, K3 wavefront, K8 binarisation, K4 deblocking -> the slice's bin string "
                                       "on the host (D2H inside the timed region, %d bytes per frame); host arithmetic coder excluded" % (value_d2h // max(1, steps)),
-                       "e2e_scope": "evx1_encoder::submit/collect (the two halves of encode, one frame in flight), pinned host RGB -> EVX1 bitstream bytes: "
+                       "e2e_scope": "evx1_encoder::submit/collect (the two halves of encode, two frames of lookahead), pinned host RGB -> EVX1 bitstream bytes: "
                                     "H2D, K1..K4 + device binarisation K8, D2H of the bin string, host arithmetic coder; all K bitstreams are on the host "
                                     "when the clock stops.  e2e.synchronous is the same through evx1_encoder::encode, one frame at a time",
                        "l2": f"{uniq} distinct 6.2 MB frames ({uniq * frame_bytes // 1000000} MB) cycle through, larger than the 126 MB L2"},

@@ -34,6 +34,8 @@ def lib():
     L.evx1c_encoder_submit.argtypes = [vp, vp, u32, u32]
     L.evx1c_encoder_collect.argtypes = [vp, vp, u32, C.POINTER(u32)]
     L.evx1c_encoder_peek.argtypes = [vp, i32, vp]
+    L.evx1c_encoder_wait_ms.restype = C.c_double
+    L.evx1c_encoder_wait_ms.argtypes = [vp]
     L.evx1c_encoder_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     L.evx1c_decoder_create.restype = vp
     L.evx1c_decoder_create.argtypes = [i32] * 3
@@ -91,7 +93,7 @@ class evx1_encoder:
             image = np.ascontiguousarray(image)
             h, w, _ = image.shape
             ptr = _p(image)
-            self._keep = (getattr(self, "_keep", (None, None))[1], image)      # submit(): the last two frames outlive their calls
+            self._keep = (getattr(self, "_keep", (None, None, None))[1:] + (image,))      # submit(): the last three frames outlive their calls
         cap = w * h * 6 + 4096
         if self._out is None or self._out.size != cap:
             self._out = np.zeros(cap, dtype=np.uint8)
@@ -137,7 +139,8 @@ class evx1_encoder:
     def stats(self):
         g, e, b, n, d = C.c_double(0), C.c_double(0), C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
         self.L.evx1c_encoder_stats(self.h, C.byref(g), C.byref(e), C.byref(b), C.byref(n), C.byref(d))
-        return {"gpu_ms": g.value, "entropy_ms": e.value, "slice_bits": b.value, "noncopy_blocks": n.value, "d2h_bytes": d.value}
+        return {"gpu_ms": g.value, "entropy_ms": e.value, "slice_bits": b.value, "noncopy_blocks": n.value, "d2h_bytes": d.value,
+                "wait_ms": self.L.evx1c_encoder_wait_ms(self.h)}
 
 
 class evx1_decoder:

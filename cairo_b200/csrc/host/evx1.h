@@ -119,6 +119,7 @@ struct evx1_frame_stats
     uint32 slice_bits;
     uint32 noncopy_blocks;
     uint32 d2h_bytes;        // what came back from the device for this frame (bin string, or table + records)
+    double wait_ms;          // of gpu_ms: how long the host waited for the device when it asked for the frame's results
 };
 
 class evx1_encoder
@@ -137,11 +138,12 @@ public:
     // additions: encode() == submit() + collect().  submit queues the frame on the device (colour
     // conversion, motion search, transform/quantisation, reconstruction, deblocking, binarisation) and
     // returns; collect appends what encode() would have appended for the oldest uncollected frame (stream
-    // header on the first frame, frame descriptor, slice).  One frame may be uncollected when submit is
-    // called: submit(n+1) first waits for frame n's device results, then starts frame n+1, so collect(n)
-    // runs the entropy coder while the device encodes frame n+1 (whose host->device copy already ran under frame n's
-    // kernels).  `image` must stay unchanged until the next submit() or the frame's own collect() returns.  A second uncollected frame makes submit (and any uncollected frame
-    // makes encode) return EVX_ERROR_NOT_READY; collect with nothing submitted returns the same.
+    // header on the first frame, frame descriptor, slice).  Up to two frames may be uncollected when submit is
+    // called.  submit(n+1) before collect(n) runs the entropy coder of frame n while the device encodes frame n+1;
+    // submit(n+2) before collect(n) additionally puts frame n+2's host->device copy under frame n+1's kernels, so
+    // the device never waits for a copy either (two frames of latency).  `image` must stay unchanged until the
+    // frame's own collect() returns.  A third uncollected frame makes submit (and any uncollected frame makes
+    // encode) return EVX_ERROR_NOT_READY; collect with nothing submitted returns the same.
     virtual evx_status submit(void *image, uint32 width, uint32 height) = 0;
     virtual evx_status collect(bit_stream *output) = 0;
 };

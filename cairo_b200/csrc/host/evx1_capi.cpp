@@ -76,6 +76,13 @@ int evx1c_encoder_peek(evx1c_encoder *e, int state, uint8_t *rgb_out)
     return e->enc->peek((EVX_PEEK_STATE) state, rgb_out);
 }
 
+double evx1c_encoder_wait_ms(evx1c_encoder *e)
+{
+    evx1_frame_stats s;
+    if (!e || e->enc->last_frame_stats(&s) != EVX_SUCCESS) return 0.0;
+    return s.wait_ms;
+}
+
 int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks, uint32_t *d2h_bytes)
 {
     if (!e) return EVX_ERROR_INVALIDARG;

@@ -76,7 +76,7 @@ class encoder_session : public evx1_encoder
     {
         bool valid, first;
         frame_desc desc;
-        double t_submit, gpu_ms;
+        double t_submit, gpu_ms, wait_ms;
         uint32 n_noncopy, d2h_bytes;
         uint64_t nbins;
     };
@@ -126,6 +126,7 @@ class encoder_session : public evx1_encoder
         dev_[0] = dev_[1];
         dev_count_--;
         int rc;
+        const double tw = now_ms();
         if (device_bins_)
         {
             const uint64_t *bins = NULL;
@@ -142,6 +143,7 @@ class encoder_session : public evx1_encoder
         }
         f.d2h_bytes = (uint32) evxgpu_d2h_bytes(gpu_);
         f.gpu_ms = now_ms() - f.t_submit;
+        f.wait_ms = now_ms() - tw;
         retired_ = f;
         return EVX_SUCCESS;
     }
@@ -178,7 +180,7 @@ public:
     evx_status submit(void *image, uint32 width, uint32 height)
     {
         if (!width || !height || !image) return EVX_ERROR_INVALIDARG;
-        if (dev_count_ + (retired_.valid ? 1 : 0) > 1) return EVX_ERROR_NOT_READY;      // two frames uncollected
+        if (dev_count_ + (retired_.valid ? 1 : 0) > 2) return EVX_ERROR_NOT_READY;      // three frames uncollected
         bool first = false;
         if (!initialized_)
         {
@@ -189,6 +191,11 @@ public:
         }
         if (width != header_.frame_width || height != header_.frame_height) return EVX_ERROR_INVALID_RESOURCE;
         const uint8 *rgb = static_cast<const uint8 *>(image);
+        if (dev_count_ == 2)
+        {   // the device holds two frames: take the older one's results off it (it is finished or about to be)
+            evx_status st = retire();
+            if (evx_failed(st)) return st;
+        }
         const double t0 = now_ms();
         int rc;
         if (dev_count_ == 1)
@@ -200,6 +207,7 @@ public:
             rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
             if (rc == 8)
             {
+                if (retired_.valid) return EVX_ERROR_NOT_READY;
                 evx_status st = retire();
                 if (evx_failed(st)) return st;
                 rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
@@ -239,7 +247,7 @@ public:
         if (!bits) return EVX_ERROR_EXECUTION_FAILURE;
         evx_status wst = output->write_bits(const_cast<uint8 *>(writer_.data()), bits);
         stats_.gpu_ms = f.gpu_ms; stats_.entropy_ms = now_ms() - t1; stats_.slice_bits = bits;
-        stats_.noncopy_blocks = f.n_noncopy; stats_.d2h_bytes = f.d2h_bytes;
+        stats_.noncopy_blocks = f.n_noncopy; stats_.d2h_bytes = f.d2h_bytes; stats_.wait_ms = f.wait_ms;
         // serialize_slice's write failures are ignored by the reference; report ours
         if (evx_failed(wst)) return EVX_ERROR_EXECUTION_FAILURE;
         return EVX_SUCCESS;

@@ -33,6 +33,7 @@ int evx1c_encoder_collect(evx1c_encoder *e, uint8_t *out, uint32_t out_cap_bytes
 /* evx1_encoder::peek (evx1enc.cpp:170-305); state = EVX_PEEK_STATE (0 source, 2 block table, 3 quant table, 4 sub-pel
  * table, 5 block variance, 6 destination); rgb_out is width*height*3 bytes. */
 int evx1c_encoder_peek(evx1c_encoder *e, int state, uint8_t *rgb_out);
+double evx1c_encoder_wait_ms(evx1c_encoder *e);      /* last collected frame: host time spent waiting for the device */
 int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks, uint32_t *d2h_bytes);
 
 evx1c_decoder *evx1c_decoder_create(int device, int linear_quant, int deblocking);

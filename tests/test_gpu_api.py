@@ -163,16 +163,19 @@ def test_pipelined_1080p_equals_synchronous_and_state_rules():
     with pytest.raises(RuntimeError):
         p.encode(frames[1])                       # encode() with a frame uncollected
     p.submit(frames[1])
+    p.submit(frames[2])                           # two uncollected frames are allowed (frame 0 is taken off the device)
     with pytest.raises(RuntimeError):
-        p.submit(frames[2])                       # a second uncollected frame
-    out = [p.collect()]
-    out[0] = (out[0][0].copy(), out[0][1])
-    for t in range(2, n):
-        p.submit(frames[t])
+        p.submit(frames[3])                       # a third uncollected frame
+    out = []
+    for t in range(3, n):                         # two frames of lookahead: submit(t), collect(t - 3 + ...)
         d, b = p.collect()
         out.append((d.copy(), b))
-    d, b = p.collect()
-    out.append((d.copy(), b))
+        p.submit(frames[t])
+    while len(out) < n:
+        d, b = p.collect()
+        out.append((d.copy(), b))
+    with pytest.raises(RuntimeError):
+        p.collect()
     d, b = p.encode(frames[0])                    # back to the synchronous call once drained
     assert b > 0
     for t in range(n):
