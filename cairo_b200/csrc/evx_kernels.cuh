@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(32, EVX_K2W_PER_SM) evx_inter_search(const __g
 //
 // Coefficient buffers are block-major: 6 blocks (Y00 Y01 Y10 Y11 U V) x 64.
 
-struct EvxMbShared
+struct __align__(16) EvxMbShared
 {
     int16_t src[384];        // source samples, block-major
     int16_t pred[384];       // prediction, block-major

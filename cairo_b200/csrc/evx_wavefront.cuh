@@ -295,6 +295,9 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     {
         const int slot = n & 1, px = n * EVX_MB, mb = by * g.mbw + n;
         evx_mbar_wait(&S.full[slot], (uint32_t) ((n >> 1) & 1));
+#ifdef EVX_K3_STATS
+        EVX_K3_PROF(9);              // waiting for the block loader (source, K2 results, predictions)
+#endif
         evx_mbar_wait(&S.fullb[slot], (uint32_t) ((n >> 1) & 1));
         EVX_K3_PROF(0);
         EVX_K3_STAMP(0);
@@ -500,28 +503,44 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         }
         else
         {
-            // residual (int16, transform.cpp:29-32) and row pass (transform.cpp:264-301)
+            // The four 1-D passes keep one output per thread (index i = tid & 7, whose basis row sits in registers)
+            // but fetch their eight inputs with ONE 16-byte shared-memory load: the passes that walk columns read
+            // buffers their producers wrote transposed.  (Sixteen 2-byte loads per output made every pass
+            // load-bound: ~800 cycles each; a non-copy macroblock is the slow case of the wavefront, and the spread
+            // between fast and slow macroblocks costs the frame as much as their mean.)
+            auto unpack8 = [](const uint4 &v, int x[8])
+            {
+                x[0] = evx_lo16(v.x); x[1] = evx_hi16(v.x); x[2] = evx_lo16(v.y); x[3] = evx_hi16(v.y);
+                x[4] = evx_lo16(v.z); x[5] = evx_hi16(v.z); x[6] = evx_lo16(v.w); x[7] = evx_hi16(v.w);
+            };
+            // residual (int16, transform.cpp:29-32) and row pass (transform.cpp:264-301); result stored transposed
             for (int e = tid; e < 384; e += EVX_K3_CT)
             {
                 const int base = e & ~7;
+                uint4 sv = *reinterpret_cast<const uint4 *>(srcb + base);
+                if (has_pred)
+                {
+                    const uint4 pv = *reinterpret_cast<const uint4 *>(sh.pred + base);
+                    sv.x = __vsub2(sv.x, pv.x); sv.y = __vsub2(sv.y, pv.y); sv.z = __vsub2(sv.z, pv.z); sv.w = __vsub2(sv.w, pv.w);   // wraps like the int16 store
+                }
+                int x[8];
+                unpack8(sv, x);
                 int t = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                {
-                    int r = has_pred ? (short) (srcb[base + k] - sh.pred[base + k]) : srcb[base + k];
-                    t += r * lut_f[k];
-                }
+                for (int k = 0; k < 8; ++k) t += x[k] * lut_f[k];
                 t = (e & 7) == 0 ? evx_tdiv_pow2(t * 45, 7) : evx_tdiv_pow2(t, 1);
-                sh.bufb[e] = (int16_t) evx_rdiv_pow2(t, 7);
+                sh.bufb[(e & ~63) + (e & 7) * 8 + ((e >> 3) & 7)] = (int16_t) evx_rdiv_pow2(t, 7);      // [block][i][row]
             }
             evx_compute_sync();
-            // column pass: thread e -> (block b, column a, output row i = e & 7)
+            // column pass: thread e -> (block b, column a, output row i = e & 7); column a is contiguous in bufb
             for (int e = tid; e < 384; e += EVX_K3_CT)
             {
                 const int b = e >> 6, a = (e >> 3) & 7, i = e & 7;
+                int x[8];
+                unpack8(*reinterpret_cast<const uint4 *>(sh.bufb + b * 64 + a * 8), x);
                 int t = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) t += sh.bufb[b * 64 + k * 8 + a] * lut_f[k];
+                for (int k = 0; k < 8; ++k) t += x[k] * lut_f[k];
                 t = i == 0 ? evx_tdiv_pow2(t * 45, 7) : evx_tdiv_pow2(t, 1);
                 sh.bufa[b * 64 + i * 8 + a] = (int16_t) evx_rdiv_pow2(t, 7);
             }
@@ -555,27 +574,29 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 const int mode = intra_q ? ((e >> 6) < 4 ? 0 : 1) : 2;
                 const int qv = evx_quant_fast(sh.bufa[e], e & 63, mode, qp, p.linear, sh.qmi, sh.qmt, sh.recip);
                 rec[evx_record_index(e)] = (int16_t) qv;
-                sh.bufb[e] = (int16_t) evx_dequant(qv, e & 63, mode, qp, p.linear, sh.qmi, sh.qmt);
+                sh.bufb[(e & ~63) + (e & 7) * 8 + ((e >> 3) & 7)] = (int16_t) evx_dequant(qv, e & 63, mode, qp, p.linear, sh.qmi, sh.qmt);   // [block][column][row]
             }
             if (tid == 0) { d.set_q(qp, var); p.table[mb] = d; p.prev_motion[mb] = S.last_motion; p.prev_coded[mb] = S.last_coded; S.last_coded = mb; }
             evx_compute_sync();
             // inverse transform (transform.cpp:330-366, 418-433): columns, then rows + prediction
             for (int e = tid; e < 384; e += EVX_K3_CT)
             {
-                const int b = e >> 6, j = (e >> 3) & 7;      // column j, output row i = e & 7
-                const int16_t *in = sh.bufb + b * 64 + j;
-                int t = evx_tdiv_pow2((in[0] * lut_i[0]) * 45, 7);
+                const int b = e >> 6, j = (e >> 3) & 7;      // column j (contiguous in bufb), output row i = e & 7
+                int x[8];
+                unpack8(*reinterpret_cast<const uint4 *>(sh.bufb + b * 64 + j * 8), x);
+                int t = evx_tdiv_pow2((x[0] * lut_i[0]) * 45, 7);
 #pragma unroll
-                for (int k = 1; k < 8; ++k) t += evx_tdiv_pow2(in[k * 8] * lut_i[k], 1);
+                for (int k = 1; k < 8; ++k) t += evx_tdiv_pow2(x[k] * lut_i[k], 1);
                 sh.bufa[b * 64 + (e & 7) * 8 + j] = (int16_t) evx_rdiv_pow2(t, 7);
             }
             evx_compute_sync();
             for (int e = tid; e < 384; e += EVX_K3_CT)
             {
-                const int16_t *in = sh.bufa + (e & ~7);      // row (e>>3), output column i = e & 7
-                int t = evx_tdiv_pow2((in[0] * lut_i[0]) * 45, 7);
+                int x[8];                                    // row (e>>3), output column i = e & 7
+                unpack8(*reinterpret_cast<const uint4 *>(sh.bufa + (e & ~7)), x);
+                int t = evx_tdiv_pow2((x[0] * lut_i[0]) * 45, 7);
 #pragma unroll
-                for (int k = 1; k < 8; ++k) t += evx_tdiv_pow2(in[k] * lut_i[k], 1);
+                for (int k = 1; k < 8; ++k) t += evx_tdiv_pow2(x[k] * lut_i[k], 1);
                 int v = evx_rdiv_pow2(t, 7);
                 if (has_pred) v += sh.pred[e];
                 store_recon(e, v);

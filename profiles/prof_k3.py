@@ -17,7 +17,7 @@ tm = p.timing()
 raw = np.zeros((p.ah // 16) * 10 + p.nblocks * 4, dtype=np.int64)
 L.evxgpu_debug_profile(p.h, 1, raw.ctypes.data_as(C.c_void_p))
 prof = raw[:(p.ah // 16) * 10].reshape(-1, 10)
-names = ['wait_loader', 'search5', 'subpel', 'classify+pred', 'transform+recon', 'unused', 'r_eval', 'r_barrier', 'r_replay', 'x']
+names = ['wait_columns', 'search5', 'subpel', 'classify+pred', 'transform+recon', 'far_col_waits', 'hold1', 'hold2', 'hold3', 'wait_block_loader(stats build)']
 mbw = p.aw // 16
 print(f"wavefront {tm['wavefront']:.3f} ms, inter {tm['inter_search']:.3f} ms, non-copy share {rec.shape[0] / p.nblocks:.2f}")
 print("mean cycles per macroblock (rows 10..60):", {n: int(v) for n, v in zip(names, prof[10:60].mean(axis=0) / mbw)})
