@@ -519,63 +519,107 @@ void slice_reader::configure(int mbw, int mbh, int ref_count)
 
 void slice_reader::reset() { dc_.resize((size_t) mbw_ * mbh_); }
 
-int slice_reader::unserialize(const uint8_t *data, uint32_t pos, uint32_t end, evxgpu_block_desc *t, int16_t *records, uint32_t *n_noncopy)
+int slice_reader::parse(const uint8_t *data, uint32_t pos, uint32_t end, parsed_slice &out) const
 {
     const int n = mbw_ * mbh_;
     {   // the slice's bytes, each turned around (see abac_reader); absolute byte positions, 16 bytes of padding
         const size_t first = pos >> 3, last = ((size_t) end + 7) >> 3;
-        if (rev_.size() < last + 16) rev_.resize(last + 16);
-        for (size_t i = first; i < last; ++i) rev_[i] = REV8[data[i]];
-        memset(rev_.data() + last, 0, 16);
+        if (out.rev.size() < last + 16) out.rev.resize(last + 16);
+        for (size_t i = first; i < last; ++i) out.rev[i] = REV8[data[i]];
+        memset(out.rev.data() + last, 0, 16);
     }
-    abac_reader rd(data, rev_.data(), pos, end);
-    for (int i = 0; i < n; ++i) t[i].block_type = (t[i].block_type & ~7) | (int32_t) rd.decode_bits_lsb(3);
+    evxgpu_block_desc zero;
+    memset(&zero, 0, sizeof(zero));
+    out.fields.assign((size_t) n, zero);
+    evxgpu_block_desc *t = out.fields.data();
+    abac_reader rd(data, out.rev.data(), pos, end);
+    for (int i = 0; i < n; ++i) t[i].block_type = (int32_t) rd.decode_bits_lsb(3);
     for (int i = 0; i < n; ++i)
-        if (!(t[i].block_type & T_INTRA))
-            t[i].prediction_target = (uint8_t) ((t[i].prediction_target & ~((1u << target_bits_) - 1u)) | rd.decode_bits_lsb(target_bits_));
+        if (!(t[i].block_type & T_INTRA)) t[i].prediction_target = (uint8_t) rd.decode_bits_lsb(target_bits_);
     int16_t last = 0;
     for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) { t[i].motion_x = (int16_t) (last + rd.decode_signed()); last = t[i].motion_x; }
     last = 0;
     for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) { t[i].motion_y = (int16_t) (last + rd.decode_signed()); last = t[i].motion_y; }
-    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) t[i].sp_pred = (uint8_t) ((t[i].sp_pred & 0xFE) | rd.decode());
-    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) t[i].sp_amount = (uint8_t) ((t[i].sp_amount & 0xFE) | rd.decode());
-    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) t[i].sp_index = (uint8_t) ((t[i].sp_index & ~7u) | rd.decode_bits_lsb(3));
+    for (int i = 0; i < n; ++i) if (t[i].block_type & T_MOTION) t[i].sp_pred = (uint8_t) rd.decode();
+    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) t[i].sp_amount = (uint8_t) rd.decode();
+    for (int i = 0; i < n; ++i) if ((t[i].block_type & T_MOTION) && t[i].sp_pred) t[i].sp_index = (uint8_t) rd.decode_bits_lsb(3);
     last = 0;
     for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_COPY)) { t[i].q_index = (uint8_t) (rd.decode_signed() + last); last = t[i].q_index; }
 
     uint32_t count = 0;
     for (int i = 0; i < n; ++i) if (!(t[i].block_type & T_COPY)) count++;
-    *n_noncopy = count;
+    out.n_noncopy = count;
+    if (out.records.size() < (size_t) count * 384) out.records.resize((size_t) count * 384);
 
     for (int comp = 0; comp < 3; ++comp)
     {
         uint32_t k = 0;
-        int idx = 0;
-        for (int by = 0; by < mbh_; ++by)
-        for (int bx = 0; bx < mbw_; ++bx, ++idx)
+        for (int idx = 0; idx < n; ++idx)
         {
             if (t[idx].block_type & T_COPY) continue;
-            int16_t *r = records + (size_t) (k++) * 384;
+            int16_t *r = out.records.data() + (size_t) (k++) * 384;
             if (comp == 0)
-            {
-                int16_t last_dc = bx >= 1 ? dc_.y_tr[idx - 1] : (by >= 1 ? dc_.y_bl[idx - mbw_] : 0);
-                get_block(rd, r, 16, last_dc);                         // unserialize.cpp:24-33
+            {   // unserialize.cpp:24-33; the first block's neighbour DC is added by apply()
+                get_block(rd, r, 16, 0);
                 get_block(rd, r + 8, 16, r[0]);
                 get_block(rd, r + 8 * 16, 16, r[0]);
                 get_block(rd, r + 8 * 16 + 8, 16, r[8 * 16]);
-                dc_.y_tr[idx] = r[8]; dc_.y_bl[idx] = r[8 * 16];
             }
-            else
-            {
-                std::vector<int16_t> &m = comp == 1 ? dc_.u : dc_.v;
-                int16_t last_dc = bx >= 1 ? m[idx - 1] : (by >= 1 ? m[idx - mbw_] : 0);
-                int16_t *b = r + 256 + (comp - 1) * 64;
-                get_block(rd, b, 8, last_dc);
-                m[idx] = b[0];
-            }
+            else get_block(rd, r + 256 + (comp - 1) * 64, 8, 0);
         }
     }
     return 0;
+}
+
+int slice_reader::apply(const parsed_slice &in, evxgpu_block_desc *t, int16_t *records, uint32_t *n_noncopy)
+{
+    const int n = mbw_ * mbh_;
+    if (in.fields.size() != (size_t) n) return 1;
+    const evxgpu_block_desc *f = in.fields.data();
+    const uint8_t tmask = (uint8_t) ((1u << target_bits_) - 1u);
+    for (int i = 0; i < n; ++i)
+    {   // a field the frame does not carry keeps its old value (unserialize.cpp:123-319)
+        t[i].block_type = (t[i].block_type & ~7) | f[i].block_type;
+        if (!(f[i].block_type & T_INTRA)) t[i].prediction_target = (uint8_t) ((t[i].prediction_target & ~tmask) | f[i].prediction_target);
+        if (f[i].block_type & T_MOTION)
+        {
+            t[i].motion_x = f[i].motion_x; t[i].motion_y = f[i].motion_y;
+            t[i].sp_pred = (uint8_t) ((t[i].sp_pred & 0xFE) | f[i].sp_pred);
+            if (f[i].sp_pred)
+            {
+                t[i].sp_amount = (uint8_t) ((t[i].sp_amount & 0xFE) | f[i].sp_amount);
+                t[i].sp_index = (uint8_t) ((t[i].sp_index & ~7u) | f[i].sp_index);
+            }
+        }
+        if (!(f[i].block_type & T_COPY)) t[i].q_index = f[i].q_index;
+    }
+    *n_noncopy = in.n_noncopy;
+    if (records != in.records.data()) memcpy(records, in.records.data(), (size_t) in.n_noncopy * 384 * sizeof(int16_t));
+    // DC prediction across macroblocks (unserialize.cpp:24-72): the neighbour's DC as of now -- from this frame if
+    // it was coded, else what the mirror kept from the last frame that coded it.  The prediction is additive in
+    // int16 arithmetic, so the neighbour's DC is added to every DC that was chained from it inside the macroblock.
+    uint32_t k = 0;
+    int idx = 0;
+    for (int by = 0; by < mbh_; ++by)
+    for (int bx = 0; bx < mbw_; ++bx, ++idx)
+    {
+        if (f[idx].block_type & T_COPY) continue;
+        int16_t *r = records + (size_t) (k++) * 384;
+        const int16_t ly = bx >= 1 ? dc_.y_tr[idx - 1] : (by >= 1 ? dc_.y_bl[idx - mbw_] : 0);
+        r[0] = (int16_t) (r[0] + ly); r[8] = (int16_t) (r[8] + ly); r[8 * 16] = (int16_t) (r[8 * 16] + ly); r[8 * 16 + 8] = (int16_t) (r[8 * 16 + 8] + ly);
+        dc_.y_tr[idx] = r[8]; dc_.y_bl[idx] = r[8 * 16];
+        const int16_t lu = bx >= 1 ? dc_.u[idx - 1] : (by >= 1 ? dc_.u[idx - mbw_] : 0);
+        r[256] = (int16_t) (r[256] + lu); dc_.u[idx] = r[256];
+        const int16_t lv = bx >= 1 ? dc_.v[idx - 1] : (by >= 1 ? dc_.v[idx - mbw_] : 0);
+        r[320] = (int16_t) (r[320] + lv); dc_.v[idx] = r[320];
+    }
+    return 0;
+}
+
+int slice_reader::unserialize(const uint8_t *data, uint32_t pos, uint32_t end, evxgpu_block_desc *t, int16_t *records, uint32_t *n_noncopy)
+{
+    int rc = parse(data, pos, end, tmp_);
+    return rc ? rc : apply(tmp_, t, records, n_noncopy);
 }
 
 }  // namespace evx

@@ -41,19 +41,35 @@ public:
     const uint8_t *data() const { return buf_.data(); }
 };
 
+// One slice, entropy-decoded but not yet merged into the stream's state.  Everything the arithmetic decoder
+// and the syntax need is inside the slice itself (the coder is reset per frame, serialize.cpp:323; motion and
+// quantiser deltas chain within the frame), so slices of consecutive frames can be parsed concurrently; what
+// depends on earlier frames -- table fields a frame does not carry, and the DC prediction from a neighbour
+// that may be a stale copy block -- is resolved by slice_reader::apply, in frame order.
+struct parsed_slice
+{
+    std::vector<evxgpu_block_desc> fields;   // per macroblock, only the fields this frame carries
+    std::vector<int16_t> records;            // non-copy macroblocks, raster order; DCs relative to a zero neighbour
+    uint32_t n_noncopy;
+    std::vector<uint8_t> rev;                // scratch: the slice's bytes bit-reversed (see abac_reader)
+};
+
 class slice_reader
 {
     int mbw_, mbh_, target_bits_;
     dc_mirror dc_;
-    std::vector<uint8_t> rev_;      // the slice being read, bytes bit-reversed (see abac_reader)
+    parsed_slice tmp_;
 
 public:
     void configure(int mbw, int mbh, int ref_count);
     void reset();
     // Decodes one slice from bits [pos, end) of data.  `table` is persistent across frames
     // (fields a frame does not carry keep their old values, as in the reference); `records`
-    // receives the non-copy macroblocks' coefficients in raster order.
+    // receives the non-copy macroblocks' coefficients in raster order.  = parse + apply.
     int unserialize(const uint8_t *data, uint32_t pos, uint32_t end, evxgpu_block_desc *table, int16_t *records, uint32_t *n_noncopy);
+    // The two halves.  parse touches no state of the reader (thread-safe, any order); apply must run in frame order.
+    int parse(const uint8_t *data, uint32_t pos, uint32_t end, parsed_slice &out) const;
+    int apply(const parsed_slice &in, evxgpu_block_desc *table, int16_t *records, uint32_t *n_noncopy);
 };
 
 }  // namespace evx

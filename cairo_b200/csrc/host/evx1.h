@@ -158,11 +158,13 @@ public:
     virtual evx_status decode(bit_stream *input, void *output) = 0;
     virtual evx_status last_frame_stats(evx1_frame_stats *out) = 0;                    // addition (entropy_ms = unserialize)
 
-    // additions: decode() == submit() + collect().  submit parses and entropy-decodes one frame on the host
-    // (and empties input, like decode); the frame starts on the device as soon as the device is free.  collect
-    // writes the oldest submitted frame's picture.  submit(n+1) before collect(n) overlaps the host entropy
-    // decoding of frame n+1 with the device's work on frame n; at most two frames may be uncollected
-    // (EVX_ERROR_NOT_READY otherwise, and for decode() with any frame uncollected, and for collect with none).
+    // additions: decode() == submit() + collect().  submit takes one frame out of input (and empties it, like
+    // decode) and hands its slice to a parser thread; collect merges the oldest submitted frame into the stream's
+    // state, runs the pixel pipeline and writes its picture.  The arithmetic decoding of a slice needs nothing from
+    // other frames, so with submit(n+1), submit(n+2) before collect(n) the slices of consecutive frames are decoded
+    // concurrently (two parser threads) while the caller's thread runs the device.  At most three frames may be
+    // uncollected (EVX_ERROR_NOT_READY otherwise, and for decode() with any frame uncollected, and for collect
+    // with none).  decode() itself parses on the calling thread.
     virtual evx_status submit(bit_stream *input) = 0;
     virtual evx_status collect(void *output) = 0;
 };

@@ -8,7 +8,10 @@
 #include <string.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "entropy.h"
@@ -326,27 +329,78 @@ class decoder_session : public evx1_decoder
     std::vector<int16> records_;
     evx1_frame_stats stats_;
 
-    // A submitted frame is parsed (entropy-decoded into table_/records_, waiting for the device) or on the device.
-    struct pending_frame
+    // A submitted frame is a job: its slice is entropy-decoded (slice_reader::parse, which needs nothing from other
+    // frames) by a worker thread; collect() merges the oldest finished job into the stream's state (apply, in
+    // frame order) and runs the pixel pipeline.  Up to kJobs frames may be uncollected.
+    enum { kJobs = 3, kWorkers = 2 };
+    enum job_state { JOB_FREE = 0, JOB_QUEUED, JOB_RUNNING, JOB_DONE };
+    struct job
     {
-        bool valid;
+        job_state state;
+        std::vector<uint8> bytes;          // the slice (bit_stream bytes, absolute bit positions)
+        uint32 pos, end;
         frame_desc desc;
-        uint32 n_noncopy, slice_bits;
-        double entropy_ms, t_submit;
+        parsed_slice ps;
+        int rc;
+        double ms;
     };
-    pending_frame parsed_, on_device_;
+    job jobs_[kJobs];
+    int head_, count_;                     // uncollected jobs: head_, head_+1, ... (mod kJobs), in frame order
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::thread workers_[kWorkers];
+    bool threads_up_, stop_;
 
     void clear_frame() { frame_.type = 0; frame_.index = 0; frame_.quality = (uint16) clip(cfg_.default_quality, 1, 100); }
 
-    evx_status launch()          // the device copies table_/records_ into its own staging before returning
+    void run_job(job &j)
     {
-        pending_frame f = parsed_;
-        parsed_.valid = false;
-        f.t_submit = now_ms();
-        int rc = evxgpu_decode_submit(gpu_, table_.data(), records_.data(), f.n_noncopy, (int) f.desc.type, f.desc.index);
-        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        on_device_ = f;
-        return EVX_SUCCESS;
+        const double t0 = now_ms();
+        j.rc = reader_.parse(j.bytes.data(), j.pos, j.end, j.ps);
+        j.ms = now_ms() - t0;
+    }
+
+    void worker()
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;)
+        {
+            job *mine = NULL;
+            for (int k = 0; k < count_ && !mine; ++k)
+            {
+                job &j = jobs_[(head_ + k) % kJobs];
+                if (j.state == JOB_QUEUED) mine = &j;
+            }
+            if (!mine)
+            {
+                if (stop_) return;
+                cv_work_.wait(lk);
+                continue;
+            }
+            mine->state = JOB_RUNNING;
+            lk.unlock();
+            run_job(*mine);
+            lk.lock();
+            mine->state = JOB_DONE;
+            cv_done_.notify_all();
+        }
+    }
+
+    void start_threads()
+    {
+        if (threads_up_) return;
+        stop_ = false;
+        for (int k = 0; k < kWorkers; ++k) workers_[k] = std::thread(&decoder_session::worker, this);
+        threads_up_ = true;
+    }
+
+    void stop_threads()
+    {
+        if (!threads_up_) return;
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_work_.notify_all();
+        for (int k = 0; k < kWorkers; ++k) workers_[k].join();
+        threads_up_ = false;
     }
 
     evx_status initialize(bit_stream *input)                 // evx1dec.cpp:41-69, verify_header common.cpp:25-43
@@ -371,80 +425,127 @@ class decoder_session : public evx1_decoder
         return EVX_SUCCESS;
     }
 
-public:
-    explicit decoder_session(const evx1_config &cfg) : cfg_(cfg), initialized_(false), gpu_(NULL)
+    // header (first frame), frame descriptor and the slice's bytes into a job; the caller decides who parses it
+    evx_status enqueue(bit_stream *input, job **out)
     {
-        memset(&header_, 0, sizeof(header_));
-        memset(&stats_, 0, sizeof(stats_));
-        memset(&parsed_, 0, sizeof(parsed_));
-        memset(&on_device_, 0, sizeof(on_device_));
-        clear_frame();
-    }
-    ~decoder_session() { clear(); }
-
-    evx_status clear()                                       // evx1dec.cpp:27-39
-    {
-        if (!initialized_) return EVX_SUCCESS;
-        clear_frame();
-        if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }
-        parsed_.valid = on_device_.valid = false;
-        initialized_ = false;
-        return EVX_SUCCESS;
-    }
-
-    // First half of decode (evx1dec.cpp:87-123 up to unserialize_slice, decode.cpp:172-180): the frame is
-    // parsed and entropy-decoded on the host; it goes to the device at once if the device is free, otherwise
-    // when collect() has taken the previous frame off it.
-    evx_status submit(bit_stream *input)
-    {
-        if (!input) return EVX_ERROR_INVALIDARG;
-        if (parsed_.valid) return EVX_ERROR_NOT_READY;                                   // one frame may wait for the device
+        if (count_ >= kJobs) return EVX_ERROR_NOT_READY;
         if (!initialized_ && evx_failed(initialize(input))) return EVX_ERROR_EXECUTION_FAILURE;
         frame_desc incoming;
         if (evx_failed(input->read_bytes(&incoming, sizeof(incoming)))) return EVX_ERROR_EXECUTION_FAILURE;
         if (incoming.index != frame_.index) return EVX_ERROR_EXECUTION_FAILURE;          // evx1dec.cpp:77-80
         frame_ = incoming;
-
-        const double t0 = now_ms();
-        const uint32 bits_before = input->query_read_index();
-        uint32 n_noncopy = 0;
-        if (reader_.unserialize(input->query_data(), input->query_read_index(), input->query_write_index(), table_.data(), records_.data(), &n_noncopy))
-            return EVX_ERROR_EXECUTION_FAILURE;
-        memset(&parsed_, 0, sizeof(parsed_));
-        parsed_.valid = true; parsed_.desc = frame_; parsed_.n_noncopy = n_noncopy;
-        parsed_.entropy_ms = now_ms() - t0; parsed_.slice_bits = input->query_write_index() - bits_before;
+        job &j = jobs_[(head_ + count_) % kJobs];
+        j.pos = input->query_read_index(); j.end = input->query_write_index();
+        const size_t nbytes = ((size_t) j.end + 7) >> 3;
+        if (j.bytes.size() < nbytes) j.bytes.resize(nbytes + nbytes / 2 + 64);
+        memcpy(j.bytes.data(), input->query_data(), nbytes);
+        j.desc = frame_; j.rc = 0; j.ms = 0.0;
         frame_.index++;
         input->empty();                                                                    // evx1dec.cpp:120
-        if (!on_device_.valid) return launch();
+        *out = &j;
         return EVX_SUCCESS;
     }
 
-    // Second half (decode_slice, deblocking, colour conversion: decode.cpp:182-198): the oldest submitted
-    // frame's RGB8 picture into output; a frame that was waiting for the device starts right after.
+public:
+    explicit decoder_session(const evx1_config &cfg) : cfg_(cfg), initialized_(false), gpu_(NULL), head_(0), count_(0), threads_up_(false), stop_(false)
+    {
+        memset(&header_, 0, sizeof(header_));
+        memset(&stats_, 0, sizeof(stats_));
+        for (int k = 0; k < kJobs; ++k) jobs_[k].state = JOB_FREE;
+        clear_frame();
+    }
+    ~decoder_session() { clear(); stop_threads(); }
+
+    evx_status clear()                                       // evx1dec.cpp:27-39
+    {
+        {   // uncollected frames are dropped; a slice being parsed is waited for
+            std::unique_lock<std::mutex> lk(m_);
+            for (int k = 0; k < count_; ++k)
+            {
+                job &j = jobs_[(head_ + k) % kJobs];
+                if (j.state == JOB_QUEUED) j.state = JOB_FREE;
+                while (j.state == JOB_RUNNING) cv_done_.wait(lk);
+                j.state = JOB_FREE;
+            }
+            head_ = 0; count_ = 0;
+        }
+        if (!initialized_) return EVX_SUCCESS;
+        clear_frame();
+        if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }
+        initialized_ = false;
+        return EVX_SUCCESS;
+    }
+
+    // First half of decode (evx1dec.cpp:87-123 up to unserialize_slice, decode.cpp:172-180): the frame is taken
+    // out of `input` (which is emptied, as decode() does) and handed to a parser thread; the call returns.
+    evx_status submit(bit_stream *input)
+    {
+        if (!input) return EVX_ERROR_INVALIDARG;
+        job *j = NULL;
+        evx_status st = enqueue(input, &j);
+        if (evx_failed(st)) return st;
+        start_threads();
+        {
+            std::lock_guard<std::mutex> g(m_);
+            j->state = JOB_QUEUED;
+            count_++;
+        }
+        cv_work_.notify_one();
+        return EVX_SUCCESS;
+    }
+
+    // Second half (the rest of unserialize_slice's effect, decode_slice, deblocking, colour conversion:
+    // decode.cpp:182-198): the oldest submitted frame's RGB8 picture into output.
     evx_status collect(void *output)
     {
         if (!output) return EVX_ERROR_INVALIDARG;
-        if (!on_device_.valid) return EVX_ERROR_NOT_READY;
-        const pending_frame f = on_device_;
-        on_device_.valid = false;
-        int rc = evxgpu_decode_collect(gpu_, static_cast<uint8 *>(output), 0);
-        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        stats_.entropy_ms = f.entropy_ms; stats_.gpu_ms = now_ms() - f.t_submit; stats_.noncopy_blocks = f.n_noncopy;
-        stats_.slice_bits = f.slice_bits; stats_.d2h_bytes = (uint32) ((size_t) header_.frame_width * header_.frame_height * 3);
-        if (parsed_.valid) return launch();
-        return EVX_SUCCESS;
+        job *j;
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            if (!count_) return EVX_ERROR_NOT_READY;
+            j = &jobs_[head_];
+            while (j->state != JOB_DONE) cv_done_.wait(lk);
+        }
+        evx_status st = finish(*j, output);
+        {
+            std::lock_guard<std::mutex> g(m_);
+            j->state = JOB_FREE;
+            head_ = (head_ + 1) % kJobs; count_--;
+        }
+        return st;
     }
 
     evx_status decode(bit_stream *input, void *output)       // evx1dec.cpp:87-123
     {
         if (!input || !output) return EVX_ERROR_INVALIDARG;
-        if (on_device_.valid || parsed_.valid) return EVX_ERROR_NOT_READY;      // finish the pipelined frames with collect() first
-        evx_status st = submit(input);
+        if (count_) return EVX_ERROR_NOT_READY;               // finish the pipelined frames with collect() first
+        job *j = NULL;
+        evx_status st = enqueue(input, &j);
         if (evx_failed(st)) return st;
-        return collect(output);
+        run_job(*j);                                          // one frame at a time: parsed right here
+        return finish(*j, output);
     }
 
     evx_status last_frame_stats(evx1_frame_stats *out) { if (!out) return EVX_ERROR_INVALIDARG; *out = stats_; return EVX_SUCCESS; }
+
+private:
+    evx_status finish(job &j, void *output)
+    {
+        if (j.rc) return EVX_ERROR_EXECUTION_FAILURE;
+        uint32 n_noncopy = 0;
+        const double t0 = now_ms();
+        int16 *rec = j.ps.records.empty() ? records_.data() : j.ps.records.data();          // resolved in place: no copy of the coefficients
+        if (reader_.apply(j.ps, table_.data(), rec, &n_noncopy)) return EVX_ERROR_EXECUTION_FAILURE;
+        const double t1 = now_ms();
+        int rc = evxgpu_decode_submit(gpu_, table_.data(), rec, n_noncopy, (int) j.desc.type, j.desc.index);
+        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+        rc = evxgpu_decode_collect(gpu_, static_cast<uint8 *>(output), 0);
+        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
+        stats_.entropy_ms = j.ms + (t1 - t0); stats_.gpu_ms = now_ms() - t1; stats_.noncopy_blocks = n_noncopy;
+        stats_.slice_bits = j.end - j.pos; stats_.d2h_bytes = (uint32) ((size_t) header_.frame_width * header_.frame_height * 3);
+        stats_.wait_ms = 0.0;
+        return EVX_SUCCESS;
+    }
 };
 
 }  // namespace
