@@ -54,6 +54,10 @@ def lib():
     L.evx1c_slice_reader_create.argtypes = [i32] * 3
     L.evx1c_slice_reader_destroy.argtypes = [vp]
     L.evx1c_slice_reader_unserialize.argtypes = [vp, vp, u32, vp, vp, C.POINTER(u32)]
+    L.evx1c_parsed_slice_create.restype = vp
+    L.evx1c_parsed_slice_destroy.argtypes = [vp]
+    L.evx1c_slice_reader_parse.argtypes = [vp, vp, u32, vp]
+    L.evx1c_slice_reader_apply.argtypes = [vp, vp, vp, vp, C.POINTER(u32)]
     _lib = L
     return L
 
@@ -238,6 +242,25 @@ class SliceReader:
         if getattr(self, "h", None):
             self.L.evx1c_slice_reader_destroy(self.h)
             self.h = None
+
+    def parse(self, data, nbits):
+        """State-free half: returns an opaque parsed slice (free it with free_parsed)."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        ps = self.L.evx1c_parsed_slice_create()
+        st = self.L.evx1c_slice_reader_parse(self.h, _p(data), nbits, ps)
+        assert st == 0, st
+        return ps
+
+    def apply(self, ps):
+        """In-order half: merges a parsed slice into the stream's state; returns (table, records)."""
+        rec = np.zeros((self.n, 384), dtype=np.int16)
+        n = C.c_uint32(0)
+        st = self.L.evx1c_slice_reader_apply(self.h, ps, _p(self.table), _p(rec), C.byref(n))
+        assert st == 0, st
+        return self.table.copy(), rec[:n.value].copy()
+
+    def free_parsed(self, ps):
+        self.L.evx1c_parsed_slice_destroy(ps)
 
     def unserialize(self, data, nbits):
         data = np.ascontiguousarray(data, dtype=np.uint8)

@@ -191,4 +191,21 @@ int evx1c_slice_reader_unserialize(evx1c_slice_reader *r, const uint8_t *data, u
     return r->r.unserialize(data, 0, nbits, static_cast<evxgpu_block_desc *>(table), records_out, n_noncopy);
 }
 
-}  // extern "C"
+struct evx1c_parsed_slice { parsed_slice p; };
+
+evx1c_parsed_slice *evx1c_parsed_slice_create(void) { return new (std::nothrow) evx1c_parsed_slice(); }
+void evx1c_parsed_slice_destroy(evx1c_parsed_slice *p) { delete p; }
+
+int evx1c_slice_reader_parse(const evx1c_slice_reader *r, const uint8_t *data, uint32_t nbits, evx1c_parsed_slice *out)
+{
+    if (!r || !data || !out) return EVX_ERROR_INVALIDARG;
+    return r->r.parse(data, 0, nbits, out->p);
+}
+
+int evx1c_slice_reader_apply(evx1c_slice_reader *r, const evx1c_parsed_slice *in, void *table, int16_t *records_out, uint32_t *n_noncopy)
+{
+    if (!r || !in || !table || !records_out || !n_noncopy) return EVX_ERROR_INVALIDARG;
+    return r->r.apply(in->p, static_cast<evxgpu_block_desc *>(table), records_out, n_noncopy);
+}
+
+}

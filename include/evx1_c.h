@@ -66,6 +66,14 @@ void evx1c_slice_reader_destroy(evx1c_slice_reader *r);
 int evx1c_slice_reader_unserialize(evx1c_slice_reader *r, const uint8_t *data, uint32_t nbits, void *table,
                                    int16_t *records_out, uint32_t *n_noncopy);
 
+/* The reader's two halves (cairo_b200/csrc/host/entropy.h): parse decodes a slice without touching the reader's
+ * state (any order, any thread); apply merges parsed slices into the stream's state, in frame order. */
+typedef struct evx1c_parsed_slice evx1c_parsed_slice;
+evx1c_parsed_slice *evx1c_parsed_slice_create(void);
+void evx1c_parsed_slice_destroy(evx1c_parsed_slice *p);
+int evx1c_slice_reader_parse(const evx1c_slice_reader *r, const uint8_t *data, uint32_t nbits, evx1c_parsed_slice *out);
+int evx1c_slice_reader_apply(evx1c_slice_reader *r, const evx1c_parsed_slice *in, void *table, int16_t *records_out, uint32_t *n_noncopy);
+
 #ifdef __cplusplus
 }
 #endif

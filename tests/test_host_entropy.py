@@ -121,3 +121,35 @@ def test_reader_matches_oracle_on_truncated_and_corrupt_slices():
         assert O.tables_equal(o.block_table().copy(), tbl, check_variance=False), nbits
         want = gpu.planes_to_records(tbl, o.planes(1), aw)
         assert want.shape == rec.shape and (want == rec).all(), nbits
+
+
+@pytest.mark.parametrize("name", G.names())
+def test_slices_parse_in_any_order_on_any_thread(name):
+    """The decoder parses the slices of consecutive frames concurrently (slice_reader::parse keeps no state) and
+    merges them in frame order (apply): parsing every frame of a golden sequence up front, in reverse order and
+    on several threads, then applying in order, must give what frame-by-frame unserialize gives."""
+    import threading
+    g = G.Golden(name)
+    mbw, mbh = (g.w + 15) // 16, (g.h + 15) // 16
+    seq = api.SliceReader(mbw, mbh, g.R)
+    slices = [g.slice_bits(t) for t in range(g.frames)]          # (the .npz reader is not thread-safe)
+    want = [seq.unserialize(*slices[t]) for t in range(g.frames)]
+    rd = api.SliceReader(mbw, mbh, g.R)
+    parsed = [None] * g.frames
+
+    def work(ts):
+        for t in ts:
+            parsed[t] = rd.parse(*slices[t])
+
+    order = list(range(g.frames))[::-1]
+    threads = [threading.Thread(target=work, args=(order[k::3],)) for k in range(3)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for t in range(g.frames):
+        tbl, rec = rd.apply(parsed[t])
+        rd.free_parsed(parsed[t])
+        for field in tbl.dtype.names:             # field by field: the descriptor has a padding byte
+            assert (tbl[field] == want[t][0][field]).all(), (name, t, field)
+        assert rec.shape == want[t][1].shape and (rec == want[t][1]).all(), (name, t)
