@@ -89,6 +89,52 @@ class encoder_session : public evx1_encoder
     std::vector<evxgpu_block_desc> table_;         // retired frame, table + records output
     std::vector<int16> records_;
 
+    // The arithmetic coder of a frame retired by submit() runs on a thread of its own, so that the caller's thread
+    // is free to queue the next frame; collect() waits for it.  One frame at a time (there is one retired slot).
+    std::thread coder_;
+    std::mutex cm_;
+    std::condition_variable ccv_;
+    enum { CODER_IDLE, CODER_WORK, CODER_DONE } cstate_;
+    bool coder_up_, coder_stop_, retired_async_, coder_thread_;
+    uint64_t coder_nbins_;
+    uint32 coder_bits_;
+    double coder_ms_;
+
+    void coder_main()
+    {
+        std::unique_lock<std::mutex> lk(cm_);
+        for (;;)
+        {
+            while (cstate_ != CODER_WORK && !coder_stop_) ccv_.wait(lk);
+            if (coder_stop_) return;
+            lk.unlock();
+            const double t0 = now_ms();
+            const uint32 bits = writer_.serialize_bins(bins_.data(), coder_nbins_);
+            const double ms = now_ms() - t0;
+            lk.lock();
+            coder_bits_ = bits; coder_ms_ = ms;
+            cstate_ = CODER_DONE;
+            ccv_.notify_all();
+        }
+    }
+
+    void coder_wait_idle()          // a job in progress is finished and forgotten
+    {
+        std::unique_lock<std::mutex> lk(cm_);
+        while (cstate_ == CODER_WORK) ccv_.wait(lk);
+        cstate_ = CODER_IDLE;
+    }
+
+    void coder_shutdown()
+    {
+        if (!coder_up_) return;
+        coder_wait_idle();
+        { std::lock_guard<std::mutex> g(cm_); coder_stop_ = true; }
+        ccv_.notify_all();
+        coder_.join();
+        coder_up_ = false;
+    }
+
     void clear_frame()          // clear_frame, common.cpp:50-64
     {
         frame_.type = 0;
@@ -112,6 +158,7 @@ class encoder_session : public evx1_encoder
         // The device binarises the slice (include/evxgpu.h, evxgpu_set_output); EVX1_HOST_BINARISE=1 keeps
         // the table + records path and binarises here instead (same bits; for A/B measurements).
         device_bins_ = getenv("EVX1_HOST_BINARISE") == NULL;
+        { const char *ct = getenv("EVX1_CODER_THREAD"); coder_thread_ = !(ct && ct[0] == '0'); }      // EVX1_CODER_THREAD=0: code on the caller's thread
         if (device_bins_ && (rc = evxgpu_set_output(gpu_, 1))) return map_gpu_status(rc);
         int mbw = (int) ((width + 15) / 16), mbh = (int) ((height + 15) / 16);
         writer_.configure(mbw, mbh, cfg_.ref_count);
@@ -123,13 +170,14 @@ class encoder_session : public evx1_encoder
 
     // Waits for the frame on the device and moves its results into session memory, which frees the device
     // library's staging buffers for the next submit.
-    evx_status retire()
+    evx_status retire(bool async_coder)
     {
         pending_frame f = dev_[0];
         dev_[0] = dev_[1];
         dev_count_--;
         int rc;
         const double tw = now_ms();
+        retired_async_ = false;
         if (device_bins_)
         {
             const uint64_t *bins = NULL;
@@ -148,11 +196,23 @@ class encoder_session : public evx1_encoder
         f.gpu_ms = now_ms() - f.t_submit;
         f.wait_ms = now_ms() - tw;
         retired_ = f;
+        if (async_coder && device_bins_ && coder_thread_)
+        {
+            if (!coder_up_)
+            {
+                coder_stop_ = false; cstate_ = CODER_IDLE;
+                coder_ = std::thread(&encoder_session::coder_main, this);
+                coder_up_ = true;
+            }
+            { std::lock_guard<std::mutex> g(cm_); coder_nbins_ = f.nbins; cstate_ = CODER_WORK; }
+            ccv_.notify_all();
+            retired_async_ = true;
+        }
         return EVX_SUCCESS;
     }
 
 public:
-    explicit encoder_session(const evx1_config &cfg) : cfg_(cfg), initialized_(false), gpu_(NULL)
+    explicit encoder_session(const evx1_config &cfg) : cfg_(cfg), initialized_(false), gpu_(NULL), cstate_(CODER_IDLE), coder_up_(false), coder_stop_(false), retired_async_(false), coder_thread_(true), coder_nbins_(0), coder_bits_(0), coder_ms_(0.0)
     {
         memset(&stats_, 0, sizeof(stats_));
         memset(&header_, 0, sizeof(header_));
@@ -161,10 +221,12 @@ public:
         dev_count_ = 0;
         clear_frame();
     }
-    ~encoder_session() { clear(); }
+    ~encoder_session() { clear(); coder_shutdown(); }
 
     evx_status clear()                                       // evx1enc.cpp:27-40
     {
+        if (coder_up_) coder_wait_idle();
+        retired_async_ = false;
         if (!initialized_) return EVX_SUCCESS;
         clear_frame();
         if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }      // drains the stream; uncollected frames are dropped
@@ -195,8 +257,9 @@ public:
         if (width != header_.frame_width || height != header_.frame_height) return EVX_ERROR_INVALID_RESOURCE;
         const uint8 *rgb = static_cast<const uint8 *>(image);
         if (dev_count_ == 2)
-        {   // the device holds two frames: take the older one's results off it (it is finished or about to be)
-            evx_status st = retire();
+        {   // the device holds two frames: take the older one's results off it (it is finished or about to be); its
+            // arithmetic coder starts on the coder thread while this thread queues the new frame
+            evx_status st = retire(true);
             if (evx_failed(st)) return st;
         }
         const double t0 = now_ms();
@@ -211,7 +274,7 @@ public:
             if (rc == 8)
             {
                 if (retired_.valid) return EVX_ERROR_NOT_READY;
-                evx_status st = retire();
+                evx_status st = retire(true);
                 if (evx_failed(st)) return st;
                 rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
             }
@@ -236,20 +299,31 @@ public:
         if (!retired_.valid)
         {
             if (!dev_count_) return EVX_ERROR_NOT_READY;
-            evx_status st = retire();
+            evx_status st = retire(false);
             if (evx_failed(st)) return st;
         }
         const pending_frame f = retired_;
         retired_.valid = false;
+        // the slice first (whatever happens to the writes below, the coder thread is idle again afterwards)
+        const double t1 = now_ms();
+        uint32 bits;
+        double coder_ms = 0.0;
+        if (retired_async_)
+        {   // coded (or being coded) by the coder thread since submit() retired the frame
+            std::unique_lock<std::mutex> lk(cm_);
+            while (cstate_ != CODER_DONE) ccv_.wait(lk);
+            cstate_ = CODER_IDLE;
+            bits = coder_bits_; coder_ms = coder_ms_;
+            retired_async_ = false;
+        }
+        else bits = device_bins_ ? writer_.serialize_bins(bins_.data(), f.nbins)
+                                 : writer_.serialize(table_.data(), records_.data(), f.n_noncopy);
         if (f.first && evx_failed(output->write_bytes(&header_, sizeof(header_)))) return EVX_ERROR_EXECUTION_FAILURE;
         frame_desc desc = f.desc;
         if (evx_failed(output->write_bytes(&desc, sizeof(desc)))) return EVX_ERROR_EXECUTION_FAILURE;
-        const double t1 = now_ms();
-        uint32 bits = device_bins_ ? writer_.serialize_bins(bins_.data(), f.nbins)
-                                   : writer_.serialize(table_.data(), records_.data(), f.n_noncopy);
         if (!bits) return EVX_ERROR_EXECUTION_FAILURE;
         evx_status wst = output->write_bits(const_cast<uint8 *>(writer_.data()), bits);
-        stats_.gpu_ms = f.gpu_ms; stats_.entropy_ms = now_ms() - t1; stats_.slice_bits = bits;
+        stats_.gpu_ms = f.gpu_ms; stats_.entropy_ms = coder_ms > 0.0 ? coder_ms : now_ms() - t1; stats_.slice_bits = bits;
         stats_.noncopy_blocks = f.n_noncopy; stats_.d2h_bytes = f.d2h_bytes; stats_.wait_ms = f.wait_ms;
         // serialize_slice's write failures are ignored by the reference; report ours
         if (evx_failed(wst)) return EVX_ERROR_EXECUTION_FAILURE;
