@@ -161,8 +161,8 @@ public:
     // additions: decode() == submit() + collect().  submit takes one frame out of input (and empties it, like
     // decode) and hands its slice to a parser thread; collect merges the oldest submitted frame into the stream's
     // state, runs the pixel pipeline and writes its picture.  The arithmetic decoding of a slice needs nothing from
-    // other frames, so with submit(n+1), submit(n+2) before collect(n) the slices of consecutive frames are decoded
-    // concurrently (two parser threads) while the caller's thread runs the device.  At most three frames may be
+    // other frames, so with submit(n+1) ... submit(n+3) before collect(n) the slices of consecutive frames are decoded
+    // concurrently (three parser threads) while the caller's thread runs the device.  At most four frames may be
     // uncollected (EVX_ERROR_NOT_READY otherwise, and for decode() with any frame uncollected, and for collect
     // with none).  decode() itself parses on the calling thread.
     virtual evx_status submit(bit_stream *input) = 0;

@@ -203,15 +203,16 @@ def test_pipelined_decode_equals_synchronous():
     with pytest.raises(RuntimeError):
         dec.decode(streams[1][0], streams[1][1], w, h)     # decode() with a frame uncollected
     dec.submit(*streams[1])
-    dec.submit(*streams[2])                        # three frames may be uncollected (their slices parse concurrently)
+    dec.submit(*streams[2])
+    dec.submit(*streams[3])                        # four frames may be uncollected (their slices parse concurrently)
     with pytest.raises(RuntimeError):
-        dec.submit(*streams[3])                    # a fourth
+        dec.submit(*streams[4])                    # a fifth
     got = [dec.collect(w, h).copy()]
-    for t in range(3, n):
+    for t in range(4, n):
         dec.submit(*streams[t])
         got.append(dec.collect(w, h).copy())
-    got.append(dec.collect(w, h).copy())
-    got.append(dec.collect(w, h).copy())
+    for _ in range(3):
+        got.append(dec.collect(w, h).copy())
     with pytest.raises(RuntimeError):
         dec.collect(w, h)
     for t in range(n):
