@@ -366,6 +366,7 @@ struct EvxK2Params
     EvxInterResult *results;
     unsigned long long *counters;
     int thr;
+    int row0;                     // first macroblock row of this launch (a frame may be searched band by band)
 };
 
 struct EvxK2Stage
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(32, EVX_K2W_PER_SM) evx_inter_search(const __g
     int16_t *wv = wu + EVX_K2W_CWIN * EVX_K2W_CWIN;
     uint64_t *bar = reinterpret_cast<uint64_t *>(wv + EVX_K2W_CWIN * EVX_K2W_CWIN);
 
-    const int lane = threadIdx.x, ref = blockIdx.z, bx = blockIdx.x, by = blockIdx.y;
+    const int lane = threadIdx.x, ref = blockIdx.z, bx = blockIdx.x, by = blockIdx.y + p.row0;
     const int px = bx * EVX_MB, py = by * EVX_MB;
     const EvxGeom g = p.g;
     EvxK2Stage stage = { &p.maps.m[ref * 3 + 0], &p.maps.m[ref * 3 + 1], &p.maps.m[ref * 3 + 2], wy, wu, wv, bar, lane };
@@ -610,6 +611,13 @@ __device__ __forceinline__ void evx_build_pred_global(EvxMbShared &sh, const Evx
 
 // Polling with an acquire load costs an L1 invalidate (CCTL.IVALL) per poll, which stalls the
 // LSU the compute warps of the same SM are using; poll relaxed, fence once on success.
+__device__ __forceinline__ unsigned int evx_ld_relaxed_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ int evx_ld_relaxed(const int *p)
 {
     int v;
@@ -657,6 +665,14 @@ struct EvxK3Params
     int16_t *records;              // [nmb][384] coefficient records, slot = macroblock index
     int *row_records;              // [mbh] non-copy macroblocks per row (for evx_pack_records)
     int *sync;                     // [0] row ticket, [1] total records, [2..] progress[mbh]
+    // frames of one stream overlapping on the device (evxgpu.cu, frame overlap): monotonic counters, value = epoch + count
+    unsigned int *rows_done;       // this frame: epoch + complete macroblock rows (NULL: not published)
+    unsigned int rows_base;
+    const unsigned int *gate_k2;   // this frame's inter search: epoch + macroblock rows searched (NULL: the search has finished)
+    unsigned int gate_k2_base;
+    const unsigned int *gate_final;// previous frame: epoch + deblocked bands (NULL: the previous frame has finished)
+    unsigned int gate_final_base;
+    int band_rows, nbands;
     unsigned long long *counters;
     long long *prof;               // optional [mbh][6] per-row phase cycle sums (NULL in production)
     // for K8 (evx_bins.cuh): what serialize_slice's deltas and DC predictions refer to
@@ -894,7 +910,11 @@ __device__ __forceinline__ void evx_filter8(int s[8], int qp, int strength, bool
     }
 }
 
-struct EvxK4Params { EvxPlanes pl; EvxGeom g; const EvxDesc *table; };
+struct EvxK4Params
+{
+    EvxPlanes pl; EvxGeom g; const EvxDesc *table;
+    int ty0[2], tyn[2];           // first tile row and number of tile rows of this launch, [0] luma, [1] chroma (a frame may be filtered band by band)
+};
 
 __global__ void __launch_bounds__(128) evx_deblock(const __grid_constant__ EvxK4Params p)
 {
@@ -905,7 +925,8 @@ __global__ void __launch_bounds__(128) evx_deblock(const __grid_constant__ EvxK4
     const int mbs = luma ? 16 : 8;
     const int wb = w / mbs;
     int16_t *img = comp == 0 ? p.pl.y : (comp == 1 ? p.pl.u : p.pl.v);
-    const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = blockIdx.y;
+    if ((int) blockIdx.y >= p.tyn[luma ? 0 : 1]) return;
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = p.ty0[luma ? 0 : 1] + (int) blockIdx.y;
     if (tx > w / 8 || ty > h / 8) return;
     const int i = tx * 8, j = ty * 8;
     const bool has_l = i > 0, has_r = i < w, has_t = j > 0, has_b = j < h;

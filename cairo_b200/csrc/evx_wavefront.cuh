@@ -648,6 +648,24 @@ __global__ void __launch_bounds__(EVX_K3_NT, EVX_K3_MINCTAS) evx_wavefront(const
             };
             rearm(&S.full[0]); rearm(&S.full[1]); rearm(&S.fullb[0]); rearm(&S.fullb[1]);
             rearm(&S.full2[0]); rearm(&S.full2[1]); rearm(&S.empty[0]); rearm(&S.empty[1]);
+            // Frame overlap: this row may start once the previous frame is final (reconstructed AND deblocked) in every
+            // row this one reads as a reference and, with a ring of two, overwrites; and once this frame's inter search has
+            // reached it.  Both counters only grow, and whoever advances them never waits for this kernel.
+            const int row = S.row;
+            if (row < p.g.mbh)
+            {
+                if (p.gate_final)
+                {
+                    const unsigned int need = p.gate_final_base + (unsigned int) min(row / p.band_rows + 2, p.nbands);
+                    while ((int) (evx_ld_relaxed_u32(p.gate_final) - need) < 0) __nanosleep(500);
+                }
+                if (p.gate_k2)
+                {
+                    const unsigned int need = p.gate_k2_base + (unsigned int) row + 1u;
+                    while ((int) (evx_ld_relaxed_u32(p.gate_k2) - need) < 0) __nanosleep(200);
+                }
+                if (p.gate_final || p.gate_k2) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            }
         }
         __syncthreads();
         const int by = S.row;
@@ -657,5 +675,11 @@ __global__ void __launch_bounds__(EVX_K3_NT, EVX_K3_MINCTAS) evx_wavefront(const
         else if (warp == EVX_K3_CW) evx_k3_block_loader(S, p, by, lane);
         else if (warp == EVX_K3_CW + 1) evx_k3_column_loader(S, p, by, lane);
         __syncthreads();      // every role has left the row: its barriers and S.row may be reused
+        if (tid == 0 && p.rows_done)
+        {   // rows complete in order (the last macroblock of a row needs the last one of the row above), but their
+            // CTAs reach this line in any order: the counter takes the maximum
+            __threadfence();
+            atomicMax(p.rows_done, p.rows_base + (unsigned int) by + 1u);
+        }
     }
 }

@@ -44,6 +44,9 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+typedef CUresult (*stream_memop_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+static stream_memop_fn g_wait32 = NULL, g_write32 = NULL;
+
 struct evxgpu_handle
 {
     int device;
@@ -108,6 +111,22 @@ struct evxgpu_handle
     cudaEvent_t ev_out[2];
     bool pending_bins[2];
     uint64_t d2h_bytes[2];          // device-to-host bytes of the slot's frame
+    // Frame overlap (EVXGPU_FRAME_OVERLAP=1, bin-only output): the two frame slots own their per-frame device state and
+    // three streams each, and consecutive frames of the stream run concurrently, gated row by row through counters in
+    // device memory (stream memory operations on the host side, polls in the wavefront kernel).  See submit_overlap.
+    bool overlap;
+    struct frame_slot
+    {
+        int16_t *src_mem; EvxPlanes src;
+        EvxDesc *d_table; EvxInterResult *d_inter; int16_t *d_records; int *d_row_records; int *d_prev; int *d_sync;
+        cudaStream_t main, k2s, k4s;
+        cudaEvent_t ev_k1done, ev_k8done, ev_k4end, ev_k2end;
+        unsigned int epoch;             // of the frame last submitted into the slot
+        bool used;
+    } fs[2];
+    unsigned int *d_flags;          // [slot][3]: rows_done, final (deblocked bands), k2 rows done; value = epoch + count
+    unsigned int frame_seq;
+    int band_rows, nbands;
     int q_head, q_count;            // queue of submitted, uncollected frames: slots q_head, q_head ^ 1
     int last_slot;                  // slot of the last collected frame (evxgpu_d2h_bytes)
     uint32_t bins_last_total;       // bin count of the previous frame (sizes the optimistic head copy)
@@ -135,6 +154,9 @@ static int make_map(encode_tiled_fn enc, CUtensorMap *m, void *base, int w, int 
 
 extern "C" {
 
+static int sync_all(evxgpu_handle *h);
+static void use_slot(evxgpu_handle *h, int q);
+
 const char *evxgpu_last_error(void) { return g_err; }
 
 int evxgpu_device_count(void)
@@ -152,6 +174,25 @@ void evxgpu_device_free(void *p) { if (p) cudaFree(p); }
 int evxgpu_destroy(evxgpu_handle *h)
 {
     if (!h) return 1;
+    if (h->overlap)
+    {   // back to slot 0's view (the original allocations); slot 1 and the extra streams go here
+        sync_all(h);
+        use_slot(h, 0);
+        evxgpu_handle::frame_slot &b = h->fs[1];
+        cudaFree(b.src_mem); cudaFree(b.d_table); cudaFree(b.d_inter); cudaFree(b.d_records); cudaFree(b.d_row_records); cudaFree(b.d_prev); cudaFree(b.d_sync);
+        cudaFree(h->d_flags);
+        if (b.main) cudaStreamDestroy(b.main);
+        for (int q = 0; q < 2; ++q)
+        {
+            if (h->fs[q].k2s) cudaStreamDestroy(h->fs[q].k2s);
+            if (h->fs[q].k4s) cudaStreamDestroy(h->fs[q].k4s);
+            if (h->fs[q].ev_k1done) cudaEventDestroy(h->fs[q].ev_k1done);
+            if (h->fs[q].ev_k8done) cudaEventDestroy(h->fs[q].ev_k8done);
+            if (h->fs[q].ev_k4end) cudaEventDestroy(h->fs[q].ev_k4end);
+            if (h->fs[q].ev_k2end) cudaEventDestroy(h->fs[q].ev_k2end);
+        }
+        h->overlap = false;
+    }
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->src_mem);
@@ -284,6 +325,19 @@ int evxgpu_reset(evxgpu_handle *h)
 {
     if (!h) return 1;
     CK(cudaSetDevice(h->device));
+    if (h->overlap)
+    {
+        int rc = sync_all(h);
+        if (rc) return rc;
+        for (int q = 0; q < 2; ++q)
+        {
+            CK(cudaMemset(h->fs[q].src_mem, 0, plane_elems(h->g) * 2));
+            CK(cudaMemset(h->fs[q].d_table, 0, (size_t) h->nmb * 16));
+            h->fs[q].used = false; h->fs[q].epoch = 0;
+        }
+        CK(cudaMemset(h->d_flags, 0, 2 * 4 * sizeof(unsigned int)));
+        h->frame_seq = 0;
+    }
     const size_t pe = plane_elems(h->g);
     CK(cudaMemsetAsync(h->src_mem, 0, pe * 2, h->stream));
     for (int i = 0; i < h->cfg.ref_count; ++i) CK(cudaMemsetAsync(h->ring_mem[i], 0, pe * 2, h->stream));
@@ -297,7 +351,7 @@ int evxgpu_reset(evxgpu_handle *h)
 }
 
 int evxgpu_block_count(const evxgpu_handle *h) { return h ? h->nmb : 0; }
-int evxgpu_synchronize(evxgpu_handle *h) { if (!h) return 1; CK(cudaSetDevice(h->device)); CK(cudaStreamSynchronize(h->stream)); return 0; }
+int evxgpu_synchronize(evxgpu_handle *h) { if (!h) return 1; CK(cudaSetDevice(h->device)); return sync_all(h); }
 uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h) { return h ? h->d2h_bytes[h->last_slot] : 0; }
 
 uint64_t evxgpu_launch_count(const evxgpu_handle *h) { return h ? h->launches : 0; }
@@ -313,8 +367,8 @@ int evxgpu_upload(evxgpu_handle *h, void *dst_device, const void *src_host, uint
 
 int evxgpu_enable_timing(evxgpu_handle *h, int on) { if (!h) return 1; h->timing = on != 0; return 0; }
 
-static void t_begin(evxgpu_handle *h, int k) { if (h->timing) { cudaEventRecord(h->ev[h->slot][k][0], h->stream); } }
-static void t_end(evxgpu_handle *h, int k) { if (h->timing) { cudaEventRecord(h->ev[h->slot][k][1], h->stream); h->ev_valid[h->slot][k] = true; } }
+static void t_begin(evxgpu_handle *h, int k) { if (h->timing && !h->overlap) { cudaEventRecord(h->ev[h->slot][k][0], h->stream); } }
+static void t_end(evxgpu_handle *h, int k) { if (h->timing && !h->overlap) { cudaEventRecord(h->ev[h->slot][k][1], h->stream); h->ev_valid[h->slot][k] = true; } }
 
 // folds the events of the last submitted frame into the running sums (its kernels have been queued; the
 // last event is waited for, which costs nothing once the frame has been collected)
@@ -412,7 +466,7 @@ static int launch_inter_search(evxgpu_handle *h, uint32_t index, int quality)
             for (int c = 0; c < 3; ++c) p.maps.m[(off - 1) * 3 + c] = h->maps_w[slot][c];
             p.ref[off - 1] = h->ring[slot];
         }
-        p.src = h->src; p.g = h->g; p.results = h->d_inter; p.counters = h->d_counters; p.thr = (quality >> 2) + 1;
+        p.src = h->src; p.g = h->g; p.results = h->d_inter; p.counters = h->d_counters; p.thr = (quality >> 2) + 1; p.row0 = 0;
         dim3 block(32), grid(h->g.mbw, h->g.mbh, R - 1);
         t_begin(h, EVXGPU_T_INTER_SEARCH);
         evx_inter_search<<<grid, block, EVX_K2W_SMEM, h->stream>>>(p);
@@ -432,6 +486,7 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
     p.frame_type = frame_type; p.quality = quality; p.frame_index = index;
     p.inter = h->d_inter; p.table = h->d_table; p.records = h->d_records; p.row_records = h->d_row_records;
     p.sync = h->d_sync; p.counters = h->d_counters; p.prof = h->d_prof;
+    p.rows_done = NULL; p.rows_base = 0; p.gate_k2 = NULL; p.gate_k2_base = 0; p.gate_final = NULL; p.gate_final_base = 0; p.band_rows = 1; p.nbands = 0;
     p.prev_motion = h->d_prev; p.prev_coded = h->d_prev + h->nmb; p.row_last = h->d_prev + 2 * h->nmb;
     CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
     t_begin(h, EVXGPU_T_WAVEFRONT);
@@ -453,6 +508,7 @@ static int launch_deblock(evxgpu_handle *h, uint32_t index)
     if (!h->cfg.deblocking) return 0;
     EvxK4Params p;
     p.pl = h->ring[index % (uint32_t) h->cfg.ref_count]; p.g = h->g; p.table = h->d_table;
+    p.ty0[0] = p.ty0[1] = 0; p.tyn[0] = h->g.h / 8 + 1; p.tyn[1] = h->g.h / 16 + 1;      // the whole frame
     dim3 block(128), grid((h->g.w / 8 + 1 + 127) / 128, h->g.h / 8 + 1, 3);
     t_begin(h, EVXGPU_T_DEBLOCK);
     evx_deblock<<<grid, block, 0, h->stream>>>(p);
@@ -494,6 +550,212 @@ static int launch_bins(evxgpu_handle *h, bool emit_only)
     return 0;
 }
 
+// ------------------------------------------------------------------ frame overlap
+
+enum { FLAG_ROWS = 0, FLAG_FINAL = 1, FLAG_K2 = 2 };
+
+// the handle's per-frame pointers and its stream become those of slot q (every launch helper uses them)
+static void use_slot(evxgpu_handle *h, int q)
+{
+    evxgpu_handle::frame_slot &f = h->fs[q];
+    h->src_mem = f.src_mem; h->src = f.src; h->d_table = f.d_table; h->d_inter = f.d_inter; h->d_records = f.d_records;
+    h->d_row_records = f.d_row_records; h->d_prev = f.d_prev; h->d_sync = f.d_sync; h->stream = f.main;
+    h->slot = q;
+}
+
+static int sync_all(evxgpu_handle *h)
+{
+    if (h->overlap)
+        for (int q = 0; q < 2; ++q)
+        {
+            CK(cudaStreamSynchronize(h->fs[q].main)); CK(cudaStreamSynchronize(h->fs[q].k2s)); CK(cudaStreamSynchronize(h->fs[q].k4s));
+        }
+    else CK(cudaStreamSynchronize(h->stream));
+    if (h->copy_stream) CK(cudaStreamSynchronize(h->copy_stream));
+    return 0;
+}
+
+static int enable_overlap(evxgpu_handle *h)
+{
+    if (h->overlap) return 0;
+    if (!h->own_stream) return 0;                         // a caller's stream cannot be one of two
+    if (!g_wait32)
+    {
+        void *f1 = NULL, *f2 = NULL;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f1, cudaEnableDefault, &qres) != cudaSuccess || !f1) return 0;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f2, cudaEnableDefault, &qres) != cudaSuccess || !f2) return 0;
+        g_wait32 = (stream_memop_fn) f1; g_write32 = (stream_memop_fn) f2;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    const size_t pe = plane_elems(h->g);
+    evxgpu_handle::frame_slot &a = h->fs[0], &b = h->fs[1];
+    a.src_mem = h->src_mem; a.src = h->src; a.d_table = h->d_table; a.d_inter = h->d_inter; a.d_records = h->d_records;
+    a.d_row_records = h->d_row_records; a.d_prev = h->d_prev; a.d_sync = h->d_sync; a.main = h->stream;
+    bool ok = true;
+    ok = ok && cudaMalloc(&b.src_mem, pe * 2) == cudaSuccess;
+    ok = ok && cudaMalloc(&b.d_table, (size_t) h->nmb * 16) == cudaSuccess;
+    ok = ok && cudaMalloc(&b.d_inter, (size_t) h->nmb * (h->cfg.ref_count - 1) * sizeof(EvxInterResult)) == cudaSuccess;
+    ok = ok && cudaMalloc(&b.d_records, (size_t) h->nmb * 384 * 2) == cudaSuccess;
+    ok = ok && cudaMalloc(&b.d_row_records, (size_t) h->g.mbh * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&b.d_prev, ((size_t) h->nmb * 2 + (size_t) h->g.mbh * 2) * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&b.d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_flags, 2 * 4 * sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&b.main, cudaStreamNonBlocking) == cudaSuccess;
+    for (int q = 0; q < 2 && ok; ++q)
+    {
+        ok = ok && cudaStreamCreateWithFlags(&h->fs[q].k2s, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&h->fs[q].k4s, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k1done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k8done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k4end, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k2end, cudaEventDisableTiming) == cudaSuccess;
+        h->fs[q].epoch = 0; h->fs[q].used = false;
+    }
+    if (!ok) return fail(3, "frame overlap: out of device memory");
+    set_planes(b.src, b.src_mem, h->g);
+    CK(cudaMemset(b.src_mem, 0, pe * 2));                 // padding rows/columns stay zero
+    CK(cudaMemset(b.d_table, 0, (size_t) h->nmb * 16));
+    CK(cudaMemset(h->d_flags, 0, 2 * 4 * sizeof(unsigned int)));
+    int br = 4;
+    if (const char *e = getenv("EVXGPU_BAND_ROWS")) { int v = atoi(e); if (v >= 3) br = v; }
+    h->band_rows = br; h->nbands = (h->g.mbh + br - 1) / br;
+    h->frame_seq = 0;
+    h->overlap = true;
+    return 0;
+}
+
+// One frame, queued so that it overlaps the previous frame of the stream.  Everything of the frame lives in slot q;
+// p = q ^ 1 holds the previous frame, which may still be running.  Dependencies on the previous frame (SURVEY H3,
+// DESIGN section 6a), all by rows: K2 and the inter predictions of rows [r-2, r+3] need it deblocked there; its band b
+// may be deblocked once its wavefront has finished row band_end(b)+3 (the intra search reads three rows up, unfiltered);
+// with a ring of two this frame overwrites the slot the previous one reads as its reference, two rows behind what K2
+// already requires.  Row counters live in device memory: the host side waits on them with stream memory operations
+// (no kernel occupies the device while it waits), the wavefront kernel polls them.
+static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device, int frame_type, uint32_t frame_index, int quality)
+{
+    const int q = (h->q_head + h->q_count) & 1, p = q ^ 1;
+    if (h->frame_seq >= (1u << 19))
+    {   // the epochs restart when nothing is in flight
+        if (h->q_count) return fail(8, "evxgpu_encode_submit: epoch wrap, collect the frame in flight first");
+        int rc = sync_all(h);
+        if (rc) return rc;
+        CK(cudaMemset(h->d_flags, 0, 2 * 4 * sizeof(unsigned int)));
+        h->frame_seq = 0; h->fs[0].used = h->fs[1].used = false;
+    }
+    use_slot(h, q);
+    evxgpu_handle::frame_slot &f = h->fs[q], &pv = h->fs[p];
+    const unsigned int E = (++h->frame_seq) << 12, Ep = pv.epoch;
+    const bool have_prev = pv.used;
+    unsigned int *fl = h->d_flags + 4 * q, *flp = h->d_flags + 4 * p;
+    const int B = h->band_rows, NB = h->nbands, mbh = h->g.mbh;
+    auto dptr = [](unsigned int *x) { return (CUdeviceptr) (uintptr_t) x; };
+#define MEMOP(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) return fail(5, "stream memory operation failed"); } while (0)
+
+    const uint8_t *d_rgb = rgb;
+    if (rgb_is_device == 2) { CK(cudaStreamWaitEvent(f.main, h->ev_up, 0)); h->uploaded = false; }
+    if (!rgb_is_device)
+    {
+        if (have_prev) CK(cudaStreamWaitEvent(f.main, pv.ev_k1done, 0));       // the single staging buffer has been consumed
+        CK(cudaMemcpyAsync(h->d_rgb, rgb, (size_t) h->g.vw * h->g.vh * 3, cudaMemcpyHostToDevice, f.main));
+        d_rgb = h->d_rgb;
+    }
+    int rc;
+    h->d2h_bytes[q] = 0;
+    if ((rc = launch_convert_in(h, d_rgb))) return rc;
+    CK(cudaEventRecord(f.ev_k1done, f.main));
+    if (rgb_is_device == 2) CK(cudaEventRecord(h->ev_k1, f.main));
+
+    // K2, band by band, on its own stream
+    if (frame_type == 1)
+    {
+        const int R = h->cfg.ref_count;
+        EvxK2Params kp;
+        for (int off = 1; off < R; ++off)
+        {
+            int slot = (int) ((frame_index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);
+            for (int c = 0; c < 3; ++c) kp.maps.m[(off - 1) * 3 + c] = h->maps_w[slot][c];
+            kp.ref[off - 1] = h->ring[slot];
+        }
+        kp.src = f.src; kp.g = h->g; kp.results = f.d_inter; kp.counters = h->d_counters; kp.thr = (quality >> 2) + 1;
+        CK(cudaStreamWaitEvent(f.k2s, f.ev_k1done, 0));
+        for (int c = 0; c < NB; ++c)
+        {
+            const int r0 = c * B, r1 = std::min(mbh, r0 + B);
+            if (have_prev) MEMOP(g_wait32((CUstream) f.k2s, dptr(flp + FLAG_FINAL), Ep + (unsigned int) std::min(c + 2, NB), CU_STREAM_WAIT_VALUE_GEQ));
+            kp.row0 = r0;
+            evx_inter_search<<<dim3(h->g.mbw, r1 - r0, R - 1), 32, EVX_K2W_SMEM, f.k2s>>>(kp);
+            MEMOP(g_write32((CUstream) f.k2s, dptr(fl + FLAG_K2), E + (unsigned int) r1, CU_STREAM_WRITE_VALUE_DEFAULT));
+            h->launches++;
+        }
+        CK(cudaEventRecord(f.ev_k2end, f.k2s));
+        CK(cudaGetLastError());
+    }
+
+    // K3: queued only when the previous frame's wavefront kernel has started to complete rows, i.e. is resident
+    if (have_prev) MEMOP(g_wait32((CUstream) f.main, dptr(flp + FLAG_ROWS), Ep + 1u, CU_STREAM_WAIT_VALUE_GEQ));
+    {
+        EvxK3Params kp;
+        kp.src = f.src;
+        for (int i = 0; i < 8; ++i) kp.ring[i] = h->ring[i];
+        kp.g = h->g; kp.R = h->cfg.ref_count; kp.linear = h->cfg.linear_quant;
+        kp.frame_type = frame_type; kp.quality = quality; kp.frame_index = frame_index;
+        kp.inter = f.d_inter; kp.table = f.d_table; kp.records = f.d_records; kp.row_records = f.d_row_records;
+        kp.sync = f.d_sync; kp.counters = h->d_counters; kp.prof = NULL;
+        kp.prev_motion = f.d_prev; kp.prev_coded = f.d_prev + h->nmb; kp.row_last = f.d_prev + 2 * h->nmb;
+        kp.rows_done = fl + FLAG_ROWS; kp.rows_base = E;
+        kp.gate_k2 = frame_type == 1 ? fl + FLAG_K2 : NULL; kp.gate_k2_base = E;
+        kp.gate_final = have_prev ? flp + FLAG_FINAL : NULL; kp.gate_final_base = Ep;
+        kp.band_rows = B; kp.nbands = NB;
+        CK(cudaMemsetAsync(f.d_sync, 0, (size_t) (mbh + 2) * 4, f.main));
+        evx_wavefront<<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), f.main>>>(kp);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+
+    // K4, band by band behind the wavefront, on its own stream; each band done advances `final`
+    {
+        EvxK4Params dp;
+        dp.pl = h->ring[frame_index % (uint32_t) h->cfg.ref_count]; dp.g = h->g; dp.table = f.d_table;
+        const int lt = h->g.h / 8 + 1, ct = h->g.h / 16 + 1;
+        for (int b = 0; b < NB; ++b)
+        {
+            MEMOP(g_wait32((CUstream) f.k4s, dptr(fl + FLAG_ROWS), E + (unsigned int) std::min(b * B + B + 3, mbh), CU_STREAM_WAIT_VALUE_GEQ));
+            if (h->cfg.deblocking)
+            {
+                dp.ty0[0] = 2 * B * b; dp.tyn[0] = (b == NB - 1) ? lt - dp.ty0[0] : 2 * B;
+                dp.ty0[1] = B * b;     dp.tyn[1] = (b == NB - 1) ? ct - dp.ty0[1] : B;
+                dim3 block(128), grid((h->g.w / 8 + 1 + 127) / 128, std::max(dp.tyn[0], dp.tyn[1]), 3);
+                evx_deblock<<<grid, block, 0, f.k4s>>>(dp);
+                h->launches++;
+            }
+            MEMOP(g_write32((CUstream) f.k4s, dptr(fl + FLAG_FINAL), E + (unsigned int) (b + 1), CU_STREAM_WRITE_VALUE_DEFAULT));
+        }
+        CK(cudaEventRecord(f.ev_k4end, f.k4s));
+        CK(cudaGetLastError());
+    }
+
+    // K8 (the DC mirror is walked in frame order) and the copies
+    if (have_prev) CK(cudaStreamWaitEvent(f.main, pv.ev_k8done, 0));
+    if ((rc = launch_bins(h, false))) return rc;
+    CK(cudaEventRecord(f.ev_k8done, f.main));
+    const uint32_t guess = h->bins_last_total ? ((h->bins_last_total + h->bins_last_total / 4 + 8192) & ~63u) : 1u << 19;
+    h->bins_prefix_bits[q] = std::min<uint32_t>(std::min(h->bins_cap_bits, h->h_bins_cap_bits[q]), std::min<uint32_t>(guess, 1u << 22));
+    CK(cudaMemcpyAsync(h->h_bins[q], h->d_bins_total[q], 16, cudaMemcpyDeviceToHost, f.main));
+    CK(cudaMemcpyAsync(h->h_bins[q] + 4, h->d_bins[q], h->bins_prefix_bits[q] / 8, cudaMemcpyDeviceToHost, f.main));
+    h->d2h_bytes[q] += 16 + h->bins_prefix_bits[q] / 8;
+    h->pending_bins[q] = true;
+    CK(cudaEventRecord(h->ev_out[q], f.main));
+    // join: the tail of the slot's main stream is the whole frame (what the next frame in this slot queues behind)
+    CK(cudaStreamWaitEvent(f.main, f.ev_k4end, 0));
+    if (frame_type == 1) CK(cudaStreamWaitEvent(f.main, f.ev_k2end, 0));
+#undef MEMOP
+    f.epoch = E; f.used = true;
+    h->q_count++;
+    h->pending_encode = true;
+    return 0;
+}
+
 // ------------------------------------------------------------------ encoder
 
 // (re)allocates the two slots' string buffers: device capacity cap_bits each, pinned host capacity hcap_bits each
@@ -527,6 +789,11 @@ int evxgpu_set_output(evxgpu_handle *h, int mode)
         if (rc) return rc;
     }
     h->out_mode = mode;
+    if (mode == 1)
+    {
+        const char *ov = getenv("EVXGPU_FRAME_OVERLAP");
+        if (ov && ov[0] == '1') { int rc = enable_overlap(h); if (rc) return rc; }
+    }
     return 0;
 }
 
@@ -551,6 +818,7 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     if (h->q_count >= 2 || (h->q_count == 1 && !(h->out_mode == 1 && h->bins_cap_bits >= h->bins_worst_bits)))
         return fail(8, "evxgpu_encode_submit: previous frame not collected");
     CK(cudaSetDevice(h->device));
+    if (h->overlap && h->out_mode == 1 && !h->k2_tile) return submit_overlap(h, rgb, rgb_is_device, frame_type, frame_index, quality);
     const int q = (h->q_head + h->q_count) & 1;
     h->slot = q;
     if (h->timing) t_fold(h, q);                 // the frame that used this slot before was collected long ago
@@ -603,7 +871,7 @@ int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins_out, uint
     CK(cudaEventSynchronize(h->ev_out[q]));
     const uint32_t total = h->h_bins[q][0], coded = h->h_bins[q][2];
     // what is left to copy goes over the copy stream: the main stream may already hold the next frame's kernels
-    cudaStream_t cs = h->q_count > 1 ? h->copy_stream : h->stream;
+    cudaStream_t cs = (h->q_count > 1 || h->overlap) ? h->copy_stream : h->stream;
     if (h->h_bins[q][1])
     {   // the string outgrew the device buffer (only possible with a capacity below the worst case, see
         // evxgpu_debug_set_bins_capacity, and then only one frame is in flight): enlarge both slots and emit again
