@@ -46,6 +46,12 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
 
 typedef CUresult (*stream_memop_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 static stream_memop_fn g_wait32 = NULL, g_write32 = NULL;
+// Encoders with frame overlap per device, process-wide.  Overlap pays when a stream has the device (mostly) to itself;
+// many streams fill the device by themselves, and their overlapped kernels would only compete (measured: 8 streams
+// 2 475 -> 1 321 frames/s).  So at most two encoders per device overlap their frames, the others run frame after frame.
+#include <atomic>
+static std::atomic<int> g_overlap_live[64];
+enum { EVX_MAX_OVERLAP_ENCODERS = 2 };
 
 struct evxgpu_handle
 {
@@ -122,6 +128,7 @@ struct evxgpu_handle
         cudaStream_t main, k2s, k4s;
         cudaEvent_t ev_k1done, ev_k8done, ev_k4end, ev_k2end;
         unsigned int epoch;             // of the frame last submitted into the slot
+        int B, NB;                      // its banding: rows per band, bands (the unit of its `final` counter)
         bool used;
     } fs[2];
     unsigned int *d_flags;          // [slot][3]: rows_done, final (deblocked bands), k2 rows done; value = epoch + count
@@ -192,6 +199,7 @@ int evxgpu_destroy(evxgpu_handle *h)
             if (h->fs[q].ev_k2end) cudaEventDestroy(h->fs[q].ev_k2end);
         }
         h->overlap = false;
+        g_overlap_live[h->device].fetch_sub(1);
     }
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -579,6 +587,8 @@ static int enable_overlap(evxgpu_handle *h)
 {
     if (h->overlap) return 0;
     if (!h->own_stream) return 0;                         // a caller's stream cannot be one of two
+    if (h->device < 0 || h->device >= 64) return 0;
+    if (g_overlap_live[h->device].fetch_add(1) >= EVX_MAX_OVERLAP_ENCODERS) { g_overlap_live[h->device].fetch_sub(1); return 0; }
     if (!g_wait32)
     {
         void *f1 = NULL, *f2 = NULL;
@@ -612,7 +622,7 @@ static int enable_overlap(evxgpu_handle *h)
         ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k2end, cudaEventDisableTiming) == cudaSuccess;
         h->fs[q].epoch = 0; h->fs[q].used = false;
     }
-    if (!ok) return fail(3, "frame overlap: out of device memory");
+    if (!ok) { g_overlap_live[h->device].fetch_sub(1); return fail(3, "frame overlap: out of device memory"); }
     set_planes(b.src, b.src_mem, h->g);
     CK(cudaMemset(b.src_mem, 0, pe * 2));                 // padding rows/columns stay zero
     CK(cudaMemset(b.d_table, 0, (size_t) h->nmb * 16));
@@ -648,7 +658,12 @@ static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_devic
     const unsigned int E = (++h->frame_seq) << 12, Ep = pv.epoch;
     const bool have_prev = pv.used;
     unsigned int *fl = h->d_flags + 4 * q, *flp = h->d_flags + 4 * p;
-    const int B = h->band_rows, NB = h->nbands, mbh = h->g.mbh;
+    const int mbh = h->g.mbh;
+    // A frame submitted with nothing in flight (encode() one frame at a time, or the first frame of a pipelined run) is
+    // queued as ONE band: no successor is waiting to follow it row by row, and a band costs three driver calls.
+    const bool whole = h->q_count == 0;
+    const int B = whole ? mbh : h->band_rows, NB = whole ? 1 : h->nbands;
+    const int Bp = pv.B > 0 ? pv.B : mbh, NBp = pv.NB > 0 ? pv.NB : 1;       // the previous frame's banding
     auto dptr = [](unsigned int *x) { return (CUdeviceptr) (uintptr_t) x; };
 #define MEMOP(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) return fail(5, "stream memory operation failed"); } while (0)
 
@@ -682,7 +697,7 @@ static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_devic
         for (int c = 0; c < NB; ++c)
         {
             const int r0 = c * B, r1 = std::min(mbh, r0 + B);
-            if (have_prev) MEMOP(g_wait32((CUstream) f.k2s, dptr(flp + FLAG_FINAL), Ep + (unsigned int) std::min(c + 2, NB), CU_STREAM_WAIT_VALUE_GEQ));
+            if (have_prev) MEMOP(g_wait32((CUstream) f.k2s, dptr(flp + FLAG_FINAL), Ep + (unsigned int) std::min((r1 - 1) / Bp + 2, NBp), CU_STREAM_WAIT_VALUE_GEQ));
             kp.row0 = r0;
             evx_inter_search<<<dim3(h->g.mbw, r1 - r0, R - 1), 32, EVX_K2W_SMEM, f.k2s>>>(kp);
             MEMOP(g_write32((CUstream) f.k2s, dptr(fl + FLAG_K2), E + (unsigned int) r1, CU_STREAM_WRITE_VALUE_DEFAULT));
@@ -706,7 +721,7 @@ static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_devic
         kp.rows_done = fl + FLAG_ROWS; kp.rows_base = E;
         kp.gate_k2 = frame_type == 1 ? fl + FLAG_K2 : NULL; kp.gate_k2_base = E;
         kp.gate_final = have_prev ? flp + FLAG_FINAL : NULL; kp.gate_final_base = Ep;
-        kp.band_rows = B; kp.nbands = NB;
+        kp.band_rows = Bp; kp.nbands = NBp;          // units of the previous frame's `final` counter
         CK(cudaMemsetAsync(f.d_sync, 0, (size_t) (mbh + 2) * 4, f.main));
         evx_wavefront<<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), f.main>>>(kp);
         h->launches++;
@@ -750,7 +765,7 @@ static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_devic
     CK(cudaStreamWaitEvent(f.main, f.ev_k4end, 0));
     if (frame_type == 1) CK(cudaStreamWaitEvent(f.main, f.ev_k2end, 0));
 #undef MEMOP
-    f.epoch = E; f.used = true;
+    f.epoch = E; f.used = true; f.B = B; f.NB = NB;
     h->q_count++;
     h->pending_encode = true;
     return 0;
@@ -791,8 +806,9 @@ int evxgpu_set_output(evxgpu_handle *h, int mode)
     h->out_mode = mode;
     if (mode == 1)
     {
+        // consecutive frames overlap on the device unless EVXGPU_FRAME_OVERLAP=0 (A/B runs, per-kernel timing)
         const char *ov = getenv("EVXGPU_FRAME_OVERLAP");
-        if (ov && ov[0] == '1') { int rc = enable_overlap(h); if (rc) return rc; }
+        if (!(ov && ov[0] == '0')) { int rc = enable_overlap(h); if (rc) return rc; }
     }
     return 0;
 }

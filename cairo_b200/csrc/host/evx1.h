@@ -138,12 +138,14 @@ public:
     // additions: encode() == submit() + collect().  submit queues the frame on the device (colour
     // conversion, motion search, transform/quantisation, reconstruction, deblocking, binarisation) and
     // returns; collect appends what encode() would have appended for the oldest uncollected frame (stream
-    // header on the first frame, frame descriptor, slice).  Up to two frames may be uncollected when submit is
-    // called.  submit(n+1) before collect(n) runs the entropy coder of frame n while the device encodes frame n+1;
-    // submit(n+2) before collect(n) additionally puts frame n+2's host->device copy under frame n+1's kernels, so
-    // the device never waits for a copy either (two frames of latency).  `image` must stay unchanged until the
-    // frame's own collect() returns.  A third uncollected frame makes submit (and any uncollected frame makes
-    // encode) return EVX_ERROR_NOT_READY; collect with nothing submitted returns the same.
+    // header on the first frame, frame descriptor, slice).  Several frames may be uncollected: two on the device,
+    // where consecutive frames overlap row by row, and up to four retired ones whose slices are being entropy-coded
+    // on the session's coder threads (a slice's coder needs nothing from other frames).  With submit(n+k) before
+    // collect(n), k = 1..4, the host entropy stage, the device's work and the host->device copies of different frames
+    // all run at the same time; collect() returns the frames in order, the same bytes encode() appends.  `image` must
+    // stay unchanged until the frame's own collect() returns.  submit returns EVX_ERROR_NOT_READY when the device
+    // holds two frames and four retired ones wait to be collected; encode() when any frame is uncollected; collect()
+    // when none is.
     virtual evx_status submit(void *image, uint32 width, uint32 height) = 0;
     virtual evx_status collect(bit_stream *output) = 0;
 };

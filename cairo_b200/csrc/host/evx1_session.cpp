@@ -69,12 +69,12 @@ class encoder_session : public evx1_encoder
     frame_desc frame_;
     stream_header header_;
     evxgpu_handle *gpu_;
-    slice_writer writer_;
+    slice_writer writer_;                          // table + records output: the stateful host binarisation (one frame at a time)
     evx1_frame_stats stats_;
-    bool device_bins_;
+    bool device_bins_, coder_threads_;
 
-    // A frame between submit() and collect() is either on the device (its kernels and copies are queued
-    // or running) or retired: its per-macroblock results are on the host, waiting for the entropy stage.
+    // A frame between submit() and collect() is on the device (its kernels and copies are queued or running; the device
+    // library holds two) or retired: a job that owns the frame's results and runs -- or has run -- the entropy stage.
     struct pending_frame
     {
         bool valid, first;
@@ -83,57 +83,96 @@ class encoder_session : public evx1_encoder
         uint32 n_noncopy, d2h_bytes;
         uint64_t nbins;
     };
-    pending_frame dev_[2], retired_;               // dev_[0] is the older of the frames on the device
+    pending_frame dev_[2];                         // dev_[0] is the older of the frames on the device
     int dev_count_;
-    std::vector<uint64_t> bins_;                   // retired frame, bin output
     std::vector<evxgpu_block_desc> table_;         // retired frame, table + records output
     std::vector<int16> records_;
 
-    // The arithmetic coder of a frame retired by submit() runs on a thread of its own, so that the caller's thread
-    // is free to queue the next frame; collect() waits for it.  One frame at a time (there is one retired slot).
-    std::thread coder_;
-    std::mutex cm_;
-    std::condition_variable ccv_;
-    enum { CODER_IDLE, CODER_WORK, CODER_DONE } cstate_;
-    bool coder_up_, coder_stop_, retired_async_, coder_thread_;
-    uint64_t coder_nbins_;
-    uint32 coder_bits_;
-    double coder_ms_;
-
-    void coder_main()
+    // Bin-string output: the arithmetic coder of a slice needs nothing but the slice's bins (the coder is reset per
+    // frame, serialize.cpp:323), so retired frames are coded by worker threads, several at a time, and collected in order.
+    enum { kJobs = 4, kWorkers = 3 };
+    enum job_state { JOB_FREE = 0, JOB_QUEUED, JOB_RUNNING, JOB_DONE };
+    struct job
     {
-        std::unique_lock<std::mutex> lk(cm_);
+        job_state state;
+        pending_frame f;
+        std::vector<uint64_t> bins;
+        slice_writer writer;                       // serialize_bins only: no state between frames
+        uint32 bits;
+        double ms;
+    };
+    job jobs_[kJobs];
+    int head_, count_;                             // retired, uncollected frames: jobs head_, head_+1, ... (mod kJobs)
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::thread workers_[kWorkers];
+    bool threads_up_, stop_;
+
+    void run_job(job &j)
+    {
+        const double t0 = now_ms();
+        j.bits = device_bins_ ? j.writer.serialize_bins(j.bins.data(), j.f.nbins)
+                              : writer_.serialize(table_.data(), records_.data(), j.f.n_noncopy);
+        j.ms = now_ms() - t0;
+    }
+
+    void worker()
+    {
+        std::unique_lock<std::mutex> lk(m_);
         for (;;)
         {
-            while (cstate_ != CODER_WORK && !coder_stop_) ccv_.wait(lk);
-            if (coder_stop_) return;
+            job *mine = NULL;
+            for (int k = 0; k < count_ && !mine; ++k)
+            {
+                job &j = jobs_[(head_ + k) % kJobs];
+                if (j.state == JOB_QUEUED) mine = &j;
+            }
+            if (!mine)
+            {
+                if (stop_) return;
+                cv_work_.wait(lk);
+                continue;
+            }
+            mine->state = JOB_RUNNING;
             lk.unlock();
-            const double t0 = now_ms();
-            const uint32 bits = writer_.serialize_bins(bins_.data(), coder_nbins_);
-            const double ms = now_ms() - t0;
+            run_job(*mine);
             lk.lock();
-            coder_bits_ = bits; coder_ms_ = ms;
-            cstate_ = CODER_DONE;
-            ccv_.notify_all();
+            mine->state = JOB_DONE;
+            cv_done_.notify_all();
         }
     }
 
-    void coder_wait_idle()          // a job in progress is finished and forgotten
+    void start_threads()
     {
-        std::unique_lock<std::mutex> lk(cm_);
-        while (cstate_ == CODER_WORK) ccv_.wait(lk);
-        cstate_ = CODER_IDLE;
+        if (threads_up_) return;
+        stop_ = false;
+        for (int k = 0; k < kWorkers; ++k) workers_[k] = std::thread(&encoder_session::worker, this);
+        threads_up_ = true;
     }
 
-    void coder_shutdown()
+    void stop_threads()
     {
-        if (!coder_up_) return;
-        coder_wait_idle();
-        { std::lock_guard<std::mutex> g(cm_); coder_stop_ = true; }
-        ccv_.notify_all();
-        coder_.join();
-        coder_up_ = false;
+        if (!threads_up_) return;
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_work_.notify_all();
+        for (int k = 0; k < kWorkers; ++k) workers_[k].join();
+        threads_up_ = false;
     }
+
+    void drop_jobs()             // uncollected retired frames are forgotten; a slice being coded is waited for
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        for (int k = 0; k < count_; ++k)
+        {
+            job &j = jobs_[(head_ + k) % kJobs];
+            if (j.state == JOB_QUEUED) j.state = JOB_FREE;
+            while (j.state == JOB_RUNNING) cv_done_.wait(lk);
+            j.state = JOB_FREE;
+        }
+        head_ = 0; count_ = 0;
+    }
+
+    int max_jobs() const { return device_bins_ ? kJobs : 1; }      // the host binarisation keeps one frame's table and records
 
     void clear_frame()          // clear_frame, common.cpp:50-64
     {
@@ -158,34 +197,36 @@ class encoder_session : public evx1_encoder
         // The device binarises the slice (include/evxgpu.h, evxgpu_set_output); EVX1_HOST_BINARISE=1 keeps
         // the table + records path and binarises here instead (same bits; for A/B measurements).
         device_bins_ = getenv("EVX1_HOST_BINARISE") == NULL;
-        { const char *ct = getenv("EVX1_CODER_THREAD"); coder_thread_ = !(ct && ct[0] == '0'); }      // EVX1_CODER_THREAD=0: code on the caller's thread
+        { const char *ct = getenv("EVX1_CODER_THREAD"); coder_threads_ = !(ct && ct[0] == '0'); }      // EVX1_CODER_THREAD=0: code on the caller's thread
         if (device_bins_ && (rc = evxgpu_set_output(gpu_, 1))) return map_gpu_status(rc);
         int mbw = (int) ((width + 15) / 16), mbh = (int) ((height + 15) / 16);
         writer_.configure(mbw, mbh, cfg_.ref_count);
+        for (int k = 0; k < kJobs; ++k) jobs_[k].writer.configure(mbw, mbh, cfg_.ref_count);
         table_.assign((size_t) mbw * mbh, evxgpu_block_desc());
         records_.assign((size_t) mbw * mbh * EVXGPU_MB_COEFFS, 0);
         initialized_ = true;
         return EVX_SUCCESS;
     }
 
-    // Waits for the frame on the device and moves its results into session memory, which frees the device
-    // library's staging buffers for the next submit.
-    evx_status retire(bool async_coder)
+    // Waits for the oldest frame on the device and moves its results into a job, which frees the device library's
+    // slot.  async: the entropy stage starts on a worker thread; else it runs here.
+    evx_status retire(bool async)
     {
+        if (count_ >= max_jobs()) return EVX_ERROR_NOT_READY;
         pending_frame f = dev_[0];
         dev_[0] = dev_[1];
         dev_count_--;
+        job &j = jobs_[(head_ + count_) % kJobs];
         int rc;
         const double tw = now_ms();
-        retired_async_ = false;
         if (device_bins_)
         {
             const uint64_t *bins = NULL;
             rc = evxgpu_encode_collect_bins(gpu_, &bins, &f.nbins, &f.n_noncopy);
             if (rc) return EVX_ERROR_EXECUTION_FAILURE;
             const size_t words = (size_t) ((f.nbins + 63) / 64);
-            if (bins_.size() < words) bins_.resize(words + words / 2 + 64);
-            memcpy(bins_.data(), bins, words * 8);
+            if (j.bins.size() < words) j.bins.resize(words + words / 2 + 64);
+            memcpy(j.bins.data(), bins, words * 8);
         }
         else
         {
@@ -195,42 +236,41 @@ class encoder_session : public evx1_encoder
         f.d2h_bytes = (uint32) evxgpu_d2h_bytes(gpu_);
         f.gpu_ms = now_ms() - f.t_submit;
         f.wait_ms = now_ms() - tw;
-        retired_ = f;
-        if (async_coder && device_bins_ && coder_thread_)
+        j.f = f; j.bits = 0; j.ms = 0.0;
+        if (async && device_bins_ && coder_threads_)
         {
-            if (!coder_up_)
-            {
-                coder_stop_ = false; cstate_ = CODER_IDLE;
-                coder_ = std::thread(&encoder_session::coder_main, this);
-                coder_up_ = true;
-            }
-            { std::lock_guard<std::mutex> g(cm_); coder_nbins_ = f.nbins; cstate_ = CODER_WORK; }
-            ccv_.notify_all();
-            retired_async_ = true;
+            start_threads();
+            { std::lock_guard<std::mutex> g(m_); j.state = JOB_QUEUED; count_++; }
+            cv_work_.notify_one();
+        }
+        else
+        {
+            run_job(j);
+            std::lock_guard<std::mutex> g(m_);
+            j.state = JOB_DONE; count_++;
         }
         return EVX_SUCCESS;
     }
 
 public:
-    explicit encoder_session(const evx1_config &cfg) : cfg_(cfg), initialized_(false), gpu_(NULL), cstate_(CODER_IDLE), coder_up_(false), coder_stop_(false), retired_async_(false), coder_thread_(true), coder_nbins_(0), coder_bits_(0), coder_ms_(0.0)
+    explicit encoder_session(const evx1_config &cfg)
+        : cfg_(cfg), initialized_(false), gpu_(NULL), device_bins_(true), coder_threads_(true), dev_count_(0), head_(0), count_(0), threads_up_(false), stop_(false)
     {
         memset(&stats_, 0, sizeof(stats_));
         memset(&header_, 0, sizeof(header_));
         memset(dev_, 0, sizeof(dev_));
-        memset(&retired_, 0, sizeof(retired_));
-        dev_count_ = 0;
+        for (int k = 0; k < kJobs; ++k) jobs_[k].state = JOB_FREE;
         clear_frame();
     }
-    ~encoder_session() { clear(); coder_shutdown(); }
+    ~encoder_session() { clear(); stop_threads(); }
 
     evx_status clear()                                       // evx1enc.cpp:27-40
     {
-        if (coder_up_) coder_wait_idle();
-        retired_async_ = false;
+        drop_jobs();
         if (!initialized_) return EVX_SUCCESS;
         clear_frame();
-        if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }      // drains the stream; uncollected frames are dropped
-        dev_count_ = 0; retired_.valid = false;
+        if (gpu_) { evxgpu_destroy(gpu_); gpu_ = NULL; }      // drains the streams; uncollected frames are dropped
+        dev_count_ = 0;
         initialized_ = false;
         return EVX_SUCCESS;
     }
@@ -245,7 +285,7 @@ public:
     evx_status submit(void *image, uint32 width, uint32 height)
     {
         if (!width || !height || !image) return EVX_ERROR_INVALIDARG;
-        if (dev_count_ + (retired_.valid ? 1 : 0) > 2) return EVX_ERROR_NOT_READY;      // three frames uncollected
+        if (dev_count_ == 2 && count_ >= max_jobs()) return EVX_ERROR_NOT_READY;        // nowhere to retire the older frame to
         bool first = false;
         if (!initialized_)
         {
@@ -258,7 +298,7 @@ public:
         const uint8 *rgb = static_cast<const uint8 *>(image);
         if (dev_count_ == 2)
         {   // the device holds two frames: take the older one's results off it (it is finished or about to be); its
-            // arithmetic coder starts on the coder thread while this thread queues the new frame
+            // arithmetic coder starts on a worker thread while this thread queues the new frame
             evx_status st = retire(true);
             if (evx_failed(st)) return st;
         }
@@ -273,7 +313,6 @@ public:
             rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
             if (rc == 8)
             {
-                if (retired_.valid) return EVX_ERROR_NOT_READY;
                 evx_status st = retire(true);
                 if (evx_failed(st)) return st;
                 rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
@@ -296,44 +335,40 @@ public:
     evx_status collect(bit_stream *output)
     {
         if (!output) return EVX_ERROR_INVALIDARG;
-        if (!retired_.valid)
+        if (!count_)
         {
             if (!dev_count_) return EVX_ERROR_NOT_READY;
             evx_status st = retire(false);
             if (evx_failed(st)) return st;
         }
-        const pending_frame f = retired_;
-        retired_.valid = false;
-        // the slice first (whatever happens to the writes below, the coder thread is idle again afterwards)
-        const double t1 = now_ms();
-        uint32 bits;
-        double coder_ms = 0.0;
-        if (retired_async_)
-        {   // coded (or being coded) by the coder thread since submit() retired the frame
-            std::unique_lock<std::mutex> lk(cm_);
-            while (cstate_ != CODER_DONE) ccv_.wait(lk);
-            cstate_ = CODER_IDLE;
-            bits = coder_bits_; coder_ms = coder_ms_;
-            retired_async_ = false;
+        job &j = jobs_[head_];
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            while (j.state != JOB_DONE) cv_done_.wait(lk);
         }
-        else bits = device_bins_ ? writer_.serialize_bins(bins_.data(), f.nbins)
-                                 : writer_.serialize(table_.data(), records_.data(), f.n_noncopy);
-        if (f.first && evx_failed(output->write_bytes(&header_, sizeof(header_)))) return EVX_ERROR_EXECUTION_FAILURE;
+        const pending_frame f = j.f;
+        const uint32 bits = j.bits;
+        evx_status st = EVX_SUCCESS;
+        if (!bits) st = EVX_ERROR_EXECUTION_FAILURE;
+        if (evx_succeeded(st) && f.first && evx_failed(output->write_bytes(&header_, sizeof(header_)))) st = EVX_ERROR_EXECUTION_FAILURE;
         frame_desc desc = f.desc;
-        if (evx_failed(output->write_bytes(&desc, sizeof(desc)))) return EVX_ERROR_EXECUTION_FAILURE;
-        if (!bits) return EVX_ERROR_EXECUTION_FAILURE;
-        evx_status wst = output->write_bits(const_cast<uint8 *>(writer_.data()), bits);
-        stats_.gpu_ms = f.gpu_ms; stats_.entropy_ms = coder_ms > 0.0 ? coder_ms : now_ms() - t1; stats_.slice_bits = bits;
-        stats_.noncopy_blocks = f.n_noncopy; stats_.d2h_bytes = f.d2h_bytes; stats_.wait_ms = f.wait_ms;
+        if (evx_succeeded(st) && evx_failed(output->write_bytes(&desc, sizeof(desc)))) st = EVX_ERROR_EXECUTION_FAILURE;
         // serialize_slice's write failures are ignored by the reference; report ours
-        if (evx_failed(wst)) return EVX_ERROR_EXECUTION_FAILURE;
-        return EVX_SUCCESS;
+        if (evx_succeeded(st) && evx_failed(output->write_bits(const_cast<uint8 *>(device_bins_ ? j.writer.data() : writer_.data()), bits))) st = EVX_ERROR_EXECUTION_FAILURE;
+        stats_.gpu_ms = f.gpu_ms; stats_.entropy_ms = j.ms; stats_.slice_bits = bits;
+        stats_.noncopy_blocks = f.n_noncopy; stats_.d2h_bytes = f.d2h_bytes; stats_.wait_ms = f.wait_ms;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            j.state = JOB_FREE;
+            head_ = (head_ + 1) % kJobs; count_--;
+        }
+        return st;
     }
 
     evx_status encode(void *image, uint32 width, uint32 height, bit_stream *output)        // evx1enc.cpp:92-156
     {
         if (!output || !width || !height || !image) return EVX_ERROR_INVALIDARG;
-        if (dev_count_ || retired_.valid) return EVX_ERROR_NOT_READY;       // finish the pipelined frames with collect() first
+        if (dev_count_ || count_) return EVX_ERROR_NOT_READY;       // finish the pipelined frames with collect() first
         const frame_desc before = frame_;
         evx_status st = submit(image, width, height);
         if (evx_failed(st)) return st;
@@ -348,7 +383,7 @@ public:
     {
         if (!output) return EVX_ERROR_INVALIDARG;
         if (!initialized_) return EVX_SUCCESS;
-        if (dev_count_ || retired_.valid) return EVX_ERROR_NOT_READY;
+        if (dev_count_ || count_) return EVX_ERROR_NOT_READY;
         const uint32 w = header_.frame_width, h = header_.frame_height, mbw = (w + 15) / 16;
         uint8 *out = static_cast<uint8 *>(output);
         switch (peek_state)

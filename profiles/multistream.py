@@ -2,6 +2,8 @@
 stream each.  Aggregate P-frame throughput of (a) the pixel pipeline with device-resident frames,
 (b) the public API end to end (host frames -> bitstreams).  python profiles/multistream.py [S ...]"""
 import os, sys, threading, time
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+os.environ.setdefault('EVXGPU_FRAME_OVERLAP', '0')      # many streams: frame after frame within each (the library would let two of them overlap)
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import numpy as np
 import torch
