@@ -195,11 +195,13 @@ __device__ __forceinline__ void evx_load_src_lane(const EvxPlanes &srcp, const E
 {
     const uint32_t *y = reinterpret_cast<const uint32_t *>(srcp.y + (size_t) (py + (lane >> 3)) * g.w + px) + (lane & 7);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) b.w[k] = __ldg(y + (size_t) 4 * k * (g.w >> 1));
+    // (L2 loads throughout: with frames overlapping on the device these planes are written by kernels that run at the
+    // same time as the reader, which rules out the non-coherent path and a stale L1 line)
+    for (int k = 0; k < 4; ++k) b.w[k] = __ldcg(y + (size_t) 4 * k * (g.w >> 1));
     int cw = g.w >> 1;
     size_t off = (size_t) ((py >> 1) + (lane >> 2)) * cw + (px >> 1);
-    b.w[4] = __ldg(reinterpret_cast<const uint32_t *>(srcp.u + off) + (lane & 3));
-    b.w[5] = __ldg(reinterpret_cast<const uint32_t *>(srcp.v + off) + (lane & 3));
+    b.w[4] = __ldcg(reinterpret_cast<const uint32_t *>(srcp.u + off) + (lane & 3));
+    b.w[5] = __ldcg(reinterpret_cast<const uint32_t *>(srcp.v + off) + (lane & 3));
 }
 
 // the sequential search of one macroblock against one window (motion.cpp:254-275, 319-352, 421-494).
@@ -872,7 +874,7 @@ __global__ void __launch_bounds__(EVX_K5_THREADS) evx_decode_recon(const __grid_
 
 __device__ __forceinline__ void evx_edge_params(const EvxDesc *table, int ia, int ib, int &qp, int &strength)
 {
-    uint32_t a0 = __ldg(&table[ia].w0), a3 = __ldg(&table[ia].w3), b0 = __ldg(&table[ib].w0), b3 = __ldg(&table[ib].w3);
+    uint32_t a0 = __ldcg(&table[ia].w0), a3 = __ldcg(&table[ia].w3), b0 = __ldcg(&table[ib].w0), b3 = __ldcg(&table[ib].w3);
     bool ac = (a0 & EVX_T_COPY) != 0, bc = (b0 & EVX_T_COPY) != 0;
     int qa = (a3 >> 8) & 0xFF, qb = (b3 >> 8) & 0xFF;
     qp = (!ac && !bc) ? (qa + qb) >> 1 : (!ac ? qa : (!bc ? qb : 0));        // deblock.cpp:49-65
@@ -937,8 +939,8 @@ __global__ void __launch_bounds__(128) evx_deblock(const __grid_constant__ EvxK4
     {
         bool rv = r < 4 ? has_t : has_b;
         uint2 a = make_uint2(0, 0), b = make_uint2(0, 0);
-        if (rv && has_l) a = *reinterpret_cast<const uint2 *>(img + (size_t) (j - 4 + r) * w + i - 4);
-        if (rv && has_r) b = *reinterpret_cast<const uint2 *>(img + (size_t) (j - 4 + r) * w + i);
+        if (rv && has_l) a = __ldcg(reinterpret_cast<const uint2 *>(img + (size_t) (j - 4 + r) * w + i - 4));
+        if (rv && has_r) b = __ldcg(reinterpret_cast<const uint2 *>(img + (size_t) (j - 4 + r) * w + i));
         t[r][0] = evx_lo16(a.x); t[r][1] = evx_hi16(a.x); t[r][2] = evx_lo16(a.y); t[r][3] = evx_hi16(a.y);
         t[r][4] = evx_lo16(b.x); t[r][5] = evx_hi16(b.x); t[r][6] = evx_lo16(b.y); t[r][7] = evx_hi16(b.y);
     }

@@ -95,12 +95,12 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
         // source macroblock -> block-major
         {
             int row = lane >> 1, half = lane & 1;
-            uint4 v = __ldg(reinterpret_cast<const uint4 *>(p.src.y + (size_t) (py + row) * g.w + px + 8 * half));
+            uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p.src.y + (size_t) (py + row) * g.w + px + 8 * half));
             *reinterpret_cast<uint4 *>(&S.src[slot][((row >> 3) * 2 + half) * 64 + (row & 7) * 8]) = v;
             if (lane < 16)
             {
                 const int16_t *pl = lane < 8 ? p.src.u : p.src.v;
-                uint4 c = __ldg(reinterpret_cast<const uint4 *>(pl + (size_t) ((py >> 1) + (lane & 7)) * cw + (px >> 1)));
+                uint4 c = __ldcg(reinterpret_cast<const uint4 *>(pl + (size_t) ((py >> 1) + (lane & 7)) * cw + (px >> 1)));
                 *reinterpret_cast<uint4 *>(&S.src[slot][256 + (lane >> 3) * 64 + (lane & 7) * 8]) = c;
             }
         }
@@ -109,8 +109,8 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
         for (int r = 0; r < nref; ++r)
         {
             const EvxInterResult *ir = p.inter + (size_t) r * nmb + mb;
-            int4 raw = __ldg(reinterpret_cast<const int4 *>(&ir->desc));
-            int isad = __ldg(&ir->sad);
+            int4 raw = __ldcg(reinterpret_cast<const int4 *>(&ir->desc));
+            int isad = __ldcg(&ir->sad);
             if (lane == 0) { S.idesc[slot][r] = raw; S.isad[slot][r] = isad; }
             EvxDesc d; d.w0 = raw.x; d.w1 = raw.y; d.w2 = raw.z; d.w3 = raw.w;
             const int type = d.type();
@@ -130,14 +130,14 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
                 b[k] = 0;
                 if (comp == 0)
                 {
-                    a[k] = __ldg(ref.y + (size_t) (byp + y) * g.w + bxp + x);
-                    if (sp) b[k] = __ldg(ref.y + (size_t) (byp + dy + y) * g.w + bxp + dx + x);
+                    a[k] = __ldcg(ref.y + (size_t) (byp + y) * g.w + bxp + x);
+                    if (sp) b[k] = __ldcg(ref.y + (size_t) (byp + dy + y) * g.w + bxp + dx + x);
                 }
                 else
                 {
                     const int16_t *pl = comp == 1 ? ref.u : ref.v;
-                    a[k] = __ldg(pl + (size_t) ((byp >> 1) + y) * cw + (bxp >> 1) + x);
-                    if (sp) b[k] = __ldg(pl + (size_t) (((byp + dy) >> 1) + y) * cw + ((bxp + dx) >> 1) + x);
+                    a[k] = __ldcg(pl + (size_t) ((byp >> 1) + y) * cw + (bxp >> 1) + x);
+                    if (sp) b[k] = __ldcg(pl + (size_t) (((byp + dy) >> 1) + y) * cw + ((bxp + dx) >> 1) + x);
                 }
             }
 #pragma unroll

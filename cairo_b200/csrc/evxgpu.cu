@@ -52,6 +52,11 @@ static stream_memop_fn g_wait32 = NULL, g_write32 = NULL;
 #include <atomic>
 static std::atomic<int> g_overlap_live[64];
 enum { EVX_MAX_OVERLAP_ENCODERS = 2 };
+// Encoders (handles that have encoded a frame) alive per device, process-wide: a stream overlaps its frames only while it
+// is the only encoder on the device.  Next to other encoders' kernels the band kernels of an overlapped stream can wait
+// for SM space while the next frame's resident wavefront CTAs poll for them (measured: hangs and stale reads with five
+// more encoders hammering the device), and many streams fill the device without overlap anyway.
+static std::atomic<int> g_encoders_live[64];
 
 struct evxgpu_handle
 {
@@ -120,7 +125,9 @@ struct evxgpu_handle
     // Frame overlap (EVXGPU_FRAME_OVERLAP=1, bin-only output): the two frame slots own their per-frame device state and
     // three streams each, and consecutive frames of the stream run concurrently, gated row by row through counters in
     // device memory (stream memory operations on the host side, polls in the wavefront kernel).  See submit_overlap.
-    bool overlap;
+    bool overlap;                   // the machinery exists (slots, streams, counters)
+    bool overlap_on;                // and the frames in flight use it (decided whenever nothing is in flight)
+    bool is_encoder;                // counted in g_encoders_live
     struct frame_slot
     {
         int16_t *src_mem; EvxPlanes src;
@@ -181,6 +188,7 @@ void evxgpu_device_free(void *p) { if (p) cudaFree(p); }
 int evxgpu_destroy(evxgpu_handle *h)
 {
     if (!h) return 1;
+    if (h->is_encoder && h->device >= 0 && h->device < 64) { g_encoders_live[h->device].fetch_sub(1); h->is_encoder = false; }
     if (h->overlap)
     {   // back to slot 0's view (the original allocations); slot 1 and the extra streams go here
         sync_all(h);
@@ -612,10 +620,15 @@ static int enable_overlap(evxgpu_handle *h)
     ok = ok && cudaMalloc(&b.d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_flags, 2 * 4 * sizeof(unsigned int)) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&b.main, cudaStreamNonBlocking) == cudaSuccess;
+    // The band kernels run at the highest priority: the next frame's wavefront CTAs are resident and poll for what these
+    // kernels produce, so they must never queue behind the floods of small CTAs other streams launch (measured: with
+    // five more encoders on the device a whole-frame deblock at default priority could wait indefinitely).
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (int q = 0; q < 2 && ok; ++q)
     {
-        ok = ok && cudaStreamCreateWithFlags(&h->fs[q].k2s, cudaStreamNonBlocking) == cudaSuccess;
-        ok = ok && cudaStreamCreateWithFlags(&h->fs[q].k4s, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&h->fs[q].k2s, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&h->fs[q].k4s, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k1done, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k8done, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k4end, cudaEventDisableTiming) == cudaSuccess;
@@ -836,7 +849,23 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     if (h->q_count >= 2 || (h->q_count == 1 && !(h->out_mode == 1 && h->bins_cap_bits >= h->bins_worst_bits)))
         return fail(8, "evxgpu_encode_submit: previous frame not collected");
     CK(cudaSetDevice(h->device));
-    if (h->overlap && h->out_mode == 1 && !h->k2_tile) return submit_overlap(h, rgb, rgb_is_device, frame_type, frame_index, quality);
+    if (!h->is_encoder && h->device >= 0 && h->device < 64) { g_encoders_live[h->device].fetch_add(1); h->is_encoder = true; }
+    if (h->overlap && h->out_mode == 1 && !h->k2_tile)
+    {
+        if (h->q_count == 0)
+        {   // nothing in flight: the moment to switch between overlapped frames and frame after frame
+            const bool want = g_encoders_live[h->device].load() <= 1;
+            if (want != h->overlap_on)
+            {
+                int rc = sync_all(h);                    // drained (collected frames may still be deblocking)
+                if (rc) return rc;
+                use_slot(h, 0);
+                h->fs[0].used = h->fs[1].used = false;   // an overlapped frame that follows has no predecessor to wait for
+                h->overlap_on = want;
+            }
+        }
+        if (h->overlap_on) return submit_overlap(h, rgb, rgb_is_device, frame_type, frame_index, quality);
+    }
     const int q = (h->q_head + h->q_count) & 1;
     h->slot = q;
     if (h->timing) t_fold(h, q);                 // the frame that used this slot before was collected long ago
@@ -1073,6 +1102,18 @@ int evxgpu_debug_set_bins_capacity(evxgpu_handle *h, uint32_t bits)
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     return alloc_bins(h, bits & ~63u, bits & ~63u);
+}
+
+// debug: the frame-overlap counters ([slot][rows_done, final, k2, -]) and the epochs of the two slots, read over the copy
+// stream so that it works while the frame streams are busy (or stuck)
+int evxgpu_debug_overlap_state(evxgpu_handle *h, unsigned int *out10)
+{
+    if (!h || !out10 || !h->overlap) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(out10, h->d_flags, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaStreamSynchronize(h->copy_stream));
+    out10[8] = h->fs[0].epoch; out10[9] = h->fs[1].epoch;
+    return 0;
 }
 
 int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas)

@@ -144,6 +144,8 @@ uint64_t evxgpu_launch_count(const evxgpu_handle *h);
 uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h);
 /* debug: per-row phase cycle sums of the encoder wavefront kernel, 6 x int64 per macroblock row */
 int evxgpu_debug_profile(evxgpu_handle *h, int enable, long long *out_host);
+/* debug: frame-overlap row counters, out10 = { slot 0: rows done, deblocked bands, rows searched, -, slot 1: the same, epoch of slot 0, of slot 1 } */
+int evxgpu_debug_overlap_state(evxgpu_handle *h, unsigned int *out10);
 /* tuning knob: number of persistent CTAs of the decoder's wavefront kernel (0 = default) */
 int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas);
 /* tuning knob: persistent CTAs of the encoder's wavefront kernel (0 = default, ceil(mbw/3) + 4: the number of
