@@ -595,6 +595,9 @@ static int enable_overlap(evxgpu_handle *h)
 {
     if (h->overlap) return 0;
     if (!h->own_stream) return 0;                         // a caller's stream cannot be one of two
+    // Under a tool that serialises kernels (Nsight Compute replays one kernel at a time, compute-sanitizer likewise) a
+    // wavefront kernel polling for the band kernels of another stream would never see them run: frame after frame there.
+    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("CUDA_INJECTION64_PATH") || getenv("NSYS_PROFILING_SESSION_ID")) return 0;
     if (h->device < 0 || h->device >= 64) return 0;
     if (g_overlap_live[h->device].fetch_add(1) >= EVX_MAX_OVERLAP_ENCODERS) { g_overlap_live[h->device].fetch_sub(1); return 0; }
     if (!g_wait32)
