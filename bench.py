@@ -10,10 +10,12 @@ N>1); each rank encodes its own independent stream (no collective on the data pa
 reduces), so scaling is weak and `value` is the frames all ranks encoded / the slowest rank's
 device time.
 
-  value  : frames already resident in HBM -> pixel pipeline (K1..K4) -> records back on the host
-           (table + coefficient D2H inside the timed region, host entropy stage excluded).
-  e2e    : evx1_encoder::encode (the reference's public API, include/evx1_c.h) with HOST frames
-           in pinned memory -> EVX1 bitstream bytes: H2D, kernels, D2H and the host entropy stage.
+  value  : frames already resident in HBM -> pixel pipeline (K1 convert, K2 inter search, K3 wavefront, K8
+           binarisation, K4 deblocking) -> the slice's bin string on the host (its D2H inside the timed region,
+           host arithmetic coder excluded); two frames in flight, overlapping on the device row by row.
+  e2e    : evx1_encoder::submit/collect (the two halves of the reference's encode(), include/evx1_c.h) with HOST
+           frames in pinned memory -> EVX1 bitstream bytes: H2D, kernels, D2H and the host arithmetic coder;
+           e2e.synchronous is the same loop through evx1_encoder::encode, one frame at a time.
   --impl reference : the unmodified reference (oracle/_ref, built from /root/reference by
            oracle/Makefile) through the same public API on the host CPU.
 """
@@ -436,7 +438,9 @@ def run_ours(args):
                        "e2e_scope": "evx1_encoder::submit/collect (the two halves of encode, four frames of lookahead: two overlapping on the device, two on the coder threads), pinned host RGB -> EVX1 bitstream bytes: "
                                     "H2D, K1..K4 + device binarisation K8, D2H of the bin string, host arithmetic coder; all K bitstreams are on the host "
                                     "when the clock stops.  e2e.synchronous is the same through evx1_encoder::encode, one frame at a time",
-                       "l2": f"{uniq} distinct 6.2 MB frames ({uniq * frame_bytes // 1000000} MB) cycle through, larger than the 126 MB L2"},
+                       "l2": f"every timed step reads a different 6.2 MB input frame ({uniq} distinct frames, {uniq * frame_bytes // 1000000} MB, resident in HBM; "
+                             f"the sequence wraps only after 59 P-frames = 367 MB > 126 MB L2), so no input is served from a previous "
+                             f"step's L2 lines; the reference planes a P-frame reads are the previous step's output by construction"},
             "e2e": {"value": world * steps / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes,
                     "d2h_bytes_per_step": d2h_bytes // steps,
                     "synchronous": {"value": world * steps / (sync_ms_max * 1e-3), "unit": "frames/s", "api": "evx1_encoder::encode"},

@@ -412,9 +412,10 @@ __device__ __forceinline__ void evx_subpel_cost(const EvxLaneBlock &best, const 
 // ------------------------------------------------------------------ transform / quantiser tables
 
 // xftables.h:57-67: LUT[j*8+i] = round(128 cos((2i+1) j pi / 16)), from the 8 magnitudes
+__constant__ int16_t EVX_C16[9] = { 128, 126, 118, 106, 91, 71, 49, 25, 0 };     // (in constant memory: a local array indexed at run time lives on the stack)
 __device__ __forceinline__ int evx_dct_lut(int j, int i)
 {
-    const int c16[9] = { 128, 126, 118, 106, 91, 71, 49, 25, 0 };
+    const int16_t *c16 = EVX_C16;
     int k = ((2 * i + 1) * j) & 31;
     if (k <= 8) return c16[k];
     if (k <= 16) return -c16[16 - k];

@@ -52,6 +52,7 @@ static stream_memop_fn g_wait32 = NULL, g_write32 = NULL;
 #include <atomic>
 static std::atomic<int> g_overlap_live[64];
 enum { EVX_MAX_OVERLAP_ENCODERS = 2 };
+enum { EVX_MAX_SLOTS = 3 };           // frame slots a handle may own (two are in use unless EVXGPU_FRAME_SLOTS=3)
 // Encoders (handles that have encoded a frame) alive per device, process-wide: a stream overlaps its frames only while it
 // is the only encoder on the device.  Next to other encoders' kernels the band kernels of an overlapped stream can wait
 // for SM space while the next frame's resident wavefront CTAs poll for them (measured: hangs and stale reads with five
@@ -95,10 +96,10 @@ struct evxgpu_handle
     uint8_t *h_rgb;
 
     bool timing;
-    cudaEvent_t ev[2][EVXGPU_T_COUNT][2];   // [frame slot][kernel][begin, end]
-    bool ev_valid[2][EVXGPU_T_COUNT];
+    cudaEvent_t ev[EVX_MAX_SLOTS][EVXGPU_T_COUNT][2];   // [frame slot][kernel][begin, end]
+    bool ev_valid[EVX_MAX_SLOTS][EVXGPU_T_COUNT];
     double t_sum[EVXGPU_T_COUNT];   // accumulated kernel times of the frames since evxgpu_get_timing_sum(reset)
-    bool t_pending[2];              // the slot's events are not in t_sum yet
+    bool t_pending[EVX_MAX_SLOTS];  // the slot's events are not in t_sum yet
     int slot;                       // frame slot of the launches being queued / last queued
     uint64_t launches;
     bool pending_encode, pending_decode;
@@ -113,15 +114,15 @@ struct evxgpu_handle
     uint32_t *d_len, *d_tile_sum;
     // Two frame slots: in bin-only output mode a second frame may be queued behind the one in flight (its
     // kernels start the moment the first one's end, the host is still busy with the first one's bins).
-    uint32_t *d_bins[2], *d_bins_total[2];
+    uint32_t *d_bins[EVX_MAX_SLOTS], *d_bins_total[EVX_MAX_SLOTS];
     uint32_t bins_cap_bits;         // capacity of each d_bins
     uint32_t bins_worst_bits;       // no slice of this geometry can be longer (evx_bins.cuh)
-    uint32_t *h_bins[2];            // pinned: [0..3] total, overflow, non-copy count; [4..] the string
-    uint32_t h_bins_cap_bits[2];
-    uint32_t bins_prefix_bits[2];   // how much of the string the submit already copied
-    cudaEvent_t ev_out[2];
-    bool pending_bins[2];
-    uint64_t d2h_bytes[2];          // device-to-host bytes of the slot's frame
+    uint32_t *h_bins[EVX_MAX_SLOTS]; // pinned: [0..3] total, overflow, non-copy count; [4..] the string
+    uint32_t h_bins_cap_bits[EVX_MAX_SLOTS];
+    uint32_t bins_prefix_bits[EVX_MAX_SLOTS];   // how much of the string the submit already copied
+    cudaEvent_t ev_out[EVX_MAX_SLOTS];
+    bool pending_bins[EVX_MAX_SLOTS];
+    uint64_t d2h_bytes[EVX_MAX_SLOTS]; // device-to-host bytes of the slot's frame
     // Frame overlap (EVXGPU_FRAME_OVERLAP=1, bin-only output): the two frame slots own their per-frame device state and
     // three streams each, and consecutive frames of the stream run concurrently, gated row by row through counters in
     // device memory (stream memory operations on the host side, polls in the wavefront kernel).  See submit_overlap.
@@ -137,11 +138,12 @@ struct evxgpu_handle
         unsigned int epoch;             // of the frame last submitted into the slot
         int B, NB;                      // its banding: rows per band, bands (the unit of its `final` counter)
         bool used;
-    } fs[2];
+    } fs[EVX_MAX_SLOTS];
+    int nslots;                     // frame slots in use: 2, or 3 with frame overlap (EVXGPU_FRAME_SLOTS)
     unsigned int *d_flags;          // [slot][3]: rows_done, final (deblocked bands), k2 rows done; value = epoch + count
     unsigned int frame_seq, epoch_limit;
     int band_rows, nbands;
-    int q_head, q_count;            // queue of submitted, uncollected frames: slots q_head, q_head ^ 1
+    int q_head, q_count;            // queue of submitted, uncollected frames: slots q_head, q_head + 1, ... (mod nslots)
     int last_slot;                  // slot of the last collected frame (evxgpu_d2h_bytes)
     uint32_t bins_last_total;       // bin count of the previous frame (sizes the optimistic head copy)
 };
@@ -319,7 +321,8 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
         if (e == cudaSuccess) e = cudaFuncSetAttribute(evx_inter_search, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         { const char *k2 = getenv("EVXGPU_K2"); h->k2_tile = k2 && !strcmp(k2, "tile"); }
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_inter_search)", e); }
-        e = cudaFuncSetAttribute(evx_wavefront, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EvxK3Smem));
+        e = cudaFuncSetAttribute(evx_wavefront<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EvxK3Smem));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(evx_wavefront<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EvxK3Smem));
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_wavefront)", e); }
     }
     for (int k = 0; k < EVXGPU_T_COUNT; ++k)
@@ -507,7 +510,11 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
     CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
     t_begin(h, EVXGPU_T_WAVEFRONT);
     // one CTA per macroblock row in flight; rows are claimed by ticket, so any residency is deadlock-free
-    evx_wavefront<<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), h->stream>>>(p);
+    // the only encoder on the device runs the kernel with the larger register budget (evx_wavefront.cuh)
+    if (h->device >= 0 && h->device < 64 && g_encoders_live[h->device].load() <= 1 && !getenv("EVXGPU_K3_NARROW"))
+        evx_wavefront<1><<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), h->stream>>>(p);
+    else
+        evx_wavefront<2><<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), h->stream>>>(p);
     h->launches++;
     if (h->out_mode != 1)
     {
@@ -741,7 +748,9 @@ static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_devic
         kp.gate_final = have_prev ? flp + FLAG_FINAL : NULL; kp.gate_final_base = Ep;
         kp.band_rows = Bp; kp.nbands = NBp;          // units of the previous frame's `final` counter
         CK(cudaMemsetAsync(f.d_sync, 0, (size_t) (mbh + 2) * 4, f.main));
-        evx_wavefront<<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), f.main>>>(kp);
+        // (frames overlap only while this is the device's only encoder: the larger register budget, evx_wavefront.cuh)
+        if (!getenv("EVXGPU_K3_NARROW")) evx_wavefront<1><<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), f.main>>>(kp);
+        else evx_wavefront<2><<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), f.main>>>(kp);
         h->launches++;
         CK(cudaGetLastError());
     }
