@@ -36,6 +36,15 @@
 #define EVX_K3_CPW (8 / EVX_K3_CW)  // search cells (and sub-pel directions) per compute warp
 #define EVX_K3_CT (EVX_K3_CW * 32)
 #define EVX_K3_NT (EVX_K3_CT + 64)
+// The 384 elements of a macroblock over the compute threads.  Written as a fully unrolled outer loop around an inner
+// loop that runs at most once, so that with 256 threads the two passes (the second one only for threads < 128) sit in one
+// basic block and their loads overlap; -DEVX_K3_ROLLED384 keeps the plain strided loop for A/B runs.
+#ifdef EVX_K3_ROLLED384
+#define EVX_K3_FOR384(e) for (int e = tid; e < 384; e += EVX_K3_CT)
+#else
+#define EVX_K3_FOR384(e) _Pragma("unroll") for (int e##_it = 0; e##_it < (384 + EVX_K3_CT - 1) / EVX_K3_CT; ++e##_it) \
+                         for (int e = tid + e##_it * EVX_K3_CT; e < 384; e += 384)
+#endif
 #define EVX_K3_ROWS 80            // window rows py-48 .. py+31
 #define EVX_K3_CROWS 40
 #define EVX_MAXREF 7
@@ -455,7 +464,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 const bool sp = d.sp_pred() != 0;
                 int dx = 0, dy = 0;
                 if (sp) evx_frac_direction(d.sp_index(), dx, dy);
-                for (int e = tid; e < 384; e += EVX_K3_CT)
+                EVX_K3_FOR384(e)
                 {
                     int comp, x, y, a, b = 0;
                     evx_mb_pos(e, comp, x, y);
@@ -475,7 +484,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             }
             else
             {
-                for (int e = tid; e < 384; e += EVX_K3_CT) sh.pred[e] = S.ipred[slot][best_ref][e];
+                EVX_K3_FOR384(e) sh.pred[e] = S.ipred[slot][best_ref][e];
             }
         }
         evx_compute_sync();
@@ -505,7 +514,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
 
         if (type & EVX_T_COPY)
         {   // copy blocks: the prediction is the reconstruction; no coefficients (encode.cpp:155-157)
-            for (int e = tid; e < 384; e += EVX_K3_CT) store_recon(e, sh.pred[e]);
+            EVX_K3_FOR384(e) store_recon(e, sh.pred[e]);
             if (tid == 0) { p.table[mb] = d; p.prev_motion[mb] = S.last_motion; p.prev_coded[mb] = S.last_coded; }
         }
         else
@@ -521,7 +530,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 x[4] = evx_lo16(v.z); x[5] = evx_hi16(v.z); x[6] = evx_lo16(v.w); x[7] = evx_hi16(v.w);
             };
             // residual (int16, transform.cpp:29-32) and row pass (transform.cpp:264-301); result stored transposed
-            for (int e = tid; e < 384; e += EVX_K3_CT)
+            EVX_K3_FOR384(e)
             {
                 const int base = e & ~7;
                 uint4 sv = *reinterpret_cast<const uint4 *>(srcb + base);
@@ -540,7 +549,8 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             }
             evx_compute_sync();
             // column pass: thread e -> (block b, column a, output row i = e & 7); column a is contiguous in bufb
-            for (int e = tid; e < 384; e += EVX_K3_CT)
+            uint32_t vsum = 0, vsq = 0; int vcnt = 0;
+            EVX_K3_FOR384(e)
             {
                 const int b = e >> 6, a = (e >> 3) & 7, i = e & 7;
                 int x[8];
@@ -549,8 +559,22 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
 #pragma unroll
                 for (int k = 0; k < 8; ++k) t += x[k] * lut_f[k];
                 t = i == 0 ? evx_tdiv_pow2(t * 45, 7) : evx_tdiv_pow2(t, 1);
-                sh.bufa[b * 64 + i * 8 + a] = (int16_t) evx_rdiv_pow2(t, 7);
+                const int16_t c16 = (int16_t) evx_rdiv_pow2(t, 7);
+                sh.bufa[b * 64 + i * 8 + a] = c16;
+#ifndef EVX_K3_VAR_PASS
+                // compute_block_variance2 over the 16x16 luma coefficients except (0,0) (analysis.h:176-198): the sums are
+                // taken here, from the value each thread just produced (uint32 sums: any order gives the same bits)
+                if (b < 4 && (b | i | a) != 0 && c16 != 0) { vsum += (uint32_t) (int) c16; vsq += (uint32_t) ((int) c16 * (int) c16); vcnt++; }
+#endif
             }
+#ifndef EVX_K3_VAR_PASS
+            {
+                const uint32_t sum = __reduce_add_sync(0xFFFFFFFFu, vsum), sq = __reduce_add_sync(0xFFFFFFFFu, vsq);
+                const int cnt = __reduce_add_sync(0xFFFFFFFFu, vcnt);
+                if (lane == 0) { sh.red[warp] = (int) sum; sh.red[32 + warp] = (int) sq; sh.red[64 + warp] = cnt; }
+            }
+            evx_compute_sync();
+#else
             evx_compute_sync();
             // compute_block_variance2 over the 16x16 luma coefficients except (0,0) (analysis.h:176-198)
             {
@@ -560,6 +584,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 if (lane == 0) { sh.red[warp] = (int) sum; sh.red[32 + warp] = (int) sq; sh.red[64 + warp] = cnt; }
                 evx_compute_sync();
             }
+#endif
             int qp, var = 0;
             {
                 uint32_t Ssum = 0, Q = 0; int C = 0;
@@ -576,7 +601,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             const bool intra_q = (type & EVX_T_INTRA) && !(type & EVX_T_MOTION);
             int16_t *rec = p.records + (size_t) mb * 384;
             // quantise (quantize.cpp:79-180), hand the record out, dequantise (quantize.cpp:182-243)
-            for (int e = tid; e < 384; e += EVX_K3_CT)
+            EVX_K3_FOR384(e)
             {
                 const int mode = intra_q ? ((e >> 6) < 4 ? 0 : 1) : 2;
                 const int qv = evx_quant_fast(sh.bufa[e], e & 63, mode, qp, p.linear, sh.qmi, sh.qmt, sh.recip);
@@ -586,7 +611,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             if (tid == 0) { d.set_q(qp, var); p.table[mb] = d; p.prev_motion[mb] = S.last_motion; p.prev_coded[mb] = S.last_coded; S.last_coded = mb; }
             evx_compute_sync();
             // inverse transform (transform.cpp:330-366, 418-433): columns, then rows + prediction
-            for (int e = tid; e < 384; e += EVX_K3_CT)
+            EVX_K3_FOR384(e)
             {
                 const int b = e >> 6, j = (e >> 3) & 7;      // column j (contiguous in bufb), output row i = e & 7
                 int x[8];
@@ -597,7 +622,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 sh.bufa[b * 64 + (e & 7) * 8 + j] = (int16_t) evx_rdiv_pow2(t, 7);
             }
             evx_compute_sync();
-            for (int e = tid; e < 384; e += EVX_K3_CT)
+            EVX_K3_FOR384(e)
             {
                 int x[8];                                    // row (e>>3), output column i = e & 7
                 unpack8(*reinterpret_cast<const uint4 *>(sh.bufa + (e & ~7)), x);
