@@ -12,7 +12,7 @@ device time.
 
   value  : frames already resident in HBM -> pixel pipeline (K1 convert, K2 inter search, K3 wavefront, K8
            binarisation, K4 deblocking) -> the slice's bin string on the host (its D2H inside the timed region,
-           host arithmetic coder excluded); two frames in flight, overlapping on the device row by row.
+           host arithmetic coder excluded); three frames in flight, overlapping on the device row by row.
   e2e    : evx1_encoder::submit/collect (the two halves of the reference's encode(), include/evx1_c.h) with HOST
            frames in pinned memory -> EVX1 bitstream bytes: H2D, kernels, D2H and the host arithmetic coder;
            e2e.synchronous is the same loop through evx1_encoder::encode, one frame at a time.
@@ -295,14 +295,18 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     value_d2h = 0
-    # frame t+1 is queued behind frame t before frame t's bins are collected: the device never waits for the host
-    pipe.encode_submit(int(dev[fidx(warmup)].data_ptr()), 1, warmup, QUALITY)
-    for t in range(warmup + 1, nframes):
+    # the frames the handle holds (two, or three frame slots) are queued before the oldest one's bins are collected: the
+    # device never waits for the host
+    ahead = min(pipe.encode_capacity() - 1, steps - 1)
+    for t in range(warmup, warmup + ahead):
+        pipe.encode_submit(int(dev[fidx(t)].data_ptr()), 1, t, QUALITY)
+    for t in range(warmup + ahead, nframes):
         pipe.encode_submit(int(dev[fidx(t)].data_ptr()), 1, t, QUALITY)
         pipe.encode_collect_bins()
         value_d2h += pipe.d2h_bytes()
-    pipe.encode_collect_bins()
-    value_d2h += pipe.d2h_bytes()
+    for _ in range(ahead):
+        pipe.encode_collect_bins()
+        value_d2h += pipe.d2h_bytes()
     e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)
@@ -339,9 +343,9 @@ def run_ours(args):
     coded = []                                   # the K frames' bitstreams (a few KB each), for the decode extra
     barrier()
     t0 = time.perf_counter()
-    # four frames of lookahead: while frame t is handed over, frames t-1 and t-2 overlap on the device and frames t-3
-    # and t-4 are being entropy-coded on the session's coder threads; collect() returns them in order
-    look = min(4, steps)
+    # six frames of lookahead: while frame t is handed over, three earlier frames overlap on the device (three frame
+    # slots) and the ones before them are being entropy-coded on the session's coder threads; collect() returns them in order
+    look = min(int(os.environ.get("EVX_BENCH_LOOKAHEAD", "6")), steps)
     for t in range(warmup, warmup + look):
         enc.submit((int(host[fidx(t)].data_ptr()), W, H))
     for t in range(warmup + look, nframes):
@@ -431,11 +435,11 @@ def run_ours(args):
             "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16/int32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "value_scope": "frames resident in HBM -> K1 convert, K2 inter search, K3 wavefront, K8 binarisation, K4 deblocking -> the slice's bin string "
-                                      "on the host (D2H inside the timed region, %d bytes per frame); host arithmetic coder excluded; two frames in "
-                                      "flight, consecutive frames overlap on the device row by row; kernel_ms_per_step and the roofline are from a "
+                                      "on the host (D2H inside the timed region, %d bytes per frame); host arithmetic coder excluded; up to three frames in "
+                                      "flight (three frame slots), consecutive frames overlap on the device row by row; kernel_ms_per_step and the roofline are from a "
                                       "separate pass with the frames one after the other (a kernel's duration next to another frame's kernels is "
                                       "not its own)" % (value_d2h // max(1, steps)),
-                       "e2e_scope": "evx1_encoder::submit/collect (the two halves of encode, four frames of lookahead: two overlapping on the device, two on the coder threads), pinned host RGB -> EVX1 bitstream bytes: "
+                       "e2e_scope": "evx1_encoder::submit/collect (the two halves of encode, six frames of lookahead: three overlapping on the device, the rest on the coder threads), pinned host RGB -> EVX1 bitstream bytes: "
                                     "H2D, K1..K4 + device binarisation K8, D2H of the bin string, host arithmetic coder; all K bitstreams are on the host "
                                     "when the clock stops.  e2e.synchronous is the same through evx1_encoder::encode, one frame at a time",
                        "l2": f"every timed step reads a different 6.2 MB input frame ({uniq} distinct frames, {uniq * frame_bytes // 1000000} MB, resident in HBM; "

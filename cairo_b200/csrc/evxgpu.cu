@@ -52,7 +52,7 @@ static stream_memop_fn g_wait32 = NULL, g_write32 = NULL;
 #include <atomic>
 static std::atomic<int> g_overlap_live[64];
 enum { EVX_MAX_OVERLAP_ENCODERS = 2 };
-enum { EVX_MAX_SLOTS = 3 };           // frame slots a handle may own (two are in use unless EVXGPU_FRAME_SLOTS=3)
+enum { EVX_MAX_SLOTS = 3, EVX_DEFAULT_SLOTS = 3 };           // frame slots a handle may own (two are in use unless EVXGPU_FRAME_SLOTS=3)
 // Encoders (handles that have encoded a frame) alive per device, process-wide: a stream overlaps its frames only while it
 // is the only encoder on the device.  Next to other encoders' kernels the band kernels of an overlapped stream can wait
 // for SM space while the next frame's resident wavefront CTAs poll for them (measured: hangs and stale reads with five
@@ -195,11 +195,14 @@ int evxgpu_destroy(evxgpu_handle *h)
     {   // back to slot 0's view (the original allocations); slot 1 and the extra streams go here
         sync_all(h);
         use_slot(h, 0);
-        evxgpu_handle::frame_slot &b = h->fs[1];
-        cudaFree(b.src_mem); cudaFree(b.d_table); cudaFree(b.d_inter); cudaFree(b.d_records); cudaFree(b.d_row_records); cudaFree(b.d_prev); cudaFree(b.d_sync);
+        for (int q = 1; q < EVX_MAX_SLOTS; ++q)
+        {
+            evxgpu_handle::frame_slot &b = h->fs[q];
+            cudaFree(b.src_mem); cudaFree(b.d_table); cudaFree(b.d_inter); cudaFree(b.d_records); cudaFree(b.d_row_records); cudaFree(b.d_prev); cudaFree(b.d_sync);
+            if (b.main) cudaStreamDestroy(b.main);
+        }
         cudaFree(h->d_flags);
-        if (b.main) cudaStreamDestroy(b.main);
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < EVX_MAX_SLOTS; ++q)
         {
             if (h->fs[q].k2s) cudaStreamDestroy(h->fs[q].k2s);
             if (h->fs[q].k4s) cudaStreamDestroy(h->fs[q].k4s);
@@ -222,9 +225,9 @@ int evxgpu_destroy(evxgpu_handle *h)
     cudaFree(h->d_rgb); cudaFree(h->d_table); cudaFree(h->d_inter); cudaFree(h->d_records); cudaFree(h->d_dense); cudaFree(h->d_row_records);
     cudaFree(h->d_record_slot); cudaFree(h->d_sync); cudaFree(h->d_done); cudaFree(h->d_counters); cudaFree(h->d_prof);
     cudaFree(h->d_dc); cudaFree(h->d_prev); cudaFree(h->d_len); cudaFree(h->d_tile_sum);
-    for (int q = 0; q < 2; ++q) { cudaFree(h->d_bins[q]); cudaFree(h->d_bins_total[q]); cudaFreeHost(h->h_bins[q]); if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]); }
+    for (int q = 0; q < EVX_MAX_SLOTS; ++q) { cudaFree(h->d_bins[q]); cudaFree(h->d_bins_total[q]); cudaFreeHost(h->h_bins[q]); if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]); }
     cudaFreeHost(h->h_table); cudaFreeHost(h->h_records); cudaFreeHost(h->h_record_slot); cudaFreeHost(h->h_sync); cudaFreeHost(h->h_rgb);
-    for (int q = 0; q < 2; ++q) for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[q][k][e]) cudaEventDestroy(h->ev[q][k][e]);
+    for (int q = 0; q < EVX_MAX_SLOTS; ++q) for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[q][k][e]) cudaEventDestroy(h->ev[q][k][e]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -242,6 +245,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     if (!h) return fail(3, "evxgpu_create: out of host memory");
     memset(h, 0, sizeof(*h));
     h->device = device;
+    h->nslots = 2;
     h->cfg = *cfg;
     h->g.vw = width; h->g.vh = height;
     h->g.w = (width + 15) & ~15; h->g.h = (height + 15) & ~15;          // evx1enc.cpp:79-80
@@ -287,7 +291,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
         ok = ok && cudaMalloc(&h->d_prev, ((size_t) h->nmb * 2 + (size_t) h->g.mbh * 2) * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&h->d_len, (size_t) EVX_BINS_ITEMS * h->nmb * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&h->d_tile_sum, ntiles * 4) == cudaSuccess;
-        for (int q = 0; q < 2; ++q) ok = ok && cudaEventCreateWithFlags(&h->ev_out[q], cudaEventDisableTiming) == cudaSuccess;
+        for (int q = 0; q < EVX_MAX_SLOTS; ++q) ok = ok && cudaEventCreateWithFlags(&h->ev_out[q], cudaEventDisableTiming) == cudaSuccess;
     }
     ok = ok && cudaHostAlloc(&h->h_table, (size_t) h->nmb * 16, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&h->h_records, (size_t) h->nmb * 384 * 2, cudaHostAllocDefault) == cudaSuccess;
@@ -327,7 +331,8 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     }
     for (int k = 0; k < EVXGPU_T_COUNT; ++k)
         for (int e = 0; e < 2; ++e)
-            if (cudaEventCreate(&h->ev[0][k][e]) != cudaSuccess || cudaEventCreate(&h->ev[1][k][e]) != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaEventCreate"); }
+            for (int q = 0; q < EVX_MAX_SLOTS; ++q)
+                if (cudaEventCreate(&h->ev[q][k][e]) != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaEventCreate"); }
     // enough CTAs to cover the widest wavefront plus a few to prefetch the next step
     h->wave_grid = std::min(h->nmb, 148 * 8);      // persistent CTAs of the decoder kernel
     // encoder wavefront: at most ceil(W/3) rows are ever active at once (row r runs during steps [3r, 3r+W));
@@ -348,13 +353,13 @@ int evxgpu_reset(evxgpu_handle *h)
     {
         int rc = sync_all(h);
         if (rc) return rc;
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < h->nslots; ++q)
         {
             CK(cudaMemset(h->fs[q].src_mem, 0, plane_elems(h->g) * 2));
             CK(cudaMemset(h->fs[q].d_table, 0, (size_t) h->nmb * 16));
             h->fs[q].used = false; h->fs[q].epoch = 0;
         }
-        CK(cudaMemset(h->d_flags, 0, 2 * 4 * sizeof(unsigned int)));
+        CK(cudaMemset(h->d_flags, 0, EVX_MAX_SLOTS * 4 * sizeof(unsigned int)));
         h->frame_seq = 0;
     }
     const size_t pe = plane_elems(h->g);
@@ -364,7 +369,8 @@ int evxgpu_reset(evxgpu_handle *h)
     CK(cudaMemsetAsync(h->d_counters, 0, 32, h->stream));
     CK(cudaMemsetAsync(h->d_dc, 0, (size_t) h->nmb * 4 * 2, h->stream));
     CK(cudaStreamSynchronize(h->stream));
-    h->pending_encode = h->pending_decode = h->pending_bins[0] = h->pending_bins[1] = false;
+    h->pending_encode = h->pending_decode = false;
+    for (int q = 0; q < EVX_MAX_SLOTS; ++q) h->pending_bins[q] = false;
     h->q_head = h->q_count = 0; h->uploaded = false;
     return 0;
 }
@@ -408,7 +414,7 @@ int evxgpu_get_timing_sum(evxgpu_handle *h, double *ms_out, int reset)
 {
     if (!h || !ms_out) return 1;
     CK(cudaSetDevice(h->device));
-    t_fold(h, 0); t_fold(h, 1);
+    for (int q = 0; q < EVX_MAX_SLOTS; ++q) t_fold(h, q);
     for (int k = 0; k < EVXGPU_T_COUNT; ++k) { ms_out[k] = h->t_sum[k]; if (reset) h->t_sum[k] = 0.0; }
     return 0;
 }
@@ -589,7 +595,7 @@ static void use_slot(evxgpu_handle *h, int q)
 static int sync_all(evxgpu_handle *h)
 {
     if (h->overlap)
-        for (int q = 0; q < 2; ++q)
+        for (int q = 0; q < h->nslots; ++q)
         {
             CK(cudaStreamSynchronize(h->fs[q].main)); CK(cudaStreamSynchronize(h->fs[q].k2s)); CK(cudaStreamSynchronize(h->fs[q].k4s));
         }
@@ -617,25 +623,33 @@ static int enable_overlap(evxgpu_handle *h)
     }
     CK(cudaStreamSynchronize(h->stream));
     const size_t pe = plane_elems(h->g);
-    evxgpu_handle::frame_slot &a = h->fs[0], &b = h->fs[1];
+    // Frame slots: two, or three with EVXGPU_FRAME_SLOTS=3 -- a frame may start once its predecessor is about nine
+    // macroblock rows ahead, so with two slots it is the slot, not the data, a third frame waits for.
+    int ns = EVX_DEFAULT_SLOTS;
+    if (const char *e = getenv("EVXGPU_FRAME_SLOTS")) { int v = atoi(e); if (v >= 2 && v <= EVX_MAX_SLOTS) ns = v; }
+    evxgpu_handle::frame_slot &a = h->fs[0];
     a.src_mem = h->src_mem; a.src = h->src; a.d_table = h->d_table; a.d_inter = h->d_inter; a.d_records = h->d_records;
     a.d_row_records = h->d_row_records; a.d_prev = h->d_prev; a.d_sync = h->d_sync; a.main = h->stream;
     bool ok = true;
-    ok = ok && cudaMalloc(&b.src_mem, pe * 2) == cudaSuccess;
-    ok = ok && cudaMalloc(&b.d_table, (size_t) h->nmb * 16) == cudaSuccess;
-    ok = ok && cudaMalloc(&b.d_inter, (size_t) h->nmb * (h->cfg.ref_count - 1) * sizeof(EvxInterResult)) == cudaSuccess;
-    ok = ok && cudaMalloc(&b.d_records, (size_t) h->nmb * 384 * 2) == cudaSuccess;
-    ok = ok && cudaMalloc(&b.d_row_records, (size_t) h->g.mbh * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&b.d_prev, ((size_t) h->nmb * 2 + (size_t) h->g.mbh * 2) * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&b.d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&h->d_flags, 2 * 4 * sizeof(unsigned int)) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&b.main, cudaStreamNonBlocking) == cudaSuccess;
+    for (int q = 1; q < ns; ++q)
+    {
+        evxgpu_handle::frame_slot &b = h->fs[q];
+        ok = ok && cudaMalloc(&b.src_mem, pe * 2) == cudaSuccess;
+        ok = ok && cudaMalloc(&b.d_table, (size_t) h->nmb * 16) == cudaSuccess;
+        ok = ok && cudaMalloc(&b.d_inter, (size_t) h->nmb * (h->cfg.ref_count - 1) * sizeof(EvxInterResult)) == cudaSuccess;
+        ok = ok && cudaMalloc(&b.d_records, (size_t) h->nmb * 384 * 2) == cudaSuccess;
+        ok = ok && cudaMalloc(&b.d_row_records, (size_t) h->g.mbh * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&b.d_prev, ((size_t) h->nmb * 2 + (size_t) h->g.mbh * 2) * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&b.d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&b.main, cudaStreamNonBlocking) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&h->d_flags, EVX_MAX_SLOTS * 4 * sizeof(unsigned int)) == cudaSuccess;
     // The band kernels run at the highest priority: the next frame's wavefront CTAs are resident and poll for what these
     // kernels produce, so they must never queue behind the floods of small CTAs other streams launch (measured: with
     // five more encoders on the device a whole-frame deblock at default priority could wait indefinitely).
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    for (int q = 0; q < 2 && ok; ++q)
+    for (int q = 0; q < ns && ok; ++q)
     {
         ok = ok && cudaStreamCreateWithPriority(&h->fs[q].k2s, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
         ok = ok && cudaStreamCreateWithPriority(&h->fs[q].k4s, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
@@ -646,11 +660,19 @@ static int enable_overlap(evxgpu_handle *h)
         h->fs[q].epoch = 0; h->fs[q].used = false;
     }
     if (!ok) { g_overlap_live[h->device].fetch_sub(1); return fail(3, "frame overlap: out of device memory"); }
-    set_planes(b.src, b.src_mem, h->g);
-    CK(cudaMemset(b.src_mem, 0, pe * 2));                 // padding rows/columns stay zero
-    CK(cudaMemset(b.d_table, 0, (size_t) h->nmb * 16));
-    CK(cudaMemset(h->d_flags, 0, 2 * 4 * sizeof(unsigned int)));
-    int br = 6;          // measured at 1080p: 3 rows 857, 4 rows 882, 6 rows 889, 8 rows 889 frames/s (each band costs three driver calls twice)
+    for (int q = 1; q < ns; ++q)
+    {
+        evxgpu_handle::frame_slot &b = h->fs[q];
+        set_planes(b.src, b.src_mem, h->g);
+        CK(cudaMemset(b.src_mem, 0, pe * 2));             // padding rows/columns stay zero
+        CK(cudaMemset(b.d_table, 0, (size_t) h->nmb * 16));
+    }
+    CK(cudaMemset(h->d_flags, 0, EVX_MAX_SLOTS * 4 * sizeof(unsigned int)));
+    h->nslots = ns;
+    // Band size, measured at 1080p.  Two slots: 3 rows 857, 4 rows 882, 6 rows 889, 8 rows 889 frames/s (each band costs three
+    // driver calls twice, and with two slots the slot, not the distance, is what the next frame waits for).  Three slots:
+    // 6 rows 1151, 4 rows 1223, 3 rows 1254 frames/s -- the distance to the previous frame is the limit, and it shrinks with the band.
+    int br = ns >= 3 ? 3 : 6;
     if (const char *e = getenv("EVXGPU_BAND_ROWS")) { int v = atoi(e); if (v >= 3) br = v; }
     h->band_rows = br; h->nbands = (h->g.mbh + br - 1) / br;
     h->frame_seq = 0;
@@ -669,14 +691,15 @@ static int enable_overlap(evxgpu_handle *h)
 // (no kernel occupies the device while it waits), the wavefront kernel polls them.
 static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device, int frame_type, uint32_t frame_index, int quality)
 {
-    const int q = (h->q_head + h->q_count) & 1, p = q ^ 1;
+    const int ns = h->nslots, q = (h->q_head + h->q_count) % ns, p = (q + ns - 1) % ns;
     if (h->frame_seq >= h->epoch_limit)
     {   // the epochs restart when nothing is in flight
         if (h->q_count) return fail(8, "evxgpu_encode_submit: epoch wrap, collect the frame in flight first");
         int rc = sync_all(h);
         if (rc) return rc;
-        CK(cudaMemset(h->d_flags, 0, 2 * 4 * sizeof(unsigned int)));
-        h->frame_seq = 0; h->fs[0].used = h->fs[1].used = false;
+        CK(cudaMemset(h->d_flags, 0, EVX_MAX_SLOTS * 4 * sizeof(unsigned int)));
+        h->frame_seq = 0;
+        for (int k = 0; k < EVX_MAX_SLOTS; ++k) h->fs[k].used = false;
     }
     use_slot(h, q);
     evxgpu_handle::frame_slot &f = h->fs[q], &pv = h->fs[p];
@@ -803,7 +826,7 @@ static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_devic
 // (re)allocates the two slots' string buffers: device capacity cap_bits each, pinned host capacity hcap_bits each
 static int alloc_bins(evxgpu_handle *h, uint32_t cap_bits, uint32_t hcap_bits)
 {
-    for (int q = 0; q < 2; ++q)
+    for (int q = 0; q < EVX_MAX_SLOTS; ++q)
     {
         cudaFree(h->d_bins[q]); h->d_bins[q] = NULL;
         cudaFreeHost(h->h_bins[q]); h->h_bins[q] = NULL;
@@ -840,6 +863,20 @@ int evxgpu_set_output(evxgpu_handle *h, int mode)
     return 0;
 }
 
+int evxgpu_encode_capacity(const evxgpu_handle *h)
+{
+    if (!h) return 0;
+    if (h->out_mode != 1 || h->bins_cap_bits < h->bins_worst_bits) return 1;
+    if (!h->overlap || h->k2_tile) return 2;
+    if (h->q_count == 0)
+    {   // the next submit decides whether frames overlap: only while this is the device's only encoder
+        const int live = (h->device >= 0 && h->device < 64 ? g_encoders_live[h->device].load() : 2) + (h->is_encoder ? 0 : 1);
+        return live <= 1 ? h->nslots : 2;
+    }
+    if (!h->overlap_on) return 2;
+    return h->frame_seq >= h->epoch_limit ? 0 : h->nslots;      // 0: the overlap epochs restart, which needs the device drained
+}
+
 int evxgpu_encode_upload(evxgpu_handle *h, const uint8_t *rgb_host)
 {
     if (!h || !rgb_host) return fail(1, "evxgpu_encode_upload: bad argument");
@@ -858,7 +895,9 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     if (h && !rgb && h->uploaded) { rgb = h->d_rgb_up; rgb_is_device = 2; }
     if (!h || !rgb || quality < 1 || quality > 31 || (frame_type != 0 && frame_type != 1)) return fail(1, "evxgpu_encode_submit: bad argument");
     // one frame in flight -- or, with bin-only output and string buffers that cannot overflow, a second one queued behind it
-    if (h->q_count >= 2 || (h->q_count == 1 && !(h->out_mode == 1 && h->bins_cap_bits >= h->bins_worst_bits)))
+    // (or, while consecutive frames overlap on the device, as many as there are frame slots)
+    const int cap = (h->overlap && h->overlap_on && h->out_mode == 1 && !h->k2_tile) ? h->nslots : 2;
+    if (h->q_count >= cap || (h->q_count >= 1 && !(h->out_mode == 1 && h->bins_cap_bits >= h->bins_worst_bits)))
         return fail(8, "evxgpu_encode_submit: previous frame not collected");
     CK(cudaSetDevice(h->device));
     if (!h->is_encoder && h->device >= 0 && h->device < 64) { g_encoders_live[h->device].fetch_add(1); h->is_encoder = true; }
@@ -872,13 +911,13 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
                 int rc = sync_all(h);                    // drained (collected frames may still be deblocking)
                 if (rc) return rc;
                 use_slot(h, 0);
-                h->fs[0].used = h->fs[1].used = false;   // an overlapped frame that follows has no predecessor to wait for
+                for (int k = 0; k < EVX_MAX_SLOTS; ++k) h->fs[k].used = false;   // an overlapped frame that follows has no predecessor to wait for
                 h->overlap_on = want;
             }
         }
         if (h->overlap_on) return submit_overlap(h, rgb, rgb_is_device, frame_type, frame_index, quality);
     }
-    const int q = (h->q_head + h->q_count) & 1;
+    const int q = (h->q_head + h->q_count) % h->nslots;
     h->slot = q;
     if (h->timing) t_fold(h, q);                 // the frame that used this slot before was collected long ago
     const uint8_t *d_rgb = rgb;
@@ -939,7 +978,7 @@ int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins_out, uint
         CK(cudaStreamSynchronize(h->stream));
         const uint64_t want = ((uint64_t) total + total / 2 + 4096) & ~63ull;
         if (want > 0xFFFFFFFFull) return fail(3, "evxgpu_encode_collect_bins: slice of more than 2^32 bins");
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < EVX_MAX_SLOTS; ++k)
         {
             cudaFree(h->d_bins[k]); h->d_bins[k] = NULL;
             if (cudaMalloc(&h->d_bins[k], (size_t) want / 8 + 8) != cudaSuccess) return fail(3, "evxgpu_encode_collect_bins: out of device memory");
@@ -968,7 +1007,7 @@ int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins_out, uint
     h->pending_bins[q] = false;
     h->bins_last_total = total;
     h->last_slot = q;
-    if (h->out_mode == 1) { h->q_head ^= 1; h->q_count--; h->pending_encode = h->q_count > 0; }
+    if (h->out_mode == 1) { h->q_head = (h->q_head + 1) % h->nslots; h->q_count--; h->pending_encode = h->q_count > 0; }
     *bins_out = reinterpret_cast<const uint64_t *>(h->h_bins[q] + 4);
     *nbins = total;
     if (n_noncopy) *n_noncopy = coded;
@@ -984,7 +1023,7 @@ int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_
     CK(cudaStreamSynchronize(h->stream));
     const int q = h->q_head;
     h->last_slot = q;
-    h->q_head ^= 1; h->q_count = 0; h->pending_encode = false;
+    h->q_head = (h->q_head + 1) % h->nslots; h->q_count = 0; h->pending_encode = false;
     const int n = h->h_sync[1];
     if (n < 0 || n > h->nmb) return fail(5, "evxgpu_encode_collect: corrupt record counter");
     memcpy(table_out, h->h_table, (size_t) h->nmb * 16);

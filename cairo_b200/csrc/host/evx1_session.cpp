@@ -5,6 +5,7 @@
 // engine_decode_frame (encode.cpp:205, decode.cpp:172) these sessions call the device
 // library (include/evxgpu.h) for the pixel pipeline and entropy.cpp for the slice.
 #include <stdlib.h>
+#include <algorithm>
 #include <string.h>
 
 #include <chrono>
@@ -83,14 +84,15 @@ class encoder_session : public evx1_encoder
         uint32 n_noncopy, d2h_bytes;
         uint64_t nbins;
     };
-    pending_frame dev_[2];                         // dev_[0] is the older of the frames on the device
-    int dev_count_;
+    enum { kDevMax = 3 };
+    pending_frame dev_[kDevMax];                   // dev_[0] is the oldest of the frames on the device
+    int dev_count_;                                // how many the device library takes: evxgpu_encode_capacity
     std::vector<evxgpu_block_desc> table_;         // retired frame, table + records output
     std::vector<int16> records_;
 
     // Bin-string output: the arithmetic coder of a slice needs nothing but the slice's bins (the coder is reset per
     // frame, serialize.cpp:323), so retired frames are coded by worker threads, several at a time, and collected in order.
-    enum { kJobs = 4, kWorkers = 3 };
+    enum { kJobs = 6, kWorkers = 4 };
     enum job_state { JOB_FREE = 0, JOB_QUEUED, JOB_RUNNING, JOB_DONE };
     struct job
     {
@@ -214,7 +216,7 @@ class encoder_session : public evx1_encoder
     {
         if (count_ >= max_jobs()) return EVX_ERROR_NOT_READY;
         pending_frame f = dev_[0];
-        dev_[0] = dev_[1];
+        for (int k = 1; k < dev_count_; ++k) dev_[k - 1] = dev_[k];
         dev_count_--;
         job &j = jobs_[(head_ + count_) % kJobs];
         int rc;
@@ -285,7 +287,6 @@ public:
     evx_status submit(void *image, uint32 width, uint32 height)
     {
         if (!width || !height || !image) return EVX_ERROR_INVALIDARG;
-        if (dev_count_ == 2 && count_ >= max_jobs()) return EVX_ERROR_NOT_READY;        // nowhere to retire the older frame to
         bool first = false;
         if (!initialized_)
         {
@@ -296,23 +297,25 @@ public:
         }
         if (width != header_.frame_width || height != header_.frame_height) return EVX_ERROR_INVALID_RESOURCE;
         const uint8 *rgb = static_cast<const uint8 *>(image);
-        if (dev_count_ == 2)
-        {   // the device holds two frames: take the older one's results off it (it is finished or about to be); its
-            // arithmetic coder starts on a worker thread while this thread queues the new frame
+        while (dev_count_ > 0 && dev_count_ >= std::min<int>(kDevMax, evxgpu_encode_capacity(gpu_)))
+        {   // the device holds all the frames it takes (two, or three overlapping ones; one with table + records output):
+            // take the oldest one's results off it (it is finished or about to be); its arithmetic coder starts on a
+            // worker thread while this thread queues the new frame
+            if (count_ >= max_jobs()) return EVX_ERROR_NOT_READY;       // nowhere to retire it to: collect() first
             evx_status st = retire(true);
             if (evx_failed(st)) return st;
         }
         const double t0 = now_ms();
         int rc;
-        if (dev_count_ == 1)
+        if (dev_count_ >= 1)
         {
             // the new frame's host->device copy runs under the kernels of the frame still on the device, and its own
             // kernels are queued right behind them; a device library that takes one frame at a time (table + records
             // output, or string buffers below the worst case) gets the older frame collected first
             if (evxgpu_encode_upload(gpu_, rgb)) return EVX_ERROR_EXECUTION_FAILURE;
             rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
-            if (rc == 8)
-            {
+            while (rc == 8 && dev_count_ > 0)
+            {   // (also: frames stopped overlapping next to another encoder, or the overlap epochs restart -- that needs the device drained)
                 evx_status st = retire(true);
                 if (evx_failed(st)) return st;
                 rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);

@@ -49,6 +49,7 @@ def lib():
     L.evxgpu_upload.argtypes = [vp, vp, vp, C.c_uint64]
     L.evxgpu_encode_submit.argtypes = [vp, vp, i32, i32, u32, i32]
     L.evxgpu_encode_collect.argtypes = [vp, vp, vp, C.POINTER(u32)]
+    L.evxgpu_encode_capacity.argtypes = [vp]
     L.evxgpu_set_output.argtypes = [vp, i32]
     L.evxgpu_encode_collect_bins.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64), C.POINTER(u32)]
     L.evxgpu_debug_set_bins_capacity.argtypes = [vp, u32]
@@ -119,6 +120,10 @@ class Pipeline:
             rgb = np.ascontiguousarray(rgb)
             self._keep = rgb
             _check(self.L.evxgpu_encode_submit(self.h, _p(rgb), 0, frame_type, index, quality), "evxgpu_encode_submit")
+
+    def encode_capacity(self):
+        """Submitted, uncollected frames the handle accepts (1, 2, or 3 with three overlapping frame slots)."""
+        return int(self.L.evxgpu_encode_capacity(self.h))
 
     def encode_collect(self):
         tbl = np.zeros(self.nblocks, dtype=BLOCK_DESC_DTYPE)

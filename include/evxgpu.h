@@ -91,6 +91,11 @@ int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_
  * and uses the uploaded frame.  rgb_host must stay unchanged until that submit's frame has been collected (or the
  * handle synchronised). */
 int evxgpu_encode_upload(evxgpu_handle *h, const uint8_t *rgb_host);
+/* How many submitted, uncollected frames the handle accepts at this moment: 1 with table + records output, 2 with
+ * bin-string output, 3 while consecutive frames overlap on the device in three frame slots (the default for the
+ * device's only encoder; EVXGPU_FRAME_SLOTS=2 keeps two), 0 when every frame in flight has to be collected first
+ * (the overlap counters restart every 2^19 frames).  A submit beyond it returns status 8. */
+int evxgpu_encode_capacity(const evxgpu_handle *h);
 
 /* The same slice as the string of bins serialize_slice feeds its arithmetic coder (serialize.cpp:156-340:
  * block table by field, then the Y, U, V residual blocks; raw bits and Exp-Golomb codes of golomb.cpp:8-91,

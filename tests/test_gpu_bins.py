@@ -102,13 +102,17 @@ def test_two_frames_queued_on_the_device():
     b = gpu.Pipeline(w, h, 2, 0, 1)
     b.set_output(1)
     got = []
-    b.encode_submit(frames[0], 0, 0, q)
-    for t in range(1, n):
+    cap = b.encode_capacity()                                 # 2, or 3 with three overlapping frame slots
+    assert cap in (2, 3)
+    for t in range(cap - 1):
+        b.encode_submit(frames[t], 0 if t == 0 else 1, t, q)
+    for t in range(cap - 1, n):
         b.encode_submit(frames[t], 1, t, q)
         with pytest.raises(RuntimeError):
-            b.encode_submit(frames[t], 1, t + 1, q)          # a third frame
+            b.encode_submit(frames[t], 1, t + 1, q)          # one frame more than the handle holds
         got.append(b.encode_collect_bins())
-    got.append(b.encode_collect_bins())
+    for _ in range(cap - 1):
+        got.append(b.encode_collect_bins())
     with pytest.raises(RuntimeError):
         b.encode_collect_bins()
     for t in range(n):
@@ -147,16 +151,24 @@ def _bins_sequence(env, w, h, R, frames, types, qualities):
         p = gpu.Pipeline(w, h, R, 0, 1)
         p.set_output(1)
         out = []
-        p.encode_submit(frames[0], types[0], 0, qualities[0])
-        for t in range(1, len(frames)):
-            try:
-                p.encode_submit(frames[t], types[t], t, qualities[t])
+        ahead = p.encode_capacity() - 1           # frames kept queued behind the one being collected
+        inflight = 0
+        for t in range(len(frames)):
+            while True:
+                try:
+                    p.encode_submit(frames[t], types[t], t, qualities[t])
+                    inflight += 1
+                    break
+                except RuntimeError as ex:        # status 8: the epochs restart, which needs the device drained first
+                    assert "status 8" in str(ex) and inflight > 0, ex
+                    out.append(p.encode_collect_bins())
+                    inflight -= 1
+            if inflight > ahead:
                 out.append(p.encode_collect_bins())
-            except RuntimeError as ex:            # status 8: the epochs restart, which needs the device drained first
-                assert "status 8" in str(ex), ex
-                out.append(p.encode_collect_bins())
-                p.encode_submit(frames[t], types[t], t, qualities[t])
-        out.append(p.encode_collect_bins())
+                inflight -= 1
+        while inflight:
+            out.append(p.encode_collect_bins())
+            inflight -= 1
         rec = [a.copy() for a in p.planes(2, (len(frames) - 1) % R)]
         p.close()
     finally:
@@ -178,7 +190,9 @@ def test_overlapped_frames_equal_serial_frames(w, h, R):
     types = [0, 1, 1, 1, 0, 1, 1, 1, 1]
     qualities = [16, 16, 8, 8, 24, 24, 16, 31, 1]
     want, wrec = _bins_sequence({"EVXGPU_FRAME_OVERLAP": "0"}, w, h, R, frames, types, qualities)
-    for env in ({"EVXGPU_FRAME_OVERLAP": "1"}, {"EVXGPU_FRAME_OVERLAP": "1", "EVXGPU_BAND_ROWS": "3", "EVXGPU_EPOCH_LIMIT": "3"}):
+    for env in ({"EVXGPU_FRAME_OVERLAP": "1", "EVXGPU_FRAME_SLOTS": "2"}, {"EVXGPU_FRAME_OVERLAP": "1", "EVXGPU_FRAME_SLOTS": "3"},
+                {"EVXGPU_FRAME_OVERLAP": "1", "EVXGPU_FRAME_SLOTS": "2", "EVXGPU_BAND_ROWS": "3", "EVXGPU_EPOCH_LIMIT": "3"},
+                {"EVXGPU_FRAME_OVERLAP": "1", "EVXGPU_FRAME_SLOTS": "3", "EVXGPU_BAND_ROWS": "3", "EVXGPU_EPOCH_LIMIT": "4"}):
         got, grec = _bins_sequence(env, w, h, R, frames, types, qualities)
         for t in range(n):
             assert _same_bins(got[t], want[t]), (env, t)
