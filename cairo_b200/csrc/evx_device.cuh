@@ -261,6 +261,32 @@ __device__ __forceinline__ void evx_load_block_ring_bf(const EvxRingWin &win, in
     b.w[5] = __byte_perm(win.v[crow + (c0 & 31)], win.v[crow + ((c0 + 1) & 31)], csel);
 }
 
+// The same for positions whose parity is known when the code is written: the full-pel rounds with steps 16, 8 and 4 only
+// ever name positions with x = 0 (mod 4) (macroblock origin + multiples of the step), the step-2 round x = 0 (mod 2): the
+// words are aligned and the neighbouring word and the byte permute are not needed.
+template <bool LUMA_ONLY_ALIGNED>      // false: luma and chroma words aligned (x % 4 == 0); true: luma aligned, chroma by parity
+__device__ __forceinline__ void evx_load_block_ring_al(const EvxRingWin &win, int x, int y, int lane, EvxLaneBlock &b)
+{
+    const uint32_t *row = win.y + (y - win.oy + (lane >> 3)) * EVX_RING_PWY;
+    const int w0 = (x >> 1) + (lane & 7);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) b.w[k] = row[4 * k * EVX_RING_PWY + (w0 & 63)];
+    const int cx = x >> 1;
+    const int crow = ((y >> 1) - win.coy + (lane >> 2)) * EVX_RING_PWC;
+    const int c0 = (cx >> 1) + (lane & 3);
+    if (LUMA_ONLY_ALIGNED)
+    {
+        const uint32_t csel = (cx & 1) ? 0x5432u : 0x3210u;
+        b.w[4] = __byte_perm(win.u[crow + (c0 & 31)], win.u[crow + ((c0 + 1) & 31)], csel);
+        b.w[5] = __byte_perm(win.v[crow + (c0 & 31)], win.v[crow + ((c0 + 1) & 31)], csel);
+    }
+    else
+    {
+        b.w[4] = win.u[crow + (c0 & 31)];
+        b.w[5] = win.v[crow + (c0 & 31)];
+    }
+}
+
 // The source macroblock of a warp, in the lane layout above: packed negation (for
 // VIADDMNMX) and the lane's luma sum.
 struct EvxLaneSrc

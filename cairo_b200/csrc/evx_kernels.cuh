@@ -220,9 +220,6 @@ __device__ __forceinline__ void evx_inter_search_warp(EvxWin &win, const EvxLane
     n_full = 1; n_sub = 0;
     if (s.mad < thr) return;                       // already a copy block: no search (motion.cpp:452)
     stage(0, px, py, win);
-#ifdef EVX_K2_UNROLL_STEPS
-#pragma unroll
-#endif
     for (int step = EVX_SEARCH_RADIUS; step > 0; step >>= 1)
     {
         // One 3x3 round (motion.cpp:254-275).  The eight outer cells are costed back to back (no

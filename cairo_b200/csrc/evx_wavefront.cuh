@@ -372,7 +372,14 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                     const int x = s.bx + (round == 0 ? cdx0[q] : cdx[q]) * step;
                     const int y = s.by + (round == 0 ? cdy0[q] : cdy[q]) * step;
                     EvxLaneBlock ref;
+#ifdef EVX_K3_NO_ALIGNED_LOADS
                     evx_load_block_ring_bf(win, x, y, lane, ref);
+#else
+                    // (the loop is unrolled: `round` is a constant here)
+                    if (round <= 2) evx_load_block_ring_al<false>(win, x, y, lane, ref);
+                    else if (round == 3) evx_load_block_ring_al<true>(win, x, y, lane, ref);
+                    else evx_load_block_ring_bf(win, x, y, lane, ref);
+#endif
                     la[q] = evx_block_sad_lane(ref, src);
                     lm[q] = evx_block_mad_lane(ref, src);
                 }
