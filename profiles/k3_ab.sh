@@ -1,4 +1,5 @@
-# A/B of compile-time variants: build, bench (per-kernel times from its frame-after-frame pass), parity tests
+# A/B of compile-time variants (each argument is a set of nvcc flags, "" = as shipped): build, bench (per-kernel times
+# from its frame-after-frame pass), parity tests.  Report: python profiles/ab_report.py
 i=0
 for v in "$@"; do
   i=$((i+1)); tag=v$i
