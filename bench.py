@@ -383,7 +383,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             if pipelined:
-                ahead = min(3, len(coded))
+                ahead = min(7, len(coded))
                 for d, b in coded[:ahead]:
                     dec.submit(d, b)
                 for d, b in coded[ahead:]:
@@ -397,7 +397,7 @@ def run_ours(args):
             return len(coded) / (time.perf_counter() - t0)
 
         dec_sync, dec_pipe = decode_run(False), decode_run(True)
-        decode_extra = {"value": dec_pipe, "unit": "frames/s", "api": "evx1_decoder::submit/collect (four frames in flight, three parser threads), bitstream -> RGB8 in pinned host memory",
+        decode_extra = {"value": dec_pipe, "unit": "frames/s", "api": "evx1_decoder::submit/collect (eight frames in flight, six parser threads), bitstream -> RGB8 in pinned host memory",
                         "synchronous": dec_sync, "frames": len(coded)}
     except Exception as ex:
         decode_extra = {"value": None, "error": str(ex)}

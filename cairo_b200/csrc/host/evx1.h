@@ -138,13 +138,13 @@ public:
     // additions: encode() == submit() + collect().  submit queues the frame on the device (colour
     // conversion, motion search, transform/quantisation, reconstruction, deblocking, binarisation) and
     // returns; collect appends what encode() would have appended for the oldest uncollected frame (stream
-    // header on the first frame, frame descriptor, slice).  Several frames may be uncollected: two on the device,
-    // where consecutive frames overlap row by row, and up to four retired ones whose slices are being entropy-coded
-    // on the session's coder threads (a slice's coder needs nothing from other frames).  With submit(n+k) before
-    // collect(n), k = 1..4, the host entropy stage, the device's work and the host->device copies of different frames
+    // header on the first frame, frame descriptor, slice).  Several frames may be uncollected: up to three on the
+    // device, where consecutive frames overlap row by row (two next to other encoders), and up to six retired ones whose
+    // slices are being entropy-coded on the session's four coder threads (a slice's coder needs nothing from other
+    // frames).  With submit(n+k) before collect(n), k = 1..6, the host entropy stage, the device's work and the host->device copies of different frames
     // all run at the same time; collect() returns the frames in order, the same bytes encode() appends.  `image` must
     // stay unchanged until the frame's own collect() returns.  submit returns EVX_ERROR_NOT_READY when the device
-    // holds two frames and four retired ones wait to be collected; encode() when any frame is uncollected; collect()
+    // holds all the frames it takes and six retired ones wait to be collected; encode() when any frame is uncollected; collect()
     // when none is.
     virtual evx_status submit(void *image, uint32 width, uint32 height) = 0;
     virtual evx_status collect(bit_stream *output) = 0;
@@ -164,7 +164,7 @@ public:
     // decode) and hands its slice to a parser thread; collect merges the oldest submitted frame into the stream's
     // state, runs the pixel pipeline and writes its picture.  The arithmetic decoding of a slice needs nothing from
     // other frames, so with submit(n+1) ... submit(n+3) before collect(n) the slices of consecutive frames are decoded
-    // concurrently (three parser threads) while the caller's thread runs the device.  At most four frames may be
+    // concurrently (six parser threads) while the caller's thread runs the device.  At most eight frames may be
     // uncollected (EVX_ERROR_NOT_READY otherwise, and for decode() with any frame uncollected, and for collect
     // with none).  decode() itself parses on the calling thread.
     virtual evx_status submit(bit_stream *input) = 0;

@@ -189,7 +189,7 @@ def test_pipelined_1080p_equals_synchronous_and_state_rules():
 def test_pipelined_decode_equals_synchronous():
     """evx1_decoder::submit(n+1) before collect(n): same pictures as decode(), one call later; state rules."""
     from cairo_b200 import api
-    w, h, n = 352, 288, 8
+    w, h, n = 352, 288, 12
     enc = api.evx1_encoder()
     enc.set_quality(16)
     streams = []
@@ -206,16 +206,17 @@ def test_pipelined_decode_equals_synchronous():
     dec.submit(*streams[0])
     with pytest.raises(RuntimeError):
         dec.decode(streams[1][0], streams[1][1], w, h)     # decode() with a frame uncollected
-    dec.submit(*streams[1])
-    dec.submit(*streams[2])
-    dec.submit(*streams[3])                        # four frames may be uncollected (their slices parse concurrently)
+    held = 1
+    for t in range(1, 8):
+        dec.submit(*streams[t])                    # eight frames may be uncollected (their slices parse concurrently)
+        held += 1
     with pytest.raises(RuntimeError):
-        dec.submit(*streams[4])                    # a fifth
+        dec.submit(*streams[held])                 # a ninth
     got = [dec.collect(w, h).copy()]
-    for t in range(4, n):
+    for t in range(held, n):
         dec.submit(*streams[t])
         got.append(dec.collect(w, h).copy())
-    for _ in range(3):
+    for _ in range(held - 1):
         got.append(dec.collect(w, h).copy())
     with pytest.raises(RuntimeError):
         dec.collect(w, h)
