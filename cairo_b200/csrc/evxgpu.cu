@@ -880,7 +880,7 @@ int evxgpu_encode_capacity(const evxgpu_handle *h)
 int evxgpu_encode_upload(evxgpu_handle *h, const uint8_t *rgb_host)
 {
     if (!h || !rgb_host) return fail(1, "evxgpu_encode_upload: bad argument");
-    if (h->uploaded) return fail(8, "evxgpu_encode_upload: the previous upload has not been submitted");
+    // (an upload that was never submitted -- its submit failed -- is simply replaced: the copies are ordered on the copy stream)
     CK(cudaSetDevice(h->device));
     if (!h->up_ready) return fail(8, "evxgpu_encode_upload: the handle has no upload stream");
     CK(cudaStreamWaitEvent(h->copy_stream, h->ev_k1, 0));       // the frame uploaded before has been converted

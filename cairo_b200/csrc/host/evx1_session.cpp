@@ -297,6 +297,12 @@ public:
         }
         if (width != header_.frame_width || height != header_.frame_height) return EVX_ERROR_INVALID_RESOURCE;
         const uint8 *rgb = static_cast<const uint8 *>(image);
+        // With frames on the device the new frame's host->device copy starts right away, on the copy stream, under their
+        // kernels -- before this thread waits for the oldest of them: a frame's kernels cannot start before its pixels are
+        // there, and with three frames overlapping the new one is due the moment its slot is free.
+        const bool early = dev_count_ >= 1;
+        if (early && dev_count_ >= std::min<int>(kDevMax, evxgpu_encode_capacity(gpu_)) && count_ >= max_jobs()) return EVX_ERROR_NOT_READY;
+        if (early && evxgpu_encode_upload(gpu_, rgb)) return EVX_ERROR_EXECUTION_FAILURE;
         while (dev_count_ > 0 && dev_count_ >= std::min<int>(kDevMax, evxgpu_encode_capacity(gpu_)))
         {   // the device holds all the frames it takes (two, or three overlapping ones; one with table + records output):
             // take the oldest one's results off it (it is finished or about to be); its arithmetic coder starts on a
@@ -307,12 +313,9 @@ public:
         }
         const double t0 = now_ms();
         int rc;
-        if (dev_count_ >= 1)
+        if (early)
         {
-            // the new frame's host->device copy runs under the kernels of the frame still on the device, and its own
-            // kernels are queued right behind them; a device library that takes one frame at a time (table + records
-            // output, or string buffers below the worst case) gets the older frame collected first
-            if (evxgpu_encode_upload(gpu_, rgb)) return EVX_ERROR_EXECUTION_FAILURE;
+            // the frame uploaded above; its kernels are queued right behind those of the frames still on the device
             rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
             while (rc == 8 && dev_count_ > 0)
             {   // (also: frames stopped overlapping next to another encoder, or the overlap epochs restart -- that needs the device drained)

@@ -89,7 +89,7 @@ int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_
 /* Optional early copy of the NEXT frame: may be called while a frame is still in flight; the host->device copy
  * runs on a second stream under the current frame's kernels.  The following evxgpu_encode_submit takes rgb = NULL
  * and uses the uploaded frame.  rgb_host must stay unchanged until that submit's frame has been collected (or the
- * handle synchronised). */
+ * handle synchronised).  An upload whose submit never happened is replaced by the next upload. */
 int evxgpu_encode_upload(evxgpu_handle *h, const uint8_t *rgb_host);
 /* How many submitted, uncollected frames the handle accepts at this moment: 1 with table + records output, 2 with
  * bin-string output, 3 while consecutive frames overlap on the device in three frame slots (the default for the
