@@ -186,6 +186,39 @@ def test_pipelined_1080p_equals_synchronous_and_state_rules():
         assert out[t][1] == sync[t][1] and (out[t][0] == sync[t][0]).all(), t
 
 
+@pytest.mark.parametrize("env", [{"EVXGPU_FRAME_SLOTS": "3", "EVXGPU_EPOCH_LIMIT": "4"}, {"EVXGPU_FRAME_SLOTS": "2", "EVXGPU_EPOCH_LIMIT": "3"},
+                                 {"EVXGPU_FRAME_OVERLAP": "0"}])
+def test_pipelined_session_across_epoch_restarts(env, monkeypatch):
+    """evx1_encoder::submit/collect while the frame-overlap epochs restart every few frames (the device library then takes
+    no frame until it is drained: evxgpu_encode_capacity = 0) and with two or three frame slots: the same bytes as encode()."""
+    from cairo_b200 import api
+    w, h, n = 640, 368, 14
+    frames = [synth.frame(w, h, t, 11, "moving") for t in range(n)]
+    a = api.evx1_encoder(ref_count=2)
+    a.set_quality(12)
+    sync = []
+    for t in range(n):
+        d, b = a.encode(frames[t])
+        sync.append((d.copy(), b))
+    del a                                         # the pipelined session is the device's only encoder: frames overlap
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    p = api.evx1_encoder(ref_count=2)
+    p.set_quality(12)
+    out = []
+    look = 5
+    for t in range(n):
+        p.submit(frames[t])
+        if t >= look:
+            d, b = p.collect()
+            out.append((d.copy(), b))
+    while len(out) < n:
+        d, b = p.collect()
+        out.append((d.copy(), b))
+    for t in range(n):
+        assert out[t][1] == sync[t][1] and (out[t][0] == sync[t][0]).all(), (env, t)
+
+
 def test_pipelined_decode_equals_synchronous():
     """evx1_decoder::submit(n+1) before collect(n): same pictures as decode(), one call later; state rules."""
     from cairo_b200 import api
