@@ -112,7 +112,7 @@ struct evxgpu_handle
     int16_t *d_dc;                  // persistent DC mirror [4][nmb]
     int *d_prev;                    // prev_motion[nmb], prev_coded[nmb], row_last[2][mbh] (written by K3)
     uint32_t *d_len, *d_tile_sum;
-    // Two frame slots: in bin-only output mode a second frame may be queued behind the one in flight (its
+    // Frame slots (EVX_MAX_SLOTS): in bin-only output mode a second frame may be queued behind the one in flight (its
     // kernels start the moment the first one's end, the host is still busy with the first one's bins).
     uint32_t *d_bins[EVX_MAX_SLOTS], *d_bins_total[EVX_MAX_SLOTS];
     uint32_t bins_cap_bits;         // capacity of each d_bins
@@ -123,7 +123,7 @@ struct evxgpu_handle
     cudaEvent_t ev_out[EVX_MAX_SLOTS];
     bool pending_bins[EVX_MAX_SLOTS];
     uint64_t d2h_bytes[EVX_MAX_SLOTS]; // device-to-host bytes of the slot's frame
-    // Frame overlap (EVXGPU_FRAME_OVERLAP=1, bin-only output): the two frame slots own their per-frame device state and
+    // Frame overlap (on unless EVXGPU_FRAME_OVERLAP=0, bin-only output): the frame slots (nslots: 3, or 2) own their per-frame device state and
     // three streams each, and consecutive frames of the stream run concurrently, gated row by row through counters in
     // device memory (stream memory operations on the host side, polls in the wavefront kernel).  See submit_overlap.
     bool overlap;                   // the machinery exists (slots, streams, counters)
@@ -683,7 +683,7 @@ static int enable_overlap(evxgpu_handle *h)
 }
 
 // One frame, queued so that it overlaps the previous frame of the stream.  Everything of the frame lives in slot q;
-// p = q ^ 1 holds the previous frame, which may still be running.  Dependencies on the previous frame (SURVEY H3,
+// p = the slot before q holds the previous frame, which may still be running (and the one before that the frame before it).  Dependencies on the previous frame (SURVEY H3,
 // DESIGN section 6a), all by rows: K2 and the inter predictions of rows [r-2, r+3] need it deblocked there; its band b
 // may be deblocked once its wavefront has finished row band_end(b)+3 (the intra search reads three rows up, unfiltered);
 // with a ring of two this frame overwrites the slot the previous one reads as its reference, two rows behind what K2
