@@ -26,6 +26,8 @@ def lib():
     vp, i32, u32 = C.c_void_p, C.c_int, C.c_uint32
     L.evx1c_encoder_create.restype = vp
     L.evx1c_encoder_create.argtypes = [i32] * 6
+    L.evx1c_encoder_create_ex.restype = vp
+    L.evx1c_encoder_create_ex.argtypes = [i32] * 9
     L.evx1c_encoder_destroy.argtypes = [vp]
     L.evx1c_encoder_clear.argtypes = [vp]
     L.evx1c_encoder_insert_intra.argtypes = [vp]
@@ -39,6 +41,8 @@ def lib():
     L.evx1c_encoder_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     L.evx1c_decoder_create.restype = vp
     L.evx1c_decoder_create.argtypes = [i32] * 3
+    L.evx1c_decoder_create_ex.restype = vp
+    L.evx1c_decoder_create_ex.argtypes = [i32] * 4
     L.evx1c_decoder_destroy.argtypes = [vp]
     L.evx1c_decoder_clear.argtypes = [vp]
     L.evx1c_decoder_decode.argtypes = [vp, vp, u32, vp]
@@ -69,9 +73,13 @@ def _p(a):
 class evx1_encoder:
     """evx1_encoder (evx1.h:66-94).  ref_count/linear_quant/deblocking default to config.h's values."""
 
-    def __init__(self, device=0, ref_count=-1, linear_quant=-1, deblocking=-1, periodic_intra=-1, default_quality=-1):
+    def __init__(self, device=0, ref_count=-1, linear_quant=-1, deblocking=-1, periodic_intra=-1, default_quality=-1,
+                 frame_slots=0, coder_threads=0, device_frames=False):
+        """frame_slots / coder_threads: evx1_config additions (0 = defaults).  device_frames=True: the frames given to
+        encode()/submit() are device pointers, passed as (ptr, width, height)."""
         self.L = lib()
-        self.h = self.L.evx1c_encoder_create(device, ref_count, linear_quant, deblocking, periodic_intra, default_quality)
+        self.h = self.L.evx1c_encoder_create_ex(device, ref_count, linear_quant, deblocking, periodic_intra, default_quality,
+                                                frame_slots, coder_threads, 1 if device_frames else 0)
         if not self.h:
             raise RuntimeError("create_encoder failed")
         self._out = None
@@ -150,9 +158,11 @@ class evx1_encoder:
 class evx1_decoder:
     """evx1_decoder (evx1.h:96-113)."""
 
-    def __init__(self, device=0, linear_quant=-1, deblocking=-1):
+    def __init__(self, device=0, linear_quant=-1, deblocking=-1, device_frames=False):
+        """device_frames=True: decode()/collect() write the picture to a device pointer given as out=ptr (int)."""
         self.L = lib()
-        self.h = self.L.evx1c_decoder_create(device, linear_quant, deblocking)
+        self.device_frames = bool(device_frames)
+        self.h = self.L.evx1c_decoder_create_ex(device, linear_quant, deblocking, 1 if device_frames else 0)
         if not self.h:
             raise RuntimeError("create_decoder failed")
 
@@ -174,7 +184,7 @@ class evx1_decoder:
         data = np.ascontiguousarray(data, dtype=np.uint8)
         if out is None:
             out = np.empty((height, width, 3), dtype=np.uint8)
-        st = self.L.evx1c_decoder_decode(self.h, _p(data), nbits, _p(out))
+        st = self.L.evx1c_decoder_decode(self.h, _p(data), nbits, out if isinstance(out, int) else _p(out))
         if st != 0:
             raise RuntimeError(f"evx1_decoder::decode failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
         return out
@@ -191,7 +201,7 @@ class evx1_decoder:
         """Second half of decode(): the oldest submitted frame's picture."""
         if out is None:
             out = np.empty((height, width, 3), dtype=np.uint8)
-        st = self.L.evx1c_decoder_collect(self.h, _p(out))
+        st = self.L.evx1c_decoder_collect(self.h, out if isinstance(out, int) else _p(out))
         if st != 0:
             raise RuntimeError(f"evx1_decoder::collect failed with status {st}: {_gpu.lib().evxgpu_last_error().decode()}")
         return out

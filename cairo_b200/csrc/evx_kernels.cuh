@@ -169,25 +169,14 @@ __device__ __forceinline__ void evx_tma_load_2d(void *dst, const CUtensorMap *ma
 
 // ------------------------------------------------------------------ K2: inter search
 //
-// grid = (ceil(mbw/8), mbh, refs), block = 8 warps.  A CTA serves eight horizontally adjacent
-// macroblocks against ONE reference frame; their +-32 px search windows overlap into one
-// 208x80 luma tile and two 104x40 chroma tiles (49.9 KB), fetched by three TMA tile loads
-// (out-of-frame samples are zero-filled and never evaluated).  Each WARP then runs the whole
-// sequential search of its macroblock (motion.cpp:421-494) with no block-level
-// synchronisation: the 16x16+8x8+8x8 candidate cost is a warp-collective (evx_block_cost),
-// the acceptance rule is replayed identically in every lane.
+// Each WARP runs the whole sequential search of one (macroblock, reference) pair (motion.cpp:421-494) with no
+// block-level synchronisation: the 16x16+8x8+8x8 candidate cost is a warp collective (evx_block_cost), the
+// acceptance rule has a closed form evaluated lane-parallel (evx_select_fullpel).
 
-#ifndef EVX_K2_MBS
-#define EVX_K2_MBS 8              // macroblocks (= warps) per CTA; 8 or 4 keep the pitches conflict-free
-#endif
-#define EVX_K2_WIN_W (32 + EVX_K2_MBS * 16 + 48)   // 208 px = 104 words = 8 (mod 32);  144 px = 72 words = 8 (mod 32)
-#define EVX_K2_WIN_H 80
-#define EVX_K2_CWIN_W (EVX_K2_WIN_W / 2)           // 52 words = 4*13 -> 20 (mod 32);  36 words = 4 (mod 32)
-#define EVX_K2_CWIN_H 40
-#define EVX_K2_CTAS_PER_SM (EVX_K2_MBS == 8 ? 4 : 6)
-#define EVX_K2_SMEM (EVX_K2_WIN_W * EVX_K2_WIN_H * 2 + 2 * EVX_K2_CWIN_W * EVX_K2_CWIN_H * 2 + 16)
-
-struct EvxInterResult { EvxDesc desc; int sad; int pad[3]; };    // 32 bytes per (macroblock, reference)
+// 32 bytes per (macroblock, reference).  `stamp` is the token of the frame the record belongs to: when the search runs as a
+// role of the frame kernel (evx_wavefront.cuh) it is stored last, with release semantics, and the wavefront's block loader
+// polls it -- the slot's records are reused by later frames and never zeroed.
+struct EvxInterResult { EvxDesc desc; int sad; uint32_t stamp; int pad[2]; };
 
 struct EvxK2Maps { CUtensorMap m[3 * 7]; };   // [ref][Y,U,V] for up to 7 past references
 
@@ -283,79 +272,20 @@ __device__ __forceinline__ void evx_inter_search_warp(EvxWin &win, const EvxLane
     }
 }
 
-__global__ void __launch_bounds__(EVX_K2_MBS * 32, EVX_K2_CTAS_PER_SM) evx_inter_search_tile(const __grid_constant__ EvxK2Maps maps, EvxPlanes srcp, EvxGeom g,
-                                                        EvxInterResult *__restrict__ results, int thr,
-                                                        unsigned long long *__restrict__ counters)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    int16_t *wy = reinterpret_cast<int16_t *>(smem);
-    int16_t *wu = wy + EVX_K2_WIN_W * EVX_K2_WIN_H;
-    int16_t *wv = wu + EVX_K2_CWIN_W * EVX_K2_CWIN_H;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(wv + EVX_K2_CWIN_W * EVX_K2_CWIN_H);
-
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int ref = blockIdx.z;                           // 0-based: ring offset ref+1
-    int bx0 = blockIdx.x * EVX_K2_MBS, by = blockIdx.y;
-    int ox = bx0 * EVX_MB - 32, oy = by * EVX_MB - 32;
-
-    if (threadIdx.x == 0) evx_mbar_init(bar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0)
-    {
-        evx_mbar_expect_tx(bar, EVX_K2_WIN_W * EVX_K2_WIN_H * 2 + 2 * EVX_K2_CWIN_W * EVX_K2_CWIN_H * 2);
-        evx_tma_load_2d(wy, &maps.m[ref * 3 + 0], ox, oy, bar);
-        evx_tma_load_2d(wu, &maps.m[ref * 3 + 1], ox >> 1, oy >> 1, bar);
-        evx_tma_load_2d(wv, &maps.m[ref * 3 + 2], ox >> 1, oy >> 1, bar);
-    }
-
-    int bx = bx0 + warp;
-    bool active = bx < g.mbw;
-    int px = bx * EVX_MB, py = by * EVX_MB;
-    EvxLaneSrc src;
-    if (active)
-    {
-        EvxLaneBlock sb;
-        evx_load_src_lane(srcp, g, px, py, lane, sb);       // overlaps the TMA flight
-        evx_make_src(sb, src);
-    }
-    evx_mbar_wait(bar, 0);
-    if (!active) return;
-
-    EvxWin win;
-    win.y = reinterpret_cast<const uint32_t *>(wy); win.u = reinterpret_cast<const uint32_t *>(wu); win.v = reinterpret_cast<const uint32_t *>(wv);
-    win.pw_y = EVX_K2_WIN_W / 2; win.pw_c = EVX_K2_CWIN_W / 2;
-    win.ox = ox; win.oy = oy; win.cox = ox >> 1; win.coy = oy >> 1;
-
-    EvxSel s;
-    uint32_t n_full, n_sub;
-    EvxLaneBlock centre;
-    evx_load_block(win, px, py, lane, centre);
-    evx_inter_search_warp(win, src, centre, g, px, py, thr, lane, s, n_full, n_sub, EvxNoStage());
-
-    if (lane == 0)
-    {
-        EvxInterResult r;
-        r.desc = evx_desc_from_sel(s, 0, ref + 1, px, py, thr);
-        r.sad = s.sad; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-        results[(size_t) ref * g.mbw * g.mbh + (size_t) by * g.mbw + bx] = r;
-        atomicAdd(&counters[0], (unsigned long long) n_full);
-        atomicAdd(&counters[1], (unsigned long long) n_sub);
-    }
-}
-
-// ------------------------------------------------------------------ K2, one warp per macroblock
+// ------------------------------------------------------------------ K2, one warp per (macroblock, reference)
 //
-// grid = (mbw, mbh, refs), block = ONE warp = one (macroblock, reference) search.  About four in ten
-// macroblocks of ordinary video are copy blocks whose search ends at the centre test; in the tile kernel
-// above their warps sit dead in a CTA until its slowest member finishes (25 % achieved occupancy of a
-// 50 % limit, and a 24 % tail).  Here a finished search frees its SM slot at once:
+// About four in ten macroblocks of ordinary video are copy blocks whose search ends at the centre test, so the
+// unit of work is ONE warp = one (macroblock, reference) search that frees its resources the moment it ends:
 //   * the centre test reads the co-located block straight from global memory (no window at all);
 //   * a macroblock that does search never needs the whole +-32 range at once.  The step-16 round touches
 //     [px-16, px+32) x [py-16, py+32); everything after it (steps 8,4,2,1 and the sub-pel taps) stays within
 //     [-16, +32) of that round's winner.  So the window is 48x48 luma + two 24x24 chroma tiles (6.9 KB),
-//     fetched by TMA twice -- 28 searches resident per SM instead of 16 live ones.
+//     fetched by TMA twice (cp.async.bulk.tensor.2d on one mbarrier; out-of-frame samples zero-filled).
 // Row pitches of 24 / 12 words keep the lane layout of evx_load_block bank-conflict free
 // (rows {0,24,48,72} + 0..7 and {0,12,..,84} + 0..3 tile the 32 banks).
+// Two callers: the stand-alone kernel evx_inter_search (grid = (mbw, mbh, refs), one warp per CTA -- the
+// kernel the integer roofline is quoted on) and the search role of the frame kernel (evx_wavefront.cuh), whose
+// warps pull (macroblock, reference) items of one macroblock row and reuse their window and barrier.
 
 #define EVX_K2W_WIN 48
 #define EVX_K2W_CWIN 24
@@ -371,7 +301,7 @@ struct EvxK2Params
     EvxInterResult *results;
     unsigned long long *counters;
     int thr;
-    int row0;                     // first macroblock row of this launch (a frame may be searched band by band)
+    int row0;                     // first macroblock row of this launch
 };
 
 struct EvxK2Stage
@@ -379,6 +309,7 @@ struct EvxK2Stage
     const CUtensorMap *my, *mu, *mv;
     int16_t *wy, *wu, *wv;
     uint64_t *bar;
+    uint32_t *phase;              // parity of the barrier's next completion (a persistent warp reuses its barrier)
     int lane;
     __device__ __forceinline__ void fetch(int cx, int cy) const
     {
@@ -390,41 +321,41 @@ struct EvxK2Stage
             evx_tma_load_2d(wv, mv, (cx - 16) >> 1, (cy - 16) >> 1, bar);
         }
     }
-    // k = 0: the window around the macroblock itself was requested when the kernel started (it flies while
-    // the centre test runs); k = 1: re-centre on the first round's winner -- unless that is the macroblock's own
+    __device__ __forceinline__ void land() const { evx_mbar_wait(bar, *phase & 1u); ++*phase; }
+    // k = 0: the window around the macroblock itself was requested before the centre test (it flies while
+    // that runs); k = 1: re-centre on the first round's winner -- unless that is the macroblock's own
     // position, whose window is the one already here.
     __device__ __forceinline__ void operator()(int k, int cx, int cy, EvxWin &win) const
     {
-        if (k == 0) { evx_mbar_wait(bar, 0); return; }
+        if (k == 0) { land(); return; }
         if (cx - 16 == win.ox && cy - 16 == win.oy) return;
         __syncwarp();                                           // every lane is done reading the previous window
         if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         fetch(cx, cy);
         win.ox = cx - 16; win.oy = cy - 16; win.cox = win.ox >> 1; win.coy = win.oy >> 1;
-        evx_mbar_wait(bar, 1);
+        land();
     }
 };
 
-__global__ void __launch_bounds__(32, EVX_K2W_PER_SM) evx_inter_search(const __grid_constant__ EvxK2Params p)
+// One (macroblock, reference) search by one warp.  `win_mem` holds EVX_K2W_BYTES of 128-byte aligned shared memory,
+// `bar` an initialised mbarrier (count 1) whose completed phases `phase` counts.  Returns through `out` (lane 0 writes it).
+__device__ __forceinline__ void evx_k2_item(const CUtensorMap *maps3, const EvxPlanes &srcp, const EvxPlanes &refp, const EvxGeom &g,
+                                            int thr, int bx, int by, int ref, int lane, uint8_t *win_mem, uint64_t *bar, uint32_t &phase,
+                                            EvxInterResult *out, unsigned long long *counters, uint32_t stamp)
 {
-    extern __shared__ __align__(128) uint8_t smem[];
-    int16_t *wy = reinterpret_cast<int16_t *>(smem);
+    int16_t *wy = reinterpret_cast<int16_t *>(win_mem);
     int16_t *wu = wy + EVX_K2W_WIN * EVX_K2W_WIN;
     int16_t *wv = wu + EVX_K2W_CWIN * EVX_K2W_CWIN;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(wv + EVX_K2W_CWIN * EVX_K2W_CWIN);
-
-    const int lane = threadIdx.x, ref = blockIdx.z, bx = blockIdx.x, by = blockIdx.y + p.row0;
     const int px = bx * EVX_MB, py = by * EVX_MB;
-    const EvxGeom g = p.g;
-    EvxK2Stage stage = { &p.maps.m[ref * 3 + 0], &p.maps.m[ref * 3 + 1], &p.maps.m[ref * 3 + 2], wy, wu, wv, bar, lane };
-    if (lane == 0) evx_mbar_init(bar, 1);
-    __syncwarp();
+    EvxK2Stage stage = { maps3, maps3 + 1, maps3 + 2, wy, wu, wv, bar, &phase, lane };
+    __syncwarp();                                               // (a persistent warp: the previous item's window reads are over)
+    if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     stage.fetch(px, py);
 
     EvxLaneSrc src;
     EvxLaneBlock sb, centre;
-    evx_load_src_lane(p.src, g, px, py, lane, sb);
-    evx_load_src_lane(p.ref[ref], g, px, py, lane, centre);
+    evx_load_src_lane(srcp, g, px, py, lane, sb);
+    evx_load_src_lane(refp, g, px, py, lane, centre);
     evx_make_src(sb, src);
 
     EvxWin win;
@@ -434,18 +365,30 @@ __global__ void __launch_bounds__(32, EVX_K2W_PER_SM) evx_inter_search(const __g
 
     EvxSel s;
     uint32_t n_full, n_sub;
-    evx_inter_search_warp(win, src, centre, g, px, py, p.thr, lane, s, n_full, n_sub, stage);
-    if (n_full == 1) evx_mbar_wait(bar, 0);      // copy block: the window was never used, but it must have landed before this CTA's shared memory is released
+    evx_inter_search_warp(win, src, centre, g, px, py, thr, lane, s, n_full, n_sub, stage);
+    if (n_full == 1) stage.land();      // copy block: the window was never used, but it must have landed before its shared memory is reused or released
 
     if (lane == 0)
     {
-        EvxInterResult r;
-        r.desc = evx_desc_from_sel(s, 0, ref + 1, px, py, p.thr);
-        r.sad = s.sad; r.pad[0] = r.pad[1] = r.pad[2] = 0;
-        p.results[(size_t) ref * g.mbw * g.mbh + (size_t) by * g.mbw + bx] = r;
-        atomicAdd(&p.counters[0], (unsigned long long) n_full);
-        atomicAdd(&p.counters[1], (unsigned long long) n_sub);
+        const EvxDesc d = evx_desc_from_sel(s, 0, ref + 1, px, py, thr);
+        *reinterpret_cast<int4 *>(&out->desc) = make_int4((int) d.w0, (int) d.w1, (int) d.w2, (int) d.w3);
+        out->sad = s.sad;
+        if (stamp) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(&out->stamp), "r"(stamp) : "memory");
+        else out->stamp = 0u;
+        atomicAdd(&counters[0], (unsigned long long) n_full);
+        atomicAdd(&counters[1], (unsigned long long) n_sub);
     }
+}
+
+__global__ void __launch_bounds__(32, EVX_K2W_PER_SM) evx_inter_search(const __grid_constant__ EvxK2Params p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + EVX_K2W_BYTES);
+    const int lane = threadIdx.x, ref = blockIdx.z, bx = blockIdx.x, by = blockIdx.y + p.row0;
+    if (lane == 0) evx_mbar_init(bar, 1);
+    uint32_t phase = 0;
+    evx_k2_item(&p.maps.m[ref * 3], p.src, p.ref[ref], p.g, p.thr, bx, by, ref, lane, smem, bar, phase,
+                p.results + (size_t) ref * p.g.mbw * p.g.mbh + (size_t) by * p.g.mbw + bx, p.counters, 0u);
 }
 
 // ------------------------------------------------------------------ K3 / K5 shared: transform + reconstruction of one macroblock
@@ -630,23 +573,60 @@ __device__ __forceinline__ int evx_ld_relaxed(const int *p)
     return v;
 }
 
-__device__ __forceinline__ void evx_wait_ge(const int *p, int need)
+// Every device-side wait on a counter another CTA advances is BOUNDED.  By construction none can last (tickets are
+// claimed in dependency order, and a frame kernel only waits for kernels launched before it: evx_wavefront.cuh), but a
+// wait that did -- a logic error, a foreign context holding the device for seconds -- would otherwise hang the GPU until
+// the process is killed.  After `budget_ns` (evxgpu.cu: 4 s, EVXGPU_WAIT_BUDGET_MS) the waiter records what it was
+// waiting for in mapped host memory and traps: the launch fails, every later call of the process reports the error.
+struct EvxWaitCtx { unsigned long long budget_ns; unsigned int *diag; };
+
+__device__ __forceinline__ unsigned long long evx_globaltimer()
 {
-    while (evx_ld_relaxed(p) < need) __nanosleep(100);
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __noinline__ void evx_wait_expired(const EvxWaitCtx &w, unsigned int what, unsigned int a, unsigned int b, unsigned int c)
+{
+    if (w.diag)
+    {
+        volatile unsigned int *d = w.diag;
+        d[1] = a; d[2] = b; d[3] = c; d[0] = what;
+        __threadfence_system();
+    }
+    __trap();
+}
+
+// `poll()` returns true when the wait is over; `ns` is the back-off between polls.  The timer is read every 32nd poll.
+#define EVX_BOUNDED_WAIT(w, cond, ns, what, a, b, c)                                                           \
+    do {                                                                                                       \
+        unsigned long long t0_ = 0; unsigned int n_ = 0;                                                       \
+        while (!(cond))                                                                                        \
+        {                                                                                                      \
+            __nanosleep(ns);                                                                                   \
+            if ((++n_ & 31u) == 0u && (w).budget_ns)                                                           \
+            {                                                                                                  \
+                const unsigned long long t_ = evx_globaltimer();                                               \
+                if (!t0_) t0_ = t_;                                                                            \
+                else if (t_ - t0_ > (w).budget_ns) evx_wait_expired((w), (what), (a), (b), (c));               \
+            }                                                                                                  \
+        }                                                                                                      \
+    } while (0)
+
+__device__ __forceinline__ void evx_wait_ge(const int *p, int need, const EvxWaitCtx &w)
+{
+    EVX_BOUNDED_WAIT(w, evx_ld_relaxed(p) >= need, 100, 1u, (unsigned int) need, (unsigned int) evx_ld_relaxed(p), 0u);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 // The same for a counter that advances in known steps (a row's progress): far from the target the poll
 // backs off (the value cannot arrive sooner than one macroblock time per missing step), next to it the
 // poll is tight.
-__device__ __forceinline__ void evx_wait_ge_far(const int *p, int need)
+__device__ __forceinline__ void evx_wait_ge_far(const int *p, int need, const EvxWaitCtx &w)
 {
-    for (;;)
-    {
-        const int have = evx_ld_relaxed(p);
-        if (have >= need) break;
-        __nanosleep(need - have > 2 ? 2000 : (need - have > 1 ? 400 : 40));
-    }
+    int have;
+    EVX_BOUNDED_WAIT(w, (have = evx_ld_relaxed(p)) >= need, (need - have > 2 ? 2000 : (need - have > 1 ? 400 : 40)), 2u, (unsigned int) need, (unsigned int) have, 0u);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
@@ -665,24 +645,32 @@ struct EvxK3Params
     int R, linear;
     int frame_type, quality;
     uint32_t frame_index;
-    const EvxInterResult *inter;   // [R-1][nmb], valid when frame_type == 1
+    EvxInterResult *inter;         // [R-1][nmb], valid when frame_type == 1 (written by this kernel's search role when fuse_k2)
     EvxDesc *table;                // block_table
     int16_t *records;              // [nmb][384] coefficient records, slot = macroblock index
     int *row_records;              // [mbh] non-copy macroblocks per row (for evx_pack_records)
     int *sync;                     // [0] row ticket, [1] total records, [2..] progress[mbh]
-    // frames of one stream overlapping on the device (evxgpu.cu, frame overlap): monotonic counters, value = epoch + count
-    unsigned int *rows_done;       // this frame: epoch + complete macroblock rows (NULL: not published)
-    unsigned int rows_base;
-    const unsigned int *gate_k2;   // this frame's inter search: epoch + macroblock rows searched (NULL: the search has finished)
-    unsigned int gate_k2_base;
-    const unsigned int *gate_final;// previous frame: epoch + deblocked bands (NULL: the previous frame has finished)
-    unsigned int gate_final_base;
-    int band_rows, nbands;
+    // Frames of one stream pipelined on the device (evxgpu.cu, submit_pipelined): the inter search and the deblocking
+    // filter run as ROLES of this kernel, and consecutive frames are gated macroblock by macroblock through per-row
+    // counters in device memory.  Cross-frame counters hold frame base + count and are compared cyclically
+    // ((int)(value - need) >= 0), so a slot's counters are never zeroed between the frames that reuse it.
+    int fuse_k2;                   // 1: macroblock rows of the inter search are tickets of this kernel (results carry `stamp`)
+    int fuse_dbk;                  // 1: every row CTA deblocks behind the wavefront and publishes dbk[]
+    int deblocking;                // EVX_ENABLE_DEBLOCKING (with fuse_dbk and no deblocking only the counters advance)
+    int thr;                       // (quality >> 2) + 1
+    uint32_t stamp;                // this frame's token in EvxInterResult::stamp (non-zero)
+    unsigned int *dbk;             // this frame: [mbh] base + tile columns of tile row Y that are filtered (see evx_wavefront.cuh)
+    unsigned int dbk_base;
+    const unsigned int *prev_dbk;  // the previous frame of the stream (NULL: no predecessor)
+    unsigned int prev_base;
+    unsigned int *started;         // takes dbk_base when the first CTA of this kernel runs (the next frame is launched behind it)
+    EvxWaitCtx wait;
     unsigned long long *counters;
     long long *prof;               // optional [mbh][6] per-row phase cycle sums (NULL in production)
     // for K8 (evx_bins.cuh): what serialize_slice's deltas and DC predictions refer to
     int *prev_motion, *prev_coded; // [nmb] previous macroblock OF THE SAME ROW with a motion vector / with coefficients, or -1
     int *row_last;                 // [2][mbh] last such macroblock of each row, or -1
+    EvxK2Maps maps;                // search windows of the inter-search role: [reference][Y,U,V], 48x48 / 24x24 boxes
 };
 
 // ------------------------------------------------------------------ K7: pack the non-copy macroblocks' records densely, raster order
@@ -758,6 +746,7 @@ struct EvxK5Params
     int *sync;                     // [0] ticket
     int *done;                     // [nmb] 1 once the macroblock is reconstructed
     int *readers;                  // [nmb] raster-earlier blocks that have yet to read this block's stale samples
+    EvxWaitCtx wait;
 };
 
 // source rectangle of a block's prediction, as the macroblocks it touches
@@ -835,7 +824,7 @@ __global__ void __launch_bounds__(EVX_K5_THREADS) evx_decode_recon(const __grid_
                 for (int x = r.bx0; x <= r.bx1; ++x)
                 {
                     const int m = y * g.mbw + x;
-                    if (m < mb) evx_wait_ge(p.done + m, 1);
+                    if (m < mb) evx_wait_ge(p.done + m, 1, p.wait);
                 }
             __syncthreads();
         }
@@ -854,7 +843,7 @@ __global__ void __launch_bounds__(EVX_K5_THREADS) evx_decode_recon(const __grid_
                 }
             }
             // and nobody may still need the samples we are about to overwrite
-            while (evx_ld_relaxed(p.readers + mb) > 0) __nanosleep(100);
+            EVX_BOUNDED_WAIT(p.wait, evx_ld_relaxed(p.readers + mb) <= 0, 100, 3u, (unsigned int) mb, 0u, 0u);
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
         __syncthreads();
@@ -918,21 +907,16 @@ __device__ __forceinline__ void evx_filter8(int s[8], int qp, int strength, bool
 struct EvxK4Params
 {
     EvxPlanes pl; EvxGeom g; const EvxDesc *table;
-    int ty0[2], tyn[2];           // first tile row and number of tile rows of this launch, [0] luma, [1] chroma (a frame may be filtered band by band)
 };
 
-__global__ void __launch_bounds__(128) evx_deblock(const __grid_constant__ EvxK4Params p)
+// One 8x8 tile of plane `comp` centred on the grid crossing (i, j) = (8 tx, 8 ty), 0 <= tx <= w/8, 0 <= ty <= h/8.
+__device__ __forceinline__ void evx_deblock_tile(const EvxPlanes &pl, const EvxGeom &g, const EvxDesc *table, int comp, int tx, int ty)
 {
-    // blockIdx.z: plane; tiles enumerated with i = 8*tx (0..w), j = 8*ty (0..h)
-    const int comp = blockIdx.z;
     const bool luma = comp == 0;
-    const int w = luma ? p.g.w : p.g.w >> 1, h = luma ? p.g.h : p.g.h >> 1;
+    const int w = luma ? g.w : g.w >> 1, h = luma ? g.h : g.h >> 1;
     const int mbs = luma ? 16 : 8;
     const int wb = w / mbs;
-    int16_t *img = comp == 0 ? p.pl.y : (comp == 1 ? p.pl.u : p.pl.v);
-    if ((int) blockIdx.y >= p.tyn[luma ? 0 : 1]) return;
-    const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = p.ty0[luma ? 0 : 1] + (int) blockIdx.y;
-    if (tx > w / 8 || ty > h / 8) return;
+    int16_t *img = comp == 0 ? pl.y : (comp == 1 ? pl.u : pl.v);
     const int i = tx * 8, j = ty * 8;
     const bool has_l = i > 0, has_r = i < w, has_t = j > 0, has_b = j < h;
 
@@ -952,7 +936,7 @@ __global__ void __launch_bounds__(128) evx_deblock(const __grid_constant__ EvxK4
     if (has_l && has_r && has_t)
     {
         int brow = ((j - 8) / mbs) * wb;
-        evx_edge_params(p.table, (i - 1) / mbs + brow, i / mbs + brow, qp, st);
+        evx_edge_params(table, (i - 1) / mbs + brow, i / mbs + brow, qp, st);
         if (st)
         {
 #pragma unroll
@@ -967,7 +951,7 @@ __global__ void __launch_bounds__(128) evx_deblock(const __grid_constant__ EvxK4
         {
             if (half == 0 ? !has_l : !has_r) continue;
             int col = half == 0 ? i - 8 : i;
-            evx_edge_params(p.table, col / mbs + ((j - 1) / mbs) * wb, col / mbs + (j / mbs) * wb, qp, st);
+            evx_edge_params(table, col / mbs + ((j - 1) / mbs) * wb, col / mbs + (j / mbs) * wb, qp, st);
             if (!st) continue;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -985,7 +969,7 @@ __global__ void __launch_bounds__(128) evx_deblock(const __grid_constant__ EvxK4
     if (has_l && has_r && has_b)
     {
         int brow = (j / mbs) * wb;
-        evx_edge_params(p.table, (i - 1) / mbs + brow, i / mbs + brow, qp, st);
+        evx_edge_params(table, (i - 1) / mbs + brow, i / mbs + brow, qp, st);
         if (st)
         {
 #pragma unroll
@@ -999,4 +983,14 @@ __global__ void __launch_bounds__(128) evx_deblock(const __grid_constant__ EvxK4
         if (rv && has_l) *reinterpret_cast<uint2 *>(img + (size_t) (j - 4 + r) * w + i - 4) = make_uint2(evx_pack16(t[r][0], t[r][1]), evx_pack16(t[r][2], t[r][3]));
         if (rv && has_r) *reinterpret_cast<uint2 *>(img + (size_t) (j - 4 + r) * w + i) = make_uint2(evx_pack16(t[r][4], t[r][5]), evx_pack16(t[r][6], t[r][7]));
     }
+}
+
+// the whole frame, one thread per tile: blockIdx.z = plane
+__global__ void __launch_bounds__(128) evx_deblock(const __grid_constant__ EvxK4Params p)
+{
+    const int comp = blockIdx.z;
+    const int w = comp == 0 ? p.g.w : p.g.w >> 1, h = comp == 0 ? p.g.h : p.g.h >> 1;
+    const int tx = blockIdx.x * blockDim.x + threadIdx.x, ty = (int) blockIdx.y;
+    if (tx > w / 8 || ty > h / 8) return;
+    evx_deblock_tile(p.pl, p.g, p.table, comp, tx, ty);
 }

@@ -23,6 +23,28 @@
 // The left-neighbour dependency is thus inside the CTA (its reconstruction is written straight
 // into the window), and the inter-row latency (flag + L2 round trip) is paid once per row
 // instead of once per macroblock: frame time ~ (W + 3(H-1)) * T_mb + (H-1) * latency.
+//
+// THE FRAME KERNEL.  With fuse_k2 / fuse_dbk (frames of a stream pipelined on the device, evxgpu.cu
+// submit_pipelined) the same kernel also carries the frame's inter search and its deblocking filter, so that a
+// frame is ONE launch whose CTAs wait for nothing but (a) tickets of the same kernel claimed earlier and (b) the
+// previous frame's kernel, which was launched -- and has started -- before this one.  No wait can point at work
+// that still needs an SM slot this kernel's waiting CTAs hold, whoever else uses the device:
+//   * tickets, claimed in this order:  S(0) S(1) W(0) S(2) W(1) ... S(H-1) W(H-3) W(H-2) W(H-1), where S(r) is the
+//     inter search of macroblock row r (all ten warps of the CTA pull (macroblock, reference) items, evx_k2_item;
+//     each result is stamped) and W(r) the wavefront row r, whose block loader waits for the stamps of the
+//     macroblock it stages;
+//   * deblocking follows the wavefront inside the row CTAs: the sweep decomposes into independent 8x8 tiles
+//     (evx_kernels.cuh, K4); the tiles of macroblock (X, Y) -- luma crossings {2X, 2X+1} x {2Y, 2Y+1}, chroma (X, Y),
+//     plus the frame's right / bottom border tiles in the last column / row -- touch macroblocks (X-1..X, Y-1..Y),
+//     whose unfiltered samples the intra search reads last from macroblock (X+2, Y+3).  So the block loader of row
+//     r filters, four macroblock columns at a time, tile row r-3 (the last row also H-3 .. H-1) up to column x-2
+//     once macroblock x of its own row is complete, and publishes dbk[Y] = base + filtered tile columns;
+//   * the NEXT frame reads this one as a reference around (bx, by): samples of macroblocks (bx-2..bx+2, by-2..by+2),
+//     final once the tiles of columns <= bx+3 in tile rows by-2 .. by+3 are done.  Its search items (and, in an intra
+//     frame, its block loaders) wait for dbk[by-2 .. by+3] >= min(bx+4, W), six lanes polling one row each.  That
+//     one rule also covers the write-after-read side (a frame overwrites the ring slot of frame n-R, which frame
+//     n-1 still searches) and the stale samples the intra search reads from that slot: every frame
+//     trails its predecessor by the same ~23 wavefront steps at every macroblock, and so transitively all older ones.
 #pragma once
 
 #include "evx_kernels.cuh"
@@ -62,9 +84,21 @@ struct EvxK3Smem
     int4 cand[2][16];                         // sub-pel tests: {sad, mad, 0, legal}
     int2 cand2[2][16];                        // full-pel rounds: raw {sad, mad} per cell
     uint64_t full[2], fullb[2], full2[2], empty[2];   // full: block data; fullb: window columns <= n+1; full2: column n+2
-    int row;
     int last_motion, last_coded;              // K8 bookkeeping (thread 0)
 };
+
+// the CTA's current ticket; the search role's per-warp windows share the wavefront role's shared memory
+struct EvxFrameCtl { int role, row; };
+enum { EVX_ROLE_WAVEFRONT = 0, EVX_ROLE_SEARCH = 1, EVX_ROLE_DONE = 2 };
+#define EVX_K3_WARPS (EVX_K3_NT / 32)
+struct EvxK2RoleSmem
+{
+    uint8_t win[EVX_K3_WARPS][EVX_K2W_BYTES];      // 128-byte aligned TMA destinations (6912 = 54 x 128)
+    uint64_t bar[EVX_K3_WARPS];
+    int next;                                      // next (macroblock, reference) item of the row
+};
+#define EVX_FRAME_CTL_BYTES 128
+#define EVX_FRAME_SMEM (EVX_FRAME_CTL_BYTES + (sizeof(EvxK3Smem) > sizeof(EvxK2RoleSmem) ? sizeof(EvxK3Smem) : sizeof(EvxK2RoleSmem)))
 
 __device__ __forceinline__ void evx_mbar_arrive(uint64_t *bar)
 {
@@ -76,6 +110,50 @@ __device__ __forceinline__ void evx_compute_sync() { asm volatile("bar.sync 1, %
 // int16 sample of the ring window
 __device__ __forceinline__ int evx_ring_y(const EvxK3Smem &S, int x, int wrow) { return reinterpret_cast<const int16_t *>(S.wy)[wrow * (EVX_RING_PWY * 2) + (x & 127)]; }
 __device__ __forceinline__ int evx_ring_c(const uint32_t *pl, int cx, int wrow) { return reinterpret_cast<const int16_t *>(pl)[wrow * (EVX_RING_PWC * 2) + (cx & 63)]; }
+
+// ---------------------------------------------------------------- the previous frame, and the search role
+
+// Waits until the previous frame of the stream is FINAL (reconstructed and deblocked) in every sample macroblock
+// (bx, by) of this frame reads as a reference: six lanes poll tile rows by-2 .. by+3 (header comment).
+__device__ __forceinline__ void evx_gate_prev(const EvxK3Params &p, int bx, int by, int lane)
+{
+    if (!p.prev_dbk) return;
+    const unsigned int need = p.prev_base + (unsigned int) min(bx + 4, p.g.mbw);
+    const int row = max(0, min(by + 3 - min(lane, 5), p.g.mbh - 1));
+    unsigned int v;
+    EVX_BOUNDED_WAIT(p.wait, (v = evx_ld_relaxed_u32(p.prev_dbk + row), __all_sync(0xFFFFFFFFu, (int) (v - need) >= 0)), 200, 4u, need, v, (unsigned int) row);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+// S(by): the inter search of one macroblock row; every warp pulls (macroblock, reference) items in column order
+__device__ __noinline__ void evx_k2_role(EvxK2RoleSmem &K, const EvxK3Params &p, int by, int tid)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nref = p.R - 1, items = p.g.mbw * nref, nmb = p.g.mbw * p.g.mbh;
+    uint32_t phase = 0;
+    for (;;)
+    {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(&K.next, 1);
+        it = __shfl_sync(0xFFFFFFFFu, it, 0);
+        if (it >= items) break;
+        const int bx = it / nref, ref = it - bx * nref;
+        evx_gate_prev(p, bx, by, lane);
+        const int rslot = (int) ((p.frame_index + (uint32_t) p.R - (uint32_t) (ref + 1)) % (uint32_t) p.R);       // common.cpp:192-195
+        evx_k2_item(&p.maps.m[ref * 3], p.src, p.ring[rslot], p.g, p.thr, bx, by, ref, lane, K.win[warp], &K.bar[warp], phase,
+                    p.inter + (size_t) ref * nmb + (size_t) by * p.g.mbw + bx, p.counters, p.stamp);
+    }
+}
+
+// A call, not inlined: the tile's 64 samples live in registers, and inlined into the frame kernel they would raise the
+// pressure of every other path of it (spills in the two-CTAs-per-SM budget); as a function the cost stays in here.
+// (arguments by value: a reference to the caller's locals would put those on its stack)
+__device__ __noinline__ void evx_deblock_tile_call(int16_t *y, int16_t *u, int16_t *v, int w, int h, const EvxDesc *table, int comp, int tx, int ty)
+{
+    EvxPlanes pl; pl.y = y; pl.u = u; pl.v = v;
+    EvxGeom g; g.w = w; g.h = h; g.vw = w; g.vh = h; g.mbw = w >> 4; g.mbh = h >> 4;
+    evx_deblock_tile(pl, g, table, comp, tx, ty);
+}
 
 // ---------------------------------------------------------------- block loader warp
 
@@ -95,11 +173,47 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
         evx_mbar_wait(&S.empty[m & 1], (uint32_t) ((m >> 1) & 1));
         if (lane == 0) evx_st_release(progress + by, m + 1);     // release is cumulative over what this thread observed through the barrier
     };
+    // Deblocking behind the wavefront (header comment): this row's CTA owns tile row by-3, the last row also the
+    // tile rows below it.  deblock_to(cnt) filters tile columns [dbk_done, cnt) of those rows -- one tile per lane and
+    // pass -- and publishes the count.  Tile column X may go once macroblock min(X+2, W-1) of THIS row is complete.
+    const int ylo = max(0, by - 3), yhi = by == g.mbh - 1 ? g.mbh - 1 : by - 3;
+    int dbk_done = 0;
+    auto deblock_to = [&](int cnt)
+    {
+        if (yhi < 0 || cnt <= dbk_done) return;
+        const int x0 = dbk_done, last = cnt == g.mbw ? 1 : 0;
+        if (p.deblocking)
+        {
+            const int nlx = 2 * (cnt - x0) + last, ncx = (cnt - x0) + last;
+            for (int Y = ylo; Y <= yhi; ++Y)
+            {
+                const int bot = Y == g.mbh - 1 ? 1 : 0;
+                const int nl = nlx * (2 + bot), nc = ncx * (1 + bot);
+                for (int k = lane; k < nl + 2 * nc; k += 32)
+                {
+                    if (k < nl) evx_deblock_tile_call(cur.y, cur.u, cur.v, g.w, g.h, p.table, 0, 2 * x0 + k % nlx, 2 * Y + k / nlx);
+                    else { const int c = (k - nl) % nc; evx_deblock_tile_call(cur.y, cur.u, cur.v, g.w, g.h, p.table, 1 + (k - nl) / nc, x0 + c % ncx, Y + c / ncx); }
+                }
+            }
+        }
+        dbk_done = cnt;
+        __syncwarp();
+        if (lane == 0)
+            for (int Y = ylo; Y <= yhi; ++Y)
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.dbk + Y), "r"(p.dbk_base + (unsigned int) cnt) : "memory");
+    };
 
     for (int n = 0; n < g.mbw; ++n)
     {
         const int slot = n & 1, px = n * EVX_MB, mb = by * g.mbw + n;
-        if (n >= 2) publish(n - 2);          // also frees this slot's staging buffers
+        if (n >= 2)
+        {
+            publish(n - 2);          // also frees this slot's staging buffers
+            if (p.fuse_dbk && n >= 4 && ((n - 4) & 3) == 3) deblock_to(n - 3);      // macroblock n-2 complete: tile columns <= n-4
+        }
+        // An intra frame has no search whose items wait for the previous frame, but it overwrites the ring slot frames
+        // before it still read and reads that slot's stale samples: the same gate, taken here.
+        if (!nref) evx_gate_prev(p, n, by, lane);
 
         // source macroblock -> block-major
         {
@@ -115,6 +229,12 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
         }
         // K2's candidates and their predictions (encode.cpp:110-141), so that classification
         // never waits on global memory
+        if (nref && p.fuse_k2)
+        {   // the search role's results of this macroblock, one lane per reference (their items passed the gate on the previous frame)
+            const uint32_t *st = &p.inter[(size_t) min(lane, nref - 1) * nmb + mb].stamp;
+            EVX_BOUNDED_WAIT(p.wait, __all_sync(0xFFFFFFFFu, evx_ld_relaxed_u32(st) == p.stamp), 100, 5u, (unsigned int) mb, p.stamp, 0u);
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        }
         for (int r = 0; r < nref; ++r)
         {
             const EvxInterResult *ir = p.inter + (size_t) r * nmb + mb;
@@ -172,6 +292,7 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
         if (lane == 0) evx_mbar_arrive(&S.full[slot]);
     }
     for (int m = max(0, g.mbw - 2); m < g.mbw; ++m) publish(m);
+    if (p.fuse_dbk) deblock_to(g.mbw);
 }
 
 // ---------------------------------------------------------------- column loader warp
@@ -236,7 +357,7 @@ __device__ __forceinline__ void evx_k3_column_loader(EvxK3Smem &S, const EvxK3Pa
         if (c >= 3) evx_mbar_wait(&S.empty[(c - 3) & 1], (uint32_t) (((c - 3) >> 1) & 1));
         if (by > 0)
         {
-            if (lane == 0) evx_wait_ge_far(progress + by - 1, min(c, g.mbw - 1) + 1);
+            if (lane == 0) evx_wait_ge_far(progress + by - 1, min(c, g.mbw - 1) + 1, p.wait);
             __syncwarp();
             if (c < g.mbw) pull_column(c);
         }
@@ -664,65 +785,78 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     }
 }
 
-// Two register budgets of the same kernel: <2> keeps two CTAs per SM (96 registers) -- what many streams sharing the
-// device need (16 streams: 2 642 against 2 191 frames/s); <1> lets ptxas have the 168 registers it asks for, 2.5 % faster
-// per frame (1.735 -> 1.691 ms at 1080p), used while the stream is the only encoder on the device.
+// Two register budgets of the same kernel: <2> keeps two CTAs per SM (96 registers) -- what several frames or streams
+// sharing the device need; <1> lets ptxas have the 168 registers it asks for, 2.5 % faster per frame alone
+// (1.735 -> 1.691 ms at 1080p), used for a frame that has the device to itself (the stand-alone launch sequence).
 template <int MINCTAS>
 __global__ void __launch_bounds__(EVX_K3_NT, MINCTAS) evx_wavefront(const __grid_constant__ EvxK3Params p)
 {
-    extern __shared__ __align__(16) uint8_t evx_k3_smem[];
-    EvxK3Smem &S = *reinterpret_cast<EvxK3Smem *>(evx_k3_smem);
+    extern __shared__ __align__(128) uint8_t evx_k3_smem[];
+    EvxFrameCtl &C = *reinterpret_cast<EvxFrameCtl *>(evx_k3_smem);
+    EvxK3Smem &S = *reinterpret_cast<EvxK3Smem *>(evx_k3_smem + EVX_FRAME_CTL_BYTES);
+    EvxK2RoleSmem &K = *reinterpret_cast<EvxK2RoleSmem *>(evx_k3_smem + EVX_FRAME_CTL_BYTES);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = p.g.mbh;
 
-    evx_init_tables(S.sh, tid, EVX_K3_NT);
-    // Persistent over rows: row r can only be active during macroblock steps [3r, 3r + W), so at most
-    // ceil(W/3) rows are in flight at any time and that many CTAs carry the whole frame (the host sizes the
-    // grid so); a CTA that finished its row claims the next unclaimed one.  Rows are claimed in order: a
-    // CTA only ever waits on rows claimed before its own, by CTAs that are running.
-    for (bool first = true;; first = false)
+    if (tid == 0 && p.started) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.started), "r"(p.dbk_base) : "memory");
+    // Persistent over tickets.  Wavefront rows: row r can only be active during macroblock steps [3r, 3r + W), so at
+    // most ceil(W/3) rows are in flight at any time and about that many CTAs carry the whole frame (the host sizes the
+    // grid so); a CTA that finished its ticket claims the next one.  Tickets are claimed in dependency order (header
+    // comment): a CTA only ever waits on tickets claimed before its own, by CTAs that are running.
+    const bool search = p.fuse_k2 && p.frame_type == 1;
+    const int lead = search ? min(2, H) : 0;
+    bool tables = false;
+    for (;;)
     {
         if (tid == 0)
         {
-            S.row = atomicAdd(&p.sync[0], 1);
-            auto rearm = [&](uint64_t *bar)
+            const int t = atomicAdd(&p.sync[0], 1);
+            int role = EVX_ROLE_DONE, row = 0;
+            if (!search) { if (t < H) { role = EVX_ROLE_WAVEFRONT; row = t; } }
+            else if (t < lead) { role = EVX_ROLE_SEARCH; row = t; }
+            else
             {
-                if (!first) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(evx_smem_addr(bar)) : "memory");
-                evx_mbar_init(bar, 1);
-            };
-            rearm(&S.full[0]); rearm(&S.full[1]); rearm(&S.fullb[0]); rearm(&S.fullb[1]);
-            rearm(&S.full2[0]); rearm(&S.full2[1]); rearm(&S.empty[0]); rearm(&S.empty[1]);
-            // Frame overlap: this row may start once the previous frame is final (reconstructed AND deblocked) in every
-            // row this one reads as a reference and, with a ring of two, overwrites; and once this frame's inter search has
-            // reached it.  Both counters only grow, and whoever advances them never waits for this kernel.
-            const int row = S.row;
-            if (row < p.g.mbh)
+                const int j = t - lead, pairs = H - lead;
+                if (j < 2 * pairs) { role = (j & 1) ? EVX_ROLE_SEARCH : EVX_ROLE_WAVEFRONT; row = (j & 1) ? lead + (j >> 1) : (j >> 1); }
+                else if (j - 2 * pairs < lead) { role = EVX_ROLE_WAVEFRONT; row = pairs + (j - 2 * pairs); }
+            }
+            C.role = role; C.row = row;
+            if (role == EVX_ROLE_WAVEFRONT)
             {
-                if (p.gate_final)
-                {
-                    const unsigned int need = p.gate_final_base + (unsigned int) min(row / p.band_rows + 2, p.nbands);
-                    while ((int) (evx_ld_relaxed_u32(p.gate_final) - need) < 0) __nanosleep(500);
-                }
-                if (p.gate_k2)
-                {
-                    const unsigned int need = p.gate_k2_base + (unsigned int) row + 1u;
-                    while ((int) (evx_ld_relaxed_u32(p.gate_k2) - need) < 0) __nanosleep(200);
-                }
-                if (p.gate_final || p.gate_k2) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                evx_mbar_init(&S.full[0], 1); evx_mbar_init(&S.full[1], 1); evx_mbar_init(&S.fullb[0], 1); evx_mbar_init(&S.fullb[1], 1);
+                evx_mbar_init(&S.full2[0], 1); evx_mbar_init(&S.full2[1], 1); evx_mbar_init(&S.empty[0], 1); evx_mbar_init(&S.empty[1], 1);
+            }
+            else if (role == EVX_ROLE_SEARCH)
+            {
+                for (int w = 0; w < EVX_K3_WARPS; ++w) evx_mbar_init(&K.bar[w], 1);
+                K.next = 0;
             }
         }
         __syncthreads();
-        const int by = S.row;
-        if (by >= p.g.mbh) return;
-
-        if (warp < EVX_K3_CW) evx_k3_compute(S, p, by, tid);
-        else if (warp == EVX_K3_CW) evx_k3_block_loader(S, p, by, lane);
-        else if (warp == EVX_K3_CW + 1) evx_k3_column_loader(S, p, by, lane);
-        __syncthreads();      // every role has left the row: its barriers and S.row may be reused
-        if (tid == 0 && p.rows_done)
-        {   // rows complete in order (the last macroblock of a row needs the last one of the row above), but their
-            // CTAs reach this line in any order: the counter takes the maximum
-            __threadfence();
-            atomicMax(p.rows_done, p.rows_base + (unsigned int) by + 1u);
+        const int role = C.role, by = C.row;
+        if (role == EVX_ROLE_DONE) return;
+        if (role == EVX_ROLE_SEARCH)
+        {
+            evx_k2_role(K, p, by, tid);
+            tables = false;                  // the windows lie over the wavefront role's tables
+        }
+        else
+        {
+            if (!tables) { evx_init_tables(S.sh, tid, EVX_K3_NT); tables = true; __syncthreads(); }
+            if (warp < EVX_K3_CW) evx_k3_compute(S, p, by, tid);
+            else if (warp == EVX_K3_CW) evx_k3_block_loader(S, p, by, lane);
+            else if (warp == EVX_K3_CW + 1) evx_k3_column_loader(S, p, by, lane);
+        }
+        __syncthreads();      // every warp has left the ticket: its barriers and shared memory may be reused
+        if (tid == 0)
+        {
+            auto inval = [](uint64_t *bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(evx_smem_addr(bar)) : "memory"); };
+            if (role == EVX_ROLE_WAVEFRONT)
+            {
+                inval(&S.full[0]); inval(&S.full[1]); inval(&S.fullb[0]); inval(&S.fullb[1]);
+                inval(&S.full2[0]); inval(&S.full2[1]); inval(&S.empty[0]); inval(&S.empty[1]);
+            }
+            else for (int w = 0; w < EVX_K3_WARPS; ++w) inval(&K.bar[w]);
         }
     }
 }

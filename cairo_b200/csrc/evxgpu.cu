@@ -45,18 +45,12 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 typedef CUresult (*stream_memop_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-static stream_memop_fn g_wait32 = NULL, g_write32 = NULL;
-// Encoders with frame overlap per device, process-wide.  Overlap pays when a stream has the device (mostly) to itself;
-// many streams fill the device by themselves, and their overlapped kernels would only compete (measured: 8 streams
-// 2 475 -> 1 321 frames/s).  So at most two encoders per device overlap their frames, the others run frame after frame.
+static stream_memop_fn g_wait32 = NULL;
 #include <atomic>
-static std::atomic<int> g_overlap_live[64];
-enum { EVX_MAX_OVERLAP_ENCODERS = 2 };
-enum { EVX_MAX_SLOTS = 3, EVX_DEFAULT_SLOTS = 3 };           // frame slots a handle may own (two are in use unless EVXGPU_FRAME_SLOTS=3)
-// Encoders (handles that have encoded a frame) alive per device, process-wide: a stream overlaps its frames only while it
-// is the only encoder on the device.  Next to other encoders' kernels the band kernels of an overlapped stream can wait
-// for SM space while the next frame's resident wavefront CTAs poll for them (measured: hangs and stale reads with five
-// more encoders hammering the device), and many streams fill the device without overlap anyway.
+enum { EVX_MAX_SLOTS = 8, EVX_DEFAULT_SLOTS = 6 };           // frame slots a handle may own (evxgpu_config::frame_slots, EVXGPU_FRAME_SLOTS)
+// Encoders (handles that have encoded a frame) alive per device, process-wide.  Only a tuning hint: a stand-alone
+// wavefront launch takes the larger register budget while the handle is the device's only encoder.  Nothing about
+// correctness or progress depends on it (frames of any number of streams and processes may share the device).
 static std::atomic<int> g_encoders_live[64];
 
 struct evxgpu_handle
@@ -84,9 +78,7 @@ struct evxgpu_handle
     int *d_sync;
     int *d_done;                      // decoder dependency tracking: done[nmb] followed by readers[nmb]
     unsigned long long *d_counters;
-    CUtensorMap maps[8][3];         // tile kernel boxes
-    CUtensorMap maps_w[8][3];       // one-warp-per-macroblock kernel boxes
-    bool k2_tile;                   // EVXGPU_K2=tile selects the tile kernel (measurements)
+    CUtensorMap maps_w[8][3];       // search windows of every ring slot: 48x48 luma / 24x24 chroma boxes
 
     // pinned host staging
     EvxDesc *h_table;
@@ -105,6 +97,7 @@ struct evxgpu_handle
     bool pending_encode, pending_decode;
     int wave_grid;
     int enc_grid;                   // persistent CTAs of the encoder's wavefront kernel
+    int k2_ctas;                    // frame kernel: CTAs on top of enc_grid for the search rows that run ahead of the wavefront
     long long *d_prof;
 
     // K8: the slice as a bin string (evx_bins.cuh)
@@ -123,26 +116,29 @@ struct evxgpu_handle
     cudaEvent_t ev_out[EVX_MAX_SLOTS];
     bool pending_bins[EVX_MAX_SLOTS];
     uint64_t d2h_bytes[EVX_MAX_SLOTS]; // device-to-host bytes of the slot's frame
-    // Frame overlap (on unless EVXGPU_FRAME_OVERLAP=0, bin-only output): the frame slots (nslots: 3, or 2) own their per-frame device state and
-    // three streams each, and consecutive frames of the stream run concurrently, gated row by row through counters in
-    // device memory (stream memory operations on the host side, polls in the wavefront kernel).  See submit_overlap.
+    uint32_t bins_dirty_bits[EVX_MAX_SLOTS];   // how much of d_bins the slot's last frame wrote (the next frame zeroes that much)
+    // Frame pipeline (bin-only output, unless EVXGPU_FRAME_OVERLAP=0): nslots frame slots own their per-frame device
+    // state and a stream each; every frame is ONE launch of the frame kernel (evx_wavefront.cuh: search role, wavefront
+    // rows, deblocking behind the wavefront) and consecutive frames run concurrently, gated macroblock by macroblock
+    // through per-row counters in device memory.  See submit_pipelined.
     bool overlap;                   // the machinery exists (slots, streams, counters)
-    bool overlap_on;                // and the frames in flight use it (decided whenever nothing is in flight)
     bool is_encoder;                // counted in g_encoders_live
     struct frame_slot
     {
         int16_t *src_mem; EvxPlanes src;
         EvxDesc *d_table; EvxInterResult *d_inter; int16_t *d_records; int *d_row_records; int *d_prev; int *d_sync;
-        cudaStream_t main, k2s, k4s;
-        cudaEvent_t ev_k1done, ev_k8done, ev_k4end, ev_k2end;
-        unsigned int epoch;             // of the frame last submitted into the slot
-        int B, NB;                      // its banding: rows per band, bands (the unit of its `final` counter)
+        unsigned int *d_dbk;            // [mbh] filtered tile columns per tile row (base + count), [mbh] = `started`
+        cudaStream_t main;
+        cudaEvent_t ev_k1done, ev_k8done;
+        unsigned int base;              // counter base of the frame last submitted into the slot
         bool used;
     } fs[EVX_MAX_SLOTS];
-    int nslots;                     // frame slots in use: 2, or 3 with frame overlap (EVXGPU_FRAME_SLOTS)
-    unsigned int *d_flags;          // [slot][3]: rows_done, final (deblocked bands), k2 rows done; value = epoch + count
-    unsigned int frame_seq, epoch_limit;
-    int band_rows, nbands;
+    int nslots;                     // frame slots in use
+    int want_slots;                 // evxgpu_config::frame_slots (0: default)
+    unsigned int frame_seq;
+    int k3_regs;                    // register budget of the frame kernel: 1 or 2 CTAs per SM
+    unsigned int *h_diag, *d_diag;  // mapped host memory: what a device-side wait that ran out of time was waiting for
+    unsigned long long wait_budget_ns;
     int q_head, q_count;            // queue of submitted, uncollected frames: slots q_head, q_head + 1, ... (mod nslots)
     int last_slot;                  // slot of the last collected frame (evxgpu_d2h_bytes)
     uint32_t bins_last_total;       // bin count of the previous frame (sizes the optimistic head copy)
@@ -192,7 +188,7 @@ int evxgpu_destroy(evxgpu_handle *h)
     if (!h) return 1;
     if (h->is_encoder && h->device >= 0 && h->device < 64) { g_encoders_live[h->device].fetch_sub(1); h->is_encoder = false; }
     if (h->overlap)
-    {   // back to slot 0's view (the original allocations); slot 1 and the extra streams go here
+    {   // back to slot 0's view (the original allocations); the other slots and their streams go here
         sync_all(h);
         use_slot(h, 0);
         for (int q = 1; q < EVX_MAX_SLOTS; ++q)
@@ -201,18 +197,13 @@ int evxgpu_destroy(evxgpu_handle *h)
             cudaFree(b.src_mem); cudaFree(b.d_table); cudaFree(b.d_inter); cudaFree(b.d_records); cudaFree(b.d_row_records); cudaFree(b.d_prev); cudaFree(b.d_sync);
             if (b.main) cudaStreamDestroy(b.main);
         }
-        cudaFree(h->d_flags);
         for (int q = 0; q < EVX_MAX_SLOTS; ++q)
         {
-            if (h->fs[q].k2s) cudaStreamDestroy(h->fs[q].k2s);
-            if (h->fs[q].k4s) cudaStreamDestroy(h->fs[q].k4s);
+            cudaFree(h->fs[q].d_dbk);
             if (h->fs[q].ev_k1done) cudaEventDestroy(h->fs[q].ev_k1done);
             if (h->fs[q].ev_k8done) cudaEventDestroy(h->fs[q].ev_k8done);
-            if (h->fs[q].ev_k4end) cudaEventDestroy(h->fs[q].ev_k4end);
-            if (h->fs[q].ev_k2end) cudaEventDestroy(h->fs[q].ev_k2end);
         }
         h->overlap = false;
-        g_overlap_live[h->device].fetch_sub(1);
     }
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -228,6 +219,7 @@ int evxgpu_destroy(evxgpu_handle *h)
     for (int q = 0; q < EVX_MAX_SLOTS; ++q) { cudaFree(h->d_bins[q]); cudaFree(h->d_bins_total[q]); cudaFreeHost(h->h_bins[q]); if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]); }
     cudaFreeHost(h->h_table); cudaFreeHost(h->h_records); cudaFreeHost(h->h_record_slot); cudaFreeHost(h->h_sync); cudaFreeHost(h->h_rgb);
     for (int q = 0; q < EVX_MAX_SLOTS; ++q) for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[q][k][e]) cudaEventDestroy(h->ev[q][k][e]);
+    if (h->h_diag) cudaFreeHost(h->h_diag);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -247,6 +239,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     h->device = device;
     h->nslots = 2;
     h->cfg = *cfg;
+    h->want_slots = cfg->frame_slots;
     h->g.vw = width; h->g.vh = height;
     h->g.w = (width + 15) & ~15; h->g.h = (height + 15) & ~15;          // evx1enc.cpp:79-80
     h->g.mbw = h->g.w / 16; h->g.mbh = h->g.h / 16;
@@ -311,23 +304,29 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
         encode_tiled_fn enc = (encode_tiled_fn) fn;
         for (int i = 0; i < cfg->ref_count; ++i)
         {
-            int r = make_map(enc, &h->maps[i][0], h->ring[i].y, h->g.w, h->g.h, EVX_K2_WIN_W, EVX_K2_WIN_H);
-            r |= make_map(enc, &h->maps[i][1], h->ring[i].u, h->g.w / 2, h->g.h / 2, EVX_K2_CWIN_W, EVX_K2_CWIN_H);
-            r |= make_map(enc, &h->maps[i][2], h->ring[i].v, h->g.w / 2, h->g.h / 2, EVX_K2_CWIN_W, EVX_K2_CWIN_H);
-            r |= make_map(enc, &h->maps_w[i][0], h->ring[i].y, h->g.w, h->g.h, EVX_K2W_WIN, EVX_K2W_WIN);
+            int r = make_map(enc, &h->maps_w[i][0], h->ring[i].y, h->g.w, h->g.h, EVX_K2W_WIN, EVX_K2W_WIN);
             r |= make_map(enc, &h->maps_w[i][1], h->ring[i].u, h->g.w / 2, h->g.h / 2, EVX_K2W_CWIN, EVX_K2W_CWIN);
             r |= make_map(enc, &h->maps_w[i][2], h->ring[i].v, h->g.w / 2, h->g.h / 2, EVX_K2W_CWIN, EVX_K2W_CWIN);
             if (r) { evxgpu_destroy(h); return fail(5, "cuTensorMapEncodeTiled failed"); }
         }
     }
     {
-        cudaError_t e = cudaFuncSetAttribute(evx_inter_search_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, EVX_K2_SMEM);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(evx_inter_search, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        { const char *k2 = getenv("EVXGPU_K2"); h->k2_tile = k2 && !strcmp(k2, "tile"); }
+        cudaError_t e = cudaFuncSetAttribute(evx_inter_search, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_inter_search)", e); }
-        e = cudaFuncSetAttribute(evx_wavefront<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EvxK3Smem));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(evx_wavefront<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EvxK3Smem));
+        e = cudaFuncSetAttribute(evx_wavefront<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) EVX_FRAME_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(evx_wavefront<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) EVX_FRAME_SMEM);
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_wavefront)", e); }
+    }
+    {   // device-side waits are bounded (evx_kernels.cuh, EVX_BOUNDED_WAIT): budget and the mapped word the reason lands in
+        h->wait_budget_ns = 4000ull * 1000000ull;
+        if (const char *e = getenv("EVXGPU_WAIT_BUDGET_MS")) { long v = atol(e); if (v >= 0) h->wait_budget_ns = (unsigned long long) v * 1000000ull; }   // 0: unbounded (compute-sanitizer runs)
+        if (cudaHostAlloc((void **) &h->h_diag, 64, cudaHostAllocMapped) == cudaSuccess)
+        {
+            memset(h->h_diag, 0, 64);
+            if (cudaHostGetDevicePointer((void **) &h->d_diag, h->h_diag, 0) != cudaSuccess) h->d_diag = NULL;
+        }
+        h->k3_regs = 2;
+        if (const char *e = getenv("EVXGPU_K3_REGS")) { int v = atoi(e); if (v == 1 || v == 2) h->k3_regs = v; }      // measurements
     }
     for (int k = 0; k < EVXGPU_T_COUNT; ++k)
         for (int e = 0; e < 2; ++e)
@@ -338,7 +337,8 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     // encoder wavefront: at most ceil(W/3) rows are ever active at once (row r runs during steps [3r, 3r+W));
     // a few spare CTAs absorb the row-to-row hand-over
     h->enc_grid = std::min(h->g.mbh, (h->g.mbw + 2) / 3 + 4);
-    if (const char *e = getenv("EVXGPU_ENC_GRID")) { int v = atoi(e); if (v > 0) h->enc_grid = std::min(h->g.mbh, v); }      // measurements
+    h->k2_ctas = 6;
+    if (const char *e = getenv("EVXGPU_K2_CTAS")) { int v = atoi(e); if (v >= 0) h->k2_ctas = v; }      // measurements
     int rc = evxgpu_reset(h);
     if (rc) { evxgpu_destroy(h); return rc; }
     *out = h;
@@ -357,9 +357,9 @@ int evxgpu_reset(evxgpu_handle *h)
         {
             CK(cudaMemset(h->fs[q].src_mem, 0, plane_elems(h->g) * 2));
             CK(cudaMemset(h->fs[q].d_table, 0, (size_t) h->nmb * 16));
-            h->fs[q].used = false; h->fs[q].epoch = 0;
+            CK(cudaMemset(h->fs[q].d_dbk, 0, (size_t) (h->g.mbh + 1) * 4));
+            h->fs[q].used = false; h->fs[q].base = 0;
         }
-        CK(cudaMemset(h->d_flags, 0, EVX_MAX_SLOTS * 4 * sizeof(unsigned int)));
         h->frame_seq = 0;
     }
     const size_t pe = plane_elems(h->g);
@@ -470,57 +470,50 @@ static int launch_convert_in(evxgpu_handle *h, const uint8_t *d_rgb)
 static int launch_inter_search(evxgpu_handle *h, uint32_t index, int quality)
 {
     const int R = h->cfg.ref_count;
-    if (h->k2_tile)
+    EvxK2Params p;
+    for (int off = 1; off < R; ++off)
     {
-        EvxK2Maps maps;
-        for (int off = 1; off < R; ++off)
-        {
-            int slot = (int) ((index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);     // common.cpp:192-195
-            for (int c = 0; c < 3; ++c) maps.m[(off - 1) * 3 + c] = h->maps[slot][c];
-        }
-        dim3 block(EVX_K2_MBS * 32), grid((h->g.mbw + EVX_K2_MBS - 1) / EVX_K2_MBS, h->g.mbh, R - 1);
-        t_begin(h, EVXGPU_T_INTER_SEARCH);
-        evx_inter_search_tile<<<grid, block, EVX_K2_SMEM, h->stream>>>(maps, h->src, h->g, h->d_inter, (quality >> 2) + 1, h->d_counters);
+        int slot = (int) ((index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);     // common.cpp:192-195
+        for (int c = 0; c < 3; ++c) p.maps.m[(off - 1) * 3 + c] = h->maps_w[slot][c];
+        p.ref[off - 1] = h->ring[slot];
     }
-    else
-    {
-        EvxK2Params p;
-        for (int off = 1; off < R; ++off)
-        {
-            int slot = (int) ((index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);     // common.cpp:192-195
-            for (int c = 0; c < 3; ++c) p.maps.m[(off - 1) * 3 + c] = h->maps_w[slot][c];
-            p.ref[off - 1] = h->ring[slot];
-        }
-        p.src = h->src; p.g = h->g; p.results = h->d_inter; p.counters = h->d_counters; p.thr = (quality >> 2) + 1; p.row0 = 0;
-        dim3 block(32), grid(h->g.mbw, h->g.mbh, R - 1);
-        t_begin(h, EVXGPU_T_INTER_SEARCH);
-        evx_inter_search<<<grid, block, EVX_K2W_SMEM, h->stream>>>(p);
-    }
+    p.src = h->src; p.g = h->g; p.results = h->d_inter; p.counters = h->d_counters; p.thr = (quality >> 2) + 1; p.row0 = 0;
+    dim3 block(32), grid(h->g.mbw, h->g.mbh, R - 1);
+    t_begin(h, EVXGPU_T_INTER_SEARCH);
+    evx_inter_search<<<grid, block, EVX_K2W_SMEM, h->stream>>>(p);
     t_end(h, EVXGPU_T_INTER_SEARCH);
     h->launches++;
     CK(cudaGetLastError());
     return 0;
 }
 
-static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, int quality)
+// the wavefront kernel's parameters for the handle's current per-frame pointers; the frame-pipeline roles are off
+static void wavefront_params(evxgpu_handle *h, EvxK3Params &p, int frame_type, uint32_t index, int quality)
 {
-    EvxK3Params p;
+    memset(&p, 0, sizeof(p));
     p.src = h->src;
     for (int i = 0; i < 8; ++i) p.ring[i] = h->ring[i];
     p.g = h->g; p.R = h->cfg.ref_count; p.linear = h->cfg.linear_quant;
     p.frame_type = frame_type; p.quality = quality; p.frame_index = index;
     p.inter = h->d_inter; p.table = h->d_table; p.records = h->d_records; p.row_records = h->d_row_records;
     p.sync = h->d_sync; p.counters = h->d_counters; p.prof = h->d_prof;
-    p.rows_done = NULL; p.rows_base = 0; p.gate_k2 = NULL; p.gate_k2_base = 0; p.gate_final = NULL; p.gate_final_base = 0; p.band_rows = 1; p.nbands = 0;
     p.prev_motion = h->d_prev; p.prev_coded = h->d_prev + h->nmb; p.row_last = h->d_prev + 2 * h->nmb;
+    p.deblocking = h->cfg.deblocking; p.thr = (quality >> 2) + 1;
+    p.wait.budget_ns = h->wait_budget_ns; p.wait.diag = h->d_diag;
+}
+
+static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, int quality)
+{
+    EvxK3Params p;
+    wavefront_params(h, p, frame_type, index, quality);
     CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
     t_begin(h, EVXGPU_T_WAVEFRONT);
     // one CTA per macroblock row in flight; rows are claimed by ticket, so any residency is deadlock-free
     // the only encoder on the device runs the kernel with the larger register budget (evx_wavefront.cuh)
-    if (h->device >= 0 && h->device < 64 && g_encoders_live[h->device].load() <= 1 && !getenv("EVXGPU_K3_NARROW"))
-        evx_wavefront<1><<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), h->stream>>>(p);
+    if (h->device >= 0 && h->device < 64 && g_encoders_live[h->device].load() <= 1 && h->k3_regs != 2)
+        evx_wavefront<1><<<h->enc_grid, EVX_K3_NT, EVX_FRAME_SMEM, h->stream>>>(p);
     else
-        evx_wavefront<2><<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), h->stream>>>(p);
+        evx_wavefront<2><<<h->enc_grid, EVX_K3_NT, EVX_FRAME_SMEM, h->stream>>>(p);
     h->launches++;
     if (h->out_mode != 1)
     {
@@ -537,7 +530,6 @@ static int launch_deblock(evxgpu_handle *h, uint32_t index)
     if (!h->cfg.deblocking) return 0;
     EvxK4Params p;
     p.pl = h->ring[index % (uint32_t) h->cfg.ref_count]; p.g = h->g; p.table = h->d_table;
-    p.ty0[0] = p.ty0[1] = 0; p.tyn[0] = h->g.h / 8 + 1; p.tyn[1] = h->g.h / 16 + 1;      // the whole frame
     dim3 block(128), grid((h->g.w / 8 + 1 + 127) / 128, h->g.h / 8 + 1, 3);
     t_begin(h, EVXGPU_T_DEBLOCK);
     evx_deblock<<<grid, block, 0, h->stream>>>(p);
@@ -565,7 +557,11 @@ static int launch_bins(evxgpu_handle *h, bool emit_only)
 {
     const EvxBinsParams p = bins_params(h);
     const int ntiles = (EVX_BINS_ITEMS * h->nmb + EVX_BINS_TILE - 1) / EVX_BINS_TILE;
-    CK(cudaMemsetAsync(h->d_bins[h->slot], 0, (size_t) h->bins_cap_bits / 8 + 8, h->stream));
+    {   // the string is OR-ed into zeroed words; only what the slot's previous frame wrote has to be cleared
+        const uint32_t dirty = std::min(h->bins_cap_bits, h->bins_dirty_bits[h->slot]);
+        if (dirty) CK(cudaMemsetAsync(h->d_bins[h->slot], 0, (size_t) dirty / 8 + 8, h->stream));
+        h->bins_dirty_bits[h->slot] = h->bins_cap_bits;          // until collect learns the length
+    }
     t_begin(h, EVXGPU_T_BINS);
     if (!emit_only)
     {
@@ -579,9 +575,7 @@ static int launch_bins(evxgpu_handle *h, bool emit_only)
     return 0;
 }
 
-// ------------------------------------------------------------------ frame overlap
-
-enum { FLAG_ROWS = 0, FLAG_FINAL = 1, FLAG_K2 = 2 };
+// ------------------------------------------------------------------ frame pipeline
 
 // the handle's per-frame pointers and its stream become those of slot q (every launch helper uses them)
 static void use_slot(evxgpu_handle *h, int q)
@@ -595,38 +589,49 @@ static void use_slot(evxgpu_handle *h, int q)
 static int sync_all(evxgpu_handle *h)
 {
     if (h->overlap)
-        for (int q = 0; q < h->nslots; ++q)
-        {
-            CK(cudaStreamSynchronize(h->fs[q].main)); CK(cudaStreamSynchronize(h->fs[q].k2s)); CK(cudaStreamSynchronize(h->fs[q].k4s));
-        }
+        for (int q = 0; q < h->nslots; ++q) CK(cudaStreamSynchronize(h->fs[q].main));
     else CK(cudaStreamSynchronize(h->stream));
     if (h->copy_stream) CK(cudaStreamSynchronize(h->copy_stream));
     return 0;
 }
 
-static int enable_overlap(evxgpu_handle *h)
+// frees what a failed enable_pipeline left behind (slot 0 keeps the handle's original allocations)
+static void drop_pipeline(evxgpu_handle *h)
+{
+    for (int q = 1; q < EVX_MAX_SLOTS; ++q)
+    {
+        evxgpu_handle::frame_slot &b = h->fs[q];
+        cudaFree(b.src_mem); cudaFree(b.d_table); cudaFree(b.d_inter); cudaFree(b.d_records); cudaFree(b.d_row_records); cudaFree(b.d_prev); cudaFree(b.d_sync);
+        if (b.main) cudaStreamDestroy(b.main);
+    }
+    for (int q = 0; q < EVX_MAX_SLOTS; ++q)
+    {
+        cudaFree(h->fs[q].d_dbk);
+        if (h->fs[q].ev_k1done) cudaEventDestroy(h->fs[q].ev_k1done);
+        if (h->fs[q].ev_k8done) cudaEventDestroy(h->fs[q].ev_k8done);
+    }
+    memset(h->fs, 0, sizeof(h->fs));
+}
+
+static int enable_pipeline(evxgpu_handle *h)
 {
     if (h->overlap) return 0;
-    if (!h->own_stream) return 0;                         // a caller's stream cannot be one of two
-    // Under a tool that serialises kernels (Nsight Compute replays one kernel at a time, compute-sanitizer likewise) a
-    // wavefront kernel polling for the band kernels of another stream would never see them run: frame after frame there.
-    if (getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("CUDA_INJECTION64_PATH") || getenv("NSYS_PROFILING_SESSION_ID")) return 0;
+    if (!h->own_stream) return 0;                         // a caller's stream cannot be one of several
     if (h->device < 0 || h->device >= 64) return 0;
-    if (g_overlap_live[h->device].fetch_add(1) >= EVX_MAX_OVERLAP_ENCODERS) { g_overlap_live[h->device].fetch_sub(1); return 0; }
     if (!g_wait32)
     {
-        void *f1 = NULL, *f2 = NULL;
+        void *f1 = NULL;
         cudaDriverEntryPointQueryResult qres;
         if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f1, cudaEnableDefault, &qres) != cudaSuccess || !f1) return 0;
-        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f2, cudaEnableDefault, &qres) != cudaSuccess || !f2) return 0;
-        g_wait32 = (stream_memop_fn) f1; g_write32 = (stream_memop_fn) f2;
+        g_wait32 = (stream_memop_fn) f1;
     }
     CK(cudaStreamSynchronize(h->stream));
     const size_t pe = plane_elems(h->g);
-    // Frame slots: two, or three with EVXGPU_FRAME_SLOTS=3 -- a frame may start once its predecessor is about nine
-    // macroblock rows ahead, so with two slots it is the slot, not the data, a third frame waits for.
-    int ns = EVX_DEFAULT_SLOTS;
-    if (const char *e = getenv("EVXGPU_FRAME_SLOTS")) { int v = atoi(e); if (v >= 2 && v <= EVX_MAX_SLOTS) ns = v; }
+    // Frame slots: a frame may start once its predecessor is about 23 wavefront steps ahead (of W + 3(H-1)), so what
+    // limits the frames in flight is the SMs, not the data: 44 row CTAs per 1080p frame, two per SM.
+    int ns = h->want_slots > 0 ? h->want_slots : EVX_DEFAULT_SLOTS;
+    if (const char *e = getenv("EVXGPU_FRAME_SLOTS")) { int v = atoi(e); if (v >= 2) ns = v; }
+    ns = std::max(2, std::min(ns, (int) EVX_MAX_SLOTS));
     evxgpu_handle::frame_slot &a = h->fs[0];
     a.src_mem = h->src_mem; a.src = h->src; a.d_table = h->d_table; a.d_inter = h->d_inter; a.d_records = h->d_records;
     a.d_row_records = h->d_row_records; a.d_prev = h->d_prev; a.d_sync = h->d_sync; a.main = h->stream;
@@ -643,77 +648,44 @@ static int enable_overlap(evxgpu_handle *h)
         ok = ok && cudaMalloc(&b.d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&b.main, cudaStreamNonBlocking) == cudaSuccess;
     }
-    ok = ok && cudaMalloc(&h->d_flags, EVX_MAX_SLOTS * 4 * sizeof(unsigned int)) == cudaSuccess;
-    // The band kernels run at the highest priority: the next frame's wavefront CTAs are resident and poll for what these
-    // kernels produce, so they must never queue behind the floods of small CTAs other streams launch (measured: with
-    // five more encoders on the device a whole-frame deblock at default priority could wait indefinitely).
-    int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (int q = 0; q < ns && ok; ++q)
     {
-        ok = ok && cudaStreamCreateWithPriority(&h->fs[q].k2s, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
-        ok = ok && cudaStreamCreateWithPriority(&h->fs[q].k4s, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        ok = ok && cudaMalloc(&h->fs[q].d_dbk, (size_t) (h->g.mbh + 1) * 4) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k1done, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k8done, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k4end, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k2end, cudaEventDisableTiming) == cudaSuccess;
-        h->fs[q].epoch = 0; h->fs[q].used = false;
+        h->fs[q].base = 0; h->fs[q].used = false;
     }
-    if (!ok) { g_overlap_live[h->device].fetch_sub(1); return fail(3, "frame overlap: out of device memory"); }
-    for (int q = 1; q < ns; ++q)
+    if (!ok) { drop_pipeline(h); return fail(3, "frame pipeline: out of device memory"); }
+    for (int q = 0; q < ns; ++q)
     {
         evxgpu_handle::frame_slot &b = h->fs[q];
-        set_planes(b.src, b.src_mem, h->g);
-        CK(cudaMemset(b.src_mem, 0, pe * 2));             // padding rows/columns stay zero
-        CK(cudaMemset(b.d_table, 0, (size_t) h->nmb * 16));
+        if (q)
+        {
+            set_planes(b.src, b.src_mem, h->g);
+            if (cudaMemset(b.src_mem, 0, pe * 2) != cudaSuccess || cudaMemset(b.d_table, 0, (size_t) h->nmb * 16) != cudaSuccess) ok = false;   // padding rows/columns stay zero
+        }
+        if (cudaMemset(b.d_dbk, 0, (size_t) (h->g.mbh + 1) * 4) != cudaSuccess) ok = false;
     }
-    CK(cudaMemset(h->d_flags, 0, EVX_MAX_SLOTS * 4 * sizeof(unsigned int)));
+    if (!ok) { drop_pipeline(h); return fail(5, "frame pipeline: cudaMemset failed"); }
     h->nslots = ns;
-    // Band size, measured at 1080p.  Two slots: 3 rows 857, 4 rows 882, 6 rows 889, 8 rows 889 frames/s (each band costs three
-    // driver calls twice, and with two slots the slot, not the distance, is what the next frame waits for).  Three slots:
-    // 6 rows 1151, 4 rows 1223, 3 rows 1254 frames/s -- the distance to the previous frame is the limit, and it shrinks with the band.
-    int br = ns >= 3 ? 3 : 6;
-    if (const char *e = getenv("EVXGPU_BAND_ROWS")) { int v = atoi(e); if (v >= 3) br = v; }
-    h->band_rows = br; h->nbands = (h->g.mbh + br - 1) / br;
     h->frame_seq = 0;
-    h->epoch_limit = 1u << 19;
-    if (const char *e = getenv("EVXGPU_EPOCH_LIMIT")) { int v = atoi(e); if (v >= 2) h->epoch_limit = (unsigned int) v; }      // tests: restart the epochs often
     h->overlap = true;
     return 0;
 }
 
-// One frame, queued so that it overlaps the previous frame of the stream.  Everything of the frame lives in slot q;
-// p = the slot before q holds the previous frame, which may still be running (and the one before that the frame before it).  Dependencies on the previous frame (SURVEY H3,
-// DESIGN section 6a), all by rows: K2 and the inter predictions of rows [r-2, r+3] need it deblocked there; its band b
-// may be deblocked once its wavefront has finished row band_end(b)+3 (the intra search reads three rows up, unfiltered);
-// with a ring of two this frame overwrites the slot the previous one reads as its reference, two rows behind what K2
-// already requires.  Row counters live in device memory: the host side waits on them with stream memory operations
-// (no kernel occupies the device while it waits), the wavefront kernel polls them.
-static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device, int frame_type, uint32_t frame_index, int quality)
+// One frame of the pipeline: K1, then ONE launch of the frame kernel (search role + wavefront rows + deblocking behind
+// the wavefront, evx_wavefront.cuh), then K8 and the copies -- all on the slot's stream.  The frame kernel follows the
+// previous frame's (slot p, possibly still running, and transitively all older ones) macroblock by macroblock through
+// that frame's dbk[] counters; it is launched only once the previous frame's kernel has started (a stream memory
+// operation on its `started` word), so that what it waits for is always already on the device.
+static int submit_pipelined(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device, int frame_type, uint32_t frame_index, int quality)
 {
     const int ns = h->nslots, q = (h->q_head + h->q_count) % ns, p = (q + ns - 1) % ns;
-    if (h->frame_seq >= h->epoch_limit)
-    {   // the epochs restart when nothing is in flight
-        if (h->q_count) return fail(8, "evxgpu_encode_submit: epoch wrap, collect the frame in flight first");
-        int rc = sync_all(h);
-        if (rc) return rc;
-        CK(cudaMemset(h->d_flags, 0, EVX_MAX_SLOTS * 4 * sizeof(unsigned int)));
-        h->frame_seq = 0;
-        for (int k = 0; k < EVX_MAX_SLOTS; ++k) h->fs[k].used = false;
-    }
     use_slot(h, q);
     evxgpu_handle::frame_slot &f = h->fs[q], &pv = h->fs[p];
-    const unsigned int E = (++h->frame_seq) << 12, Ep = pv.epoch;
+    // counter base of this frame: 13 bits of count (mbw <= 4096), compared cyclically -- no restart, ever
+    const unsigned int E = (++h->frame_seq) << 13, Ep = pv.base;
     const bool have_prev = pv.used;
-    unsigned int *fl = h->d_flags + 4 * q, *flp = h->d_flags + 4 * p;
-    const int mbh = h->g.mbh;
-    // A frame submitted with nothing in flight (encode() one frame at a time, or the first frame of a pipelined run) is
-    // queued as ONE band: no successor is waiting to follow it row by row, and a band costs three driver calls.
-    const bool whole = h->q_count == 0;
-    const int B = whole ? mbh : h->band_rows, NB = whole ? 1 : h->nbands;
-    const int Bp = pv.B > 0 ? pv.B : mbh, NBp = pv.NB > 0 ? pv.NB : 1;       // the previous frame's banding
-    auto dptr = [](unsigned int *x) { return (CUdeviceptr) (uintptr_t) x; };
-#define MEMOP(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) return fail(5, "stream memory operation failed"); } while (0)
 
     const uint8_t *d_rgb = rgb;
     if (rgb_is_device == 2) { CK(cudaStreamWaitEvent(f.main, h->ev_up, 0)); h->uploaded = false; }
@@ -729,74 +701,29 @@ static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_devic
     CK(cudaEventRecord(f.ev_k1done, f.main));
     if (rgb_is_device == 2) CK(cudaEventRecord(h->ev_k1, f.main));
 
-    // K2, band by band, on its own stream
-    if (frame_type == 1)
     {
+        EvxK3Params kp;
+        wavefront_params(h, kp, frame_type, frame_index, quality);
+        kp.prof = NULL;
+        kp.fuse_k2 = 1; kp.fuse_dbk = 1;
+        kp.stamp = h->frame_seq ? h->frame_seq : 1u;
+        kp.dbk = f.d_dbk; kp.dbk_base = E; kp.started = f.d_dbk + h->g.mbh;
+        kp.prev_dbk = have_prev ? pv.d_dbk : NULL; kp.prev_base = Ep;
         const int R = h->cfg.ref_count;
-        EvxK2Params kp;
         for (int off = 1; off < R; ++off)
         {
             int slot = (int) ((frame_index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);
             for (int c = 0; c < 3; ++c) kp.maps.m[(off - 1) * 3 + c] = h->maps_w[slot][c];
-            kp.ref[off - 1] = h->ring[slot];
         }
-        kp.src = f.src; kp.g = h->g; kp.results = f.d_inter; kp.counters = h->d_counters; kp.thr = (quality >> 2) + 1;
-        CK(cudaStreamWaitEvent(f.k2s, f.ev_k1done, 0));
-        for (int c = 0; c < NB; ++c)
-        {
-            const int r0 = c * B, r1 = std::min(mbh, r0 + B);
-            if (have_prev) MEMOP(g_wait32((CUstream) f.k2s, dptr(flp + FLAG_FINAL), Ep + (unsigned int) std::min((r1 - 1) / Bp + 2, NBp), CU_STREAM_WAIT_VALUE_GEQ));
-            kp.row0 = r0;
-            evx_inter_search<<<dim3(h->g.mbw, r1 - r0, R - 1), 32, EVX_K2W_SMEM, f.k2s>>>(kp);
-            MEMOP(g_write32((CUstream) f.k2s, dptr(fl + FLAG_K2), E + (unsigned int) r1, CU_STREAM_WRITE_VALUE_DEFAULT));
-            h->launches++;
-        }
-        CK(cudaEventRecord(f.ev_k2end, f.k2s));
-        CK(cudaGetLastError());
-    }
-
-    // K3: queued only when the previous frame's wavefront kernel has started to complete rows, i.e. is resident
-    if (have_prev) MEMOP(g_wait32((CUstream) f.main, dptr(flp + FLAG_ROWS), Ep + 1u, CU_STREAM_WAIT_VALUE_GEQ));
-    {
-        EvxK3Params kp;
-        kp.src = f.src;
-        for (int i = 0; i < 8; ++i) kp.ring[i] = h->ring[i];
-        kp.g = h->g; kp.R = h->cfg.ref_count; kp.linear = h->cfg.linear_quant;
-        kp.frame_type = frame_type; kp.quality = quality; kp.frame_index = frame_index;
-        kp.inter = f.d_inter; kp.table = f.d_table; kp.records = f.d_records; kp.row_records = f.d_row_records;
-        kp.sync = f.d_sync; kp.counters = h->d_counters; kp.prof = NULL;
-        kp.prev_motion = f.d_prev; kp.prev_coded = f.d_prev + h->nmb; kp.row_last = f.d_prev + 2 * h->nmb;
-        kp.rows_done = fl + FLAG_ROWS; kp.rows_base = E;
-        kp.gate_k2 = frame_type == 1 ? fl + FLAG_K2 : NULL; kp.gate_k2_base = E;
-        kp.gate_final = have_prev ? flp + FLAG_FINAL : NULL; kp.gate_final_base = Ep;
-        kp.band_rows = Bp; kp.nbands = NBp;          // units of the previous frame's `final` counter
-        CK(cudaMemsetAsync(f.d_sync, 0, (size_t) (mbh + 2) * 4, f.main));
-        // (frames overlap only while this is the device's only encoder: the larger register budget, evx_wavefront.cuh)
-        if (!getenv("EVXGPU_K3_NARROW")) evx_wavefront<1><<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), f.main>>>(kp);
-        else evx_wavefront<2><<<h->enc_grid, EVX_K3_NT, sizeof(EvxK3Smem), f.main>>>(kp);
+        CK(cudaMemsetAsync(f.d_sync, 0, (size_t) (h->g.mbh + 2) * 4, f.main));
+        if (have_prev && g_wait32((CUstream) f.main, (CUdeviceptr) (uintptr_t) (pv.d_dbk + h->g.mbh), Ep, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            return fail(5, "stream memory operation failed");
+        // wavefront rows in flight at once + a few CTAs for the search rows that run ahead of them
+        const int tickets = h->g.mbh * (frame_type == 1 ? 2 : 1);
+        const int grid = std::min(tickets, h->enc_grid + (frame_type == 1 ? h->k2_ctas : 0));
+        if (h->k3_regs == 1) evx_wavefront<1><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
+        else evx_wavefront<2><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
         h->launches++;
-        CK(cudaGetLastError());
-    }
-
-    // K4, band by band behind the wavefront, on its own stream; each band done advances `final`
-    {
-        EvxK4Params dp;
-        dp.pl = h->ring[frame_index % (uint32_t) h->cfg.ref_count]; dp.g = h->g; dp.table = f.d_table;
-        const int lt = h->g.h / 8 + 1, ct = h->g.h / 16 + 1;
-        for (int b = 0; b < NB; ++b)
-        {
-            MEMOP(g_wait32((CUstream) f.k4s, dptr(fl + FLAG_ROWS), E + (unsigned int) std::min(b * B + B + 3, mbh), CU_STREAM_WAIT_VALUE_GEQ));
-            if (h->cfg.deblocking)
-            {
-                dp.ty0[0] = 2 * B * b; dp.tyn[0] = (b == NB - 1) ? lt - dp.ty0[0] : 2 * B;
-                dp.ty0[1] = B * b;     dp.tyn[1] = (b == NB - 1) ? ct - dp.ty0[1] : B;
-                dim3 block(128), grid((h->g.w / 8 + 1 + 127) / 128, std::max(dp.tyn[0], dp.tyn[1]), 3);
-                evx_deblock<<<grid, block, 0, f.k4s>>>(dp);
-                h->launches++;
-            }
-            MEMOP(g_write32((CUstream) f.k4s, dptr(fl + FLAG_FINAL), E + (unsigned int) (b + 1), CU_STREAM_WRITE_VALUE_DEFAULT));
-        }
-        CK(cudaEventRecord(f.ev_k4end, f.k4s));
         CK(cudaGetLastError());
     }
 
@@ -811,11 +738,7 @@ static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_devic
     h->d2h_bytes[q] += 16 + h->bins_prefix_bits[q] / 8;
     h->pending_bins[q] = true;
     CK(cudaEventRecord(h->ev_out[q], f.main));
-    // join: the tail of the slot's main stream is the whole frame (what the next frame in this slot queues behind)
-    CK(cudaStreamWaitEvent(f.main, f.ev_k4end, 0));
-    if (frame_type == 1) CK(cudaStreamWaitEvent(f.main, f.ev_k2end, 0));
-#undef MEMOP
-    f.epoch = E; f.used = true; f.B = B; f.NB = NB;
+    f.base = E; f.used = true;
     h->q_count++;
     h->pending_encode = true;
     return 0;
@@ -823,15 +746,17 @@ static int submit_overlap(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_devic
 
 // ------------------------------------------------------------------ encoder
 
-// (re)allocates the two slots' string buffers: device capacity cap_bits each, pinned host capacity hcap_bits each
+// (re)allocates the frame slots' string buffers: device capacity cap_bits each, pinned host capacity hcap_bits each
 static int alloc_bins(evxgpu_handle *h, uint32_t cap_bits, uint32_t hcap_bits)
 {
-    for (int q = 0; q < EVX_MAX_SLOTS; ++q)
+    for (int q = 0; q < h->nslots; ++q)
     {
         cudaFree(h->d_bins[q]); h->d_bins[q] = NULL;
         cudaFreeHost(h->h_bins[q]); h->h_bins[q] = NULL;
         if (!h->d_bins_total[q] && cudaMalloc(&h->d_bins_total[q], 16) != cudaSuccess) return fail(3, "bin buffers: out of device memory");
         if (cudaMalloc(&h->d_bins[q], (size_t) cap_bits / 8 + 8) != cudaSuccess) return fail(3, "bin buffers: out of device memory");
+        if (cudaMemset(h->d_bins[q], 0, (size_t) cap_bits / 8 + 8) != cudaSuccess) return fail(5, "bin buffers: cudaMemset failed");
+        h->bins_dirty_bits[q] = 0;
         if (cudaHostAlloc(&h->h_bins[q], (size_t) hcap_bits / 8 + 32, cudaHostAllocDefault) != cudaSuccess) return fail(3, "bin buffers: out of pinned memory");
         h->h_bins_cap_bits[q] = hcap_bits;
     }
@@ -844,9 +769,16 @@ int evxgpu_set_output(evxgpu_handle *h, int mode)
     if (!h || mode < 0 || mode > 2) return fail(1, "evxgpu_set_output: bad argument");
     if (h->pending_encode) return fail(8, "evxgpu_set_output: a frame is in flight");
     CK(cudaSetDevice(h->device));
+    if (mode == 1 && !h->d_bins[0])
+    {
+        // consecutive frames are pipelined on the device unless EVXGPU_FRAME_OVERLAP=0 (A/B runs, per-kernel timing);
+        // decided once, before the string buffers (one per frame slot) are made
+        const char *ov = getenv("EVXGPU_FRAME_OVERLAP");
+        if (!(ov && ov[0] == '0')) { int rc = enable_pipeline(h); if (rc) return rc; }
+    }
     if (mode != 0 && !h->d_bins[0])
     {
-        // device: the longest slice this geometry can produce, so the string always fits (and a second frame may be
+        // device: the longest slice this geometry can produce, so the string always fits (and further frames may be
         // queued behind the first); pinned host side: 256 bins per macroblock to start with (a 1080p intra frame needs
         // about 45), grown on demand
         CK(cudaStreamSynchronize(h->stream));
@@ -854,12 +786,6 @@ int evxgpu_set_output(evxgpu_handle *h, int mode)
         if (rc) return rc;
     }
     h->out_mode = mode;
-    if (mode == 1)
-    {
-        // consecutive frames overlap on the device unless EVXGPU_FRAME_OVERLAP=0 (A/B runs, per-kernel timing)
-        const char *ov = getenv("EVXGPU_FRAME_OVERLAP");
-        if (!(ov && ov[0] == '0')) { int rc = enable_overlap(h); if (rc) return rc; }
-    }
     return 0;
 }
 
@@ -867,14 +793,7 @@ int evxgpu_encode_capacity(const evxgpu_handle *h)
 {
     if (!h) return 0;
     if (h->out_mode != 1 || h->bins_cap_bits < h->bins_worst_bits) return 1;
-    if (!h->overlap || h->k2_tile) return 2;
-    if (h->q_count == 0)
-    {   // the next submit decides whether frames overlap: only while this is the device's only encoder
-        const int live = (h->device >= 0 && h->device < 64 ? g_encoders_live[h->device].load() : 2) + (h->is_encoder ? 0 : 1);
-        return live <= 1 ? h->nslots : 2;
-    }
-    if (!h->overlap_on) return 2;
-    return h->frame_seq >= h->epoch_limit ? 0 : h->nslots;      // 0: the overlap epochs restart, which needs the device drained
+    return h->overlap ? h->nslots : 2;
 }
 
 int evxgpu_encode_upload(evxgpu_handle *h, const uint8_t *rgb_host)
@@ -896,27 +815,14 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     if (!h || !rgb || quality < 1 || quality > 31 || (frame_type != 0 && frame_type != 1)) return fail(1, "evxgpu_encode_submit: bad argument");
     // one frame in flight -- or, with bin-only output and string buffers that cannot overflow, a second one queued behind it
     // (or, while consecutive frames overlap on the device, as many as there are frame slots)
-    const int cap = (h->overlap && h->overlap_on && h->out_mode == 1 && !h->k2_tile) ? h->nslots : 2;
+    const int cap = (h->overlap && h->out_mode == 1) ? h->nslots : 2;
     if (h->q_count >= cap || (h->q_count >= 1 && !(h->out_mode == 1 && h->bins_cap_bits >= h->bins_worst_bits)))
         return fail(8, "evxgpu_encode_submit: previous frame not collected");
     CK(cudaSetDevice(h->device));
+    if (h->h_diag && h->h_diag[0])
+        return fail(5, "evxgpu_encode_submit: a device-side wait of an earlier frame ran out of time (the context is lost)");
     if (!h->is_encoder && h->device >= 0 && h->device < 64) { g_encoders_live[h->device].fetch_add(1); h->is_encoder = true; }
-    if (h->overlap && h->out_mode == 1 && !h->k2_tile)
-    {
-        if (h->q_count == 0)
-        {   // nothing in flight: the moment to switch between overlapped frames and frame after frame
-            const bool want = g_encoders_live[h->device].load() <= 1;
-            if (want != h->overlap_on)
-            {
-                int rc = sync_all(h);                    // drained (collected frames may still be deblocking)
-                if (rc) return rc;
-                use_slot(h, 0);
-                for (int k = 0; k < EVX_MAX_SLOTS; ++k) h->fs[k].used = false;   // an overlapped frame that follows has no predecessor to wait for
-                h->overlap_on = want;
-            }
-        }
-        if (h->overlap_on) return submit_overlap(h, rgb, rgb_is_device, frame_type, frame_index, quality);
-    }
+    if (h->overlap && h->out_mode == 1) return submit_pipelined(h, rgb, rgb_is_device, frame_type, frame_index, quality);
     const int q = (h->q_head + h->q_count) % h->nslots;
     h->slot = q;
     if (h->timing) t_fold(h, q);                 // the frame that used this slot before was collected long ago
@@ -978,10 +884,11 @@ int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins_out, uint
         CK(cudaStreamSynchronize(h->stream));
         const uint64_t want = ((uint64_t) total + total / 2 + 4096) & ~63ull;
         if (want > 0xFFFFFFFFull) return fail(3, "evxgpu_encode_collect_bins: slice of more than 2^32 bins");
-        for (int k = 0; k < EVX_MAX_SLOTS; ++k)
+        for (int k = 0; k < h->nslots; ++k)
         {
             cudaFree(h->d_bins[k]); h->d_bins[k] = NULL;
             if (cudaMalloc(&h->d_bins[k], (size_t) want / 8 + 8) != cudaSuccess) return fail(3, "evxgpu_encode_collect_bins: out of device memory");
+            h->bins_dirty_bits[k] = (uint32_t) want;            // fresh memory: all of it is cleared before its next use
         }
         h->bins_cap_bits = (uint32_t) want;
         h->slot = q;
@@ -1006,6 +913,7 @@ int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins_out, uint
     }
     h->pending_bins[q] = false;
     h->bins_last_total = total;
+    h->bins_dirty_bits[q] = std::min<uint32_t>(h->bins_cap_bits, total);
     h->last_slot = q;
     if (h->out_mode == 1) { h->q_head = (h->q_head + 1) % h->nslots; h->q_count--; h->pending_encode = h->q_count > 0; }
     *bins_out = reinterpret_cast<const uint64_t *>(h->h_bins[q] + 4);
@@ -1155,15 +1063,11 @@ int evxgpu_debug_set_bins_capacity(evxgpu_handle *h, uint32_t bits)
     return alloc_bins(h, bits & ~63u, bits & ~63u);
 }
 
-// debug: the frame-overlap counters ([slot][rows_done, final, k2, -]) and the epochs of the two slots, read over the copy
-// stream so that it works while the frame streams are busy (or stuck)
-int evxgpu_debug_overlap_state(evxgpu_handle *h, unsigned int *out10)
+// debug: the last diagnostic of a device-side wait that ran out of time: out4 = { what, a, b, c } (what = 0: none)
+int evxgpu_debug_wait_diag(evxgpu_handle *h, unsigned int *out4)
 {
-    if (!h || !out10 || !h->overlap) return 1;
-    CK(cudaSetDevice(h->device));
-    CK(cudaMemcpyAsync(out10, h->d_flags, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, h->copy_stream));
-    CK(cudaStreamSynchronize(h->copy_stream));
-    out10[8] = h->fs[0].epoch; out10[9] = h->fs[1].epoch;
+    if (!h || !out4) return 1;
+    for (int k = 0; k < 4; ++k) out4[k] = h->h_diag ? h->h_diag[k] : 0u;
     return 0;
 }
 

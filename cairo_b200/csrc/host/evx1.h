@@ -180,6 +180,10 @@ struct evx1_config
     int32 deblocking;        // EVX_ENABLE_DEBLOCKING (default 1)
     int32 periodic_intra;    // EVX_PERIODIC_INTRA_RATE (default 3600; 0 = never)
     int32 default_quality;   // EVX_DEFAULT_QUALITY_LEVEL (default 8)
+    int32 frame_slots;       // encoder: frames of the stream in flight on the device at once (0 = the device library's default)
+    int32 coder_threads;     // encoder: threads running the arithmetic coder of retired frames (0 = default 6, at most 8)
+    int32 device_frames;     // 1: the image pointers of encode()/submit() and decode()/collect() are DEVICE memory
+                             //    (RGB8, tightly pitched) on cfg.device -- capture / present paths that never touch the host
 };
 
 void default_config(evx1_config *cfg);

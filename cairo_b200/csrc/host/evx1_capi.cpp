@@ -35,6 +35,19 @@ evx1c_encoder *evx1c_encoder_create(int device, int ref_count, int linear_quant,
     return e;
 }
 
+evx1c_encoder *evx1c_encoder_create_ex(int device, int ref_count, int linear_quant, int deblocking, int periodic_intra, int default_quality,
+                                       int frame_slots, int coder_threads, int device_frames)
+{
+    evx1c_encoder *e = new (std::nothrow) evx1c_encoder();
+    if (!e) return NULL;
+    evx1_config c = make_config(device, ref_count, linear_quant, deblocking, periodic_intra, default_quality);
+    if (frame_slots > 0) c.frame_slots = frame_slots;
+    if (coder_threads > 0) c.coder_threads = coder_threads;
+    c.device_frames = device_frames > 0 ? 1 : 0;
+    if (create_encoder_ex(c, &e->enc) != EVX_SUCCESS) { delete e; return NULL; }
+    return e;
+}
+
 void evx1c_encoder_destroy(evx1c_encoder *e) { if (e) { destroy_encoder(e->enc); delete e; } }
 int evx1c_encoder_clear(evx1c_encoder *e) { return e ? e->enc->clear() : EVX_ERROR_INVALIDARG; }
 int evx1c_encoder_insert_intra(evx1c_encoder *e) { return e ? e->enc->insert_intra() : EVX_ERROR_INVALIDARG; }
@@ -101,6 +114,16 @@ evx1c_decoder *evx1c_decoder_create(int device, int linear_quant, int deblocking
     evx1c_decoder *d = new (std::nothrow) evx1c_decoder();
     if (!d) return NULL;
     if (create_decoder_ex(make_config(device, -1, linear_quant, deblocking, -1, -1), &d->dec) != EVX_SUCCESS) { delete d; return NULL; }
+    return d;
+}
+
+evx1c_decoder *evx1c_decoder_create_ex(int device, int linear_quant, int deblocking, int device_frames)
+{
+    evx1c_decoder *d = new (std::nothrow) evx1c_decoder();
+    if (!d) return NULL;
+    evx1_config c = make_config(device, -1, linear_quant, deblocking, -1, -1);
+    c.device_frames = device_frames > 0 ? 1 : 0;
+    if (create_decoder_ex(c, &d->dec) != EVX_SUCCESS) { delete d; return NULL; }
     return d;
 }
 

@@ -84,7 +84,7 @@ class encoder_session : public evx1_encoder
         uint32 n_noncopy, d2h_bytes;
         uint64_t nbins;
     };
-    enum { kDevMax = 3 };
+    enum { kDevMax = 8 };
     pending_frame dev_[kDevMax];                   // dev_[0] is the oldest of the frames on the device
     int dev_count_;                                // how many the device library takes: evxgpu_encode_capacity
     std::vector<evxgpu_block_desc> table_;         // retired frame, table + records output
@@ -92,7 +92,8 @@ class encoder_session : public evx1_encoder
 
     // Bin-string output: the arithmetic coder of a slice needs nothing but the slice's bins (the coder is reset per
     // frame, serialize.cpp:323), so retired frames are coded by worker threads, several at a time, and collected in order.
-    enum { kJobs = 6, kWorkers = 4 };
+    enum { kJobs = 12, kMaxWorkers = 8 };
+    int kWorkers;                                  // evx1_config::coder_threads
     enum job_state { JOB_FREE = 0, JOB_QUEUED, JOB_RUNNING, JOB_DONE };
     struct job
     {
@@ -107,7 +108,7 @@ class encoder_session : public evx1_encoder
     int head_, count_;                             // retired, uncollected frames: jobs head_, head_+1, ... (mod kJobs)
     std::mutex m_;
     std::condition_variable cv_work_, cv_done_;
-    std::thread workers_[kWorkers];
+    std::thread workers_[kMaxWorkers];
     bool threads_up_, stop_;
 
     void run_job(job &j)
@@ -193,14 +194,14 @@ class encoder_session : public evx1_encoder
         header_.frame_width = (uint16) width;
         header_.frame_height = (uint16) height;
         header_.size = sizeof(stream_header);
-        evxgpu_config gc = { cfg_.ref_count, cfg_.linear_quant, cfg_.deblocking, 0 };
+        evxgpu_config gc = { cfg_.ref_count, cfg_.linear_quant, cfg_.deblocking, cfg_.frame_slots };
         int rc = evxgpu_create(cfg_.device, (int) width, (int) height, &gc, NULL, &gpu_);
         if (rc) return map_gpu_status(rc);
         // The device binarises the slice (include/evxgpu.h, evxgpu_set_output); EVX1_HOST_BINARISE=1 keeps
         // the table + records path and binarises here instead (same bits; for A/B measurements).
         device_bins_ = getenv("EVX1_HOST_BINARISE") == NULL;
         { const char *ct = getenv("EVX1_CODER_THREAD"); coder_threads_ = !(ct && ct[0] == '0'); }      // EVX1_CODER_THREAD=0: code on the caller's thread
-        if (device_bins_ && (rc = evxgpu_set_output(gpu_, 1))) return map_gpu_status(rc);
+        if (device_bins_ && (rc = evxgpu_set_output(gpu_, 1))) { evxgpu_destroy(gpu_); gpu_ = NULL; return map_gpu_status(rc); }
         int mbw = (int) ((width + 15) / 16), mbh = (int) ((height + 15) / 16);
         writer_.configure(mbw, mbh, cfg_.ref_count);
         for (int k = 0; k < kJobs; ++k) jobs_[k].writer.configure(mbw, mbh, cfg_.ref_count);
@@ -216,8 +217,6 @@ class encoder_session : public evx1_encoder
     {
         if (count_ >= max_jobs()) return EVX_ERROR_NOT_READY;
         pending_frame f = dev_[0];
-        for (int k = 1; k < dev_count_; ++k) dev_[k - 1] = dev_[k];
-        dev_count_--;
         job &j = jobs_[(head_ + count_) % kJobs];
         int rc;
         const double tw = now_ms();
@@ -235,6 +234,8 @@ class encoder_session : public evx1_encoder
             rc = evxgpu_encode_collect(gpu_, table_.data(), records_.data(), &f.n_noncopy);
             if (rc) return EVX_ERROR_EXECUTION_FAILURE;
         }
+        for (int k = 1; k < dev_count_; ++k) dev_[k - 1] = dev_[k];       // (only now: a failed collect keeps the frame)
+        dev_count_--;
         f.d2h_bytes = (uint32) evxgpu_d2h_bytes(gpu_);
         f.gpu_ms = now_ms() - f.t_submit;
         f.wait_ms = now_ms() - tw;
@@ -258,6 +259,7 @@ public:
     explicit encoder_session(const evx1_config &cfg)
         : cfg_(cfg), initialized_(false), gpu_(NULL), device_bins_(true), coder_threads_(true), dev_count_(0), head_(0), count_(0), threads_up_(false), stop_(false)
     {
+        kWorkers = cfg.coder_threads > 0 ? std::min<int>(cfg.coder_threads, kMaxWorkers) : 6;
         memset(&stats_, 0, sizeof(stats_));
         memset(&header_, 0, sizeof(header_));
         memset(dev_, 0, sizeof(dev_));
@@ -300,7 +302,7 @@ public:
         // With frames on the device the new frame's host->device copy starts right away, on the copy stream, under their
         // kernels -- before this thread waits for the oldest of them: a frame's kernels cannot start before its pixels are
         // there, and with three frames overlapping the new one is due the moment its slot is free.
-        const bool early = dev_count_ >= 1;
+        const bool early = dev_count_ >= 1 && !cfg_.device_frames;        // (a frame already on the device needs no upload)
         if (early && dev_count_ >= std::min<int>(kDevMax, evxgpu_encode_capacity(gpu_)) && count_ >= max_jobs()) return EVX_ERROR_NOT_READY;
         if (early && evxgpu_encode_upload(gpu_, rgb)) return EVX_ERROR_EXECUTION_FAILURE;
         while (dev_count_ > 0 && dev_count_ >= std::min<int>(kDevMax, evxgpu_encode_capacity(gpu_)))
@@ -318,13 +320,22 @@ public:
             // the frame uploaded above; its kernels are queued right behind those of the frames still on the device
             rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
             while (rc == 8 && dev_count_ > 0)
-            {   // (also: frames stopped overlapping next to another encoder, or the overlap epochs restart -- that needs the device drained)
+            {
                 evx_status st = retire(true);
                 if (evx_failed(st)) return st;
                 rc = evxgpu_encode_submit(gpu_, NULL, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
             }
         }
-        else rc = evxgpu_encode_submit(gpu_, rgb, 0, (int) frame_.type, frame_.index, (int) frame_.quality);
+        else
+        {
+            rc = evxgpu_encode_submit(gpu_, rgb, cfg_.device_frames ? 1 : 0, (int) frame_.type, frame_.index, (int) frame_.quality);
+            while (rc == 8 && dev_count_ > 0)
+            {
+                evx_status st = retire(true);
+                if (evx_failed(st)) return st;
+                rc = evxgpu_encode_submit(gpu_, rgb, cfg_.device_frames ? 1 : 0, (int) frame_.type, frame_.index, (int) frame_.quality);
+            }
+        }
         if (rc) return EVX_ERROR_EXECUTION_FAILURE;
         pending_frame &f = dev_[dev_count_++];
         memset(&f, 0, sizeof(f));
@@ -654,7 +665,7 @@ private:
         const double t1 = now_ms();
         int rc = evxgpu_decode_submit(gpu_, table_.data(), rec, n_noncopy, (int) j.desc.type, j.desc.index);
         if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        rc = evxgpu_decode_collect(gpu_, static_cast<uint8 *>(output), 0);
+        rc = evxgpu_decode_collect(gpu_, static_cast<uint8 *>(output), cfg_.device_frames ? 1 : 0);
         if (rc) return EVX_ERROR_EXECUTION_FAILURE;
         stats_.entropy_ms = j.ms + (t1 - t0); stats_.gpu_ms = now_ms() - t1; stats_.noncopy_blocks = n_noncopy;
         stats_.slice_bits = j.end - j.pos; stats_.d2h_bytes = (uint32) ((size_t) header_.frame_width * header_.frame_height * 3);
@@ -673,6 +684,9 @@ void default_config(evx1_config *cfg)                        // config.h:38-53
     cfg->deblocking = 1;
     cfg->periodic_intra = 3600;
     cfg->default_quality = 8;
+    cfg->frame_slots = 0;
+    cfg->coder_threads = 0;
+    cfg->device_frames = 0;
 }
 
 static bool config_ok(const evx1_config &c) { return c.ref_count >= 2 && c.ref_count <= 8 && c.device >= 0; }

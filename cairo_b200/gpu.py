@@ -20,7 +20,7 @@ T_NAMES = ["convert_in", "inter_search", "wavefront", "deblock", "decode_recon",
 
 
 class Config(C.Structure):
-    _fields_ = [("ref_count", C.c_int32), ("linear_quant", C.c_int32), ("deblocking", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("ref_count", C.c_int32), ("linear_quant", C.c_int32), ("deblocking", C.c_int32), ("frame_slots", C.c_int32)]
 
 
 _lib = None
@@ -90,12 +90,12 @@ def _check(rc, what):
 class Pipeline:
     """One video stream's device state (evxgpu_handle)."""
 
-    def __init__(self, width, height, ref_count=4, linear_quant=0, deblocking=1, device=0, stream=None):
+    def __init__(self, width, height, ref_count=4, linear_quant=0, deblocking=1, device=0, stream=None, frame_slots=0):
         self.L = lib()
         self.w, self.h_ = width, height
         self.aw, self.ah = (width + 15) // 16 * 16, (height + 15) // 16 * 16
         self.R = ref_count
-        cfg = Config(ref_count, linear_quant, deblocking, 0)
+        cfg = Config(ref_count, linear_quant, deblocking, frame_slots)
         h = C.c_void_p()
         _check(self.L.evxgpu_create(device, width, height, C.byref(cfg), stream, C.byref(h)), "evxgpu_create")
         self.h = h
@@ -122,7 +122,7 @@ class Pipeline:
             _check(self.L.evxgpu_encode_submit(self.h, _p(rgb), 0, frame_type, index, quality), "evxgpu_encode_submit")
 
     def encode_capacity(self):
-        """Submitted, uncollected frames the handle accepts (1, 2, or 3 with three overlapping frame slots)."""
+        """Submitted, uncollected frames the handle accepts (1, or its number of frame slots with bin-string output)."""
         return int(self.L.evxgpu_encode_capacity(self.h))
 
     def encode_collect(self):

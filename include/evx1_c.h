@@ -18,6 +18,11 @@ typedef struct evx1c_decoder evx1c_decoder;
 /* ref_count / linear_quant / deblocking / periodic_intra / default_quality < 0 select the
  * reference's config.h defaults (4, 0, 1, 3600, 8). */
 evx1c_encoder *evx1c_encoder_create(int device, int ref_count, int linear_quant, int deblocking, int periodic_intra, int default_quality);
+/* the same plus the additions of this build (evx1_config, cairo_b200/csrc/host/evx1.h): frames of the stream in flight on
+ * the device (0 = default), arithmetic-coder threads (0 = default), and device_frames = 1: the rgb pointers given to
+ * encode/submit are DEVICE memory on `device` (RGB8, tightly pitched; the frame must stay unchanged until collected). */
+evx1c_encoder *evx1c_encoder_create_ex(int device, int ref_count, int linear_quant, int deblocking, int periodic_intra, int default_quality,
+                                       int frame_slots, int coder_threads, int device_frames);
 void evx1c_encoder_destroy(evx1c_encoder *e);
 int evx1c_encoder_clear(evx1c_encoder *e);                       /* evx1_encoder::clear */
 int evx1c_encoder_insert_intra(evx1c_encoder *e);                /* evx1_encoder::insert_intra */
@@ -37,6 +42,8 @@ double evx1c_encoder_wait_ms(evx1c_encoder *e);      /* last collected frame: ho
 int evx1c_encoder_stats(evx1c_encoder *e, double *gpu_ms, double *entropy_ms, uint32_t *slice_bits, uint32_t *noncopy_blocks, uint32_t *d2h_bytes);
 
 evx1c_decoder *evx1c_decoder_create(int device, int linear_quant, int deblocking);
+/* device_frames = 1: rgb_out of decode/collect is DEVICE memory on `device` (the picture never visits the host) */
+evx1c_decoder *evx1c_decoder_create_ex(int device, int linear_quant, int deblocking, int device_frames);
 void evx1c_decoder_destroy(evx1c_decoder *d);
 int evx1c_decoder_clear(evx1c_decoder *d);                       /* evx1_decoder::clear */
 int evx1c_decoder_stats(evx1c_decoder *d, double *gpu_ms, double *entropy_ms);   /* last frame: submit->collect, unserialize */

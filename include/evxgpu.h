@@ -51,7 +51,7 @@ typedef struct evxgpu_config
     int32_t ref_count;        /* EVX_REFERENCE_FRAME_COUNT: ring slots incl. the current frame, 2..8 */
     int32_t linear_quant;     /* EVX_ENABLE_LINEAR_QUANTIZATION */
     int32_t deblocking;       /* EVX_ENABLE_DEBLOCKING */
-    int32_t reserved;
+    int32_t frame_slots;      /* encoder, bin-string output: frames of the stream in flight on the device at once (0 = default 6, max 8) */
 } evxgpu_config;
 
 #define EVXGPU_MB_COEFFS 384   /* 16x16 luma (row-major, stride 16) + 8x8 U + 8x8 V, int16 */
@@ -91,10 +91,9 @@ int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_
  * and uses the uploaded frame.  rgb_host must stay unchanged until that submit's frame has been collected (or the
  * handle synchronised).  An upload whose submit never happened is replaced by the next upload. */
 int evxgpu_encode_upload(evxgpu_handle *h, const uint8_t *rgb_host);
-/* How many submitted, uncollected frames the handle accepts at this moment: 1 with table + records output, 2 with
- * bin-string output, 3 while consecutive frames overlap on the device in three frame slots (the default for the
- * device's only encoder; EVXGPU_FRAME_SLOTS=2 keeps two), 0 when every frame in flight has to be collected first
- * (the overlap counters restart every 2^19 frames).  A submit beyond it returns status 8. */
+/* How many submitted, uncollected frames the handle accepts: 1 with table + records output, with bin-string output as
+ * many as it has frame slots (evxgpu_config::frame_slots; 2 with EVXGPU_FRAME_OVERLAP=0).  A submit beyond it returns
+ * status 8.  Frames in flight run concurrently on the device, each following its predecessor macroblock by macroblock. */
 int evxgpu_encode_capacity(const evxgpu_handle *h);
 
 /* The same slice as the string of bins serialize_slice feeds its arithmetic coder (serialize.cpp:156-340:
@@ -149,8 +148,9 @@ uint64_t evxgpu_launch_count(const evxgpu_handle *h);
 uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h);
 /* debug: per-row phase cycle sums of the encoder wavefront kernel, 6 x int64 per macroblock row */
 int evxgpu_debug_profile(evxgpu_handle *h, int enable, long long *out_host);
-/* debug: frame-overlap row counters, out10 = { slot 0: rows done, deblocked bands, rows searched, -, slot 1: the same, epoch of slot 0, of slot 1 } */
-int evxgpu_debug_overlap_state(evxgpu_handle *h, unsigned int *out10);
+/* debug: what a device-side wait that ran out of its time budget was waiting for (out4[0] = 0: none did).  Such a wait
+ * traps, the launch fails and every later call reports status 5; EVXGPU_WAIT_BUDGET_MS sets the budget (default 4000, 0 = none). */
+int evxgpu_debug_wait_diag(evxgpu_handle *h, unsigned int *out4);
 /* tuning knob: number of persistent CTAs of the decoder's wavefront kernel (0 = default) */
 int evxgpu_set_wave_grid(evxgpu_handle *h, int ctas);
 /* tuning knob: persistent CTAs of the encoder's wavefront kernel (0 = default, ceil(mbw/3) + 4: the number of

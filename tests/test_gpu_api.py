@@ -169,7 +169,7 @@ def test_pipelined_1080p_equals_synchronous_and_state_rules():
         except RuntimeError:                      # one uncollected frame too many: EVX_ERROR_NOT_READY
             break
         held += 1
-    assert held in (8, 9), held
+    assert held >= 8, held                        # (frame slots on the device + retired frames being coded)
     out = []
     for t in range(held, n):                      # that much lookahead from here on
         d, b = p.collect()
@@ -186,11 +186,9 @@ def test_pipelined_1080p_equals_synchronous_and_state_rules():
         assert out[t][1] == sync[t][1] and (out[t][0] == sync[t][0]).all(), t
 
 
-@pytest.mark.parametrize("env", [{"EVXGPU_FRAME_SLOTS": "3", "EVXGPU_EPOCH_LIMIT": "4"}, {"EVXGPU_FRAME_SLOTS": "2", "EVXGPU_EPOCH_LIMIT": "3"},
-                                 {"EVXGPU_FRAME_OVERLAP": "0"}])
-def test_pipelined_session_across_epoch_restarts(env, monkeypatch):
-    """evx1_encoder::submit/collect while the frame-overlap epochs restart every few frames (the device library then takes
-    no frame until it is drained: evxgpu_encode_capacity = 0) and with two or three frame slots: the same bytes as encode()."""
+@pytest.mark.parametrize("env", [{"EVXGPU_FRAME_SLOTS": "3"}, {"EVXGPU_FRAME_SLOTS": "2"}, {"EVXGPU_FRAME_SLOTS": "8"}, {"EVXGPU_FRAME_OVERLAP": "0"}])
+def test_pipelined_session_frame_slots(env, monkeypatch):
+    """evx1_encoder::submit/collect with two, three and eight frame slots and without the frame pipeline: the same bytes as encode()."""
     from cairo_b200 import api
     w, h, n = 640, 368, 14
     frames = [synth.frame(w, h, t, 11, "moving") for t in range(n)]
@@ -200,13 +198,13 @@ def test_pipelined_session_across_epoch_restarts(env, monkeypatch):
     for t in range(n):
         d, b = a.encode(frames[t])
         sync.append((d.copy(), b))
-    del a                                         # the pipelined session is the device's only encoder: frames overlap
+    del a
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     p = api.evx1_encoder(ref_count=2)
     p.set_quality(12)
     out = []
-    look = 5
+    look = 9
     for t in range(n):
         p.submit(frames[t])
         if t >= look:
