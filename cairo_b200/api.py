@@ -62,6 +62,10 @@ def lib():
     L.evx1c_parsed_slice_destroy.argtypes = [vp]
     L.evx1c_slice_reader_parse.argtypes = [vp, vp, u32, vp]
     L.evx1c_slice_reader_apply.argtypes = [vp, vp, vp, vp, C.POINTER(u32)]
+    L.evx1c_scatter_records.restype = u32
+    L.evx1c_scatter_records.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.evx1c_gather_records.restype = u32
+    L.evx1c_gather_records.argtypes = [vp, vp, vp, vp, i32, i32, vp]
     _lib = L
     return L
 
@@ -279,3 +283,20 @@ class SliceReader:
         st = self.L.evx1c_slice_reader_unserialize(self.h, _p(data), nbits, _p(self.table), _p(rec), C.byref(n))
         assert st == 0, st
         return self.table.copy(), rec[:n.value].copy()
+
+
+def scatter_records(table, records, planes, aw, ah):
+    """include/evxgpu_records.h: the non-copy macroblocks' records into persistent coefficient planes (Y, U, V int16)."""
+    table = np.ascontiguousarray(table)
+    records = np.ascontiguousarray(records, dtype=np.int16)
+    y, u, v = planes
+    return int(lib().evx1c_scatter_records(_p(table), _p(records), aw, ah, _p(y), _p(u), _p(v)))
+
+
+def gather_records(table, planes, aw, ah):
+    """include/evxgpu_records.h: the records of the table's non-copy macroblocks out of coefficient planes."""
+    table = np.ascontiguousarray(table)
+    y, u, v = [np.ascontiguousarray(a, dtype=np.int16) for a in planes]
+    out = np.zeros((table.shape[0], 384), dtype=np.int16)
+    n = int(lib().evx1c_gather_records(_p(table), _p(y), _p(u), _p(v), aw, ah, _p(out)))
+    return out[:n].copy()

@@ -29,16 +29,22 @@
 // frame is ONE launch whose CTAs wait for nothing but (a) tickets of the same kernel claimed earlier and (b) the
 // previous frame's kernel, which was launched -- and has started -- before this one.  No wait can point at work
 // that still needs an SM slot this kernel's waiting CTAs hold, whoever else uses the device:
-//   * tickets, claimed in this order:  S(0) S(1) W(0) S(2) W(1) ... S(H-1) W(H-3) W(H-2) W(H-1), where S(r) is the
-//     inter search of macroblock row r (all ten warps of the CTA pull (macroblock, reference) items, evx_k2_item;
-//     each result is stamped) and W(r) the wavefront row r, whose block loader waits for the stamps of the
-//     macroblock it stages;
-//   * deblocking follows the wavefront inside the row CTAs: the sweep decomposes into independent 8x8 tiles
-//     (evx_kernels.cuh, K4); the tiles of macroblock (X, Y) -- luma crossings {2X, 2X+1} x {2Y, 2Y+1}, chroma (X, Y),
-//     plus the frame's right / bottom border tiles in the last column / row -- touch macroblocks (X-1..X, Y-1..Y),
-//     whose unfiltered samples the intra search reads last from macroblock (X+2, Y+3).  So the block loader of row
-//     r filters, four macroblock columns at a time, tile row r-3 (the last row also H-3 .. H-1) up to column x-2
-//     once macroblock x of its own row is complete, and publishes dbk[Y] = base + filtered tile columns;
+//   * tickets are the wavefront rows W(0) .. W(H-1), claimed in order by the ROW CTAs.  The inter search is a set of
+//     per-row queues: row y's (macroblock, reference) items are claimed in column order through a counter k2c[y].
+//     SERVICE CTAs (the first blocks of the grid; they take no row) scan the rows and take, among the items the previous
+//     frame is already final around, the one its row will need soonest; such an item never waits.  And a row's block
+//     loader, before it waits for the stamps of the macroblock it stages, claims and runs whatever item of ITS OWN row up
+//     to that macroblock nobody has taken yet (waiting, if it must, for the previous frame around it) -- so the stamps it
+//     then waits for are in the hands of running warps, whether or not any service CTA is resident;
+//   * deblocking follows the wavefront: the sweep decomposes into independent 8x8 tiles (evx_kernels.cuh, K4); the
+//     tiles of macroblock (X, Y) -- luma crossings {2X, 2X+1} x {2Y, 2Y+1}, chroma (X, Y), plus the frame's right /
+//     bottom border tiles in the last column / row -- touch macroblocks (X-1..X, Y-1..Y), whose unfiltered samples the
+//     intra search reads last from macroblock (X+2, Y+3).  A JOB is four tile columns of one tile row; tile row Y's
+//     jobs are claimed in order through a counter jc[Y] by the service CTAs, each one once the wavefront has passed it,
+//     filtered one tile per lane, and dbk[Y] = base + filtered tile columns is published in order.  The CTA of the last
+//     row takes whatever is left when the frame's rows are done.  (Per-row counters, not one queue in wavefront order:
+//     rows do not keep the ideal three-step formation, and one late row at the head of a global queue held up
+//     everything behind it -- measured: frames trailed each other by 150 steps instead of 30);
 //   * the NEXT frame reads this one as a reference around (bx, by): samples of macroblocks (bx-2..bx+2, by-2..by+2),
 //     final once the tiles of columns <= bx+3 in tile rows by-2 .. by+3 are done.  Its search items (and, in an intra
 //     frame, its block loaders) wait for dbk[by-2 .. by+3] >= min(bx+4, W), six lanes polling one row each.  That
@@ -84,18 +90,18 @@ struct EvxK3Smem
     int4 cand[2][16];                         // sub-pel tests: {sad, mad, 0, legal}
     int2 cand2[2][16];                        // full-pel rounds: raw {sad, mad} per cell
     uint64_t full[2], fullb[2], full2[2], empty[2];   // full: block data; fullb: window columns <= n+1; full2: column n+2
+    uint64_t k2bar;                           // the block loader's own search window (it serves the search queue when it must)
+    __align__(128) uint8_t k2win[EVX_K2W_BYTES];
     int last_motion, last_coded;              // K8 bookkeeping (thread 0)
 };
 
 // the CTA's current ticket; the search role's per-warp windows share the wavefront role's shared memory
-struct EvxFrameCtl { int role, row; };
-enum { EVX_ROLE_WAVEFRONT = 0, EVX_ROLE_SEARCH = 1, EVX_ROLE_DONE = 2 };
+struct EvxFrameCtl { int row; };
 #define EVX_K3_WARPS (EVX_K3_NT / 32)
 struct EvxK2RoleSmem
 {
     uint8_t win[EVX_K3_WARPS][EVX_K2W_BYTES];      // 128-byte aligned TMA destinations (6912 = 54 x 128)
     uint64_t bar[EVX_K3_WARPS];
-    int next;                                      // next (macroblock, reference) item of the row
 };
 #define EVX_FRAME_CTL_BYTES 128
 #define EVX_FRAME_SMEM (EVX_FRAME_CTL_BYTES + (sizeof(EvxK3Smem) > sizeof(EvxK2RoleSmem) ? sizeof(EvxK3Smem) : sizeof(EvxK2RoleSmem)))
@@ -125,24 +131,13 @@ __device__ __forceinline__ void evx_gate_prev(const EvxK3Params &p, int bx, int 
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
-// S(by): the inter search of one macroblock row; every warp pulls (macroblock, reference) items in column order
-__device__ __noinline__ void evx_k2_role(EvxK2RoleSmem &K, const EvxK3Params &p, int by, int tid)
+// How many tile columns the previous frame still lacks around macroblock (bx, row) (<= 0: final there): six lanes look at
+// tile rows row-2 .. row+3 (evx_gate_prev).
+__device__ __forceinline__ int evx_gate_shortfall(const EvxK3Params &p, int bx, int row, int lane)
 {
-    const int warp = tid >> 5, lane = tid & 31;
-    const int nref = p.R - 1, items = p.g.mbw * nref, nmb = p.g.mbw * p.g.mbh;
-    uint32_t phase = 0;
-    for (;;)
-    {
-        int it = 0;
-        if (lane == 0) it = atomicAdd(&K.next, 1);
-        it = __shfl_sync(0xFFFFFFFFu, it, 0);
-        if (it >= items) break;
-        const int bx = it / nref, ref = it - bx * nref;
-        evx_gate_prev(p, bx, by, lane);
-        const int rslot = (int) ((p.frame_index + (uint32_t) p.R - (uint32_t) (ref + 1)) % (uint32_t) p.R);       // common.cpp:192-195
-        evx_k2_item(&p.maps.m[ref * 3], p.src, p.ring[rslot], p.g, p.thr, bx, by, ref, lane, K.win[warp], &K.bar[warp], phase,
-                    p.inter + (size_t) ref * nmb + (size_t) by * p.g.mbw + bx, p.counters, p.stamp);
-    }
+    const unsigned int want = p.prev_base + (unsigned int) min(bx + 4, p.g.mbw);
+    const int short_by = (int) (want - evx_ld_relaxed_u32(p.prev_dbk + max(0, min(row + 3 - min(lane, 5), p.g.mbh - 1))));
+    return __reduce_max_sync(0xFFFFFFFFu, short_by);
 }
 
 // A call, not inlined: the tile's 64 samples live in registers, and inlined into the frame kernel they would raise the
@@ -153,6 +148,218 @@ __device__ __noinline__ void evx_deblock_tile_call(int16_t *y, int16_t *u, int16
     EvxPlanes pl; pl.y = y; pl.u = u; pl.v = v;
     EvxGeom g; g.w = w; g.h = h; g.vw = w; g.vh = h; g.mbw = w >> 4; g.mbh = h >> 4;
     evx_deblock_tile(pl, g, table, comp, tx, ty);
+}
+
+// One deblocking job: tile columns [x0, cnt) of tile row Y, one tile per lane and pass; then the job's count is
+// published in order (the job before it in the row was claimed earlier and is in a running warp's hands).
+__device__ __noinline__ void evx_deblock_job(const EvxK3Params &p, int Y, int x0, int cnt, int lane)
+{
+    const EvxGeom g = p.g;
+    if (p.deblocking)
+    {
+        const EvxPlanes cur = p.ring[(int) (p.frame_index % (uint32_t) p.R)];
+        const int last = cnt == g.mbw ? 1 : 0, bot = Y == g.mbh - 1 ? 1 : 0;
+        const int nlx = 2 * (cnt - x0) + last, ncx = (cnt - x0) + last;
+        const int nl = nlx * (2 + bot), nc = ncx * (1 + bot);
+        for (int k = lane; k < nl + 2 * nc; k += 32)
+        {
+            if (k < nl) evx_deblock_tile_call(cur.y, cur.u, cur.v, g.w, g.h, p.table, 0, 2 * x0 + k % nlx, 2 * Y + k / nlx);
+            else { const int c = (k - nl) % nc; evx_deblock_tile_call(cur.y, cur.u, cur.v, g.w, g.h, p.table, 1 + (k - nl) / nc, x0 + c % ncx, Y + c / ncx); }
+        }
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+        if (x0 > 0) EVX_BOUNDED_WAIT(p.wait, (int) (evx_ld_relaxed_u32(p.dbk + Y) - (p.dbk_base + (unsigned int) x0)) >= 0, 200, 8u, (unsigned int) Y, (unsigned int) x0, 0u);
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.dbk + Y), "r"(p.dbk_base + (unsigned int) cnt) : "memory");
+    }
+    __syncwarp();
+}
+
+#define EVX_DBK_CHUNK 4           // tile columns per deblocking job
+
+// per-row counters in p.sync: progress[y] (macroblocks of wavefront row y complete), k2c[y] (search items of row y
+// claimed), jc[Y] (deblocking jobs of tile row Y claimed)
+__device__ __forceinline__ int *evx_progress(const EvxK3Params &p) { return p.sync + 2; }
+__device__ __forceinline__ int *evx_k2c(const EvxK3Params &p) { return p.sync + 2 + p.g.mbh; }
+__device__ __forceinline__ int *evx_jc(const EvxK3Params &p) { return p.sync + 2 + 2 * p.g.mbh; }
+
+// Scans the tile rows (lane = row within a chunk of 32) for a deblocking job the wavefront has passed -- tile columns
+// [4c, 4c+4) of tile row Y may be filtered once macroblock (min(4c+5, W-1), min(Y+3, H-1)) is complete -- claims one by
+// compare-and-swap on jc[Y] (a claimed job must never wait for the wavefront) and runs it.  `rot` spreads the warps
+// over the ready rows.  Returns 1 if a job was done, 0 if none is ready, -1 if every job of the frame is claimed.
+__device__ __forceinline__ int evx_serve_deblock(const EvxK3Params &p, int lane, unsigned int rot)
+{
+    const int H = p.g.mbh, W = p.g.mbw, nch = (W + EVX_DBK_CHUNK - 1) / EVX_DBK_CHUNK;
+    int *jc = evx_jc(p);
+    const int *progress = evx_progress(p);
+    bool all = true;
+    for (int base = 0; base < H; base += 32)
+    {
+        const int Y = base + lane;
+        int c = nch;
+        if (Y < H) c = evx_ld_relaxed(jc + Y);
+        bool ready = false;
+        if (c < nch) ready = evx_ld_relaxed(progress + min(Y + 3, H - 1)) >= min(min(c * EVX_DBK_CHUNK + EVX_DBK_CHUNK, W) + 1, W - 1) + 1;
+        if (__any_sync(0xFFFFFFFFu, c < nch)) all = false;
+        unsigned int mask = __ballot_sync(0xFFFFFFFFu, ready);
+        while (mask)
+        {
+            const unsigned int r = rot & 31u, m2 = (mask >> r) | (r ? mask << (32u - r) : 0u);       // first ready lane at or after `rot`
+            const int l = (int) ((__ffs(m2) - 1 + r) & 31u);
+            int ok = 0;
+            if (lane == l) ok = atomicCAS(jc + Y, c, c + 1) == c;
+            ok = __shfl_sync(0xFFFFFFFFu, ok, l);
+            if (ok)
+            {
+                const int Yj = __shfl_sync(0xFFFFFFFFu, Y, l), cj = __shfl_sync(0xFFFFFFFFu, c, l);
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+                evx_deblock_job(p, Yj, cj * EVX_DBK_CHUNK, min(cj * EVX_DBK_CHUNK + EVX_DBK_CHUNK, W), lane);
+                return 1;
+            }
+            mask &= ~(1u << l);
+        }
+    }
+    return all ? -1 : 0;
+}
+
+// One search item of row y: item index it = x * nref + ref.
+__device__ __forceinline__ void evx_run_search_item(const EvxK3Params &p, int y, int it, int lane, uint8_t *win, uint64_t *bar, uint32_t &phase)
+{
+    const int nref = p.R - 1, nmb = p.g.mbw * p.g.mbh, bx = it / nref, ref = it - bx * nref;
+    const int rslot = (int) ((p.frame_index + (uint32_t) p.R - (uint32_t) (ref + 1)) % (uint32_t) p.R);       // common.cpp:192-195
+    evx_k2_item(&p.maps.m[ref * 3], p.src, p.ring[rslot], p.g, p.thr, bx, y, ref, lane, win, bar, phase,
+                p.inter + (size_t) ref * nmb + (size_t) y * p.g.mbw + bx, p.counters, p.stamp);
+}
+
+// Picks the search item to run next and runs it.  Every lane looks at three rows (groups of 96 rows): how far the search
+// is ahead of the wavefront there, and whether the previous frame is final around the row's next item -- all loads of a
+// group in two round trips.  A row is URGENT when the search is fewer than EVX_K2_AHEAD columns ahead of its wavefront
+// (or it is one of the next few rows to start and has fewer than that many columns done); the warp takes the first
+// urgent open row at or after its own offset `rot` (so that the warps spread over the rows instead of all racing for
+// the single most urgent one), else the open row that will need its item soonest.  Claimed by compare-and-swap on
+// k2c[y].  Returns 1 / 0 (nothing ready) / -1 (every item of the frame is claimed).
+#define EVX_K2_AHEAD 12
+__device__ __forceinline__ int evx_serve_search(const EvxK3Params &p, int lane, uint8_t *win, uint64_t *bar, uint32_t &phase, unsigned int rot)
+{
+    const int H = p.g.mbh, W = p.g.mbw, nref = p.R - 1, per_row = W * nref;
+    int *k2c = evx_k2c(p);
+    const int *progress = evx_progress(p);
+    for (int attempt = 0; attempt < 3; ++attempt)
+    {
+        bool all = true;
+        int pick = -1, pick_wait = 0x7FFFFFFF, first_idle = -1;
+        for (int g0 = 0; g0 < H && pick < 0; g0 += 96)
+        {
+            int it[3], prog[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                const int y = g0 + 32 * k + lane;
+                it[k] = per_row; prog[k] = 1;
+                if (y < H) { it[k] = evx_ld_relaxed(k2c + y); prog[k] = evx_ld_relaxed(progress + y); }
+            }
+            bool open[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                const int y = g0 + 32 * k + lane;
+                open[k] = it[k] < per_row;
+                if (open[k] && p.prev_dbk)
+                {
+                    const unsigned int want = p.prev_base + (unsigned int) min(it[k] / nref + 4, W);
+                    int worst = -1;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) worst = max(worst, (int) (want - evx_ld_relaxed_u32(p.prev_dbk + max(0, min(y + 3 - j, H - 1)))));
+                    open[k] = worst <= 0;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                if (__any_sync(0xFFFFFFFFu, it[k] < per_row)) all = false;
+                // rows are claimed in order, so the rows that have not started form a suffix: the first of them
+                const unsigned int idle = __ballot_sync(0xFFFFFFFFu, g0 + 32 * k + lane < H && prog[k] == 0);
+                if (first_idle < 0 && idle) first_idle = g0 + 32 * k + __ffs(idle) - 1;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                const int y = g0 + 32 * k + lane, x = it[k] / nref;
+                const int wait = prog[k] > 0 ? x - prog[k] : x + 3 * (first_idle >= 0 ? max(0, y - first_idle) : 0);
+                const bool urgent = open[k] && (prog[k] > 0 ? wait < EVX_K2_AHEAD : (first_idle >= 0 && y - first_idle < 6 && x < EVX_K2_AHEAD));
+                const unsigned int um = __ballot_sync(0xFFFFFFFFu, urgent);
+                if (um && pick < 0)
+                {
+                    const unsigned int r = (rot + 11u * (unsigned int) attempt) & 31u, m2 = (um >> r) | (r ? um << (32u - r) : 0u);
+                    pick = g0 + 32 * k + (int) ((__ffs(m2) - 1 + r) & 31u);
+                }
+                const int mw = __reduce_min_sync(0xFFFFFFFFu, open[k] ? ((max(wait, 0) << 12) | (y & 0xFFF)) : 0x7FFFFFFF);
+                pick_wait = min(pick_wait, mw);
+            }
+        }
+        if (pick < 0)
+        {
+            if (pick_wait == 0x7FFFFFFF) return all ? -1 : 0;
+            pick = pick_wait & 0xFFF;               // nothing urgent: the open row that needs its next item soonest
+        }
+        int it = 0, ok = 0;
+        if (lane == 0)
+        {
+            it = evx_ld_relaxed(k2c + pick);
+            ok = it < per_row && atomicCAS(k2c + pick, it, it + 1) == it;
+        }
+        ok = __shfl_sync(0xFFFFFFFFu, ok, 0); it = __shfl_sync(0xFFFFFFFFu, it, 0);
+        if (!ok) continue;                          // somebody else took it: look again
+        if (p.prev_dbk)
+        {   // (the claim may be one item further than the one whose gate was seen open: the next column of the same row)
+            while (evx_gate_shortfall(p, it / nref, pick, lane) > 0) __nanosleep(200);
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        }
+        evx_run_search_item(p, pick, it, lane, win, bar, phase);
+        return 1;
+    }
+    return 0;
+}
+
+// A service CTA's warp: the two kinds of work until the frame has none left
+__device__ __noinline__ void evx_service(const EvxK3Params &p, uint8_t *win, uint64_t *bar, int lane, unsigned int rot)
+{
+    const bool search = p.fuse_k2 && p.frame_type == 1;
+    uint32_t phase = 0;
+    unsigned long long t0 = 0;
+    unsigned int polls = 0;
+    for (;;)
+    {
+        const int dj = p.fuse_dbk ? evx_serve_deblock(p, lane, rot) : -1;
+        if (dj == 1) { t0 = 0; continue; }
+        const int sj = search ? evx_serve_search(p, lane, win, bar, phase, rot) : -1;
+        if (sj == 1) { t0 = 0; continue; }
+        if (dj < 0 && sj < 0) break;
+        __nanosleep(400);
+        if ((++polls & 31u) == 0u && p.wait.budget_ns)
+        {
+            const unsigned long long t = evx_globaltimer();
+            if (!t0) t0 = t;
+            else if (t - t0 > p.wait.budget_ns) evx_wait_expired(p.wait, 6u, (unsigned int) dj, (unsigned int) sj, 0u);
+        }
+    }
+}
+
+// The block loader's part: every item of ITS row up to macroblock n must be claimed before it waits for their stamps.
+__device__ __noinline__ void evx_claim_own_items(const EvxK3Params &p, int by, int n, int lane, uint8_t *win, uint64_t *bar, uint32_t &phase)
+{
+    const int nref = p.R - 1, until = (n + 1) * nref, per_row = p.g.mbw * nref;
+    int *k2c = evx_k2c(p) + by;
+    for (;;)
+    {
+        int it = per_row;
+        if (lane == 0 && evx_ld_relaxed(k2c) < until) it = atomicAdd(k2c, 1);
+        it = __shfl_sync(0xFFFFFFFFu, it, 0);
+        if (it >= per_row) break;
+        evx_gate_prev(p, it / nref, by, lane);
+        evx_run_search_item(p, by, it, lane, win, bar, phase);
+    }
 }
 
 // ---------------------------------------------------------------- block loader warp
@@ -173,44 +380,13 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
         evx_mbar_wait(&S.empty[m & 1], (uint32_t) ((m >> 1) & 1));
         if (lane == 0) evx_st_release(progress + by, m + 1);     // release is cumulative over what this thread observed through the barrier
     };
-    // Deblocking behind the wavefront (header comment): this row's CTA owns tile row by-3, the last row also the
-    // tile rows below it.  deblock_to(cnt) filters tile columns [dbk_done, cnt) of those rows -- one tile per lane and
-    // pass -- and publishes the count.  Tile column X may go once macroblock min(X+2, W-1) of THIS row is complete.
-    const int ylo = max(0, by - 3), yhi = by == g.mbh - 1 ? g.mbh - 1 : by - 3;
-    int dbk_done = 0;
-    auto deblock_to = [&](int cnt)
-    {
-        if (yhi < 0 || cnt <= dbk_done) return;
-        const int x0 = dbk_done, last = cnt == g.mbw ? 1 : 0;
-        if (p.deblocking)
-        {
-            const int nlx = 2 * (cnt - x0) + last, ncx = (cnt - x0) + last;
-            for (int Y = ylo; Y <= yhi; ++Y)
-            {
-                const int bot = Y == g.mbh - 1 ? 1 : 0;
-                const int nl = nlx * (2 + bot), nc = ncx * (1 + bot);
-                for (int k = lane; k < nl + 2 * nc; k += 32)
-                {
-                    if (k < nl) evx_deblock_tile_call(cur.y, cur.u, cur.v, g.w, g.h, p.table, 0, 2 * x0 + k % nlx, 2 * Y + k / nlx);
-                    else { const int c = (k - nl) % nc; evx_deblock_tile_call(cur.y, cur.u, cur.v, g.w, g.h, p.table, 1 + (k - nl) / nc, x0 + c % ncx, Y + c / ncx); }
-                }
-            }
-        }
-        dbk_done = cnt;
-        __syncwarp();
-        if (lane == 0)
-            for (int Y = ylo; Y <= yhi; ++Y)
-                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.dbk + Y), "r"(p.dbk_base + (unsigned int) cnt) : "memory");
-    };
+    uint32_t k2phase = 0;
+    bool stamps_seen = false;       // the stamps of the macroblock about to be staged were already seen (looked at one macroblock early)
 
     for (int n = 0; n < g.mbw; ++n)
     {
         const int slot = n & 1, px = n * EVX_MB, mb = by * g.mbw + n;
-        if (n >= 2)
-        {
-            publish(n - 2);          // also frees this slot's staging buffers
-            if (p.fuse_dbk && n >= 4 && ((n - 4) & 3) == 3) deblock_to(n - 3);      // macroblock n-2 complete: tile columns <= n-4
-        }
+        if (n >= 2) publish(n - 2);          // also frees this slot's staging buffers
         // An intra frame has no search whose items wait for the previous frame, but it overwrites the ring slot frames
         // before it still read and reads that slot's stale samples: the same gate, taken here.
         if (!nref) evx_gate_prev(p, n, by, lane);
@@ -230,9 +406,14 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
         // K2's candidates and their predictions (encode.cpp:110-141), so that classification
         // never waits on global memory
         if (nref && p.fuse_k2)
-        {   // the search role's results of this macroblock, one lane per reference (their items passed the gate on the previous frame)
-            const uint32_t *st = &p.inter[(size_t) min(lane, nref - 1) * nmb + mb].stamp;
-            EVX_BOUNDED_WAIT(p.wait, __all_sync(0xFFFFFFFFu, evx_ld_relaxed_u32(st) == p.stamp), 100, 5u, (unsigned int) mb, p.stamp, 0u);
+        {   // the search results of this macroblock: every item up to its own must be claimed (this warp claims and runs what
+            // nobody has yet), then one lane per reference waits for the stamps (a claimed item is in a running warp's hands)
+            if (!stamps_seen)
+            {
+                evx_claim_own_items(p, by, n, lane, S.k2win, &S.k2bar, k2phase);
+                const uint32_t *st = &p.inter[(size_t) min(lane, nref - 1) * nmb + mb].stamp;
+                EVX_BOUNDED_WAIT(p.wait, __all_sync(0xFFFFFFFFu, evx_ld_relaxed_u32(st) == p.stamp), 100, 5u, (unsigned int) mb, p.stamp, 0u);
+            }
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
         for (int r = 0; r < nref; ++r)
@@ -290,9 +471,12 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
         }
         __syncwarp();
         if (lane == 0) evx_mbar_arrive(&S.full[slot]);
+        // a look at the next macroblock's stamps (the search usually is far ahead): one round trip less on its path
+        stamps_seen = false;
+        if (nref && p.fuse_k2 && n + 1 < g.mbw)
+            stamps_seen = __all_sync(0xFFFFFFFFu, evx_ld_relaxed_u32(&p.inter[(size_t) min(lane, nref - 1) * nmb + mb + 1].stamp) == p.stamp) != 0;
     }
     for (int m = max(0, g.mbw - 2); m < g.mbw; ++m) publish(m);
-    if (p.fuse_dbk) deblock_to(g.mbw);
 }
 
 // ---------------------------------------------------------------- column loader warp
@@ -773,6 +957,9 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         if (tid == 0)
         {
             evx_mbar_arrive(&S.empty[slot]);
+#ifdef EVX_K3_TIMELINE
+            if (p.prof && n == 0) p.prof[(size_t) g.mbh * 10 + (size_t) by * 4 + 3] = (long long) evx_globaltimer();     // first macroblock of the row complete
+#endif
         }
     }
     if (tid == 0)
@@ -799,64 +986,54 @@ __global__ void __launch_bounds__(EVX_K3_NT, MINCTAS) evx_wavefront(const __grid
     const int H = p.g.mbh;
 
     if (tid == 0 && p.started) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p.started), "r"(p.dbk_base) : "memory");
-    // Persistent over tickets.  Wavefront rows: row r can only be active during macroblock steps [3r, 3r + W), so at
-    // most ceil(W/3) rows are in flight at any time and about that many CTAs carry the whole frame (the host sizes the
-    // grid so); a CTA that finished its ticket claims the next one.  Tickets are claimed in dependency order (header
-    // comment): a CTA only ever waits on tickets claimed before its own, by CTAs that are running.
-    const bool search = p.fuse_k2 && p.frame_type == 1;
-    const int lead = search ? min(2, H) : 0;
-    bool tables = false;
+    // Persistent over tickets = wavefront rows, claimed in order: row r can only be active during macroblock steps
+    // [3r, 3r + W), so at most ceil(W/3) rows are in flight at any time; the host sizes the grid for that many CTAs plus
+    // the ones that serve the search queue while they wait for their row.  A CTA only ever waits on rows claimed before
+    // its own (by CTAs that are running), on search items that are claimed, and on the previous frame.
+    auto inval = [](uint64_t *bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(evx_smem_addr(bar)) : "memory"); };
+    if ((int) blockIdx.x < p.n_service)
+    {   // a service CTA: no row, the search items and deblocking jobs of the frame until none is left (header comment)
+        if (tid == 0) for (int w = 0; w < EVX_K3_WARPS; ++w) evx_mbar_init(&K.bar[w], 1);
+        __syncthreads();
+        evx_service(p, K.win[warp], &K.bar[warp], lane, (unsigned int) (blockIdx.x * EVX_K3_WARPS + warp) * 7u);
+        return;
+    }
     for (;;)
     {
-        if (tid == 0)
-        {
-            const int t = atomicAdd(&p.sync[0], 1);
-            int role = EVX_ROLE_DONE, row = 0;
-            if (!search) { if (t < H) { role = EVX_ROLE_WAVEFRONT; row = t; } }
-            else if (t < lead) { role = EVX_ROLE_SEARCH; row = t; }
-            else
-            {
-                const int j = t - lead, pairs = H - lead;
-                if (j < 2 * pairs) { role = (j & 1) ? EVX_ROLE_SEARCH : EVX_ROLE_WAVEFRONT; row = (j & 1) ? lead + (j >> 1) : (j >> 1); }
-                else if (j - 2 * pairs < lead) { role = EVX_ROLE_WAVEFRONT; row = pairs + (j - 2 * pairs); }
-            }
-            C.role = role; C.row = row;
-            if (role == EVX_ROLE_WAVEFRONT)
-            {
-                evx_mbar_init(&S.full[0], 1); evx_mbar_init(&S.full[1], 1); evx_mbar_init(&S.fullb[0], 1); evx_mbar_init(&S.fullb[1], 1);
-                evx_mbar_init(&S.full2[0], 1); evx_mbar_init(&S.full2[1], 1); evx_mbar_init(&S.empty[0], 1); evx_mbar_init(&S.empty[1], 1);
-            }
-            else if (role == EVX_ROLE_SEARCH)
-            {
-                for (int w = 0; w < EVX_K3_WARPS; ++w) evx_mbar_init(&K.bar[w], 1);
-                K.next = 0;
-            }
-        }
+        if (tid == 0) C.row = atomicAdd(&p.sync[0], 1);
         __syncthreads();
-        const int role = C.role, by = C.row;
-        if (role == EVX_ROLE_DONE) return;
-        if (role == EVX_ROLE_SEARCH)
-        {
-            evx_k2_role(K, p, by, tid);
-            tables = false;                  // the windows lie over the wavefront role's tables
-        }
-        else
-        {
-            if (!tables) { evx_init_tables(S.sh, tid, EVX_K3_NT); tables = true; __syncthreads(); }
-            if (warp < EVX_K3_CW) evx_k3_compute(S, p, by, tid);
-            else if (warp == EVX_K3_CW) evx_k3_block_loader(S, p, by, lane);
-            else if (warp == EVX_K3_CW + 1) evx_k3_column_loader(S, p, by, lane);
-        }
-        __syncthreads();      // every warp has left the ticket: its barriers and shared memory may be reused
+        const int by = C.row;
+        if (by >= H) return;
+#ifdef EVX_K3_TIMELINE
+        if (p.prof && tid == 0) p.prof[(size_t) H * 10 + (size_t) by * 4 + 0] = (long long) evx_globaltimer();      // row claimed
+#endif
         if (tid == 0)
         {
-            auto inval = [](uint64_t *bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(evx_smem_addr(bar)) : "memory"); };
-            if (role == EVX_ROLE_WAVEFRONT)
-            {
-                inval(&S.full[0]); inval(&S.full[1]); inval(&S.fullb[0]); inval(&S.fullb[1]);
-                inval(&S.full2[0]); inval(&S.full2[1]); inval(&S.empty[0]); inval(&S.empty[1]);
-            }
-            else for (int w = 0; w < EVX_K3_WARPS; ++w) inval(&K.bar[w]);
+            evx_mbar_init(&S.full[0], 1); evx_mbar_init(&S.full[1], 1); evx_mbar_init(&S.fullb[0], 1); evx_mbar_init(&S.fullb[1], 1);
+            evx_mbar_init(&S.full2[0], 1); evx_mbar_init(&S.full2[1], 1); evx_mbar_init(&S.empty[0], 1); evx_mbar_init(&S.empty[1], 1);
+            evx_mbar_init(&S.k2bar, 1);
+        }
+        evx_init_tables(S.sh, tid, EVX_K3_NT);
+        __syncthreads();
+#ifdef EVX_K3_TIMELINE
+        if (p.prof && tid == 0) p.prof[(size_t) H * 10 + (size_t) by * 4 + 1] = (long long) evx_globaltimer();      // left the queues, row starts
+#endif
+        if (warp < EVX_K3_CW) evx_k3_compute(S, p, by, tid);
+        else if (warp == EVX_K3_CW) evx_k3_block_loader(S, p, by, lane);
+        else if (warp == EVX_K3_CW + 1) evx_k3_column_loader(S, p, by, lane);
+        __syncthreads();      // every warp has left the row: its barriers and shared memory may be reused
+#ifdef EVX_K3_TIMELINE
+        if (p.prof && tid == 0) p.prof[(size_t) H * 10 + (size_t) by * 4 + 2] = (long long) evx_globaltimer();      // row complete
+#endif
+        if (tid == 0)
+        {
+            inval(&S.full[0]); inval(&S.full[1]); inval(&S.fullb[0]); inval(&S.fullb[1]);
+            inval(&S.full2[0]); inval(&S.full2[1]); inval(&S.empty[0]); inval(&S.empty[1]); inval(&S.k2bar);
+        }
+        if (p.fuse_dbk && by == H - 1)
+        {   // the frame's last row is complete, so every deblocking job is ready: whatever nobody has taken yet is done here
+            int r;
+            while ((r = evx_serve_deblock(p, lane, (unsigned int) warp * 7u)) >= 0) if (r == 0) __nanosleep(200);
         }
     }
 }

@@ -47,7 +47,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
 typedef CUresult (*stream_memop_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 static stream_memop_fn g_wait32 = NULL;
 #include <atomic>
-enum { EVX_MAX_SLOTS = 8, EVX_DEFAULT_SLOTS = 6 };           // frame slots a handle may own (evxgpu_config::frame_slots, EVXGPU_FRAME_SLOTS)
+enum { EVX_MAX_SLOTS = 16, EVX_DEFAULT_SLOTS = 6 };           // frame slots a handle may own (evxgpu_config::frame_slots, EVXGPU_FRAME_SLOTS)
 // Encoders (handles that have encoded a frame) alive per device, process-wide.  Only a tuning hint: a stand-alone
 // wavefront launch takes the larger register budget while the handle is the device's only encoder.  Nothing about
 // correctness or progress depends on it (frames of any number of streams and processes may share the device).
@@ -97,7 +97,9 @@ struct evxgpu_handle
     bool pending_encode, pending_decode;
     int wave_grid;
     int enc_grid;                   // persistent CTAs of the encoder's wavefront kernel
-    int k2_ctas;                    // frame kernel: CTAs on top of enc_grid for the search rows that run ahead of the wavefront
+    int k2_ctas;                    // frame kernel: service CTAs (search and deblocking queues)
+    int pipe_rows;                  // frame kernel: row CTAs per frame in the pipeline
+    int launch_row;                 // a frame's kernel is launched once the previous frame has begun to deblock this tile row (0: once it runs)
     long long *d_prof;
 
     // K8: the slice as a bin string (evx_bins.cuh)
@@ -114,6 +116,8 @@ struct evxgpu_handle
     uint32_t h_bins_cap_bits[EVX_MAX_SLOTS];
     uint32_t bins_prefix_bits[EVX_MAX_SLOTS];   // how much of the string the submit already copied
     cudaEvent_t ev_out[EVX_MAX_SLOTS];
+    cudaEvent_t ev_done[EVX_MAX_SLOTS], ev_mark;     // evxgpu_timeline_mark: device time at which each frame's results had left the device
+    bool timeline;
     bool pending_bins[EVX_MAX_SLOTS];
     uint64_t d2h_bytes[EVX_MAX_SLOTS]; // device-to-host bytes of the slot's frame
     uint32_t bins_dirty_bits[EVX_MAX_SLOTS];   // how much of d_bins the slot's last frame wrote (the next frame zeroes that much)
@@ -137,6 +141,7 @@ struct evxgpu_handle
     int want_slots;                 // evxgpu_config::frame_slots (0: default)
     unsigned int frame_seq;
     int k3_regs;                    // register budget of the frame kernel: 1 or 2 CTAs per SM
+    bool k3_regs_forced;            // EVXGPU_K3_REGS given: also for the stand-alone wavefront launch
     unsigned int *h_diag, *d_diag;  // mapped host memory: what a device-side wait that ran out of time was waiting for
     unsigned long long wait_budget_ns;
     int q_head, q_count;            // queue of submitted, uncollected frames: slots q_head, q_head + 1, ... (mod nslots)
@@ -216,7 +221,8 @@ int evxgpu_destroy(evxgpu_handle *h)
     cudaFree(h->d_rgb); cudaFree(h->d_table); cudaFree(h->d_inter); cudaFree(h->d_records); cudaFree(h->d_dense); cudaFree(h->d_row_records);
     cudaFree(h->d_record_slot); cudaFree(h->d_sync); cudaFree(h->d_done); cudaFree(h->d_counters); cudaFree(h->d_prof);
     cudaFree(h->d_dc); cudaFree(h->d_prev); cudaFree(h->d_len); cudaFree(h->d_tile_sum);
-    for (int q = 0; q < EVX_MAX_SLOTS; ++q) { cudaFree(h->d_bins[q]); cudaFree(h->d_bins_total[q]); cudaFreeHost(h->h_bins[q]); if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]); }
+    for (int q = 0; q < EVX_MAX_SLOTS; ++q) { cudaFree(h->d_bins[q]); cudaFree(h->d_bins_total[q]); cudaFreeHost(h->h_bins[q]); if (h->ev_out[q]) cudaEventDestroy(h->ev_out[q]); if (h->ev_done[q]) cudaEventDestroy(h->ev_done[q]); }
+    if (h->ev_mark) cudaEventDestroy(h->ev_mark);
     cudaFreeHost(h->h_table); cudaFreeHost(h->h_records); cudaFreeHost(h->h_record_slot); cudaFreeHost(h->h_sync); cudaFreeHost(h->h_rgb);
     for (int q = 0; q < EVX_MAX_SLOTS; ++q) for (int k = 0; k < EVXGPU_T_COUNT; ++k) for (int e = 0; e < 2; ++e) if (h->ev[q][k][e]) cudaEventDestroy(h->ev[q][k][e]);
     if (h->h_diag) cudaFreeHost(h->h_diag);
@@ -271,7 +277,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     ok = ok && cudaMalloc(&h->d_dense, (size_t) h->nmb * 384 * 2) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_row_records, (size_t) h->g.mbh * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_record_slot, (size_t) h->nmb * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&h->d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_sync, ((size_t) h->g.mbh * 3 + 2) * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_done, (size_t) h->nmb * 8) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_counters, 32) == cudaSuccess;
     {   // K8 (bin string): the scratch every encoder needs; the string buffers come with evxgpu_set_output
@@ -285,6 +291,8 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
         ok = ok && cudaMalloc(&h->d_len, (size_t) EVX_BINS_ITEMS * h->nmb * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&h->d_tile_sum, ntiles * 4) == cudaSuccess;
         for (int q = 0; q < EVX_MAX_SLOTS; ++q) ok = ok && cudaEventCreateWithFlags(&h->ev_out[q], cudaEventDisableTiming) == cudaSuccess;
+        for (int q = 0; q < EVX_MAX_SLOTS; ++q) ok = ok && cudaEventCreate(&h->ev_done[q]) == cudaSuccess;
+        ok = ok && cudaEventCreate(&h->ev_mark) == cudaSuccess;
     }
     ok = ok && cudaHostAlloc(&h->h_table, (size_t) h->nmb * 16, cudaHostAllocDefault) == cudaSuccess;
     ok = ok && cudaHostAlloc(&h->h_records, (size_t) h->nmb * 384 * 2, cudaHostAllocDefault) == cudaSuccess;
@@ -326,7 +334,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
             if (cudaHostGetDevicePointer((void **) &h->d_diag, h->h_diag, 0) != cudaSuccess) h->d_diag = NULL;
         }
         h->k3_regs = 2;
-        if (const char *e = getenv("EVXGPU_K3_REGS")) { int v = atoi(e); if (v == 1 || v == 2) h->k3_regs = v; }      // measurements
+        if (const char *e = getenv("EVXGPU_K3_REGS")) { int v = atoi(e); if (v == 1 || v == 2) { h->k3_regs = v; h->k3_regs_forced = v == 2; } }      // measurements
     }
     for (int k = 0; k < EVXGPU_T_COUNT; ++k)
         for (int e = 0; e < 2; ++e)
@@ -337,7 +345,11 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     // encoder wavefront: at most ceil(W/3) rows are ever active at once (row r runs during steps [3r, 3r+W));
     // a few spare CTAs absorb the row-to-row hand-over
     h->enc_grid = std::min(h->g.mbh, (h->g.mbw + 2) / 3 + 4);
-    h->k2_ctas = 6;
+    h->k2_ctas = 10;
+    h->pipe_rows = h->enc_grid;
+    h->launch_row = 0;
+    if (const char *e = getenv("EVXGPU_LAUNCH_ROW")) { int v = atoi(e); if (v >= 0) h->launch_row = v; }      // measurements
+    if (const char *e = getenv("EVXGPU_PIPE_ROWS")) { int v = atoi(e); if (v > 0) h->pipe_rows = std::min(h->g.mbh, v); }      // measurements
     if (const char *e = getenv("EVXGPU_K2_CTAS")) { int v = atoi(e); if (v >= 0) h->k2_ctas = v; }      // measurements
     int rc = evxgpu_reset(h);
     if (rc) { evxgpu_destroy(h); return rc; }
@@ -380,6 +392,27 @@ int evxgpu_synchronize(evxgpu_handle *h) { if (!h) return 1; CK(cudaSetDevice(h-
 uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h) { return h ? h->d2h_bytes[h->last_slot] : 0; }
 
 uint64_t evxgpu_launch_count(const evxgpu_handle *h) { return h ? h->launches : 0; }
+
+// Device-side clock of the frame pipeline: mark() stamps "now" on the device; from then on every submitted frame records
+// an event when its results have left the device (after its last device-to-host copy), on the stream it ran on, and
+// last_done_ms() gives that moment for the frame collected last, in ms since the mark.
+int evxgpu_timeline_mark(evxgpu_handle *h)
+{
+    if (!h) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaEventRecord(h->ev_mark, h->copy_stream));
+    CK(cudaEventSynchronize(h->ev_mark));
+    h->timeline = true;
+    return 0;
+}
+
+double evxgpu_last_done_ms(evxgpu_handle *h)
+{
+    if (!h || !h->timeline) return -1.0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_mark, h->ev_done[h->last_slot]) != cudaSuccess) return -1.0;
+    return (double) ms;
+}
 
 int evxgpu_upload(evxgpu_handle *h, void *dst_device, const void *src_host, uint64_t bytes)
 {
@@ -506,11 +539,11 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
 {
     EvxK3Params p;
     wavefront_params(h, p, frame_type, index, quality);
-    CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_sync, 0, ((size_t) h->g.mbh * 3 + 2) * 4, h->stream));
     t_begin(h, EVXGPU_T_WAVEFRONT);
     // one CTA per macroblock row in flight; rows are claimed by ticket, so any residency is deadlock-free
     // the only encoder on the device runs the kernel with the larger register budget (evx_wavefront.cuh)
-    if (h->device >= 0 && h->device < 64 && g_encoders_live[h->device].load() <= 1 && h->k3_regs != 2)
+    if (h->device >= 0 && h->device < 64 && g_encoders_live[h->device].load() <= 1 && !h->k3_regs_forced)
         evx_wavefront<1><<<h->enc_grid, EVX_K3_NT, EVX_FRAME_SMEM, h->stream>>>(p);
     else
         evx_wavefront<2><<<h->enc_grid, EVX_K3_NT, EVX_FRAME_SMEM, h->stream>>>(p);
@@ -645,7 +678,7 @@ static int enable_pipeline(evxgpu_handle *h)
         ok = ok && cudaMalloc(&b.d_records, (size_t) h->nmb * 384 * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&b.d_row_records, (size_t) h->g.mbh * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&b.d_prev, ((size_t) h->nmb * 2 + (size_t) h->g.mbh * 2) * 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&b.d_sync, (size_t) (h->g.mbh + 2) * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&b.d_sync, ((size_t) h->g.mbh * 3 + 2) * 4) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&b.main, cudaStreamNonBlocking) == cudaSuccess;
     }
     for (int q = 0; q < ns && ok; ++q)
@@ -704,8 +737,8 @@ static int submit_pipelined(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_dev
     {
         EvxK3Params kp;
         wavefront_params(h, kp, frame_type, frame_index, quality);
-        kp.prof = NULL;
         kp.fuse_k2 = 1; kp.fuse_dbk = 1;
+        if (kp.prof) kp.prof += (size_t) (h->frame_seq % 8u) * ((size_t) h->g.mbh * 10 + (size_t) h->nmb * 4);
         kp.stamp = h->frame_seq ? h->frame_seq : 1u;
         kp.dbk = f.d_dbk; kp.dbk_base = E; kp.started = f.d_dbk + h->g.mbh;
         kp.prev_dbk = have_prev ? pv.d_dbk : NULL; kp.prev_base = Ep;
@@ -715,12 +748,21 @@ static int submit_pipelined(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_dev
             int slot = (int) ((frame_index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);
             for (int c = 0; c < 3; ++c) kp.maps.m[(off - 1) * 3 + c] = h->maps_w[slot][c];
         }
-        CK(cudaMemsetAsync(f.d_sync, 0, (size_t) (h->g.mbh + 2) * 4, f.main));
-        if (have_prev && g_wait32((CUstream) f.main, (CUdeviceptr) (uintptr_t) (pv.d_dbk + h->g.mbh), Ep, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
-            return fail(5, "stream memory operation failed");
-        // wavefront rows in flight at once + a few CTAs for the search rows that run ahead of them
-        const int tickets = h->g.mbh * (frame_type == 1 ? 2 : 1);
-        const int grid = std::min(tickets, h->enc_grid + (frame_type == 1 ? h->k2_ctas : 0));
+        CK(cudaMemsetAsync(f.d_sync, 0, ((size_t) h->g.mbh * 3 + 2) * 4, f.main));
+        // Launched behind the previous frame's kernel: not before that one runs (so that whatever this kernel waits for is
+        // already on the device) and, with launch_row > 0, not before it has deblocked the first tile columns of that tile row --
+        // a frame whose CTAs become resident long before the previous frame lets them work only holds SM slots.
+        if (have_prev)
+        {
+            const int lr = std::min(h->launch_row, h->g.mbh - 1);
+            CUdeviceptr addr = (CUdeviceptr) (uintptr_t) (lr > 0 ? pv.d_dbk + lr : pv.d_dbk + h->g.mbh);
+            if (g_wait32((CUstream) f.main, addr, lr > 0 ? Ep + 1u : Ep, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                return fail(5, "stream memory operation failed");
+        }
+        // wavefront rows in flight at once + the service CTAs of the search and deblocking queues
+        const int nsvc = frame_type == 1 ? h->k2_ctas : std::min(h->k2_ctas, 2);      // (an intra frame has deblocking jobs only)
+        const int grid = h->pipe_rows + nsvc;
+        kp.n_service = nsvc;
         if (h->k3_regs == 1) evx_wavefront<1><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
         else evx_wavefront<2><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
         h->launches++;
@@ -738,6 +780,7 @@ static int submit_pipelined(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_dev
     h->d2h_bytes[q] += 16 + h->bins_prefix_bits[q] / 8;
     h->pending_bins[q] = true;
     CK(cudaEventRecord(h->ev_out[q], f.main));
+    if (h->timeline) CK(cudaEventRecord(h->ev_done[q], f.main));
     f.base = E; f.used = true;
     h->q_count++;
     h->pending_encode = true;
@@ -859,6 +902,7 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
         h->pending_bins[q] = true;
     }
     CK(cudaEventRecord(h->ev_out[q], h->stream));
+    if (h->timeline) CK(cudaEventRecord(h->ev_done[q], h->stream));
     if ((rc = launch_deblock(h, frame_index))) return rc;
     h->q_count++;
     h->pending_encode = true;
@@ -973,7 +1017,7 @@ int evxgpu_decode_submit(evxgpu_handle *h, const evxgpu_block_desc *table, const
     p.g = h->g; p.R = h->cfg.ref_count; p.linear = h->cfg.linear_quant; p.frame_index = frame_index;
     p.table = h->d_table; p.records = h->d_dense; p.record_slot = h->d_record_slot; p.sync = h->d_sync;
     p.done = h->d_done; p.readers = h->d_done + h->nmb;
-    CK(cudaMemsetAsync(h->d_sync, 0, (size_t) (h->g.mbh + 2) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_sync, 0, ((size_t) h->g.mbh * 3 + 2) * 4, h->stream));
     CK(cudaMemsetAsync(h->d_done, 0, (size_t) h->nmb * 8, h->stream));
     t_begin(h, EVXGPU_T_DECODE_RECON);
     evx_decode_deps<<<(h->nmb + 255) / 256, 256, 0, h->stream>>>(h->d_table, h->g, frame_index, h->cfg.ref_count, p.readers);
@@ -1094,7 +1138,7 @@ int evxgpu_debug_profile(evxgpu_handle *h, int enable, long long *out_host)
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
     // [mbh][10] phase sums, then (builds with -DEVX_K3_TRACE only) [nmb][4] globaltimer stamps per macroblock
-    const size_t elems = (size_t) h->g.mbh * 10 + (size_t) h->nmb * 4;
+    const size_t elems = ((size_t) h->g.mbh * 10 + (size_t) h->nmb * 4) * 8;        // eight consecutive frames of the pipeline (frame_seq % 8), or [0] for the stand-alone launch
     if (enable && !h->d_prof) { CK(cudaMalloc(&h->d_prof, elems * 8)); CK(cudaMemset(h->d_prof, 0, elems * 8)); }
     if (out_host && h->d_prof) CK(cudaMemcpy(out_host, h->d_prof, elems * 8, cudaMemcpyDeviceToHost));
     if (!enable && h->d_prof) { cudaFree(h->d_prof); h->d_prof = NULL; }

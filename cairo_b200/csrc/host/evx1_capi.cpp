@@ -25,7 +25,19 @@ static evx1_config make_config(int device, int ref_count, int linear_quant, int 
     return c;
 }
 
+#include "evxgpu_records.h"
+
 extern "C" {
+
+// include/evxgpu_records.h through the library, for FFI callers (the header itself is all a C or C++ binding needs)
+uint32_t evx1c_scatter_records(const void *table, const int16_t *records, int aligned_width, int aligned_height, int16_t *y, int16_t *u, int16_t *v)
+{
+    return evxgpu_scatter_records(static_cast<const evxgpu_block_desc *>(table), records, aligned_width, aligned_height, y, u, v);
+}
+uint32_t evx1c_gather_records(const void *table, const int16_t *y, const int16_t *u, const int16_t *v, int aligned_width, int aligned_height, int16_t *records)
+{
+    return evxgpu_gather_records(static_cast<const evxgpu_block_desc *>(table), y, u, v, aligned_width, aligned_height, records);
+}
 
 evx1c_encoder *evx1c_encoder_create(int device, int ref_count, int linear_quant, int deblocking, int periodic_intra, int default_quality)
 {

@@ -84,7 +84,7 @@ class encoder_session : public evx1_encoder
         uint32 n_noncopy, d2h_bytes;
         uint64_t nbins;
     };
-    enum { kDevMax = 8 };
+    enum { kDevMax = 16 };
     pending_frame dev_[kDevMax];                   // dev_[0] is the oldest of the frames on the device
     int dev_count_;                                // how many the device library takes: evxgpu_encode_capacity
     std::vector<evxgpu_block_desc> table_;         // retired frame, table + records output

@@ -72,6 +72,9 @@ def lib():
     L.evxgpu_d2h_bytes.argtypes = [vp]
     L.evxgpu_launch_count.restype = C.c_uint64
     L.evxgpu_launch_count.argtypes = [vp]
+    L.evxgpu_timeline_mark.argtypes = [vp]
+    L.evxgpu_last_done_ms.restype = C.c_double
+    L.evxgpu_last_done_ms.argtypes = [vp]
     L.evxgpu_measure_int_peak.restype = C.c_double
     L.evxgpu_measure_int_peak.argtypes = [i32, i32]
     _lib = L
@@ -223,6 +226,13 @@ class Pipeline:
 
     def d2h_bytes(self):
         return int(self.L.evxgpu_d2h_bytes(self.h))
+
+    def timeline_mark(self):
+        _check(self.L.evxgpu_timeline_mark(self.h), "evxgpu_timeline_mark")
+
+    def last_done_ms(self):
+        """Device time (ms since timeline_mark) at which the results of the frame collected last had left the device."""
+        return float(self.L.evxgpu_last_done_ms(self.h))
 
     def launch_count(self):
         return int(self.L.evxgpu_launch_count(self.h))

@@ -81,6 +81,11 @@ void evx1c_parsed_slice_destroy(evx1c_parsed_slice *p);
 int evx1c_slice_reader_parse(const evx1c_slice_reader *r, const uint8_t *data, uint32_t nbits, evx1c_parsed_slice *out);
 int evx1c_slice_reader_apply(evx1c_slice_reader *r, const evx1c_parsed_slice *in, void *table, int16_t *records_out, uint32_t *n_noncopy);
 
+/* include/evxgpu_records.h exported for FFI callers: records of the non-copy macroblocks <-> the reference's persistent
+ * coefficient planes (output_cache on the encoder side, input_cache on the decoder side).  Return the record count. */
+uint32_t evx1c_scatter_records(const void *table, const int16_t *records, int aligned_width, int aligned_height, int16_t *y, int16_t *u, int16_t *v);
+uint32_t evx1c_gather_records(const void *table, const int16_t *y, const int16_t *u, const int16_t *v, int aligned_width, int aligned_height, int16_t *records);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,7 +51,7 @@ typedef struct evxgpu_config
     int32_t ref_count;        /* EVX_REFERENCE_FRAME_COUNT: ring slots incl. the current frame, 2..8 */
     int32_t linear_quant;     /* EVX_ENABLE_LINEAR_QUANTIZATION */
     int32_t deblocking;       /* EVX_ENABLE_DEBLOCKING */
-    int32_t frame_slots;      /* encoder, bin-string output: frames of the stream in flight on the device at once (0 = default 6, max 8) */
+    int32_t frame_slots;      /* encoder, bin-string output: frames of the stream in flight on the device at once (0 = default, at most 16) */
 } evxgpu_config;
 
 #define EVXGPU_MB_COEFFS 384   /* 16x16 luma (row-major, stride 16) + 8x8 U + 8x8 V, int16 */
@@ -144,6 +144,11 @@ int evxgpu_get_counters(evxgpu_handle *h, uint64_t *fullpel, uint64_t *subpel, i
 /* the same split by kernel: out4 = { inter full-pel, inter sub-pel, intra full-pel, intra sub-pel } */
 int evxgpu_get_counters_split(evxgpu_handle *h, uint64_t *out4, int reset);
 uint64_t evxgpu_launch_count(const evxgpu_handle *h);
+/* device-side clock of the pipeline (bench.py): mark() stamps now; every frame submitted afterwards records a CUDA event on
+ * its own stream once its results have left the device, and last_done_ms() is that moment for the frame collected last, in
+ * milliseconds since the mark (-1 before any mark, or when that frame was submitted before the mark) */
+int evxgpu_timeline_mark(evxgpu_handle *h);
+double evxgpu_last_done_ms(evxgpu_handle *h);
 /* bytes copied device -> host for the last submitted frame, as queued by submit and the collect calls so far */
 uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h);
 /* debug: per-row phase cycle sums of the encoder wavefront kernel, 6 x int64 per macroblock row */

@@ -14,7 +14,7 @@ for t in range(3):
 L.evxgpu_debug_profile(p.h, 1, None)
 tbl, rec = p.encode(frames[3], 1, 3, 16)
 tm = p.timing()
-raw = np.zeros((p.ah // 16) * 10 + p.nblocks * 4, dtype=np.int64)
+raw = np.zeros(((p.ah // 16) * 10 + p.nblocks * 4) * 8, dtype=np.int64)      # (the buffer is eight pipeline frames deep; the stand-alone launch uses the first)
 L.evxgpu_debug_profile(p.h, 1, raw.ctypes.data_as(C.c_void_p))
 prof = raw[:(p.ah // 16) * 10].reshape(-1, 10)
 names = ['wait_columns', 'search5', 'subpel', 'classify+pred', 'transform+recon', 'far_col_waits', 'hold1', 'hold2', 'hold3', 'wait_block_loader(stats build)']

@@ -16,7 +16,7 @@ for kind in ['moving', 'noise', 'static']:
         p.encode(frames[t], 0 if t == 0 else 1, t, 16)
     L.evxgpu_debug_profile(p.h, 1, None)
     tbl, rec = p.encode(frames[3], 1, 3, 16)
-    raw = np.zeros((p.ah // 16) * 10 + p.nblocks * 4, dtype=np.int64)
+    raw = np.zeros(((p.ah // 16) * 10 + p.nblocks * 4) * 8, dtype=np.int64)      # (eight pipeline frames deep; the stand-alone launch uses the first)
     L.evxgpu_debug_profile(p.h, 1, raw.ctypes.data_as(C.c_void_p))
     prof = raw[:(p.ah // 16) * 10].reshape(-1, 10)
     holds = prof[:, 5:10].sum(axis=0) / p.nblocks

@@ -15,7 +15,7 @@ for t in range(3):
 L.evxgpu_debug_profile(p.h, 1, None)
 tbl, rec = p.encode(frames[3], 1, 3, 16)
 mbh, mbw = p.ah // 16, p.aw // 16
-raw = np.zeros(mbh * 10 + p.nblocks * 4, dtype=np.int64)
+raw = np.zeros((mbh * 10 + p.nblocks * 4) * 8, dtype=np.int64)      # (eight pipeline frames deep; the stand-alone launch uses the first)
 L.evxgpu_debug_profile(p.h, 1, raw.ctypes.data_as(C.c_void_p))
 tr = raw[mbh * 10:].reshape(mbh, mbw, 4).astype(np.float64)
 if tr[:, :, 0].max() == 0:

@@ -64,6 +64,28 @@ def test_product_never_imports_the_oracle():
                 assert "oracleharness" not in text and "evx_oracle" not in text and "libevxref" not in text, os.path.join(dirpath, f)
 
 
+def test_record_scatter_gather_round_trip():
+    """include/evxgpu_records.h (through libevx1.so): records of the non-copy macroblocks -> persistent coefficient planes
+    -> records; copy blocks leave the planes' stale values alone; same result as the numpy restatement."""
+    import numpy as np
+    from cairo_b200 import api, gpu
+    aw, ah = 80, 48
+    n = (aw // 16) * (ah // 16)
+    rng = np.random.default_rng(5)
+    tbl = np.zeros(n, dtype=gpu.BLOCK_DESC_DTYPE)
+    tbl["block_type"] = rng.integers(0, 8, n)
+    k = int((tbl["block_type"] & 4 == 0).sum())
+    rec = rng.integers(-300, 300, (k, 384)).astype(np.int16)
+    planes = [np.full((ah, aw), 7, np.int16), np.full((ah // 2, aw // 2), 8, np.int16), np.full((ah // 2, aw // 2), 9, np.int16)]
+    want = [a.copy() for a in planes]
+    gpu.records_to_planes(tbl, rec, want, aw, ah)
+    assert api.scatter_records(tbl, rec, planes, aw, ah) == k
+    assert all((a == b).all() for a, b in zip(planes, want))
+    assert (planes[0] == 7).any() or k == n                    # the copy blocks' samples were not touched
+    back = api.gather_records(tbl, planes, aw, ah)
+    assert back.shape == rec.shape and (back == rec).all()
+
+
 def test_stream_partition():
     from cairo_b200 import fanout
     assert fanout.streams_of_rank(64, 3, 8) == [3, 11, 19, 27, 35, 43, 51, 59]
