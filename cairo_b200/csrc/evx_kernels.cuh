@@ -650,14 +650,14 @@ struct EvxK3Params
     int16_t *records;              // [nmb][384] coefficient records, slot = macroblock index
     int *row_records;              // [mbh] non-copy macroblocks per row (for evx_pack_records)
     int *sync;                     // [0] row ticket, [1] total records, then three per-row counters of mbh entries each: progress[] (macroblocks of the
-                                   // wavefront row complete), k2c[] (search items of the row claimed), jc[] (deblocking jobs of the tile row claimed)
+                                   // wavefront row complete), k2c[] (search items of the row claimed), jc[] (deblocking jobs of the tile row claimed); then the row
+                                   // tickets of the search follower and of the deblocking follower
     // Frames of one stream pipelined on the device (evxgpu.cu, submit_pipelined): the inter search and the deblocking
     // filter run as ROLES of this kernel, and consecutive frames are gated macroblock by macroblock through per-row
     // counters in device memory.  Cross-frame counters hold frame base + count and are compared cyclically
     // ((int)(value - need) >= 0), so a slot's counters are never zeroed between the frames that reuse it.
-    int fuse_k2;                   // 1: the inter search is done by this kernel's service CTAs and block loaders (results carry `stamp`)
-    int fuse_dbk;                  // 1: the deblocking filter runs as jobs of this kernel behind the wavefront, publishing dbk[]
-    int n_service;                 // the first n_service blocks hold no row: they run search items and deblocking jobs for the whole frame
+    int fuse_k2;                   // 1: the inter search runs beside this kernel (evx_search_follow; results carry `stamp`, the block loaders take what is missing)
+    int fuse_dbk;                  // 1: the deblocking filter runs as jobs behind the wavefront (evx_deblock_follow, and the last row's CTA), publishing dbk[]
     int deblocking;                // EVX_ENABLE_DEBLOCKING (with fuse_dbk and no deblocking only the counters advance)
     int thr;                       // (quality >> 2) + 1
     uint32_t stamp;                // this frame's token in EvxInterResult::stamp (non-zero)

@@ -24,33 +24,34 @@
 // into the window), and the inter-row latency (flag + L2 round trip) is paid once per row
 // instead of once per macroblock: frame time ~ (W + 3(H-1)) * T_mb + (H-1) * latency.
 //
-// THE FRAME KERNEL.  With fuse_k2 / fuse_dbk (frames of a stream pipelined on the device, evxgpu.cu
-// submit_pipelined) the same kernel also carries the frame's inter search and its deblocking filter, so that a
-// frame is ONE launch whose CTAs wait for nothing but (a) tickets of the same kernel claimed earlier and (b) the
-// previous frame's kernel, which was launched -- and has started -- before this one.  No wait can point at work
-// that still needs an SM slot this kernel's waiting CTAs hold, whoever else uses the device:
-//   * tickets are the wavefront rows W(0) .. W(H-1), claimed in order by the ROW CTAs.  The inter search is a set of
-//     per-row queues: row y's (macroblock, reference) items are claimed in column order through a counter k2c[y].
-//     SERVICE CTAs (the first blocks of the grid; they take no row) scan the rows and take, among the items the previous
-//     frame is already final around, the one its row will need soonest; such an item never waits.  And a row's block
-//     loader, before it waits for the stamps of the macroblock it stages, claims and runs whatever item of ITS OWN row up
-//     to that macroblock nobody has taken yet (waiting, if it must, for the previous frame around it) -- so the stamps it
-//     then waits for are in the hands of running warps, whether or not any service CTA is resident;
-//   * deblocking follows the wavefront: the sweep decomposes into independent 8x8 tiles (evx_kernels.cuh, K4); the
-//     tiles of macroblock (X, Y) -- luma crossings {2X, 2X+1} x {2Y, 2Y+1}, chroma (X, Y), plus the frame's right /
-//     bottom border tiles in the last column / row -- touch macroblocks (X-1..X, Y-1..Y), whose unfiltered samples the
-//     intra search reads last from macroblock (X+2, Y+3).  A JOB is four tile columns of one tile row; tile row Y's
-//     jobs are claimed in order through a counter jc[Y] by the service CTAs, each one once the wavefront has passed it,
-//     filtered one tile per lane, and dbk[Y] = base + filtered tile columns is published in order.  The CTA of the last
-//     row takes whatever is left when the frame's rows are done.  (Per-row counters, not one queue in wavefront order:
-//     rows do not keep the ideal three-step formation, and one late row at the head of a global queue held up
-//     everything behind it -- measured: frames trailed each other by 150 steps instead of 30);
+// THE FRAME PIPELINE (frames of a stream in flight on the device at once, evxgpu.cu submit_pipelined).  A frame is
+// THREE launches that run side by side, each following the one before it through counters in device memory:
+//   evx_search_follow    the frame's inter search.  Persistent CTAs take macroblock ROWS by ticket, in order; a row's
+//                        (macroblock, reference) items are claimed in column order through a counter k2c[y] by the
+//                        CTA's warps, each item once the previous frame is final around it (evx_gate_prev); every
+//                        result is stamped;
+//   evx_wavefront        the wavefront rows (this file's main kernel).  A row's block loader waits for the stamps of
+//                        the macroblock it stages -- after it has claimed, and run itself, whatever item of ITS OWN row
+//                        up to that macroblock nobody has taken (so the stamps it waits for are always in the hands of
+//                        running warps, whether or not a search CTA is resident);
+//   evx_deblock_follow   the deblocking filter behind the wavefront.  The sweep decomposes into independent 8x8 tiles
+//                        (evx_kernels.cuh, K4); the tiles of macroblock (X, Y) -- luma crossings {2X, 2X+1} x {2Y, 2Y+1},
+//                        chroma (X, Y), plus the frame's right / bottom border tiles in the last column / row -- touch
+//                        macroblocks (X-1..X, Y-1..Y), whose unfiltered samples the intra search reads last from
+//                        macroblock (X+2, Y+3).  A JOB is four tile columns of one tile row; persistent one-warp CTAs take
+//                        TILE ROWS by ticket and run a row's jobs as the wavefront passes them (claimed through jc[Y],
+//                        a compare-and-swap: a claimed job never waits), publishing dbk[Y] = base + filtered tile
+//                        columns.  The wavefront kernel's last row takes whatever jobs are left when the rows are done.
+// Nobody waits for work that could still need an SM slot the waiter holds: tickets are claimed in dependency order, the
+// wavefront kernel has a fallback for everything it consumes, and the other waits point at the previous frame, whose
+// kernels were launched -- and have started -- before this frame's.  Any number of streams and processes may share
+// the device.  Cross-frame counters hold frame base + count and are compared cyclically; every wait is bounded.
 //   * the NEXT frame reads this one as a reference around (bx, by): samples of macroblocks (bx-2..bx+2, by-2..by+2),
 //     final once the tiles of columns <= bx+3 in tile rows by-2 .. by+3 are done.  Its search items (and, in an intra
 //     frame, its block loaders) wait for dbk[by-2 .. by+3] >= min(bx+4, W), six lanes polling one row each.  That
 //     one rule also covers the write-after-read side (a frame overwrites the ring slot of frame n-R, which frame
 //     n-1 still searches) and the stale samples the intra search reads from that slot: every frame
-//     trails its predecessor by the same ~23 wavefront steps at every macroblock, and so transitively all older ones.
+//     trails its predecessor by the same ~30 wavefront steps at every macroblock, and so transitively all older ones.
 #pragma once
 
 #include "evx_kernels.cuh"
@@ -188,6 +189,7 @@ __device__ __forceinline__ int *evx_jc(const EvxK3Params &p) { return p.sync + 2
 // [4c, 4c+4) of tile row Y may be filtered once macroblock (min(4c+5, W-1), min(Y+3, H-1)) is complete -- claims one by
 // compare-and-swap on jc[Y] (a claimed job must never wait for the wavefront) and runs it.  `rot` spreads the warps
 // over the ready rows.  Returns 1 if a job was done, 0 if none is ready, -1 if every job of the frame is claimed.
+// (The wavefront kernel's last row: whatever the deblocking follower has not taken.)
 __device__ __forceinline__ int evx_serve_deblock(const EvxK3Params &p, int lane, unsigned int rot)
 {
     const int H = p.g.mbh, W = p.g.mbw, nch = (W + EVX_DBK_CHUNK - 1) / EVX_DBK_CHUNK;
@@ -230,120 +232,6 @@ __device__ __forceinline__ void evx_run_search_item(const EvxK3Params &p, int y,
     const int rslot = (int) ((p.frame_index + (uint32_t) p.R - (uint32_t) (ref + 1)) % (uint32_t) p.R);       // common.cpp:192-195
     evx_k2_item(&p.maps.m[ref * 3], p.src, p.ring[rslot], p.g, p.thr, bx, y, ref, lane, win, bar, phase,
                 p.inter + (size_t) ref * nmb + (size_t) y * p.g.mbw + bx, p.counters, p.stamp);
-}
-
-// Picks the search item to run next and runs it.  Every lane looks at three rows (groups of 96 rows): how far the search
-// is ahead of the wavefront there, and whether the previous frame is final around the row's next item -- all loads of a
-// group in two round trips.  A row is URGENT when the search is fewer than EVX_K2_AHEAD columns ahead of its wavefront
-// (or it is one of the next few rows to start and has fewer than that many columns done); the warp takes the first
-// urgent open row at or after its own offset `rot` (so that the warps spread over the rows instead of all racing for
-// the single most urgent one), else the open row that will need its item soonest.  Claimed by compare-and-swap on
-// k2c[y].  Returns 1 / 0 (nothing ready) / -1 (every item of the frame is claimed).
-#define EVX_K2_AHEAD 12
-__device__ __forceinline__ int evx_serve_search(const EvxK3Params &p, int lane, uint8_t *win, uint64_t *bar, uint32_t &phase, unsigned int rot)
-{
-    const int H = p.g.mbh, W = p.g.mbw, nref = p.R - 1, per_row = W * nref;
-    int *k2c = evx_k2c(p);
-    const int *progress = evx_progress(p);
-    for (int attempt = 0; attempt < 3; ++attempt)
-    {
-        bool all = true;
-        int pick = -1, pick_wait = 0x7FFFFFFF, first_idle = -1;
-        for (int g0 = 0; g0 < H && pick < 0; g0 += 96)
-        {
-            int it[3], prog[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-            {
-                const int y = g0 + 32 * k + lane;
-                it[k] = per_row; prog[k] = 1;
-                if (y < H) { it[k] = evx_ld_relaxed(k2c + y); prog[k] = evx_ld_relaxed(progress + y); }
-            }
-            bool open[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-            {
-                const int y = g0 + 32 * k + lane;
-                open[k] = it[k] < per_row;
-                if (open[k] && p.prev_dbk)
-                {
-                    const unsigned int want = p.prev_base + (unsigned int) min(it[k] / nref + 4, W);
-                    int worst = -1;
-#pragma unroll
-                    for (int j = 0; j < 6; ++j) worst = max(worst, (int) (want - evx_ld_relaxed_u32(p.prev_dbk + max(0, min(y + 3 - j, H - 1)))));
-                    open[k] = worst <= 0;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-            {
-                if (__any_sync(0xFFFFFFFFu, it[k] < per_row)) all = false;
-                // rows are claimed in order, so the rows that have not started form a suffix: the first of them
-                const unsigned int idle = __ballot_sync(0xFFFFFFFFu, g0 + 32 * k + lane < H && prog[k] == 0);
-                if (first_idle < 0 && idle) first_idle = g0 + 32 * k + __ffs(idle) - 1;
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k)
-            {
-                const int y = g0 + 32 * k + lane, x = it[k] / nref;
-                const int wait = prog[k] > 0 ? x - prog[k] : x + 3 * (first_idle >= 0 ? max(0, y - first_idle) : 0);
-                const bool urgent = open[k] && (prog[k] > 0 ? wait < EVX_K2_AHEAD : (first_idle >= 0 && y - first_idle < 6 && x < EVX_K2_AHEAD));
-                const unsigned int um = __ballot_sync(0xFFFFFFFFu, urgent);
-                if (um && pick < 0)
-                {
-                    const unsigned int r = (rot + 11u * (unsigned int) attempt) & 31u, m2 = (um >> r) | (r ? um << (32u - r) : 0u);
-                    pick = g0 + 32 * k + (int) ((__ffs(m2) - 1 + r) & 31u);
-                }
-                const int mw = __reduce_min_sync(0xFFFFFFFFu, open[k] ? ((max(wait, 0) << 12) | (y & 0xFFF)) : 0x7FFFFFFF);
-                pick_wait = min(pick_wait, mw);
-            }
-        }
-        if (pick < 0)
-        {
-            if (pick_wait == 0x7FFFFFFF) return all ? -1 : 0;
-            pick = pick_wait & 0xFFF;               // nothing urgent: the open row that needs its next item soonest
-        }
-        int it = 0, ok = 0;
-        if (lane == 0)
-        {
-            it = evx_ld_relaxed(k2c + pick);
-            ok = it < per_row && atomicCAS(k2c + pick, it, it + 1) == it;
-        }
-        ok = __shfl_sync(0xFFFFFFFFu, ok, 0); it = __shfl_sync(0xFFFFFFFFu, it, 0);
-        if (!ok) continue;                          // somebody else took it: look again
-        if (p.prev_dbk)
-        {   // (the claim may be one item further than the one whose gate was seen open: the next column of the same row)
-            while (evx_gate_shortfall(p, it / nref, pick, lane) > 0) __nanosleep(200);
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        }
-        evx_run_search_item(p, pick, it, lane, win, bar, phase);
-        return 1;
-    }
-    return 0;
-}
-
-// A service CTA's warp: the two kinds of work until the frame has none left
-__device__ __noinline__ void evx_service(const EvxK3Params &p, uint8_t *win, uint64_t *bar, int lane, unsigned int rot)
-{
-    const bool search = p.fuse_k2 && p.frame_type == 1;
-    uint32_t phase = 0;
-    unsigned long long t0 = 0;
-    unsigned int polls = 0;
-    for (;;)
-    {
-        const int dj = p.fuse_dbk ? evx_serve_deblock(p, lane, rot) : -1;
-        if (dj == 1) { t0 = 0; continue; }
-        const int sj = search ? evx_serve_search(p, lane, win, bar, phase, rot) : -1;
-        if (sj == 1) { t0 = 0; continue; }
-        if (dj < 0 && sj < 0) break;
-        __nanosleep(400);
-        if ((++polls & 31u) == 0u && p.wait.budget_ns)
-        {
-            const unsigned long long t = evx_globaltimer();
-            if (!t0) t0 = t;
-            else if (t - t0 > p.wait.budget_ns) evx_wait_expired(p.wait, 6u, (unsigned int) dj, (unsigned int) sj, 0u);
-        }
-    }
 }
 
 // The block loader's part: every item of ITS row up to macroblock n must be claimed before it waits for their stamps.
@@ -991,13 +879,6 @@ __global__ void __launch_bounds__(EVX_K3_NT, MINCTAS) evx_wavefront(const __grid
     // the ones that serve the search queue while they wait for their row.  A CTA only ever waits on rows claimed before
     // its own (by CTAs that are running), on search items that are claimed, and on the previous frame.
     auto inval = [](uint64_t *bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(evx_smem_addr(bar)) : "memory"); };
-    if ((int) blockIdx.x < p.n_service)
-    {   // a service CTA: no row, the search items and deblocking jobs of the frame until none is left (header comment)
-        if (tid == 0) for (int w = 0; w < EVX_K3_WARPS; ++w) evx_mbar_init(&K.bar[w], 1);
-        __syncthreads();
-        evx_service(p, K.win[warp], &K.bar[warp], lane, (unsigned int) (blockIdx.x * EVX_K3_WARPS + warp) * 7u);
-        return;
-    }
     for (;;)
     {
         if (tid == 0) C.row = atomicAdd(&p.sync[0], 1);
@@ -1034,6 +915,82 @@ __global__ void __launch_bounds__(EVX_K3_NT, MINCTAS) evx_wavefront(const __grid
         {   // the frame's last row is complete, so every deblocking job is ready: whatever nobody has taken yet is done here
             int r;
             while ((r = evx_serve_deblock(p, lane, (unsigned int) warp * 7u)) >= 0) if (r == 0) __nanosleep(200);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ the followers (header comment)
+
+#define EVX_SF_WARPS 8            // warps of a search-follower CTA: a row's 120 items in ~300 us, twice the pace its wavefront row needs
+struct EvxSearchFollowSmem
+{
+    uint8_t win[EVX_SF_WARPS][EVX_K2W_BYTES];
+    uint64_t bar[EVX_SF_WARPS];
+    int row;
+};
+
+__global__ void __launch_bounds__(EVX_SF_WARPS * 32, 4) evx_search_follow(const __grid_constant__ EvxK3Params p)
+{
+    extern __shared__ __align__(128) uint8_t evx_sf_smem[];
+    EvxSearchFollowSmem &F = *reinterpret_cast<EvxSearchFollowSmem *>(evx_sf_smem);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int H = p.g.mbh, nref = p.R - 1, per_row = p.g.mbw * nref;
+    int *ticket = p.sync + 2 + 3 * H;
+    if (tid == 0) for (int w = 0; w < EVX_SF_WARPS; ++w) evx_mbar_init(&F.bar[w], 1);
+    uint32_t phase = 0;
+    for (;;)
+    {
+        __syncthreads();
+        if (tid == 0) F.row = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int y = F.row;
+        if (y >= H) return;
+        int *k2c = evx_k2c(p) + y;
+        for (;;)
+        {
+            int it = 0;
+            if (lane == 0) it = atomicAdd(k2c, 1);
+            it = __shfl_sync(0xFFFFFFFFu, it, 0);
+            if (it >= per_row) break;
+            evx_gate_prev(p, it / nref, y, lane);
+            evx_run_search_item(p, y, it, lane, F.win[warp], &F.bar[warp], phase);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32, 16) evx_deblock_follow(const __grid_constant__ EvxK3Params p)
+{
+    const int lane = threadIdx.x;
+    const int H = p.g.mbh, W = p.g.mbw, nch = (W + EVX_DBK_CHUNK - 1) / EVX_DBK_CHUNK;
+    int *ticket = p.sync + 3 + 3 * H;
+    const int *progress = evx_progress(p);
+    for (;;)
+    {
+        int Y = 0;
+        if (lane == 0) Y = atomicAdd(ticket, 1);
+        Y = __shfl_sync(0xFFFFFFFFu, Y, 0);
+        if (Y >= H) return;
+        int *jc = evx_jc(p) + Y;
+        const int *prow = progress + min(Y + 3, H - 1);
+        for (;;)
+        {
+            // the row's next job, once the wavefront has passed it: macroblock min(4c+5, W-1) of row min(Y+3, H-1) complete
+            int c = 0;
+            if (lane == 0) c = evx_ld_relaxed(jc);
+            c = __shfl_sync(0xFFFFFFFFu, c, 0);
+            if (c >= nch) break;
+            const int cnt = min(c * EVX_DBK_CHUNK + EVX_DBK_CHUNK, W), need = min(cnt + 1, W - 1) + 1;
+            if (lane == 0)
+            {
+                int have;
+                EVX_BOUNDED_WAIT(p.wait, (have = evx_ld_relaxed(prow)) >= need, (need - have > 8 ? 4000 : 500 * (need - have)), 9u, (unsigned int) Y, (unsigned int) need, (unsigned int) have);
+            }
+            __syncwarp();
+            int ok = 0;
+            if (lane == 0) ok = atomicCAS(jc, c, c + 1) == c;
+            if (!__shfl_sync(0xFFFFFFFFu, ok, 0)) continue;           // (the wavefront kernel's last row took it)
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            evx_deblock_job(p, Y, c * EVX_DBK_CHUNK, cnt, lane);
         }
     }
 }

@@ -97,7 +97,7 @@ struct evxgpu_handle
     bool pending_encode, pending_decode;
     int wave_grid;
     int enc_grid;                   // persistent CTAs of the encoder's wavefront kernel
-    int k2_ctas;                    // frame kernel: service CTAs (search and deblocking queues)
+    int search_ctas, deblock_ctas;  // persistent CTAs of the search follower (8 warps each) and of the deblocking follower (one warp each)
     int pipe_rows;                  // frame kernel: row CTAs per frame in the pipeline
     int launch_row;                 // a frame's kernel is launched once the previous frame has begun to deblock this tile row (0: once it runs)
     long long *d_prof;
@@ -132,8 +132,8 @@ struct evxgpu_handle
         int16_t *src_mem; EvxPlanes src;
         EvxDesc *d_table; EvxInterResult *d_inter; int16_t *d_records; int *d_row_records; int *d_prev; int *d_sync;
         unsigned int *d_dbk;            // [mbh] filtered tile columns per tile row (base + count), [mbh] = `started`
-        cudaStream_t main;
-        cudaEvent_t ev_k1done, ev_k8done;
+        cudaStream_t main, k2s, k4s;    // the slot's frame: K1, wavefront kernel, K8, copies | search follower | deblocking follower
+        cudaEvent_t ev_k1done, ev_k8done, ev_go, ev_k2end, ev_k4end;
         unsigned int base;              // counter base of the frame last submitted into the slot
         bool used;
     } fs[EVX_MAX_SLOTS];
@@ -173,6 +173,7 @@ extern "C" {
 
 static int sync_all(evxgpu_handle *h);
 static void use_slot(evxgpu_handle *h, int q);
+static void free_slot_extras(evxgpu_handle::frame_slot &f);
 
 const char *evxgpu_last_error(void) { return g_err; }
 
@@ -202,12 +203,7 @@ int evxgpu_destroy(evxgpu_handle *h)
             cudaFree(b.src_mem); cudaFree(b.d_table); cudaFree(b.d_inter); cudaFree(b.d_records); cudaFree(b.d_row_records); cudaFree(b.d_prev); cudaFree(b.d_sync);
             if (b.main) cudaStreamDestroy(b.main);
         }
-        for (int q = 0; q < EVX_MAX_SLOTS; ++q)
-        {
-            cudaFree(h->fs[q].d_dbk);
-            if (h->fs[q].ev_k1done) cudaEventDestroy(h->fs[q].ev_k1done);
-            if (h->fs[q].ev_k8done) cudaEventDestroy(h->fs[q].ev_k8done);
-        }
+        for (int q = 0; q < EVX_MAX_SLOTS; ++q) free_slot_extras(h->fs[q]);
         h->overlap = false;
     }
     cudaSetDevice(h->device);
@@ -277,7 +273,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     ok = ok && cudaMalloc(&h->d_dense, (size_t) h->nmb * 384 * 2) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_row_records, (size_t) h->g.mbh * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_record_slot, (size_t) h->nmb * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&h->d_sync, ((size_t) h->g.mbh * 3 + 2) * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->d_sync, ((size_t) h->g.mbh * 3 + 4) * 4) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_done, (size_t) h->nmb * 8) == cudaSuccess;
     ok = ok && cudaMalloc(&h->d_counters, 32) == cudaSuccess;
     {   // K8 (bin string): the scratch every encoder needs; the string buffers come with evxgpu_set_output
@@ -323,6 +319,7 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_inter_search)", e); }
         e = cudaFuncSetAttribute(evx_wavefront<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) EVX_FRAME_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(evx_wavefront<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) EVX_FRAME_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(evx_search_follow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EvxSearchFollowSmem));
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_wavefront)", e); }
     }
     {   // device-side waits are bounded (evx_kernels.cuh, EVX_BOUNDED_WAIT): budget and the mapped word the reason lands in
@@ -345,12 +342,13 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     // encoder wavefront: at most ceil(W/3) rows are ever active at once (row r runs during steps [3r, 3r+W));
     // a few spare CTAs absorb the row-to-row hand-over
     h->enc_grid = std::min(h->g.mbh, (h->g.mbw + 2) / 3 + 4);
-    h->k2_ctas = 10;
+    h->search_ctas = 24; h->deblock_ctas = 48;
     h->pipe_rows = h->enc_grid;
     h->launch_row = 0;
     if (const char *e = getenv("EVXGPU_LAUNCH_ROW")) { int v = atoi(e); if (v >= 0) h->launch_row = v; }      // measurements
     if (const char *e = getenv("EVXGPU_PIPE_ROWS")) { int v = atoi(e); if (v > 0) h->pipe_rows = std::min(h->g.mbh, v); }      // measurements
-    if (const char *e = getenv("EVXGPU_K2_CTAS")) { int v = atoi(e); if (v >= 0) h->k2_ctas = v; }      // measurements
+    if (const char *e = getenv("EVXGPU_SEARCH_CTAS")) { int v = atoi(e); if (v >= 0) h->search_ctas = v; }      // measurements (0: no search follower, the block loaders search)
+    if (const char *e = getenv("EVXGPU_DEBLOCK_CTAS")) { int v = atoi(e); if (v >= 0) h->deblock_ctas = v; }          // (0: no deblocking follower, the last row deblocks)
     int rc = evxgpu_reset(h);
     if (rc) { evxgpu_destroy(h); return rc; }
     *out = h;
@@ -370,6 +368,7 @@ int evxgpu_reset(evxgpu_handle *h)
             CK(cudaMemset(h->fs[q].src_mem, 0, plane_elems(h->g) * 2));
             CK(cudaMemset(h->fs[q].d_table, 0, (size_t) h->nmb * 16));
             CK(cudaMemset(h->fs[q].d_dbk, 0, (size_t) (h->g.mbh + 1) * 4));
+            CK(cudaMemset(h->fs[q].d_inter, 0, (size_t) h->nmb * (h->cfg.ref_count - 1) * sizeof(EvxInterResult)));      // (the stamps restart with frame_seq)
             h->fs[q].used = false; h->fs[q].base = 0;
         }
         h->frame_seq = 0;
@@ -378,6 +377,8 @@ int evxgpu_reset(evxgpu_handle *h)
     CK(cudaMemsetAsync(h->src_mem, 0, pe * 2, h->stream));
     for (int i = 0; i < h->cfg.ref_count; ++i) CK(cudaMemsetAsync(h->ring_mem[i], 0, pe * 2, h->stream));
     CK(cudaMemsetAsync(h->d_table, 0, (size_t) h->nmb * 16, h->stream));
+    // search results carry the stamp of their frame (never 0): fresh memory may hold anything, also another handle's stamps
+    CK(cudaMemsetAsync(h->d_inter, 0, (size_t) h->nmb * (h->cfg.ref_count - 1) * sizeof(EvxInterResult), h->stream));
     CK(cudaMemsetAsync(h->d_counters, 0, 32, h->stream));
     CK(cudaMemsetAsync(h->d_dc, 0, (size_t) h->nmb * 4 * 2, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -539,7 +540,7 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
 {
     EvxK3Params p;
     wavefront_params(h, p, frame_type, index, quality);
-    CK(cudaMemsetAsync(h->d_sync, 0, ((size_t) h->g.mbh * 3 + 2) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_sync, 0, ((size_t) h->g.mbh * 3 + 4) * 4, h->stream));
     t_begin(h, EVXGPU_T_WAVEFRONT);
     // one CTA per macroblock row in flight; rows are claimed by ticket, so any residency is deadlock-free
     // the only encoder on the device runs the kernel with the larger register budget (evx_wavefront.cuh)
@@ -622,10 +623,19 @@ static void use_slot(evxgpu_handle *h, int q)
 static int sync_all(evxgpu_handle *h)
 {
     if (h->overlap)
-        for (int q = 0; q < h->nslots; ++q) CK(cudaStreamSynchronize(h->fs[q].main));
+        for (int q = 0; q < h->nslots; ++q) { CK(cudaStreamSynchronize(h->fs[q].main)); CK(cudaStreamSynchronize(h->fs[q].k2s)); CK(cudaStreamSynchronize(h->fs[q].k4s)); }
     else CK(cudaStreamSynchronize(h->stream));
     if (h->copy_stream) CK(cudaStreamSynchronize(h->copy_stream));
     return 0;
+}
+
+static void free_slot_extras(evxgpu_handle::frame_slot &f)
+{
+    cudaFree(f.d_dbk);
+    if (f.k2s) cudaStreamDestroy(f.k2s);
+    if (f.k4s) cudaStreamDestroy(f.k4s);
+    cudaEvent_t *ev[5] = { &f.ev_k1done, &f.ev_k8done, &f.ev_go, &f.ev_k2end, &f.ev_k4end };
+    for (int k = 0; k < 5; ++k) if (*ev[k]) cudaEventDestroy(*ev[k]);
 }
 
 // frees what a failed enable_pipeline left behind (slot 0 keeps the handle's original allocations)
@@ -637,12 +647,7 @@ static void drop_pipeline(evxgpu_handle *h)
         cudaFree(b.src_mem); cudaFree(b.d_table); cudaFree(b.d_inter); cudaFree(b.d_records); cudaFree(b.d_row_records); cudaFree(b.d_prev); cudaFree(b.d_sync);
         if (b.main) cudaStreamDestroy(b.main);
     }
-    for (int q = 0; q < EVX_MAX_SLOTS; ++q)
-    {
-        cudaFree(h->fs[q].d_dbk);
-        if (h->fs[q].ev_k1done) cudaEventDestroy(h->fs[q].ev_k1done);
-        if (h->fs[q].ev_k8done) cudaEventDestroy(h->fs[q].ev_k8done);
-    }
+    for (int q = 0; q < EVX_MAX_SLOTS; ++q) free_slot_extras(h->fs[q]);
     memset(h->fs, 0, sizeof(h->fs));
 }
 
@@ -650,6 +655,8 @@ static int enable_pipeline(evxgpu_handle *h)
 {
     if (h->overlap) return 0;
     if (!h->own_stream) return 0;                         // a caller's stream cannot be one of several
+    if (const char *e = getenv("EVXGPU_FRAME_SLOTS")) { int v = atoi(e); if (v >= 1) h->want_slots = v; }
+    if (h->want_slots == 1) return 0;                     // evxgpu_config::frame_slots = 1: frame after frame (stand-alone kernels) -- many streams sharing a device
     if (h->device < 0 || h->device >= 64) return 0;
     if (!g_wait32)
     {
@@ -663,7 +670,6 @@ static int enable_pipeline(evxgpu_handle *h)
     // Frame slots: a frame may start once its predecessor is about 23 wavefront steps ahead (of W + 3(H-1)), so what
     // limits the frames in flight is the SMs, not the data: 44 row CTAs per 1080p frame, two per SM.
     int ns = h->want_slots > 0 ? h->want_slots : EVX_DEFAULT_SLOTS;
-    if (const char *e = getenv("EVXGPU_FRAME_SLOTS")) { int v = atoi(e); if (v >= 2) ns = v; }
     ns = std::max(2, std::min(ns, (int) EVX_MAX_SLOTS));
     evxgpu_handle::frame_slot &a = h->fs[0];
     a.src_mem = h->src_mem; a.src = h->src; a.d_table = h->d_table; a.d_inter = h->d_inter; a.d_records = h->d_records;
@@ -678,14 +684,20 @@ static int enable_pipeline(evxgpu_handle *h)
         ok = ok && cudaMalloc(&b.d_records, (size_t) h->nmb * 384 * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&b.d_row_records, (size_t) h->g.mbh * 4) == cudaSuccess;
         ok = ok && cudaMalloc(&b.d_prev, ((size_t) h->nmb * 2 + (size_t) h->g.mbh * 2) * 4) == cudaSuccess;
-        ok = ok && cudaMalloc(&b.d_sync, ((size_t) h->g.mbh * 3 + 2) * 4) == cudaSuccess;
+        ok = ok && cudaMalloc(&b.d_sync, ((size_t) h->g.mbh * 3 + 4) * 4) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&b.main, cudaStreamNonBlocking) == cudaSuccess;
     }
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (int q = 0; q < ns && ok; ++q)
     {
         ok = ok && cudaMalloc(&h->fs[q].d_dbk, (size_t) (h->g.mbh + 1) * 4) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k1done, cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&h->fs[q].ev_k8done, cudaEventDisableTiming) == cudaSuccess;
+        // the followers run at the highest priority: what they produce is what resident row CTAs (of this frame, and of
+        // the next) wait for, so their blocks should not queue behind other streams' launches
+        ok = ok && cudaStreamCreateWithPriority(&h->fs[q].k2s, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&h->fs[q].k4s, cudaStreamNonBlocking, prio_hi) == cudaSuccess;
+        cudaEvent_t *ev[5] = { &h->fs[q].ev_k1done, &h->fs[q].ev_k8done, &h->fs[q].ev_go, &h->fs[q].ev_k2end, &h->fs[q].ev_k4end };
+        for (int k = 0; k < 5; ++k) ok = ok && cudaEventCreateWithFlags(ev[k], cudaEventDisableTiming) == cudaSuccess;
         h->fs[q].base = 0; h->fs[q].used = false;
     }
     if (!ok) { drop_pipeline(h); return fail(3, "frame pipeline: out of device memory"); }
@@ -696,6 +708,7 @@ static int enable_pipeline(evxgpu_handle *h)
         {
             set_planes(b.src, b.src_mem, h->g);
             if (cudaMemset(b.src_mem, 0, pe * 2) != cudaSuccess || cudaMemset(b.d_table, 0, (size_t) h->nmb * 16) != cudaSuccess) ok = false;   // padding rows/columns stay zero
+            if (cudaMemset(b.d_inter, 0, (size_t) h->nmb * (h->cfg.ref_count - 1) * sizeof(EvxInterResult)) != cudaSuccess) ok = false;       // no stale stamps
         }
         if (cudaMemset(b.d_dbk, 0, (size_t) (h->g.mbh + 1) * 4) != cudaSuccess) ok = false;
     }
@@ -748,7 +761,7 @@ static int submit_pipelined(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_dev
             int slot = (int) ((frame_index + (uint32_t) R - (uint32_t) off) % (uint32_t) R);
             for (int c = 0; c < 3; ++c) kp.maps.m[(off - 1) * 3 + c] = h->maps_w[slot][c];
         }
-        CK(cudaMemsetAsync(f.d_sync, 0, ((size_t) h->g.mbh * 3 + 2) * 4, f.main));
+        CK(cudaMemsetAsync(f.d_sync, 0, ((size_t) h->g.mbh * 3 + 4) * 4, f.main));
         // Launched behind the previous frame's kernel: not before that one runs (so that whatever this kernel waits for is
         // already on the device) and, with launch_row > 0, not before it has deblocked the first tile columns of that tile row --
         // a frame whose CTAs become resident long before the previous frame lets them work only holds SM slots.
@@ -759,13 +772,28 @@ static int submit_pipelined(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_dev
             if (g_wait32((CUstream) f.main, addr, lr > 0 ? Ep + 1u : Ep, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
                 return fail(5, "stream memory operation failed");
         }
-        // wavefront rows in flight at once + the service CTAs of the search and deblocking queues
-        const int nsvc = frame_type == 1 ? h->k2_ctas : std::min(h->k2_ctas, 2);      // (an intra frame has deblocking jobs only)
-        const int grid = h->pipe_rows + nsvc;
-        kp.n_service = nsvc;
+        CK(cudaEventRecord(f.ev_go, f.main));
+        // the search follower: rows by ticket, search_ctas of them in flight ahead of the wavefront
+        if (frame_type == 1 && h->search_ctas > 0)
+        {
+            CK(cudaStreamWaitEvent(f.k2s, f.ev_go, 0));
+            evx_search_follow<<<std::min(h->g.mbh, h->search_ctas), EVX_SF_WARPS * 32, sizeof(EvxSearchFollowSmem), f.k2s>>>(kp);
+            CK(cudaEventRecord(f.ev_k2end, f.k2s));
+            h->launches++;
+        }
+        // the wavefront rows
+        const int grid = std::min(h->g.mbh, h->pipe_rows);
         if (h->k3_regs == 1) evx_wavefront<1><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
         else evx_wavefront<2><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
         h->launches++;
+        // the deblocking follower: tile rows by ticket, one warp each
+        CK(cudaStreamWaitEvent(f.k4s, f.ev_go, 0));
+        if (h->deblock_ctas > 0)
+        {
+            evx_deblock_follow<<<std::min(h->g.mbh, h->deblock_ctas), 32, 0, f.k4s>>>(kp);
+            h->launches++;
+        }
+        CK(cudaEventRecord(f.ev_k4end, f.k4s));
         CK(cudaGetLastError());
     }
 
@@ -781,6 +809,9 @@ static int submit_pipelined(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_dev
     h->pending_bins[q] = true;
     CK(cudaEventRecord(h->ev_out[q], f.main));
     if (h->timeline) CK(cudaEventRecord(h->ev_done[q], f.main));
+    // join: the tail of the slot's main stream is the whole frame (what the next frame in this slot queues behind)
+    CK(cudaStreamWaitEvent(f.main, f.ev_k4end, 0));
+    if (frame_type == 1 && h->search_ctas > 0) CK(cudaStreamWaitEvent(f.main, f.ev_k2end, 0));
     f.base = E; f.used = true;
     h->q_count++;
     h->pending_encode = true;
@@ -1017,7 +1048,7 @@ int evxgpu_decode_submit(evxgpu_handle *h, const evxgpu_block_desc *table, const
     p.g = h->g; p.R = h->cfg.ref_count; p.linear = h->cfg.linear_quant; p.frame_index = frame_index;
     p.table = h->d_table; p.records = h->d_dense; p.record_slot = h->d_record_slot; p.sync = h->d_sync;
     p.done = h->d_done; p.readers = h->d_done + h->nmb;
-    CK(cudaMemsetAsync(h->d_sync, 0, ((size_t) h->g.mbh * 3 + 2) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_sync, 0, ((size_t) h->g.mbh * 3 + 4) * 4, h->stream));
     CK(cudaMemsetAsync(h->d_done, 0, (size_t) h->nmb * 8, h->stream));
     t_begin(h, EVXGPU_T_DECODE_RECON);
     evx_decode_deps<<<(h->nmb + 255) / 256, 256, 0, h->stream>>>(h->d_table, h->g, frame_index, h->cfg.ref_count, p.readers);
