@@ -366,6 +366,31 @@ __device__ __forceinline__ void evx_block_cost_both(const EvxLaneBlock &ref, con
     mad = __reduce_max_sync(0xFFFFFFFFu, m);
 }
 
+// The exact scalar form of one sub-pel direction for this lane's twelve samples (samples outside [0, 16383]: never in real
+// video).  A call: inlined into every caller it doubled the size of the sub-pel code on the hot path.
+__device__ __noinline__ int4 evx_subpel_exact_lane(EvxLaneBlock best, EvxLaneBlock nb, EvxLaneBlock pos)
+{
+    int sh = 0, mh = 0, sq = 0, mq = 0;
+#pragma unroll 1
+    for (int k = 0; k < 6; ++k)
+    {
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+        {
+            int a = half ? evx_hi16(best.w[k]) : evx_lo16(best.w[k]);
+            int b = half ? evx_hi16(nb.w[k]) : evx_lo16(nb.w[k]);
+            int s = half ? evx_hi16(pos.w[k]) : evx_lo16(pos.w[k]);
+            // the blended sample is stored as int16 before it is compared (macroblock.h:210, 230)
+            int dh = abs(s - (int) (short) evx_lerp_half(a, b));
+            int dq = abs(s - (int) (short) evx_lerp_quarter(a, b));
+            if (k < 4) { sh += dh; sq += dq; }
+            mh = max(mh, dh);
+            mq = max(mq, dq);
+        }
+    }
+    return make_int4(sh, mh, sq, mq);
+}
+
 // One sub-pel direction: both the half- and the quarter-pel blend of `best` with its
 // neighbour `nb` (macroblock.h:203-241), SAD/MAD of each against the source.
 //
@@ -410,24 +435,11 @@ __device__ __forceinline__ void evx_subpel_cost(const EvxLaneBlock &best, const 
     }
     else
     {
-        sh = 0; mh = 0; sq = 0; mq = 0;
+        EvxLaneBlock pos;
 #pragma unroll
-        for (int k = 0; k < 6; ++k)
-        {
-#pragma unroll
-            for (int half = 0; half < 2; ++half)
-            {
-                int a = half ? evx_hi16(best.w[k]) : evx_lo16(best.w[k]);
-                int b = half ? evx_hi16(nb.w[k]) : evx_lo16(nb.w[k]);
-                int s = half ? evx_hi16(src.pos[k]) : evx_lo16(src.pos[k]);
-                // the blended sample is stored as int16 before it is compared (macroblock.h:210, 230)
-                int dh = abs(s - (int) (short) evx_lerp_half(a, b));
-                int dq = abs(s - (int) (short) evx_lerp_quarter(a, b));
-                if (k < 4) { sh += dh; sq += dq; }
-                mh = max(mh, dh);
-                mq = max(mq, dq);
-            }
-        }
+        for (int k = 0; k < 6; ++k) pos.w[k] = src.pos[k];
+        const int4 r = evx_subpel_exact_lane(best, nb, pos);
+        sh = r.x; mh = r.y; sq = r.z; mq = r.w;
     }
     sad_h = __reduce_add_sync(0xFFFFFFFFu, sh);
     mad_h = __reduce_max_sync(0xFFFFFFFFu, mh);

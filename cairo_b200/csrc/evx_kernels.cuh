@@ -209,6 +209,12 @@ __device__ __forceinline__ void evx_inter_search_warp(EvxWin &win, const EvxLane
     n_full = 1; n_sub = 0;
     if (s.mad < thr) return;                       // already a copy block: no search (motion.cpp:452)
     stage(0, px, py, win);
+    // The five rounds and the eight sub-pel directions are ROLLED loops: the search runs on ~28 warps per SM, each at its own
+    // place in the code, and what limits them next to other kernels is instruction supply, not the latency a rolled loop
+    // adds (unrolled the search is 70 KB of SASS per kernel; -DEVX_K2_UNROLLED keeps that form for A/B runs).
+#ifndef EVX_K2_UNROLLED
+#pragma unroll 1
+#endif
     for (int step = EVX_SEARCH_RADIUS; step > 0; step >>= 1)
     {
         // One 3x3 round (motion.cpp:254-275).  The eight outer cells are costed back to back (no
@@ -245,7 +251,11 @@ __device__ __forceinline__ void evx_inter_search_warp(EvxWin &win, const EvxLane
     EvxLaneBlock best;
     evx_load_block(win, s.bx, s.by, lane, best);
     int tsad = 0, tmad = 0;
+#if defined(EVX_K2_UNROLLED) || defined(EVX_K2_UNROLLED_SUBPEL)
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
     for (int d8 = 0; d8 < 8; ++d8)
     {
         const int d = d8 < 4 ? d8 : d8 + 1;
@@ -875,35 +885,41 @@ __device__ __forceinline__ void evx_edge_params(const EvxDesc *table, int ia, in
     strength = (ac && bc) ? 0 : ((ac != bc) ? 1 : 2);                          // deblock.cpp:67-79
 }
 
-// deblock.cpp:81-129 on p3..q3 = s[0..7]
-__device__ __forceinline__ void evx_filter8(int s[8], int qp, int strength, bool luma)
+// deblock.cpp:81-129 on p3..q3 = the eight int16 samples of v (x = p3|p2<<16 ... w = q2|q3<<16).  A CALL, not inlined: a tile
+// filters sixteen such lines, and sixteen inlined copies made the tile 50 KB of code -- next to the wavefront rows on the
+// same SMs it is instruction supply that limits everybody (evx_wavefront.cuh, evx_k3_compute).
+__device__ __noinline__ uint4 evx_filter8(uint4 v, int qp, int strength, int luma)
 {
-    int p3 = s[0], p2 = s[1], p1 = s[2], p0 = s[3], q0 = s[4], q1 = s[5], q2 = s[6], q3 = s[7];
-    int d0 = (short) abs(p0 - q0), d1 = (short) abs(p1 - p0), d2 = (short) abs(q1 - q0);
-    int al = EVX_ALPHA[qp & 31], be = EVX_BETA[qp & 31];
-    if (d0 >= al || d1 >= be || d2 >= be) return;
+    const int p3 = evx_lo16(v.x), p2 = evx_hi16(v.x), p1 = evx_lo16(v.y), p0 = evx_hi16(v.y);
+    const int q0 = evx_lo16(v.z), q1 = evx_hi16(v.z), q2 = evx_lo16(v.w), q3 = evx_hi16(v.w);
+    const int d0 = (short) abs(p0 - q0), d1 = (short) abs(p1 - p0), d2 = (short) abs(q1 - q0);
+    const int al = EVX_ALPHA[qp & 31], be = EVX_BETA[qp & 31];
+    if (d0 >= al || d1 >= be || d2 >= be) return v;
+    int s1 = p2, s2 = p1, s3 = p0, s4 = q0, s5 = q1, s6 = q2;
     if (strength == 2)
     {
-        s[3] = (short) evx_rdiv_pow2(p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1, 3);
-        s[2] = (short) evx_rdiv_pow2(p2 + p1 + p0 + q0, 2);
-        s[4] = (short) evx_rdiv_pow2(p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2, 3);
-        s[5] = (short) evx_rdiv_pow2(p0 + q0 + q1 + q2, 2);
+        s3 = evx_rdiv_pow2(p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1, 3);
+        s2 = evx_rdiv_pow2(p2 + p1 + p0 + q0, 2);
+        s4 = evx_rdiv_pow2(p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2, 3);
+        s5 = evx_rdiv_pow2(p0 + q0 + q1 + q2, 2);
         if (luma)
         {
-            s[1] = (short) evx_rdiv_pow2(2 * p3 + 3 * p2 + p1 + p0 + q0, 3);
-            s[6] = (short) evx_rdiv_pow2(2 * q3 + 3 * q2 + q1 + q0 + p0, 3);
+            s1 = evx_rdiv_pow2(2 * p3 + 3 * p2 + p1 + p0 + q0, 3);
+            s6 = evx_rdiv_pow2(2 * q3 + 3 * q2 + q1 + q0 + p0, 3);
         }
     }
     else if (strength == 1)
     {
-        s[3] = (short) evx_rdiv_pow2(((q0 + p0) * 4) + p1 - q1, 3);
-        s[4] = (short) evx_rdiv_pow2(((q0 + p0) * 4) + q1 - p1, 3);
+        s3 = evx_rdiv_pow2(((q0 + p0) * 4) + p1 - q1, 3);
+        s4 = evx_rdiv_pow2(((q0 + p0) * 4) + q1 - p1, 3);
         if (luma)
         {
-            s[2] = (short) evx_rdiv_pow2((p2 * 4) + (p0 * 2) + (q0 * 2), 3);
-            s[5] = (short) evx_rdiv_pow2((q2 * 4) + (q0 * 2) + (p0 * 2), 3);
+            s2 = evx_rdiv_pow2((p2 * 4) + (p0 * 2) + (q0 * 2), 3);
+            s5 = evx_rdiv_pow2((q2 * 4) + (q0 * 2) + (p0 * 2), 3);
         }
     }
+    // (every result is stored as a short, deblock.cpp: the pack keeps the low 16 bits)
+    return make_uint4(evx_pack16(p3, s1), evx_pack16(s2, s3), evx_pack16(s4, s5), evx_pack16(s6, q3));
 }
 
 struct EvxK4Params
@@ -922,7 +938,8 @@ __device__ __forceinline__ void evx_deblock_tile(const EvxPlanes &pl, const EvxG
     const int i = tx * 8, j = ty * 8;
     const bool has_l = i > 0, has_r = i < w, has_t = j > 0, has_b = j < h;
 
-    int t[8][8];          // t[row][col], rows j-4..j+3, cols i-4..i+3
+    // the tile as eight packed rows: t[r] = columns i-4..i+3 of row j-4+r, two int16 samples per word
+    uint4 t[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
     {
@@ -930,8 +947,7 @@ __device__ __forceinline__ void evx_deblock_tile(const EvxPlanes &pl, const EvxG
         uint2 a = make_uint2(0, 0), b = make_uint2(0, 0);
         if (rv && has_l) a = __ldcg(reinterpret_cast<const uint2 *>(img + (size_t) (j - 4 + r) * w + i - 4));
         if (rv && has_r) b = __ldcg(reinterpret_cast<const uint2 *>(img + (size_t) (j - 4 + r) * w + i));
-        t[r][0] = evx_lo16(a.x); t[r][1] = evx_hi16(a.x); t[r][2] = evx_lo16(a.y); t[r][3] = evx_hi16(a.y);
-        t[r][4] = evx_lo16(b.x); t[r][5] = evx_hi16(b.x); t[r][6] = evx_lo16(b.y); t[r][7] = evx_hi16(b.y);
+        t[r] = make_uint4(a.x, a.y, b.x, b.y);
     }
     int qp, st;
     // 1. vertical edge at column i, upper band (rows j-4..j-1 belong to band j-8)
@@ -942,10 +958,11 @@ __device__ __forceinline__ void evx_deblock_tile(const EvxPlanes &pl, const EvxG
         if (st)
         {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) evx_filter8(t[r], qp, st, luma);
+            for (int r = 0; r < 4; ++r) t[r] = evx_filter8(t[r], qp, st, luma);
         }
     }
-    // 2. horizontal edge at row j: columns i-4..i-1 belong to edge segment i-8, columns i..i+3 to segment i
+    // 2. horizontal edge at row j: columns i-4..i-1 belong to edge segment i-8, columns i..i+3 to segment i.  A column
+    // pair (2m, 2m+1) is word m of every row: the two columns are gathered by byte permutes, filtered, scattered back.
     if (has_t && has_b)
     {
 #pragma unroll
@@ -956,14 +973,22 @@ __device__ __forceinline__ void evx_deblock_tile(const EvxPlanes &pl, const EvxG
             evx_edge_params(table, col / mbs + ((j - 1) / mbs) * wb, col / mbs + (j / mbs) * wb, qp, st);
             if (!st) continue;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int m = 2 * half; m < 2 * half + 2; ++m)
             {
-                int s[8];
+                uint32_t wr[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) s[r] = t[r][half * 4 + c];
-                evx_filter8(s, qp, st, luma);
+                for (int r = 0; r < 8; ++r) wr[r] = m == 0 ? t[r].x : m == 1 ? t[r].y : m == 2 ? t[r].z : t[r].w;
+                uint4 c0 = make_uint4(__byte_perm(wr[0], wr[1], 0x5410), __byte_perm(wr[2], wr[3], 0x5410), __byte_perm(wr[4], wr[5], 0x5410), __byte_perm(wr[6], wr[7], 0x5410));
+                uint4 c1 = make_uint4(__byte_perm(wr[0], wr[1], 0x7632), __byte_perm(wr[2], wr[3], 0x7632), __byte_perm(wr[4], wr[5], 0x7632), __byte_perm(wr[6], wr[7], 0x7632));
+                c0 = evx_filter8(c0, qp, st, luma);
+                c1 = evx_filter8(c1, qp, st, luma);
+                const uint32_t a0[4] = { c0.x, c0.y, c0.z, c0.w }, a1[4] = { c1.x, c1.y, c1.z, c1.w };
 #pragma unroll
-                for (int r = 0; r < 8; ++r) t[r][half * 4 + c] = s[r];
+                for (int r = 0; r < 8; ++r)
+                {
+                    const uint32_t v = (r & 1) ? __byte_perm(a0[r >> 1], a1[r >> 1], 0x7632) : __byte_perm(a0[r >> 1], a1[r >> 1], 0x5410);
+                    if (m == 0) t[r].x = v; else if (m == 1) t[r].y = v; else if (m == 2) t[r].z = v; else t[r].w = v;
+                }
             }
         }
     }
@@ -975,15 +1000,15 @@ __device__ __forceinline__ void evx_deblock_tile(const EvxPlanes &pl, const EvxG
         if (st)
         {
 #pragma unroll
-            for (int r = 4; r < 8; ++r) evx_filter8(t[r], qp, st, luma);
+            for (int r = 4; r < 8; ++r) t[r] = evx_filter8(t[r], qp, st, luma);
         }
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r)
     {
         bool rv = r < 4 ? has_t : has_b;
-        if (rv && has_l) *reinterpret_cast<uint2 *>(img + (size_t) (j - 4 + r) * w + i - 4) = make_uint2(evx_pack16(t[r][0], t[r][1]), evx_pack16(t[r][2], t[r][3]));
-        if (rv && has_r) *reinterpret_cast<uint2 *>(img + (size_t) (j - 4 + r) * w + i) = make_uint2(evx_pack16(t[r][4], t[r][5]), evx_pack16(t[r][6], t[r][7]));
+        if (rv && has_l) *reinterpret_cast<uint2 *>(img + (size_t) (j - 4 + r) * w + i - 4) = make_uint2(t[r].x, t[r].y);
+        if (rv && has_r) *reinterpret_cast<uint2 *>(img + (size_t) (j - 4 + r) * w + i) = make_uint2(t[r].z, t[r].w);
     }
 }
 

@@ -65,15 +65,12 @@
 #define EVX_K3_CPW (8 / EVX_K3_CW)  // search cells (and sub-pel directions) per compute warp
 #define EVX_K3_CT (EVX_K3_CW * 32)
 #define EVX_K3_NT (EVX_K3_CT + 64)
-// The 384 elements of a macroblock over the compute threads.  Written as a fully unrolled outer loop around an inner
-// loop that runs at most once, so that with 256 threads the two passes (the second one only for threads < 128) sit in one
-// basic block and their loads overlap; -DEVX_K3_ROLLED384 keeps the plain strided loop for A/B runs.
-#ifdef EVX_K3_ROLLED384
-#define EVX_K3_FOR384(e) for (int e = tid; e < 384; e += EVX_K3_CT)
-#else
-#define EVX_K3_FOR384(e) _Pragma("unroll") for (int e##_it = 0; e##_it < (384 + EVX_K3_CT - 1) / EVX_K3_CT; ++e##_it) \
-                         for (int e = tid + e##_it * EVX_K3_CT; e < 384; e += 384)
-#endif
+// The 384 elements of a macroblock over the compute threads.  UNROLLED (a constant in scope: the latency-optimised build of
+// the kernel): a fully unrolled outer loop around an inner loop that runs at most once, so that with 256 threads the two
+// passes (the second one only for threads < 128) sit in one basic block and their loads overlap.  Otherwise the plain
+// strided loop: a third of the code.  See evx_k3_compute for when which form is used.
+#define EVX_K3_FOR384(e) _Pragma("unroll") for (int e##_it = 0; e##_it < (UNROLLED ? (384 + EVX_K3_CT - 1) / EVX_K3_CT : 1); ++e##_it) \
+                         for (int e = tid + e##_it * EVX_K3_CT; e < 384; e += (UNROLLED ? 384 : EVX_K3_CT))
 #define EVX_K3_ROWS 80            // window rows py-48 .. py+31
 #define EVX_K3_CROWS 40
 #define EVX_MAXREF 7
@@ -449,6 +446,12 @@ __device__ __forceinline__ bool evx_intra_legal(int x, int y, int px, int py, co
     return !(y > py - EVX_MB && x > px - EVX_MB) && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);   // motion.cpp:238-248
 }
 
+// UNROLLED: the five search rounds and the 384-element passes fully unrolled -- each round's step, cell table and buffer
+// index are then compile-time constants: 1.90 -> 1.73 -> 1.63 ms per 1080p frame ALONE on the device.  Next to other
+// kernels (frames of a stream pipelined, many streams) the SMs' instruction supply is what limits the rows, and the
+// rolled form is the faster one: 1 443 -> 1 654 frames/s in the six-slot pipeline for 4 % more latency alone.  So the
+// kernel that has the device to itself (evx_wavefront<1>) is built unrolled, the one that shares it (<2>) rolled.
+template <bool UNROLLED>
 __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &p, int by, int tid)
 {
     const int warp = tid >> 5, lane = tid & 31;
@@ -536,14 +539,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
 #ifdef EVX_K3_STATS
         uint32_t n_hold = 0;
 #endif
-        // Fully unrolled: each round's step, its cell table (round 0 scans other rows) and buffer index are then
-        // compile-time constants.  Measured at 1080p: 1.90 -> 1.73 ms per frame against the rolled loop
-        // (-DEVX_K3_ROLLED_ROUNDS keeps it for A/B runs).
-#ifdef EVX_K3_ROLLED_ROUNDS
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
+#pragma unroll (UNROLLED ? 5 : 1)
         for (int round = 0; round < 5; ++round)
         {
             const int step = EVX_SEARCH_RADIUS >> (round == 0 ? 0 : round);
@@ -899,7 +895,7 @@ __global__ void __launch_bounds__(EVX_K3_NT, MINCTAS) evx_wavefront(const __grid
 #ifdef EVX_K3_TIMELINE
         if (p.prof && tid == 0) p.prof[(size_t) H * 10 + (size_t) by * 4 + 1] = (long long) evx_globaltimer();      // left the queues, row starts
 #endif
-        if (warp < EVX_K3_CW) evx_k3_compute(S, p, by, tid);
+        if (warp < EVX_K3_CW) evx_k3_compute<MINCTAS == 1>(S, p, by, tid);
         else if (warp == EVX_K3_CW) evx_k3_block_loader(S, p, by, lane);
         else if (warp == EVX_K3_CW + 1) evx_k3_column_loader(S, p, by, lane);
         __syncthreads();      // every warp has left the row: its barriers and shared memory may be reused

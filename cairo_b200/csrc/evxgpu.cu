@@ -317,10 +317,15 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     {
         cudaError_t e = cudaFuncSetAttribute(evx_inter_search, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_inter_search)", e); }
-        e = cudaFuncSetAttribute(evx_wavefront<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) EVX_FRAME_SMEM);
+        e = cudaFuncSetAttribute(evx_wavefront<EVX_K3_MINCTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) EVX_FRAME_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(evx_wavefront<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) EVX_FRAME_SMEM);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(evx_search_follow, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(EvxSearchFollowSmem));
         if (e != cudaSuccess) { evxgpu_destroy(h); return fail(5, "cudaFuncSetAttribute(evx_wavefront)", e); }
+        if (const char *cv = getenv("EVXGPU_CARVEOUT"))      // measurements: shared-memory carve-out of the wavefront kernel in percent (what is left is L1)
+        {
+            cudaFuncSetAttribute(evx_wavefront<EVX_K3_MINCTAS>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+            cudaFuncSetAttribute(evx_wavefront<1>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+        }
     }
     {   // device-side waits are bounded (evx_kernels.cuh, EVX_BOUNDED_WAIT): budget and the mapped word the reason lands in
         h->wait_budget_ns = 4000ull * 1000000ull;
@@ -547,7 +552,7 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
     if (h->device >= 0 && h->device < 64 && g_encoders_live[h->device].load() <= 1 && !h->k3_regs_forced)
         evx_wavefront<1><<<h->enc_grid, EVX_K3_NT, EVX_FRAME_SMEM, h->stream>>>(p);
     else
-        evx_wavefront<2><<<h->enc_grid, EVX_K3_NT, EVX_FRAME_SMEM, h->stream>>>(p);
+        evx_wavefront<EVX_K3_MINCTAS><<<h->enc_grid, EVX_K3_NT, EVX_FRAME_SMEM, h->stream>>>(p);
     h->launches++;
     if (h->out_mode != 1)
     {
@@ -784,7 +789,7 @@ static int submit_pipelined(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_dev
         // the wavefront rows
         const int grid = std::min(h->g.mbh, h->pipe_rows);
         if (h->k3_regs == 1) evx_wavefront<1><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
-        else evx_wavefront<2><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
+        else evx_wavefront<EVX_K3_MINCTAS><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
         h->launches++;
         // the deblocking follower: tile rows by ticket, one warp each
         CK(cudaStreamWaitEvent(f.k4s, f.ev_go, 0));
