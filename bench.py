@@ -59,7 +59,7 @@ METRIC = "1080p P-frame encode frames/s per B200 (+1/2/4/8-GPU streams), bit-exa
 WORKLOAD = "configs[1]: 1080p synthetic 60-frame sequence, quality 16, 1 reference frame (ring of 2), quarter-pel ME"
 # algorithmic integer ops of one full-pel candidate / one sub-pel test
 OPS_FULLPEL, OPS_SUBPEL = 1024, 2560
-LOOKAHEAD = int(os.environ.get("EVX_BENCH_LOOKAHEAD", "12"))      # frames between submit() and collect(): six on the device + six with the coder threads
+LOOKAHEAD = int(os.environ.get("EVX_BENCH_LOOKAHEAD", "14"))      # frames between submit() and collect(): eight on the device + six with the coder threads
 
 
 def config_block():

@@ -199,7 +199,10 @@ __device__ __forceinline__ void evx_load_src_lane(const EvxPlanes &srcp, const E
 // +-32 range re-centres it there (every later position stays within [-16, +32) of that winner).
 struct EvxNoStage { __device__ __forceinline__ void operator()(int, int, int, EvxWin &) const {} };
 
-template <class Stage>
+// CELL_UNROLL: how many of a round's eight cells are costed per loop iteration.  8 (the round as one basic block) is the
+// fastest form for the stand-alone kernel (49 against 53 us per 1080p frame); 2 is a third of the code, which is what counts
+// for the search follower next to the wavefront rows (evx_wavefront.cuh).
+template <int CELL_UNROLL, class Stage>
 __device__ __forceinline__ void evx_inter_search_warp(EvxWin &win, const EvxLaneSrc &src, const EvxLaneBlock &centre, const EvxGeom &g, int px, int py, int thr,
                                                       int lane, EvxSel &s, uint32_t &n_full, uint32_t &n_sub, Stage stage)
 {
@@ -222,19 +225,18 @@ __device__ __forceinline__ void evx_inter_search_warp(EvxWin &win, const EvxLane
         // running best itself, whose sad/mad are already in the state.  Out-of-frame cells still
         // lie inside the zero-filled TMA window, so they are costed too and simply not accepted.
         const int basex = s.bx, basey = s.by;
-        int csad[9], cmad[9];
-        csad[4] = s.sad; cmad[4] = s.mad;
-#pragma unroll
-        for (int c = 0; c < 9; ++c)
+        // lane c keeps the cost of cell c (lane 4: the centre, i.e. the state's own); the cells two at a time
+        int mysad = s.sad, mymad = s.mad;
+#pragma unroll CELL_UNROLL
+        for (int o = 0; o < 8; ++o)
         {
-            if (c == 4) continue;
-            evx_load_block(win, basex + (c % 3 - 1) * step, basey + (c / 3 - 1) * step, lane, ref);
-            evx_block_cost(ref, src, thr, csad[c], cmad[c]);
+            const int c = o < 4 ? o : o + 1;
+            const int cy = c / 3, cx = c - 3 * cy;
+            int csad, cmad;
+            evx_load_block(win, basex + (cx - 1) * step, basey + (cy - 1) * step, lane, ref);
+            evx_block_cost(ref, src, thr, csad, cmad);
+            if (lane == c) { mysad = csad; mymad = cmad; }
         }
-        // acceptance in closed form (evx_select_fullpel): lane c takes cell c
-        int mysad = csad[0], mymad = cmad[0];
-#pragma unroll
-        for (int c = 1; c < 9; ++c) { mysad = lane == c ? csad[c] : mysad; mymad = lane == c ? cmad[c] : mymad; }
         const int lc = lane < 9 ? lane : 0;
         const int x = basex + (lc % 3 - 1) * step, y = basey + (lc / 3 - 1) * step;
         const bool legal = lane < 9 && !(x < 0 || x > g.w - EVX_MB || y < 0 || y > g.h - EVX_MB);
@@ -349,6 +351,7 @@ struct EvxK2Stage
 
 // One (macroblock, reference) search by one warp.  `win_mem` holds EVX_K2W_BYTES of 128-byte aligned shared memory,
 // `bar` an initialised mbarrier (count 1) whose completed phases `phase` counts.  Returns through `out` (lane 0 writes it).
+template <int CELL_UNROLL>
 __device__ __forceinline__ void evx_k2_item(const CUtensorMap *maps3, const EvxPlanes &srcp, const EvxPlanes &refp, const EvxGeom &g,
                                             int thr, int bx, int by, int ref, int lane, uint8_t *win_mem, uint64_t *bar, uint32_t &phase,
                                             EvxInterResult *out, unsigned long long *counters, uint32_t stamp)
@@ -375,7 +378,7 @@ __device__ __forceinline__ void evx_k2_item(const CUtensorMap *maps3, const EvxP
 
     EvxSel s;
     uint32_t n_full, n_sub;
-    evx_inter_search_warp(win, src, centre, g, px, py, thr, lane, s, n_full, n_sub, stage);
+    evx_inter_search_warp<CELL_UNROLL>(win, src, centre, g, px, py, thr, lane, s, n_full, n_sub, stage);
     if (n_full == 1) stage.land();      // copy block: the window was never used, but it must have landed before its shared memory is reused or released
 
     if (lane == 0)
@@ -390,6 +393,9 @@ __device__ __forceinline__ void evx_k2_item(const CUtensorMap *maps3, const EvxP
     }
 }
 
+// (Measured and rejected: persistent CTAs of eight warps, four per SM = 32 searches per SM, pulling items off a ticket
+// counter: 51.7 against 49.2 us per 1080p frame, 128 against 119 us with three references -- the hardware's own CTA
+// dispatch of one-warp CTAs is the better ticket machine.)
 __global__ void __launch_bounds__(32, EVX_K2W_PER_SM) evx_inter_search(const __grid_constant__ EvxK2Params p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -397,8 +403,8 @@ __global__ void __launch_bounds__(32, EVX_K2W_PER_SM) evx_inter_search(const __g
     const int lane = threadIdx.x, ref = blockIdx.z, bx = blockIdx.x, by = blockIdx.y + p.row0;
     if (lane == 0) evx_mbar_init(bar, 1);
     uint32_t phase = 0;
-    evx_k2_item(&p.maps.m[ref * 3], p.src, p.ref[ref], p.g, p.thr, bx, by, ref, lane, smem, bar, phase,
-                p.results + (size_t) ref * p.g.mbw * p.g.mbh + (size_t) by * p.g.mbw + bx, p.counters, 0u);
+    evx_k2_item<8>(&p.maps.m[ref * 3], p.src, p.ref[ref], p.g, p.thr, bx, by, ref, lane, smem, bar, phase,
+                   p.results + (size_t) ref * p.g.mbw * p.g.mbh + (size_t) by * p.g.mbw + bx, p.counters, 0u);
 }
 
 // ------------------------------------------------------------------ K3 / K5 shared: transform + reconstruction of one macroblock

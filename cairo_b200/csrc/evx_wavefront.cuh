@@ -227,7 +227,7 @@ __device__ __forceinline__ void evx_run_search_item(const EvxK3Params &p, int y,
 {
     const int nref = p.R - 1, nmb = p.g.mbw * p.g.mbh, bx = it / nref, ref = it - bx * nref;
     const int rslot = (int) ((p.frame_index + (uint32_t) p.R - (uint32_t) (ref + 1)) % (uint32_t) p.R);       // common.cpp:192-195
-    evx_k2_item(&p.maps.m[ref * 3], p.src, p.ring[rslot], p.g, p.thr, bx, y, ref, lane, win, bar, phase,
+    evx_k2_item<2>(&p.maps.m[ref * 3], p.src, p.ring[rslot], p.g, p.thr, bx, y, ref, lane, win, bar, phase,
                 p.inter + (size_t) ref * nmb + (size_t) y * p.g.mbw + bx, p.counters, p.stamp);
 }
 
@@ -640,6 +640,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         // ---- classify, encode.cpp:17-67
         EvxDesc d = evx_desc_from_sel(s, 1, 0, px, py, thr);
         int best_sad = s.sad, best_ref = -1;
+#pragma unroll 1
         for (int r = 0; r < nref; ++r)
         {
             const int4 raw = S.idesc[slot][r];

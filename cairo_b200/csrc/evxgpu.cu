@@ -47,7 +47,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
 typedef CUresult (*stream_memop_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 static stream_memop_fn g_wait32 = NULL;
 #include <atomic>
-enum { EVX_MAX_SLOTS = 16, EVX_DEFAULT_SLOTS = 6 };           // frame slots a handle may own (evxgpu_config::frame_slots, EVXGPU_FRAME_SLOTS)
+enum { EVX_MAX_SLOTS = 16, EVX_DEFAULT_SLOTS = 8 };           // frame slots a handle may own (evxgpu_config::frame_slots, EVXGPU_FRAME_SLOTS)
 // Encoders (handles that have encoded a frame) alive per device, process-wide.  Only a tuning hint: a stand-alone
 // wavefront launch takes the larger register budget while the handle is the device's only encoder.  Nothing about
 // correctness or progress depends on it (frames of any number of streams and processes may share the device).
