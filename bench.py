@@ -510,7 +510,7 @@ def run_ours(args):
     # string, the input of the host arithmetic coder.  Nothing but submit/collect runs inside the timed region.
     sampler = ClockSampler(local_rank)
     sampler.start()
-    nwin = windows_for(K, 0.72, args.min_ms)
+    nwin = windows_for(K, 0.42, args.min_ms)
     dv = device_run(gpu, dev, fidx, W, H, REF_COUNT, 0, K, warmup, nwin, local_rank, barrier)
 
     # ---- e2e: the public API with host frames.  Two loops over the same frames: the reference's synchronous call
@@ -541,7 +541,7 @@ def run_ours(args):
     del enc
 
     enc, head = fresh_encoder()
-    nwin_e = windows_for(K, 0.8, args.min_ms)
+    nwin_e = windows_for(K, 0.45, args.min_ms)
     ee = e2e_run(enc, host, fidx, W, H, K, warmup, nwin_e, LOOKAHEAD, K, barrier)
     clocks = sampler.stop()
     del enc
@@ -679,7 +679,7 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
         e.set_quality(QUALITY)
         for t in range(warmup):
             e.encode((int(dev[fidx(t)].data_ptr()), W, H))
-        r = e2e_run(e, None, fidx, W, H, K, warmup, windows_for(K, 0.8, args.min_ms / 2), LOOKAHEAD, min(K, 8), barrier, ptr_of=lambda t: int(dev[fidx(t)].data_ptr()))
+        r = e2e_run(e, None, fidx, W, H, K, warmup, windows_for(K, 0.45, args.min_ms / 2), LOOKAHEAD, min(K, 8), barrier, ptr_of=lambda t: int(dev[fidx(t)].data_ptr()))
         del e
         for i, (d, b) in enumerate(r["coded"]):
             if not streams_equal(d, b, coded[i][0], coded[i][1], False):
@@ -749,7 +749,7 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
     for name, linear in (("r4", 0), ("r4_linear", 1)):
         try:
             ks, cn = kernel_pass(gpu, dev, fidx, W, H, 4, linear, warmup, 12, device)
-            r = device_run(gpu, dev, fidx, W, H, 4, linear, K, warmup, windows_for(K, 1.1, args.min_ms / 2), device, barrier)
+            r = device_run(gpu, dev, fidx, W, H, 4, linear, K, warmup, windows_for(K, 0.62, args.min_ms / 2), device, barrier)
             blk = {"workload": "configs[2]: 1080p, quality 16, ring of 4 (3 past reference frames)%s, adaptive QP, deblocking" % (", linear quantiser" if linear else ", MPEG quantiser"),
                    "value": agg(r["stats"]["median_ms"] / K), "unit": "frames/s", "windows": r["stats"], "kernel_ms_per_step": ks,
                    "parity": "tests/test_gpu_fullsize.py::test_1080p_pipelined_stream_equals_reference[%s]" % name}
@@ -763,7 +763,7 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
                 e.set_quality(QUALITY)
                 for t in range(warmup):
                     e.encode((int(host[fidx(t)].data_ptr()), W, H))
-                rr = e2e_run(e, host, fidx, W, H, K, warmup, windows_for(K, 1.2, args.min_ms / 2), LOOKAHEAD, 0, barrier)
+                rr = e2e_run(e, host, fidx, W, H, K, warmup, windows_for(K, 0.65, args.min_ms / 2), LOOKAHEAD, 0, barrier)
                 del e
                 blk["e2e"] = {"value": agg(rr["stats"]["median_ms"] / K), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes, "windows": rr["stats"]}
             out[name] = blk

@@ -347,8 +347,14 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     // encoder wavefront: at most ceil(W/3) rows are ever active at once (row r runs during steps [3r, 3r+W));
     // a few spare CTAs absorb the row-to-row hand-over
     h->enc_grid = std::min(h->g.mbh, (h->g.mbw + 2) / 3 + 4);
-    h->search_ctas = 24; h->deblock_ctas = 48;
-    h->pipe_rows = h->enc_grid;
+    // The frame pipeline (several frames of the stream on the device at once): what limits it is the SMs' instruction supply,
+    // and fewer resident CTAs per frame are the faster choice -- measured at 1080p with eight slots: 44 / 36 / 32 / 28 row CTAs
+    // per frame 2 188 / 2 339 / 2 464 / 2 396 frames/s; 48 / 24 / 16 deblocking warps 2 188 / 2 277 / 2 160; 16 / 24 / 34
+    // search CTAs 2 050 / 2 188 / 2 090.
+    // (ring of 4: 24 / 36 / 48 search CTAs 1 460 / 1 648 / 1 648 frames/s; 3840x2160: 46 / 24 search CTAs 743 / 787, 64 / 48 / 84
+    // row CTAs 743 / 692 / 683, 46 / 24 deblocking warps 743 / 723)
+    h->search_ctas = std::min(h->g.mbh, 12 * h->cfg.ref_count); h->deblock_ctas = (h->g.mbh + 2) / 3 + 1;
+    h->pipe_rows = std::min(h->g.mbh, std::max(4, (4 * h->g.mbw + 14) / 15));
     h->launch_row = 0;
     if (const char *e = getenv("EVXGPU_LAUNCH_ROW")) { int v = atoi(e); if (v >= 0) h->launch_row = v; }      // measurements
     if (const char *e = getenv("EVXGPU_PIPE_ROWS")) { int v = atoi(e); if (v > 0) h->pipe_rows = std::min(h->g.mbh, v); }      // measurements
