@@ -13,7 +13,7 @@ device time.
   value  : frames already resident in HBM -> pixel pipeline (K1 convert, search follower, wavefront rows,
            deblocking follower, K8 binarisation) -> the slice's bin string on the host (its D2H inside the timed
            region, host arithmetic coder excluded); the frames of the stream follow each other macroblock by
-           macroblock on the device (six frame slots).
+           macroblock on the device (ten frame slots).
   e2e    : evx1_encoder::submit/collect (the two halves of the reference's encode(), include/evx1_c.h) with HOST
            frames in pinned memory -> EVX1 bitstream bytes: H2D, kernels, D2H and the host arithmetic coder;
            e2e.synchronous is the same loop through evx1_encoder::encode, one frame at a time.
@@ -59,7 +59,7 @@ METRIC = "1080p P-frame encode frames/s per B200 (+1/2/4/8-GPU streams), bit-exa
 WORKLOAD = "configs[1]: 1080p synthetic 60-frame sequence, quality 16, 1 reference frame (ring of 2), quarter-pel ME"
 # algorithmic integer ops of one full-pel candidate / one sub-pel test
 OPS_FULLPEL, OPS_SUBPEL = 1024, 2560
-LOOKAHEAD = int(os.environ.get("EVX_BENCH_LOOKAHEAD", "14"))      # frames between submit() and collect(): eight on the device + six with the coder threads
+LOOKAHEAD = int(os.environ.get("EVX_BENCH_LOOKAHEAD", "16"))      # frames between submit() and collect(): ten on the device + six with the coder threads
 
 
 def config_block():
@@ -542,7 +542,7 @@ def run_ours(args):
 
     enc, head = fresh_encoder()
     nwin_e = windows_for(K, 0.45, args.min_ms)
-    ee = e2e_run(enc, host, fidx, W, H, K, warmup, nwin_e, LOOKAHEAD, K, barrier)
+    ee = e2e_run(enc, host, fidx, W, H, K, warmup, nwin_e, LOOKAHEAD, max(K, 240), barrier)      # (the first 240 streams feed the decode extra)
     clocks = sampler.stop()
     del enc
 
@@ -620,7 +620,7 @@ def run_ours(args):
             "scope": {"value": "frames resident in HBM -> K1 convert, search follower, wavefront rows, deblocking follower, K8 binarisation -> the slice's "
                                "bin string on the host (D2H inside the timed region, %d bytes per frame); host arithmetic coder excluded; %d frame slots: "
                                "consecutive frames follow each other macroblock by macroblock on the device" % (dv["d2h_bytes"] // dv["frames"], dv["slots"]),
-                      "e2e": "evx1_encoder::submit/collect (the two halves of encode, %d frames between a frame's submit and its collect: six on the device, "
+                      "e2e": "evx1_encoder::submit/collect (the two halves of encode, %d frames between a frame's submit and its collect: ten on the device, "
                              "the rest with the coder threads), pinned host RGB -> EVX1 bitstream bytes: H2D, kernels, D2H of the bin string, host arithmetic "
                              "coder.  e2e.synchronous is the same through evx1_encoder::encode, one frame at a time" % LOOKAHEAD,
                       "kernels": "kernel_ms_per_step and the rooflines are from a separate pass with the frames one after the other (stand-alone kernels)"},
@@ -805,7 +805,10 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
         mine = fanout.streams_of_rank(64, rank, world)
         uniq, wu = 6, 2
         nfr = 24 * 64 // max(1, len(mine))              # the same number of timed frames per GPU whatever the partition
-        slots = 1 if len(mine) >= 4 else 0              # many streams fill the device by themselves: frame after frame within each
+        # Frames in flight per stream: about 24 across the streams of a GPU saturate it (measured: 16 streams x 1 slot 2 958,
+        # 8 x 3 2 889, 4 x 4 2 752, 2 x 8 2 604, 1 x 8 2 432 frames/s; 16 x 2 only 2 260) -- many streams fill the device
+        # by themselves, frame after frame within each.
+        slots = max(1, min(10, 24 // max(1, len(mine))))
         # distinct content per stream: four generator seeds, each shifted horizontally by 16 * (stream // 4) samples
         base = {s: synth_frames(W, H, uniq, 1000 + s) for s in sorted({m % 4 for m in mine})}
         hosts = [torch.empty((uniq, H, W, 3), dtype=torch.uint8).pin_memory() for _ in mine]
@@ -819,14 +822,14 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
             list(ex.map(fill, range(len(mine))))
         wrap = lambda t: t if t < uniq else 1 + (t - 1) % (uniq - 1)
         barrier()
-        fps, dt = multi_stream_e2e(api, hosts, wrap, wu, nfr, device, slots)
+        fps, dt = multi_stream_e2e(api, hosts, wrap, wu, nfr, device, slots, look=max(3, slots + 3))
         total_frames = fanout.sum_over_ranks([len(mine) * nfr], device="cuda")[0]
         worst = fanout.max_over_ranks([dt], device="cuda")[0]
         out["fanout64"] = {"workload": "configs[4]: 64 independent 1080p streams (distinct content: 4 generator seeds x 16 horizontal shifts, 6 distinct frames each, "
                                        "wrapping inside the P-frames), quality 16, ring of 2, partitioned round-robin over the ranks (cairo_b200.fanout.streams_of_rank); "
                                        "one host thread + two coder threads per stream, evx1_encoder::submit/collect with pinned host frames -> bitstreams",
                            "value": total_frames / worst, "unit": "frames/s", "streams": 64, "streams_per_gpu": len(mine), "frames_per_stream": nfr,
-                           "host_cores": os.cpu_count(), "frame_slots_per_stream": slots if slots else 6, "seconds": worst}
+                           "host_cores": os.cpu_count(), "frame_slots_per_stream": slots, "seconds": worst}
         del hosts
     except Exception as ex:
         out["fanout64"] = {"value": None, "error": str(ex)}

@@ -7,14 +7,14 @@
 // schedule is a wavefront: (bx,by) after (bx-1,by) and (min(bx+2,W-1),by-1).
 //
 // Mapping: ONE CTA PER MACROBLOCK ROW, warp specialised --
-//   warps 0..7  compute: the eight outer candidates of a 3x3 search round, one per warp (the
+//   warps 0..CW-1  compute (CW = 8 or 4, EvxK3Cfg): the eight outer candidates of a 3x3 search round, 8 / CW per warp (the
 //               centre is the running best, whose cost is already known), then the transform
 //               path of the macroblock;
-//   warp  8     publisher + block loader.  Each time a macroblock of the row completes it first
+//   warp  CW    publisher + block loader.  Each time a macroblock of the row completes it first
 //               fences and releases progress[by] so the row below can follow, then stages the
 //               macroblock after next: source block, K2's inter results and their predictions,
 //               the stale columns of the row below -- nothing that depends on the row above;
-//   warp  9     column loader: slides the search window (a ring of 8 macroblock columns in
+//   warp  CW+1  column loader: slides the search window (a ring of 8 macroblock columns in
 //               shared memory) -- the 16 new columns of the three rows above as soon as the row
 //               above has published them.  A loader of its own, because this is the row-to-row
 //               critical path: with one loader doing both, staging macroblock n+1 queued behind
@@ -56,21 +56,33 @@
 
 #include "evx_kernels.cuh"
 
-#ifndef EVX_K3_CW
-#define EVX_K3_CW 8               // compute warps
+// Compute warps of a row CTA, per build of the kernel (the eight outer cells of a search round and the eight sub-pel
+// directions are spread over them: 8 / CW each).  Eight warps make the shortest macroblock, so the kernel that has the
+// device to itself uses eight (1.65 against 1.79 ms per 1080p frame).  Every warp repeats the selection and the state
+// update of a round, so four warps execute a third fewer instructions per macroblock -- and next to other kernels
+// instruction supply is the limit: 2 432 -> 2 844 frames/s in the eight-slot pipeline, 2 958 -> 3 256 with
+// 16 streams.  So the kernel that shares the device uses four.
+#ifndef EVX_K3_CW_ALONE
+#define EVX_K3_CW_ALONE 8
+#endif
+#ifndef EVX_K3_CW_SHARED
+#define EVX_K3_CW_SHARED 4
 #endif
 #ifndef EVX_K3_MINCTAS
-#define EVX_K3_MINCTAS 2            // CTAs per SM the register budget is set for (3 = 64 registers, spills: measured slower)
+#define EVX_K3_MINCTAS 2            // CTAs per SM the register budget of the sharing build is set for
 #endif
-#define EVX_K3_CPW (8 / EVX_K3_CW)  // search cells (and sub-pel directions) per compute warp
-#define EVX_K3_CT (EVX_K3_CW * 32)
-#define EVX_K3_NT (EVX_K3_CT + 64)
+template <int MINCTAS> struct EvxK3Cfg
+{
+    static constexpr int CW = MINCTAS == 1 ? EVX_K3_CW_ALONE : EVX_K3_CW_SHARED;      // compute warps
+    static constexpr int CT = CW * 32;                                               // compute threads
+    static constexpr int NT = CT + 64;                                               // + block loader + column loader
+};
 // The 384 elements of a macroblock over the compute threads.  UNROLLED (a constant in scope: the latency-optimised build of
 // the kernel): a fully unrolled outer loop around an inner loop that runs at most once, so that with 256 threads the two
 // passes (the second one only for threads < 128) sit in one basic block and their loads overlap.  Otherwise the plain
-// strided loop: a third of the code.  See evx_k3_compute for when which form is used.
-#define EVX_K3_FOR384(e) _Pragma("unroll") for (int e##_it = 0; e##_it < (UNROLLED ? (384 + EVX_K3_CT - 1) / EVX_K3_CT : 1); ++e##_it) \
-                         for (int e = tid + e##_it * EVX_K3_CT; e < 384; e += (UNROLLED ? 384 : EVX_K3_CT))
+// strided loop: a third of the code.  See evx_k3_compute for when which form is used.  (CT: the compute threads, in scope.)
+#define EVX_K3_FOR384(e) _Pragma("unroll") for (int e##_it = 0; e##_it < (UNROLLED ? (384 + CT - 1) / CT : 1); ++e##_it) \
+                         for (int e = tid + e##_it * CT; e < 384; e += (UNROLLED ? 384 : CT))
 #define EVX_K3_ROWS 80            // window rows py-48 .. py+31
 #define EVX_K3_CROWS 40
 #define EVX_MAXREF 7
@@ -93,23 +105,17 @@ struct EvxK3Smem
     int last_motion, last_coded;              // K8 bookkeeping (thread 0)
 };
 
-// the CTA's current ticket; the search role's per-warp windows share the wavefront role's shared memory
+// the CTA's current ticket
 struct EvxFrameCtl { int row; };
-#define EVX_K3_WARPS (EVX_K3_NT / 32)
-struct EvxK2RoleSmem
-{
-    uint8_t win[EVX_K3_WARPS][EVX_K2W_BYTES];      // 128-byte aligned TMA destinations (6912 = 54 x 128)
-    uint64_t bar[EVX_K3_WARPS];
-};
 #define EVX_FRAME_CTL_BYTES 128
-#define EVX_FRAME_SMEM (EVX_FRAME_CTL_BYTES + (sizeof(EvxK3Smem) > sizeof(EvxK2RoleSmem) ? sizeof(EvxK3Smem) : sizeof(EvxK2RoleSmem)))
+#define EVX_FRAME_SMEM (EVX_FRAME_CTL_BYTES + sizeof(EvxK3Smem))
 
 __device__ __forceinline__ void evx_mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(evx_smem_addr(bar)) : "memory");
 }
 
-__device__ __forceinline__ void evx_compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EVX_K3_CT) : "memory"); }
+template <int CT> __device__ __forceinline__ void evx_compute_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory"); }
 
 // int16 sample of the ring window
 __device__ __forceinline__ int evx_ring_y(const EvxK3Smem &S, int x, int wrow) { return reinterpret_cast<const int16_t *>(S.wy)[wrow * (EVX_RING_PWY * 2) + (x & 127)]; }
@@ -451,9 +457,10 @@ __device__ __forceinline__ bool evx_intra_legal(int x, int y, int px, int py, co
 // kernels (frames of a stream pipelined, many streams) the SMs' instruction supply is what limits the rows, and the
 // rolled form is the faster one: 1 443 -> 1 654 frames/s in the six-slot pipeline for 4 % more latency alone.  So the
 // kernel that has the device to itself (evx_wavefront<1>) is built unrolled, the one that shares it (<2>) rolled.
-template <bool UNROLLED>
+template <bool UNROLLED, int CW>
 __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &p, int by, int tid)
 {
+    constexpr int CT = CW * 32, CPW = 8 / CW;      // compute threads; search cells (and sub-pel directions) per compute warp
     const int warp = tid >> 5, lane = tid & 31;
     const EvxGeom g = p.g;
     const int cw = g.w >> 1, py = by * EVX_MB;
@@ -473,11 +480,11 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     for (int k = 0; k < 8; ++k) { lut_f[k] = evx_dct_lut(tid & 7, k); lut_i[k] = evx_dct_lut(k, tid & 7); }
 
     // the search cells this warp owns: (dx,dy) in units of the round's step
-    int cdx0[EVX_K3_CPW], cdy0[EVX_K3_CPW], cdx[EVX_K3_CPW], cdy[EVX_K3_CPW], ccell0[EVX_K3_CPW], ccell[EVX_K3_CPW];
+    int cdx0[CPW], cdy0[CPW], cdx[CPW], cdy[CPW], ccell0[CPW], ccell[CPW];
 #pragma unroll
-    for (int q = 0; q < EVX_K3_CPW; ++q)
+    for (int q = 0; q < CPW; ++q)
     {
-        const int k = warp + q * EVX_K3_CW;
+        const int k = warp + q * CW;
         ccell0[q] = k; cdx0[q] = k % 3 - 1; cdy0[q] = k / 3 - 2;          // round 0: rows -32,-16,0
         ccell[q] = k < 4 ? k : k + 1; cdx[q] = ccell[q] % 3 - 1; cdy[q] = ccell[q] / 3 - 1;
     }
@@ -554,9 +561,9 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             {
                 // this warp's cells: loads and packed arithmetic first, then every reduction back to back;
                 // only the raw (sad, mad) pair is published -- keys are built by the selecting lanes
-                int la[EVX_K3_CPW], lm[EVX_K3_CPW];
+                int la[CPW], lm[CPW];
 #pragma unroll
-                for (int q = 0; q < EVX_K3_CPW; ++q)
+                for (int q = 0; q < CPW; ++q)
                 {
                     const int x = s.bx + (round == 0 ? cdx0[q] : cdx[q]) * step;
                     const int y = s.by + (round == 0 ? cdy0[q] : cdy[q]) * step;
@@ -573,7 +580,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                     lm[q] = evx_block_mad_lane(ref, src);
                 }
 #pragma unroll
-                for (int q = 0; q < EVX_K3_CPW; ++q)
+                for (int q = 0; q < CPW; ++q)
                 {
                     const int sad = __reduce_add_sync(0xFFFFFFFFu, la[q]), mad = __reduce_max_sync(0xFFFFFFFFu, lm[q]);
                     if (lane == 0) S.cand2[buf][round == 0 ? ccell0[q] : ccell[q]] = make_int2(sad, mad);
@@ -585,7 +592,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
             const int ssdl = (cxl - px) * (cxl - px) + (cyl - py) * (cyl - py);
             const bool from_state = round != 0 && lane == 4;            // the centre is the running best itself
             const bool legall = lane < 9 && evx_intra_legal(cxl, cyl, px, py, g) && !(round == 0 && lane == 8);
-            evx_compute_sync();
+            evx_compute_sync<CT>();
             {
                 int2 v = S.cand2[buf][lc];
                 if (from_state) v = make_int2(s.sad, s.mad);
@@ -610,9 +617,9 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         {
             if (s.bx + 1 >= px + 17) EVX_K3_NEED2();
 #pragma unroll
-            for (int q = 0; q < EVX_K3_CPW; ++q)
+            for (int q = 0; q < CPW; ++q)
             {
-                const int k = warp + q * EVX_K3_CW;                       // direction slot 0..7 (centre skipped)
+                const int k = warp + q * CW;                       // direction slot 0..7 (centre skipped)
                 const int x = s.bx + cdx[q], y = s.by + cdy[q];
                 EvxLaneBlock best, nb;
                 int shh, mh, sq, mq;
@@ -622,7 +629,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 const int ok = evx_intra_legal(x, y, px, py, g) ? 1 : 0;
                 if (lane == 0) { S.cand[buf][2 * k] = make_int4(shh, mh, 0, ok); S.cand[buf][2 * k + 1] = make_int4(sq, mq, 0, ok); }
             }
-            evx_compute_sync();
+            evx_compute_sync<CT>();
             // sub-pel acceptance in closed form (evx_select_subpel), lane t = test t
             {
                 const int4 v = lane < 16 ? S.cand[buf][lane] : make_int4(0, 0, 0, 0);
@@ -684,7 +691,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 EVX_K3_FOR384(e) sh.pred[e] = S.ipred[slot][best_ref][e];
             }
         }
-        evx_compute_sync();
+        evx_compute_sync<CT>();
         EVX_K3_PROF(3);
 
         // Writing this macroblock needs no further wait.  The row above reads the stale samples under it only
@@ -744,7 +751,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 t = (e & 7) == 0 ? evx_tdiv_pow2(t * 45, 7) : evx_tdiv_pow2(t, 1);
                 sh.bufb[(e & ~63) + (e & 7) * 8 + ((e >> 3) & 7)] = (int16_t) evx_rdiv_pow2(t, 7);      // [block][i][row]
             }
-            evx_compute_sync();
+            evx_compute_sync<CT>();
             // column pass: thread e -> (block b, column a, output row i = e & 7); column a is contiguous in bufb
             uint32_t vsum = 0, vsq = 0; int vcnt = 0;
             EVX_K3_FOR384(e)
@@ -770,23 +777,23 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 const int cnt = __reduce_add_sync(0xFFFFFFFFu, vcnt);
                 if (lane == 0) { sh.red[warp] = (int) sum; sh.red[32 + warp] = (int) sq; sh.red[64 + warp] = cnt; }
             }
-            evx_compute_sync();
+            evx_compute_sync<CT>();
 #else
-            evx_compute_sync();
+            evx_compute_sync<CT>();
             // compute_block_variance2 over the 16x16 luma coefficients except (0,0) (analysis.h:176-198)
             {
                 uint32_t sum = 0, sq = 0; int cnt = 0;
-                for (int e = tid; e < 256; e += EVX_K3_CT) { int t = e ? sh.bufa[e] : 0; if (t) { sum += (uint32_t) t; sq += (uint32_t) (t * t); cnt++; } }
+                for (int e = tid; e < 256; e += CT) { int t = e ? sh.bufa[e] : 0; if (t) { sum += (uint32_t) t; sq += (uint32_t) (t * t); cnt++; } }
                 sum = __reduce_add_sync(0xFFFFFFFFu, sum); sq = __reduce_add_sync(0xFFFFFFFFu, sq); cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
                 if (lane == 0) { sh.red[warp] = (int) sum; sh.red[32 + warp] = (int) sq; sh.red[64 + warp] = cnt; }
-                evx_compute_sync();
+                evx_compute_sync<CT>();
             }
 #endif
             int qp, var = 0;
             {
                 uint32_t Ssum = 0, Q = 0; int C = 0;
 #pragma unroll
-                for (int w8 = 0; w8 < EVX_K3_CW; ++w8) { Ssum += (uint32_t) sh.red[w8]; Q += (uint32_t) sh.red[32 + w8]; C += sh.red[64 + w8]; }
+                for (int w8 = 0; w8 < CW; ++w8) { Ssum += (uint32_t) sh.red[w8]; Q += (uint32_t) sh.red[32 + w8]; C += sh.red[64 + w8]; }
                 if (C > 0) var = (int) (Q - (uint32_t) evx_rdiv((int) (Ssum * Ssum), C));
                 // query_block_quantization_parameter, quantize.cpp:60-77
                 const int q = p.quality & 0xFF;
@@ -806,7 +813,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 sh.bufb[(e & ~63) + (e & 7) * 8 + ((e >> 3) & 7)] = (int16_t) evx_dequant(qv, e & 63, mode, qp, p.linear, sh.qmi, sh.qmt);   // [block][column][row]
             }
             if (tid == 0) { d.set_q(qp, var); p.table[mb] = d; p.prev_motion[mb] = S.last_motion; p.prev_coded[mb] = S.last_coded; S.last_coded = mb; }
-            evx_compute_sync();
+            evx_compute_sync<CT>();
             // inverse transform (transform.cpp:330-366, 418-433): columns, then rows + prediction
             EVX_K3_FOR384(e)
             {
@@ -818,7 +825,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
                 for (int k = 1; k < 8; ++k) t += evx_tdiv_pow2(x[k] * lut_i[k], 1);
                 sh.bufa[b * 64 + (e & 7) * 8 + j] = (int16_t) evx_rdiv_pow2(t, 7);
             }
-            evx_compute_sync();
+            evx_compute_sync<CT>();
             EVX_K3_FOR384(e)
             {
                 int x[8];                                    // row (e>>3), output column i = e & 7
@@ -836,7 +843,7 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
         prof[5] += have2 ? 1 : 0;       // macroblocks that waited for column n+2 of the row above
 #endif
         if (tid == 0 && (type & EVX_T_MOTION)) S.last_motion = mb;
-        evx_compute_sync();
+        evx_compute_sync<CT>();
         EVX_K3_PROF(4);
         EVX_K3_STAMP(2);
         if (tid == 0)
@@ -861,12 +868,12 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
 // sharing the device need; <1> lets ptxas have the 168 registers it asks for, 2.5 % faster per frame alone
 // (1.735 -> 1.691 ms at 1080p), used for a frame that has the device to itself (the stand-alone launch sequence).
 template <int MINCTAS>
-__global__ void __launch_bounds__(EVX_K3_NT, MINCTAS) evx_wavefront(const __grid_constant__ EvxK3Params p)
+__global__ void __launch_bounds__(EvxK3Cfg<MINCTAS>::NT, MINCTAS) evx_wavefront(const __grid_constant__ EvxK3Params p)
 {
     extern __shared__ __align__(128) uint8_t evx_k3_smem[];
     EvxFrameCtl &C = *reinterpret_cast<EvxFrameCtl *>(evx_k3_smem);
     EvxK3Smem &S = *reinterpret_cast<EvxK3Smem *>(evx_k3_smem + EVX_FRAME_CTL_BYTES);
-    EvxK2RoleSmem &K = *reinterpret_cast<EvxK2RoleSmem *>(evx_k3_smem + EVX_FRAME_CTL_BYTES);
+    constexpr int CW = EvxK3Cfg<MINCTAS>::CW;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int H = p.g.mbh;
 
@@ -891,14 +898,14 @@ __global__ void __launch_bounds__(EVX_K3_NT, MINCTAS) evx_wavefront(const __grid
             evx_mbar_init(&S.full2[0], 1); evx_mbar_init(&S.full2[1], 1); evx_mbar_init(&S.empty[0], 1); evx_mbar_init(&S.empty[1], 1);
             evx_mbar_init(&S.k2bar, 1);
         }
-        evx_init_tables(S.sh, tid, EVX_K3_NT);
+        evx_init_tables(S.sh, tid, EvxK3Cfg<MINCTAS>::NT);
         __syncthreads();
 #ifdef EVX_K3_TIMELINE
         if (p.prof && tid == 0) p.prof[(size_t) H * 10 + (size_t) by * 4 + 1] = (long long) evx_globaltimer();      // left the queues, row starts
 #endif
-        if (warp < EVX_K3_CW) evx_k3_compute<MINCTAS == 1>(S, p, by, tid);
-        else if (warp == EVX_K3_CW) evx_k3_block_loader(S, p, by, lane);
-        else if (warp == EVX_K3_CW + 1) evx_k3_column_loader(S, p, by, lane);
+        if (warp < CW) evx_k3_compute<MINCTAS == 1, CW>(S, p, by, tid);
+        else if (warp == CW) evx_k3_block_loader(S, p, by, lane);
+        else if (warp == CW + 1) evx_k3_column_loader(S, p, by, lane);
         __syncthreads();      // every warp has left the row: its barriers and shared memory may be reused
 #ifdef EVX_K3_TIMELINE
         if (p.prof && tid == 0) p.prof[(size_t) H * 10 + (size_t) by * 4 + 2] = (long long) evx_globaltimer();      // row complete

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "../../include/evxgpu.h"
@@ -47,7 +48,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
 typedef CUresult (*stream_memop_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 static stream_memop_fn g_wait32 = NULL;
 #include <atomic>
-enum { EVX_MAX_SLOTS = 16, EVX_DEFAULT_SLOTS = 8 };           // frame slots a handle may own (evxgpu_config::frame_slots, EVXGPU_FRAME_SLOTS)
+enum { EVX_MAX_SLOTS = 16, EVX_DEFAULT_SLOTS = 10 };           // frame slots a handle may own (evxgpu_config::frame_slots, EVXGPU_FRAME_SLOTS)
 // Encoders (handles that have encoded a frame) alive per device, process-wide.  Only a tuning hint: a stand-alone
 // wavefront launch takes the larger register budget while the handle is the device's only encoder.  Nothing about
 // correctness or progress depends on it (frames of any number of streams and processes may share the device).
@@ -95,6 +96,7 @@ struct evxgpu_handle
     int slot;                       // frame slot of the launches being queued / last queued
     uint64_t launches;
     bool pending_encode, pending_decode;
+    bool broken;                    // a pipelined submit failed half-way: only evxgpu_reset / evxgpu_destroy are accepted
     int wave_grid;
     int enc_grid;                   // persistent CTAs of the encoder's wavefront kernel
     int search_ctas, deblock_ctas;  // persistent CTAs of the search follower (8 warps each) and of the deblocking follower (one warp each)
@@ -370,6 +372,7 @@ int evxgpu_reset(evxgpu_handle *h)
 {
     if (!h) return 1;
     CK(cudaSetDevice(h->device));
+    h->broken = false;
     if (h->overlap)
     {
         int rc = sync_all(h);
@@ -556,9 +559,9 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
     // one CTA per macroblock row in flight; rows are claimed by ticket, so any residency is deadlock-free
     // the only encoder on the device runs the kernel with the larger register budget (evx_wavefront.cuh)
     if (h->device >= 0 && h->device < 64 && g_encoders_live[h->device].load() <= 1 && !h->k3_regs_forced)
-        evx_wavefront<1><<<h->enc_grid, EVX_K3_NT, EVX_FRAME_SMEM, h->stream>>>(p);
+        evx_wavefront<1><<<h->enc_grid, EvxK3Cfg<1>::NT, EVX_FRAME_SMEM, h->stream>>>(p);
     else
-        evx_wavefront<EVX_K3_MINCTAS><<<h->enc_grid, EVX_K3_NT, EVX_FRAME_SMEM, h->stream>>>(p);
+        evx_wavefront<EVX_K3_MINCTAS><<<h->enc_grid, EvxK3Cfg<EVX_K3_MINCTAS>::NT, EVX_FRAME_SMEM, h->stream>>>(p);
     h->launches++;
     if (h->out_mode != 1)
     {
@@ -794,8 +797,8 @@ static int submit_pipelined(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_dev
         }
         // the wavefront rows
         const int grid = std::min(h->g.mbh, h->pipe_rows);
-        if (h->k3_regs == 1) evx_wavefront<1><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
-        else evx_wavefront<EVX_K3_MINCTAS><<<grid, EVX_K3_NT, EVX_FRAME_SMEM, f.main>>>(kp);
+        if (h->k3_regs == 1) evx_wavefront<1><<<grid, EvxK3Cfg<1>::NT, EVX_FRAME_SMEM, f.main>>>(kp);
+        else evx_wavefront<EVX_K3_MINCTAS><<<grid, EvxK3Cfg<EVX_K3_MINCTAS>::NT, EVX_FRAME_SMEM, f.main>>>(kp);
         h->launches++;
         // the deblocking follower: tile rows by ticket, one warp each
         CK(cudaStreamWaitEvent(f.k4s, f.ev_go, 0));
@@ -907,7 +910,21 @@ int evxgpu_encode_submit(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device
     if (h->h_diag && h->h_diag[0])
         return fail(5, "evxgpu_encode_submit: a device-side wait of an earlier frame ran out of time (the context is lost)");
     if (!h->is_encoder && h->device >= 0 && h->device < 64) { g_encoders_live[h->device].fetch_add(1); h->is_encoder = true; }
-    if (h->overlap && h->out_mode == 1) return submit_pipelined(h, rgb, rgb_is_device, frame_type, frame_index, quality);
+    if (h->overlap && h->out_mode == 1)
+    {
+        if (h->broken) return fail(5, "evxgpu_encode_submit: an earlier submit failed half-way; evxgpu_reset the handle");
+        const int rc = submit_pipelined(h, rgb, rgb_is_device, frame_type, frame_index, quality);
+        if (rc)
+        {   // part of the frame may be queued (its kernels wait on counters nobody will advance: their waits are bounded) and
+            // the slot bookkeeping was not updated: drain what is there and refuse further frames until the stream is reset
+            const std::string why = g_err;
+            for (int q = 0; q < h->nslots; ++q) { cudaStreamSynchronize(h->fs[q].main); cudaStreamSynchronize(h->fs[q].k2s); cudaStreamSynchronize(h->fs[q].k4s); }
+            cudaGetLastError();
+            h->broken = true;
+            return fail(rc, why.c_str());
+        }
+        return 0;
+    }
     const int q = (h->q_head + h->q_count) % h->nslots;
     h->slot = q;
     if (h->timing) t_fold(h, q);                 // the frame that used this slot before was collected long ago

@@ -52,7 +52,7 @@ const zigzag_tables ZZ;
 // every coder of the process and grown on demand, replaces the hardware divide on the bin path.
 class reciprocal_table
 {
-    static const size_t kMax = size_t(1) << 24;
+    static const size_t kMax = size_t(1) << 23;      // (the fast loop takes tot < 2^23 only; address space, touched on demand)
     uint64_t *m_;
     std::atomic<size_t> size_;
     std::mutex lock_;
@@ -169,7 +169,11 @@ inline void put_block(bin_string &w, const int16_t *blk, const uint8_t *zz, int1
 // bit-at-a-time path.  Returns the number of bits written to out.
 // (built twice: a portable clone and one for BMI2/LZCNT machines, whose three-operand shifts
 // and leading-zero count shave a fifth off the instruction count; picked at load time)
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
 __attribute__((noinline, target_clones("default", "arch=haswell")))
+#else
+__attribute__((noinline))
+#endif
 uint64_t abac_encode_bins(const uint64_t *bins, size_t nbins, std::vector<uint8_t> &outv)
 {
     uint64_t low = 0, high = AB_MAX, h0 = 1, tot = 2;

@@ -51,7 +51,7 @@ typedef struct evxgpu_config
     int32_t ref_count;        /* EVX_REFERENCE_FRAME_COUNT: ring slots incl. the current frame, 2..8 */
     int32_t linear_quant;     /* EVX_ENABLE_LINEAR_QUANTIZATION */
     int32_t deblocking;       /* EVX_ENABLE_DEBLOCKING */
-    int32_t frame_slots;      /* encoder, bin-string output: frames of the stream in flight on the device at once (0 = default 6, at most 16);
+    int32_t frame_slots;      /* encoder, bin-string output: frames of the stream in flight on the device at once (0 = default 10, at most 16);
                                * 1 = no frame pipeline: frame after frame with the stand-alone kernels (a second frame may still be queued
                                * behind the first) -- the better choice when many streams share one device */
 } evxgpu_config;
