@@ -755,8 +755,15 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
                    "parity": "tests/test_gpu_fullsize.py::test_1080p_pipelined_stream_equals_reference[%s]" % name}
             if rank == 0:
                 rf = search_roofline(ks, cn, int_peak)
+                tr = None
+                tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+                if os.path.exists(tp):
+                    with open(tp) as f:
+                        tj = json.load(f).get("evx_inter_search (ring of 4)", {})
+                    tr = (tj.get("dram_bytes_read") or 0) + (tj.get("dram_bytes_write") or 0) or None
                 blk["roofline"] = {"bound": "int_alu", "kernel": "evx_inter_search, 3 references", "achieved": rf["inter_search"]["achieved"], "peak": int_peak,
-                                   "unit": "Tiop/s", "frac": rf["inter_search"]["frac"], "dominant": {"kernel": "evx_wavefront", "ms_per_launch": ks["wavefront"],
+                                   "unit": "Tiop/s", "frac": rf["inter_search"]["frac"], "traffic": tr,
+                                   "traffic_note": "DRAM bytes per launch, ncu --set full (profiles/r02_traffic.json); algorithmic: 4 plane sets x 6.27 MB", "dominant": {"kernel": "evx_wavefront", "ms_per_launch": ks["wavefront"],
                                                                                                        "achieved": rf["wavefront"]["achieved"], "frac": rf["wavefront"]["frac"]}}
             if not linear:
                 e = api.evx1_encoder(device=device, ref_count=4)
