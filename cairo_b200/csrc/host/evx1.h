@@ -138,14 +138,15 @@ public:
     // additions: encode() == submit() + collect().  submit queues the frame on the device (colour
     // conversion, motion search, transform/quantisation, reconstruction, deblocking, binarisation) and
     // returns; collect appends what encode() would have appended for the oldest uncollected frame (stream
-    // header on the first frame, frame descriptor, slice).  Several frames may be uncollected: up to three on the
-    // device, where consecutive frames overlap row by row (two next to other encoders), and up to six retired ones whose
-    // slices are being entropy-coded on the session's four coder threads (a slice's coder needs nothing from other
-    // frames).  With submit(n+k) before collect(n), k = 1..6, the host entropy stage, the device's work and the host->device copies of different frames
-    // all run at the same time; collect() returns the frames in order, the same bytes encode() appends.  `image` must
-    // stay unchanged until the frame's own collect() returns.  submit returns EVX_ERROR_NOT_READY when the device
-    // holds all the frames it takes and six retired ones wait to be collected; encode() when any frame is uncollected; collect()
-    // when none is.
+    // header on the first frame, frame descriptor, slice).  Several frames may be uncollected: as many as the device
+    // library has frame slots (evx1_config::frame_slots, ten by default), which follow each other macroblock by macroblock
+    // on the device, and up to twelve retired ones whose slices are being entropy-coded on the session's coder threads
+    // (evx1_config::coder_threads, six by default; a slice's coder needs nothing from other frames).  With submit(n+k) before
+    // collect(n) the host entropy stage, the device's work and the host->device copies of different frames all run at the
+    // same time; k should exceed the frame slots by a few frames, or every collect() waits for a coder that has only just
+    // started.  collect() returns the frames in order, the same bytes encode() appends.  `image` must stay unchanged until
+    // the frame's own collect() returns.  submit returns EVX_ERROR_NOT_READY when the device holds all the frames it takes
+    // and twelve retired ones wait to be collected; encode() when any frame is uncollected; collect() when none is.
     virtual evx_status submit(void *image, uint32 width, uint32 height) = 0;
     virtual evx_status collect(bit_stream *output) = 0;
 };
