@@ -701,7 +701,7 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             if pipelined:
-                ahead = min(7, len(coded))
+                ahead = min(11, len(coded))
                 for d, b in coded[:ahead]:
                     dec.submit(d, b)
                 for d, b in coded[ahead:]:
@@ -716,7 +716,7 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
 
         dec_sync, dec_pipe = decode_run(False), decode_run(True)
         out["decode"] = {"value": agg(dec_pipe), "unit": "frames/s",
-                         "api": "evx1_decoder::submit/collect (eight frames in flight, six parser threads), bitstream -> RGB8 in pinned host memory",
+                         "api": "evx1_decoder::submit/collect (twelve frames in flight, eight parser threads, the next frame handed to the device under the copy-out of the current one), bitstream -> RGB8 in pinned host memory",
                          "synchronous": agg(dec_sync), "frames": len(coded)}
         # K5 / K6 alone, for their HBM fractions
         if rank == 0:

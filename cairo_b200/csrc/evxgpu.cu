@@ -96,6 +96,9 @@ struct evxgpu_handle
     int slot;                       // frame slot of the launches being queued / last queued
     uint64_t launches;
     bool pending_encode, pending_decode;
+    // decoder: two frames may be on the device (the second one submitted once the first one's copy-out has begun)
+    struct dec_set { EvxDesc *h_table; int16_t *h_records; int *h_record_slot; uint8_t *d_rgb; cudaEvent_t ev_h2d, ev_done, ev_out; bool h2d_rec, out_rec; } dec[2];
+    uint32_t dec_seq; int dec_pending; bool dec_out_begun;
     bool broken;                    // a pipelined submit failed half-way: only evxgpu_reset / evxgpu_destroy are accepted
     int wave_grid;
     int enc_grid;                   // persistent CTAs of the encoder's wavefront kernel
@@ -213,6 +216,8 @@ int evxgpu_destroy(evxgpu_handle *h)
     cudaFree(h->src_mem);
     for (int i = 0; i < 8; ++i) cudaFree(h->ring_mem[i]);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->dec[1].h_table) { cudaFreeHost(h->dec[1].h_table); cudaFreeHost(h->dec[1].h_records); cudaFreeHost(h->dec[1].h_record_slot); cudaFree(h->dec[1].d_rgb); }
+    for (int k = 0; k < 2; ++k) { if (h->dec[k].ev_h2d) cudaEventDestroy(h->dec[k].ev_h2d); if (h->dec[k].ev_done) cudaEventDestroy(h->dec[k].ev_done); if (h->dec[k].ev_out) cudaEventDestroy(h->dec[k].ev_out); }
     cudaFree(h->d_rgb_up);
     if (h->ev_up) cudaEventDestroy(h->ev_up);
     if (h->ev_k1) cudaEventDestroy(h->ev_k1);
@@ -397,6 +402,7 @@ int evxgpu_reset(evxgpu_handle *h)
     CK(cudaMemsetAsync(h->d_dc, 0, (size_t) h->nmb * 4 * 2, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->pending_encode = h->pending_decode = false;
+    h->dec_pending = 0; h->dec_out_begun = false; h->dec[0].h2d_rec = h->dec[1].h2d_rec = h->dec[0].out_rec = h->dec[1].out_rec = false;
     for (int q = 0; q < EVX_MAX_SLOTS; ++q) h->pending_bins[q] = false;
     h->q_head = h->q_count = 0; h->uploaded = false;
     return 0;
@@ -1052,30 +1058,59 @@ int evxgpu_encode_collect(evxgpu_handle *h, evxgpu_block_desc *table_out, int16_
 
 // ------------------------------------------------------------------ decoder
 
+// The decoder's second staging set (pinned table / records / slots, RGB output buffer) and the events of both sets
+static int dec_prepare(evxgpu_handle *h)
+{
+    if (h->dec[0].ev_h2d) return 0;
+    h->dec[0].h_table = h->h_table; h->dec[0].h_records = h->h_records; h->dec[0].h_record_slot = h->h_record_slot; h->dec[0].d_rgb = h->d_rgb;
+    bool ok = true;
+    ok = ok && cudaHostAlloc(&h->dec[1].h_table, (size_t) h->nmb * 16, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&h->dec[1].h_records, (size_t) h->nmb * 384 * 2, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(&h->dec[1].h_record_slot, (size_t) h->nmb * 4, cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->dec[1].d_rgb, (size_t) h->g.vw * h->g.vh * 3) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; ++k)
+    {
+        ok = ok && cudaEventCreateWithFlags(&h->dec[k].ev_h2d, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->dec[k].ev_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->dec[k].ev_out, cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) return fail(3, "decoder staging: out of memory");
+    return 0;
+}
+
 int evxgpu_decode_submit(evxgpu_handle *h, const evxgpu_block_desc *table, const int16_t *records, uint32_t n_noncopy,
                          int frame_type, uint32_t frame_index)
 {
     (void) frame_type;
     if (!h || !table || (n_noncopy && !records) || n_noncopy > (uint32_t) h->nmb) return fail(1, "evxgpu_decode_submit: bad argument");
+    // a second frame is taken once the copy-out of the first one has been queued (evxgpu_decode_collect_begin): its
+    // staging copies and kernels then run under that copy
+    if (h->dec_pending >= 2 || (h->dec_pending == 1 && !h->dec_out_begun)) return fail(8, "evxgpu_decode_submit: previous frame not collected");
     CK(cudaSetDevice(h->device));
-    CK(cudaStreamSynchronize(h->stream));           // staging buffers are reused
-    memcpy(h->h_table, table, (size_t) h->nmb * 16);
+    int rc;
+    if ((rc = dec_prepare(h))) return rc;
+    evxgpu_handle::dec_set &d = h->dec[h->dec_seq & 1u];
+    if (d.h2d_rec) CK(cudaEventSynchronize(d.ev_h2d));          // the set's staging buffers have been read (two frames ago)
+    memcpy(d.h_table, table, (size_t) h->nmb * 16);
     uint32_t k = 0;
     for (int mb = 0; mb < h->nmb; ++mb)
     {
         bool copy = (table[mb].block_type & 4) != 0;
-        h->h_record_slot[mb] = copy ? -1 : (int) k++;
+        d.h_record_slot[mb] = copy ? -1 : (int) k++;
     }
     if (k != n_noncopy) return fail(1, "evxgpu_decode_submit: n_noncopy does not match the table");
-    if (k) memcpy(h->h_records, records, (size_t) k * 768);
-    CK(cudaMemcpyAsync(h->d_table, h->h_table, (size_t) h->nmb * 16, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_record_slot, h->h_record_slot, (size_t) h->nmb * 4, cudaMemcpyHostToDevice, h->stream));
-    if (k) CK(cudaMemcpyAsync(h->d_dense, h->h_records, (size_t) k * 768, cudaMemcpyHostToDevice, h->stream));
+    if (k) memcpy(d.h_records, records, (size_t) k * 768);
+    CK(cudaMemcpyAsync(h->d_table, d.h_table, (size_t) h->nmb * 16, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_record_slot, d.h_record_slot, (size_t) h->nmb * 4, cudaMemcpyHostToDevice, h->stream));
+    if (k) CK(cudaMemcpyAsync(h->d_dense, d.h_records, (size_t) k * 768, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(d.ev_h2d, h->stream));
+    d.h2d_rec = true;
     EvxK5Params p;
     for (int i = 0; i < 8; ++i) p.ring[i] = h->ring[i];
     p.g = h->g; p.R = h->cfg.ref_count; p.linear = h->cfg.linear_quant; p.frame_index = frame_index;
     p.table = h->d_table; p.records = h->d_dense; p.record_slot = h->d_record_slot; p.sync = h->d_sync;
     p.done = h->d_done; p.readers = h->d_done + h->nmb;
+    p.wait.budget_ns = h->wait_budget_ns; p.wait.diag = h->d_diag;      // (was left uninitialised before round 2)
     CK(cudaMemsetAsync(h->d_sync, 0, ((size_t) h->g.mbh * 3 + 4) * 4, h->stream));
     CK(cudaMemsetAsync(h->d_done, 0, (size_t) h->nmb * 8, h->stream));
     t_begin(h, EVXGPU_T_DECODE_RECON);
@@ -1084,27 +1119,56 @@ int evxgpu_decode_submit(evxgpu_handle *h, const evxgpu_block_desc *table, const
     t_end(h, EVXGPU_T_DECODE_RECON);
     h->launches += 2;
     CK(cudaGetLastError());
-    int rc;
     if ((rc = launch_deblock(h, frame_index))) return rc;
+    if (d.out_rec) CK(cudaStreamWaitEvent(h->stream, d.ev_out, 0));      // the picture two frames back has left this set's RGB buffer
     dim3 block(256), grid(((h->g.vw + 7) / 8 + 255) / 256, h->g.vh / 2);
     t_begin(h, EVXGPU_T_CONVERT_OUT);
-    evx_yuv420_to_rgb<<<grid, block, 0, h->stream>>>(h->ring[frame_index % (uint32_t) h->cfg.ref_count], h->d_rgb, h->g);
+    evx_yuv420_to_rgb<<<grid, block, 0, h->stream>>>(h->ring[frame_index % (uint32_t) h->cfg.ref_count], d.d_rgb, h->g);
     t_end(h, EVXGPU_T_CONVERT_OUT);
     h->launches++;
     CK(cudaGetLastError());
+    CK(cudaEventRecord(d.ev_done, h->stream));
+    h->dec_seq++; h->dec_pending++;
     h->pending_decode = true;
+    return 0;
+}
+
+// The copy-out of the oldest submitted frame's picture, on the copy stream (so the next frame's kernels run under it)
+int evxgpu_decode_collect_begin(evxgpu_handle *h, uint8_t *rgb_out, int rgb_is_device)
+{
+    if (!h || !rgb_out) return fail(1, "evxgpu_decode_collect_begin: bad argument");
+    if (!h->dec_pending) return fail(15, "evxgpu_decode_collect_begin: nothing submitted");
+    if (h->dec_out_begun) return fail(8, "evxgpu_decode_collect_begin: the copy-out has begun already");
+    CK(cudaSetDevice(h->device));
+    evxgpu_handle::dec_set &d = h->dec[(h->dec_seq - (uint32_t) h->dec_pending) & 1u];
+    CK(cudaStreamWaitEvent(h->copy_stream, d.ev_done, 0));
+    CK(cudaMemcpyAsync(rgb_out, d.d_rgb, (size_t) h->g.vw * h->g.vh * 3, rgb_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->copy_stream));
+    CK(cudaEventRecord(d.ev_out, h->copy_stream));
+    d.out_rec = true;
+    h->dec_out_begun = true;
+    return 0;
+}
+
+int evxgpu_decode_collect_end(evxgpu_handle *h)
+{
+    if (!h) return fail(1, "evxgpu_decode_collect_end: bad argument");
+    if (!h->dec_pending || !h->dec_out_begun) return fail(15, "evxgpu_decode_collect_end: no copy-out in flight");
+    CK(cudaSetDevice(h->device));
+    evxgpu_handle::dec_set &d = h->dec[(h->dec_seq - (uint32_t) h->dec_pending) & 1u];
+    CK(cudaEventSynchronize(d.ev_out));
+    CK(cudaGetLastError());
+    h->dec_pending--; h->dec_out_begun = false;
+    h->pending_decode = h->dec_pending > 0;
     return 0;
 }
 
 int evxgpu_decode_collect(evxgpu_handle *h, uint8_t *rgb_out, int rgb_is_device)
 {
     if (!h || !rgb_out) return fail(1, "evxgpu_decode_collect: bad argument");
-    if (!h->pending_decode) return fail(15, "evxgpu_decode_collect: nothing submitted");
-    CK(cudaSetDevice(h->device));
-    CK(cudaMemcpyAsync(rgb_out, h->d_rgb, (size_t) h->g.vw * h->g.vh * 3, rgb_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    h->pending_decode = false;
-    return 0;
+    if (!h->dec_pending) return fail(15, "evxgpu_decode_collect: nothing submitted");
+    int rc = h->dec_out_begun ? 0 : evxgpu_decode_collect_begin(h, rgb_out, rgb_is_device);
+    if (rc) return rc;
+    return evxgpu_decode_collect_end(h);
 }
 
 // ------------------------------------------------------------------ single stages

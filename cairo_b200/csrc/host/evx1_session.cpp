@@ -458,7 +458,7 @@ class decoder_session : public evx1_decoder
     // A submitted frame is a job: its slice is entropy-decoded (slice_reader::parse, which needs nothing from other
     // frames) by a worker thread; collect() merges the oldest finished job into the stream's state (apply, in
     // frame order) and runs the pixel pipeline.  Up to kJobs frames may be uncollected.
-    enum { kJobs = 8, kWorkers = 6 };      // a slice takes ≈2.4 ms to parse and ≈0.6 ms to apply and reconstruct: six parsers keep the device side busy
+    enum { kJobs = 12, kWorkers = 8 };     // a slice takes ≈2.4 ms to parse and ≈0.5 ms to apply and hand to the device: eight parsers keep the collecting thread busy
     enum job_state { JOB_FREE = 0, JOB_QUEUED, JOB_RUNNING, JOB_DONE };
     struct job
     {
@@ -469,6 +469,9 @@ class decoder_session : public evx1_decoder
         parsed_slice ps;
         int rc;
         double ms;
+        bool on_device;                    // applied and submitted to the device (start()), its picture not yet collected
+        uint32 n_noncopy;
+        double apply_ms, t_start;
     };
     job jobs_[kJobs];
     int head_, count_;                     // uncollected jobs: head_, head_+1, ... (mod kJobs), in frame order
@@ -565,7 +568,7 @@ class decoder_session : public evx1_decoder
         const size_t nbytes = ((size_t) j.end + 7) >> 3;
         if (j.bytes.size() < nbytes) j.bytes.resize(nbytes + nbytes / 2 + 64);
         memcpy(j.bytes.data(), input->query_data(), nbytes);
-        j.desc = frame_; j.rc = 0; j.ms = 0.0;
+        j.desc = frame_; j.rc = 0; j.ms = 0.0; j.on_device = false; j.n_noncopy = 0; j.apply_ms = 0.0; j.t_start = 0.0;
         frame_.index++;
         input->empty();                                                                    // evx1dec.cpp:120
         *out = &j;
@@ -625,14 +628,21 @@ public:
     evx_status collect(void *output)
     {
         if (!output) return EVX_ERROR_INVALIDARG;
-        job *j;
+        job *j, *next = NULL;
         {
             std::unique_lock<std::mutex> lk(m_);
             if (!count_) return EVX_ERROR_NOT_READY;
             j = &jobs_[head_];
             while (j->state != JOB_DONE) cv_done_.wait(lk);
+            if (count_ >= 2 && jobs_[(head_ + 1) % kJobs].state == JOB_DONE) next = &jobs_[(head_ + 1) % kJobs];
         }
-        evx_status st = finish(*j, output);
+        // The oldest frame's picture leaves the device on the copy stream; under that copy the next parsed frame is merged
+        // into the stream's state and handed to the device (apply is in frame order: this frame's came first).
+        evx_status st = j->on_device ? EVX_SUCCESS : start(*j);
+        if (evx_succeeded(st) && evxgpu_decode_collect_begin(gpu_, static_cast<uint8 *>(output), cfg_.device_frames ? 1 : 0)) st = EVX_ERROR_EXECUTION_FAILURE;
+        if (evx_succeeded(st) && next && !next->on_device && evx_failed(start(*next))) next->rc = 1;      // reported by that frame's collect
+        if (evx_succeeded(st) && evxgpu_decode_collect_end(gpu_)) st = EVX_ERROR_EXECUTION_FAILURE;
+        if (evx_succeeded(st)) finish_stats(*j);
         {
             std::lock_guard<std::mutex> g(m_);
             j->state = JOB_FREE;
@@ -649,13 +659,18 @@ public:
         evx_status st = enqueue(input, &j);
         if (evx_failed(st)) return st;
         run_job(*j);                                          // one frame at a time: parsed right here
-        return finish(*j, output);
+        st = start(*j);
+        if (evx_failed(st)) return st;
+        if (evxgpu_decode_collect(gpu_, static_cast<uint8 *>(output), cfg_.device_frames ? 1 : 0)) return EVX_ERROR_EXECUTION_FAILURE;
+        finish_stats(*j);
+        return EVX_SUCCESS;
     }
 
     evx_status last_frame_stats(evx1_frame_stats *out) { if (!out) return EVX_ERROR_INVALIDARG; *out = stats_; return EVX_SUCCESS; }
 
 private:
-    evx_status finish(job &j, void *output)
+    // unserialize_slice's in-order half (apply) and the frame's kernels queued on the device
+    evx_status start(job &j)
     {
         if (j.rc) return EVX_ERROR_EXECUTION_FAILURE;
         uint32 n_noncopy = 0;
@@ -663,14 +678,16 @@ private:
         int16 *rec = j.ps.records.empty() ? records_.data() : j.ps.records.data();          // resolved in place: no copy of the coefficients
         if (reader_.apply(j.ps, table_.data(), rec, &n_noncopy)) return EVX_ERROR_EXECUTION_FAILURE;
         const double t1 = now_ms();
-        int rc = evxgpu_decode_submit(gpu_, table_.data(), rec, n_noncopy, (int) j.desc.type, j.desc.index);
-        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        rc = evxgpu_decode_collect(gpu_, static_cast<uint8 *>(output), cfg_.device_frames ? 1 : 0);
-        if (rc) return EVX_ERROR_EXECUTION_FAILURE;
-        stats_.entropy_ms = j.ms + (t1 - t0); stats_.gpu_ms = now_ms() - t1; stats_.noncopy_blocks = n_noncopy;
+        if (evxgpu_decode_submit(gpu_, table_.data(), rec, n_noncopy, (int) j.desc.type, j.desc.index)) return EVX_ERROR_EXECUTION_FAILURE;
+        j.on_device = true; j.n_noncopy = n_noncopy; j.apply_ms = t1 - t0; j.t_start = t1;
+        return EVX_SUCCESS;
+    }
+
+    void finish_stats(const job &j)
+    {
+        stats_.entropy_ms = j.ms + j.apply_ms; stats_.gpu_ms = now_ms() - j.t_start; stats_.noncopy_blocks = j.n_noncopy;
         stats_.slice_bits = j.end - j.pos; stats_.d2h_bytes = (uint32) ((size_t) header_.frame_width * header_.frame_height * 3);
         stats_.wait_ms = 0.0;
-        return EVX_SUCCESS;
     }
 };
 

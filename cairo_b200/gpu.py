@@ -55,6 +55,8 @@ def lib():
     L.evxgpu_debug_set_bins_capacity.argtypes = [vp, u32]
     L.evxgpu_decode_submit.argtypes = [vp, vp, vp, u32, i32, u32]
     L.evxgpu_decode_collect.argtypes = [vp, vp, i32]
+    L.evxgpu_decode_collect_begin.argtypes = [vp, vp, i32]
+    L.evxgpu_decode_collect_end.argtypes = [vp]
     L.evxgpu_stage_convert_in.argtypes = [vp, vp]
     L.evxgpu_stage_inter_search.argtypes = [vp, u32, i32]
     L.evxgpu_stage_get_inter_result.argtypes = [vp, i32, vp, vp]

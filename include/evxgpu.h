@@ -118,6 +118,12 @@ int evxgpu_encode_collect_bins(evxgpu_handle *h, const uint64_t **bins, uint64_t
 int evxgpu_decode_submit(evxgpu_handle *h, const evxgpu_block_desc *table, const int16_t *records, uint32_t n_noncopy,
                          int frame_type, uint32_t frame_index);
 int evxgpu_decode_collect(evxgpu_handle *h, uint8_t *rgb_out, int rgb_is_device);
+/* The two halves of evxgpu_decode_collect: begin queues the copy-out of the oldest submitted frame's picture (on a copy
+ * stream), end waits for it.  Between the two a SECOND frame may be submitted: its staging copies and kernels run under
+ * the first frame's copy-out (two staging sets and two RGB buffers per handle).  Status 8 when a second frame is
+ * submitted before the first one's copy-out has begun, or a third one at all. */
+int evxgpu_decode_collect_begin(evxgpu_handle *h, uint8_t *rgb_out, int rgb_is_device);
+int evxgpu_decode_collect_end(evxgpu_handle *h);
 
 /* ---- single stages, for parity tests and profiling ---- */
 int evxgpu_stage_convert_in(evxgpu_handle *h, const uint8_t *rgb_host);
