@@ -164,8 +164,9 @@ public:
     // additions: decode() == submit() + collect().  submit takes one frame out of input (and empties it, like
     // decode) and hands its slice to a parser thread; collect merges the oldest submitted frame into the stream's
     // state, runs the pixel pipeline and writes its picture.  The arithmetic decoding of a slice needs nothing from
-    // other frames, so with submit(n+1) ... submit(n+3) before collect(n) the slices of consecutive frames are decoded
-    // concurrently (six parser threads) while the caller's thread runs the device.  At most eight frames may be
+    // other frames, so with submit(n+1) ... submit(n+k) before collect(n) the slices of consecutive frames are decoded
+    // concurrently (eight parser threads) while the caller's thread runs the device; collect(n) also hands frame n+1 to the
+    // device, if it is parsed, before it waits for picture n.  At most twelve frames may be
     // uncollected (EVX_ERROR_NOT_READY otherwise, and for decode() with any frame uncollected, and for collect
     // with none).  decode() itself parses on the calling thread.
     virtual evx_status submit(bit_stream *input) = 0;
