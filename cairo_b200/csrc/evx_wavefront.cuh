@@ -180,7 +180,12 @@ __device__ __noinline__ void evx_deblock_job(const EvxK3Params &p, int Y, int x0
     __syncwarp();
 }
 
+#ifndef EVX_DBK_CHUNK
 #define EVX_DBK_CHUNK 4           // tile columns per deblocking job
+#endif
+#ifndef EVX_DBK_POLL_NS
+#define EVX_DBK_POLL_NS 4000      // longest back-off of the deblocking follower's poll
+#endif
 
 // per-row counters in p.sync: progress[y] (macroblocks of wavefront row y complete), k2c[y] (search items of row y
 // claimed), jc[Y] (deblocking jobs of tile row Y claimed)
@@ -272,6 +277,9 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
         if (lane == 0) evx_st_release(progress + by, m + 1);     // release is cumulative over what this thread observed through the barrier
     };
     uint32_t k2phase = 0;
+#ifdef EVX_K3_LOADER_STATS
+    long long ls_own = 0, ls_own_cyc = 0, ls_stamp_cyc = 0;
+#endif
     bool stamps_seen = false;       // the stamps of the macroblock about to be staged were already seen (looked at one macroblock early)
 
     for (int n = 0; n < g.mbw; ++n)
@@ -301,9 +309,20 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
             // nobody has yet), then one lane per reference waits for the stamps (a claimed item is in a running warp's hands)
             if (!stamps_seen)
             {
+#ifdef EVX_K3_LOADER_STATS
+                const long long t0 = clock64();
+                const int c0 = evx_ld_relaxed(evx_k2c(p) + by);
+#endif
                 evx_claim_own_items(p, by, n, lane, S.k2win, &S.k2bar, k2phase);
+#ifdef EVX_K3_LOADER_STATS
+                const long long t1 = clock64();
+                if (evx_ld_relaxed(evx_k2c(p) + by) != c0 && t1 - t0 > 2000) { ls_own++; ls_own_cyc += t1 - t0; }
+#endif
                 const uint32_t *st = &p.inter[(size_t) min(lane, nref - 1) * nmb + mb].stamp;
                 EVX_BOUNDED_WAIT(p.wait, __all_sync(0xFFFFFFFFu, evx_ld_relaxed_u32(st) == p.stamp), 100, 5u, (unsigned int) mb, p.stamp, 0u);
+#ifdef EVX_K3_LOADER_STATS
+                ls_stamp_cyc += clock64() - t1;
+#endif
             }
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
@@ -368,6 +387,9 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
             stamps_seen = __all_sync(0xFFFFFFFFu, evx_ld_relaxed_u32(&p.inter[(size_t) min(lane, nref - 1) * nmb + mb + 1].stamp) == p.stamp) != 0;
     }
     for (int m = max(0, g.mbw - 2); m < g.mbw; ++m) publish(m);
+#ifdef EVX_K3_LOADER_STATS
+    if (p.prof && lane == 0) { p.prof[by * 10 + 6] = ls_own; p.prof[by * 10 + 7] = ls_stamp_cyc; p.prof[by * 10 + 8] = ls_own_cyc; }
+#endif
 }
 
 // ---------------------------------------------------------------- column loader warp
@@ -858,7 +880,11 @@ __device__ __forceinline__ void evx_k3_compute(EvxK3Smem &S, const EvxK3Params &
     {
         p.row_records[by] = row_records;
         p.row_last[by] = S.last_motion; p.row_last[g.mbh + by] = S.last_coded;
+#ifdef EVX_K3_LOADER_STATS
+        if (p.prof) for (int k = 0; k < 10; ++k) if (k < 6 || k > 8) p.prof[by * 10 + k] = prof[k];      // (6..8: the block loader's)
+#else
         if (p.prof) for (int k = 0; k < 10; ++k) p.prof[by * 10 + k] = prof[k];
+#endif
         atomicAdd(&p.counters[2], (unsigned long long) n_full);
         atomicAdd(&p.counters[3], (unsigned long long) n_sub);
     }
@@ -987,7 +1013,7 @@ __global__ void __launch_bounds__(32, 16) evx_deblock_follow(const __grid_consta
             if (lane == 0)
             {
                 int have;
-                EVX_BOUNDED_WAIT(p.wait, (have = evx_ld_relaxed(prow)) >= need, (need - have > 8 ? 4000 : 500 * (need - have)), 9u, (unsigned int) Y, (unsigned int) need, (unsigned int) have);
+                EVX_BOUNDED_WAIT(p.wait, (have = evx_ld_relaxed(prow)) >= need, min(EVX_DBK_POLL_NS, 500 * (need - have)), 9u, (unsigned int) Y, (unsigned int) need, (unsigned int) have);
             }
             __syncwarp();
             int ok = 0;

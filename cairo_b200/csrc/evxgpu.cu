@@ -101,7 +101,8 @@ struct evxgpu_handle
     uint32_t dec_seq; int dec_pending; bool dec_out_begun;
     bool broken;                    // a pipelined submit failed half-way: only evxgpu_reset / evxgpu_destroy are accepted
     int wave_grid;
-    int enc_grid;                   // persistent CTAs of the encoder's wavefront kernel
+    int enc_grid;                   // persistent CTAs of the encoder's wavefront kernel (the device's only encoder)
+    int shared_grid;                // the same next to other encoders
     int search_ctas, deblock_ctas;  // persistent CTAs of the search follower (8 warps each) and of the deblocking follower (one warp each)
     int pipe_rows;                  // frame kernel: row CTAs per frame in the pipeline
     int launch_row;                 // a frame's kernel is launched once the previous frame has begun to deblock this tile row (0: once it runs)
@@ -354,6 +355,11 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     // encoder wavefront: at most ceil(W/3) rows are ever active at once (row r runs during steps [3r, 3r+W));
     // a few spare CTAs absorb the row-to-row hand-over
     h->enc_grid = std::min(h->g.mbh, (h->g.mbw + 2) / 3 + 4);
+    // ... and the same kernel next to other streams' kernels (evx_wavefront<2>, frame after frame within each stream): fewer
+    // row CTAs per frame are the faster choice there too -- 16 streams of 1080p with 44 / 36 / 32 / 28 / 24 / 20 / 16 CTAs per
+    // frame: 3 234 / 3 575 / 3 829 / 3 970 / 4 064 / 3 976 / 3 785 frames/s (a frame alone: 1.72 ms with 44 or 32, 1.90 with 24)
+    h->shared_grid = std::min(h->g.mbh, std::max(4, (h->g.mbw + 2) / 5));
+    if (const char *e = getenv("EVXGPU_ENC_GRID")) { int v = atoi(e); if (v > 0) h->enc_grid = h->shared_grid = std::min(h->g.mbh, v); }      // measurements
     // The frame pipeline (several frames of the stream on the device at once): what limits it is the SMs' instruction supply,
     // and fewer resident CTAs per frame are the faster choice -- measured at 1080p with eight slots: 44 / 36 / 32 / 28 row CTAs
     // per frame 2 188 / 2 339 / 2 464 / 2 396 frames/s; 48 / 24 / 16 deblocking warps 2 188 / 2 277 / 2 160; 16 / 24 / 34
@@ -567,7 +573,7 @@ static int launch_wavefront(evxgpu_handle *h, int frame_type, uint32_t index, in
     if (h->device >= 0 && h->device < 64 && g_encoders_live[h->device].load() <= 1 && !h->k3_regs_forced)
         evx_wavefront<1><<<h->enc_grid, EvxK3Cfg<1>::NT, EVX_FRAME_SMEM, h->stream>>>(p);
     else
-        evx_wavefront<EVX_K3_MINCTAS><<<h->enc_grid, EvxK3Cfg<EVX_K3_MINCTAS>::NT, EVX_FRAME_SMEM, h->stream>>>(p);
+        evx_wavefront<EVX_K3_MINCTAS><<<h->k3_regs_forced ? h->enc_grid : h->shared_grid, EvxK3Cfg<EVX_K3_MINCTAS>::NT, EVX_FRAME_SMEM, h->stream>>>(p);
     h->launches++;
     if (h->out_mode != 1)
     {
@@ -1250,7 +1256,7 @@ int evxgpu_set_encode_grid(evxgpu_handle *h, int ctas)
 {
     if (!h) return 1;
     if (ctas <= 0) ctas = (h->g.mbw + 2) / 3 + 4;
-    h->enc_grid = std::max(1, std::min(h->g.mbh, ctas));
+    h->enc_grid = h->shared_grid = std::max(1, std::min(h->g.mbh, ctas));
     return 0;
 }
 

@@ -53,4 +53,6 @@ for k in order:
     prev = tl[33, 1]
     print(line)
     print("     cycles/MB rows 10..60:", {n: int(v) for n, v in zip(names, mid) if not n.startswith('hold') and n != 'far_waits'}, "row time us (median):", round(float(np.median(tl[10:60, 2] - tl[10:60, 1])), 1),
-          "claim->start us:", round(float(np.median(tl[10:60, 1] - tl[10:60, 0])), 1))
+          "claim->start us:", round(float(np.median(tl[10:60, 1] - tl[10:60, 0])), 1),
+          "| loader (build with -DEVX_K3_LOADER_STATS): own searches per row", round(float(prof[10:60, 6].mean()), 1), "cycles/MB in them", int(prof[10:60, 8].mean() / mbw),
+          "cycles/MB waiting for stamps", int(prof[10:60, 7].mean() / mbw))

@@ -124,3 +124,44 @@ def test_device_resident_frames_through_the_public_api():
         dec.decode(want[t][0], want[t][1], w, h, out=int(out.data_ptr()))
         torch.cuda.synchronize()
         assert (out.cpu().numpy() == pics[t]).all(), t
+
+
+def test_decode_two_frames_on_the_device():
+    """include/evxgpu.h, evxgpu_decode_collect_begin / _end: once the copy-out of frame n has begun, frame n+1 may be
+    submitted (its staging copies and kernels run under that copy).  Same pictures as one frame at a time; a second
+    submit before the copy-out has begun, and a third frame, are refused with status 8."""
+    import ctypes as C
+    from cairo_b200 import gpu
+    w, h, q, n = 352, 288, 16, 7
+    frames = [synth.frame(w, h, t, 3, "moving") for t in range(n)]
+    enc = gpu.Pipeline(w, h, 2, 0, 1)
+    coded = []
+    for t in range(n):
+        tbl, rec = enc.encode(frames[t], 0 if t == 0 else 1, t, q)
+        coded.append((tbl.copy(), rec.copy()))
+    one = gpu.Pipeline(w, h, 2, 0, 1)
+    want = [one.decode(tbl, rec, 0 if t == 0 else 1, t).copy() for t, (tbl, rec) in enumerate(coded)]
+
+    L = gpu.lib()
+    two = gpu.Pipeline(w, h, 2, 0, 1)
+    outs = [np.zeros((h, w, 3), dtype=np.uint8) for _ in range(n)]
+
+    def submit(t):
+        tbl, rec = coded[t]
+        tbl = np.ascontiguousarray(tbl); rec = np.ascontiguousarray(rec, dtype=np.int16)
+        return L.evxgpu_decode_submit(two.h, tbl.ctypes.data_as(C.c_void_p), rec.ctypes.data_as(C.c_void_p), rec.shape[0] if rec.size else 0,
+                                      0 if t == 0 else 1, t)
+
+    assert L.evxgpu_decode_collect_end(two.h) == 15                       # nothing submitted
+    assert submit(0) == 0
+    assert submit(1) == 8                                                  # frame 0's copy-out has not begun
+    for t in range(n):
+        assert L.evxgpu_decode_collect_begin(two.h, outs[t].ctypes.data_as(C.c_void_p), 0) == 0
+        assert L.evxgpu_decode_collect_begin(two.h, outs[t].ctypes.data_as(C.c_void_p), 0) == 8      # begun already
+        if t + 1 < n:
+            assert submit(t + 1) == 0                                      # under frame t's copy-out
+            assert submit(t + 1) == 8                                      # a third frame
+        assert L.evxgpu_decode_collect_end(two.h) == 0
+    assert L.evxgpu_decode_collect_begin(two.h, outs[0].ctypes.data_as(C.c_void_p), 0) == 15
+    for t in range(n):
+        assert (outs[t] == want[t]).all(), t
