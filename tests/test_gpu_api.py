@@ -220,7 +220,7 @@ def test_pipelined_session_frame_slots(env, monkeypatch):
 def test_pipelined_decode_equals_synchronous():
     """evx1_decoder::submit(n+1) before collect(n): same pictures as decode(), one call later; state rules."""
     from cairo_b200 import api
-    w, h, n = 352, 288, 12
+    w, h, n = 352, 288, 16
     enc = api.evx1_encoder()
     enc.set_quality(16)
     streams = []
@@ -238,11 +238,11 @@ def test_pipelined_decode_equals_synchronous():
     with pytest.raises(RuntimeError):
         dec.decode(streams[1][0], streams[1][1], w, h)     # decode() with a frame uncollected
     held = 1
-    for t in range(1, 8):
-        dec.submit(*streams[t])                    # eight frames may be uncollected (their slices parse concurrently)
+    for t in range(1, 12):
+        dec.submit(*streams[t])                    # twelve frames may be uncollected (their slices parse concurrently)
         held += 1
     with pytest.raises(RuntimeError):
-        dec.submit(*streams[held])                 # a ninth
+        dec.submit(*streams[held])                 # a thirteenth
     got = [dec.collect(w, h).copy()]
     for t in range(held, n):
         dec.submit(*streams[t])
