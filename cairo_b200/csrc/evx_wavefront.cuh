@@ -951,7 +951,9 @@ __global__ void __launch_bounds__(EvxK3Cfg<MINCTAS>::NT, MINCTAS) evx_wavefront(
 
 // ------------------------------------------------------------------ the followers (header comment)
 
+#ifndef EVX_SF_WARPS
 #define EVX_SF_WARPS 8            // warps of a search-follower CTA: a row's 120 items in ~300 us, twice the pace its wavefront row needs
+#endif
 struct EvxSearchFollowSmem
 {
     uint8_t win[EVX_SF_WARPS][EVX_K2W_BYTES];

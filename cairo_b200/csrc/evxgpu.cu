@@ -366,7 +366,8 @@ int evxgpu_create(int device, int width, int height, const evxgpu_config *cfg, v
     // search CTAs 2 050 / 2 188 / 2 090.
     // (ring of 4: 24 / 36 / 48 search CTAs 1 460 / 1 648 / 1 648 frames/s; 3840x2160: 46 / 24 search CTAs 743 / 787, 64 / 48 / 84
     // row CTAs 743 / 692 / 683, 46 / 24 deblocking warps 743 / 723)
-    h->search_ctas = std::min(h->g.mbh, 12 * h->cfg.ref_count); h->deblock_ctas = (h->g.mbh + 2) / 3 + 1;
+    // (four compute warps per row CTA, 3840x2160: 24 / 36 search CTAs 790 / 871 frames/s)
+    h->search_ctas = std::min(h->g.mbh, 12 * h->cfg.ref_count * std::max(160, h->g.mbw) / 160); h->deblock_ctas = (h->g.mbh + 2) / 3 + 1;
     h->pipe_rows = std::min(h->g.mbh, std::max(4, (4 * h->g.mbw + 14) / 15));
     h->launch_row = 0;
     if (const char *e = getenv("EVXGPU_LAUNCH_ROW")) { int v = atoi(e); if (v >= 0) h->launch_row = v; }      // measurements
