@@ -173,8 +173,8 @@ __device__ __forceinline__ void evx_tma_load_2d(void *dst, const CUtensorMap *ma
 // block-level synchronisation: the 16x16+8x8+8x8 candidate cost is a warp collective (evx_block_cost), the
 // acceptance rule has a closed form evaluated lane-parallel (evx_select_fullpel).
 
-// 32 bytes per (macroblock, reference).  `stamp` is the token of the frame the record belongs to: when the search runs as a
-// role of the frame kernel (evx_wavefront.cuh) it is stored last, with release semantics, and the wavefront's block loader
+// 32 bytes per (macroblock, reference).  `stamp` is the token of the frame the record belongs to: when the search runs in
+// the frame pipeline (evx_search_follow, evx_wavefront.cuh) it is stored last, with release semantics, and the wavefront's block loader
 // polls it -- the slot's records are reused by later frames and never zeroed.
 struct EvxInterResult { EvxDesc desc; int sad; uint32_t stamp; int pad[2]; };
 
@@ -296,7 +296,7 @@ __device__ __forceinline__ void evx_inter_search_warp(EvxWin &win, const EvxLane
 // Row pitches of 24 / 12 words keep the lane layout of evx_load_block bank-conflict free
 // (rows {0,24,48,72} + 0..7 and {0,12,..,84} + 0..3 tile the 32 banks).
 // Two callers: the stand-alone kernel evx_inter_search (grid = (mbw, mbh, refs), one warp per CTA -- the
-// kernel the integer roofline is quoted on) and the search role of the frame kernel (evx_wavefront.cuh), whose
+// kernel the integer roofline is quoted on) and the search follower of the frame pipeline (evx_wavefront.cuh), whose
 // warps pull (macroblock, reference) items of one macroblock row and reuse their window and barrier.
 
 #define EVX_K2W_WIN 48
@@ -590,7 +590,7 @@ __device__ __forceinline__ int evx_ld_relaxed(const int *p)
 }
 
 // Every device-side wait on a counter another CTA advances is BOUNDED.  By construction none can last (tickets are
-// claimed in dependency order, and a frame kernel only waits for kernels launched before it: evx_wavefront.cuh), but a
+// claimed in dependency order, and a frame's kernels only wait for kernels launched before them: evx_wavefront.cuh), but a
 // wait that did -- a logic error, a foreign context holding the device for seconds -- would otherwise hang the GPU until
 // the process is killed.  After `budget_ns` (evxgpu.cu: 4 s, EVXGPU_WAIT_BUDGET_MS) the waiter records what it was
 // waiting for in mapped host memory and traps: the launch fails, every later call of the process reports the error.

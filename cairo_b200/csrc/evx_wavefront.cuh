@@ -144,7 +144,7 @@ __device__ __forceinline__ int evx_gate_shortfall(const EvxK3Params &p, int bx, 
     return __reduce_max_sync(0xFFFFFFFFu, short_by);
 }
 
-// A call, not inlined: the tile's 64 samples live in registers, and inlined into the frame kernel they would raise the
+// A call, not inlined: the tile's 64 samples live in registers, and inlined into the wavefront kernel they would raise the
 // pressure of every other path of it (spills in the two-CTAs-per-SM budget); as a function the cost stays in here.
 // (arguments by value: a reference to the caller's locals would put those on its stack)
 __device__ __noinline__ void evx_deblock_tile_call(int16_t *y, int16_t *u, int16_t *v, int w, int h, const EvxDesc *table, int comp, int tx, int ty)
@@ -929,7 +929,11 @@ __global__ void __launch_bounds__(EvxK3Cfg<MINCTAS>::NT, MINCTAS) evx_wavefront(
 #ifdef EVX_K3_TIMELINE
         if (p.prof && tid == 0) p.prof[(size_t) H * 10 + (size_t) by * 4 + 1] = (long long) evx_globaltimer();      // left the queues, row starts
 #endif
+#ifdef EVX_K3_ALONE_ROLLED
+        if (warp < CW) evx_k3_compute<false, CW>(S, p, by, tid);
+#else
         if (warp < CW) evx_k3_compute<MINCTAS == 1, CW>(S, p, by, tid);
+#endif
         else if (warp == CW) evx_k3_block_loader(S, p, by, lane);
         else if (warp == CW + 1) evx_k3_column_loader(S, p, by, lane);
         __syncthreads();      // every warp has left the row: its barriers and shared memory may be reused

@@ -50,7 +50,8 @@ static stream_memop_fn g_wait32 = NULL;
 #include <atomic>
 enum { EVX_MAX_SLOTS = 16, EVX_DEFAULT_SLOTS = 10 };           // frame slots a handle may own (evxgpu_config::frame_slots, EVXGPU_FRAME_SLOTS)
 // Encoders (handles that have encoded a frame) alive per device, process-wide.  Only a tuning hint: a stand-alone
-// wavefront launch takes the larger register budget while the handle is the device's only encoder.  Nothing about
+// wavefront launch takes the latency-optimised build of the kernel (evx_wavefront<1>: eight compute warps, unrolled search,
+// 168 registers) while the handle is the device's only encoder, the throughput build (<2>) next to others.  Nothing about
 // correctness or progress depends on it (frames of any number of streams and processes may share the device).
 static std::atomic<int> g_encoders_live[64];
 
@@ -104,7 +105,7 @@ struct evxgpu_handle
     int enc_grid;                   // persistent CTAs of the encoder's wavefront kernel (the device's only encoder)
     int shared_grid;                // the same next to other encoders
     int search_ctas, deblock_ctas;  // persistent CTAs of the search follower (8 warps each) and of the deblocking follower (one warp each)
-    int pipe_rows;                  // frame kernel: row CTAs per frame in the pipeline
+    int pipe_rows;                  // frame pipeline: row CTAs per frame
     int launch_row;                 // a frame's kernel is launched once the previous frame has begun to deblock this tile row (0: once it runs)
     long long *d_prof;
 
@@ -128,8 +129,8 @@ struct evxgpu_handle
     uint64_t d2h_bytes[EVX_MAX_SLOTS]; // device-to-host bytes of the slot's frame
     uint32_t bins_dirty_bits[EVX_MAX_SLOTS];   // how much of d_bins the slot's last frame wrote (the next frame zeroes that much)
     // Frame pipeline (bin-only output, unless EVXGPU_FRAME_OVERLAP=0): nslots frame slots own their per-frame device
-    // state and a stream each; every frame is ONE launch of the frame kernel (evx_wavefront.cuh: search role, wavefront
-    // rows, deblocking behind the wavefront) and consecutive frames run concurrently, gated macroblock by macroblock
+    // state and three streams each; every frame is three launches side by side (evx_wavefront.cuh: search follower,
+    // wavefront rows, deblocking follower) and consecutive frames run concurrently, gated macroblock by macroblock
     // through per-row counters in device memory.  See submit_pipelined.
     bool overlap;                   // the machinery exists (slots, streams, counters)
     bool is_encoder;                // counted in g_encoders_live
@@ -146,7 +147,7 @@ struct evxgpu_handle
     int nslots;                     // frame slots in use
     int want_slots;                 // evxgpu_config::frame_slots (0: default)
     unsigned int frame_seq;
-    int k3_regs;                    // register budget of the frame kernel: 1 or 2 CTAs per SM
+    int k3_regs;                    // build of the wavefront kernel used in the frame pipeline: 1 (latency) or 2 (throughput: two CTAs per SM)
     bool k3_regs_forced;            // EVXGPU_K3_REGS given: also for the stand-alone wavefront launch
     unsigned int *h_diag, *d_diag;  // mapped host memory: what a device-side wait that ran out of time was waiting for
     unsigned long long wait_budget_ns;
@@ -746,11 +747,11 @@ static int enable_pipeline(evxgpu_handle *h)
     return 0;
 }
 
-// One frame of the pipeline: K1, then ONE launch of the frame kernel (search role + wavefront rows + deblocking behind
-// the wavefront, evx_wavefront.cuh), then K8 and the copies -- all on the slot's stream.  The frame kernel follows the
-// previous frame's (slot p, possibly still running, and transitively all older ones) macroblock by macroblock through
-// that frame's dbk[] counters; it is launched only once the previous frame's kernel has started (a stream memory
-// operation on its `started` word), so that what it waits for is always already on the device.
+// One frame of the pipeline: K1, then three launches side by side (search follower on the slot's k2s stream, wavefront rows
+// on its main stream, deblocking follower on k4s: evx_wavefront.cuh), then K8 and the copies on the main stream.  The frame
+// follows the previous frame's (slot p, possibly still running, and transitively all older ones) macroblock by macroblock
+// through that frame's dbk[] counters; its kernels are launched only once the previous frame's wavefront kernel has started
+// (a stream memory operation on its `started` word), so that what they wait for is always already on the device.
 static int submit_pipelined(evxgpu_handle *h, const uint8_t *rgb, int rgb_is_device, int frame_type, uint32_t frame_index, int quality)
 {
     const int ns = h->nslots, q = (h->q_head + h->q_count) % ns, p = (q + ns - 1) % ns;
