@@ -152,3 +152,49 @@ def test_concurrent_1080p_streams_pipelined_are_deterministic():
             d, b = results[sidx][t]
             wd, wb = want[sidx % 2][t]
             assert b == wb and (d == wd).all(), (sidx, t)
+
+
+_TWO_PROC = r"""
+import sys
+sys.path.insert(0, {root!r})
+import numpy as np
+from cairo_b200 import gpu, synth
+w, h, q, n = 640, 368, 16, 12
+seed = int(sys.argv[1])
+frames = [synth.frame(w, h, t, seed, "moving") for t in range(n)]
+one = gpu.Pipeline(w, h, 2, 0, 1, frame_slots=1); one.set_output(1)
+want = []
+for t in range(n):
+    one.encode_submit(frames[t], 0 if t in (0, 7) else 1, t, q); want.append(one.encode_collect_bins())
+for rep in range(3):
+    p = gpu.Pipeline(w, h, 2, 0, 1); p.set_output(1)
+    cap, got, inflight = p.encode_capacity(), [], 0
+    for t in range(n):
+        p.encode_submit(frames[t], 0 if t in (0, 7) else 1, t, q); inflight += 1
+        if inflight >= cap:
+            got.append(p.encode_collect_bins()); inflight -= 1
+    while inflight:
+        got.append(p.encode_collect_bins()); inflight -= 1
+    for t in range(n):
+        a, b = got[t], want[t]
+        assert a[1] == b[1] and a[2] == b[2] and (a[0][:a[1] // 64] == b[0][:b[1] // 64]).all(), (rep, t)
+    p.close()
+print("ok", seed)
+"""
+
+
+def test_two_processes_share_the_device(tmp_path):
+    """Two PROCESSES (two CUDA contexts time-sliced on the one GPU), each with a pipelined stream, ten frames in flight:
+    every device-side wait points at work that is already on the device, so neither can starve the other; the strings
+    equal the frame-after-frame run."""
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_TWO_PROC.format(root=root))
+    procs = [subprocess.Popen([sys.executable, str(script), str(s)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for s in (1, 2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-2000:]
+        assert "ok" in o
