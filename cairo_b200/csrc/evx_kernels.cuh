@@ -12,6 +12,29 @@
 
 #include "evx_device.cuh"
 
+// the arithmetic of one 8x2 strip (convert.cpp:11-14, 30-73)
+__device__ __forceinline__ void evx_rgb8x2_to_yuv(const uint8_t (&px)[2][24], short (&yv)[2][8], short (&uv)[4], short (&vv)[4])
+{
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+    {
+        short su = 0, sv = 0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int d = 0; d < 2; ++d)
+        {
+            int i = 2 * q + d;
+            int R = px[r][3 * i], G = px[r][3 * i + 1], B = px[r][3 * i + 2];
+            yv[r][i] = (short) (((77 * R + 150 * G + 29 * B + 128) >> 8) + 16);
+            su = (short) (su + ((-43 * R - 85 * G + 128 * B + 128) / 256 + 128));
+            sv = (short) (sv + ((128 * R - 107 * G - 21 * B + 128) / 256 + 128));
+        }
+        uv[q] = (short) ((su + 2) >> 2);
+        vv[q] = (short) ((sv + 2) >> 2);
+    }
+}
+
 // ------------------------------------------------------------------ K1: RGB -> YUV 4:2:0
 // One thread per 8x2 pixel strip: 2 x 24 B in, 2 x 16 B luma + 2 x 8 B chroma out.
 // y uses >>8, chroma uses C '/' (toward zero); the four chroma samples of a quad are
@@ -43,24 +66,7 @@ __global__ void __launch_bounds__(256) evx_rgb_to_yuv420(const uint8_t *__restri
         }
     }
     short yv[2][8], uv[4], vv[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-    {
-        short su = 0, sv = 0;
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int d = 0; d < 2; ++d)
-        {
-            int i = 2 * q + d;
-            int R = px[r][3 * i], G = px[r][3 * i + 1], B = px[r][3 * i + 2];
-            yv[r][i] = (short) (((77 * R + 150 * G + 29 * B + 128) >> 8) + 16);
-            su = (short) (su + ((-43 * R - 85 * G + 128 * B + 128) / 256 + 128));
-            sv = (short) (sv + ((128 * R - 107 * G - 21 * B + 128) / 256 + 128));
-        }
-        uv[q] = (short) ((su + 2) >> 2);
-        vv[q] = (short) ((sv + 2) >> 2);
-    }
+    evx_rgb8x2_to_yuv(px, yv, uv, vv);
     int cw = g.w >> 1;
     if (n == 8)
     {
@@ -82,6 +88,52 @@ __global__ void __launch_bounds__(256) evx_rgb_to_yuv420(const uint8_t *__restri
         for (int i = 0; i < n; ++i) { dst.y[(size_t) y0 * g.w + x0 + i] = yv[0][i]; dst.y[(size_t) (y0 + 1) * g.w + x0 + i] = yv[1][i]; }
         for (int q = 0; q < n / 2; ++q) { dst.u[(size_t) sy * cw + (x0 >> 1) + q] = uv[q]; dst.v[(size_t) sy * cw + (x0 >> 1) + q] = vv[q]; }
     }
+}
+
+// The same for frames whose width is a multiple of 16 and whose rows are 16-byte aligned: one thread per 16x2 strip, 2 x 3
+// 128-bit loads in, 2 x 2 128-bit luma stores + 2 x 1 128-bit chroma stores out; threads flattened over the whole frame.
+__global__ void __launch_bounds__(256) evx_rgb_to_yuv420_wide(const uint8_t *__restrict__ rgb, EvxPlanes dst, EvxGeom g)
+{
+    const int strips_x = g.vw >> 4;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= strips_x * (g.vh >> 1)) return;
+    const int sy = id / strips_x, sx = id - sy * strips_x, x0 = sx * 16, y0 = sy * 2;
+    uint4 in[2][3];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+    {
+        const uint4 *row = reinterpret_cast<const uint4 *>(rgb + ((size_t) (y0 + r) * g.vw + x0) * 3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) in[r][k] = __ldg(row + k);
+    }
+    const int cw = g.w >> 1;
+    uint4 ou, ov;
+#pragma unroll
+    for (int half = 0; half < 2; ++half)
+    {
+        uint8_t px[2][24];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+        {
+            const uint32_t w[12] = { in[r][0].x, in[r][0].y, in[r][0].z, in[r][0].w, in[r][1].x, in[r][1].y, in[r][1].z, in[r][1].w, in[r][2].x, in[r][2].y, in[r][2].z, in[r][2].w };
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { const uint32_t v = w[6 * half + k]; px[r][4 * k] = v; px[r][4 * k + 1] = v >> 8; px[r][4 * k + 2] = v >> 16; px[r][4 * k + 3] = v >> 24; }
+        }
+        short yv[2][8], uv[4], vv[4];
+        evx_rgb8x2_to_yuv(px, yv, uv, vv);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+        {
+            uint4 o;
+            o.x = evx_pack16(yv[r][0], yv[r][1]); o.y = evx_pack16(yv[r][2], yv[r][3]);
+            o.z = evx_pack16(yv[r][4], yv[r][5]); o.w = evx_pack16(yv[r][6], yv[r][7]);
+            *reinterpret_cast<uint4 *>(dst.y + (size_t) (y0 + r) * g.w + x0 + 8 * half) = o;
+        }
+        if (half == 0) { ou.x = evx_pack16(uv[0], uv[1]); ou.y = evx_pack16(uv[2], uv[3]); ov.x = evx_pack16(vv[0], vv[1]); ov.y = evx_pack16(vv[2], vv[3]); }
+        else { ou.z = evx_pack16(uv[0], uv[1]); ou.w = evx_pack16(uv[2], uv[3]); ov.z = evx_pack16(vv[0], vv[1]); ov.w = evx_pack16(vv[2], vv[3]); }
+    }
+    *reinterpret_cast<uint4 *>(dst.u + (size_t) sy * cw + (x0 >> 1)) = ou;
+    *reinterpret_cast<uint4 *>(dst.v + (size_t) sy * cw + (x0 >> 1)) = ov;
 }
 
 // ------------------------------------------------------------------ K6: YUV 4:2:0 -> RGB
@@ -129,6 +181,45 @@ __global__ void __launch_bounds__(256) evx_yuv420_to_rgb(EvxPlanes src, uint8_t 
         else
         {
             for (int k = 0; k < n * 3; ++k) row[k] = o[k];
+        }
+    }
+}
+
+// The same for frames whose width is a multiple of 16 and whose rows are 16-byte aligned: one thread per 16x2 strip, 128-bit
+// loads of both planes' rows, 2 x 3 128-bit stores.
+__global__ void __launch_bounds__(256) evx_yuv420_to_rgb_wide(EvxPlanes src, uint8_t *__restrict__ rgb, EvxGeom g)
+{
+    const int strips_x = g.vw >> 4;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= strips_x * (g.vh >> 1)) return;
+    const int sy = id / strips_x, sx = id - sy * strips_x, x0 = sx * 16, y0 = sy * 2;
+    const int cw = g.w >> 1;
+    const uint4 ua = *reinterpret_cast<const uint4 *>(src.u + (size_t) sy * cw + (x0 >> 1));
+    const uint4 va = *reinterpret_cast<const uint4 *>(src.v + (size_t) sy * cw + (x0 >> 1));
+    const uint32_t uw[4] = { ua.x, ua.y, ua.z, ua.w }, vw4[4] = { va.x, va.y, va.z, va.w };
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+    {
+        const uint4 *yrow = reinterpret_cast<const uint4 *>(src.y + (size_t) (y0 + r) * g.w + x0);
+        const uint4 ya = yrow[0], yb = yrow[1];
+        const uint32_t yw[8] = { ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w };
+        uint8_t o[48];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+        {
+            const int y = (short) (yw[i >> 1] >> (16 * (i & 1))), u = (short) (uw[i >> 2] >> (16 * ((i >> 1) & 1))), v = (short) (vw4[i >> 2] >> (16 * ((i >> 1) & 1)));
+            o[3 * i]     = evx_sat8((256 * (y - 16) + 358 * (v - 128) + 128) >> 8);
+            o[3 * i + 1] = evx_sat8((256 * (y - 16) - 88 * (u - 128) - 182 * (v - 128) + 128) >> 8);
+            o[3 * i + 2] = evx_sat8((256 * (y - 16) + 452 * (u - 128) + 128) >> 8);
+        }
+        uint4 *row = reinterpret_cast<uint4 *>(rgb + ((size_t) (y0 + r) * g.vw + x0) * 3);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const int b = 16 * k + 4 * j; w[j] = o[b] | (o[b + 1] << 8) | (o[b + 2] << 16) | ((uint32_t) o[b + 3] << 24); }
+            row[k] = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
 }

@@ -522,7 +522,11 @@ static int launch_convert_in(evxgpu_handle *h, const uint8_t *d_rgb)
 {
     dim3 block(256), grid(((h->g.vw + 7) / 8 + 255) / 256, h->g.vh / 2);
     t_begin(h, EVXGPU_T_CONVERT_IN);
-    evx_rgb_to_yuv420<<<grid, block, 0, h->stream>>>(d_rgb, h->src, h->g);
+    // rows of 16-byte aligned 48-byte groups: the 128-bit form (one thread per 16x2 strip)
+    if ((h->g.vw & 15) == 0 && (((uintptr_t) d_rgb) & 15) == 0)
+        evx_rgb_to_yuv420_wide<<<((h->g.vw >> 4) * (h->g.vh >> 1) + 255) / 256, 256, 0, h->stream>>>(d_rgb, h->src, h->g);
+    else
+        evx_rgb_to_yuv420<<<grid, block, 0, h->stream>>>(d_rgb, h->src, h->g);
     t_end(h, EVXGPU_T_CONVERT_IN);
     h->launches++;
     CK(cudaGetLastError());
@@ -1131,7 +1135,10 @@ int evxgpu_decode_submit(evxgpu_handle *h, const evxgpu_block_desc *table, const
     if (d.out_rec) CK(cudaStreamWaitEvent(h->stream, d.ev_out, 0));      // the picture two frames back has left this set's RGB buffer
     dim3 block(256), grid(((h->g.vw + 7) / 8 + 255) / 256, h->g.vh / 2);
     t_begin(h, EVXGPU_T_CONVERT_OUT);
-    evx_yuv420_to_rgb<<<grid, block, 0, h->stream>>>(h->ring[frame_index % (uint32_t) h->cfg.ref_count], d.d_rgb, h->g);
+    if ((h->g.vw & 15) == 0 && (((uintptr_t) d.d_rgb) & 15) == 0)
+        evx_yuv420_to_rgb_wide<<<((h->g.vw >> 4) * (h->g.vh >> 1) + 255) / 256, 256, 0, h->stream>>>(h->ring[frame_index % (uint32_t) h->cfg.ref_count], d.d_rgb, h->g);
+    else
+        evx_yuv420_to_rgb<<<grid, block, 0, h->stream>>>(h->ring[frame_index % (uint32_t) h->cfg.ref_count], d.d_rgb, h->g);
     t_end(h, EVXGPU_T_CONVERT_OUT);
     h->launches++;
     CK(cudaGetLastError());
