@@ -620,21 +620,52 @@ __device__ __forceinline__ void evx_reconstruct(EvxMbShared &sh, int type, int q
 __device__ __forceinline__ void evx_store_pred_as_recon(const EvxMbShared &sh, const EvxPlanes &dst, const EvxGeom &g, int px, int py, int tid, int nt)
 {
     int cw = g.w >> 1;
-    for (int e = tid; e < 384; e += nt)
+    // (px, py are multiples of 16: 48 aligned 16-byte chunks)
+    for (int idx = tid; idx < 48; idx += nt)
     {
-        int comp, x, y;
-        evx_mb_pos(e, comp, x, y);
-        if (comp == 0) dst.y[(size_t) (py + y) * g.w + px + x] = sh.pred[e];
-        else (comp == 1 ? dst.u : dst.v)[(size_t) ((py >> 1) + y) * cw + (px >> 1) + x] = sh.pred[e];
+        if (idx < 32)
+        {
+            const int row = idx >> 1, half = idx & 1;
+            *reinterpret_cast<uint4 *>(dst.y + (size_t) (py + row) * g.w + px + 8 * half) = *reinterpret_cast<const uint4 *>(sh.pred + ((row >> 3) * 2 + half) * 64 + (row & 7) * 8);
+        }
+        else
+        {
+            const int plane = (idx - 32) >> 3, row = (idx - 32) & 7;
+            *reinterpret_cast<uint4 *>((plane ? dst.v : dst.u) + (size_t) ((py >> 1) + row) * cw + (px >> 1)) = *reinterpret_cast<const uint4 *>(sh.pred + 256 + plane * 64 + row * 8);
+        }
     }
 }
 
 // Prediction of a block type straight from a ring slot in global memory (L2 loads: the slot
 // may be the frame under construction).  encode.cpp:83-141 / decode.cpp:27-135.
+// Full-pel prediction at a position whose x is a multiple of 16 (zero motion above all: most macroblocks of ordinary
+// video): chunk idx of the 48 16-byte chunks of a 16x16 + 8x8 + 8x8 block, from the reference planes to a block-major
+// buffer (6 blocks x 64, the layout of EvxMbShared::pred).  128-bit loads; idx 0..31 luma (row, half), 32..47 chroma.
+__device__ __forceinline__ void evx_pred_chunk16(int16_t *dst, const EvxPlanes &ref, const EvxGeom &g, int bxp, int byp, int idx)
+{
+    if (idx < 32)
+    {
+        const int row = idx >> 1, half = idx & 1;
+        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(ref.y + (size_t) (byp + row) * g.w + bxp + 8 * half));
+        *reinterpret_cast<uint4 *>(dst + ((row >> 3) * 2 + half) * 64 + (row & 7) * 8) = v;
+    }
+    else
+    {
+        const int plane = (idx - 32) >> 3, row = (idx - 32) & 7;
+        const uint4 v = __ldcg(reinterpret_cast<const uint4 *>((plane ? ref.v : ref.u) + (size_t) ((byp >> 1) + row) * (g.w >> 1) + (bxp >> 1)));
+        *reinterpret_cast<uint4 *>(dst + 256 + plane * 64 + row * 8) = v;
+    }
+}
+
 __device__ __forceinline__ void evx_build_pred_global(EvxMbShared &sh, const EvxPlanes &ref, const EvxGeom &g,
                                                       int bxp, int byp, bool sp, int sp_amount, int dx, int dy, int tid, int nt)
 {
     int cw = g.w >> 1;
+    if (!sp && (bxp & 15) == 0)
+    {
+        for (int idx = tid; idx < 48; idx += nt) evx_pred_chunk16(sh.pred, ref, g, bxp, byp, idx);
+        return;
+    }
     for (int e = tid; e < 384; e += nt)
     {
         int comp, x, y;

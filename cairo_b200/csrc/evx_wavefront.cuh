@@ -341,6 +341,12 @@ __device__ __forceinline__ void evx_k3_block_loader(EvxK3Smem &S, const EvxK3Par
             int dx = 0, dy = 0;
             if (sp) evx_frac_direction(d.sp_index(), dx, dy);
             const int bxp = px + mx, byp = py + my;
+            if (!sp && (bxp & 15) == 0)
+            {   // (zero motion above all: 128-bit loads, two chunks per lane; warp-uniform)
+                evx_pred_chunk16(S.ipred[slot][r], ref, g, bxp, byp, lane);
+                if (lane < 16) evx_pred_chunk16(S.ipred[slot][r], ref, g, bxp, byp, 32 + lane);
+                continue;
+            }
             int a[12], b[12];
 #pragma unroll
             for (int k = 0; k < 12; ++k)
