@@ -597,12 +597,30 @@ def run_ours(args):
         dominant = max(ksum, key=ksum.get)
         plane_bytes = 3 * W * H                      # int16 4:2:0 planes of a frame
         hbm_kernels = {}
-        for name, key, nbytes in (("evx_convert_in (K1)", "convert_in", frame_bytes + plane_bytes),
-                                  ("evx_deblock (K4)", "deblock", 2 * plane_bytes + (W // 16) * ((H + 15) // 16) * 16)):
-            ms = ksum.get(key, 0.0)
+        # The three streaming kernels.  `ms` is one launch per frame between its own events in the kernel pass (every launch reads
+        # a frame that is not in L2; the event pair adds a few microseconds to a 6 us kernel, so the fraction is a lower bound);
+        # `warm_ms` is the average of 50 back-to-back launches on the same 12 MB, which stay in L2: the kernel's own
+        # duration without event overhead, NOT an HBM figure.
+        b2b = {}
+        try:
+            sp = gpu.Pipeline(W, H, REF_COUNT, 0, 1, device=local_rank, frame_slots=1)
+            for t in range(2):
+                sp.encode(int(dev[fidx(t)].data_ptr()), 0 if t == 0 else 1, t, QUALITY)
+            b2b = {"convert_in": sp.time_kernel(0, 50), "deblock": sp.time_kernel(1, 50), "convert_out": sp.time_kernel(2, 50)}
+            sp.close()
+        except Exception:
+            b2b = {}
+        kcold = dict(ksum)
+        if extras.get("decode_kernels", {}).get("convert_out_ms"):
+            kcold["convert_out"] = extras["decode_kernels"].pop("convert_out_ms")
+        for name, key, nbytes in (("evx_rgb_to_yuv420_wide (K1)", "convert_in", frame_bytes + plane_bytes),
+                                  ("evx_deblock (K4)", "deblock", 2 * plane_bytes + (W // 16) * ((H + 15) // 16) * 16),
+                                  ("evx_yuv420_to_rgb_wide (K6)", "convert_out", frame_bytes + plane_bytes)):
+            ms = kcold.get(key, 0.0)
             if ms > 0:
                 gbs = nbytes / (ms * 1e-3) / 1e9
-                hbm_kernels[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved_gbs": gbs, "frac": gbs / hbm}
+                hbm_kernels[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved_gbs": gbs, "frac": gbs / hbm,
+                                     "warm_ms": b2b.get(key) if b2b.get(key, -1) > 0 else None}
         if extras.get("decode_kernels"):
             hbm_kernels.update(extras.pop("decode_kernels"))
         for v in hbm_kernels.values():
@@ -736,8 +754,7 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
             plane_bytes = 3 * W * H
             dk = {}
             if ks.get("convert_out", 0) > 0:
-                dk["evx_convert_out (K6)"] = {"algorithmic_bytes": frame_bytes + plane_bytes, "ms": ks["convert_out"],
-                                              "achieved_gbs": (frame_bytes + plane_bytes) / (ks["convert_out"] * 1e-3) / 1e9}
+                dk["convert_out_ms"] = ks["convert_out"]
             if ks.get("decode_recon", 0) > 0:
                 nb = 3 * plane_bytes      # prediction read + coefficient records read (upper bound: every block coded) + reconstruction write
                 dk["evx_decode_recon (K5, P-frame)"] = {"algorithmic_bytes": nb, "ms": ks["decode_recon"], "achieved_gbs": nb / (ks["decode_recon"] * 1e-3) / 1e9}

@@ -422,6 +422,40 @@ uint64_t evxgpu_d2h_bytes(const evxgpu_handle *h) { return h ? h->d2h_bytes[h->l
 
 uint64_t evxgpu_launch_count(const evxgpu_handle *h) { return h ? h->launches : 0; }
 
+// Average duration (ms) of `reps` back-to-back launches of one of the streaming kernels between two events: a 6 us kernel
+// timed by an event pair of its own mostly measures the events.  kind 0: K1 (the RGB staging buffer -> source planes),
+// 1: K4 (ring slot 0 in place: the samples change, the time does not), 2: K6 (ring slot 0 -> the RGB staging buffer).
+// A measurement aid for idle handles (nothing in flight); the planes it touches are left modified.
+double evxgpu_time_kernel(evxgpu_handle *h, int kind, int reps)
+{
+    if (!h || kind < 0 || kind > 2 || reps < 1 || h->pending_encode || h->pending_decode) return -1.0;
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1.0;
+    cudaEvent_t a, b;
+    if (cudaEventCreate(&a) != cudaSuccess) return -1.0;
+    if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); return -1.0; }
+    const bool wide = (h->g.vw & 15) == 0 && (((uintptr_t) h->d_rgb) & 15) == 0;
+    const int wide_grid = ((h->g.vw >> 4) * (h->g.vh >> 1) + 255) / 256;
+    const dim3 cgrid(((h->g.vw + 7) / 8 + 255) / 256, h->g.vh / 2);
+    EvxK4Params p4; p4.pl = h->ring[0]; p4.g = h->g; p4.table = h->d_table;
+    const dim3 dgrid((h->g.w / 8 + 1 + 127) / 128, h->g.h / 8 + 1, 3);
+    for (int pass = 0; pass < 2; ++pass)          // the first pass warms up
+    {
+        cudaEventRecord(a, h->stream);
+        for (int r = 0; r < (pass ? reps : 3); ++r)
+        {
+            if (kind == 0) { if (wide) evx_rgb_to_yuv420_wide<<<wide_grid, 256, 0, h->stream>>>(h->d_rgb, h->src, h->g); else evx_rgb_to_yuv420<<<cgrid, 256, 0, h->stream>>>(h->d_rgb, h->src, h->g); }
+            else if (kind == 1) evx_deblock<<<dgrid, 128, 0, h->stream>>>(p4);
+            else { if (wide) evx_yuv420_to_rgb_wide<<<wide_grid, 256, 0, h->stream>>>(h->ring[0], h->d_rgb, h->g); else evx_yuv420_to_rgb<<<cgrid, 256, 0, h->stream>>>(h->ring[0], h->d_rgb, h->g); }
+        }
+        cudaEventRecord(b, h->stream);
+        cudaEventSynchronize(b);
+    }
+    float ms = 0.f;
+    const bool ok = cudaEventElapsedTime(&ms, a, b) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return ok ? (double) ms / reps : -1.0;
+}
+
 // Device-side clock of the frame pipeline: mark() stamps "now" on the device; from then on every submitted frame records
 // an event when its results have left the device (after its last device-to-host copy), on the stream it ran on, and
 // last_done_ms() gives that moment for the frame collected last, in ms since the mark.

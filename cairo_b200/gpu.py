@@ -74,6 +74,8 @@ def lib():
     L.evxgpu_d2h_bytes.argtypes = [vp]
     L.evxgpu_launch_count.restype = C.c_uint64
     L.evxgpu_launch_count.argtypes = [vp]
+    L.evxgpu_time_kernel.restype = C.c_double
+    L.evxgpu_time_kernel.argtypes = [vp, i32, i32]
     L.evxgpu_timeline_mark.argtypes = [vp]
     L.evxgpu_last_done_ms.restype = C.c_double
     L.evxgpu_last_done_ms.argtypes = [vp]
@@ -238,6 +240,10 @@ class Pipeline:
 
     def launch_count(self):
         return int(self.L.evxgpu_launch_count(self.h))
+
+    def time_kernel(self, kind, reps=50):
+        """Average ms of `reps` back-to-back launches of K1 (0), K4 (1) or K6 (2) on this idle handle."""
+        return float(self.L.evxgpu_time_kernel(self.h, int(kind), int(reps)))
 
 
 def records_to_planes(table, records, coef_planes, aw, ah):

@@ -152,6 +152,9 @@ int evxgpu_get_counters(evxgpu_handle *h, uint64_t *fullpel, uint64_t *subpel, i
 /* the same split by kernel: out4 = { inter full-pel, inter sub-pel, intra full-pel, intra sub-pel } */
 int evxgpu_get_counters_split(evxgpu_handle *h, uint64_t *out4, int reset);
 uint64_t evxgpu_launch_count(const evxgpu_handle *h);
+/* Average duration (ms) of `reps` back-to-back launches of a streaming kernel on an idle handle: 0 = RGB->YUV, 1 = deblocking
+ * (ring slot 0, in place), 2 = YUV->RGB.  A measurement aid (bench.py's HBM fractions); -1 on failure. */
+double evxgpu_time_kernel(evxgpu_handle *h, int kind, int reps);
 /* device-side clock of the pipeline (bench.py): mark() stamps now; every frame submitted afterwards records a CUDA event on
  * its own stream once its results have left the device, and last_done_ms() is that moment for the frame collected last, in
  * milliseconds since the mark (-1 before any mark, or when that frame was submitted before the mark) */
