@@ -755,6 +755,7 @@ static int enable_pipeline(evxgpu_handle *h)
     }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (const char *e = getenv("EVXGPU_FOLLOW_PRIO")) { if (e[0] == '0') prio_hi = prio_lo; }      // measurements: followers at the default priority
     for (int q = 0; q < ns && ok; ++q)
     {
         ok = ok && cudaMalloc(&h->fs[q].d_dbk, (size_t) (h->g.mbh + 1) * 4) == cudaSuccess;
@@ -1120,7 +1121,19 @@ static int dec_prepare(evxgpu_handle *h)
         ok = ok && cudaEventCreateWithFlags(&h->dec[k].ev_done, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->dec[k].ev_out, cudaEventDisableTiming) == cudaSuccess;
     }
-    if (!ok) return fail(3, "decoder staging: out of memory");
+    if (!ok)
+    {   // nothing half-made stays behind: the next call starts over
+        cudaFreeHost(h->dec[1].h_table); cudaFreeHost(h->dec[1].h_records); cudaFreeHost(h->dec[1].h_record_slot); cudaFree(h->dec[1].d_rgb);
+        for (int k = 0; k < 2; ++k)
+        {
+            if (h->dec[k].ev_h2d) cudaEventDestroy(h->dec[k].ev_h2d);
+            if (h->dec[k].ev_done) cudaEventDestroy(h->dec[k].ev_done);
+            if (h->dec[k].ev_out) cudaEventDestroy(h->dec[k].ev_out);
+        }
+        memset(h->dec, 0, sizeof(h->dec));
+        cudaGetLastError();
+        return fail(3, "decoder staging: out of memory");
+    }
     return 0;
 }
 
