@@ -123,6 +123,9 @@ __device__ __forceinline__ int evx_ring_c(const uint32_t *pl, int cx, int wrow) 
 
 // ---------------------------------------------------------------- the previous frame, and the search role
 
+#ifndef EVX_GATE_POLL_NS
+#define EVX_GATE_POLL_NS 200      // back-off of the poll of the previous frame's deblocking counters
+#endif
 // Waits until the previous frame of the stream is FINAL (reconstructed and deblocked) in every sample macroblock
 // (bx, by) of this frame reads as a reference: six lanes poll tile rows by-2 .. by+3 (header comment).
 __device__ __forceinline__ void evx_gate_prev(const EvxK3Params &p, int bx, int by, int lane)
@@ -131,7 +134,7 @@ __device__ __forceinline__ void evx_gate_prev(const EvxK3Params &p, int bx, int 
     const unsigned int need = p.prev_base + (unsigned int) min(bx + 4, p.g.mbw);
     const int row = max(0, min(by + 3 - min(lane, 5), p.g.mbh - 1));
     unsigned int v;
-    EVX_BOUNDED_WAIT(p.wait, (v = evx_ld_relaxed_u32(p.prev_dbk + row), __all_sync(0xFFFFFFFFu, (int) (v - need) >= 0)), 200, 4u, need, v, (unsigned int) row);
+    EVX_BOUNDED_WAIT(p.wait, (v = evx_ld_relaxed_u32(p.prev_dbk + row), __all_sync(0xFFFFFFFFu, (int) (v - need) >= 0)), EVX_GATE_POLL_NS, 4u, need, v, (unsigned int) row);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
