@@ -70,6 +70,20 @@ def config_block():
                   "P-frame reads are the previous step's output by construction"}
 
 
+def coder_threads_for(world):
+    """Arithmetic-coder threads of a single-stream session (evx1_config::coder_threads): as many as this rank has host cores,
+    between 2 and 6.  With four cores per GPU (the eight-GPU box) six coder threads plus the submitting thread thrash:
+    measured with the process pinned to four cores, e2e 1 616 (six threads) / 1 464 (three) / 1 853 (four) frames/s."""
+    env = int(os.environ.get("EVX_BENCH_CODER_THREADS", "0"))
+    if env > 0:
+        return env
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    return max(2, min(6, cores // max(1, world)))
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -517,7 +531,7 @@ def run_ours(args):
     # (encode), and its two halves (submit / collect) with LOOKAHEAD frames in between, so the host entropy stage of a frame
     # overlaps the device's work on the following ones -- the same bytes a few calls later.
     def fresh_encoder(**kw):
-        kw.setdefault("coder_threads", int(os.environ.get("EVX_BENCH_CODER_THREADS", "0")))      # 0: the session's default
+        kw.setdefault("coder_threads", coder_threads_for(world))
         e = api.evx1_encoder(device=local_rank, ref_count=REF_COUNT, **kw)
         e.set_quality(QUALITY)
         head = []
@@ -647,7 +661,7 @@ def run_ours(args):
             "e2e": {"value": world * K / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": frame_bytes,
                     "d2h_bytes_per_step": d2h_bytes // K,
                     "synchronous": {"value": world * K / (sync_ms_max * 1e-3), "unit": "frames/s", "api": "evx1_encoder::encode"},
-                    "entropy_ms_per_step": ent_ms / K, "gpu_ms_per_step": gpu_ms / K,
+                    "entropy_ms_per_step": ent_ms / K, "gpu_ms_per_step": gpu_ms / K, "coder_threads": coder_threads_for(world),
                     "bits_per_frame": ee["bits"] // ee["frames"]},
             "gpu_launches": int(round(dv["launches"] * K / dv["frames"])),
             "gpu_launches_note": "kernels of libevxgpu.so launched per window of `steps` frames in the value loop (%d over the %d frames timed)" % (dv["launches"], dv["frames"]),
@@ -694,7 +708,7 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
 
     # ---- f3: device-resident frames through the public API (no 6.2 MB H2D per frame)
     try:
-        e = api.evx1_encoder(device=device, ref_count=REF_COUNT, device_frames=True)
+        e = api.evx1_encoder(device=device, ref_count=REF_COUNT, device_frames=True, coder_threads=coder_threads_for(world))
         e.set_quality(QUALITY)
         for t in range(warmup):
             e.encode((int(dev[fidx(t)].data_ptr()), W, H))
@@ -784,7 +798,7 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
                                    "traffic_note": "DRAM bytes per launch, ncu --set full (profiles/r02_traffic.json); algorithmic: 4 plane sets x 6.27 MB", "dominant": {"kernel": "evx_wavefront", "ms_per_launch": ks["wavefront"],
                                                                                                        "achieved": rf["wavefront"]["achieved"], "frac": rf["wavefront"]["frac"]}}
             if not linear:
-                e = api.evx1_encoder(device=device, ref_count=4)
+                e = api.evx1_encoder(device=device, ref_count=4, coder_threads=coder_threads_for(world))
                 e.set_quality(QUALITY)
                 for t in range(warmup):
                     e.encode((int(host[fidx(t)].data_ptr()), W, H))
@@ -804,7 +818,7 @@ def run_extras(args, torch, api, gpu, fanout, host, dev, fidx, head, coded, K, w
         K4 = 30                                          # one intra period per window
         ks, cn = kernel_pass(gpu, dev4, f4, w4, h4, 2, 0, 3, 10, device)
         r = device_run(gpu, dev4, f4, w4, h4, 2, 0, K4, 3, 4, device, barrier, intra_every=30)
-        e = api.evx1_encoder(device=device, ref_count=2, periodic_intra=30)
+        e = api.evx1_encoder(device=device, ref_count=2, periodic_intra=30, coder_threads=coder_threads_for(world))
         e.set_quality(QUALITY)
         for t in range(3):
             e.encode((int(host4[f4(t)].data_ptr()), w4, h4))
